@@ -1,0 +1,1198 @@
+// vpm_abi.cu -- C ABI of libvpm_cuda.so (see include/vpm_cuda.h).
+//
+// Host-side orchestration only: buffer management, strided host<->device
+// copies of the rows of ParticleField.particles the path touches, launch
+// planning and the per-call timing record.  All arithmetic of the hot path is
+// in vpm_kernels.cuh.  There is deliberately no CPU implementation here: if a
+// CUDA call fails the entry point returns VPM_ECUDA.
+#include "../../include/vpm_cuda.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vpm_kernels.cuh"
+#include "vpm_leaf.cuh"
+
+using namespace vpm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// rows of ParticleField.particles, 0-based (src/FLOWVPM_particlefield.jl:239-252)
+enum { R_X = 0, R_G = 3, R_SIGMA = 6, R_U = 9, R_W = 12, R_J = 15, R_PSE = 24, R_SFS = 39,
+       R_STATIC = 42, MIN_FIELDS = 43 };
+// rows inside the device-side result block res18 = particle rows 9..26
+enum { RES_ROWS = 18, RES_U = 0, RES_W = 3, RES_J = 6, RES_PSE = 15 };
+
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct Dev {
+  int id = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  Buf in7, stat, res18, sfs3, rec, srec, partial, tbuf, sbuf, ibuf, jbuf;
+};
+
+struct Plan {
+  int T = 1;
+  int nsplit = 1;
+  int tiles_per_split = 1;
+  int64_t pstride = 0;
+  dim3 grid;
+};
+
+}  // namespace
+
+struct vpm_handle {
+  std::vector<Dev> devs;
+  std::string err;
+  vpm_timing timing{};
+  int64_t np_resident = -1;   // particles held by the staged API
+  bool resident_static = false;
+  bool resident_prior = false;
+  double *h_stat = nullptr;   // pinned staging for compact static flags
+  size_t h_stat_cap = 0;
+  std::vector<void *> pinned;
+  int launches = 0;
+  // single-process multi-GPU (n_gpus > 1): NCCL communicators, one per device
+  void *nccl_lib = nullptr;
+  std::vector<void *> comms;
+};
+
+namespace {
+
+int fail(vpm_handle *h, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(h, call)                                                                        \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(h, e_ == cudaErrorMemoryAllocation ? VPM_ENOMEM : VPM_ECUDA,             \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define TRY(expr)            \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_ != VPM_OK) return rc_; \
+  } while (0)
+
+int ensure(vpm_handle *h, Buf &b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return VPM_OK;
+  if (b.p) CK(h, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = std::max<size_t>(bytes + bytes / 4, 4096);
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&b.p, want);
+  }
+  if (e != cudaSuccess)
+    return fail(h, VPM_ENOMEM, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+  b.cap = want;
+  return VPM_OK;
+}
+
+int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+bool valid_kernel(int k) { return k >= 0 && k <= 3; }
+
+// Launch plan: enough CTAs to fill the machine several times over; when the
+// target count alone cannot do that the sources are split and each split's
+// partial sums are combined (in order) by the finish kernel.
+Plan make_plan(int64_t nt, int64_t ns, int sm_count, int force_T = 0) {
+  Plan p;
+  const int64_t ntiles = std::max<int64_t>(1, (ns + kTile - 1) / kTile);
+  p.T = force_T ? force_T : (nt >= (int64_t)sm_count * kThreads * 2 * 6 ? 2 : 1);
+  const int64_t nblk = std::max<int64_t>(1, (nt + (int64_t)kThreads * p.T - 1) / ((int64_t)kThreads * p.T));
+  const int64_t want_ctas = (int64_t)sm_count * 8;
+  int64_t nsplit = (want_ctas + nblk - 1) / nblk;
+  nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, std::min<int64_t>(ntiles, 256)));
+  p.tiles_per_split = (int)((ntiles + nsplit - 1) / nsplit);
+  p.nsplit = (int)((ntiles + p.tiles_per_split - 1) / p.tiles_per_split);
+  p.pstride = round_up(std::max<int64_t>(nt, 1), 32);
+  p.grid = dim3((unsigned)nblk, (unsigned)p.nsplit, 1);
+  return p;
+}
+
+template <int K>
+void launch_uj_T(const Plan &p, const UjArgs &a, cudaStream_t st) {
+  if (p.T == 2) uj_pairs_kernel<K, 2><<<p.grid, kThreads, 0, st>>>(a);
+  else uj_pairs_kernel<K, 1><<<p.grid, kThreads, 0, st>>>(a);
+}
+void launch_uj(int kernel, const Plan &p, const UjArgs &a, cudaStream_t st) {
+  switch (kernel) {
+    case K_SING: launch_uj_T<K_SING>(p, a, st); break;
+    case K_GAUS: launch_uj_T<K_GAUS>(p, a, st); break;
+    case K_GERF: launch_uj_T<K_GERF>(p, a, st); break;
+    default: launch_uj_T<K_WINCK>(p, a, st); break;
+  }
+}
+template <int K>
+void launch_sfs_T(const Plan &p, const SfsArgs &a, cudaStream_t st) {
+  if (p.T == 2) sfs_pairs_kernel<K, 2><<<p.grid, kThreads, 0, st>>>(a);
+  else sfs_pairs_kernel<K, 1><<<p.grid, kThreads, 0, st>>>(a);
+}
+void launch_sfs(int kernel, const Plan &p, const SfsArgs &a, cudaStream_t st) {
+  switch (kernel) {
+    case K_SING: launch_sfs_T<K_SING>(p, a, st); break;
+    case K_GAUS: launch_sfs_T<K_GAUS>(p, a, st); break;
+    case K_GERF: launch_sfs_T<K_GERF>(p, a, st); break;
+    default: launch_sfs_T<K_WINCK>(p, a, st); break;
+  }
+}
+
+unsigned blocks_for(int64_t n, int threads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
+
+// U/J sweep: records from `src` columns [s0, s0+ns), targets tpos[0..nt), partial
+// sums left in d.partial; the caller runs the finish kernel with its own output.
+int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *tpos, int64_t tld,
+             int64_t nt, SrcView src, int64_t s0, int64_t ns, int flags, Plan &plan) {
+  const int64_t ns_pad = round_up(std::max<int64_t>(ns, 1), kTile);
+  TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
+  plan = make_plan(nt, ns, d.sm_count);
+  TRY(ensure(h, d.partial, (size_t)plan.nsplit * kAcc * plan.pstride * sizeof(double)));
+  prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, s0, ns, ns_pad, kernel,
+                                                           (double *)d.rec.p);
+  h->launches++;
+  if (nt > 0 && ns > 0) {
+    UjArgs a;
+    a.tpos = tpos; a.tld = tld; a.nt = nt;
+    a.rec = (const double *)d.rec.p; a.ns = ns;
+    a.tiles_per_split = plan.tiles_per_split;
+    a.partial = (double *)d.partial.p; a.pstride = plan.pstride;
+    a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
+    launch_uj(kernel, plan, a, st);
+    h->launches++;
+  } else {
+    plan.nsplit = 0;
+  }
+  CK(h, cudaGetLastError());
+  return VPM_OK;
+}
+
+int sfs_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *tpos, int64_t tld,
+              const double *tJ, int64_t jld, const int64_t *tindex, int64_t nt, SrcView src,
+              const double *sJ, int64_t sjld, int sjoff, const double *stat, int64_t sld,
+              const int64_t *sindex, int64_t ns, int flags, Plan &plan) {
+  const int64_t ns_pad = round_up(std::max<int64_t>(ns, 1), kTile);
+  TRY(ensure(h, d.srec, (size_t)ns_pad * kSfsRec * sizeof(double)));
+  plan = make_plan(nt, ns, d.sm_count);
+  TRY(ensure(h, d.partial, (size_t)std::max(1, plan.nsplit) * kAcc * plan.pstride * sizeof(double)));
+  const int transposed = (flags & VPM_FLAG_TRANSPOSED) ? 1 : 0;
+  prep_sfs_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, sJ, sjld, sjoff, stat, sld, sindex,
+                                                            ns, ns_pad, kernel, transposed,
+                                                            (double *)d.srec.p);
+  h->launches++;
+  if (nt > 0 && ns > 0) {
+    SfsArgs a;
+    a.tpos = tpos; a.tld = tld; a.tJ = tJ; a.jld = jld; a.tindex = tindex; a.nt = nt;
+    a.rec = (const double *)d.srec.p; a.ns = ns;
+    a.tiles_per_split = plan.tiles_per_split;
+    a.partial = (double *)d.partial.p; a.pstride = plan.pstride;
+    a.transposed = transposed;
+    a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
+    launch_sfs(kernel, plan, a, st);
+    h->launches++;
+  } else {
+    plan.nsplit = 0;
+  }
+  CK(h, cudaGetLastError());
+  return VPM_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+  return ms;
+}
+
+// ---- Hook 1 pieces (single device d; targets = all particles) ---------------
+
+// host -> device: X, Gamma, sigma rows; static flags (compacted on the host,
+// only if any is set); previous U..PSE and SFS rows when they are accumulated on.
+int h1_upload(vpm_handle *h, Dev &d, const double *P, int64_t nf, int64_t np, bool need_prior,
+              bool need_sfs_rows, bool &has_static) {
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  const size_t n = (size_t)std::max<int64_t>(np, 1);
+  TRY(ensure(h, d.in7, n * 7 * sizeof(double)));
+  TRY(ensure(h, d.res18, n * RES_ROWS * sizeof(double)));
+  TRY(ensure(h, d.sfs3, n * 3 * sizeof(double)));
+  has_static = false;
+  if (np == 0) return VPM_OK;
+  for (int64_t i = 0; i < np; ++i)
+    if (P[nf * i + R_STATIC] != 0.0) { has_static = true; break; }
+  CK(h, cudaMemcpy2DAsync(d.in7.p, 7 * sizeof(double), P, nf * sizeof(double), 7 * sizeof(double),
+                          (size_t)np, cudaMemcpyHostToDevice, st));
+  if (has_static) {
+    if (h->h_stat_cap < (size_t)np) {
+      if (h->h_stat) cudaFreeHost(h->h_stat);
+      h->h_stat = nullptr;
+      h->h_stat_cap = 0;
+      CK(h, cudaMallocHost((void **)&h->h_stat, (size_t)np * sizeof(double)));
+      h->h_stat_cap = (size_t)np;
+    }
+    for (int64_t i = 0; i < np; ++i) h->h_stat[i] = P[nf * i + R_STATIC];
+    TRY(ensure(h, d.stat, (size_t)np * sizeof(double)));
+    CK(h, cudaMemcpyAsync(d.stat.p, h->h_stat, (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  if (need_prior || has_static) {
+    CK(h, cudaMemcpy2DAsync(d.res18.p, RES_ROWS * sizeof(double), P + R_U, nf * sizeof(double),
+                            RES_ROWS * sizeof(double), (size_t)np, cudaMemcpyHostToDevice, st));
+  }
+  if (need_sfs_rows) {
+    CK(h, cudaMemcpy2DAsync(d.sfs3.p, 3 * sizeof(double), P + R_SFS, nf * sizeof(double),
+                            3 * sizeof(double), (size_t)np, cudaMemcpyHostToDevice, st));
+  }
+  return VPM_OK;
+}
+
+// device-resident evaluation: U/J sweep (+ SFS sweep) over all particles.
+// `prior` says res18/sfs3 hold previous values that must be accumulated on.
+int h1_eval(vpm_handle *h, Dev &d, int64_t np, int kernel, int flags, bool has_static, bool prior) {
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  const double *stat = has_static ? (const double *)d.stat.p : nullptr;
+  SrcView src{(const double *)d.in7.p, 7, 0, 3, 6};
+  Plan plan;
+  CK(h, cudaEventRecord(d.ev[1], st));
+  TRY(uj_sweep(h, d, st, kernel, (const double *)d.in7.p, 7, np, src, 0, np, flags, plan));
+  CK(h, cudaEventRecord(d.ev[2], st));
+  if (np > 0) {
+    UjFinishArgs f;
+    f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+    f.nt = np; f.out = (double *)d.res18.p; f.ld = RES_ROWS; f.urow = RES_U; f.jrow = RES_J;
+    f.zrow0 = RES_W; f.zrow1 = RES_PSE; f.want_U = 1; f.want_J = 1;
+    f.accumulate = prior ? 1 : 0;
+    f.reset = (flags & VPM_FLAG_RESET) ? 1 : 0;
+    f.stat = stat; f.sld = 1;
+    if (!prior) {
+      // nothing uploaded: vorticity / PSE rows of the block must still be defined
+      CK(h, cudaMemsetAsync(d.res18.p, 0, (size_t)np * RES_ROWS * sizeof(double), st));
+    }
+    uj_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(f);
+    h->launches++;
+    CK(h, cudaGetLastError());
+  }
+  CK(h, cudaEventRecord(d.ev[3], st));
+  h->timing.uj_pairs = np * np;
+  h->timing.sfs_pairs = 0;
+  if (np > 0 && (flags & VPM_FLAG_SFS)) {
+    Plan sp;
+    const double *J = (const double *)d.res18.p + RES_J;
+    TRY(sfs_sweep(h, d, st, kernel, (const double *)d.in7.p, 7, J, RES_ROWS, nullptr, np, src, J,
+                  RES_ROWS, 0, stat, 1, nullptr, np, flags, sp));
+    SfsFinishArgs f;
+    f.partial = (const double *)d.partial.p; f.pstride = sp.pstride; f.nsplit = sp.nsplit;
+    f.nt = np; f.tindex = nullptr; f.out = (double *)d.sfs3.p; f.ld = 3; f.row = 0;
+    f.accumulate = 1;  // sfs3 holds either the uploaded rows or (below) zeros
+    f.reset = (flags & VPM_FLAG_RESET_SFS) ? 1 : 0;
+    f.filter_static = 1; f.stat = stat; f.sld = 1;
+    sfs_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(f);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    h->timing.sfs_pairs = np * np;
+  } else if (np > 0 && (flags & VPM_FLAG_RESET_SFS)) {
+    zero_rows_kernel<<<blocks_for(np, 256), 256, 0, st>>>((double *)d.sfs3.p, 3, 0, 3, np, stat, 1);
+    h->launches++;
+    CK(h, cudaGetLastError());
+  }
+  CK(h, cudaEventRecord(d.ev[4], st));
+  return VPM_OK;
+}
+
+int h1_download(vpm_handle *h, Dev &d, double *P, int64_t nf, int64_t np, int flags) {
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  if (np > 0) {
+    CK(h, cudaMemcpy2DAsync(P + R_U, nf * sizeof(double), d.res18.p, RES_ROWS * sizeof(double),
+                            RES_ROWS * sizeof(double), (size_t)np, cudaMemcpyDeviceToHost, st));
+    if (flags & (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS))
+      CK(h, cudaMemcpy2DAsync(P + R_SFS, nf * sizeof(double), d.sfs3.p, 3 * sizeof(double),
+                              3 * sizeof(double), (size_t)np, cudaMemcpyDeviceToHost, st));
+  }
+  CK(h, cudaEventRecord(d.ev[5], st));
+  CK(h, cudaStreamSynchronize(st));
+  return VPM_OK;
+}
+
+void h1_fill_timing(vpm_handle *h, Dev &d) {
+  vpm_timing &t = h->timing;
+  t.h2d_ms = ev_ms(d.ev[0], d.ev[1]);
+  t.uj_ms = ev_ms(d.ev[1], d.ev[2]);
+  t.finish_ms = ev_ms(d.ev[2], d.ev[3]);
+  t.sfs_ms = ev_ms(d.ev[3], d.ev[4]);
+  t.d2h_ms = ev_ms(d.ev[4], d.ev[5]);
+  t.total_ms = ev_ms(d.ev[0], d.ev[5]);
+  t.prep_ms = 0.0;
+  t.kernel_launches = h->launches;
+  t.n_gpus = (int32_t)h->devs.size();
+}
+
+
+// ---- NCCL, loaded lazily: only the single-process multi-GPU path needs it ----
+typedef int (*nccl_comm_init_all_t)(void **comms, int ndev, const int *devlist);
+typedef int (*nccl_all_gather_t)(const void *send, void *recv, size_t count, int dtype, void *comm,
+                                 cudaStream_t stream);
+typedef int (*nccl_group_t)(void);
+typedef int (*nccl_comm_destroy_t)(void *comm);
+typedef const char *(*nccl_err_t)(int);
+struct NcclApi {
+  nccl_comm_init_all_t comm_init_all = nullptr;
+  nccl_all_gather_t all_gather = nullptr;
+  nccl_group_t group_start = nullptr, group_end = nullptr;
+  nccl_comm_destroy_t comm_destroy = nullptr;
+  nccl_err_t err_string = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8;  // ncclDouble (nccl.h ncclDataType_t)
+
+int nccl_load(vpm_handle *h) {
+  if (h->nccl_lib) return VPM_OK;
+  void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return fail(h, VPM_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+  g_nccl.comm_init_all = (nccl_comm_init_all_t)dlsym(lib, "ncclCommInitAll");
+  g_nccl.all_gather = (nccl_all_gather_t)dlsym(lib, "ncclAllGather");
+  g_nccl.group_start = (nccl_group_t)dlsym(lib, "ncclGroupStart");
+  g_nccl.group_end = (nccl_group_t)dlsym(lib, "ncclGroupEnd");
+  g_nccl.comm_destroy = (nccl_comm_destroy_t)dlsym(lib, "ncclCommDestroy");
+  g_nccl.err_string = (nccl_err_t)dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.comm_init_all || !g_nccl.all_gather || !g_nccl.group_start || !g_nccl.group_end ||
+      !g_nccl.comm_destroy)
+    return fail(h, VPM_ENCCL, "libnccl.so.2 lacks a required symbol");
+  h->nccl_lib = lib;
+  return VPM_OK;
+}
+
+#define NCK(h, call)                                                                   \
+  do {                                                                                 \
+    int r_ = (call);                                                                   \
+    if (r_ != 0)                                                                       \
+      return fail(h, VPM_ENCCL, "%s failed: %s", #call,                                \
+                  g_nccl.err_string ? g_nccl.err_string(r_) : "nccl error");           \
+  } while (0)
+
+// UJ_direct on G devices of this process: targets block-sharded, sources
+// replicated by the host upload; with SFS the final J of every shard is
+// all-gathered (NCCL over NVLink) before the second sweep.
+int uj_direct_multi(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel, int flags) {
+  const int G = (int)h->devs.size();
+  h->launches = 0;
+  if (np == 0) return VPM_OK;
+  if (h->comms.empty()) {
+    TRY(nccl_load(h));
+    std::vector<int> ids(G);
+    for (int g = 0; g < G; ++g) ids[g] = h->devs[g].id;
+    h->comms.assign(G, nullptr);
+    NCK(h, g_nccl.comm_init_all(h->comms.data(), G, ids.data()));
+  }
+  const bool reset = flags & VPM_FLAG_RESET;
+  const bool do_sfs = flags & VPM_FLAG_SFS;
+  const bool sfs_rows = do_sfs || (flags & VPM_FLAG_RESET_SFS);
+  const int64_t shard = (np + G - 1) / G;
+  const int64_t np_pad = shard * G;
+  bool has_static = false;
+  for (int64_t i = 0; i < np; ++i)
+    if (P[nf * i + R_STATIC] != 0.0) { has_static = true; break; }
+  if (has_static) {
+    if (h->h_stat_cap < (size_t)np) {
+      if (h->h_stat) cudaFreeHost(h->h_stat);
+      h->h_stat = nullptr; h->h_stat_cap = 0;
+      CK(h, cudaMallocHost((void **)&h->h_stat, (size_t)np * sizeof(double)));
+      h->h_stat_cap = (size_t)np;
+    }
+    for (int64_t i = 0; i < np; ++i) h->h_stat[i] = P[nf * i + R_STATIC];
+  }
+  const bool prior = !reset || has_static;
+  std::vector<Plan> plans(G);
+  // upload + U/J sweep on every device
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    cudaStream_t st = d.stream;
+    const int64_t t0 = std::min(np, g * shard), t1 = std::min(np, t0 + shard), nt = t1 - t0;
+    CK(h, cudaSetDevice(d.id));
+    TRY(ensure(h, d.in7, (size_t)np * 7 * sizeof(double)));
+    TRY(ensure(h, d.res18, (size_t)np_pad * RES_ROWS * sizeof(double)));
+    TRY(ensure(h, d.sfs3, (size_t)np_pad * 3 * sizeof(double)));
+    if (g == 0) CK(h, cudaEventRecord(d.ev[0], st));
+    CK(h, cudaMemcpy2DAsync(d.in7.p, 7 * sizeof(double), P, nf * sizeof(double), 7 * sizeof(double),
+                            (size_t)np, cudaMemcpyHostToDevice, st));
+    if (has_static) {
+      TRY(ensure(h, d.stat, (size_t)np * sizeof(double)));
+      CK(h, cudaMemcpyAsync(d.stat.p, h->h_stat, (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    double *res = (double *)d.res18.p + t0 * RES_ROWS;
+    double *sfs = (double *)d.sfs3.p + t0 * 3;
+    if (nt > 0) {
+      if (prior)
+        CK(h, cudaMemcpy2DAsync(res, RES_ROWS * sizeof(double), P + nf * t0 + R_U, nf * sizeof(double),
+                                RES_ROWS * sizeof(double), (size_t)nt, cudaMemcpyHostToDevice, st));
+      else
+        CK(h, cudaMemsetAsync(res, 0, (size_t)nt * RES_ROWS * sizeof(double), st));
+      if (sfs_rows)
+        CK(h, cudaMemcpy2DAsync(sfs, 3 * sizeof(double), P + nf * t0 + R_SFS, nf * sizeof(double),
+                                3 * sizeof(double), (size_t)nt, cudaMemcpyHostToDevice, st));
+    }
+    if (g == 0) CK(h, cudaEventRecord(d.ev[1], st));
+    SrcView src{(const double *)d.in7.p, 7, 0, 3, 6};
+    TRY(uj_sweep(h, d, st, kernel, (const double *)d.in7.p + t0 * 7, 7, nt, src, 0, np, flags, plans[g]));
+    if (g == 0) CK(h, cudaEventRecord(d.ev[2], st));
+    if (nt > 0) {
+      UjFinishArgs f;
+      f.partial = (const double *)d.partial.p; f.pstride = plans[g].pstride; f.nsplit = plans[g].nsplit;
+      f.nt = nt; f.out = res; f.ld = RES_ROWS; f.urow = RES_U; f.jrow = RES_J;
+      f.zrow0 = RES_W; f.zrow1 = RES_PSE; f.want_U = 1; f.want_J = 1;
+      f.accumulate = prior ? 1 : 0; f.reset = reset ? 1 : 0;
+      f.stat = has_static ? (const double *)d.stat.p + t0 : nullptr; f.sld = 1;
+      uj_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+      h->launches++;
+      CK(h, cudaGetLastError());
+    }
+    if (g == 0) CK(h, cudaEventRecord(d.ev[3], st));
+  }
+  h->timing.uj_pairs = np * np;
+  h->timing.sfs_pairs = 0;
+  if (do_sfs) {
+    // every device needs the final J of every particle: all-gather the result shards
+    NCK(h, g_nccl.group_start());
+    for (int g = 0; g < G; ++g) {
+      Dev &d = h->devs[g];
+      double *base = (double *)d.res18.p;
+      NCK(h, g_nccl.all_gather(base + (int64_t)g * shard * RES_ROWS, base, (size_t)shard * RES_ROWS,
+                               kNcclFloat64, h->comms[g], d.stream));
+    }
+    NCK(h, g_nccl.group_end());
+    for (int g = 0; g < G; ++g) {
+      Dev &d = h->devs[g];
+      cudaStream_t st = d.stream;
+      const int64_t t0 = std::min(np, g * shard), t1 = std::min(np, t0 + shard), nt = t1 - t0;
+      CK(h, cudaSetDevice(d.id));
+      const double *stat = has_static ? (const double *)d.stat.p : nullptr;
+      SrcView src{(const double *)d.in7.p, 7, 0, 3, 6};
+      const double *J = (const double *)d.res18.p + RES_J;
+      Plan sp;
+      TRY(sfs_sweep(h, d, st, kernel, (const double *)d.in7.p + t0 * 7, 7, J + t0 * RES_ROWS, RES_ROWS,
+                    nullptr, nt, src, J, RES_ROWS, 0, stat, 1, nullptr, np, flags, sp));
+      if (nt > 0) {
+        SfsFinishArgs f;
+        f.partial = (const double *)d.partial.p; f.pstride = sp.pstride; f.nsplit = sp.nsplit;
+        f.nt = nt; f.tindex = nullptr; f.out = (double *)d.sfs3.p + t0 * 3; f.ld = 3; f.row = 0;
+        f.accumulate = 1; f.reset = (flags & VPM_FLAG_RESET_SFS) ? 1 : 0;
+        f.filter_static = 1; f.stat = stat ? stat + t0 : nullptr; f.sld = 1;
+        sfs_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+        h->launches++;
+        CK(h, cudaGetLastError());
+      }
+    }
+    h->timing.sfs_pairs = np * np;
+  } else if (flags & VPM_FLAG_RESET_SFS) {
+    for (int g = 0; g < G; ++g) {
+      Dev &d = h->devs[g];
+      const int64_t t0 = std::min(np, g * shard), t1 = std::min(np, t0 + shard), nt = t1 - t0;
+      if (nt == 0) continue;
+      CK(h, cudaSetDevice(d.id));
+      zero_rows_kernel<<<blocks_for(nt, 256), 256, 0, d.stream>>>(
+          (double *)d.sfs3.p + t0 * 3, 3, 0, 3, nt, has_static ? (const double *)d.stat.p + t0 : nullptr, 1);
+      h->launches++;
+      CK(h, cudaGetLastError());
+    }
+  }
+  CK(h, cudaSetDevice(h->devs[0].id));
+  CK(h, cudaEventRecord(h->devs[0].ev[4], h->devs[0].stream));
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    const int64_t t0 = std::min(np, g * shard), t1 = std::min(np, t0 + shard), nt = t1 - t0;
+    if (nt == 0) continue;
+    CK(h, cudaSetDevice(d.id));
+    CK(h, cudaMemcpy2DAsync(P + nf * t0 + R_U, nf * sizeof(double), (double *)d.res18.p + t0 * RES_ROWS,
+                            RES_ROWS * sizeof(double), RES_ROWS * sizeof(double), (size_t)nt,
+                            cudaMemcpyDeviceToHost, d.stream));
+    if (sfs_rows)
+      CK(h, cudaMemcpy2DAsync(P + nf * t0 + R_SFS, nf * sizeof(double), (double *)d.sfs3.p + t0 * 3,
+                              3 * sizeof(double), 3 * sizeof(double), (size_t)nt, cudaMemcpyDeviceToHost,
+                              d.stream));
+  }
+  for (int g = G - 1; g >= 0; --g) {
+    Dev &d = h->devs[g];
+    CK(h, cudaSetDevice(d.id));
+    if (g == 0) CK(h, cudaEventRecord(d.ev[5], d.stream));
+    CK(h, cudaStreamSynchronize(d.stream));
+  }
+  h1_fill_timing(h, h->devs[0]);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+// ---- leaf-pair list (Hook 3) host side: CSR by target leaf -------------------
+struct HostCsr {
+  std::vector<int64_t> ptr;
+  std::vector<int32_t> src, wi_leaf, wi_off;
+};
+
+int build_csr(vpm_handle *h, const char *fn, const int64_t *tb, const int64_t *te, int64_t ntl,
+              int64_t n_tgt, const int64_t *sb, const int64_t *se, int64_t nsl, int64_t n_src,
+              const int32_t *pt, const int32_t *ps, int64_t npairs, HostCsr &c) {
+  for (int64_t l = 0; l < ntl; ++l)
+    if (tb[l] < 0 || te[l] < tb[l] || te[l] > n_tgt)
+      return fail(h, VPM_EINVAL, "%s: target leaf %lld range [%lld,%lld) outside 0..%lld", fn, (long long)l, (long long)tb[l], (long long)te[l], (long long)n_tgt);
+  for (int64_t l = 0; l < nsl; ++l)
+    if (sb[l] < 0 || se[l] < sb[l] || se[l] > n_src)
+      return fail(h, VPM_EINVAL, "%s: source leaf %lld range [%lld,%lld) outside 0..%lld", fn, (long long)l, (long long)sb[l], (long long)se[l], (long long)n_src);
+  c.ptr.assign((size_t)ntl + 1, 0);
+  for (int64_t k = 0; k < npairs; ++k) {
+    if (pt[k] < 0 || pt[k] >= ntl || ps[k] < 0 || ps[k] >= nsl)
+      return fail(h, VPM_EINVAL, "%s: pair %lld = (%d,%d) outside the leaf tables", fn, (long long)k, pt[k], ps[k]);
+    c.ptr[(size_t)pt[k] + 1]++;
+  }
+  for (int64_t l = 0; l < ntl; ++l) c.ptr[(size_t)l + 1] += c.ptr[(size_t)l];
+  c.src.resize((size_t)npairs);
+  std::vector<int64_t> cur(c.ptr.begin(), c.ptr.end() - 1);
+  for (int64_t k = 0; k < npairs; ++k) c.src[(size_t)cur[(size_t)pt[k]]++] = ps[k];  // stable
+  c.wi_leaf.clear();
+  c.wi_off.clear();
+  for (int64_t l = 0; l < ntl; ++l) {
+    if (c.ptr[(size_t)l + 1] == c.ptr[(size_t)l]) continue;
+    for (int64_t off = 0; off < te[l] - tb[l]; off += kThreads) {
+      c.wi_leaf.push_back((int32_t)l);
+      c.wi_off.push_back((int32_t)off);
+    }
+  }
+  return VPM_OK;
+}
+
+// carve aligned sub-arrays out of one device allocation and fill them
+struct Carver {
+  char *base;
+  size_t off = 0;
+  explicit Carver(void *p) : base((char *)p) {}
+  template <class T>
+  T *take(size_t n) {
+    off = (off + 15) / 16 * 16;
+    T *r = (T *)(base + off);
+    off += n * sizeof(T);
+    return r;
+  }
+};
+
+int upload_csr(vpm_handle *h, Dev &d, cudaStream_t st, const HostCsr &c, const int64_t *tb,
+               const int64_t *te, int64_t ntl, const int64_t *sb, const int64_t *se, int64_t nsl,
+               const int64_t *tsort, int64_t n_tsort, const int64_t *ssort, int64_t n_ssort,
+               LeafCsr &out, const int64_t *&d_tsort, const int64_t *&d_ssort) {
+  size_t bytes = 16 * 12 + c.wi_leaf.size() * 8 + (size_t)ntl * 16 + c.ptr.size() * 8 +
+                 c.src.size() * 4 + (size_t)nsl * 16 + (size_t)(n_tsort + n_ssort) * 8;
+  TRY(ensure(h, d.ibuf, bytes));
+  Carver cv(d.ibuf.p);
+  auto put = [&](auto *dst, const auto *srcp, size_t n) -> cudaError_t {
+    if (n == 0) return cudaSuccess;
+    return cudaMemcpyAsync((void *)dst, (const void *)srcp, n * sizeof(*srcp), cudaMemcpyHostToDevice, st);
+  };
+  int32_t *wl = cv.take<int32_t>(c.wi_leaf.size());
+  int32_t *wo = cv.take<int32_t>(c.wi_off.size());
+  int64_t *dtb = cv.take<int64_t>((size_t)ntl), *dte = cv.take<int64_t>((size_t)ntl);
+  int64_t *dptr = cv.take<int64_t>(c.ptr.size());
+  int32_t *dsrc = cv.take<int32_t>(c.src.size());
+  int64_t *dsb = cv.take<int64_t>((size_t)nsl), *dse = cv.take<int64_t>((size_t)nsl);
+  int64_t *dts = cv.take<int64_t>((size_t)n_tsort), *dss = cv.take<int64_t>((size_t)n_ssort);
+  CK(h, put(wl, c.wi_leaf.data(), c.wi_leaf.size()));
+  CK(h, put(wo, c.wi_off.data(), c.wi_off.size()));
+  CK(h, put(dtb, tb, (size_t)ntl));
+  CK(h, put(dte, te, (size_t)ntl));
+  CK(h, put(dptr, c.ptr.data(), c.ptr.size()));
+  CK(h, put(dsrc, c.src.data(), c.src.size()));
+  CK(h, put(dsb, sb, (size_t)nsl));
+  CK(h, put(dse, se, (size_t)nsl));
+  if (n_tsort) CK(h, put(dts, tsort, (size_t)n_tsort));
+  if (n_ssort) CK(h, put(dss, ssort, (size_t)n_ssort));
+  out.wi_leaf = wl; out.wi_off = wo; out.tleaf_begin = dtb; out.tleaf_end = dte;
+  out.csr_ptr = dptr; out.csr_src = dsrc; out.sleaf_begin = dsb; out.sleaf_end = dse;
+  d_tsort = dts; d_ssort = dss;
+  return VPM_OK;
+}
+
+int64_t count_pairs(const int64_t *tb, const int64_t *te, const int64_t *sb, const int64_t *se,
+                    const int32_t *pt, const int32_t *ps, int64_t npairs) {
+  int64_t n = 0;
+  for (int64_t k = 0; k < npairs; ++k) n += (te[pt[k]] - tb[pt[k]]) * (se[ps[k]] - sb[ps[k]]);
+  return n;
+}
+
+}  // namespace
+
+// ============================================================== C ABI
+extern "C" {
+
+int vpm_abi_version(void) { return VPM_ABI_VERSION; }
+
+const char *vpm_last_error(const vpm_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vpm_num_devices(const vpm_handle *h) { return h ? (int)h->devs.size() : 0; }
+
+int vpm_create(vpm_handle **out, int n_gpus, const int *device_ids) {
+  if (!out) return fail(nullptr, VPM_EINVAL, "vpm_create: out is NULL");
+  *out = nullptr;
+  if (n_gpus < 1 || n_gpus > 64) return fail(nullptr, VPM_EINVAL, "vpm_create: n_gpus=%d", n_gpus);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count < 1) {
+    cudaGetLastError();
+    return fail(nullptr, VPM_ENODEV, "vpm_create: no usable CUDA device (%s); there is no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  vpm_handle *h = new (std::nothrow) vpm_handle();
+  if (!h) return fail(nullptr, VPM_ENOMEM, "vpm_create: out of host memory");
+  for (int g = 0; g < n_gpus; ++g) {
+    Dev d;
+    d.id = device_ids ? device_ids[g] : g;
+    if (d.id < 0 || d.id >= count) {
+      int rc = fail(nullptr, VPM_ENODEV, "vpm_create: device %d not present (%d visible)", d.id, count);
+      delete h;
+      return rc;
+    }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(d.id) != cudaSuccess || cudaGetDeviceProperties(&prop, d.id) != cudaSuccess) {
+      int rc = fail(nullptr, VPM_ECUDA, "vpm_create: cannot open device %d: %s", d.id,
+                    cudaGetErrorString(cudaGetLastError()));
+      delete h;
+      return rc;
+    }
+    if (prop.major < 10) {
+      int rc = fail(nullptr, VPM_ENODEV,
+                    "vpm_create: device %d is sm_%d%d; libvpm_cuda is built for sm_100a only", d.id,
+                    prop.major, prop.minor);
+      delete h;
+      return rc;
+    }
+    d.sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) {
+      int rc = fail(nullptr, VPM_ECUDA, "vpm_create: stream: %s", cudaGetErrorString(cudaGetLastError()));
+      delete h;
+      return rc;
+    }
+    for (auto &ev : d.ev) cudaEventCreate(&ev);
+    h->devs.push_back(d);
+  }
+  *out = h;
+  return VPM_OK;
+}
+
+int vpm_destroy(vpm_handle *h) {
+  if (!h) return VPM_OK;
+  for (void *p : h->pinned) cudaHostUnregister(p);
+  if (g_nccl.comm_destroy)
+    for (void *c : h->comms) if (c) g_nccl.comm_destroy(c);
+  for (Dev &d : h->devs) {
+    cudaSetDevice(d.id);
+    cudaStreamSynchronize(d.stream);
+    for (Buf *b : {&d.in7, &d.stat, &d.res18, &d.sfs3, &d.rec, &d.srec, &d.partial, &d.tbuf, &d.sbuf,
+                   &d.ibuf, &d.jbuf})
+      if (b->p) cudaFree(b->p);
+    for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
+    if (d.stream) cudaStreamDestroy(d.stream);
+  }
+  if (h->h_stat) cudaFreeHost(h->h_stat);
+  cudaGetLastError();
+  delete h;
+  return VPM_OK;
+}
+
+int vpm_pin_host(vpm_handle *h, void *ptr, size_t bytes) {
+  if (!h || !ptr || bytes == 0) return fail(h, VPM_EINVAL, "vpm_pin_host: bad argument");
+  CK(h, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  h->pinned.push_back(ptr);
+  return VPM_OK;
+}
+
+int vpm_unpin_host(vpm_handle *h, void *ptr) {
+  if (!h || !ptr) return fail(h, VPM_EINVAL, "vpm_unpin_host: bad argument");
+  auto it = std::find(h->pinned.begin(), h->pinned.end(), ptr);
+  if (it == h->pinned.end()) return fail(h, VPM_EINVAL, "vpm_unpin_host: pointer was not pinned by this handle");
+  CK(h, cudaHostUnregister(ptr));
+  h->pinned.erase(it);
+  return VPM_OK;
+}
+
+static int check_field(vpm_handle *h, const char *fn, const void *P, int64_t nf, int64_t np, int kernel) {
+  if (!h) return VPM_EINVAL;
+  if (np < 0 || nf < MIN_FIELDS) return fail(h, VPM_EINVAL, "%s: need nfields >= 43 and np >= 0 (got %lld, %lld)", fn, (long long)nf, (long long)np);
+  if (!P && np > 0) return fail(h, VPM_EINVAL, "%s: particles is NULL", fn);
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "%s: unknown kernel_id %d", fn, kernel);
+  return VPM_OK;
+}
+
+int vpm_uj_direct(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel, int flags) {
+  TRY(check_field(h, "vpm_uj_direct", P, nf, np, kernel));
+  if (h->devs.size() > 1) return uj_direct_multi(h, P, nf, np, kernel, flags);
+  Dev &d = h->devs[0];
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  CK(h, cudaEventRecord(d.ev[0], d.stream));
+  const bool reset = flags & VPM_FLAG_RESET;
+  const bool sfs_rows = (flags & VPM_FLAG_SFS) || (flags & VPM_FLAG_RESET_SFS);
+  bool has_static = false;
+  // previous SFS rows are needed unless every one of them is overwritten
+  TRY(h1_upload(h, d, P, nf, np, !reset, sfs_rows, has_static));
+  TRY(h1_eval(h, d, np, kernel, flags, has_static, !reset || has_static));
+  TRY(h1_download(h, d, P, nf, np, flags));
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+
+int vpm_uj_direct_f32(vpm_handle *h, float *P, int64_t nf, int64_t np, int kernel, int flags) {
+  TRY(check_field(h, "vpm_uj_direct_f32", P, nf, np, kernel));
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  CK(h, cudaEventRecord(d.ev[0], st));
+  const bool reset = flags & VPM_FLAG_RESET;
+  const bool sfs_rows = (flags & VPM_FLAG_SFS) || (flags & VPM_FLAG_RESET_SFS);
+  const size_t n = (size_t)std::max<int64_t>(np, 1);
+  TRY(ensure(h, d.in7, n * 7 * sizeof(double)));
+  TRY(ensure(h, d.res18, n * RES_ROWS * sizeof(double)));
+  TRY(ensure(h, d.sfs3, n * 3 * sizeof(double)));
+  TRY(ensure(h, d.jbuf, n * (7 + RES_ROWS + 3) * sizeof(float) + 64));
+  float *f_in7 = (float *)d.jbuf.p, *f_res = f_in7 + n * 7, *f_sfs = f_res + n * RES_ROWS;
+  bool has_static = false;
+  for (int64_t i = 0; i < np; ++i)
+    if (P[nf * i + R_STATIC] != 0.0f) { has_static = true; break; }
+  const bool prior = !reset || has_static;
+  if (np > 0) {
+    CK(h, cudaMemcpy2DAsync(f_in7, 7 * sizeof(float), P, nf * sizeof(float), 7 * sizeof(float), (size_t)np,
+                            cudaMemcpyHostToDevice, st));
+    cvt_f32_to_f64_kernel<<<blocks_for(np * 7, 256), 256, 0, st>>>(f_in7, (double *)d.in7.p, np * 7);
+    h->launches++;
+    if (has_static) {
+      if (h->h_stat_cap < (size_t)np) {
+        if (h->h_stat) cudaFreeHost(h->h_stat);
+        h->h_stat = nullptr; h->h_stat_cap = 0;
+        CK(h, cudaMallocHost((void **)&h->h_stat, (size_t)np * sizeof(double)));
+        h->h_stat_cap = (size_t)np;
+      }
+      for (int64_t i = 0; i < np; ++i) h->h_stat[i] = (double)P[nf * i + R_STATIC];
+      TRY(ensure(h, d.stat, (size_t)np * sizeof(double)));
+      CK(h, cudaMemcpyAsync(d.stat.p, h->h_stat, (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (prior) {
+      CK(h, cudaMemcpy2DAsync(f_res, RES_ROWS * sizeof(float), P + R_U, nf * sizeof(float),
+                              RES_ROWS * sizeof(float), (size_t)np, cudaMemcpyHostToDevice, st));
+      cvt_f32_to_f64_kernel<<<blocks_for(np * RES_ROWS, 256), 256, 0, st>>>(f_res, (double *)d.res18.p, np * RES_ROWS);
+      h->launches++;
+    }
+    if (sfs_rows) {
+      CK(h, cudaMemcpy2DAsync(f_sfs, 3 * sizeof(float), P + R_SFS, nf * sizeof(float), 3 * sizeof(float),
+                              (size_t)np, cudaMemcpyHostToDevice, st));
+      cvt_f32_to_f64_kernel<<<blocks_for(np * 3, 256), 256, 0, st>>>(f_sfs, (double *)d.sfs3.p, np * 3);
+      h->launches++;
+    }
+    CK(h, cudaGetLastError());
+  }
+  TRY(h1_eval(h, d, np, kernel, flags, has_static, prior));
+  if (np > 0) {
+    cvt_f64_to_f32_kernel<<<blocks_for(np * RES_ROWS, 256), 256, 0, st>>>((const double *)d.res18.p, f_res, np * RES_ROWS);
+    h->launches++;
+    CK(h, cudaMemcpy2DAsync(P + R_U, nf * sizeof(float), f_res, RES_ROWS * sizeof(float),
+                            RES_ROWS * sizeof(float), (size_t)np, cudaMemcpyDeviceToHost, st));
+    if (sfs_rows) {
+      cvt_f64_to_f32_kernel<<<blocks_for(np * 3, 256), 256, 0, st>>>((const double *)d.sfs3.p, f_sfs, np * 3);
+      h->launches++;
+      CK(h, cudaMemcpy2DAsync(P + R_SFS, nf * sizeof(float), f_sfs, 3 * sizeof(float), 3 * sizeof(float),
+                              (size_t)np, cudaMemcpyDeviceToHost, st));
+    }
+    CK(h, cudaGetLastError());
+  }
+  CK(h, cudaEventRecord(d.ev[5], st));
+  CK(h, cudaStreamSynchronize(st));
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+int vpm_upload_state(vpm_handle *h, const double *P, int64_t nf, int64_t np) {
+  TRY(check_field(h, "vpm_upload_state", P, nf, np, 0));
+  Dev &d = h->devs[0];
+  CK(h, cudaSetDevice(d.id));
+  CK(h, cudaEventRecord(d.ev[0], d.stream));
+  bool has_static = false;
+  TRY(h1_upload(h, d, P, nf, np, true, true, has_static));
+  CK(h, cudaStreamSynchronize(d.stream));
+  h->np_resident = np;
+  h->resident_static = has_static;
+  h->resident_prior = true;
+  return VPM_OK;
+}
+
+int vpm_eval(vpm_handle *h, int kernel, int flags) {
+  if (!h) return VPM_EINVAL;
+  if (h->np_resident < 0) return fail(h, VPM_ESTATE, "vpm_eval: no resident state (call vpm_upload_state first)");
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "vpm_eval: unknown kernel_id %d", kernel);
+  Dev &d = h->devs[0];
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  CK(h, cudaEventRecord(d.ev[0], d.stream));
+  TRY(h1_eval(h, d, h->np_resident, kernel, flags, h->resident_static, true));
+  CK(h, cudaEventRecord(d.ev[5], d.stream));
+  CK(h, cudaStreamSynchronize(d.stream));
+  h1_fill_timing(h, d);
+  return VPM_OK;
+}
+
+int vpm_download_results(vpm_handle *h, double *P, int64_t nf, int64_t np, int flags) {
+  TRY(check_field(h, "vpm_download_results", P, nf, np, 0));
+  if (h->np_resident != np) return fail(h, VPM_ESTATE, "vpm_download_results: np=%lld but %lld particles are resident", (long long)np, (long long)h->np_resident);
+  return h1_download(h, h->devs[0], P, nf, np, flags | VPM_FLAG_SFS);
+}
+
+int vpm_uj_direct_st(vpm_handle *h, const double *S, int64_t nfs, int64_t nps, double *Tg, int64_t nft,
+                     int64_t npt, int kernel) {
+  TRY(check_field(h, "vpm_uj_direct_st(source)", S, nfs, nps, kernel));
+  TRY(check_field(h, "vpm_uj_direct_st(target)", Tg, nft, npt, kernel));
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  if (npt == 0) return VPM_OK;
+  TRY(ensure(h, d.in7, (size_t)std::max<int64_t>(nps, 1) * 7 * sizeof(double)));
+  TRY(ensure(h, d.tbuf, (size_t)npt * 3 * sizeof(double)));
+  TRY(ensure(h, d.res18, (size_t)npt * RES_ROWS * sizeof(double)));
+  CK(h, cudaEventRecord(d.ev[0], st));
+  if (nps > 0)
+    CK(h, cudaMemcpy2DAsync(d.in7.p, 7 * sizeof(double), S, nfs * sizeof(double), 7 * sizeof(double),
+                            (size_t)nps, cudaMemcpyHostToDevice, st));
+  CK(h, cudaMemcpy2DAsync(d.tbuf.p, 3 * sizeof(double), Tg, nft * sizeof(double), 3 * sizeof(double),
+                          (size_t)npt, cudaMemcpyHostToDevice, st));
+  CK(h, cudaMemcpy2DAsync(d.res18.p, RES_ROWS * sizeof(double), Tg + R_U, nft * sizeof(double),
+                          RES_ROWS * sizeof(double), (size_t)npt, cudaMemcpyHostToDevice, st));
+  CK(h, cudaEventRecord(d.ev[1], st));
+  SrcView src{(const double *)d.in7.p, 7, 0, 3, 6};
+  Plan plan;
+  TRY(uj_sweep(h, d, st, kernel, (const double *)d.tbuf.p, 3, npt, src, 0, nps, 0, plan));
+  CK(h, cudaEventRecord(d.ev[2], st));
+  UjFinishArgs f;
+  f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+  f.nt = npt; f.out = (double *)d.res18.p; f.ld = RES_ROWS; f.urow = RES_U; f.jrow = RES_J;
+  f.zrow0 = -1; f.zrow1 = -1; f.want_U = 1; f.want_J = 1; f.accumulate = 1; f.reset = 0;
+  f.stat = nullptr; f.sld = 1;
+  uj_finish_kernel<<<blocks_for(npt, 256), 256, 0, st>>>(f);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(d.ev[3], st));
+  CK(h, cudaEventRecord(d.ev[4], st));
+  CK(h, cudaMemcpy2DAsync(Tg + R_U, nft * sizeof(double), d.res18.p, RES_ROWS * sizeof(double),
+                          RES_ROWS * sizeof(double), (size_t)npt, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaEventRecord(d.ev[5], st));
+  CK(h, cudaStreamSynchronize(st));
+  h->timing.uj_pairs = nps * npt;
+  h->timing.sfs_pairs = 0;
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+int vpm_p2p_buffers(vpm_handle *h, double *tgt, int64_t ld, int64_t t0, int64_t t1, int row_pos,
+                    int row_grad, int row_hess, const double *src, int64_t s0, int64_t s1, int kernel,
+                    int want_U, int want_J) {
+  if (!h) return VPM_EINVAL;
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "vpm_p2p_buffers: unknown kernel_id %d", kernel);
+  if (t0 < 0 || t1 < t0 || s0 < 0 || s1 < s0 || ld < 3)
+    return fail(h, VPM_EINVAL, "vpm_p2p_buffers: bad ranges [%lld,%lld) [%lld,%lld) ld=%lld", (long long)t0, (long long)t1, (long long)s0, (long long)s1, (long long)ld);
+  if (row_pos < 0 || row_pos + 3 > ld || (want_U && (row_grad < 0 || row_grad + 3 > ld)) ||
+      (want_J && (row_hess < 0 || row_hess + 9 > ld)))
+    return fail(h, VPM_EINVAL, "vpm_p2p_buffers: row offsets outside the %lld-row target buffer", (long long)ld);
+  const int64_t nt = t1 - t0, ns = s1 - s0;
+  if (nt == 0 || ns == 0 || (!want_U && !want_J)) return VPM_OK;
+  if (!tgt || !src) return fail(h, VPM_EINVAL, "vpm_p2p_buffers: NULL buffer");
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  TRY(ensure(h, d.tbuf, (size_t)nt * ld * sizeof(double)));
+  TRY(ensure(h, d.sbuf, (size_t)ns * 8 * sizeof(double)));
+  CK(h, cudaEventRecord(d.ev[0], st));
+  CK(h, cudaMemcpyAsync(d.tbuf.p, tgt + t0 * ld, (size_t)nt * ld * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(h, cudaMemcpyAsync(d.sbuf.p, src + s0 * 8, (size_t)ns * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(h, cudaEventRecord(d.ev[1], st));
+  SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
+  Plan plan;
+  TRY(uj_sweep(h, d, st, kernel, (const double *)d.tbuf.p + row_pos, ld, nt, sv, 0, ns, 0, plan));
+  CK(h, cudaEventRecord(d.ev[2], st));
+  UjFinishArgs f;
+  f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+  f.nt = nt; f.out = (double *)d.tbuf.p; f.ld = ld; f.urow = row_grad; f.jrow = row_hess;
+  f.zrow0 = -1; f.zrow1 = -1; f.want_U = want_U; f.want_J = want_J; f.accumulate = 1; f.reset = 0;
+  f.stat = nullptr; f.sld = 1;
+  uj_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(d.ev[3], st));
+  CK(h, cudaEventRecord(d.ev[4], st));
+  CK(h, cudaMemcpyAsync(tgt + t0 * ld, d.tbuf.p, (size_t)nt * ld * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaEventRecord(d.ev[5], st));
+  CK(h, cudaStreamSynchronize(st));
+  h->timing.uj_pairs = nt * ns;
+  h->timing.sfs_pairs = 0;
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+int vpm_uj_device(vpm_handle *h, const double *d_src8, int64_t ns, int64_t t0, int64_t t1,
+                  double *d_out12, int kernel, int flags, void *stream) {
+  if (!h) return VPM_EINVAL;
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "vpm_uj_device: unknown kernel_id %d", kernel);
+  if (ns < 0 || t0 < 0 || t1 < t0 || t1 > ns) return fail(h, VPM_EINVAL, "vpm_uj_device: bad target range [%lld,%lld) of %lld", (long long)t0, (long long)t1, (long long)ns);
+  const int64_t nt = t1 - t0;
+  if (nt == 0) return VPM_OK;
+  if (!d_src8 || !d_out12) return fail(h, VPM_EINVAL, "vpm_uj_device: NULL device pointer");
+  Dev &d = h->devs[0];
+  cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  SrcView sv{d_src8, 8, 0, 4, 7};
+  Plan plan;
+  TRY(uj_sweep(h, d, st, kernel, d_src8 + t0 * 8, 8, nt, sv, 0, ns, flags, plan));
+  UjFinishArgs f;
+  f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+  f.nt = nt; f.out = d_out12; f.ld = 12; f.urow = 0; f.jrow = 3;
+  f.zrow0 = -1; f.zrow1 = -1; f.want_U = 1; f.want_J = 1; f.accumulate = 0; f.reset = 0;
+  f.stat = nullptr; f.sld = 1;
+  uj_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  h->timing.uj_pairs = nt * ns;
+  h->timing.kernel_launches = h->launches;
+  return VPM_OK;
+}
+
+int vpm_sfs_device(vpm_handle *h, const double *d_src8, const double *d_J9, const double *d_static,
+                   int64_t ns, int64_t t0, int64_t t1, double *d_out3, int kernel, int flags,
+                   void *stream) {
+  if (!h) return VPM_EINVAL;
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "vpm_sfs_device: unknown kernel_id %d", kernel);
+  if (ns < 0 || t0 < 0 || t1 < t0 || t1 > ns) return fail(h, VPM_EINVAL, "vpm_sfs_device: bad target range");
+  const int64_t nt = t1 - t0;
+  if (nt == 0) return VPM_OK;
+  if (!d_src8 || !d_J9 || !d_out3) return fail(h, VPM_EINVAL, "vpm_sfs_device: NULL device pointer");
+  Dev &d = h->devs[0];
+  cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  SrcView sv{d_src8, 8, 0, 4, 7};
+  Plan plan;
+  TRY(sfs_sweep(h, d, st, kernel, d_src8 + t0 * 8, 8, d_J9 + t0 * 9, 9, nullptr, nt, sv, d_J9, 9, 0,
+                d_static, 1, nullptr, ns, flags, plan));
+  SfsFinishArgs f;
+  f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+  f.nt = nt; f.tindex = nullptr; f.out = d_out3; f.ld = 3; f.row = 0; f.accumulate = 0; f.reset = 0;
+  f.filter_static = 0;  // static targets get an (ignored) value; the caller masks them
+  f.stat = nullptr; f.sld = 1;
+  sfs_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  h->timing.sfs_pairs = nt * ns;
+  h->timing.kernel_launches = h->launches;
+  return VPM_OK;
+}
+
+
+int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int row_pos, int row_grad,
+                      int row_hess, const double *src, int64_t n_src, const int64_t *tb,
+                      const int64_t *te, int64_t ntl, const int64_t *sb, const int64_t *se, int64_t nsl,
+                      const int32_t *pt, const int32_t *ps, int64_t npairs, int kernel, int want_U,
+                      int want_J) {
+  if (!h) return VPM_EINVAL;
+  const char *fn = "vpm_p2p_leafpairs";
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "%s: unknown kernel_id %d", fn, kernel);
+  if (n_tgt < 0 || n_src < 0 || ntl < 0 || nsl < 0 || npairs < 0 || ld < 3)
+    return fail(h, VPM_EINVAL, "%s: negative size or ld < 3", fn);
+  if (row_pos < 0 || row_pos + 3 > ld || (want_U && (row_grad < 0 || row_grad + 3 > ld)) ||
+      (want_J && (row_hess < 0 || row_hess + 9 > ld)))
+    return fail(h, VPM_EINVAL, "%s: row offsets outside the %lld-row target buffer", fn, (long long)ld);
+  if (npairs == 0 || n_tgt == 0 || n_src == 0 || (!want_U && !want_J)) return VPM_OK;
+  if (!tgt || !src || !tb || !te || !sb || !se || !pt || !ps) return fail(h, VPM_EINVAL, "%s: NULL argument", fn);
+  HostCsr c;
+  TRY(build_csr(h, fn, tb, te, ntl, n_tgt, sb, se, nsl, n_src, pt, ps, npairs, c));
+  if (c.wi_leaf.empty()) return VPM_OK;
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  TRY(ensure(h, d.tbuf, (size_t)n_tgt * ld * sizeof(double)));
+  TRY(ensure(h, d.sbuf, (size_t)n_src * 8 * sizeof(double)));
+  const int64_t ns_pad = round_up(n_src, kTile);
+  TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
+  CK(h, cudaEventRecord(d.ev[0], st));
+  CK(h, cudaMemcpyAsync(d.tbuf.p, tgt, (size_t)n_tgt * ld * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(h, cudaMemcpyAsync(d.sbuf.p, src, (size_t)n_src * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+  LeafUjArgs a;
+  const int64_t *dts, *dss;
+  TRY(upload_csr(h, d, st, c, tb, te, ntl, sb, se, nsl, nullptr, 0, nullptr, 0, a.csr, dts, dss));
+  CK(h, cudaEventRecord(d.ev[1], st));
+  SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
+  prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (double *)d.rec.p);
+  h->launches++;
+  a.tpos = (const double *)d.tbuf.p + row_pos; a.tld = ld; a.rec = (const double *)d.rec.p;
+  a.out = (double *)d.tbuf.p; a.urow = row_grad; a.jrow = row_hess; a.want_U = want_U; a.want_J = want_J;
+  a.shortcut = 1;
+  const unsigned nwi = (unsigned)c.wi_leaf.size();
+  switch (kernel) {
+    case K_SING: uj_leaf_kernel<K_SING><<<nwi, kThreads, 0, st>>>(a); break;
+    case K_GAUS: uj_leaf_kernel<K_GAUS><<<nwi, kThreads, 0, st>>>(a); break;
+    case K_GERF: uj_leaf_kernel<K_GERF><<<nwi, kThreads, 0, st>>>(a); break;
+    default: uj_leaf_kernel<K_WINCK><<<nwi, kThreads, 0, st>>>(a); break;
+  }
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(d.ev[2], st));
+  CK(h, cudaEventRecord(d.ev[3], st));
+  CK(h, cudaEventRecord(d.ev[4], st));
+  CK(h, cudaMemcpyAsync(tgt, d.tbuf.p, (size_t)n_tgt * ld * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaEventRecord(d.ev[5], st));
+  CK(h, cudaStreamSynchronize(st));
+  h->timing.uj_pairs = count_pairs(tb, te, sb, se, pt, ps, npairs);
+  h->timing.sfs_pairs = 0;
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+int vpm_estr_leafpairs(vpm_handle *h, double *P, int64_t nf, int64_t np, const int64_t *tsort,
+                       const int64_t *ssort, const int64_t *tb, const int64_t *te, int64_t ntl,
+                       const int64_t *sb, const int64_t *se, int64_t nsl, const int32_t *pt,
+                       const int32_t *ps, int64_t npairs, int kernel, int flags) {
+  const char *fn = "vpm_estr_leafpairs";
+  TRY(check_field(h, fn, P, nf, np, kernel));
+  if (ntl < 0 || nsl < 0 || npairs < 0) return fail(h, VPM_EINVAL, "%s: negative size", fn);
+  if (npairs == 0 || np == 0) return VPM_OK;
+  if (!tsort || !ssort || !tb || !te || !sb || !se || !pt || !ps) return fail(h, VPM_EINVAL, "%s: NULL argument", fn);
+  for (int64_t i = 0; i < np; ++i)
+    if (tsort[i] < 0 || tsort[i] >= np || ssort[i] < 0 || ssort[i] >= np)
+      return fail(h, VPM_EINVAL, "%s: sort index %lld out of range", fn, (long long)i);
+  HostCsr c;
+  TRY(build_csr(h, fn, tb, te, ntl, np, sb, se, nsl, np, pt, ps, npairs, c));
+  if (c.wi_leaf.empty()) return VPM_OK;
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  TRY(ensure(h, d.in7, (size_t)np * 7 * sizeof(double)));
+  TRY(ensure(h, d.jbuf, (size_t)np * 9 * sizeof(double)));
+  TRY(ensure(h, d.sfs3, (size_t)np * 3 * sizeof(double)));
+  const int64_t ns_pad = round_up(np, kTile);
+  TRY(ensure(h, d.srec, (size_t)ns_pad * kSfsRec * sizeof(double)));
+  CK(h, cudaEventRecord(d.ev[0], st));
+  CK(h, cudaMemcpy2DAsync(d.in7.p, 7 * sizeof(double), P, nf * sizeof(double), 7 * sizeof(double),
+                          (size_t)np, cudaMemcpyHostToDevice, st));
+  CK(h, cudaMemcpy2DAsync(d.jbuf.p, 9 * sizeof(double), P + R_J, nf * sizeof(double), 9 * sizeof(double),
+                          (size_t)np, cudaMemcpyHostToDevice, st));
+  CK(h, cudaMemcpy2DAsync(d.sfs3.p, 3 * sizeof(double), P + R_SFS, nf * sizeof(double), 3 * sizeof(double),
+                          (size_t)np, cudaMemcpyHostToDevice, st));
+  LeafSfsArgs a;
+  const int64_t *dts, *dss;
+  TRY(upload_csr(h, d, st, c, tb, te, ntl, sb, se, nsl, tsort, np, ssort, np, a.csr, dts, dss));
+  CK(h, cudaEventRecord(d.ev[1], st));
+  CK(h, cudaEventRecord(d.ev[2], st));
+  CK(h, cudaEventRecord(d.ev[3], st));
+  const int transposed = (flags & VPM_FLAG_TRANSPOSED) ? 1 : 0;
+  SrcView sv{(const double *)d.in7.p, 7, 0, 3, 6};
+  prep_sfs_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, (const double *)d.jbuf.p, 9, 0, nullptr, 1,
+                                                            dss, np, ns_pad, kernel, transposed,
+                                                            (double *)d.srec.p);
+  h->launches++;
+  a.tpos = (const double *)d.in7.p; a.tld = 7; a.tJ = (const double *)d.jbuf.p; a.jld = 9;
+  a.tindex = dts; a.rec = (const double *)d.srec.p; a.out = (double *)d.sfs3.p; a.old = 3; a.orow = 0;
+  a.transposed = transposed;
+  a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
+  const unsigned nwi = (unsigned)c.wi_leaf.size();
+  switch (kernel) {
+    case K_SING: sfs_leaf_kernel<K_SING><<<nwi, kThreads, 0, st>>>(a); break;
+    case K_GAUS: sfs_leaf_kernel<K_GAUS><<<nwi, kThreads, 0, st>>>(a); break;
+    case K_GERF: sfs_leaf_kernel<K_GERF><<<nwi, kThreads, 0, st>>>(a); break;
+    default: sfs_leaf_kernel<K_WINCK><<<nwi, kThreads, 0, st>>>(a); break;
+  }
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(d.ev[4], st));
+  CK(h, cudaMemcpy2DAsync(P + R_SFS, nf * sizeof(double), d.sfs3.p, 3 * sizeof(double), 3 * sizeof(double),
+                          (size_t)np, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaEventRecord(d.ev[5], st));
+  CK(h, cudaStreamSynchronize(st));
+  h->timing.uj_pairs = 0;
+  h->timing.sfs_pairs = count_pairs(tb, te, sb, se, pt, ps, npairs);
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+int vpm_get_timing(const vpm_handle *h, vpm_timing *out) {
+  if (!h || !out) return VPM_EINVAL;
+  *out = h->timing;
+  return VPM_OK;
+}
+
+int vpm_measure_dfma_peak(vpm_handle *h, double *dfma_per_s, double *elapsed_ms) {
+  if (!h || !dfma_per_s) return VPM_EINVAL;
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  TRY(ensure(h, d.ibuf, 4096));
+  const int threads = 256, blocks = d.sm_count * 8, iters = 4096;
+  dfma_peak_kernel<<<blocks, threads, 0, st>>>((double *)d.ibuf.p, 64, 1.0);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(h, cudaEventRecord(d.ev[6], st));
+    dfma_peak_kernel<<<blocks, threads, 0, st>>>((double *)d.ibuf.p, iters, 1.0);
+    CK(h, cudaEventRecord(d.ev[7], st));
+    CK(h, cudaStreamSynchronize(st));
+    CK(h, cudaGetLastError());
+    best = std::min(best, ev_ms(d.ev[6], d.ev[7]));
+  }
+  const double n = (double)blocks * threads * (double)iters * 16.0 * 8.0;
+  *dfma_per_s = n / (best * 1e-3);
+  if (elapsed_ms) *elapsed_ms = best;
+  return VPM_OK;
+}
+
+int vpm_test_math(vpm_handle *h, int op, int arg, const double *in, double *out, double *out2, int64_t n) {
+  if (!h || !in || !out || n < 0) return fail(h, VPM_EINVAL, "vpm_test_math: bad argument");
+  if (n == 0) return VPM_OK;
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  TRY(ensure(h, d.tbuf, (size_t)n * sizeof(double)));
+  TRY(ensure(h, d.sbuf, (size_t)n * 2 * sizeof(double)));
+  CK(h, cudaMemcpyAsync(d.tbuf.p, in, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  double *o1 = (double *)d.sbuf.p, *o2 = o1 + n;
+  test_math_kernel<<<blocks_for(n, 256), 256, 0, st>>>(op, arg, (const double *)d.tbuf.p, o1, o2, n);
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(out, o1, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (out2) CK(h, cudaMemcpyAsync(out2, o2, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  return VPM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,703 @@
+// vpm_kernels.cuh -- sm_100a kernels of the rVPM particle-to-particle path.
+//
+// Reference arithmetic being evaluated (paths under FLOWVPM.jl v4.0.3):
+//   U/J pair loop   src/FLOWVPM_fmm.jl:102-168   (fmm.direct! overload)
+//   kernel families src/FLOWVPM_kernel.jl:44-84
+//   SFS pair term   src/FLOWVPM_subfilterscale_models.jl:16-41
+//
+// Design: one thread owns T targets and keeps their 15 FP64
+// accumulators in registers; source particles are pre-digested once per sweep
+// into fixed-size records (positions, -Gamma/4pi, powers of 1/sigma) so that
+// the O(N^2) loop contains no division and no square root -- only FP64 FMA-pipe
+// work plus one MUFU.RSQ64H seed per pair; records are streamed into shared
+// memory tile by tile with 1-D TMA bulk copies (cp.async.bulk + mbarrier,
+// double buffered) and read back as warp-wide broadcasts (LDS.128).  No
+// atomics: every (target, source-split) partial sum has one owner and the
+// splits are combined in a fixed order, so results are run-to-run identical.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "vpm_math.cuh"
+
+namespace vpm {
+
+enum { K_SING = 0, K_GAUS = 1, K_GERF = 2, K_WINCK = 3 };
+
+constexpr int kRec = 10;      // doubles per U/J source record (80 B, 5 x LDS.128)
+constexpr int kSfsRec = 18;   // doubles per SFS source record (144 B, 9 x LDS.128)
+constexpr int kTile = 128;    // sources per shared-memory tile
+constexpr int kThreads = 128; // threads per CTA of the pair kernels
+constexpr int kAcc = 15;      // U(3) + J(9) + W(3) partial sums per target
+constexpr int kStages = 2;
+
+// far-field cutoffs in u = (r/sigma)^2 beyond which g == 1 and dg == 0 to
+// < 2e-16 relative (gaussianerf: s >= 9; gaussian: s >= 3.45, s^3 >= 41)
+__device__ constexpr double kFarU_gerf = 81.0;
+__device__ constexpr double kFarU_gaus = 11.9025;
+// SFS: zeta below 1e-26 of zeta(0) (gaussianerf u >= 120; gaussian s^3 >= 60)
+__device__ constexpr double kSfsFarU_gerf = 120.0;
+__device__ constexpr double kSfsFarU_gaus = 15.4;
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                             uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ------------------------------------------------------------ record builders
+// U/J record of source i:  [x y z q0 | G'x G'y G'z q1 | q2 0],  G' = -Gamma/(4 pi)
+//   winckelmans: q0 = 1/s^2, q1 = 1/s^3, q2 = -3/s^5
+//   gaussian(erf): q0 = 1/s^2, q1 = 1/s
+struct SrcView {
+  const double *p;  // base of a column-major matrix
+  int64_t ld;       // rows per column
+  int ox, og, osig; // 0-based rows of X, Gamma, sigma
+};
+
+__global__ void prep_uj_records(SrcView src, int64_t s0, int64_t ns, int64_t ns_pad, int kernel,
+                                double *__restrict__ rec) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns_pad) return;
+  double *r = rec + i * kRec;
+  if (i >= ns) {
+#pragma unroll
+    for (int k = 0; k < kRec; ++k) r[k] = 0.0;
+    return;
+  }
+  const double *p = src.p + (s0 + i) * src.ld;
+  double sigma = p[src.osig];
+  double isig = 1.0 / sigma;
+  double isig2 = isig * isig;
+  double isig3 = isig2 * isig;
+  double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+  if (kernel == K_WINCK) {
+    q0 = isig2; q1 = isig3; q2 = -3.0 * isig3 * isig2;
+  } else if (kernel == K_GERF || kernel == K_GAUS) {
+    q0 = isig2; q1 = isig;
+  }
+  r[0] = p[src.ox]; r[1] = p[src.ox + 1]; r[2] = p[src.ox + 2]; r[3] = q0;
+  r[4] = -kConst4 * p[src.og]; r[5] = -kConst4 * p[src.og + 1]; r[6] = -kConst4 * p[src.og + 2];
+  r[7] = q1; r[8] = q2; r[9] = 0.0;
+}
+
+// SFS record of source i: [x y z q0 | Gx Gy Gz q1 | J(row-of-3 order) 0], q0 = 1/s^2,
+// q1 = zeta-prefactor / s^3 (0 for sources the sweep must ignore).
+// src_index (nullable) maps record i -> particle column (leaf-list form).
+__global__ void prep_sfs_records(SrcView src, const double *__restrict__ J, int64_t jld, int joff,
+                                 const double *__restrict__ stat, int64_t sld,
+                                 const int64_t *__restrict__ src_index, int64_t ns,
+                                 int64_t ns_pad, int kernel, int transposed,
+                                 double *__restrict__ rec) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns_pad) return;
+  double *r = rec + i * kSfsRec;
+  if (i >= ns) {
+#pragma unroll
+    for (int k = 0; k < kSfsRec; ++k) r[k] = 0.0;
+    return;
+  }
+  int64_t c = src_index ? src_index[i] : i;
+  const double *p = src.p + c * src.ld;
+  double isig = 1.0 / p[src.osig];
+  double isig3 = isig * isig * isig;
+  double pref = kernel == K_WINCK  ? kConst4 * 7.5
+                : kernel == K_GERF ? kConst1
+                : kernel == K_GAUS ? kConst3
+                                   : 1.0;
+  bool is_static = stat != nullptr && stat[c * sld] != 0.0;
+  r[0] = p[src.ox]; r[1] = p[src.ox + 1]; r[2] = p[src.ox + 2]; r[3] = isig * isig;
+  r[4] = p[src.og]; r[5] = p[src.og + 1]; r[6] = p[src.og + 2];
+  r[7] = is_static ? 0.0 : pref * isig3;
+  // J is stored so that S_k = sum_m D[3k+m] G_m in both schemes: the classic
+  // scheme reads the transpose (src/FLOWVPM_subfilterscale_models.jl:24-31)
+  const double *j = J + c * jld + joff;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int m = 0; m < 3; ++m) r[8 + 3 * k + m] = transposed ? j[3 * k + m] : j[k + 3 * m];
+  r[17] = 0.0;
+}
+
+// ------------------------------------------------------- per-pair kernel math
+// Every family is reduced to two scalars per pair,
+//   A = g(s) / r^3                      (U += A c,  W += A G',  c = dx x G')
+//   B = (dg/(sigma r) - 3 g / r^2)/r^3  (J_ij += B c_i dx_j)
+// so that U and J need no 1/r at all where the family allows it.
+//
+// winckelmans (src/FLOWVPM_kernel.jl:77-84), with a = s^2 + 1:
+//   g/r^3 = (s^2 + 2.5) a^-5/2 / sigma^3
+//   B     = -3 (s^2 + 3.5) a^-7/2 / sigma^5      (the reference's aux/r^3 after
+//           cancelling dg/(sigma r) against 3g/r^2 analytically)
+// Both are regular at r = 0; the reference skips r2 == 0 (src/FLOWVPM_fmm.jl:118),
+// which only matters for the W term (c and dx vanish), so A is masked there.
+__device__ __forceinline__ void ab_winck(double r2, double q0, double q1, double q2, double &A,
+                                         double &B) {
+  double a = fma(r2, q0, 1.0);
+  double y = rsqrt_fp64(a);
+  double y2 = y * y;
+  double y4 = y2 * y2;
+  double y5 = y4 * y;
+  double y7 = y5 * y2;
+  A = (q1 * y5) * (a + 1.5);
+  B = (q2 * y7) * (a + 2.5);
+  A = select_zero(is_zero_bits(r2), A);
+}
+
+// singular (src/FLOWVPM_kernel.jl:48): g = 1, dg = 0  ->  A = 1/r^3, B = -3/r^5
+__device__ __forceinline__ void ab_sing(double r2, double &A, double &B) {
+  double rinv = rsqrt_fp64(r2);
+  double rinv2 = rinv * rinv;
+  double a = rinv2 * rinv;
+  double b = -3.0 * a * rinv2;
+  bool z = is_zero_bits(r2);
+  A = select_zero(z, a);
+  B = select_zero(z, b);
+}
+
+// gaussianerf near field (src/FLOWVPM_kernel.jl:54-57), reference formula order:
+//   aux = sqrt(2/pi) s e^{-s^2/2};  g = erf(s/sqrt2) - aux;  dg = s aux
+__device__ __forceinline__ void ab_gerf(double r2, double q0, double q1, double &A, double &B) {
+  double rinv = rsqrt_fp64(r2);
+  double r = r2 * rinv;
+  double s = r * q1;
+  double E = exp_neg_fp64(0.5 * (r2 * q0));
+  double aux = kConst2 * s * E;
+  double g = erf(s * kInvSqrt2) - aux;
+  double dg = s * aux;
+  double rinv2 = rinv * rinv;
+  double rinv3 = rinv2 * rinv;
+  double a = g * rinv3;
+  double b = (dg * q1 * rinv - 3.0 * g * rinv2) * rinv3;
+  bool z = is_zero_bits(r2);
+  A = select_zero(z, a);
+  B = select_zero(z, b);
+}
+
+// gaussian near field (src/FLOWVPM_kernel.jl:63-66): g = 1 - e^{-s^3}, dg = 3 s^2 e^{-s^3}
+__device__ __forceinline__ void ab_gaus(double r2, double q0, double q1, double &A, double &B) {
+  double rinv = rsqrt_fp64(r2);
+  double r = r2 * rinv;
+  double s = r * q1;
+  double E = exp_neg_fp64(s * s * s);
+  double g = 1.0 - E;
+  double dg = 3.0 * s * s * E;
+  double rinv2 = rinv * rinv;
+  double rinv3 = rinv2 * rinv;
+  double a = g * rinv3;
+  double b = (dg * q1 * rinv - 3.0 * g * rinv2) * rinv3;
+  bool z = is_zero_bits(r2);
+  A = select_zero(z, a);
+  B = select_zero(z, b);
+}
+
+// zeta(s)/sigma^3 weight of the SFS sweep (src/FLOWVPM_kernel.jl:45,51,60,69-74),
+// q1 carries prefactor/sigma^3.
+template <int K>
+__device__ __forceinline__ double sfs_weight(double r2, double q0, double q1) {
+  if constexpr (K == K_WINCK) {
+    double a = fma(r2, q0, 1.0);
+    double y = rsqrt_fp64(a);
+    double y2 = y * y;
+    double y4 = y2 * y2;
+    return q1 * (y4 * y2 * y);
+  } else if constexpr (K == K_GERF) {
+    return q1 * exp_neg_fp64(0.5 * (r2 * q0));
+  } else if constexpr (K == K_GAUS) {
+    double u = r2 * q0;
+    double s = select_zero(is_zero_bits(u), u * rsqrt_fp64(u));
+    return q1 * exp_neg_fp64(u * s);
+  } else {
+    return is_zero_bits(r2) ? q1 : 0.0;
+  }
+}
+
+// ------------------------------------------------------------- U/J pair sweep
+// One shared-memory tile of n source records against the T targets of this
+// thread (the O(N^2) inner loop of the U/J sweep).
+template <int K, int T>
+__device__ __forceinline__ void uj_tile(const double2 *__restrict__ tile, int n,
+                                        const double (&tx)[T], const double (&ty)[T],
+                                        const double (&tz)[T], double (&acc)[T][kAcc],
+                                        int shortcut) {
+#pragma unroll 2
+  for (int j = 0; j < n; ++j) {
+    const double2 v0 = tile[j * 5 + 0];
+    const double2 v1 = tile[j * 5 + 1];
+    const double2 v2 = tile[j * 5 + 2];
+    const double2 v3 = tile[j * 5 + 3];
+    const double2 v4 = tile[j * 5 + 4];
+    const double sx = v0.x, sy = v0.y, sz = v1.x, q0 = v1.y;
+    const double gx = v2.x, gy = v2.y, gz = v3.x, q1 = v3.y;
+    const double q2 = v4.x;
+
+    double dx[T], dy[T], dz[T], r2[T], A[T], B[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      dx[t] = tx[t] - sx; dy[t] = ty[t] - sy; dz[t] = tz[t] - sz;
+      r2[t] = fma(dz[t], dz[t], fma(dy[t], dy[t], dx[t] * dx[t]));
+    }
+    if constexpr (K == K_WINCK) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) ab_winck(r2[t], q0, q1, q2, A[t], B[t]);
+    } else if constexpr (K == K_SING) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) ab_sing(r2[t], A[t], B[t]);
+    } else {
+      const double far_u = (K == K_GERF) ? kFarU_gerf : kFarU_gaus;
+      bool near = !shortcut;
+#pragma unroll
+      for (int t = 0; t < T; ++t) near |= (r2[t] * q0 < far_u);
+      if (__any_sync(0xffffffffu, near)) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          if constexpr (K == K_GERF) ab_gerf(r2[t], q0, q1, A[t], B[t]);
+          else ab_gaus(r2[t], q0, q1, A[t], B[t]);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < T; ++t) ab_sing(r2[t], A[t], B[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      // c = dx x G'   (G' = -Gamma/4pi : c == reference crss * r^3)
+      double cx = fma(dy[t], gz, -(dz[t] * gy));
+      double cy = fma(dz[t], gx, -(dx[t] * gz));
+      double cz = fma(dx[t], gy, -(dy[t] * gx));
+      double *s = acc[t];
+      s[0] = fma(A[t], cx, s[0]);
+      s[1] = fma(A[t], cy, s[1]);
+      s[2] = fma(A[t], cz, s[2]);
+      s[12] = fma(A[t], gx, s[12]);
+      s[13] = fma(A[t], gy, s[13]);
+      s[14] = fma(A[t], gz, s[14]);
+      double bx = B[t] * cx, by = B[t] * cy, bz = B[t] * cz;
+      s[3] = fma(bx, dx[t], s[3]);
+      s[4] = fma(by, dx[t], s[4]);
+      s[5] = fma(bz, dx[t], s[5]);
+      s[6] = fma(bx, dy[t], s[6]);
+      s[7] = fma(by, dy[t], s[7]);
+      s[8] = fma(bz, dy[t], s[8]);
+      s[9] = fma(bx, dz[t], s[9]);
+      s[10] = fma(by, dz[t], s[10]);
+      s[11] = fma(bz, dz[t], s[11]);
+    }
+  }
+}
+
+
+struct UjArgs {
+  const double *tpos;  // target positions: tpos[i*tld + 0..2]
+  int64_t tld;
+  int64_t nt;
+  const double *rec;   // source records [ns_pad][kRec]
+  int64_t ns;
+  int tiles_per_split;
+  double *partial;     // [nsplit][kAcc][pstride]
+  int64_t pstride;
+  int shortcut;        // far-field shortcut for gaussian / gaussianerf
+};
+
+template <int K, int T>
+__global__ void __launch_bounds__(kThreads) uj_pairs_kernel(const UjArgs a) {
+  __shared__ __align__(128) double tiles[kStages][kTile * kRec];
+  __shared__ __align__(8) uint64_t full[kStages];
+
+  const int tid = threadIdx.x;
+  const int64_t tbase = (int64_t)blockIdx.x * (kThreads * T);
+
+  double tx[T], ty[T], tz[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    int64_t i = tbase + (int64_t)t * kThreads + tid;
+    if (i >= a.nt) i = a.nt - 1;
+    const double *p = a.tpos + i * a.tld;
+    tx[t] = p[0]; ty[t] = p[1]; tz[t] = p[2];
+  }
+  double acc[T][kAcc];
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc[t][k] = 0.0;
+
+  const int64_t ntiles = (a.ns + kTile - 1) / kTile;
+  const int64_t tile0 = (int64_t)blockIdx.y * a.tiles_per_split;
+  int64_t tile1 = tile0 + a.tiles_per_split;
+  if (tile1 > ntiles) tile1 = ntiles;
+  const int ntl = tile1 > tile0 ? (int)(tile1 - tile0) : 0;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int it) {
+    int64_t tile = tile0 + it;
+    int64_t first = tile * kTile;
+    int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
+    uint32_t bytes = (uint32_t)n * kRec * sizeof(double);
+    int st = it % kStages;
+    mbar_expect_tx(&full[st], bytes);
+    tma_bulk_g2s(&tiles[st][0], a.rec + first * kRec, bytes, &full[st]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kStages && s < ntl; ++s) issue(s);
+  }
+
+  for (int it = 0; it < ntl; ++it) {
+    const int st = it % kStages;
+    mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
+    const int64_t first = (tile0 + it) * kTile;
+    const int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
+    const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
+
+    uj_tile<K, T>(tile, n, tx, ty, tz, acc, a.shortcut);
+    __syncthreads();  // everyone is done reading stage st
+    if (tid == 0 && it + kStages < ntl) issue(it + kStages);
+  }
+
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    int64_t i = tbase + (int64_t)t * kThreads + tid;
+    if (i < a.nt) {
+      double *o = a.partial + (int64_t)blockIdx.y * kAcc * a.pstride + i;
+#pragma unroll
+      for (int k = 0; k < kAcc; ++k) o[(int64_t)k * a.pstride] = acc[t][k];
+    }
+  }
+}
+
+// Combine the source splits in increasing order, fold the W (Kronecker-delta)
+// sums into J (src/FLOWVPM_fmm.jl:146-158), and apply the reference's
+// reset-then-accumulate rule (src/FLOWVPM_particlefield.jl:464-490,
+// src/FLOWVPM_fmm.jl:170-176):   out = (reset && !static ? 0 : out) + sum.
+struct UjFinishArgs {
+  const double *partial;
+  int64_t pstride;
+  int nsplit;
+  int64_t nt;
+  double *out;       // column-major, column i <-> target i
+  int64_t ld;
+  int urow, jrow;    // 0-based rows of U(3) and J(9) in out
+  int zrow0, zrow1;  // extra 3-row groups zeroed on reset (vorticity, PSE), -1 = none
+  int want_U, want_J;
+  int accumulate;    // 0: overwrite
+  int reset;         // with accumulate: zero first where not static
+  const double *stat; // static flags (nullable), stride sld
+  int64_t sld;
+};
+
+__global__ void uj_finish_kernel(const UjFinishArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nt) return;
+  double s[kAcc];
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) s[k] = 0.0;
+  for (int sp = 0; sp < a.nsplit; ++sp) {
+    const double *p = a.partial + (int64_t)sp * kAcc * a.pstride + i;
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) s[k] += p[(int64_t)k * a.pstride];
+  }
+  // J flat index = row + 3*col; aux2*Gamma == W
+  s[3 + 1] -= s[14];
+  s[3 + 2] += s[13];
+  s[3 + 3] += s[14];
+  s[3 + 5] -= s[12];
+  s[3 + 6] -= s[13];
+  s[3 + 7] += s[12];
+  double *o = a.out + i * a.ld;
+  bool is_static = a.stat != nullptr && a.stat[i * a.sld] != 0.0;
+  bool keep = a.accumulate && !(a.reset && !is_static);
+  if (a.want_U) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[a.urow + k] = (keep ? o[a.urow + k] : 0.0) + s[k];
+  }
+  if (a.want_J) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[a.jrow + k] = (keep ? o[a.jrow + k] : 0.0) + s[3 + k];
+  }
+  if (a.reset && !is_static) {
+    if (a.zrow0 >= 0) { o[a.zrow0] = 0.0; o[a.zrow0 + 1] = 0.0; o[a.zrow0 + 2] = 0.0; }
+    if (a.zrow1 >= 0) { o[a.zrow1] = 0.0; o[a.zrow1 + 1] = 0.0; o[a.zrow1 + 2] = 0.0; }
+  }
+}
+
+// --------------------------------------------------------------- SFS pair sweep
+// One tile of SFS source records against the T targets of this thread.
+template <int K, int T>
+__device__ __forceinline__ void sfs_tile(const double2 *__restrict__ tile, int n,
+                                         const double (&tx)[T], const double (&ty)[T],
+                                         const double (&tz)[T], const double (&JT)[T][9],
+                                         double (&acc)[T][3], int shortcut) {
+#pragma unroll 2
+  for (int j = 0; j < n; ++j) {
+    const double2 v0 = tile[j * 9 + 0];
+    const double2 v1 = tile[j * 9 + 1];
+    const double sx = v0.x, sy = v0.y, sz = v1.x, q0 = v1.y;
+    double r2[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      double dx = sx - tx[t], dy = sy - ty[t], dz = sz - tz[t];
+      r2[t] = fma(dz, dz, fma(dy, dy, dx * dx));
+    }
+    if constexpr (K == K_GERF || K == K_GAUS) {
+      const double far_u = (K == K_GERF) ? kSfsFarU_gerf : kSfsFarU_gaus;
+      bool near = !shortcut;
+#pragma unroll
+      for (int t = 0; t < T; ++t) near |= (r2[t] * q0 < far_u);
+      if (!__any_sync(0xffffffffu, near)) continue;
+    }
+    const double2 v2 = tile[j * 9 + 2];
+    const double2 v3 = tile[j * 9 + 3];
+    const double gx = v2.x, gy = v2.y, gz = v3.x, q1 = v3.y;
+    const double2 j0 = tile[j * 9 + 4], j1 = tile[j * 9 + 5], j2 = tile[j * 9 + 6],
+                  j3 = tile[j * 9 + 7], j4 = tile[j * 9 + 8];
+    const double JS[9] = {j0.x, j0.y, j1.x, j1.y, j2.x, j2.y, j3.x, j3.y, j4.x};
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      double w = sfs_weight<K>(r2[t], q0, q1);
+      double S1 = (JT[t][0] - JS[0]) * gx;
+      S1 = fma(JT[t][1] - JS[1], gy, S1);
+      S1 = fma(JT[t][2] - JS[2], gz, S1);
+      double S2 = (JT[t][3] - JS[3]) * gx;
+      S2 = fma(JT[t][4] - JS[4], gy, S2);
+      S2 = fma(JT[t][5] - JS[5], gz, S2);
+      double S3 = (JT[t][6] - JS[6]) * gx;
+      S3 = fma(JT[t][7] - JS[7], gy, S3);
+      S3 = fma(JT[t][8] - JS[8], gz, S3);
+      acc[t][0] = fma(w, S1, acc[t][0]);
+      acc[t][1] = fma(w, S2, acc[t][1]);
+      acc[t][2] = fma(w, S3, acc[t][2]);
+    }
+  }
+}
+
+
+struct SfsArgs {
+  const double *tpos;  // tpos[c*tld + 0..2]
+  int64_t tld;
+  const double *tJ;    // tJ[c*jld + 0..8]
+  int64_t jld;
+  const int64_t *tindex;  // nullable: target i -> column c
+  int64_t nt;
+  const double *rec;
+  int64_t ns;
+  int tiles_per_split;
+  double *partial;     // [nsplit][3][pstride]
+  int64_t pstride;
+  int transposed;
+  int shortcut;
+};
+
+template <int K, int T>
+__global__ void __launch_bounds__(kThreads) sfs_pairs_kernel(const SfsArgs a) {
+  __shared__ __align__(128) double tiles[kStages][kTile * kSfsRec];
+  __shared__ __align__(8) uint64_t full[kStages];
+
+  const int tid = threadIdx.x;
+  const int64_t tbase = (int64_t)blockIdx.x * (kThreads * T);
+
+  double tx[T], ty[T], tz[T], JT[T][9], acc[T][3];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    int64_t i = tbase + (int64_t)t * kThreads + tid;
+    if (i >= a.nt) i = a.nt - 1;
+    int64_t c = a.tindex ? a.tindex[i] : i;
+    const double *p = a.tpos + c * a.tld;
+    tx[t] = p[0]; ty[t] = p[1]; tz[t] = p[2];
+    const double *j = a.tJ + c * a.jld;
+    // same row-of-3 order as the source records (see prep_sfs_records)
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int m = 0; m < 3; ++m) JT[t][3 * k + m] = a.transposed ? j[3 * k + m] : j[k + 3 * m];
+    acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
+  }
+
+  const int64_t ntiles = (a.ns + kTile - 1) / kTile;
+  const int64_t tile0 = (int64_t)blockIdx.y * a.tiles_per_split;
+  int64_t tile1 = tile0 + a.tiles_per_split;
+  if (tile1 > ntiles) tile1 = ntiles;
+  const int ntl = tile1 > tile0 ? (int)(tile1 - tile0) : 0;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int it) {
+    int64_t first = (tile0 + it) * kTile;
+    int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
+    uint32_t bytes = (uint32_t)n * kSfsRec * sizeof(double);
+    int st = it % kStages;
+    mbar_expect_tx(&full[st], bytes);
+    tma_bulk_g2s(&tiles[st][0], a.rec + first * kSfsRec, bytes, &full[st]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kStages && s < ntl; ++s) issue(s);
+  }
+
+  for (int it = 0; it < ntl; ++it) {
+    const int st = it % kStages;
+    mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
+    const int64_t first = (tile0 + it) * kTile;
+    const int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
+    const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
+
+    sfs_tile<K, T>(tile, n, tx, ty, tz, JT, acc, a.shortcut);
+    __syncthreads();
+    if (tid == 0 && it + kStages < ntl) issue(it + kStages);
+  }
+
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    int64_t i = tbase + (int64_t)t * kThreads + tid;
+    if (i < a.nt) {
+      double *o = a.partial + (int64_t)blockIdx.y * 3 * a.pstride + i;
+      o[0] = acc[t][0];
+      o[a.pstride] = acc[t][1];
+      o[2 * a.pstride] = acc[t][2];
+    }
+  }
+}
+
+// out = (reset_sfs && !static ? 0 : out) + sum   for non-static targets;
+// static targets are not touched (src/FLOWVPM_subfilterscale_models.jl:63,80,
+// src/FLOWVPM_particlefield.jl:492-507).  filter_static = 0 in the leaf-list
+// form, which adds into every listed target.
+struct SfsFinishArgs {
+  const double *partial;
+  int64_t pstride;
+  int nsplit;
+  int64_t nt;
+  const int64_t *tindex;
+  double *out;
+  int64_t ld;
+  int row;
+  int accumulate, reset;
+  int filter_static;
+  const double *stat;
+  int64_t sld;
+};
+
+__global__ void sfs_finish_kernel(const SfsFinishArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nt) return;
+  int64_t c = a.tindex ? a.tindex[i] : i;
+  bool is_static = a.stat != nullptr && a.stat[c * a.sld] != 0.0;
+  if (is_static && a.filter_static) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int sp = 0; sp < a.nsplit; ++sp) {
+    const double *p = a.partial + (int64_t)sp * 3 * a.pstride + i;
+    s0 += p[0]; s1 += p[a.pstride]; s2 += p[2 * a.pstride];
+  }
+  double *o = a.out + c * a.ld + a.row;
+  bool keep = a.accumulate && !(a.reset && !is_static);
+  o[0] = (keep ? o[0] : 0.0) + s0;
+  o[1] = (keep ? o[1] : 0.0) + s1;
+  o[2] = (keep ? o[2] : 0.0) + s2;
+}
+
+// reset-only (reset_sfs without sfs): zero SFS rows of non-static particles
+__global__ void zero_rows_kernel(double *out, int64_t ld, int row, int nrows, int64_t n,
+                                 const double *stat, int64_t sld) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (stat != nullptr && stat[i * sld] != 0.0) return;
+  for (int k = 0; k < nrows; ++k) out[i * ld + row + k] = 0.0;
+}
+
+// ------------------------------------------------------------ instrumentation
+// DFMA roofline probe: 8 independent FMA chains per thread, no memory traffic.
+__global__ void dfma_peak_kernel(double *out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5,
+         a6 = seed + 6, a7 = seed + 7;
+  const double m = 0.999999, c = 1e-9;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
+}
+
+// element-wise precision conversion for the Matrix{Float32} entry point
+__global__ void cvt_f32_to_f64_kernel(const float *__restrict__ src, double *__restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)src[i];
+}
+__global__ void cvt_f64_to_f32_kernel(const double *__restrict__ src, float *__restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+
+__global__ void test_math_kernel(int op, int arg, const double *in, double *out, double *out2,
+                                 int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = in[i];
+  if (op == 0) {
+    out[i] = rsqrt_fp64(x);
+  } else if (op == 1) {
+    out[i] = exp_fp64(x);
+  } else if (op == 2) {
+    // (A, B) of the pair math at r2 = x with sigma = 1, returned as the
+    // reference's g = A r^3 and aux*r^3-free form B (tests rebuild the rest)
+    double A = 0, B = 0;
+    if (arg == K_WINCK) ab_winck(x, 1.0, 1.0, -3.0, A, B);
+    else if (arg == K_SING) ab_sing(x, A, B);
+    else if (arg == K_GERF) ab_gerf(x, 1.0, 1.0, A, B);
+    else ab_gaus(x, 1.0, 1.0, A, B);
+    out[i] = A;
+    if (out2) out2[i] = B;
+  } else if (op == 3) {
+    double w;
+    if (arg == K_WINCK) w = sfs_weight<K_WINCK>(x, 1.0, kConst4 * 7.5);
+    else if (arg == K_GERF) w = sfs_weight<K_GERF>(x, 1.0, kConst1);
+    else if (arg == K_GAUS) w = sfs_weight<K_GAUS>(x, 1.0, kConst3);
+    else w = sfs_weight<K_SING>(x, 1.0, 1.0);
+    out[i] = w;
+  }
+}
+
+}  // namespace vpm

@@ -1,0 +1,214 @@
+// vpm_leaf.cuh -- FMM near-field form of the two sweeps: the pair arithmetic of
+// vpm_kernels.cuh evaluated over a list of (target leaf, source leaf) pairs
+// (FastMultipole's direct_list; SURVEY 3.3, reference call shape
+// src/FLOWVPM_gpu.jl:637-643 and src/FLOWVPM_subfilterscale_models.jl:94-188).
+//
+// The list is regrouped by target leaf (CSR, list order kept inside a group) so
+// that one CTA owns up to kThreads targets of one leaf and walks all of that
+// leaf's source leaves: one owner per target, no atomics, and the per-target
+// summation order is the order of the pairs in the reference's list.
+#pragma once
+#include "vpm_kernels.cuh"
+
+namespace vpm {
+
+struct LeafCsr {
+  const int32_t *wi_leaf;      // work item -> target leaf
+  const int32_t *wi_off;       // work item -> offset of its first target inside the leaf
+  const int64_t *tleaf_begin;  // half-open sorted-body ranges of the target leaves
+  const int64_t *tleaf_end;
+  const int64_t *csr_ptr;      // [n_tgt_leaves + 1] into csr_src
+  const int32_t *csr_src;      // source leaves of each target leaf, list order
+  const int64_t *sleaf_begin;
+  const int64_t *sleaf_end;
+};
+
+// walks the source bodies of one target leaf tile by tile
+struct LeafTileIter {
+  int64_t li, le;    // position / end in csr_src
+  int64_t cur, end;  // remaining sorted-body range of the current source leaf
+  __device__ __forceinline__ void init(const LeafCsr &c, int leaf) {
+    li = c.csr_ptr[leaf];
+    le = c.csr_ptr[leaf + 1];
+    cur = end = 0;
+  }
+  // next tile [first, first+n); n == 0 when the list is exhausted
+  __device__ __forceinline__ int next(const LeafCsr &c, int64_t &first) {
+    while (cur >= end) {
+      if (li >= le) return 0;
+      int s = c.csr_src[li++];
+      cur = c.sleaf_begin[s];
+      end = c.sleaf_end[s];
+    }
+    first = cur;
+    int64_t n = end - cur;
+    if (n > kTile) n = kTile;
+    cur += n;
+    return (int)n;
+  }
+};
+
+struct LeafUjArgs {
+  LeafCsr csr;
+  const double *tpos;  // sorted target buffer: tpos[i*tld + 0..2]
+  int64_t tld;
+  const double *rec;   // U/J records of the sorted source buffer
+  double *out;         // sorted target buffer (same matrix as tpos), ld = tld
+  int urow, jrow;
+  int want_U, want_J;
+  int shortcut;
+};
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) uj_leaf_kernel(const LeafUjArgs a) {
+  __shared__ __align__(128) double tiles[kStages][kTile * kRec];
+  __shared__ __align__(8) uint64_t full[kStages];
+  const int tid = threadIdx.x;
+  const int leaf = a.csr.wi_leaf[blockIdx.x];
+  const int64_t tb = a.csr.tleaf_begin[leaf] + a.csr.wi_off[blockIdx.x];
+  int64_t te = a.csr.tleaf_end[leaf];
+  if (te > tb + kThreads) te = tb + kThreads;
+  const int64_t i = tb + tid;
+  const bool valid = i < te;
+  const double *p = a.tpos + (valid ? i : te - 1) * a.tld;
+  double tx[1] = {p[0]}, ty[1] = {p[1]}, tz[1] = {p[2]};
+  double acc[1][kAcc];
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[0][k] = 0.0;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  LeafTileIter prod, cons;
+  prod.init(a.csr, leaf);
+  cons.init(a.csr, leaf);
+  int issued = 0;
+  auto issue = [&]() {
+    int64_t first;
+    int n = prod.next(a.csr, first);
+    if (n == 0) return;
+    uint32_t bytes = (uint32_t)n * kRec * sizeof(double);
+    int st = issued % kStages;
+    mbar_expect_tx(&full[st], bytes);
+    tma_bulk_g2s(&tiles[st][0], a.rec + first * kRec, bytes, &full[st]);
+    ++issued;
+  };
+  if (tid == 0)
+    for (int s = 0; s < kStages; ++s) issue();
+
+  for (int it = 0;; ++it) {
+    int64_t first;
+    const int n = cons.next(a.csr, first);
+    if (n == 0) break;
+    const int st = it % kStages;
+    mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
+    uj_tile<K, 1>(reinterpret_cast<const double2 *>(&tiles[st][0]), n, tx, ty, tz, acc, a.shortcut);
+    __syncthreads();
+    if (tid == 0) issue();
+  }
+
+  if (valid) {
+    double *s = acc[0];
+    s[3 + 1] -= s[14];
+    s[3 + 2] += s[13];
+    s[3 + 3] += s[14];
+    s[3 + 5] -= s[12];
+    s[3 + 6] -= s[13];
+    s[3 + 7] += s[12];
+    double *o = a.out + i * a.tld;
+    if (a.want_U) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o[a.urow + k] += s[k];
+    }
+    if (a.want_J) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) o[a.jrow + k] += s[3 + k];
+    }
+  }
+}
+
+struct LeafSfsArgs {
+  LeafCsr csr;
+  const double *tpos;  // particle-indexed: tpos[c*tld + 0..2]
+  int64_t tld;
+  const double *tJ;    // tJ[c*jld + 0..8]
+  int64_t jld;
+  const int64_t *tindex;  // sorted target body -> particle column
+  const double *rec;   // SFS records in sorted source order
+  double *out;         // out[c*old + orow + 0..2] +=
+  int64_t old;
+  int orow;
+  int transposed;
+  int shortcut;
+};
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) sfs_leaf_kernel(const LeafSfsArgs a) {
+  __shared__ __align__(128) double tiles[kStages][kTile * kSfsRec];
+  __shared__ __align__(8) uint64_t full[kStages];
+  const int tid = threadIdx.x;
+  const int leaf = a.csr.wi_leaf[blockIdx.x];
+  const int64_t tb = a.csr.tleaf_begin[leaf] + a.csr.wi_off[blockIdx.x];
+  int64_t te = a.csr.tleaf_end[leaf];
+  if (te > tb + kThreads) te = tb + kThreads;
+  const int64_t i = tb + tid;
+  const bool valid = i < te;
+  const int64_t c = a.tindex[valid ? i : te - 1];
+  const double *p = a.tpos + c * a.tld;
+  double tx[1] = {p[0]}, ty[1] = {p[1]}, tz[1] = {p[2]};
+  double JT[1][9], acc[1][3] = {{0.0, 0.0, 0.0}};
+  const double *j = a.tJ + c * a.jld;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int m = 0; m < 3; ++m) JT[0][3 * k + m] = a.transposed ? j[3 * k + m] : j[k + 3 * m];
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  LeafTileIter prod, cons;
+  prod.init(a.csr, leaf);
+  cons.init(a.csr, leaf);
+  int issued = 0;
+  auto issue = [&]() {
+    int64_t first;
+    int n = prod.next(a.csr, first);
+    if (n == 0) return;
+    uint32_t bytes = (uint32_t)n * kSfsRec * sizeof(double);
+    int st = issued % kStages;
+    mbar_expect_tx(&full[st], bytes);
+    tma_bulk_g2s(&tiles[st][0], a.rec + first * kSfsRec, bytes, &full[st]);
+    ++issued;
+  };
+  if (tid == 0)
+    for (int s = 0; s < kStages; ++s) issue();
+
+  for (int it = 0;; ++it) {
+    int64_t first;
+    const int n = cons.next(a.csr, first);
+    if (n == 0) break;
+    const int st = it % kStages;
+    mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
+    sfs_tile<K, 1>(reinterpret_cast<const double2 *>(&tiles[st][0]), n, tx, ty, tz, JT, acc,
+                   a.shortcut);
+    __syncthreads();
+    if (tid == 0) issue();
+  }
+
+  if (valid) {
+    double *o = a.out + c * a.old + a.orow;
+    o[0] += acc[0][0];
+    o[1] += acc[0][1];
+    o[2] += acc[0][2];
+  }
+}
+
+}  // namespace vpm

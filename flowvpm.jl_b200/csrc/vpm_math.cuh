@@ -1,0 +1,85 @@
+// vpm_math.cuh -- FP64 device math for the pair loops (sm_100a).
+//
+// B200's SFU has no FP64 transcendentals: MUFU.RSQ64H / MUFU.RCP64H give a
+// ~20-bit seed from the high word of a double; everything else is FMA-pipe
+// work.  The routines here are the "accuracy-checked polynomials" of the design
+// (tests/test_device_math.py compares each with mpmath / libm on the GPU).
+#pragma once
+#include <cuda_runtime.h>
+#include "vpm_coeffs.cuh"
+
+namespace vpm {
+
+// constants as the reference computes them (src/FLOWVPM.jl:62-66)
+__device__ constexpr double kPi = 3.14159265358979323846;
+__device__ constexpr double kConst1 = 0.063493635934240969389;  // 1/(2*pi)^1.5
+__device__ constexpr double kConst2 = 0.79788456080286535588;   // sqrt(2/pi)
+__device__ constexpr double kConst3 = 0.23873241463784300365;   // 3/(4*pi)
+__device__ constexpr double kConst4 = 0.079577471545947667884;  // 1/(4*pi)
+__device__ constexpr double kInvSqrt2 = 0.70710678118654752440;
+
+// MUFU.RSQ64H seed: relative error <~ 2^-20 (uses the top 20 mantissa bits).
+__device__ __forceinline__ double rsqrt_seed(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  return y;
+}
+
+// 1/sqrt(a) for normal a > 0: seed + one third-order (Halley-type) step,
+// y = y0 (1 + e/2 + 3e^2/8), e = 1 - a y0^2; truncation 5e^3/16 < 3e-19.
+// 5 FP64-pipe instructions, ~1 ulp.  a == 0 -> +inf, a == +inf -> NaN-free 0
+// is NOT guaranteed: callers mask those lanes.
+__device__ __forceinline__ double rsqrt_fp64(double a) {
+  double y0 = rsqrt_seed(a);
+  double t = a * y0;
+  double e = fma(-t, y0, 1.0);
+  double p = fma(0.375, e, 0.5);
+  double q = y0 * e;
+  return fma(q, p, y0);
+}
+
+// exp(x) for -700 <= x <= 700 (callers clamp).  Cody-Waite reduction by
+// k = round(x log2 e) taken from the low word of x*log2e + 1.5*2^52, degree-11
+// near-minimax polynomial (tools/gen_coeffs.py, 1.6e-17), scaling by adding k to
+// the exponent field (integer pipe).  15 FP64-pipe instructions, < 1 ulp.
+__device__ __forceinline__ double exp_fp64(double x) {
+  const double kL2E = 1.4426950408889634074;
+  const double kShift = 6755399441055744.0;  // 1.5 * 2^52
+  const double kLn2Hi = 6.93147180369123816490e-01;
+  const double kLn2Lo = 1.90821492927058770002e-10;
+  double kd = fma(x, kL2E, kShift);
+  int k = __double2loint(kd);
+  kd -= kShift;
+  double r = fma(kd, -kLn2Hi, x);
+  r = fma(kd, -kLn2Lo, r);
+  double p = kExpPoly[11];
+  p = fma(p, r, kExpPoly[10]);
+  p = fma(p, r, kExpPoly[9]);
+  p = fma(p, r, kExpPoly[8]);
+  p = fma(p, r, kExpPoly[7]);
+  p = fma(p, r, kExpPoly[6]);
+  p = fma(p, r, kExpPoly[5]);
+  p = fma(p, r, kExpPoly[4]);
+  p = fma(p, r, kExpPoly[3]);
+  p = fma(p, r, kExpPoly[2]);
+  p = fma(p, r, kExpPoly[1]);
+  p = fma(p, r, kExpPoly[0]);
+  int hi = __double2hiint(p) + (k << 20);
+  return __hiloint2double(hi, __double2loint(p));
+}
+
+// exp(-x) for x >= 0 with the clamp the pair loops need (anything below
+// e^-700 is treated as e^-700 ~ 1e-304, i.e. zero at any tolerance).
+__device__ __forceinline__ double exp_neg_fp64(double x) { return exp_fp64(-fmin(x, 700.0)); }
+
+// r2 == +0 tested on the integer pipe (r2 is a sum of squares, never -0)
+__device__ __forceinline__ bool is_zero_bits(double r2) {
+  return (__double2hiint(r2) | __double2loint(r2)) == 0;
+}
+__device__ __forceinline__ double select_zero(bool z, double v) {
+  int hi = z ? 0 : __double2hiint(v);
+  int lo = z ? 0 : __double2loint(v);
+  return __hiloint2double(hi, lo);
+}
+
+}  // namespace vpm

@@ -1,0 +1,175 @@
+"""The UJ slot of the reference, backed by libvpm_cuda.so.
+
+Mirrors src/FLOWVPM_UJ.jl: `UJ_direct(pfield; rbf, sfs, reset, reset_sfs)`
+(:21-37), `UJ_direct(source, target)` (:48-50) and the near-field half of
+`UJ_fmm` (:62-129): FastMultipole's 6-argument `fmm.direct!` overload on
+buffers (src/FLOWVPM_fmm.jl:102-168), the `nearfield_device!` hook over a
+direct_list, and `Estr_fmm!` (src/FLOWVPM_subfilterscale_models.jl:94-188).
+Every function calls the C ABI; nothing here computes pair arithmetic.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from .particlefield import ParticleField, NFIELDS
+
+_default_handle = None
+
+
+def get_handle():
+    """Process-wide single-GPU handle (created on first use; raises without a GPU)."""
+    global _default_handle
+    if _default_handle is None:
+        _default_handle = _cabi.Handle(1)
+    return _default_handle
+
+
+def set_handle(handle):
+    global _default_handle
+    _default_handle = handle
+
+
+def _flags(pfield, sfs, reset, reset_sfs, no_shortcut=False):
+    f = 0
+    if reset:
+        f |= _cabi.FLAG_RESET
+    if reset_sfs:
+        f |= _cabi.FLAG_RESET_SFS
+    if sfs:
+        f |= _cabi.FLAG_SFS
+    if pfield.transposed:
+        f |= _cabi.FLAG_TRANSPOSED
+    if no_shortcut:
+        f |= _cabi.FLAG_NO_FARFIELD_SHORTCUT
+    return f
+
+
+def _check_matrix(P):
+    if not (isinstance(P, np.ndarray) and P.ndim == 2 and P.flags.f_contiguous):
+        raise ValueError("particles must be a Fortran-ordered 2-D array (Julia Matrix layout)")
+
+
+def UJ_direct(pfield, target=None, *, rbf=False, sfs=False, reset=True, reset_sfs=False,
+              handle=None, no_farfield_shortcut=False, **optargs):
+    """UJ_direct(pfield; rbf, sfs, reset=true, reset_sfs=false)  -- src/FLOWVPM_UJ.jl:21-37
+    UJ_direct(source, target)                                    -- src/FLOWVPM_UJ.jl:48-50
+
+    `rbf` is accepted and ignored, as in the reference."""
+    h = handle or get_handle()
+    if target is not None:
+        src = pfield
+        _check_matrix(src.particles)
+        _check_matrix(target.particles)
+        if src.particles.dtype != np.float64 or target.particles.dtype != np.float64:
+            raise TypeError("UJ_direct(source, target) is FP64 only")
+        h.check(h.lib.vpm_uj_direct_st(h.ptr, src.particles.ctypes.data, src.particles.shape[0],
+                                       src.np, target.particles.ctypes.data,
+                                       target.particles.shape[0], target.np, src.kernel.id))
+        return None
+    P = pfield.particles
+    _check_matrix(P)
+    flags = _flags(pfield, sfs, reset, reset_sfs, no_farfield_shortcut)
+    if P.dtype == np.float64:
+        fn = h.lib.vpm_uj_direct
+    elif P.dtype == np.float32:
+        fn = h.lib.vpm_uj_direct_f32
+    else:
+        raise TypeError(f"unsupported element type {P.dtype}")
+    h.check(fn(h.ptr, P.ctypes.data, P.shape[0], pfield.np, pfield.kernel.id, flags))
+    return None
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+# FastMultipole's target-buffer convention as used through its accessors:
+# position rows 1:3, scalar potential 4, gradient 5:7, hessian 8:16 (0-based below)
+ROW_POS, ROW_GRAD, ROW_HESS = 0, 4, 7
+
+
+def direct_buffers(target_buffer, target_index, source_buffer, source_index, kernel, *,
+                   want_U=True, want_J=True, row_pos=ROW_POS, row_grad=ROW_GRAD,
+                   row_hess=ROW_HESS, handle=None):
+    """fmm.direct!(target_buffer, target_index, switch, source_system, source_buffer,
+    source_index) -- src/FLOWVPM_fmm.jl:102-168.  Index arguments are half-open 0-based
+    (start, stop) ranges."""
+    h = handle or get_handle()
+    _check_matrix(target_buffer)
+    _check_matrix(source_buffer)
+    if source_buffer.shape[0] != 8:
+        raise ValueError("source buffer must have 8 rows [x y z rho Gx Gy Gz sigma]")
+    t0, t1 = target_index
+    s0, s1 = source_index
+    if t1 > target_buffer.shape[1] or s1 > source_buffer.shape[1]:
+        raise IndexError("index range outside the buffer")
+    h.check(h.lib.vpm_p2p_buffers(h.ptr, target_buffer.ctypes.data, target_buffer.shape[0], t0, t1,
+                                  row_pos, row_grad, row_hess, source_buffer.ctypes.data, s0, s1,
+                                  kernel.id, int(want_U), int(want_J)))
+
+
+def nearfield_device(target_buffer, target_leaves, source_buffer, source_leaves, direct_list,
+                     kernel, *, want_U=True, want_J=True, row_pos=ROW_POS, row_grad=ROW_GRAD,
+                     row_hess=ROW_HESS, handle=None):
+    """The FMM near field: nearfield_device!(...) reached from UJ_fmm when useGPU>0
+    (src/FLOWVPM_UJ.jl:97; shape src/FLOWVPM_gpu.jl:637-643).
+
+    target_leaves / source_leaves: (begin, end) int64 arrays of half-open body
+    ranges in the tree-sorted buffers; direct_list: (n_pairs, 2) leaf index pairs."""
+    h = handle or get_handle()
+    _check_matrix(target_buffer)
+    _check_matrix(source_buffer)
+    tb, te = _i64(target_leaves[0]), _i64(target_leaves[1])
+    sb, se = _i64(source_leaves[0]), _i64(source_leaves[1])
+    dl = np.asarray(direct_list)
+    pt, ps = _i32(dl[:, 0]), _i32(dl[:, 1])
+    h.check(h.lib.vpm_p2p_leafpairs(
+        h.ptr, target_buffer.ctypes.data, target_buffer.shape[0], target_buffer.shape[1],
+        row_pos, row_grad, row_hess, source_buffer.ctypes.data, source_buffer.shape[1],
+        tb.ctypes.data, te.ctypes.data, len(tb), sb.ctypes.data, se.ctypes.data, len(sb),
+        pt.ctypes.data, ps.ctypes.data, len(pt), kernel.id, int(want_U), int(want_J)))
+
+
+def Estr_fmm(pfield, target_sort_index, source_sort_index, target_leaves, source_leaves,
+             direct_list, *, handle=None, no_farfield_shortcut=False):
+    """Estr_fmm!(target_pfield, source_pfield, target_tree, source_tree, direct_list)
+    -- src/FLOWVPM_subfilterscale_models.jl:94-188 with target == source field."""
+    h = handle or get_handle()
+    P = pfield.particles
+    _check_matrix(P)
+    ts, ss = _i64(target_sort_index), _i64(source_sort_index)
+    if len(ts) != pfield.np or len(ss) != pfield.np:
+        raise ValueError("sort index length must equal pfield.np")
+    tb, te = _i64(target_leaves[0]), _i64(target_leaves[1])
+    sb, se = _i64(source_leaves[0]), _i64(source_leaves[1])
+    dl = np.asarray(direct_list)
+    pt, ps = _i32(dl[:, 0]), _i32(dl[:, 1])
+    flags = _flags(pfield, True, False, False, no_farfield_shortcut)
+    h.check(h.lib.vpm_estr_leafpairs(
+        h.ptr, P.ctypes.data, P.shape[0], pfield.np, ts.ctypes.data, ss.ctypes.data,
+        tb.ctypes.data, te.ctypes.data, len(tb), sb.ctypes.data, se.ctypes.data, len(sb),
+        pt.ctypes.data, ps.ctypes.data, len(pt), pfield.kernel.id, flags))
+
+
+def source_system_to_buffer(pfield):
+    """fmm.source_system_to_buffer! for every particle (src/FLOWVPM_fmm.jl:62-71) with the
+    default rho/sigma = 1 (autotune_reg_error off); returns the 8 x np buffer."""
+    P = pfield.live()
+    buf = np.zeros((8, pfield.np), dtype=np.float64, order="F")
+    buf[0:3] = P[0:3]
+    buf[3] = P[6]
+    buf[4:7] = P[3:6]
+    buf[7] = P[6]
+    return buf
+
+
+def buffer_to_target_system(pfield, target_buffer, *, row_grad=ROW_GRAD, row_hess=ROW_HESS):
+    """fmm.buffer_to_target_system! (src/FLOWVPM_fmm.jl:170-176): U += gradient, J += hessian"""
+    P = pfield.live()
+    P[9:12] += target_buffer[row_grad:row_grad + 3, : pfield.np]
+    P[15:24] += target_buffer[row_hess:row_hess + 9, : pfield.np]

@@ -1,0 +1,173 @@
+/*
+ * vpm_cuda.h -- C ABI of libvpm_cuda.so, the B200 (sm_100a) implementation of
+ * the rVPM particle-to-particle hot path of byuflowlab/FLOWVPM.jl v4.0.3.
+ *
+ * The entry points are what the reference's Julia host code binds through
+ * `ccall` (see INTEGRATION.md and flowvpm.jl_b200/julia/FLOWVPMCuda.jl).  Each
+ * one cites the reference interface (path:line under the FLOWVPM.jl tree) it
+ * replaces.  Plain pointers and sizes only; no C++ or torch types cross it.
+ *
+ * Conventions
+ *  - every function returns VPM_OK (0) or a negative VPM_E* code and never
+ *    throws or aborts; vpm_last_error() gives the message.
+ *  - matrices are column-major as Julia owns them; "particles" is the
+ *    ParticleField.particles matrix (nfields x maxparticles, nfields >= 43,
+ *    46 in v4.0.3: src/FLOWVPM_particlefield.jl:11,134) of which the first np
+ *    columns are live.  Row map (1-based, src/FLOWVPM_particlefield.jl:239-252):
+ *    X 1:3, Gamma 4:6, sigma 7, U 10:12, vorticity 13:15, J 16:24, PSE 25:27,
+ *    SFS 40:42, static 43.
+ *  - a handle is not re-entrant; calls block until results are in host memory
+ *    unless the function name says _device (then they are stream-ordered).
+ *  - there is no CPU fallback: without a usable CUDA device vpm_create fails.
+ */
+#ifndef VPM_CUDA_H
+#define VPM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPM_ABI_VERSION 1
+
+/* status codes */
+#define VPM_OK 0
+#define VPM_EINVAL (-1)  /* bad argument */
+#define VPM_ECUDA (-2)   /* CUDA runtime error (message has the CUDA string) */
+#define VPM_ENOMEM (-3)  /* device or host allocation failed */
+#define VPM_ENODEV (-4)  /* no usable CUDA device */
+#define VPM_ENCCL (-5)   /* NCCL error / NCCL not loadable */
+#define VPM_ESTATE (-6)  /* call sequence error (e.g. eval before upload) */
+
+/* kernel families: src/FLOWVPM.jl:129-133, src/FLOWVPM_kernel.jl:44-84 */
+#define VPM_KERNEL_SINGULAR 0
+#define VPM_KERNEL_GAUSSIAN 1
+#define VPM_KERNEL_GAUSSIANERF 2
+#define VPM_KERNEL_WINCKELMANS 3
+
+/* flags of the UJ call: keywords of UJ_direct, src/FLOWVPM_UJ.jl:21-25, and
+ * pfield.transposed, src/FLOWVPM_particlefield.jl:84,109 */
+#define VPM_FLAG_RESET 1       /* reset=true   : _reset_particles      */
+#define VPM_FLAG_RESET_SFS 2   /* reset_sfs    : _reset_particles_sfs  */
+#define VPM_FLAG_SFS 4         /* sfs=true     : Estr_direct! sweep    */
+#define VPM_FLAG_TRANSPOSED 8  /* pfield.transposed (default true)     */
+/* library-only switches (no reference counterpart) */
+#define VPM_FLAG_NO_FARFIELD_SHORTCUT 16 /* gaussian/gaussianerf: evaluate exp/erf for
+                                            every pair instead of g==1 beyond the cutoff */
+
+typedef struct vpm_handle vpm_handle;
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* n_gpus >= 1 devices driven by this one process (the Julia caller is a single
+ * process: src/FLOWVPM_utils.jl:87-133).  device_ids may be NULL (0..n-1).
+ * Replaces nothing in the reference (ParticleField(...; useGPU) only stores a
+ * flag, src/FLOWVPM_particlefield.jl:91,137). */
+int vpm_create(vpm_handle **out, int n_gpus, const int *device_ids);
+int vpm_destroy(vpm_handle *h);
+/* message of the last failing call on h (h == NULL: last vpm_create failure) */
+const char *vpm_last_error(const vpm_handle *h);
+int vpm_abi_version(void);
+int vpm_num_devices(const vpm_handle *h);
+
+/* ---- Hook 1: the UJ slot ---------------------------------------------- */
+/* UJ_direct(pfield; sfs, reset, reset_sfs): src/FLOWVPM_UJ.jl:21-37.
+ * Uploads rows X, Gamma, sigma (+ static, + previous U/J/SFS when they must be
+ * accumulated on), evaluates U, J (and SFS) on the GPU(s) and writes rows
+ * 10:27 (and 40:42) back in place with the reference's reset-then-accumulate
+ * semantics (src/FLOWVPM_particlefield.jl:464-511, src/FLOWVPM_fmm.jl:170-176). */
+int vpm_uj_direct(vpm_handle *h, double *particles, int64_t nfields, int64_t np,
+                  int kernel_id, int flags);
+/* same for a Matrix{Float32} field (ParticleField(n, Float32)); arithmetic in
+ * FP32 with FP64 tile sums, tolerance 1e-5 */
+int vpm_uj_direct_f32(vpm_handle *h, float *particles, int64_t nfields, int64_t np,
+                      int kernel_id, int flags);
+/* UJ_direct(source, target): src/FLOWVPM_UJ.jl:48-50 -- the field `source`
+ * induces U, J on every particle of `target` (accumulated, no reset, no SFS). */
+int vpm_uj_direct_st(vpm_handle *h, const double *source_particles, int64_t nfields_s,
+                     int64_t np_s, double *target_particles, int64_t nfields_t, int64_t np_t,
+                     int kernel_id);
+
+/* staged form of Hook 1 for device residency between RK stages */
+int vpm_upload_state(vpm_handle *h, const double *particles, int64_t nfields, int64_t np);
+int vpm_eval(vpm_handle *h, int kernel_id, int flags);
+int vpm_download_results(vpm_handle *h, double *particles, int64_t nfields, int64_t np,
+                         int flags);
+
+/* page-lock a host range the caller keeps alive (pfield.particles is allocated
+ * once at maxparticles: src/FLOWVPM_particlefield.jl:134), so the strided
+ * host<->device copies run at PCIe speed */
+int vpm_pin_host(vpm_handle *h, void *ptr, size_t bytes);
+int vpm_unpin_host(vpm_handle *h, void *ptr);
+
+/* ---- Hook 2: FastMultipole pair-loop overload --------------------------- */
+/* fmm.direct!(target_buffer, target_index, switch, source_system, source_buffer,
+ * source_index): src/FLOWVPM_fmm.jl:102-168.  target buffer: tgt_ld x (>= t1)
+ * with position at rows row_pos..+2, velocity accumulated into rows
+ * row_grad..+2 and J into rows row_hess..+8 (0-based row offsets; FastMultipole
+ * owns that layout, so they are arguments).  source buffer: 8 x (>= s1),
+ * [x y z rho Gx Gy Gz sigma] (src/FLOWVPM_fmm.jl:62-71).  Half-open 0-based
+ * ranges [t0,t1), [s0,s1).  want_U / want_J are the VS / GS switches. */
+int vpm_p2p_buffers(vpm_handle *h, double *tgt_buf, int64_t tgt_ld, int64_t t0, int64_t t1,
+                    int row_pos, int row_grad, int row_hess, const double *src_buf, int64_t s0,
+                    int64_t s1, int kernel_id, int want_U, int want_J);
+
+/* ---- Hook 3: FMM near-field device hook -------------------------------- */
+/* nearfield_device!(target_system, target_indices, switch, source_system,
+ * source_indices) as reached from UJ_fmm with useGPU>0: src/FLOWVPM_UJ.jl:97,
+ * call shape src/FLOWVPM_gpu.jl:637-643.  Buffers as in Hook 2, tree-sorted;
+ * leaves are half-open body ranges; pair k = (pair_tgt[k], pair_src[k]) is the
+ * direct_list.  Every listed pair is evaluated with fmm.direct!'s arithmetic. */
+int vpm_p2p_leafpairs(vpm_handle *h, double *tgt_buf, int64_t tgt_ld, int64_t n_tgt,
+                      int row_pos, int row_grad, int row_hess, const double *src_buf,
+                      int64_t n_src, const int64_t *tgt_leaf_begin, const int64_t *tgt_leaf_end,
+                      int64_t n_tgt_leaves, const int64_t *src_leaf_begin,
+                      const int64_t *src_leaf_end, int64_t n_src_leaves, const int32_t *pair_tgt,
+                      const int32_t *pair_src, int64_t n_pairs, int kernel_id, int want_U,
+                      int want_J);
+/* Estr_fmm!(pfield, pfield, target_tree, source_tree, direct_list):
+ * src/FLOWVPM_subfilterscale_models.jl:94-188.  sort_index maps sorted body ->
+ * particle column (0-based); no static filtering (as the reference). */
+int vpm_estr_leafpairs(vpm_handle *h, double *particles, int64_t nfields, int64_t np,
+                       const int64_t *tgt_sort_index, const int64_t *src_sort_index,
+                       const int64_t *tgt_leaf_begin, const int64_t *tgt_leaf_end,
+                       int64_t n_tgt_leaves, const int64_t *src_leaf_begin,
+                       const int64_t *src_leaf_end, int64_t n_src_leaves,
+                       const int32_t *pair_tgt, const int32_t *pair_src, int64_t n_pairs,
+                       int kernel_id, int flags);
+
+/* ---- device-pointer entry points (one process per GPU; the caller owns the
+ * collective, e.g. an NCCL all-gather of the 8 x N source buffer) ---------- */
+/* targets [t0,t1) of the same 8 x ns buffer; out12 is 12 x (t1-t0): U then J.
+ * All pointers are device memory on the handle's first device; `stream` is a
+ * cudaStream_t (NULL = the handle's own stream).  Overwrites out12. */
+int vpm_uj_device(vpm_handle *h, const double *d_src8, int64_t ns, int64_t t0, int64_t t1,
+                  double *d_out12, int kernel_id, int flags, void *stream);
+/* SFS sweep for targets [t0,t1): d_J9 is 9 x ns (final J of every particle),
+ * d_static ns flags (nonzero = static; NULL = none); out3 is 3 x (t1-t0). */
+int vpm_sfs_device(vpm_handle *h, const double *d_src8, const double *d_J9,
+                   const double *d_static, int64_t ns, int64_t t0, int64_t t1, double *d_out3,
+                   int kernel_id, int flags, void *stream);
+
+/* ---- instrumentation ---------------------------------------------------- */
+typedef struct vpm_timing {
+  double h2d_ms, prep_ms, uj_ms, sfs_ms, finish_ms, d2h_ms, total_ms; /* last call */
+  int64_t uj_pairs, sfs_pairs; /* ordered pairs visited by the two sweeps */
+  int32_t kernel_launches;     /* kernels of this library launched by the last call */
+  int32_t n_gpus;
+} vpm_timing;
+int vpm_get_timing(const vpm_handle *h, vpm_timing *out);
+
+/* FP64 FMA pipe peak of device 0, measured with a dependent-chain-free DFMA
+ * loop: the roofline denominator. */
+int vpm_measure_dfma_peak(vpm_handle *h, double *dfma_per_s, double *elapsed_ms);
+/* evaluate one device math routine on an array (accuracy tests):
+ * op 0 rsqrt, 1 exp, 2 (g, dg) of kernel `arg` at s, 3 zeta of kernel `arg` */
+int vpm_test_math(vpm_handle *h, int op, int arg, const double *in, double *out, double *out2,
+                  int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPM_CUDA_H */

@@ -1,0 +1,149 @@
+"""ctypes wrapper of oracle/libvpm_oracle.so (the C restatement of the reference).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/vpm_oracle.c for what is restated and how
+the oracle is pinned.  Builds the shared object on first use with oracle/Makefile.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvpm_oracle.so")
+
+KERNEL_IDS = {"singular": 0, "gaussian": 1, "gaussianerf": 2, "winckelmans": 3}
+FLAG_RESET, FLAG_RESET_SFS, FLAG_SFS, FLAG_TRANSPOSED = 1, 2, 4, 8
+
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(HERE, "vpm_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(src) > os.path.getmtime(LIB_PATH):
+        res = subprocess.run(["make", "-C", HERE, "-B", "libvpm_oracle.so"], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        p, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
+        L.vpm_oracle_erf64.argtypes = [dbl]
+        L.vpm_oracle_erf64.restype = dbl
+        L.vpm_oracle_g_dgdr.argtypes = [i32, dbl, C.POINTER(dbl), C.POINTER(dbl)]
+        L.vpm_oracle_g_dgdr.restype = None
+        L.vpm_oracle_zeta.argtypes = [i32, dbl]
+        L.vpm_oracle_zeta.restype = dbl
+        L.vpm_oracle_direct_buffers.argtypes = [p, i64, i64, i64, p, i64, i64, i32, i32, i32]
+        L.vpm_oracle_direct_buffers.restype = None
+        L.vpm_oracle_direct_buffers_mt.argtypes = [p, i64, i64, i64, p, i64, i64, i32, i32, i32, i32]
+        L.vpm_oracle_direct_buffers_mt.restype = None
+        L.vpm_oracle_reset_particles.argtypes = [p, i64, i64]
+        L.vpm_oracle_reset_particles_sfs.argtypes = [p, i64, i64]
+        L.vpm_oracle_estr_direct.argtypes = [p, i64, i64, i32, i32, i32]
+        L.vpm_oracle_estr_direct.restype = None
+        L.vpm_oracle_uj_direct.argtypes = [p, i64, i64, i32, i32, i32]
+        L.vpm_oracle_uj_direct.restype = i32
+        L.vpm_oracle_direct_leafpairs.argtypes = [p, i64, p, p, p, p, p, p, p, i64, i32, i32, i32]
+        L.vpm_oracle_direct_leafpairs.restype = None
+        L.vpm_oracle_estr_leafpairs.argtypes = [p, i64, p, p, p, p, p, p, p, p, i64, i32, i32]
+        L.vpm_oracle_estr_leafpairs.restype = None
+        L.vpm_oracle_max_threads.restype = i32
+        _lib = L
+    return _lib
+
+
+def _kid(kernel):
+    if isinstance(kernel, str):
+        return KERNEL_IDS[kernel]
+    return int(getattr(kernel, "id", kernel))
+
+
+def _f(P):
+    assert isinstance(P, np.ndarray) and P.dtype == np.float64 and P.flags.f_contiguous, \
+        "oracle works on Fortran-ordered float64 matrices"
+    return P
+
+
+def max_threads():
+    return int(lib().vpm_oracle_max_threads())
+
+
+def erf64(x):
+    return float(lib().vpm_oracle_erf64(float(x)))
+
+
+def g_dgdr(kernel, s):
+    g, dg = C.c_double(), C.c_double()
+    lib().vpm_oracle_g_dgdr(_kid(kernel), float(s), C.byref(g), C.byref(dg))
+    return g.value, dg.value
+
+
+def zeta(kernel, s):
+    return float(lib().vpm_oracle_zeta(_kid(kernel), float(s)))
+
+
+def flags(sfs=False, reset=True, reset_sfs=False, transposed=True):
+    return (FLAG_RESET * bool(reset)) | (FLAG_RESET_SFS * bool(reset_sfs)) | (FLAG_SFS * bool(sfs)) | \
+        (FLAG_TRANSPOSED * bool(transposed))
+
+
+def uj_direct(P, np_, kernel, *, sfs=False, reset=True, reset_sfs=False, transposed=True, nthreads=0):
+    """UJ_direct(pfield; sfs, reset, reset_sfs) on the 46 x N matrix P, in place."""
+    _f(P)
+    nthreads = nthreads or max_threads()
+    rc = lib().vpm_oracle_uj_direct(P.ctypes.data, P.shape[0], int(np_), _kid(kernel),
+                                    flags(sfs, reset, reset_sfs, transposed), int(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"oracle uj_direct failed ({rc})")
+
+
+def estr_direct(P, np_, kernel, transposed=True, nthreads=0):
+    _f(P)
+    lib().vpm_oracle_estr_direct(P.ctypes.data, P.shape[0], int(np_), _kid(kernel), int(transposed),
+                                 int(nthreads or max_threads()))
+
+
+def direct_buffers(tgt, t0, t1, src, s0, s1, kernel, want_U=True, want_J=True, nthreads=1):
+    """fmm.direct! on FastMultipole-style buffers (16-row target, 8-row source), in place."""
+    _f(tgt)
+    _f(src)
+    assert src.shape[0] == 8 and tgt.shape[0] >= 16
+    lib().vpm_oracle_direct_buffers_mt(tgt.ctypes.data, tgt.shape[0], int(t0), int(t1), src.ctypes.data,
+                                       int(s0), int(s1), _kid(kernel), int(want_U), int(want_J),
+                                       int(nthreads))
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def direct_leafpairs(tgt, src, tleaves, sleaves, direct_list, kernel, want_U=True, want_J=True):
+    _f(tgt)
+    _f(src)
+    tb, te, sb, se = _i64(tleaves[0]), _i64(tleaves[1]), _i64(sleaves[0]), _i64(sleaves[1])
+    dl = np.asarray(direct_list)
+    pt, ps = _i32(dl[:, 0]), _i32(dl[:, 1])
+    lib().vpm_oracle_direct_leafpairs(tgt.ctypes.data, tgt.shape[0], src.ctypes.data, tb.ctypes.data,
+                                      te.ctypes.data, sb.ctypes.data, se.ctypes.data, pt.ctypes.data,
+                                      ps.ctypes.data, len(pt), _kid(kernel), int(want_U), int(want_J))
+
+
+def estr_leafpairs(P, tsort, ssort, tleaves, sleaves, direct_list, kernel, transposed=True):
+    _f(P)
+    ts, ss = _i64(tsort), _i64(ssort)
+    tb, te, sb, se = _i64(tleaves[0]), _i64(tleaves[1]), _i64(sleaves[0]), _i64(sleaves[1])
+    dl = np.asarray(direct_list)
+    pt, ps = _i32(dl[:, 0]), _i32(dl[:, 1])
+    lib().vpm_oracle_estr_leafpairs(P.ctypes.data, P.shape[0], ts.ctypes.data, ss.ctypes.data,
+                                    tb.ctypes.data, te.ctypes.data, sb.ctypes.data, se.ctypes.data,
+                                    pt.ctypes.data, ps.ctypes.data, len(pt), _kid(kernel), int(transposed))

@@ -1,0 +1,416 @@
+/*
+ * vpm_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, FP64, no FMA contraction) of the arithmetic of
+ * byuflowlab/FLOWVPM.jl v4.0.3 on the particle-to-particle hot path.  It is
+ * the checker the CUDA path is compared with; only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The
+ * product (libvpm_cuda.so and the flowvpm.jl_b200 host layer) never does.
+ *
+ * PARITY PINNING: the reference ships no golden vectors for this path and
+ * Julia is not installable here, so the reference itself cannot be run.  The
+ * oracle is pinned by (i) the analytic two-particle known-answer formulas of
+ * the reference's scripts/check_fmm.jl:39-98, (ii) a 50-digit mpmath
+ * evaluation of the reference formulas (oracle/hp_oracle.py), (iii) the
+ * physics assertion of test/runtests_singlevortexring.jl:127-143.  Against
+ * reference-run outputs it is UNPINNED (see DESIGN.md "Oracle").
+ *
+ * Every function cites the reference file:line (relative to /root/reference)
+ * whose operation order it follows.  Build: oracle/Makefile
+ * (gcc -O2 -ffp-contract=off -fopenmp): Julia does not contract a*b+c into an
+ * FMA unless asked, so neither may the compiler here.
+ *
+ * Layouts (all column-major, as the Julia side owns them):
+ *   particle field  : nfields(=46) x np, rows per src/FLOWVPM_particlefield.jl:239-252
+ *                     (0-based here: X 0:3, Gamma 3:6, sigma 6, U 9:12, vort 12:15,
+ *                      J 15:24, PSE 24:27, SFS 39:42, static 42)
+ *   source buffer   : 8 x ns  [x y z rho Gx Gy Gz sigma]   src/FLOWVPM_fmm.jl:62-71
+ *   target buffer   : ld x nt, rows 0:3 position, 3 scalar potential,
+ *                     4:7 gradient (velocity), 7:16 hessian (J, column-major 3x3)
+ *                     -- FastMultipole's convention, reached in the reference only
+ *                     through get_position/set_gradient!/set_hessian!.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define VPM_KERNEL_SINGULAR 0
+#define VPM_KERNEL_GAUSSIAN 1
+#define VPM_KERNEL_GAUSSIANERF 2
+#define VPM_KERNEL_WINCKELMANS 3
+
+#define VPM_FLAG_RESET 1
+#define VPM_FLAG_RESET_SFS 2
+#define VPM_FLAG_SFS 4
+#define VPM_FLAG_TRANSPOSED 8
+
+/* rows of the particle matrix, 0-based (src/FLOWVPM_particlefield.jl:239-252) */
+enum { R_X = 0, R_G = 3, R_SIGMA = 6, R_U = 9, R_W = 12, R_J = 15, R_PSE = 24,
+       R_SFS = 39, R_STATIC = 42 };
+
+/* ---- constants as the reference computes them (src/FLOWVPM.jl:62-66) ---- */
+static double c_const1, c_const2, c_const3, c_const4, c_sqr2;
+static int c_init_done = 0;
+static void init_consts(void) {
+  if (c_init_done) return;
+  const double pi = 3.14159265358979323846; /* Julia's pi rounds to this double */
+  c_const1 = 1.0 / pow(2.0 * pi, 1.5);
+  c_const2 = sqrt(2.0 / pi);
+  c_const3 = 3.0 / (4.0 * pi);
+  c_const4 = 1.0 / (4.0 * pi);
+  c_sqr2 = sqrt(2.0);
+  c_init_done = 1;
+}
+
+/* ---- custom_erf64: src/FLOWVPM_gpu_erf.jl:159-191, coefficients :63-121 ---- */
+static const double erx = 8.45062911510467529297e-01;
+static const double pp0 = 1.28379167095512558561e-01, pp1 = -3.25042107247001499370e-01,
+                    pp2 = -2.84817495755985104766e-02, pp3 = -5.77027029648944159157e-03,
+                    pp4 = -2.37630166566501626084e-05;
+static const double qq1 = 3.97917223959155352819e-01, qq2 = 6.50222499887672944485e-02,
+                    qq3 = 5.08130628187576562776e-03, qq4 = 1.32494738004321644526e-04,
+                    qq5 = -3.96022827877536812320e-06;
+static const double pa0 = -2.36211856075265944077e-03, pa1 = 4.14856118683748331666e-01,
+                    pa2 = -3.72207876035701323847e-01, pa3 = 3.18346619901161753674e-01,
+                    pa4 = -1.10894694282396677476e-01, pa5 = 3.54783043256182359371e-02,
+                    pa6 = -2.16637559486879084300e-03;
+static const double qa1 = 1.06420880400844228286e-01, qa2 = 5.40397917702171048937e-01,
+                    qa3 = 7.18286544141962662868e-02, qa4 = 1.26171219808761642112e-01,
+                    qa5 = 1.36370839120290507362e-02, qa6 = 1.19844998467991074170e-02;
+static const double ra0 = -9.86494403484714822705e-03, ra1 = -6.93858572707181764372e-01,
+                    ra2 = -1.05586262253232909814e+01, ra3 = -6.23753324503260060396e+01,
+                    ra4 = -1.62396669462573470355e+02, ra5 = -1.84605092906711035994e+02,
+                    ra6 = -8.12874355063065934246e+01, ra7 = -9.81432934416914548592e+00;
+static const double sa1 = 1.96512716674392571292e+01, sa2 = 1.37657754143519042600e+02,
+                    sa3 = 4.34565877475229228821e+02, sa4 = 6.45387271733267880336e+02,
+                    sa5 = 4.29008140027567833386e+02, sa6 = 1.08635005541779435134e+02,
+                    sa7 = 6.57024977031928170135e+00, sa8 = -6.04244152148580987438e-02;
+static const double rb0 = -9.86494292470009928597e-03, rb1 = -7.99283237680523006574e-01,
+                    rb2 = -1.77579549177547519889e+01, rb3 = -1.60636384855821916062e+02,
+                    rb4 = -6.37566443368389627722e+02, rb5 = -1.02509513161107724954e+03,
+                    rb6 = -4.83519191608651397019e+02;
+static const double sb1 = 3.03380607434824582924e+01, sb2 = 3.25792512996573918826e+02,
+                    sb3 = 1.53672958608443695994e+03, sb4 = 3.19985821950859553908e+03,
+                    sb5 = 2.55305040643316442583e+03, sb6 = 4.74528541206955367215e+02,
+                    sb7 = -2.24409524465858183362e+01;
+
+static double jl_sign(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : x); }
+
+double vpm_oracle_erf64(double x) {
+  double xabs = fabs(x), sgn = jl_sign(x), val = sgn * 1.0;
+  if (xabs < 0.84375) { /* :166-170 */
+    double z = x * x;
+    double r = pp0 + z * (pp1 + z * (pp2 + z * (pp3 + z * pp4)));
+    double s = 1.0 + z * (qq1 + z * (qq2 + z * (qq3 + z * (qq4 + z * qq5))));
+    double y = r / s;
+    val = sgn * (xabs + xabs * y);
+  } else if (xabs < 1.25) { /* :171-175 */
+    double s = xabs - 1.0;
+    double P = pa0 + s * (pa1 + s * (pa2 + s * (pa3 + s * (pa4 + s * (pa5 + s * pa6)))));
+    double Q = 1.0 + s * (qa1 + s * (qa2 + s * (qa3 + s * (qa4 + s * (qa5 + s * qa6)))));
+    val = sgn * (erx + P / Q);
+  } else if (xabs < 2.857142857142857) { /* :176-181 */
+    double s = 1.0 / (x * x);
+    double R = ra0 + s * (ra1 + s * (ra2 + s * (ra3 + s * (ra4 + s * (ra5 + s * (ra6 + s * ra7))))));
+    double S = 1.0 + s * (sa1 + s * (sa2 + s * (sa3 + s * (sa4 + s * (sa5 + s * (sa6 + s * (sa7 + s * sa8)))))));
+    double r = exp(-x * x - 0.5625 + R / S);
+    val = sgn * (1.0 - r / xabs);
+  } else if (xabs < 6.0) { /* :182-187 */
+    double s = 1.0 / (x * x);
+    double R = rb0 + s * (rb1 + s * (rb2 + s * (rb3 + s * (rb4 + s * (rb5 + s * rb6)))));
+    double S = 1.0 + s * (sb1 + s * (sb2 + s * (sb3 + s * (sb4 + s * (sb5 + s * (sb6 + s * sb7))))));
+    double r = exp(-x * x - 0.5625 + R / S);
+    val = sgn * (1.0 - r / xabs);
+  }
+  return val;
+}
+
+/* ---- g_dgdr of the four families: src/FLOWVPM_kernel.jl:44-84 ---- */
+static inline void g_dgdr(int kernel, double r, double *g, double *dg) {
+  switch (kernel) {
+    case VPM_KERNEL_SINGULAR: /* :48 */
+      *g = 1.0; *dg = 0.0; break;
+    case VPM_KERNEL_GAUSSIANERF: { /* :54-57 */
+      double aux = c_const2 * r * exp(-r * r / 2);
+      *g = vpm_oracle_erf64(r / c_sqr2) - aux;
+      *dg = r * aux;
+    } break;
+    case VPM_KERNEL_GAUSSIAN: { /* :63-66 */
+      double aux = exp(-r * r * r);
+      *g = 1 - aux;
+      *dg = 3 * r * r * aux;
+    } break;
+    default: { /* winckelmans :77-84 */
+      double aux0 = r * r + 1;
+      double aux02 = aux0 * aux0;
+      aux0 = aux02 * aux02 * aux0;
+      aux0 = sqrt(aux0);
+      *g = r * r * r * (r * r + 2.5) / aux0;
+      *dg = 7.5 * r * r / (aux0 * (r * r + 1));
+    }
+  }
+}
+
+/* zeta: src/FLOWVPM_kernel.jl:45,51,60,69-74 */
+static inline double zeta_fn(int kernel, double r) {
+  switch (kernel) {
+    case VPM_KERNEL_SINGULAR: return r == 0.0 ? 1.0 : 0.0;
+    case VPM_KERNEL_GAUSSIANERF: return c_const1 * exp(-r * r / 2);
+    case VPM_KERNEL_GAUSSIAN: return c_const3 * exp(-r * r * r);
+    default: {
+      double temp = r * r + 1;
+      double temp2 = temp * temp * temp;
+      temp = temp2 * temp2 * temp;
+      return c_const4 * 7.5 / sqrt(temp);
+    }
+  }
+}
+
+void vpm_oracle_g_dgdr(int kernel, double r, double *g, double *dg) {
+  init_consts();
+  g_dgdr(kernel, r, g, dg);
+}
+double vpm_oracle_zeta(int kernel, double r) {
+  init_consts();
+  return zeta_fn(kernel, r);
+}
+
+/*
+ * The 6-argument fmm.direct! overload, src/FLOWVPM_fmm.jl:102-168: sources in
+ * the outer loop, targets in the inner loop, pair skipped iff r2 == 0, the
+ * setters accumulate.  Half-open 0-based ranges [t0,t1), [s0,s1).
+ */
+void vpm_oracle_direct_buffers(double *tgt, int64_t ld, int64_t t0, int64_t t1,
+                               const double *src, int64_t s0, int64_t s1,
+                               int kernel, int want_U, int want_J) {
+  init_consts();
+  for (int64_t is = s0; is < s1; ++is) {
+    const double *S = src + 8 * is;
+    const double gamma_x = S[4], gamma_y = S[5], gamma_z = S[6];
+    const double source_x = S[0], source_y = S[1], source_z = S[2];
+    const double sigma = S[7];
+    for (int64_t jt = t0; jt < t1; ++jt) {
+      double *T = tgt + ld * jt;
+      double dx = T[0] - source_x, dy = T[1] - source_y, dz = T[2] - source_z;
+      double r2 = dx * dx + dy * dy + dz * dz;
+      if (r2 != 0.0) {
+        double r = sqrt(r2);
+        double g_sgm, dg_sgmdr;
+        g_dgdr(kernel, r / sigma, &g_sgm, &dg_sgmdr);
+        double r3inv = 1.0 / (r2 * r);
+        double crss1 = -c_const4 * r3inv * (dy * gamma_z - dz * gamma_y);
+        double crss2 = -c_const4 * r3inv * (dz * gamma_x - dx * gamma_z);
+        double crss3 = -c_const4 * r3inv * (dx * gamma_y - dy * gamma_x);
+        if (want_U) {
+          T[4] += g_sgm * crss1;
+          T[5] += g_sgm * crss2;
+          T[6] += g_sgm * crss3;
+        }
+        if (want_J) {
+          double aux = dg_sgmdr / (sigma * r) - 3 * g_sgm / r2;
+          double aux2 = -c_const4 * g_sgm * r3inv;
+          T[7] += aux * crss1 * dx;
+          T[8] += aux * crss2 * dx - aux2 * gamma_z;
+          T[9] += aux * crss3 * dx + aux2 * gamma_y;
+          T[10] += aux * crss1 * dy + aux2 * gamma_z;
+          T[11] += aux * crss2 * dy;
+          T[12] += aux * crss3 * dy - aux2 * gamma_x;
+          T[13] += aux * crss1 * dz - aux2 * gamma_y;
+          T[14] += aux * crss2 * dz + aux2 * gamma_x;
+          T[15] += aux * crss3 * dz;
+        }
+      }
+    }
+  }
+}
+
+/*
+ * Threaded form: contiguous target blocks per thread, every block sees all
+ * sources in index order -- the per-target accumulation order is therefore the
+ * same as the serial loop (FastMultipole's threaded driver is not under
+ * /root/reference; the block split mirrors Estr_direct_multithreaded,
+ * src/FLOWVPM_subfilterscale_models.jl:51-59).
+ */
+void vpm_oracle_direct_buffers_mt(double *tgt, int64_t ld, int64_t t0, int64_t t1,
+                                  const double *src, int64_t s0, int64_t s1,
+                                  int kernel, int want_U, int want_J, int nthreads) {
+  if (nthreads <= 1 || t1 - t0 < 2) {
+    vpm_oracle_direct_buffers(tgt, ld, t0, t1, src, s0, s1, kernel, want_U, want_J);
+    return;
+  }
+  init_consts();
+  int64_t nt = t1 - t0;
+  /* blocks small enough that a block of targets stays in L1/L2 while sources stream */
+  int64_t blk = 256;
+  int64_t nblk = (nt + blk - 1) / blk;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (int64_t b = 0; b < nblk; ++b) {
+    int64_t a = t0 + b * blk, e = a + blk < t1 ? a + blk : t1;
+    vpm_oracle_direct_buffers(tgt, ld, a, e, src, s0, s1, kernel, want_U, want_J);
+  }
+}
+
+/* reset rules: src/FLOWVPM_particlefield.jl:464-511 */
+void vpm_oracle_reset_particles(double *P, int64_t nf, int64_t np) {
+  for (int64_t i = 0; i < np; ++i) {
+    double *p = P + nf * i;
+    if (p[R_STATIC] == 0.0) {
+      for (int k = 0; k < 3; ++k) p[R_U + k] = 0.0;
+      for (int k = 0; k < 3; ++k) p[R_W + k] = 0.0;
+      for (int k = 0; k < 9; ++k) p[R_J + k] = 0.0;
+      for (int k = 0; k < 3; ++k) p[R_PSE + k] = 0.0;
+    }
+  }
+}
+void vpm_oracle_reset_particles_sfs(double *P, int64_t nf, int64_t np) {
+  for (int64_t i = 0; i < np; ++i) {
+    double *p = P + nf * i;
+    if (p[R_STATIC] == 0.0)
+      for (int k = 0; k < 3; ++k) p[R_SFS + k] = 0.0;
+  }
+}
+
+/* Estr_direct pair term: src/FLOWVPM_subfilterscale_models.jl:16-41 */
+static inline void estr_pair(double *tp, const double *sp, double r, int kernel, int transposed) {
+  const double *GS = sp + R_G, *JS = sp + R_J, *JT = tp + R_J;
+  double S1, S2, S3;
+  if (transposed) {
+    S1 = (JT[0] - JS[0]) * GS[0] + (JT[1] - JS[1]) * GS[1] + (JT[2] - JS[2]) * GS[2];
+    S2 = (JT[3] - JS[3]) * GS[0] + (JT[4] - JS[4]) * GS[1] + (JT[5] - JS[5]) * GS[2];
+    S3 = (JT[6] - JS[6]) * GS[0] + (JT[7] - JS[7]) * GS[1] + (JT[8] - JS[8]) * GS[2];
+  } else {
+    S1 = (JT[0] - JS[0]) * GS[0] + (JT[3] - JS[3]) * GS[1] + (JT[6] - JS[6]) * GS[2];
+    S2 = (JT[1] - JS[1]) * GS[0] + (JT[4] - JS[4]) * GS[1] + (JT[7] - JS[7]) * GS[2];
+    S3 = (JT[2] - JS[2]) * GS[0] + (JT[5] - JS[5]) * GS[1] + (JT[8] - JS[8]) * GS[2];
+  }
+  double sigma_inv = 1.0 / sp[R_SIGMA];
+  double zeta_sgm = zeta_fn(kernel, r * sigma_inv) * sigma_inv * sigma_inv * sigma_inv;
+  tp[R_SFS + 0] += zeta_sgm * S1;
+  tp[R_SFS + 1] += zeta_sgm * S2;
+  tp[R_SFS + 2] += zeta_sgm * S3;
+}
+
+/*
+ * Estr_direct!: src/FLOWVPM_subfilterscale_models.jl:43-92.  Targets in the
+ * outer loop (static targets skipped, :63,80), sources = iterator(pfield) =
+ * non-static particles in index order (src/FLOWVPM_particlefield.jl:368-374).
+ */
+void vpm_oracle_estr_direct(double *P, int64_t nf, int64_t np, int kernel, int transposed,
+                            int nthreads) {
+  init_consts();
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int64_t it = 0; it < np; ++it) {
+    double *tp = P + nf * it;
+    if (tp[R_STATIC] != 0.0) continue;
+    double tx = tp[0], ty = tp[1], tz = tp[2];
+    for (int64_t is = 0; is < np; ++is) {
+      const double *sp = P + nf * is;
+      if (sp[R_STATIC] != 0.0) continue;
+      double dx = sp[0] - tx, dy = sp[1] - ty, dz = sp[2] - tz;
+      double r = sqrt(dx * dx + dy * dy + dz * dz);
+      estr_pair(tp, sp, r, kernel, transposed);
+    }
+  }
+}
+
+/*
+ * UJ_direct(pfield; sfs, reset, reset_sfs): src/FLOWVPM_UJ.jl:21-37, with the
+ * FastMultipole driver it calls restated from the callbacks it must use
+ * (source_system_to_buffer! src/FLOWVPM_fmm.jl:62-71, zeroed target buffer,
+ * direct! :102-168, buffer_to_target_system! :170-176).
+ */
+int vpm_oracle_uj_direct(double *P, int64_t nf, int64_t np, int kernel, int flags, int nthreads) {
+  init_consts();
+  if (nf < 43) return -1;
+  if (flags & VPM_FLAG_RESET) vpm_oracle_reset_particles(P, nf, np);
+  if (flags & VPM_FLAG_RESET_SFS) vpm_oracle_reset_particles_sfs(P, nf, np);
+  if (np > 0) {
+    double *src = (double *)malloc(sizeof(double) * 8 * np);
+    double *tgt = (double *)calloc(16 * np, sizeof(double));
+    if (!src || !tgt) { free(src); free(tgt); return -2; }
+    for (int64_t i = 0; i < np; ++i) {
+      const double *p = P + nf * i;
+      double *s = src + 8 * i;
+      s[0] = p[0]; s[1] = p[1]; s[2] = p[2];
+      s[3] = p[R_SIGMA]; /* rho: regularisation radius, unused by direct! */
+      s[4] = p[3]; s[5] = p[4]; s[6] = p[5];
+      s[7] = p[R_SIGMA];
+      double *t = tgt + 16 * i;
+      t[0] = p[0]; t[1] = p[1]; t[2] = p[2];
+    }
+    vpm_oracle_direct_buffers_mt(tgt, 16, 0, np, src, 0, np, kernel, 1, 1, nthreads);
+    for (int64_t i = 0; i < np; ++i) {
+      double *p = P + nf * i;
+      const double *t = tgt + 16 * i;
+      for (int k = 0; k < 3; ++k) p[R_U + k] += t[4 + k];
+      for (int k = 0; k < 9; ++k) p[R_J + k] += t[7 + k];
+    }
+    free(src);
+    free(tgt);
+  }
+  if (flags & VPM_FLAG_SFS)
+    vpm_oracle_estr_direct(P, nf, np, kernel, (flags & VPM_FLAG_TRANSPOSED) != 0, nthreads);
+  return 0;
+}
+
+/*
+ * FMM near field over a leaf-pair list ("direct_list"): for each
+ * (target leaf, source leaf) the 6-argument direct! on the tree-sorted buffers
+ * (call shape src/FLOWVPM_gpu.jl:637-643).  Leaves are half-open
+ * 0-based body ranges of the sorted buffers.  Pairs are visited in list order.
+ */
+void vpm_oracle_direct_leafpairs(double *tgt, int64_t ld, const double *src,
+                                 const int64_t *tleaf_begin, const int64_t *tleaf_end,
+                                 const int64_t *sleaf_begin, const int64_t *sleaf_end,
+                                 const int32_t *pair_t, const int32_t *pair_s, int64_t npairs,
+                                 int kernel, int want_U, int want_J) {
+  for (int64_t k = 0; k < npairs; ++k) {
+    int32_t a = pair_t[k], b = pair_s[k];
+    vpm_oracle_direct_buffers(tgt, ld, tleaf_begin[a], tleaf_end[a], src, sleaf_begin[b],
+                              sleaf_end[b], kernel, want_U, want_J);
+  }
+}
+
+/*
+ * Estr_fmm! over the same list: src/FLOWVPM_subfilterscale_models.jl:157-188
+ * (single-thread form; the threaded form :102-155 visits the same pairs).
+ * Sorted body index -> particle column through sort_index (0-based here),
+ * source-outer / target-inner, NO static filtering (:131-149).
+ */
+void vpm_oracle_estr_leafpairs(double *P, int64_t nf, const int64_t *tsort, const int64_t *ssort,
+                               const int64_t *tleaf_begin, const int64_t *tleaf_end,
+                               const int64_t *sleaf_begin, const int64_t *sleaf_end,
+                               const int32_t *pair_t, const int32_t *pair_s, int64_t npairs,
+                               int kernel, int transposed) {
+  init_consts();
+  for (int64_t k = 0; k < npairs; ++k) {
+    int32_t a = pair_t[k], b = pair_s[k];
+    for (int64_t is = sleaf_begin[b]; is < sleaf_end[b]; ++is) {
+      const double *sp = P + nf * ssort[is];
+      double sx = sp[0], sy = sp[1], sz = sp[2];
+      for (int64_t it = tleaf_begin[a]; it < tleaf_end[a]; ++it) {
+        double *tp = P + nf * tsort[it];
+        double dx = sx - tp[0], dy = sy - tp[1], dz = sz - tp[2];
+        double r = sqrt(dx * dx + dy * dy + dz * dz);
+        estr_pair(tp, sp, r, kernel, transposed);
+      }
+    }
+  }
+}
+
+/*
+ * Timing helper for bench.py's cpu_baseline / --impl reference legs: all ns
+ * sources against the target slice [t0,t1) on `nthreads` threads, returning
+ * nothing but the accumulated buffer (the caller times the call).
+ */
+int vpm_oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

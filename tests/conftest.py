@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def vpm():
+    from vpm_import import load
+    return load()
+
+
+@pytest.fixture(scope="session")
+def handle(vpm):
+    """one libvpm_cuda handle for the whole GPU session (fails loudly without a GPU)"""
+    h = vpm.get_handle()
+    yield h

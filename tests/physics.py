@@ -1,0 +1,91 @@
+"""TEST HARNESS ONLY: restatement of the reference's time integration for the
+physics regression of test/runtests_singlevortexring.jl rows 1-2 (Euler and RK3,
+cVPM = ReformulatedVPM(0,0), inviscid, no SFS, Pedrizzetti relaxation every step).
+
+  _euler                 src/FLOWVPM_timeintegration.jl:103-173
+  rungekutta3            src/FLOWVPM_timeintegration.jl:388-461
+  update_particle_states src/FLOWVPM_timeintegration.jl:463-534
+  relax_pedrizzetti      src/FLOWVPM_relaxation.jl:41-60
+  calc_rings_weighted!   examples/vortexrings/vortexrings_functions.jl:284-322
+
+The UJ evaluation is a callable `UJ(pfield, reset=True)` so the same driver runs
+on the oracle (CPU tests) and on libvpm_cuda (GPU tests)."""
+import numpy as np
+
+
+def _stretch(J, G, transposed):
+    if transposed:
+        return np.stack([J[3 * k] * G[0] + J[3 * k + 1] * G[1] + J[3 * k + 2] * G[2] for k in range(3)])
+    return np.stack([J[k] * G[0] + J[k + 3] * G[1] + J[k + 6] * G[2] for k in range(3)])
+
+
+def relax_pedrizzetti(P, n, rlxf=0.3):
+    J = P[15:24, :n]
+    G = P[3:6, :n]
+    w = np.stack([J[5] - J[7], J[6] - J[2], J[1] - J[3]])
+    nrmw = np.sqrt((w * w).sum(axis=0))
+    nrmG = np.sqrt((G * G).sum(axis=0))
+    ok = nrmw != 0
+    G[:, ok] = (1 - rlxf) * G[:, ok] + rlxf * nrmG[ok] * w[:, ok] / nrmw[ok]
+
+
+def euler_step(pf, dt, UJ, f=0.0, g=0.0, relax=True):
+    n = pf.np
+    P = pf.particles
+    UJ(pf, reset=True)
+    P[0:3, :n] += dt * P[9:12, :n]
+    G = P[3:6, :n]
+    S = _stretch(P[15:24, :n], G, pf.transposed)
+    Gn2 = (G * G).sum(axis=0)
+    Z = np.where(Gn2 > 0, (f + g) / (1 + 3 * f) * (S * G).sum(axis=0) / np.where(Gn2 > 0, Gn2, 1), 0.0)
+    sig = P[6, :n].copy()
+    G += dt * (S - 3 * Z * G)
+    P[6, :n] -= dt * sig * Z
+    if relax:
+        relax_pedrizzetti(P, n)
+
+
+def rk3_step(pf, dt, UJ, f=0.0, g=0.0, relax=True):
+    n = pf.np
+    P = pf.particles
+    M = P[27:36, :n]
+    M[:] = 0
+    for a, b in ((0.0, 1 / 3), (-5 / 9, 15 / 16), (-153 / 128, 8 / 15)):
+        UJ(pf, reset=True)
+        G = P[3:6, :n]
+        M[0:3] = a * M[0:3] + dt * P[9:12, :n]
+        P[0:3, :n] += b * M[0:3]
+        S = _stretch(P[15:24, :n], G, pf.transposed)
+        Gn2 = (G * G).sum(axis=0)
+        Z = np.where(Gn2 > 0, (f + g) / (1 + 3 * f) * (S * G).sum(axis=0) / np.where(Gn2 > 0, Gn2, 1), 0.0)
+        M[3:6] = a * M[3:6] + dt * (S - 3 * Z * G)
+        M[7] = a * M[7] - dt * (P[6, :n] * Z)
+        G += b * M[3:6]
+        P[6, :n] += b * M[7]
+    if relax:
+        UJ(pf, reset=True)
+        relax_pedrizzetti(P, n)
+
+
+def ring_centroid_weighted(pf):
+    n = pf.np
+    P = pf.particles
+    w = np.sqrt((P[3:6, :n] ** 2).sum(axis=0))
+    return (P[0:3, :n] * w).sum(axis=1) / w.sum()
+
+
+def run_single_ring(vpm, UJ, integration, nsteps=50, Nphi=100, nc=0, R=1.0, Rtot=2.0, beta=0.5, faux=0.25):
+    """test/runtests_singlevortexring.jl:40-143; returns (U_vpm, U_ana)."""
+    Rcross = 0.15 * R
+    sigma = Rcross
+    Uref = vpm.fields.Uring(1.0, R, Rcross, beta)
+    dt = (Rtot / Uref) / nsteps
+    pf = vpm.ParticleField(vpm.fields.number_particles(Nphi, nc), kernel=vpm.winckelmans, transposed=True)
+    vpm.fields.addvortexring(pf, 1.0, R, 1.0, faux * Rcross, Nphi, nc, sigma)
+    step = euler_step if integration == "euler" else rk3_step
+    t = 0.0
+    for _ in range(nsteps):
+        step(pf, dt, UJ)
+        t += dt
+    Zc = ring_centroid_weighted(pf)
+    return float(np.linalg.norm(Zc) / t), float(Uref)

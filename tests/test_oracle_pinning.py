@@ -1,0 +1,214 @@
+"""Pins the CPU oracle (oracle/vpm_oracle.c) -- the checker of every GPU parity test --
+against everything available without a Julia runtime:
+  * the analytic two-particle known answers of the reference's scripts/check_fmm.jl:39-98,
+  * the committed 50-digit mpmath golden vectors (tests/golden/p2p_golden.npz),
+  * fdlibm-accuracy of custom_erf64 (src/FLOWVPM_gpu_erf.jl:159-191) against libm,
+  * the reset / static / accumulate rules of src/FLOWVPM_particlefield.jl:464-511,
+  * the physics assertion of test/runtests_singlevortexring.jl:127-143 (ring speed, 2 %).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle, hp_oracle
+from helpers import KERNELS, relerr, TOL_FP64
+import physics
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "p2p_golden.npz"))
+
+
+def make_field(n=None):
+    n = n or GOLD["X"].shape[1]
+    P = np.zeros((46, n), order="F")
+    P[0:3] = GOLD["X"][:, :n]
+    P[3:6] = GOLD["Gamma"][:, :n]
+    P[6] = GOLD["sigma"][:n]
+    return P
+
+
+# ---------------------------------------------------------------- custom_erf64
+def test_erf64_matches_libm_to_2ulp():
+    xs = np.concatenate([np.linspace(-7, 7, 20001), [0.0, 0.84375, 1.25, 1 / 0.35, 6.0, -0.84375, 5.999999],
+                         np.nextafter([0.84375, 1.25, 2.857142857142857, 6.0], 0),
+                         10.0 ** np.linspace(-300, -1, 200)])
+    worst = 0.0
+    for x in xs:
+        a, b = oracle.erf64(x), math.erf(x)
+        ulp = np.spacing(abs(b)) if b != 0 else 5e-324
+        worst = max(worst, abs(a - b) / ulp)
+    assert worst <= 2.0, worst
+    assert oracle.erf64(6.0) == 1.0 and oracle.erf64(-6.0) == -1.0 and oracle.erf64(0.0) == 0.0
+
+
+def _tail_tol(v, eps):
+    v = abs(v)
+    return 1e-300 if v == 0 else eps * v * (1 + abs(math.log(v))) + 1e-300
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_g_dgdr_zeta_vs_mpmath(kernel):
+    for s in [1e-3, 0.01, 0.1, 0.3, 0.7, 1.0, 1.5, 2.5, 4.0, 6.0, 8.4, 8.6, 12.0, 40.0]:
+        g, dg = oracle.g_dgdr(kernel, s)
+        G, DG = hp_oracle.g_dgdr(kernel, s)
+        # absolute accuracy relative to the O(1) scale of g (the reference's own
+        # formulas cancel for small s, e.g. g = erf - aux)
+        assert abs(g - float(G)) <= 4e-16 * max(1.0, abs(float(G))) + 2e-16
+        assert abs(dg - float(DG)) <= _tail_tol(float(DG), 1e-15)
+        z, Z = oracle.zeta(kernel, s), float(hp_oracle.zeta(kernel, s))
+        # exp(-x) carries a relative error ~ |x| eps (argument rounding) in any FP64 evaluation
+        assert abs(z - Z) <= _tail_tol(Z, 2e-15)
+    assert oracle.zeta("singular", 0.0) == 1.0 and oracle.zeta("singular", 1e-300) == 0.0
+
+
+# ------------------------------------------- scripts/check_fmm.jl known answers
+BODIES = np.array([[0.4, 0.1], [0.1, -0.5], [-0.3, 0.2], [1 / 8, 1 / 8], [0.3, -0.4], [-0.1, -0.2],
+                   [0.08, 0.5]])  # scripts/check_fmm.jl:90-98: rows x y z sigma Gx Gy Gz
+
+
+def _u(xt, xs, gs):  # scripts/check_fmm.jl:39-47
+    dx = xt - xs
+    n = np.linalg.norm(dx)
+    return 1 / 4 / np.pi / n**3 * np.array([-dx[1] * gs[2] + dx[2] * gs[1], -dx[2] * gs[0] + dx[0] * gs[2],
+                                            -dx[0] * gs[1] + dx[1] * gs[0]])
+
+
+def _duidxj(xt, xs, gs):  # scripts/check_fmm.jl:57-71
+    x, y, z = xt - xs
+    xy, yz, xz = x * y, y * z, x * z
+    gx, gy, gz = gs
+    n = np.sqrt(x * x + y * y + z * z)
+    m = np.array([
+        [3 * xy * gz - 3 * xz * gy, (2 * y**2 - x**2 - z**2) * gz - 3 * yz * gy, 3 * yz * gz - (2 * z**2 - x**2 - y**2) * gy],
+        [3 * xz * gx - (2 * x**2 - y**2 - z**2) * gz, 3 * yz * gx - 3 * xy * gz, (2 * z**2 - x**2 - y**2) * gx - 3 * xz * gz],
+        [(2 * x**2 - y**2 - z**2) * gy - 3 * xy * gx, 3 * xy * gy - (2 * y**2 - x**2 - z**2) * gx, 3 * xz * gy - 3 * yz * gx]]) / n**5
+    return m / 4 / np.pi
+
+
+def _two_particle_field():
+    P = np.zeros((46, 2), order="F")
+    for i in range(2):
+        P[0:3, i] = BODIES[0:3, i]
+        P[6, i] = BODIES[3, i]
+        P[3:6, i] = BODIES[4:7, i]
+    return P
+
+
+def test_check_fmm_known_answers_singular():
+    P = _two_particle_field()
+    oracle.uj_direct(P, 2, "singular")
+    for t, s in ((0, 1), (1, 0)):
+        u = _u(BODIES[0:3, t], BODIES[0:3, s], BODIES[4:7, s])
+        Jm = _duidxj(BODIES[0:3, t], BODIES[0:3, s], BODIES[4:7, s])
+        assert relerr(P[9:12, t], u) < 1e-14
+        # reference J flat index i + 3 j = du_i/dx_j -> column-major of the 3x3
+        assert relerr(P[15:24, t].reshape(3, 3, order="F"), Jm) < 1e-14
+        # stretching (classic scheme) J * Gamma_target, scripts/check_fmm.jl:73-88
+        st = Jm @ BODIES[4:7, t]
+        Jo = P[15:24, t]
+        st_o = np.array([Jo[k] * BODIES[4, t] + Jo[k + 3] * BODIES[5, t] + Jo[k + 6] * BODIES[6, t] for k in range(3)])
+        assert relerr(st_o, st) < 1e-14
+
+
+@pytest.mark.parametrize("kernel", ["gaussian", "gaussianerf", "winckelmans"])
+def test_check_fmm_known_answers_regularised_far(kernel):
+    """r/sigma = 6.7 here: every regularised family is within its tail of the singular answer"""
+    P = _two_particle_field()
+    oracle.uj_direct(P, 2, kernel)
+    tail = {"gaussian": 1e-15, "gaussianerf": 1e-7, "winckelmans": 5e-3}[kernel]
+    for t, s in ((0, 1), (1, 0)):
+        u = _u(BODIES[0:3, t], BODIES[0:3, s], BODIES[4:7, s])
+        assert relerr(P[9:12, t], u) < tail + 1e-14
+
+
+# ------------------------------------------------------ mpmath golden vectors
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_oracle_uj_vs_golden(kernel):
+    P = make_field()
+    n = P.shape[1]
+    oracle.uj_direct(P, n, kernel, nthreads=1)
+    assert relerr(P[9:12], GOLD[f"U_{kernel}"]) < 1e-14
+    assert relerr(P[15:24], GOLD[f"J_{kernel}"]) < 1e-14
+    # threaded form gives bit-identical results (same per-target source order)
+    P2 = make_field()
+    oracle.uj_direct(P2, n, kernel, nthreads=4)
+    assert np.array_equal(P, P2)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("transposed", [True, False])
+def test_oracle_sfs_vs_golden(kernel, transposed):
+    P = make_field()
+    n = P.shape[1]
+    P[42] = GOLD["static"]
+    P[15:24] = GOLD["Jin"]
+    P[39:42] = 7.0  # must survive on static targets, be accumulated on elsewhere
+    oracle.estr_direct(P, n, kernel, transposed)
+    ref = GOLD[f"SFS_{kernel}_{'T' if transposed else 'C'}"]
+    st = GOLD["static"] != 0
+    assert np.all(P[39:42, st] == 7.0)
+    assert relerr(P[39:42, ~st] - 7.0, ref[:, ~st]) < 2e-13 if np.abs(ref).max() > 0 else True
+
+
+# ------------------------------------------------- reset / static / accumulate
+def test_reset_and_static_rules():
+    n = 12
+    P = make_field(n)
+    P[42, [2, 5]] = 1.0
+    rng = np.random.default_rng(0)
+    P[9:27] = rng.standard_normal((18, n))
+    P[39:42] = rng.standard_normal((3, n))
+    prior = P.copy(order="F")
+    fresh = make_field(n)
+    oracle.uj_direct(fresh, n, "winckelmans", sfs=False, reset=True)
+    # reset=True: non-static rows are zeroed then accumulated; static accumulate on the old values
+    oracle.uj_direct(P, n, "winckelmans", sfs=False, reset=True, reset_sfs=False)
+    st = prior[42, :n] != 0
+    assert np.allclose(P[9:12, ~st], fresh[9:12, ~st], rtol=0, atol=0)
+    assert np.all(P[12:15, ~st] == 0) and np.all(P[24:27, ~st] == 0)
+    assert np.allclose(P[9:12, st], prior[9:12, st] + fresh[9:12, st], rtol=1e-15)
+    assert np.array_equal(P[12:15, st], prior[12:15, st])
+    assert np.array_equal(P[39:42], prior[39:42])  # SFS untouched without sfs / reset_sfs
+    # reset=False: everything accumulates
+    P2 = prior.copy(order="F")
+    oracle.uj_direct(P2, n, "winckelmans", reset=False)
+    assert np.allclose(P2[15:24], prior[15:24] + fresh[15:24], rtol=1e-14)
+    # reset_sfs zeroes non-static SFS only
+    P3 = prior.copy(order="F")
+    oracle.uj_direct(P3, n, "winckelmans", reset=True, reset_sfs=True)
+    assert np.all(P3[39:42, ~st] == 0) and np.array_equal(P3[39:42, st], prior[39:42, st])
+
+
+def test_self_pair_and_coincident_particles_are_skipped():
+    P = np.zeros((46, 3), order="F")
+    P[0:3, 0] = P[0:3, 1] = [0.1, 0.2, 0.3]   # coincident pair: r2 == 0 -> skipped
+    P[0:3, 2] = [0.5, 0.2, 0.3]
+    P[3:6] = [[0.1, 0.2, 0.3], [0.0, -0.1, 0.2], [0.3, 0.0, 0.1]]
+    P[6] = 0.2
+    for k in KERNELS:
+        Q = P.copy(order="F")
+        oracle.uj_direct(Q, 3, k)
+        assert np.all(np.isfinite(Q))
+        # particles 0 and 1 see only particle 2, identically
+        assert np.array_equal(Q[9:12, 0], Q[9:12, 1]) and np.array_equal(Q[15:24, 0], Q[15:24, 1])
+
+
+def test_empty_field():
+    P = np.zeros((46, 4), order="F")
+    oracle.uj_direct(P, 0, "gaussianerf", sfs=True)
+    assert not P.any()
+
+
+# ---------------------------------------------- physics regression (reference test)
+class _VpmStub:
+    """the physics driver only needs the host mirror (no GPU): import lazily"""
+
+
+@pytest.mark.parametrize("integration", ["euler", "rk3"])
+def test_single_ring_speed_within_2_percent(integration, vpm):
+    def UJ(pf, reset=True):
+        oracle.uj_direct(pf.particles, pf.np, pf.kernel.name, reset=reset, transposed=pf.transposed)
+    U_vpm, U_ana = physics.run_single_ring(vpm, UJ, integration)
+    err = (U_vpm - U_ana) / U_ana
+    assert abs(err) < 0.02, (U_vpm, U_ana, err)  # test/runtests_singlevortexring.jl:143
