@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- particle interactions/s of the FP64 U/J sweep (UJ_direct) on B200.
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): a
+synthetic random vortex particle cloud (jittered lattice in a 1x1x7 box, recipe of the
+reference's scripts/benchmark_fmm2.jl:11-34), N = 2^20 particles by default, strong
+scaling over 1/2/4/8 GPUs: targets are block-sharded over ranks and every step starts
+with an all-gather (NCCL) of the 8 x N source buffer.
+
+One step = one U/J sweep of the whole field: N^2 ordered (source, target) interactions
+(SURVEY 8d).  `value` = N^2 / device time with particle state resident in HBM; `e2e`
+is the same sweep through the public host API with host buffers (H2D + D2H inside the
+timed region).  The SFS sweep and the other kernel families are measured after the
+timed region and reported in extra keys.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n PARTICLES] [--kernel NAME]
+  python bench.py --impl reference ...   # the CPU restatement of the reference on host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle interactions/sec (FP64 UJ_direct)"
+UNIT = "interactions/s"
+# algorithmic flops per U/J interaction: singular / gaussian / gaussianerf / winckelmans
+F_UJ = {"singular": 68, "gaussian": 75, "gaussianerf": 78, "winckelmans": 82}
+F_SFS = {"singular": 44, "gaussian": 48, "gaussianerf": 48, "winckelmans": 53}
+WORKLOAD = "C4 synthetic random vortex particle cloud (jittered lattice 1x1x7, scripts/benchmark_fmm2.jl recipe)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=1 << 20)
+    ap.add_argument("--kernel", default="winckelmans", choices=sorted(F_UJ))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip SFS / other-kernel / CPU extras")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------- clocks
+class ClockSampler:
+    """samples nvidia-smi SM clocks / throttle reasons while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------------- reference arm
+def cpu_sample(n, kernel, seconds, threads=None, repeats=1):
+    """The CPU restatement of the reference's UJ_direct pair loop (oracle port: Julia is not
+    available on this box) on all host cores: all n sources x a target slice sized to
+    about `seconds` of work.  Returns (interactions/s, description, cores)."""
+    from vpm_import import load
+    from oracle import oracle
+    vpm = load()
+    threads = threads or oracle.max_threads()
+    pf = vpm.fields.cloud_field(n, kernel=vpm.KERNELS[kernel])
+    sb = vpm.source_system_to_buffer(pf)
+
+    def run(nt):
+        tb = np.zeros((16, nt), order="F")
+        tb[0:3] = pf.get_X()[:, :nt]
+        t = time.perf_counter()
+        oracle.direct_buffers(tb, 0, nt, sb, 0, n, kernel, True, True, threads)
+        return time.perf_counter() - t
+
+    probe = min(n, 64 * threads)
+    dt = run(probe)
+    rate = probe * n / dt
+    nt = int(min(n, max(probe, seconds * rate / n // (32 * threads) * (32 * threads))))
+    best = None
+    for _ in range(repeats):
+        dt = run(nt)
+        best = dt if best is None else min(best, dt)
+    return nt * n / best, f"all {n} sources x first {nt} targets of the same cloud ({nt * n:.3g} interactions, {best:.1f} s)", threads
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    threads = oracle.max_threads()
+    times, inter = [], 0
+    per_step_seconds = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    desc = ""
+    for i in range(args.warmup + args.steps):
+        v, desc, _ = cpu_sample(args.n, args.kernel, per_step_seconds, threads)
+        if i >= args.warmup:
+            times.append(v)
+    value = float(np.mean(times))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": args.n * args.n / value * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_particles": args.n, "kernel": args.kernel,
+                   "note": "ms_per_step is the full N^2 sweep extrapolated from the bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": desc + "; reference-equivalent C restatement (oracle/), Julia not available"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ B200 arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from vpm_import import load
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libvpm_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    vpm = load()
+    from flowvpm_jl_b200 import sharding
+    h = vpm.Handle(device_ids=[local_rank])
+    vpm.set_handle(h)
+    lib = h.lib
+    n, kernel = args.n, vpm.KERNELS[args.kernel]
+    dev = torch.device("cuda", local_rank)
+
+    # ---- synthetic field (same seed on every rank), shard resident in HBM
+    pf = vpm.fields.cloud_field(n, kernel=kernel)
+    src8 = vpm.source_system_to_buffer(pf)  # 8 x n, the reference's source-buffer layout
+    t0, t1 = sharding.shard_bounds(n, world, rank)
+    host_local = torch.from_numpy(np.ascontiguousarray(src8[:, t0:t1].T)).pin_memory()
+    field = sharding.ShardedField(h, host_local.to(dev), n, rank, world, kernel.id)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed_steps(fn, k, w):
+        """W warm-ups, then K steps each bracketed by CUDA events on the launching stream,
+        L2 flushed between steps; returns (list of ms, list of pair-kernel ms)."""
+        for _ in range(w):
+            fn()
+        sync_all()
+        ms, kms = [], []
+        for _ in range(k):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ms.append(a.elapsed_time(b))
+            tm = h.timing()
+            kms.append(tm["uj_ms"] if tm["uj_ms"] > 0 else tm["sfs_ms"])
+        sync_all()
+        return ms, kms
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- roofline denominator: FP64 FMA pipe, measured on this GPU right now
+    dfma = np.zeros(1)
+    dms = np.zeros(1)
+    import ctypes as C
+    h.check(lib.vpm_measure_dfma_peak(h.ptr, dfma.ctypes.data_as(C.POINTER(C.c_double)),
+                                      dms.ctypes.data_as(C.POINTER(C.c_double))))
+    dfma_per_s = float(dfma[0])
+
+    # ---- timed region: K U/J sweeps, state resident
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    field.launches = 0
+    ms, kms = timed_steps(lambda: field.uj(0), args.steps, max(3, args.warmup))
+    clk = clocks.stop()
+    total_ms = reduce_max(float(np.sum(ms)))
+    ms_per_step = total_ms / args.steps
+    value = n * n / (ms_per_step * 1e-3)
+    launches = 3 * args.steps  # prep_uj_records + uj_pairs_kernel + uj_finish_kernel per step
+    kernel_ms = float(np.mean(kms))
+    my_pairs = (min(n, t1) - t0) * (world * field.c)
+    achieved_tflops = my_pairs / (kernel_ms * 1e-3) * F_UJ[args.kernel] / 1e12
+    peak_tflops = 2 * dfma_per_s / 1e12
+
+    # ---- e2e: the same sweep through the host API with host buffers
+    if world == 1:
+        P = pf.particles
+        h.check(lib.vpm_pin_host(h.ptr, P.ctypes.data, P.nbytes))
+
+        def e2e_step():
+            vpm.UJ_direct(pf, reset=True)
+        h2d, d2h = n * 7 * 8, n * 18 * 8
+    else:
+        host_out = torch.empty((field.c, 12), dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            field.src8_local[: t1 - t0].copy_(host_local, non_blocking=True)
+            field.uj(0)
+            host_out.copy_(field.out12, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h2d, d2h = (t1 - t0) * 8 * 8, field.c * 12 * 8
+    e2e_k = max(1, min(args.steps, 2))
+    e2e_step()
+    sync_all()
+    tw = time.perf_counter()
+    for _ in range(e2e_k):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = reduce_max((time.perf_counter() - tw) / e2e_k)
+    e2e_value = n * n / e2e_s
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_particles": n, "kernel": args.kernel,
+                   "parallelism": f"targets block-sharded over {world} GPU(s), all-gather of the 8xN source buffer per sweep",
+                   "l2": "flushed between timed steps (256 MiB write); per-step CUDA events, max over ranks",
+                   "interaction": "one ordered (source,target) pair visit of the U+J loop; N^2 per step"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_k, "api": "UJ_direct(pfield) -> vpm_uj_direct (pinned host matrix)" if world == 1
+                else "sharding.ShardedField.uj with pinned H2D/D2H of the local shard"},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "fp64_fma", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+                     "frac": achieved_tflops / peak_tflops, "traffic": None,
+                     "kernel": f"uj_pairs_kernel<{args.kernel}>", "kernel_ms": kernel_ms,
+                     "flop_per_interaction": F_UJ[args.kernel],
+                     "peak_source": "2 x DFMA/s measured live by vpm_measure_dfma_peak on this GPU "
+                                    "(MEASURED_PEAKS.json has no FP64 figure; theoretical 37.2 TFLOP/s at 1965 MHz)",
+                     "dfma_per_s": dfma_per_s,
+                     "note": "the path is FP64-FMA-pipe bound, not HBM or tensor bound (SURVEY 8d)"},
+    }
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = {}
+        # SFS sweep over the J just computed
+        sms, skms = timed_steps(lambda: field.sfs(vpm._cabi.FLAG_TRANSPOSED), 1, 1)
+        extras["sfs"] = {"interactions_per_s": n * n / (np.mean(sms) * 1e-3), "ms": float(np.mean(sms)),
+                         "kernel": args.kernel,
+                         "roofline_frac": n * n / (np.mean(skms) * 1e-3) * F_SFS[args.kernel] / 1e12 / peak_tflops}
+        by = {}
+        for name in sorted(F_UJ):
+            if name == args.kernel:
+                continue
+            field.kernel_id = vpm.KERNELS[name].id
+            m, km = timed_steps(lambda: field.uj(0), 1, 1)
+            by[name] = {"interactions_per_s": n * n / (np.mean(m) * 1e-3),
+                        "roofline_frac": n * n / (np.mean(km) * 1e-3) * F_UJ[name] / 1e12 / peak_tflops}
+            if name in ("gaussian", "gaussianerf"):
+                m2, km2 = timed_steps(lambda: field.uj(vpm._cabi.FLAG_NO_FARFIELD_SHORTCUT), 1, 0)
+                by[name]["no_farfield_shortcut_interactions_per_s"] = n * n / (np.mean(m2) * 1e-3)
+        field.kernel_id = kernel.id
+        extras["by_kernel"] = by
+        uj_ms = ms_per_step
+        extras["rvpm_step_ms_estimate"] = {"value": 5 * uj_ms + 4 * extras["sfs"]["ms"],
+                                           "what": "5 U/J + 4 SFS sweeps (RK3 + DynamicSFS + relaxation, SURVEY 3.1), O(N) host work excluded"}
+        line["extras"] = extras
+        v, desc, cores = cpu_sample(n, args.kernel, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": desc + "; reference-equivalent C restatement (oracle/), Julia not available"}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

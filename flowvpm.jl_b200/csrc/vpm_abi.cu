@@ -65,6 +65,7 @@ struct vpm_handle {
   size_t h_stat_cap = 0;
   std::vector<void *> pinned;
   int launches = 0;
+  int device_timing = 0;  // 1/2: ev[6..7] bracket the last _device U/J / SFS pair kernel
   // single-process multi-GPU (n_gpus > 1): NCCL communicators, one per device
   void *nccl_lib = nullptr;
   std::vector<void *> comms;
@@ -168,7 +169,8 @@ unsigned blocks_for(int64_t n, int threads) { return (unsigned)std::max<int64_t>
 // U/J sweep: records from `src` columns [s0, s0+ns), targets tpos[0..nt), partial
 // sums left in d.partial; the caller runs the finish kernel with its own output.
 int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *tpos, int64_t tld,
-             int64_t nt, SrcView src, int64_t s0, int64_t ns, int flags, Plan &plan) {
+             int64_t nt, SrcView src, int64_t s0, int64_t ns, int flags, Plan &plan,
+             bool time_pairs = false) {
   const int64_t ns_pad = round_up(std::max<int64_t>(ns, 1), kTile);
   TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
   plan = make_plan(nt, ns, d.sm_count);
@@ -183,7 +185,9 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
     a.tiles_per_split = plan.tiles_per_split;
     a.partial = (double *)d.partial.p; a.pstride = plan.pstride;
     a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
+    if (time_pairs) CK(h, cudaEventRecord(d.ev[6], st));
     launch_uj(kernel, plan, a, st);
+    if (time_pairs) CK(h, cudaEventRecord(d.ev[7], st));
     h->launches++;
   } else {
     plan.nsplit = 0;
@@ -195,7 +199,7 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
 int sfs_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *tpos, int64_t tld,
               const double *tJ, int64_t jld, const int64_t *tindex, int64_t nt, SrcView src,
               const double *sJ, int64_t sjld, int sjoff, const double *stat, int64_t sld,
-              const int64_t *sindex, int64_t ns, int flags, Plan &plan) {
+              const int64_t *sindex, int64_t ns, int flags, Plan &plan, bool time_pairs = false) {
   const int64_t ns_pad = round_up(std::max<int64_t>(ns, 1), kTile);
   TRY(ensure(h, d.srec, (size_t)ns_pad * kSfsRec * sizeof(double)));
   plan = make_plan(nt, ns, d.sm_count);
@@ -213,7 +217,9 @@ int sfs_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *
     a.partial = (double *)d.partial.p; a.pstride = plan.pstride;
     a.transposed = transposed;
     a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
+    if (time_pairs) CK(h, cudaEventRecord(d.ev[6], st));
     launch_sfs(kernel, plan, a, st);
+    if (time_pairs) CK(h, cudaEventRecord(d.ev[7], st));
     h->launches++;
   } else {
     plan.nsplit = 0;
@@ -340,6 +346,7 @@ int h1_download(vpm_handle *h, Dev &d, double *P, int64_t nf, int64_t np, int fl
 
 void h1_fill_timing(vpm_handle *h, Dev &d) {
   vpm_timing &t = h->timing;
+  h->device_timing = 0;
   t.h2d_ms = ev_ms(d.ev[0], d.ev[1]);
   t.uj_ms = ev_ms(d.ev[1], d.ev[2]);
   t.finish_ms = ev_ms(d.ev[2], d.ev[3]);
@@ -974,7 +981,8 @@ int vpm_uj_device(vpm_handle *h, const double *d_src8, int64_t ns, int64_t t0, i
   CK(h, cudaSetDevice(d.id));
   SrcView sv{d_src8, 8, 0, 4, 7};
   Plan plan;
-  TRY(uj_sweep(h, d, st, kernel, d_src8 + t0 * 8, 8, nt, sv, 0, ns, flags, plan));
+  TRY(uj_sweep(h, d, st, kernel, d_src8 + t0 * 8, 8, nt, sv, 0, ns, flags, plan, true));
+  h->device_timing = 1;
   UjFinishArgs f;
   f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
   f.nt = nt; f.out = d_out12; f.ld = 12; f.urow = 0; f.jrow = 3;
@@ -1004,7 +1012,8 @@ int vpm_sfs_device(vpm_handle *h, const double *d_src8, const double *d_J9, cons
   SrcView sv{d_src8, 8, 0, 4, 7};
   Plan plan;
   TRY(sfs_sweep(h, d, st, kernel, d_src8 + t0 * 8, 8, d_J9 + t0 * 9, 9, nullptr, nt, sv, d_J9, 9, 0,
-                d_static, 1, nullptr, ns, flags, plan));
+                d_static, 1, nullptr, ns, flags, plan, true));
+  h->device_timing = 2;
   SfsFinishArgs f;
   f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
   f.nt = nt; f.tindex = nullptr; f.out = d_out3; f.ld = 3; f.row = 0; f.accumulate = 0; f.reset = 0;
@@ -1151,6 +1160,15 @@ int vpm_estr_leafpairs(vpm_handle *h, double *P, int64_t nf, int64_t np, const i
 int vpm_get_timing(const vpm_handle *h, vpm_timing *out) {
   if (!h || !out) return VPM_EINVAL;
   *out = h->timing;
+  if (h->device_timing) {
+    // stream-ordered entry points: the pair kernel's own duration, valid once the
+    // caller has synchronised the stream it passed
+    const Dev &d = h->devs[0];
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, d.ev[6], d.ev[7]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+    if (h->device_timing == 1) out->uj_ms = ms; else out->sfs_ms = ms;
+    out->n_gpus = (int32_t)h->devs.size();
+  }
   return VPM_OK;
 }
 

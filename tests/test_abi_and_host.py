@@ -1,0 +1,126 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/vpm_cuda.h
+declares (no compute call -- there is no GPU here), the host mirror behaves like the
+reference's container API, and the product never routes through the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "vpm_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vpm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(vpm):
+    from vpm_import import load_build
+    lib_path = load_build().build()
+    lib = ctypes.CDLL(lib_path)
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/vpm_cuda.h but not exported"
+    assert sorted(vpm._cabi.SYMBOLS) == syms
+    assert lib.vpm_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure_not_fallback(vpm):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(vpm.VpmError) as e:
+        vpm.Handle(1)
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+    pf = vpm.fields.cloud_field(16)
+    vpm.set_handle(None)
+    with pytest.raises(vpm.VpmError):
+        vpm.UJ_direct(pf)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "flowvpm.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "fields.py", f"{f} mentions the oracle"
+    text = open(os.path.join(pkg, "fields.py")).read()
+    assert "import oracle" not in text and "from oracle" not in text
+
+
+def test_particlefield_container(vpm):
+    pf = vpm.ParticleField(4, kernel=vpm.winckelmans)
+    assert pf.particles.shape == (46, 4) and pf.particles.flags.f_contiguous
+    pf.add_particle([1, 2, 3], [4, 5, 6], 0.5, vol=0.1, circulation=-2.0, static=True)
+    pf.add_particle([0, 0, 0], [1, 0, 0], 0.2)
+    assert pf.get_np() == 2
+    col = pf.particles[:, 0]
+    assert list(col[0:7]) == [1, 2, 3, 4, 5, 6, 0.5] and col[7] == 0.1 and col[8] == 2.0 and col[42] == 1.0
+    # column stride equals Julia's Matrix{Float64}(46, n): 368 bytes per particle
+    assert pf.particles.strides == (8, 368)
+    pf.add_particle([9, 9, 9], [0, 0, 1], 0.3)
+    pf.remove_particle(0)          # swap-remove
+    assert pf.get_np() == 2 and list(pf.particles[0:3, 0]) == [9, 9, 9]
+    pf.add_particle([0, 0, 0], [1, 0, 0], 0.2)
+    pf.add_particle([0, 0, 0], [1, 0, 0], 0.2)
+    with pytest.raises(RuntimeError):
+        pf.add_particle([0, 0, 0], [1, 0, 0], 0.2)
+    assert vpm.kernel_default is vpm.gaussianerf and pf.UJ is vpm.UJ_direct
+
+
+def test_reset_container_functions(vpm):
+    pf = vpm.fields.cloud_field(20, static_fraction=0.3)
+    vpm.fields.random_results(pf)
+    before = pf.particles.copy(order="F")
+    st = pf.get_static()
+    assert st.any() and (~st).any()
+    vpm._reset_particles(pf)
+    assert np.all(pf.particles[9:27][:, :20][:, ~st] == 0)
+    assert np.array_equal(pf.particles[9:27][:, :20][:, st], before[9:27][:, :20][:, st])
+    assert np.array_equal(pf.particles[39:42], before[39:42])
+    vpm._reset_particles_sfs(pf)
+    assert np.all(pf.particles[39:42][:, :20][:, ~st] == 0)
+
+
+def test_field_generators(vpm):
+    assert vpm.fields.number_particles(100, 3) == 4900 and vpm.fields.number_particles(100, 0) == 100
+    pf = vpm.fields.ring_field(Nphi=100, nc=1)
+    assert pf.np == 900
+    # total vortex strength of a ring is tangential: sum Gamma = 0, circulation recovered
+    assert np.abs(pf.get_Gamma().sum(axis=1)).max() < 1e-12
+    G = np.linalg.norm(pf.get_Gamma(), axis=0).sum()
+    assert abs(G / (2 * np.pi * 1.0) - 1.0) < 2e-2
+    c = vpm.fields.cloud_field(1000)
+    X = c.get_X()
+    d = (7.0 / 1000) ** (1 / 3)
+    assert X.min() > -0.3 * d and X[2].max() < 7.5
+    # minimum separation of the jittered lattice: > 0.5 d
+    from scipy.spatial import cKDTree
+    dd, _ = cKDTree(X.T).query(X.T, k=2)
+    assert dd[:, 1].min() > 0.45 * d
+    assert abs(c.get_sigma().mean() / (0.65 * d) - 1) < 0.01
+
+
+def test_leaf_lists_cover_all_near_pairs(vpm):
+    c = vpm.fields.cloud_field(3000, seed=8)
+    ll = vpm.fields.build_leaf_lists(c.get_X(), c.get_sigma(), ncrit=40, theta=0.4)
+    b, e, dl = ll["leaf_begin"], ll["leaf_end"], ll["direct_list"]
+    assert b[0] == 0 and e[-1] == 3000 and np.all(b[1:] == e[:-1])
+    assert sorted(ll["sort_index"]) == list(range(3000))
+    s = set(map(tuple, dl))
+    assert all((i, i) in s for i in range(len(b)))       # self pairs are near field
+    assert all((j, i) in s for (i, j) in list(s)[:2000])  # MAC is symmetric
+
+
+def test_sharding_bounds(vpm):
+    from flowvpm_jl_b200 import sharding
+    for n, w in ((10, 4), (1 << 20, 8), (7, 8), (0, 2)):
+        segs = [sharding.shard_bounds(n, w, r) for r in range(w)]
+        assert segs[0][0] == 0 and segs[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+        assert all(t1 - t0 <= sharding.shard_size(n, w) for t0, t1 in segs)

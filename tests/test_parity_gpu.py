@@ -1,0 +1,299 @@
+"""GPU parity: libvpm_cuda (through the C ABI / host mirror) against the CPU oracle on the
+same seeded inputs, and against the committed mpmath golden vectors.
+
+Bar (BASELINE.json north_star): relative error <= 1e-12 in FP64 for U, J, stretching and
+SFS, measured norm-wise per field (helpers.relerr); <= 1e-5 for the Float32 entry point.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import KERNELS, TOL_FP64, TOL_FP32, assert_parity, relerr, stretching
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "p2p_golden.npz"))
+
+
+def oracle_uj(pf, **kw):
+    ref = pf.particles.copy(order="F")
+    oracle.uj_direct(ref, pf.np, pf.kernel.name, transposed=pf.transposed, **kw)
+    return ref
+
+
+# ------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_uj_vs_mpmath_golden(vpm, handle, kernel):
+    n = GOLD["X"].shape[1]
+    pf = vpm.ParticleField(n, kernel=vpm.KERNELS[kernel])
+    pf.particles[0:3] = GOLD["X"]
+    pf.particles[3:6] = GOLD["Gamma"]
+    pf.particles[6] = GOLD["sigma"]
+    pf.np = n
+    vpm.UJ_direct(pf)
+    assert relerr(pf.get_U(), GOLD[f"U_{kernel}"]) < TOL_FP64
+    assert relerr(pf.get_J(), GOLD[f"J_{kernel}"]) < TOL_FP64
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("transposed", [True, False])
+def test_sfs_vs_mpmath_golden(vpm, handle, kernel, transposed):
+    """Estr over a given J field: the device API takes J as an input, like the golden set-up"""
+    import torch
+    n = GOLD["X"].shape[1]
+    src8 = np.zeros((8, n), order="F")
+    src8[0:3], src8[4:7], src8[7] = GOLD["X"], GOLD["Gamma"], GOLD["sigma"]
+    src8[3] = GOLD["sigma"]
+    d_src = torch.from_numpy(np.ascontiguousarray(src8.T)).cuda()
+    d_J = torch.from_numpy(np.ascontiguousarray(GOLD["Jin"].T)).cuda()
+    d_stat = torch.from_numpy(GOLD["static"].copy()).cuda()
+    d_out = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+    flags = vpm._cabi.FLAG_SFS | (vpm._cabi.FLAG_TRANSPOSED if transposed else 0)
+    torch.cuda.synchronize()
+    handle.check(handle.lib.vpm_sfs_device(handle.ptr, d_src.data_ptr(), d_J.data_ptr(), d_stat.data_ptr(), n, 0, n,
+                                           d_out.data_ptr(), vpm.KERNELS[kernel].id, flags,
+                                           torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy().T
+    ref = GOLD[f"SFS_{kernel}_{'T' if transposed else 'C'}"]
+    st = GOLD["static"] != 0
+    if np.abs(ref).max() > 0:
+        assert relerr(out[:, ~st], ref[:, ~st]) < TOL_FP64
+    else:
+        assert np.abs(out[:, ~st]).max() == 0
+
+
+# ---------------------------------------------------- UJ_direct vs the oracle
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_uj_direct_ring_c1(vpm, handle, kernel):
+    """config C1: isolated vortex ring, Nphi=100, nc=3 -> 4900 particles"""
+    pf = vpm.fields.ring_field(Nphi=100, nc=3, kernel=vpm.KERNELS[kernel])
+    ref = oracle_uj(pf, sfs=True, reset=True, reset_sfs=True)
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    errs = assert_parity(pf.particles, ref, pf.np, what=f"ring/{kernel}")
+    assert relerr(stretching(pf.particles, pf.np), stretching(ref, pf.np)) < TOL_FP64
+    print(kernel, errs)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("n", [1, 2, 31, 129, 1000, 3001])
+def test_uj_direct_cloud_sizes(vpm, handle, kernel, n):
+    """ragged sizes around the tile (128) and CTA boundaries, down to a single particle"""
+    pf = vpm.fields.cloud_field(n, kernel=vpm.KERNELS[kernel], seed=100 + n)
+    ref = oracle_uj(pf, sfs=True, reset=True, reset_sfs=True)
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    assert_parity(pf.particles, ref, n, what=f"cloud{n}/{kernel}")
+
+
+@pytest.mark.parametrize("kernel", ["gaussianerf", "gaussian"])
+def test_farfield_shortcut_matches_full_evaluation(vpm, handle, kernel):
+    """g == 1 beyond the cutoff: with and without the shortcut agree to 1e-14, both in parity"""
+    pf = vpm.fields.cloud_field(6000, kernel=vpm.KERNELS[kernel], seed=5)
+    ref = oracle_uj(pf, sfs=True, reset=True, reset_sfs=True)
+    a = pf.particles.copy(order="F")
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    fast = pf.particles.copy(order="F")
+    pf.particles[:] = a
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True, no_farfield_shortcut=True)
+    assert_parity(fast, ref, pf.np)
+    assert_parity(pf.particles, ref, pf.np)
+    assert_parity(fast, pf.particles, pf.np, tol=1e-14)
+
+
+@pytest.mark.parametrize("kernel", ["winckelmans", "gaussianerf"])
+@pytest.mark.parametrize("reset,reset_sfs,sfs", [(True, False, False), (False, False, True), (True, True, False),
+                                                 (False, True, True), (False, False, False)])
+def test_reset_static_accumulate_rules(vpm, handle, kernel, reset, reset_sfs, sfs):
+    """static particles are targets of U/J but are never reset and take no part in SFS
+    (src/FLOWVPM_particlefield.jl:464-511, src/FLOWVPM_subfilterscale_models.jl:63)"""
+    pf = vpm.fields.cloud_field(1500, kernel=vpm.KERNELS[kernel], static_fraction=0.15, seed=9)
+    vpm.fields.random_results(pf, scale=1e-3)
+    ref = oracle_uj(pf, sfs=sfs, reset=reset, reset_sfs=reset_sfs)
+    vpm.UJ_direct(pf, sfs=sfs, reset=reset, reset_sfs=reset_sfs)
+    assert_parity(pf.particles, ref, pf.np, rows=("U", "J", "SFS", "W", "PSE"))
+    # rows the path must not touch
+    for rows in (slice(0, 9), slice(27, 39), slice(42, 46)):
+        assert np.array_equal(pf.particles[rows], ref[rows])
+
+
+def test_classic_scheme_sfs(vpm, handle):
+    pf = vpm.fields.ring_field(Nphi=40, nc=2, kernel=vpm.winckelmans, transposed=False)
+    ref = oracle_uj(pf, sfs=True, reset=True, reset_sfs=True)
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    assert_parity(pf.particles, ref, pf.np)
+
+
+def test_two_rings_c2_slice(vpm, handle):
+    """config C2 geometry (two coaxial rings, R=0.7906, Rcross=0.1R, dZ=0.7906), nc=3 here"""
+    R = 0.7906
+    pf = vpm.fields.ring_field(Nphi=100, nc=3, R=R, Rcross=0.1 * R, rings=2, dZ=0.7906, kernel=vpm.gaussianerf)
+    ref = oracle_uj(pf, sfs=True, reset=True, reset_sfs=True)
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    assert_parity(pf.particles, ref, pf.np)
+
+
+def test_jet_c3_with_static_inflow(vpm, handle):
+    pf = vpm.fields.jet_field(n_target=6000, kernel=vpm.gaussianerf)
+    assert pf.get_static().sum() > 0
+    ref = oracle_uj(pf, sfs=True, reset=True, reset_sfs=True)
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    assert_parity(pf.particles, ref, pf.np)
+
+
+def test_empty_and_coincident(vpm, handle):
+    pf = vpm.ParticleField(8, kernel=vpm.winckelmans)
+    vpm.UJ_direct(pf, sfs=True)  # np == 0: nothing to do, no error
+    assert not pf.particles.any()
+    for k in KERNELS:
+        pf = vpm.ParticleField(3, kernel=vpm.KERNELS[k])
+        pf.add_particle([0.1, 0.2, 0.3], [0.1, 0.2, 0.3], 0.2)
+        pf.add_particle([0.1, 0.2, 0.3], [0.0, -0.1, 0.2], 0.2)   # coincident: r2 == 0 -> skipped
+        pf.add_particle([0.5, 0.2, 0.3], [0.3, 0.0, 0.1], 0.2)
+        ref = oracle_uj(pf, sfs=True, reset=True, reset_sfs=True)
+        vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+        assert np.all(np.isfinite(pf.particles))
+        assert_parity(pf.particles, ref, 3, what=f"coincident/{k}")
+
+
+def test_run_to_run_bit_identical(vpm, handle):
+    pf = vpm.fields.cloud_field(5000, kernel=vpm.winckelmans)
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    a = pf.particles.copy(order="F")
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    assert np.array_equal(a, pf.particles)
+
+
+def test_uj_direct_source_target(vpm, handle):
+    """UJ_direct(source, target): probes accumulate U, J from another field"""
+    src = vpm.fields.cloud_field(2000, kernel=vpm.gaussianerf, seed=1)
+    tgt = vpm.fields.cloud_field(333, kernel=vpm.gaussianerf, seed=2)
+    vpm.fields.random_results(tgt, scale=1e-2)
+    sb = vpm.source_system_to_buffer(src)
+    tb = np.zeros((16, tgt.np), order="F")
+    tb[0:3] = tgt.get_X()
+    oracle.direct_buffers(tb, 0, tgt.np, sb, 0, src.np, "gaussianerf")
+    ref = tgt.particles.copy(order="F")
+    ref[9:12] += tb[4:7]
+    ref[15:24] += tb[7:16]
+    vpm.UJ_direct(src, tgt)
+    assert_parity(tgt.particles, ref, tgt.np, rows=("U", "J"))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_staged_api_device_residency(vpm, handle, kernel):
+    pf = vpm.fields.cloud_field(2500, kernel=vpm.KERNELS[kernel], static_fraction=0.1)
+    vpm.fields.random_results(pf, scale=1e-3)
+    ref = oracle_uj(pf, sfs=True, reset=True, reset_sfs=True)
+    P = pf.particles
+    lib = handle.lib
+    handle.check(lib.vpm_upload_state(handle.ptr, P.ctypes.data, P.shape[0], pf.np))
+    flags = 1 | 2 | 4 | 8
+    handle.check(lib.vpm_eval(handle.ptr, pf.kernel.id, flags))
+    handle.check(lib.vpm_download_results(handle.ptr, P.ctypes.data, P.shape[0], pf.np, flags))
+    assert_parity(P, ref, pf.np)
+    # second evaluation on the resident state: static particles accumulate again
+    oracle.uj_direct(ref, pf.np, kernel, sfs=True, reset=True, reset_sfs=True)
+    handle.check(lib.vpm_eval(handle.ptr, pf.kernel.id, flags))
+    handle.check(lib.vpm_download_results(handle.ptr, P.ctypes.data, P.shape[0], pf.np, flags))
+    assert_parity(P, ref, pf.np)
+
+
+def test_pinned_host_matrix(vpm, handle):
+    pf = vpm.fields.cloud_field(4000, kernel=vpm.winckelmans)
+    ref = oracle_uj(pf)
+    P = pf.particles
+    handle.check(handle.lib.vpm_pin_host(handle.ptr, P.ctypes.data, P.nbytes))
+    try:
+        vpm.UJ_direct(pf)
+    finally:
+        handle.check(handle.lib.vpm_unpin_host(handle.ptr, P.ctypes.data))
+    assert_parity(P, ref, pf.np, rows=("U", "J"))
+
+
+# ------------------------------------------------- Float32 entry point (1e-5)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_uj_direct_f32(vpm, handle, kernel):
+    pf64 = vpm.fields.cloud_field(3000, kernel=vpm.KERNELS[kernel], static_fraction=0.1, seed=4)
+    pf32 = vpm.fields.cloud_field(3000, kernel=vpm.KERNELS[kernel], static_fraction=0.1, seed=4, R=np.float32)
+    # the oracle sees the same (float32-rounded) inputs
+    pf64.particles[:] = pf32.particles.astype(np.float64)
+    ref = oracle_uj(pf64, sfs=True, reset=True, reset_sfs=True)
+    vpm.UJ_direct(pf32, sfs=True, reset=True, reset_sfs=True)
+    assert pf32.particles.dtype == np.float32
+    assert_parity(pf32.particles, ref, pf32.np, tol=TOL_FP32)
+
+
+# ------------------------------------------------ Hook 2: fmm.direct! buffers
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("want_U,want_J", [(True, True), (True, False), (False, True)])
+def test_direct_buffers_ranges(vpm, handle, kernel, want_U, want_J):
+    src = vpm.fields.cloud_field(1200, kernel=vpm.KERNELS[kernel], seed=11)
+    sb = vpm.source_system_to_buffer(src)
+    rng = np.random.default_rng(3)
+    tb = np.asfortranarray(rng.standard_normal((16, 700)) * 1e-3)
+    tb[0:3] = src.get_X()[:, :700] + 0.003
+    ref = tb.copy(order="F")
+    oracle.direct_buffers(ref, 100, 650, sb, 37, 1111, kernel, want_U, want_J)
+    vpm.direct_buffers(tb, (100, 650), sb, (37, 1111), vpm.KERNELS[kernel], want_U=want_U, want_J=want_J)
+    assert relerr(tb[4:7], ref[4:7]) < TOL_FP64 and relerr(tb[7:16], ref[7:16]) < TOL_FP64
+    assert np.array_equal(tb[:, :100], ref[:, :100]) and np.array_equal(tb[:, 650:], ref[:, 650:])
+    assert np.array_equal(tb[0:4], ref[0:4])
+
+
+# ---------------------------------------- Hook 3: FMM near field over leaf pairs
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("ncrit", [16, 200])
+def test_nearfield_leafpairs(vpm, handle, kernel, ncrit):
+    pf = vpm.fields.cloud_field(5000, kernel=vpm.KERNELS[kernel], seed=21)
+    ll = vpm.fields.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=ncrit, theta=0.4)
+    order = ll["sort_index"]
+    sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
+    tb = np.zeros((16, pf.np), order="F")
+    tb[0:3] = pf.get_X()[:, order]
+    leaves = (ll["leaf_begin"], ll["leaf_end"])
+    ref = tb.copy(order="F")
+    oracle.direct_leafpairs(ref, sb, leaves, leaves, ll["direct_list"], kernel)
+    vpm.nearfield_device(tb, leaves, sb, leaves, ll["direct_list"], vpm.KERNELS[kernel])
+    assert relerr(tb[4:7], ref[4:7]) < TOL_FP64 and relerr(tb[7:16], ref[7:16]) < TOL_FP64
+    # SFS over the same list (Estr_fmm!): J taken from the near-field result
+    pf.particles[15:24, order] = ref[7:16]
+    pf.particles[42, ::7] = 1.0  # static flags are NOT filtered in the list form
+    refP = pf.particles.copy(order="F")
+    oracle.estr_leafpairs(refP, order, order, leaves, leaves, ll["direct_list"], kernel, True)
+    vpm.Estr_fmm(pf, order, order, leaves, leaves, ll["direct_list"])
+    assert relerr(pf.particles[39:42], refP[39:42]) < TOL_FP64
+
+
+def test_leafpairs_unsorted_list_and_empty_leaves(vpm, handle):
+    pf = vpm.fields.cloud_field(900, kernel=vpm.winckelmans, seed=2)
+    ll = vpm.fields.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=32)
+    order = ll["sort_index"]
+    rng = np.random.default_rng(0)
+    dl = ll["direct_list"][rng.permutation(len(ll["direct_list"]))]
+    # add an empty leaf referenced by the list
+    lb = np.append(ll["leaf_begin"], 900)
+    le = np.append(ll["leaf_end"], 900)
+    dl = np.vstack([dl, [[len(lb) - 1, 0], [0, len(lb) - 1]]]).astype(np.int32)
+    sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
+    tb = np.zeros((16, pf.np), order="F")
+    tb[0:3] = pf.get_X()[:, order]
+    ref = tb.copy(order="F")
+    oracle.direct_leafpairs(ref, sb, (lb, le), (lb, le), dl, "winckelmans")
+    vpm.nearfield_device(tb, (lb, le), sb, (lb, le), dl, vpm.winckelmans)
+    assert relerr(tb[4:7], ref[4:7]) < TOL_FP64 and relerr(tb[7:16], ref[7:16]) < TOL_FP64
+
+
+# ------------------------------------------------------------ error behaviour
+def test_errors_are_codes_with_messages(vpm, handle):
+    pf = vpm.fields.cloud_field(10)
+    P = pf.particles
+    rc = handle.lib.vpm_uj_direct(handle.ptr, P.ctypes.data, 46, 10, 99, 1)
+    assert rc == -1 and b"kernel_id" in handle.lib.vpm_last_error(handle.ptr)
+    rc = handle.lib.vpm_uj_direct(handle.ptr, P.ctypes.data, 12, 10, 3, 1)
+    assert rc == -1
+    rc = handle.lib.vpm_eval(handle.ptr, 3, 1)
+    assert rc in (-6, 0)  # ESTATE unless a previous test left state resident
+    with pytest.raises(vpm.VpmError):
+        vpm.Handle(device_ids=[10_000])
