@@ -976,7 +976,7 @@ int vpm_uj_device(vpm_handle *h, const double *d_src8, int64_t ns, int64_t t0, i
   if (nt == 0) return VPM_OK;
   if (!d_src8 || !d_out12) return fail(h, VPM_EINVAL, "vpm_uj_device: NULL device pointer");
   Dev &d = h->devs[0];
-  cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+  cudaStream_t st = (cudaStream_t)stream;  // as given: NULL is CUDA's default stream
   h->launches = 0;
   CK(h, cudaSetDevice(d.id));
   SrcView sv{d_src8, 8, 0, 4, 7};
@@ -1006,7 +1006,7 @@ int vpm_sfs_device(vpm_handle *h, const double *d_src8, const double *d_J9, cons
   if (nt == 0) return VPM_OK;
   if (!d_src8 || !d_J9 || !d_out3) return fail(h, VPM_EINVAL, "vpm_sfs_device: NULL device pointer");
   Dev &d = h->devs[0];
-  cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+  cudaStream_t st = (cudaStream_t)stream;  // as given: NULL is CUDA's default stream
   h->launches = 0;
   CK(h, cudaSetDevice(d.id));
   SrcView sv{d_src8, 8, 0, 4, 7};

@@ -141,7 +141,8 @@ int vpm_estr_leafpairs(vpm_handle *h, double *particles, int64_t nfields, int64_
  * collective, e.g. an NCCL all-gather of the 8 x N source buffer) ---------- */
 /* targets [t0,t1) of the same 8 x ns buffer; out12 is 12 x (t1-t0): U then J.
  * All pointers are device memory on the handle's first device; `stream` is a
- * cudaStream_t (NULL = the handle's own stream).  Overwrites out12. */
+ * cudaStream_t used as given (NULL = CUDA's default stream, e.g. torch's current
+ * stream handle 0).  Overwrites out12. */
 int vpm_uj_device(vpm_handle *h, const double *d_src8, int64_t ns, int64_t t0, int64_t t1,
                   double *d_out12, int kernel_id, int flags, void *stream);
 /* SFS sweep for targets [t0,t1): d_J9 is 9 x ns (final J of every particle),
