@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -46,6 +47,7 @@ struct Dev {
 
 struct Plan {
   int T = 1;
+  int unroll = 2;
   int nsplit = 1;
   int tiles_per_split = 1;
   int64_t pstride = 0;
@@ -119,17 +121,27 @@ int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 bool valid_kernel(int k) { return k >= 0 && k <= 3; }
 
-// Launch plan: enough CTAs to fill the machine several times over; when the
-// target count alone cannot do that the sources are split and each split's
-// partial sums are combined (in order) by the finish kernel.
-Plan make_plan(int64_t nt, int64_t ns, int sm_count, int force_T = 0) {
+// Launch plan.  One CTA = kThreads * T targets x one contiguous range of source tiles.
+// The grid is sized to ~16 waves of resident CTAs so that the tail of the last wave is a
+// few percent at most; when the target count alone cannot provide that, the sources are
+// split (>= 4 tiles per split) and the finish kernel adds the splits in order.
+enum PlanKind { PLAN_UJ = 0, PLAN_SFS = 1 };
+Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind) {
   Plan p;
   const int64_t ntiles = std::max<int64_t>(1, (ns + kTile - 1) / kTile);
-  p.T = force_T ? force_T : (nt >= (int64_t)sm_count * kThreads * 2 * 6 ? 2 : 1);
+  p.T = nt >= 4096 ? 2 : 1;
+  p.unroll = p.T == 2 ? 1 : 2;
+  if (const char *v = getenv(kind == PLAN_UJ ? "VPM_UJ_VARIANT" : "VPM_SFS_VARIANT")) {
+    int x = atoi(v);  // tuning aid: "<T><unroll>", e.g. 12, 21, 22
+    if (x / 10 >= 1 && x / 10 <= 4) { p.T = x / 10; p.unroll = x % 10; }
+  }
+  if (kind == PLAN_SFS && p.T > 2) p.T = 2;
+  const int ctas_per_sm = p.T == 1 ? 6 : 4;
   const int64_t nblk = std::max<int64_t>(1, (nt + (int64_t)kThreads * p.T - 1) / ((int64_t)kThreads * p.T));
-  const int64_t want_ctas = (int64_t)sm_count * 8;
+  const int64_t want_ctas = (int64_t)sm_count * ctas_per_sm * 16;
   int64_t nsplit = (want_ctas + nblk - 1) / nblk;
-  nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, std::min<int64_t>(ntiles, 256)));
+  nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, std::max<int64_t>(1, ntiles / 4)));
+  nsplit = std::min<int64_t>(nsplit, 1024);
   p.tiles_per_split = (int)((ntiles + nsplit - 1) / nsplit);
   p.nsplit = (int)((ntiles + p.tiles_per_split - 1) / p.tiles_per_split);
   p.pstride = round_up(std::max<int64_t>(nt, 1), 32);
@@ -139,8 +151,33 @@ Plan make_plan(int64_t nt, int64_t ns, int sm_count, int force_T = 0) {
 
 template <int K>
 void launch_uj_T(const Plan &p, const UjArgs &a, cudaStream_t st) {
-  if (p.T == 2) uj_pairs_kernel<K, 2><<<p.grid, kThreads, 0, st>>>(a);
-  else uj_pairs_kernel<K, 1><<<p.grid, kThreads, 0, st>>>(a);
+  switch (p.T * 10 + p.unroll) {
+    case 11: uj_pairs_kernel<K, 1, 1><<<p.grid, kThreads, 0, st>>>(a); break;
+    case 12: uj_pairs_kernel<K, 1, 2><<<p.grid, kThreads, 0, st>>>(a); break;
+    case 14: uj_pairs_kernel<K, 1, 4><<<p.grid, kThreads, 0, st>>>(a); break;
+    case 21: uj_pairs_kernel<K, 2, 1><<<p.grid, kThreads, 0, st>>>(a); break;
+    case 41: uj_pairs_kernel<K, 4, 1><<<p.grid, kThreads, 0, st>>>(a); break;
+    case 31: uj_pairs_kernel<K, 3, 1><<<p.grid, kThreads, 0, st>>>(a); break;
+    default: uj_pairs_kernel<K, 2, 2><<<p.grid, kThreads, 0, st>>>(a); break;
+  }
+}
+template <int K>
+void launch_ujc_T(const Plan &p, const UjConstArgs &a, cudaStream_t st) {
+  const dim3 grid(p.grid.x, 1, 1);
+  switch (p.T * 10 + p.unroll) {
+    case 11: uj_const_kernel<K, 1, 1><<<grid, kThreads, 0, st>>>(a); break;
+    case 12: uj_const_kernel<K, 1, 2><<<grid, kThreads, 0, st>>>(a); break;
+    case 22: uj_const_kernel<K, 2, 2><<<grid, kThreads, 0, st>>>(a); break;
+    default: uj_const_kernel<K, 2, 1><<<grid, kThreads, 0, st>>>(a); break;
+  }
+}
+void launch_ujc(int kernel, const Plan &p, const UjConstArgs &a, cudaStream_t st) {
+  switch (kernel) {
+    case K_SING: launch_ujc_T<K_SING>(p, a, st); break;
+    case K_GAUS: launch_ujc_T<K_GAUS>(p, a, st); break;
+    case K_GERF: launch_ujc_T<K_GERF>(p, a, st); break;
+    default: launch_ujc_T<K_WINCK>(p, a, st); break;
+  }
 }
 void launch_uj(int kernel, const Plan &p, const UjArgs &a, cudaStream_t st) {
   switch (kernel) {
@@ -173,12 +210,30 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
              bool time_pairs = false) {
   const int64_t ns_pad = round_up(std::max<int64_t>(ns, 1), kTile);
   TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
-  plan = make_plan(nt, ns, d.sm_count);
+  plan = make_plan(nt, ns, d.sm_count, PLAN_UJ);
   TRY(ensure(h, d.partial, (size_t)plan.nsplit * kAcc * plan.pstride * sizeof(double)));
   prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, s0, ns, ns_pad, kernel,
                                                            (double *)d.rec.p);
   h->launches++;
-  if (nt > 0 && ns > 0) {
+  const char *cenv = getenv("VPM_UJ_CONST");
+  const bool use_const = cenv && atoi(cenv) != 0;
+  if (nt > 0 && ns > 0 && use_const) {
+    plan.nsplit = 1;
+    UjConstArgs a;
+    a.tpos = tpos; a.tld = tld; a.nt = nt;
+    a.partial = (double *)d.partial.p; a.pstride = plan.pstride;
+    a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
+    if (time_pairs) CK(h, cudaEventRecord(d.ev[6], st));
+    for (int64_t c0 = 0; c0 < ns; c0 += kCChunk) {
+      a.n = (int)std::min<int64_t>(kCChunk, ns - c0);
+      a.first = c0 == 0;
+      CK(h, cudaMemcpyToSymbolAsync(c_rec, (const double *)d.rec.p + c0 * kRec,
+                                    (size_t)a.n * kRec * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
+      launch_ujc(kernel, plan, a, st);
+      h->launches++;
+    }
+    if (time_pairs) CK(h, cudaEventRecord(d.ev[7], st));
+  } else if (nt > 0 && ns > 0) {
     UjArgs a;
     a.tpos = tpos; a.tld = tld; a.nt = nt;
     a.rec = (const double *)d.rec.p; a.ns = ns;
@@ -202,7 +257,7 @@ int sfs_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *
               const int64_t *sindex, int64_t ns, int flags, Plan &plan, bool time_pairs = false) {
   const int64_t ns_pad = round_up(std::max<int64_t>(ns, 1), kTile);
   TRY(ensure(h, d.srec, (size_t)ns_pad * kSfsRec * sizeof(double)));
-  plan = make_plan(nt, ns, d.sm_count);
+  plan = make_plan(nt, ns, d.sm_count, PLAN_SFS);
   TRY(ensure(h, d.partial, (size_t)std::max(1, plan.nsplit) * kAcc * plan.pstride * sizeof(double)));
   const int transposed = (flags & VPM_FLAG_TRANSPOSED) ? 1 : 0;
   prep_sfs_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, sJ, sjld, sjoff, stat, sld, sindex,

@@ -106,27 +106,22 @@ __global__ void __launch_bounds__(kThreads) uj_leaf_kernel(const LeafUjArgs a) {
     if (n == 0) break;
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
-    uj_tile<K, 1>(reinterpret_cast<const double2 *>(&tiles[st][0]), n, tx, ty, tz, acc, a.shortcut);
+    uj_tile<K, 1, 2>(reinterpret_cast<const double2 *>(&tiles[st][0]), n, tx, ty, tz, acc, a.shortcut);
     __syncthreads();
     if (tid == 0) issue();
   }
 
   if (valid) {
-    double *s = acc[0];
-    s[3 + 1] -= s[14];
-    s[3 + 2] += s[13];
-    s[3 + 3] += s[14];
-    s[3 + 5] -= s[12];
-    s[3 + 6] -= s[13];
-    s[3 + 7] += s[12];
+    double U[3], J[9];
+    finish_sums(acc[0], U, J);
     double *o = a.out + i * a.tld;
     if (a.want_U) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) o[a.urow + k] += s[k];
+      for (int k = 0; k < 3; ++k) o[a.urow + k] += U[k];
     }
     if (a.want_J) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) o[a.jrow + k] += s[3 + k];
+      for (int k = 0; k < 9; ++k) o[a.jrow + k] += J[k];
     }
   }
 }

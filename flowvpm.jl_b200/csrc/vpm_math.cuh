@@ -26,16 +26,17 @@ __device__ __forceinline__ double rsqrt_seed(double a) {
 }
 
 // 1/sqrt(a) for normal a > 0: seed + one third-order (Halley-type) step,
-// y = y0 (1 + e/2 + 3e^2/8), e = 1 - a y0^2; truncation 5e^3/16 < 3e-19.
-// 5 FP64-pipe instructions, ~1 ulp.  a == 0 -> +inf, a == +inf -> NaN-free 0
-// is NOT guaranteed: callers mask those lanes.
+// y = y0 (1 + e (1/2 + 3e/8)), e = 1 - a y0^2; truncation 5e^3/16 < 3e-19.
+// 5 FP64-pipe instructions, none of which reads three distinct registers (a
+// 3-register DFMA issues every 3 cycles on B200, a 2-register one every 2:
+// tools/dfma_probe.cu), ~1 ulp.  a == 0 gives NaN/inf: callers mask those lanes.
 __device__ __forceinline__ double rsqrt_fp64(double a) {
   double y0 = rsqrt_seed(a);
   double t = a * y0;
   double e = fma(-t, y0, 1.0);
   double p = fma(0.375, e, 0.5);
-  double q = y0 * e;
-  return fma(q, p, y0);
+  double s = fma(e, p, 1.0);
+  return y0 * s;
 }
 
 // exp(x) for -700 <= x <= 700 (callers clamp).  Cody-Waite reduction by
