@@ -13,7 +13,7 @@ is the same sweep through the public host API with host buffers (H2D + D2H insid
 timed region).  The SFS sweep and the other kernel families are measured after the
 timed region and reported in extra keys.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--n PARTICLES] [--kernel NAME]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--particles N] [--kernel NAME]
   python bench.py --impl reference ...   # the CPU restatement of the reference on host cores
 """
 import argparse
@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=1 << 20)
+    ap.add_argument("--particles", dest="n", type=int, default=1 << 20)
     ap.add_argument("--kernel", default="winckelmans", choices=sorted(F_UJ))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip SFS / other-kernel / CPU extras")
@@ -120,13 +120,17 @@ def cpu_sample(n, kernel, seconds, threads=None, repeats=1):
         return time.perf_counter() - t
 
     probe = min(n, 64 * threads)
+    run(min(n, 8 * threads))  # spin the thread pool up
     dt = run(probe)
     rate = probe * n / dt
-    nt = int(min(n, max(probe, seconds * rate / n // (32 * threads) * (32 * threads))))
-    best = None
-    for _ in range(repeats):
-        dt = run(nt)
-        best = dt if best is None else min(best, dt)
+    g = 32 * threads
+    nt = int(min(n, max(probe, seconds * rate / n // g * g)))
+    best = run(nt)
+    if best < 0.6 * seconds and nt < n:  # the probe under-estimated the rate: size once more
+        nt = int(min(n, max(nt, seconds * (nt * n / best) / n // g * g)))
+        best = run(nt)
+    for _ in range(repeats - 1):
+        best = min(best, run(nt))
     return nt * n / best, f"all {n} sources x first {nt} targets of the same cloud ({nt * n:.3g} interactions, {best:.1f} s)", threads
 
 

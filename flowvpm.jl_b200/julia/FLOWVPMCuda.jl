@@ -1,0 +1,193 @@
+#=##############################################################################
+# FLOWVPMCuda.jl -- Julia binding of libvpm_cuda.so for FLOWVPM.jl v4.0.x
+#
+# The reference keeps its whole host side (ParticleField, formulations, RK3,
+# relaxation, dynamic SFS, I/O).  This file is the only thing a maintainer adds:
+# a callable for the `UJ` slot of the ParticleField plus, optionally, overloads of
+# the two FastMultipole hooks, all of which `ccall` the C ABI of
+# include/vpm_cuda.h.  It cannot be executed in the build environment of this
+# repository (no Julia there); tests/ exercise the identical ABI through ctypes.
+#
+# Usage
+#     import FLOWVPM; const vpm = FLOWVPM
+#     include("FLOWVPMCuda.jl"); using .FLOWVPMCuda
+#     FLOWVPMCuda.init!("/path/to/libvpm_cuda.so"; n_gpus=1)
+#     pfield = vpm.ParticleField(maxp; UJ=FLOWVPMCuda.UJ_cuda, kernel=vpm.winckelmans, ...)
+#     FLOWVPMCuda.pin!(pfield)                 # optional: page-lock pfield.particles once
+#     vpm.run_vpm!(pfield, dt, nsteps)         # every pfield.UJ(...) call now runs on the GPU(s)
+#
+# Install it in the slot, not only as `custom_UJ`: the dynamic-SFS test filter and the
+# relaxation step call `pfield.UJ` directly (src/FLOWVPM_subfilterscale.jl:478,
+# src/FLOWVPM_timeintegration.jl:244,443).
+=###############################################################################
+module FLOWVPMCuda
+
+import FLOWVPM
+const vpm = FLOWVPM
+const fmm = FLOWVPM.fmm
+
+const VPM_OK = Cint(0)
+const FLAG_RESET = Cint(1)
+const FLAG_RESET_SFS = Cint(2)
+const FLAG_SFS = Cint(4)
+const FLAG_TRANSPOSED = Cint(8)
+
+const lib = Ref{String}("libvpm_cuda.so")
+const handle = Ref{Ptr{Cvoid}}(C_NULL)
+
+"Kernel family id of include/vpm_cuda.h from the reference's singletons (src/FLOWVPM.jl:129-133)"
+function kernel_id(k::vpm.Kernel)
+    k === vpm.kernel_singular    && return Cint(0)
+    k === vpm.kernel_gaussian    && return Cint(1)
+    k === vpm.kernel_gaussianerf && return Cint(2)
+    k === vpm.kernel_winckelmans && return Cint(3)
+    error("FLOWVPMCuda: kernel $(k) has no CUDA implementation (user-defined kernels stay on UJ_direct/UJ_fmm)")
+end
+
+function check(rc::Cint)
+    rc == VPM_OK && return nothing
+    msg = unsafe_string(ccall((:vpm_last_error, lib[]), Cstring, (Ptr{Cvoid},), handle[]))
+    error("libvpm_cuda error $(rc): $(msg)")   # the reference reports failures with error(...)
+end
+
+"Open the library and create the handle (device buffers, streams, NCCL communicators)."
+function init!(path::AbstractString="libvpm_cuda.so"; n_gpus::Integer=1, devices=nothing)
+    lib[] = String(path)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    ids = devices === nothing ? C_NULL : Cint.(collect(devices))
+    n = devices === nothing ? Cint(n_gpus) : Cint(length(devices))
+    rc = ccall((:vpm_create, lib[]), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Cint}), h, n, ids)
+    if rc != VPM_OK
+        msg = unsafe_string(ccall((:vpm_last_error, lib[]), Cstring, (Ptr{Cvoid},), C_NULL))
+        error("libvpm_cuda: vpm_create failed ($(rc)): $(msg)")
+    end
+    handle[] = h[]
+    atexit(shutdown!)
+    return nothing
+end
+
+function shutdown!()
+    if handle[] != C_NULL
+        ccall((:vpm_destroy, lib[]), Cint, (Ptr{Cvoid},), handle[])
+        handle[] = C_NULL
+    end
+end
+
+"Page-lock pfield.particles (allocated once at maxparticles, src/FLOWVPM_particlefield.jl:134)."
+function pin!(pfield::vpm.ParticleField)
+    P = pfield.particles
+    GC.@preserve P check(ccall((:vpm_pin_host, lib[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t),
+                               handle[], pointer(P), sizeof(P)))
+end
+
+function flags(pfield; sfs, reset, reset_sfs)
+    f = Cint(0)
+    reset && (f |= FLAG_RESET)
+    reset_sfs && (f |= FLAG_RESET_SFS)
+    sfs && (f |= FLAG_SFS)
+    pfield.transposed && (f |= FLAG_TRANSPOSED)
+    return f
+end
+
+"""
+    UJ_cuda(pfield; rbf=false, sfs=false, reset=true, reset_sfs=false, optargs...)
+
+Drop-in for `UJ_direct(pfield; ...)` (src/FLOWVPM_UJ.jl:21-37): same keywords, same
+effects on rows 10:27 and 40:42 of `pfield.particles` (reset-then-accumulate, static
+particles never reset, SFS sweep after the final J).  `rbf` is accepted and ignored,
+as in the reference.
+"""
+function UJ_cuda(pfield::vpm.ParticleField{Float64}; rbf::Bool=false, sfs::Bool=false,
+                 reset::Bool=true, reset_sfs::Bool=false, optargs...)
+    P = pfield.particles
+    GC.@preserve P check(ccall((:vpm_uj_direct, lib[]), Cint,
+                               (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Cint, Cint),
+                               handle[], P, size(P, 1), pfield.np, kernel_id(pfield.kernel),
+                               flags(pfield; sfs, reset, reset_sfs)))
+    return nothing
+end
+
+function UJ_cuda(pfield::vpm.ParticleField{Float32}; rbf::Bool=false, sfs::Bool=false,
+                 reset::Bool=true, reset_sfs::Bool=false, optargs...)
+    P = pfield.particles
+    GC.@preserve P check(ccall((:vpm_uj_direct_f32, lib[]), Cint,
+                               (Ptr{Cvoid}, Ptr{Float32}, Int64, Int64, Cint, Cint),
+                               handle[], P, size(P, 1), pfield.np, kernel_id(pfield.kernel),
+                               flags(pfield; sfs, reset, reset_sfs)))
+    return nothing
+end
+
+"`UJ_direct(source, target)` (src/FLOWVPM_UJ.jl:48-50): probes / fluid-domain evaluation."
+function UJ_cuda(source::vpm.ParticleField{Float64}, target::vpm.ParticleField{Float64})
+    S, T = source.particles, target.particles
+    GC.@preserve S T check(ccall((:vpm_uj_direct_st, lib[]), Cint,
+                                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Int64, Int64, Cint),
+                                 handle[], S, size(S, 1), source.np, T, size(T, 1), target.np,
+                                 kernel_id(source.kernel)))
+    return nothing
+end
+
+# ------------------------------------------------------------------------------
+# Hook 2 -- the FastMultipole pair-loop overload (src/FLOWVPM_fmm.jl:102-168).
+# Replaces the body of FLOWVPM's own `fmm.direct!` method: FastMultipole calls it for
+# `direct!(system)` and for every near-field leaf pair on the CPU path.  Row offsets of
+# the target buffer are FastMultipole's (position 1:3, scalar potential 4, gradient
+# 5:7, hessian 8:16) and therefore arguments of the ABI.
+# ------------------------------------------------------------------------------
+function direct_cuda!(target_buffer::Matrix{Float64}, target_index::UnitRange,
+                      ::fmm.DerivativesSwitch{PS,VS,GS}, source_system::vpm.ParticleField,
+                      source_buffer::Matrix{Float64}, source_index::UnitRange) where {PS,VS,GS}
+    GC.@preserve target_buffer source_buffer check(ccall((:vpm_p2p_buffers, lib[]), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Cint, Cint, Cint, Ptr{Float64}, Int64, Int64, Cint, Cint, Cint),
+        handle[], target_buffer, size(target_buffer, 1), first(target_index) - 1, last(target_index),
+        0, 4, 7, source_buffer, first(source_index) - 1, last(source_index),
+        kernel_id(source_system.kernel), VS, GS))
+    return nothing
+end
+
+# ------------------------------------------------------------------------------
+# Hook 3 -- the FMM near-field device hook.  With `useGPU>0`, UJ_fmm passes
+# `nearfield_device=true` (src/FLOWVPM_UJ.jl:97) and FastMultipole calls
+# `nearfield_device!`; the whole direct_list goes to the GPU in one call instead of one
+# launch per target leaf (the removed CUDA.jl path, src/FLOWVPM_gpu.jl:554-643).
+# ------------------------------------------------------------------------------
+function nearfield_cuda!(target_buffer::Matrix{Float64}, target_branches, source_system::vpm.ParticleField,
+                         source_buffer::Matrix{Float64}, source_branches, direct_list;
+                         velocity::Bool=true, velocity_gradient::Bool=true)
+    tb = Int64[first(b.bodies_index[1]) - 1 for b in target_branches]
+    te = Int64[last(b.bodies_index[1]) for b in target_branches]
+    sb = Int64[first(b.bodies_index[1]) - 1 for b in source_branches]
+    se = Int64[last(b.bodies_index[1]) for b in source_branches]
+    pt = Int32[p[1] - 1 for p in direct_list]
+    ps = Int32[p[2] - 1 for p in direct_list]
+    GC.@preserve target_buffer source_buffer tb te sb se pt ps check(ccall((:vpm_p2p_leafpairs, lib[]), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Cint, Cint, Cint, Ptr{Float64}, Int64,
+         Ptr{Int64}, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Ptr{Int32}, Ptr{Int32}, Int64, Cint, Cint, Cint),
+        handle[], target_buffer, size(target_buffer, 1), size(target_buffer, 2), 0, 4, 7,
+        source_buffer, size(source_buffer, 2), tb, te, length(tb), sb, se, length(sb), pt, ps, length(pt),
+        kernel_id(source_system.kernel), velocity, velocity_gradient))
+    return nothing
+end
+
+"`Estr_fmm!` over the near-field list (src/FLOWVPM_subfilterscale_models.jl:94-188)."
+function Estr_cuda!(pfield::vpm.ParticleField{Float64}, target_tree, source_tree, direct_list)
+    P = pfield.particles
+    ts = Int64.(target_tree.sort_index_list[1]) .- 1
+    ss = Int64.(source_tree.sort_index_list[1]) .- 1
+    tb = Int64[first(b.bodies_index[1]) - 1 for b in target_tree.branches]
+    te = Int64[last(b.bodies_index[1]) for b in target_tree.branches]
+    sb = Int64[first(b.bodies_index[1]) - 1 for b in source_tree.branches]
+    se = Int64[last(b.bodies_index[1]) for b in source_tree.branches]
+    pt = Int32[p[1] - 1 for p in direct_list]
+    ps = Int32[p[2] - 1 for p in direct_list]
+    GC.@preserve P ts ss tb te sb se pt ps check(ccall((:vpm_estr_leafpairs, lib[]), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64,
+         Ptr{Int64}, Ptr{Int64}, Int64, Ptr{Int32}, Ptr{Int32}, Int64, Cint, Cint),
+        handle[], P, size(P, 1), pfield.np, ts, ss, tb, te, length(tb), sb, se, length(sb), pt, ps, length(pt),
+        kernel_id(pfield.kernel), flags(pfield; sfs=true, reset=false, reset_sfs=false)))
+    return nothing
+end
+
+export UJ_cuda
+
+end # module

@@ -79,8 +79,8 @@ int vpm_num_devices(const vpm_handle *h);
  * semantics (src/FLOWVPM_particlefield.jl:464-511, src/FLOWVPM_fmm.jl:170-176). */
 int vpm_uj_direct(vpm_handle *h, double *particles, int64_t nfields, int64_t np,
                   int kernel_id, int flags);
-/* same for a Matrix{Float32} field (ParticleField(n, Float32)); arithmetic in
- * FP32 with FP64 tile sums, tolerance 1e-5 */
+/* same for a Matrix{Float32} field (ParticleField(n, Float32)): Float32 storage,
+ * converted on the device, FP64 arithmetic; tolerance 1e-5 */
 int vpm_uj_direct_f32(vpm_handle *h, float *particles, int64_t nfields, int64_t np,
                       int kernel_id, int flags);
 /* UJ_direct(source, target): src/FLOWVPM_UJ.jl:48-50 -- the field `source`

@@ -1,0 +1,95 @@
+"""Multi-GPU paths (need >= 2 GPUs; skipped otherwise):
+  * one process driving G devices through one handle (the Julia caller's situation):
+    targets block-sharded, NCCL all-gather of the final J before the SFS sweep;
+  * one process per GPU (torch.distributed + NCCL) through flowvpm_jl_b200.sharding,
+    the path bench.py --gpus N times."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import assert_parity, relerr, TOL_FP64
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("kernel", ["winckelmans", "gaussianerf"])
+@pytest.mark.parametrize("n", [5001, 64])
+def test_single_process_multi_gpu_handle(vpm, kernel, n):
+    g = _ngpu()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    h = vpm.Handle(min(g, 4))
+    try:
+        pf = vpm.fields.cloud_field(n, kernel=vpm.KERNELS[kernel], static_fraction=0.1, seed=3)
+        vpm.fields.random_results(pf, scale=1e-3)
+        ref = pf.particles.copy(order="F")
+        oracle.uj_direct(ref, n, kernel, sfs=True, reset=True, reset_sfs=True)
+        vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True, handle=h)
+        assert_parity(pf.particles, ref, n, rows=("U", "J", "SFS", "W", "PSE"))
+        # accumulate semantics across devices
+        oracle.uj_direct(ref, n, kernel, sfs=True, reset=False, reset_sfs=False)
+        vpm.UJ_direct(pf, sfs=True, reset=False, reset_sfs=False, handle=h)
+        assert_parity(pf.particles, ref, n)
+        assert h.timing()["n_gpus"] == min(g, 4)
+    finally:
+        h.close()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from vpm_import import load
+    vpm = load()
+    from flowvpm_jl_b200 import sharding
+    h = vpm.Handle(device_ids=[rank])
+    pf = vpm.fields.cloud_field(n, kernel=vpm.gaussianerf, seed=44)
+    src8 = vpm.source_system_to_buffer(pf)
+    t0, t1 = sharding.shard_bounds(n, world, rank)
+    local = torch.from_numpy(np.ascontiguousarray(src8[:, t0:t1].T)).cuda()
+    f = sharding.ShardedField(h, local, n, rank, world, vpm.gaussianerf.id)
+    uj = f.uj(0)
+    sfs = f.sfs(8)
+    torch.cuda.synchronize()
+    np.save(os.path.join(out_dir, f"uj_{rank}.npy"), uj[: t1 - t0].cpu().numpy())
+    np.save(os.path.join(out_dir, f"sfs_{rank}.npy"), sfs[: t1 - t0].cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_one_process_per_gpu_sharding(vpm, tmp_path):
+    g = _ngpu()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    n, world = 7001, 2
+    mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    pf = vpm.fields.cloud_field(n, kernel=vpm.gaussianerf, seed=44)
+    ref = pf.particles.copy(order="F")
+    oracle.uj_direct(ref, n, "gaussianerf", sfs=True, reset=True, reset_sfs=True)
+    uj = np.concatenate([np.load(tmp_path / f"uj_{r}.npy") for r in range(world)]).T
+    sfs = np.concatenate([np.load(tmp_path / f"sfs_{r}.npy") for r in range(world)]).T
+    assert relerr(uj[0:3], ref[9:12, :n]) < TOL_FP64
+    assert relerr(uj[3:12], ref[15:24, :n]) < TOL_FP64
+    assert relerr(sfs, ref[39:42, :n]) < TOL_FP64
