@@ -77,9 +77,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 
 // ------------------------------------------------------------ record builders
-// U/J record of source i:  [x y z q0 | G'x G'y G'z q1 | q2 0],  G' = -Gamma/(4 pi)
+// U/J record of source i:  [x y z q0 | G'x G'y G'z q1 | q2 q3],  G' = -Gamma/(4 pi)
 //   winckelmans: q0 = sigma^2, q1 = 1.5 sigma^2, q2 = -7.5 sigma^2
-//   gaussian(erf): q0 = 1/sigma^2, q1 = 1/sigma, q2 = r^2 beyond which g == 1
+//   gaussianerf: q0 = 1/sigma^2, q1 = 1/sigma^3, q2 = r^2 beyond which g == 1, q3 = 2/sigma^5
+//   gaussian:    q0 = 1/sigma^2, q1 = 1/sigma,   q2 = r^2 beyond which g == 1
 struct SrcView {
   const double *p;  // base of a column-major matrix
   int64_t ld;       // rows per column
@@ -101,17 +102,20 @@ __global__ void prep_uj_records(SrcView src, int64_t s0, int64_t ns, int64_t ns_
   double isig = 1.0 / sigma;
   double isig2 = isig * isig;
   double isig3 = isig2 * isig;
-  double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+  double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
   if (kernel == K_WINCK) {
     q0 = sigma * sigma; q1 = 1.5 * q0; q2 = -7.5 * q0;
-  } else if (kernel == K_GERF || kernel == K_GAUS) {
+  } else if (kernel == K_GERF) {
+    q0 = isig2; q1 = isig3;
+    q2 = kFarU_gerf * (sigma * sigma);  // far-field cutoff in r^2
+    q3 = 2.0 * isig3 * isig2;
+  } else if (kernel == K_GAUS) {
     q0 = isig2; q1 = isig;
-    q2 = (kernel == K_GERF ? kFarU_gerf : kFarU_gaus) * (sigma * sigma);  // far-field cutoff in r^2
+    q2 = kFarU_gaus * (sigma * sigma);
   }
-  (void)isig3;
   r[0] = p[src.ox]; r[1] = p[src.ox + 1]; r[2] = p[src.ox + 2]; r[3] = q0;
   r[4] = -kConst4 * p[src.og]; r[5] = -kConst4 * p[src.og + 1]; r[6] = -kConst4 * p[src.og + 2];
-  r[7] = q1; r[8] = q2; r[9] = 0.0;
+  r[7] = q1; r[8] = q2; r[9] = q3;
 }
 
 // SFS record of source i: [x y z q0 | Gx Gy Gz q1 | J(row-of-3 order) 0], q0 = 1/s^2,
@@ -189,23 +193,42 @@ __device__ __forceinline__ void ab_sing(double r2, double &A, double &B) {
   B = select_zero(z, b);
 }
 
-// gaussianerf near field (src/FLOWVPM_kernel.jl:54-57), reference formula order:
-//   aux = sqrt(2/pi) s e^{-s^2/2};  g = erf(s/sqrt2) - aux;  dg = s aux
-__device__ __forceinline__ void ab_gerf(double r2, double q0, double q1, double &A, double &B) {
-  double rinv = rsqrt_fp64(r2);
-  double r = r2 * rinv;
-  double s = r * q1;
-  double E = exp_neg_fp64(0.5 * (r2 * q0));
-  double aux = kConst2 * s * E;
-  double g = erf(s * kInvSqrt2) - aux;
-  double dg = s * aux;
-  double rinv2 = rinv * rinv;
-  double rinv3 = rinv2 * rinv;
-  double a = g * rinv3;
-  double b = (dg * q1 * rinv - 3.0 * g * rinv2) * rinv3;
-  bool z = is_zero_bits(r2);
-  A = select_zero(z, a);
-  B = select_zero(z, b);
+// gaussianerf near field (src/FLOWVPM_kernel.jl:54-57):
+//   g = erf(s/sqrt2) - sqrt(2/pi) s e^{-s^2/2},  dg = sqrt(2/pi) s^2 e^{-s^2/2}.
+// With u = s^2:  A = G(u)/sigma^3,  G = g/s^3  (regular: G(0) = sqrt(2/pi)/3), and
+//   B = (dg/(sigma r) - 3g/r^2)/r^3 = H(u)/sigma^5,  H = (sqrt(2/pi) e^{-u/2} - 3G)/u = 2 dG/du,
+// so ONE piecewise polynomial (degree 9 on 163 intervals of width 1/2 in u, generated at
+// 60 digits by tools/gen_coeffs.py, 1.2e-16) gives both: value and derivative from the
+// same Horner pass.  No erf, no exp, no 1/r, and none of the small-s cancellation of the
+// reference's g = erf - aux.  `tab` is the table staged in shared memory, 5 double2 per row.
+constexpr double kGerfMagic = 6755399441055744.0;  // 1.5 * 2^52: low word of u*2 + magic = rint(2u)
+__device__ __forceinline__ void ab_gerf_tab(double r2, double q0, double q1, double q3,
+                                            const double2 *__restrict__ tab, double &A, double &B) {
+  double u = r2 * q0;
+  double kd = fma(u, 2.0, kGerfMagic);
+  int idx = __double2loint(kd);
+  idx = min(max(idx, 0), kGerfIntervals - 1);
+  double x = fma(kd - kGerfMagic, -0.5, u);
+  const double2 *row = tab + idx * (kGerfCoeffs / 2);
+  const double2 c01 = row[0], c23 = row[1], c45 = row[2], c67 = row[3], c89 = row[4];
+  double p = c89.y, dp;
+  dp = p;               p = fma(p, x, c89.x);
+  dp = fma(dp, x, p);   p = fma(p, x, c67.y);
+  dp = fma(dp, x, p);   p = fma(p, x, c67.x);
+  dp = fma(dp, x, p);   p = fma(p, x, c45.y);
+  dp = fma(dp, x, p);   p = fma(p, x, c45.x);
+  dp = fma(dp, x, p);   p = fma(p, x, c23.y);
+  dp = fma(dp, x, p);   p = fma(p, x, c23.x);
+  dp = fma(dp, x, p);   p = fma(p, x, c01.y);
+  dp = fma(dp, x, p);   p = fma(p, x, c01.x);
+  A = select_zero(is_zero_bits(r2), q1 * p);
+  B = q3 * dp;
+}
+
+// cooperative copy of the G(u) table into shared memory (13 KB, once per CTA)
+__device__ __forceinline__ void load_gerf_table(double2 *tab) {
+  const double2 *src = reinterpret_cast<const double2 *>(kGerfTable);
+  for (int i = threadIdx.x; i < kGerfIntervals * kGerfCoeffs / 2; i += blockDim.x) tab[i] = src[i];
 }
 
 // gaussian near field (src/FLOWVPM_kernel.jl:63-66): g = 1 - e^{-s^3}, dg = 3 s^2 e^{-s^3}
@@ -260,10 +283,11 @@ __constant__ double c_rec[kCChunk * kRec];
 template <bool CONST>
 __device__ __forceinline__ void load_rec(const double2 *__restrict__ tile, int j, double &sx, double &sy,
                                          double &sz, double &q0, double &gx, double &gy, double &gz,
-                                         double &q1, double &q2) {
+                                         double &q1, double &q2, double &q3) {
   if constexpr (CONST) {
     const double *r = c_rec + j * kRec;
     sx = r[0]; sy = r[1]; sz = r[2]; q0 = r[3]; gx = r[4]; gy = r[5]; gz = r[6]; q1 = r[7]; q2 = r[8];
+    q3 = r[9];
   } else {
     const double2 v0 = tile[j * 5 + 0];
     const double2 v1 = tile[j * 5 + 1];
@@ -272,7 +296,7 @@ __device__ __forceinline__ void load_rec(const double2 *__restrict__ tile, int j
     const double2 v4 = tile[j * 5 + 4];
     sx = v0.x; sy = v0.y; sz = v1.x; q0 = v1.y;
     gx = v2.x; gy = v2.y; gz = v3.x; q1 = v3.y;
-    q2 = v4.x;
+    q2 = v4.x; q3 = v4.y;
   }
 }
 
@@ -286,11 +310,11 @@ template <int K, int T, int UNROLL, bool CONST = false>
 __device__ __forceinline__ void uj_tile(const double2 *__restrict__ tile, int n,
                                         const double (&tx)[T], const double (&ty)[T],
                                         const double (&tz)[T], double (&acc)[T][kAcc],
-                                        int shortcut) {
+                                        int shortcut, const double2 *__restrict__ gtab = nullptr) {
 #pragma unroll UNROLL
   for (int j = 0; j < n; ++j) {
-    double sx, sy, sz, q0, gx, gy, gz, q1, q2;
-    load_rec<CONST>(tile, j, sx, sy, sz, q0, gx, gy, gz, q1, q2);
+    double sx, sy, sz, q0, gx, gy, gz, q1, q2, q3;
+    load_rec<CONST>(tile, j, sx, sy, sz, q0, gx, gy, gz, q1, q2, q3);
 
     double dx[T], dy[T], dz[T], A[T], B[T];
 #pragma unroll
@@ -317,14 +341,31 @@ __device__ __forceinline__ void uj_tile(const double2 *__restrict__ tile, int n,
       } else {
         // far-field test on the integer pipe: r2 > cutoff  <=  hi word strictly greater
         const int far_hi = __double2hiint(q2);
-        bool near = !shortcut;
+        bool near = !shortcut, beyond = false;
 #pragma unroll
-        for (int t = 0; t < T; ++t) near |= (__double2hiint(r2[t]) <= far_hi);
+        for (int t = 0; t < T; ++t) {
+          const bool nr = __double2hiint(r2[t]) <= far_hi;
+          near |= nr;
+          beyond |= !nr;
+        }
         if (__any_sync(0xffffffffu, near)) {
+          if constexpr (K == K_GERF) {
+            // lanes past the end of the table (s > 9) take the far-field values
+            const bool mixed = __any_sync(0xffffffffu, beyond);
 #pragma unroll
-          for (int t = 0; t < T; ++t) {
-            if constexpr (K == K_GERF) ab_gerf(r2[t], q0, q1, A[t], B[t]);
-            else ab_gaus(r2[t], q0, q1, A[t], B[t]);
+            for (int t = 0; t < T; ++t) {
+              ab_gerf_tab(r2[t], q0, q1, q3, gtab, A[t], B[t]);
+              if (mixed) {
+                double As, Bs;
+                ab_sing(r2[t], As, Bs);
+                const bool far = __double2hiint(r2[t]) > far_hi;
+                A[t] = far ? As : A[t];
+                B[t] = far ? Bs : B[t];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < T; ++t) ab_gaus(r2[t], q0, q1, A[t], B[t]);
           }
         } else {
 #pragma unroll
@@ -390,6 +431,8 @@ template <int K, int T, int UNROLL>
 __global__ void __launch_bounds__(kThreads, (T == 1 ? 6 : T == 2 ? 4 : T == 3 ? 3 : 2)) uj_pairs_kernel(const UjArgs a) {
   __shared__ __align__(128) double tiles[kStages][kTile * kRec];
   __shared__ __align__(8) uint64_t full[kStages];
+  __shared__ __align__(16) double2 gtab[K == K_GERF ? kGerfIntervals * kGerfCoeffs / 2 : 1];
+  if constexpr (K == K_GERF) load_gerf_table(gtab);  // visible after the __syncthreads below
 
   const int tid = threadIdx.x;
   const int64_t tbase = (int64_t)blockIdx.x * (kThreads * T);
@@ -441,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, (T == 1 ? 6 : T == 2 ? 4 : T == 3 ? 
     const int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
     const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
 
-    uj_tile<K, T, UNROLL>(tile, n, tx, ty, tz, acc, a.shortcut);
+    uj_tile<K, T, UNROLL>(tile, n, tx, ty, tz, acc, a.shortcut, gtab);
     __syncthreads();  // everyone is done reading stage st
     if (tid == 0 && it + kStages < ntl) issue(it + kStages);
   }
@@ -474,6 +517,11 @@ struct UjConstArgs {
 template <int K, int T, int UNROLL>
 __global__ void __launch_bounds__(kThreads, (T == 1 ? 6 : T == 2 ? 4 : T == 3 ? 3 : 2))
     uj_const_kernel(const UjConstArgs a) {
+  __shared__ __align__(16) double2 gtab[K == K_GERF ? kGerfIntervals * kGerfCoeffs / 2 : 1];
+  if constexpr (K == K_GERF) {
+    load_gerf_table(gtab);
+    __syncthreads();
+  }
   const int tid = threadIdx.x;
   const int64_t tbase = (int64_t)blockIdx.x * (kThreads * T);
   double tx[T], ty[T], tz[T], acc[T][kAcc];
@@ -486,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, (T == 1 ? 6 : T == 2 ? 4 : T == 3 ? 
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) acc[t][k] = a.first ? 0.0 : a.partial[(int64_t)k * a.pstride + i];
   }
-  uj_tile<K, T, UNROLL, true>(nullptr, a.n, tx, ty, tz, acc, a.shortcut);
+  uj_tile<K, T, UNROLL, true>(nullptr, a.n, tx, ty, tz, acc, a.shortcut, gtab);
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     int64_t i = tbase + (int64_t)t * kThreads + tid;
@@ -777,7 +825,7 @@ __global__ void test_math_kernel(int op, int arg, const double *in, double *out,
     double A = 0, B = 0;
     if (arg == K_WINCK) { ab_winck(x + 1.0, 1.5, -7.5, A, B); A = select_zero(is_zero_bits(x), A); }
     else if (arg == K_SING) ab_sing(x, A, B);
-    else if (arg == K_GERF) ab_gerf(x, 1.0, 1.0, A, B);
+    else if (arg == K_GERF) ab_gerf_tab(x, 1.0, 1.0, 2.0, reinterpret_cast<const double2 *>(kGerfTable), A, B);
     else ab_gaus(x, 1.0, 1.0, A, B);
     out[i] = A;
     if (out2) out2[i] = B;

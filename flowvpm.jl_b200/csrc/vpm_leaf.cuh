@@ -63,6 +63,8 @@ template <int K>
 __global__ void __launch_bounds__(kThreads) uj_leaf_kernel(const LeafUjArgs a) {
   __shared__ __align__(128) double tiles[kStages][kTile * kRec];
   __shared__ __align__(8) uint64_t full[kStages];
+  __shared__ __align__(16) double2 gtab[K == K_GERF ? kGerfIntervals * kGerfCoeffs / 2 : 1];
+  if constexpr (K == K_GERF) load_gerf_table(gtab);  // visible after the __syncthreads below
   const int tid = threadIdx.x;
   const int leaf = a.csr.wi_leaf[blockIdx.x];
   const int64_t tb = a.csr.tleaf_begin[leaf] + a.csr.wi_off[blockIdx.x];
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(kThreads) uj_leaf_kernel(const LeafUjArgs a) {
     if (n == 0) break;
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
-    uj_tile<K, 1, 2>(reinterpret_cast<const double2 *>(&tiles[st][0]), n, tx, ty, tz, acc, a.shortcut);
+    uj_tile<K, 1, 2>(reinterpret_cast<const double2 *>(&tiles[st][0]), n, tx, ty, tz, acc, a.shortcut, gtab);
     __syncthreads();
     if (tid == 0) issue();
   }
