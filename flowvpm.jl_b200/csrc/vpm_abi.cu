@@ -612,6 +612,7 @@ int uj_direct_multi(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
 struct HostCsr {
   std::vector<int64_t> ptr;
   std::vector<int32_t> src, wi_leaf, wi_off;
+  int nt = kThreads;  // threads per CTA (targets per work item): 32, 64 or 128
 };
 
 int build_csr(vpm_handle *h, const char *fn, const int64_t *tb, const int64_t *te, int64_t ntl,
@@ -633,11 +634,24 @@ int build_csr(vpm_handle *h, const char *fn, const int64_t *tb, const int64_t *t
   c.src.resize((size_t)npairs);
   std::vector<int64_t> cur(c.ptr.begin(), c.ptr.end() - 1);
   for (int64_t k = 0; k < npairs; ++k) c.src[(size_t)cur[(size_t)pt[k]]++] = ps[k];  // stable
+  // CTA width: minimise the padded lane-work  sum_leaf ceil(size/NT)*NT * (its source bodies)
+  std::vector<int64_t> srcw((size_t)ntl, 0);
+  for (int64_t k = 0; k < npairs; ++k) srcw[(size_t)pt[k]] += se[ps[k]] - sb[ps[k]];
+  double best = -1.0;
+  for (int cand : {128, 64, 32}) {
+    double w = 0.0;
+    for (int64_t l = 0; l < ntl; ++l) {
+      const int64_t sz = te[l] - tb[l];
+      w += (double)((sz + cand - 1) / cand * cand) * (double)srcw[(size_t)l];
+    }
+    // wider CTAs amortise the tile traffic better: require a 10 % gain to go narrower
+    if (best < 0.0 || w < 0.9 * best) { best = w; c.nt = cand; }
+  }
   c.wi_leaf.clear();
   c.wi_off.clear();
   for (int64_t l = 0; l < ntl; ++l) {
     if (c.ptr[(size_t)l + 1] == c.ptr[(size_t)l]) continue;
-    for (int64_t off = 0; off < te[l] - tb[l]; off += kThreads) {
+    for (int64_t off = 0; off < te[l] - tb[l]; off += c.nt) {
       c.wi_leaf.push_back((int32_t)l);
       c.wi_off.push_back((int32_t)off);
     }
@@ -692,6 +706,35 @@ int upload_csr(vpm_handle *h, Dev &d, cudaStream_t st, const HostCsr &c, const i
   out.csr_ptr = dptr; out.csr_src = dsrc; out.sleaf_begin = dsb; out.sleaf_end = dse;
   d_tsort = dts; d_ssort = dss;
   return VPM_OK;
+}
+
+template <int K>
+void launch_uj_leaf_K(int nt, unsigned nwi, const LeafUjArgs &a, cudaStream_t st) {
+  if (nt == 32) uj_leaf_kernel<K, 32, 64><<<nwi, 32, 0, st>>>(a);
+  else if (nt == 64) uj_leaf_kernel<K, 64, 64><<<nwi, 64, 0, st>>>(a);
+  else uj_leaf_kernel<K, 128, 128><<<nwi, 128, 0, st>>>(a);
+}
+void launch_uj_leaf(int kernel, int nt, unsigned nwi, const LeafUjArgs &a, cudaStream_t st) {
+  switch (kernel) {
+    case K_SING: launch_uj_leaf_K<K_SING>(nt, nwi, a, st); break;
+    case K_GAUS: launch_uj_leaf_K<K_GAUS>(nt, nwi, a, st); break;
+    case K_GERF: launch_uj_leaf_K<K_GERF>(nt, nwi, a, st); break;
+    default: launch_uj_leaf_K<K_WINCK>(nt, nwi, a, st); break;
+  }
+}
+template <int K>
+void launch_sfs_leaf_K(int nt, unsigned nwi, const LeafSfsArgs &a, cudaStream_t st) {
+  if (nt == 32) sfs_leaf_kernel<K, 32, 64><<<nwi, 32, 0, st>>>(a);
+  else if (nt == 64) sfs_leaf_kernel<K, 64, 64><<<nwi, 64, 0, st>>>(a);
+  else sfs_leaf_kernel<K, 128, 128><<<nwi, 128, 0, st>>>(a);
+}
+void launch_sfs_leaf(int kernel, int nt, unsigned nwi, const LeafSfsArgs &a, cudaStream_t st) {
+  switch (kernel) {
+    case K_SING: launch_sfs_leaf_K<K_SING>(nt, nwi, a, st); break;
+    case K_GAUS: launch_sfs_leaf_K<K_GAUS>(nt, nwi, a, st); break;
+    case K_GERF: launch_sfs_leaf_K<K_GERF>(nt, nwi, a, st); break;
+    default: launch_sfs_leaf_K<K_WINCK>(nt, nwi, a, st); break;
+  }
 }
 
 int64_t count_pairs(const int64_t *tb, const int64_t *te, const int64_t *sb, const int64_t *se,
@@ -1123,12 +1166,7 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
   a.out = (double *)d.tbuf.p; a.urow = row_grad; a.jrow = row_hess; a.want_U = want_U; a.want_J = want_J;
   a.shortcut = 1;
   const unsigned nwi = (unsigned)c.wi_leaf.size();
-  switch (kernel) {
-    case K_SING: uj_leaf_kernel<K_SING><<<nwi, kThreads, 0, st>>>(a); break;
-    case K_GAUS: uj_leaf_kernel<K_GAUS><<<nwi, kThreads, 0, st>>>(a); break;
-    case K_GERF: uj_leaf_kernel<K_GERF><<<nwi, kThreads, 0, st>>>(a); break;
-    default: uj_leaf_kernel<K_WINCK><<<nwi, kThreads, 0, st>>>(a); break;
-  }
+  launch_uj_leaf(kernel, c.nt, nwi, a, st);
   h->launches++;
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(d.ev[2], st));
@@ -1192,12 +1230,7 @@ int vpm_estr_leafpairs(vpm_handle *h, double *P, int64_t nf, int64_t np, const i
   a.transposed = transposed;
   a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
   const unsigned nwi = (unsigned)c.wi_leaf.size();
-  switch (kernel) {
-    case K_SING: sfs_leaf_kernel<K_SING><<<nwi, kThreads, 0, st>>>(a); break;
-    case K_GAUS: sfs_leaf_kernel<K_GAUS><<<nwi, kThreads, 0, st>>>(a); break;
-    case K_GERF: sfs_leaf_kernel<K_GERF><<<nwi, kThreads, 0, st>>>(a); break;
-    default: sfs_leaf_kernel<K_WINCK><<<nwi, kThreads, 0, st>>>(a); break;
-  }
+  launch_sfs_leaf(kernel, c.nt, nwi, a, st);
   h->launches++;
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(d.ev[4], st));

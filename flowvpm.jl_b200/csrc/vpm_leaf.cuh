@@ -32,8 +32,8 @@ struct LeafTileIter {
     le = c.csr_ptr[leaf + 1];
     cur = end = 0;
   }
-  // next tile [first, first+n); n == 0 when the list is exhausted
-  __device__ __forceinline__ int next(const LeafCsr &c, int64_t &first) {
+  // next tile [first, first+n) of at most `tile` bodies; n == 0 when the list is exhausted
+  __device__ __forceinline__ int next(const LeafCsr &c, int64_t &first, int tile) {
     while (cur >= end) {
       if (li >= le) return 0;
       int s = c.csr_src[li++];
@@ -42,7 +42,7 @@ struct LeafTileIter {
     }
     first = cur;
     int64_t n = end - cur;
-    if (n > kTile) n = kTile;
+    if (n > tile) n = tile;
     cur += n;
     return (int)n;
   }
@@ -59,9 +59,12 @@ struct LeafUjArgs {
   int shortcut;
 };
 
-template <int K>
-__global__ void __launch_bounds__(kThreads) uj_leaf_kernel(const LeafUjArgs a) {
-  __shared__ __align__(128) double tiles[kStages][kTile * kRec];
+// NT threads per CTA (= targets per work item) and TILE records per shared-memory tile are
+// chosen on the host from the leaf-size distribution: small leaves (ncrit ~ 64) would leave
+// most lanes of a 128-thread CTA idle.
+template <int K, int NT, int TILE>
+__global__ void __launch_bounds__(NT) uj_leaf_kernel(const LeafUjArgs a) {
+  __shared__ __align__(128) double tiles[kStages][TILE * kRec];
   __shared__ __align__(8) uint64_t full[kStages];
   __shared__ __align__(16) double2 gtab[K == K_GERF ? kGerfIntervals * kGerfCoeffs / 2 : 1];
   if constexpr (K == K_GERF) load_gerf_table(gtab);  // visible after the __syncthreads below
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(kThreads) uj_leaf_kernel(const LeafUjArgs a) {
   const int leaf = a.csr.wi_leaf[blockIdx.x];
   const int64_t tb = a.csr.tleaf_begin[leaf] + a.csr.wi_off[blockIdx.x];
   int64_t te = a.csr.tleaf_end[leaf];
-  if (te > tb + kThreads) te = tb + kThreads;
+  if (te > tb + NT) te = tb + NT;
   const int64_t i = tb + tid;
   const bool valid = i < te;
   const double *p = a.tpos + (valid ? i : te - 1) * a.tld;
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(kThreads) uj_leaf_kernel(const LeafUjArgs a) {
   int issued = 0;
   auto issue = [&]() {
     int64_t first;
-    int n = prod.next(a.csr, first);
+    int n = prod.next(a.csr, first, TILE);
     if (n == 0) return;
     uint32_t bytes = (uint32_t)n * kRec * sizeof(double);
     int st = issued % kStages;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(kThreads) uj_leaf_kernel(const LeafUjArgs a) {
 
   for (int it = 0;; ++it) {
     int64_t first;
-    const int n = cons.next(a.csr, first);
+    const int n = cons.next(a.csr, first, TILE);
     if (n == 0) break;
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
@@ -143,15 +146,15 @@ struct LeafSfsArgs {
   int shortcut;
 };
 
-template <int K>
-__global__ void __launch_bounds__(kThreads) sfs_leaf_kernel(const LeafSfsArgs a) {
-  __shared__ __align__(128) double tiles[kStages][kTile * kSfsRec];
+template <int K, int NT, int TILE>
+__global__ void __launch_bounds__(NT) sfs_leaf_kernel(const LeafSfsArgs a) {
+  __shared__ __align__(128) double tiles[kStages][TILE * kSfsRec];
   __shared__ __align__(8) uint64_t full[kStages];
   const int tid = threadIdx.x;
   const int leaf = a.csr.wi_leaf[blockIdx.x];
   const int64_t tb = a.csr.tleaf_begin[leaf] + a.csr.wi_off[blockIdx.x];
   int64_t te = a.csr.tleaf_end[leaf];
-  if (te > tb + kThreads) te = tb + kThreads;
+  if (te > tb + NT) te = tb + NT;
   const int64_t i = tb + tid;
   const bool valid = i < te;
   const int64_t c = a.tindex[valid ? i : te - 1];
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) sfs_leaf_kernel(const LeafSfsArgs a)
   int issued = 0;
   auto issue = [&]() {
     int64_t first;
-    int n = prod.next(a.csr, first);
+    int n = prod.next(a.csr, first, TILE);
     if (n == 0) return;
     uint32_t bytes = (uint32_t)n * kSfsRec * sizeof(double);
     int st = issued % kStages;
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(kThreads) sfs_leaf_kernel(const LeafSfsArgs a)
 
   for (int it = 0;; ++it) {
     int64_t first;
-    const int n = cons.next(a.csr, first);
+    const int n = cons.next(a.csr, first, TILE);
     if (n == 0) break;
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
