@@ -1144,40 +1144,78 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
   HostCsr c;
   TRY(build_csr(h, fn, tb, te, ntl, n_tgt, sb, se, nsl, n_src, pt, ps, npairs, c));
   if (c.wi_leaf.empty()) return VPM_OK;
-  Dev &d = h->devs[0];
-  cudaStream_t st = d.stream;
   h->launches = 0;
-  CK(h, cudaSetDevice(d.id));
-  TRY(ensure(h, d.tbuf, (size_t)n_tgt * ld * sizeof(double)));
-  TRY(ensure(h, d.sbuf, (size_t)n_src * 8 * sizeof(double)));
+  const int64_t nwi = (int64_t)c.wi_leaf.size();
+  // Multi-GPU: target leaves are sharded into G contiguous runs of work items
+  // with balanced  sum nt*ns ; sources are replicated by the host upload.  Needs the leaves
+  // in increasing, non-overlapping body order (tree-sorted buffers) so that a device's
+  // targets are one contiguous column range; otherwise device 0 does everything.
+  int G = (int)h->devs.size();
+  for (int64_t l = 0; l + 1 < ntl && G > 1; ++l)
+    if (tb[l + 1] < te[l]) G = 1;
+  std::vector<int64_t> cut(G + 1, nwi);
+  cut[0] = 0;
+  if (G > 1) {
+    std::vector<double> w((size_t)nwi + 1, 0.0);
+    std::vector<int64_t> srcw((size_t)ntl, 0);
+    for (int64_t k = 0; k < npairs; ++k) srcw[(size_t)pt[k]] += se[ps[k]] - sb[ps[k]];
+    for (int64_t k = 0; k < nwi; ++k) {
+      const int l = c.wi_leaf[(size_t)k];
+      const int64_t cnt = std::min<int64_t>(c.nt, te[l] - tb[l] - c.wi_off[(size_t)k]);
+      w[(size_t)k + 1] = w[(size_t)k] + (double)cnt * (double)srcw[(size_t)l];
+    }
+    for (int g = 1; g < G; ++g)
+      cut[g] = std::lower_bound(w.begin(), w.end(), w[(size_t)nwi] * g / G) - w.begin();
+  }
   const int64_t ns_pad = round_up(n_src, kTile);
-  TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
-  CK(h, cudaEventRecord(d.ev[0], st));
-  CK(h, cudaMemcpyAsync(d.tbuf.p, tgt, (size_t)n_tgt * ld * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(h, cudaMemcpyAsync(d.sbuf.p, src, (size_t)n_src * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
-  LeafUjArgs a;
-  const int64_t *dts, *dss;
-  TRY(upload_csr(h, d, st, c, tb, te, ntl, sb, se, nsl, nullptr, 0, nullptr, 0, a.csr, dts, dss));
-  CK(h, cudaEventRecord(d.ev[1], st));
-  SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
-  prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (double *)d.rec.p);
-  h->launches++;
-  a.tpos = (const double *)d.tbuf.p + row_pos; a.tld = ld; a.rec = (const double *)d.rec.p;
-  a.out = (double *)d.tbuf.p; a.urow = row_grad; a.jrow = row_hess; a.want_U = want_U; a.want_J = want_J;
-  a.shortcut = 1;
-  const unsigned nwi = (unsigned)c.wi_leaf.size();
-  launch_uj_leaf(kernel, c.nt, nwi, a, st);
-  h->launches++;
-  CK(h, cudaGetLastError());
-  CK(h, cudaEventRecord(d.ev[2], st));
-  CK(h, cudaEventRecord(d.ev[3], st));
-  CK(h, cudaEventRecord(d.ev[4], st));
-  CK(h, cudaMemcpyAsync(tgt, d.tbuf.p, (size_t)n_tgt * ld * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(h, cudaEventRecord(d.ev[5], st));
-  CK(h, cudaStreamSynchronize(st));
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    cudaStream_t st = d.stream;
+    const int64_t k0 = cut[g], k1 = cut[g + 1];
+    if (k1 <= k0) continue;
+    CK(h, cudaSetDevice(d.id));
+    TRY(ensure(h, d.tbuf, (size_t)n_tgt * ld * sizeof(double)));
+    TRY(ensure(h, d.sbuf, (size_t)n_src * 8 * sizeof(double)));
+    TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
+    if (g == 0) CK(h, cudaEventRecord(d.ev[0], st));
+    // this device's target columns: first target of its first item .. last target of its last
+    const int lf = c.wi_leaf[(size_t)k0], ll = c.wi_leaf[(size_t)k1 - 1];
+    const int64_t col0 = G == 1 ? 0 : tb[lf] + c.wi_off[(size_t)k0];
+    const int64_t col1 = G == 1 ? n_tgt : std::min<int64_t>(te[ll], tb[ll] + c.wi_off[(size_t)k1 - 1] + c.nt);
+    CK(h, cudaMemcpyAsync((double *)d.tbuf.p + col0 * ld, tgt + col0 * ld, (size_t)(col1 - col0) * ld * sizeof(double),
+                          cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(d.sbuf.p, src, (size_t)n_src * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+    LeafUjArgs a;
+    const int64_t *dts, *dss;
+    TRY(upload_csr(h, d, st, c, tb, te, ntl, sb, se, nsl, nullptr, 0, nullptr, 0, a.csr, dts, dss));
+    a.csr.wi_leaf += k0;
+    a.csr.wi_off += k0;
+    if (g == 0) CK(h, cudaEventRecord(d.ev[1], st));
+    SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
+    prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (double *)d.rec.p);
+    h->launches++;
+    a.tpos = (const double *)d.tbuf.p + row_pos; a.tld = ld; a.rec = (const double *)d.rec.p;
+    a.out = (double *)d.tbuf.p; a.urow = row_grad; a.jrow = row_hess; a.want_U = want_U; a.want_J = want_J;
+    a.shortcut = 1;
+    launch_uj_leaf(kernel, c.nt, (unsigned)(k1 - k0), a, st);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    if (g == 0) {
+      CK(h, cudaEventRecord(d.ev[2], st));
+      CK(h, cudaEventRecord(d.ev[3], st));
+      CK(h, cudaEventRecord(d.ev[4], st));
+    }
+    CK(h, cudaMemcpyAsync(tgt + col0 * ld, (double *)d.tbuf.p + col0 * ld, (size_t)(col1 - col0) * ld * sizeof(double),
+                          cudaMemcpyDeviceToHost, st));
+    if (g == 0) CK(h, cudaEventRecord(d.ev[5], st));
+  }
+  for (int g = G - 1; g >= 0; --g) {
+    CK(h, cudaSetDevice(h->devs[g].id));
+    CK(h, cudaStreamSynchronize(h->devs[g].stream));
+  }
   h->timing.uj_pairs = count_pairs(tb, te, sb, se, pt, ps, npairs);
   h->timing.sfs_pairs = 0;
-  h1_fill_timing(h, d);
+  h1_fill_timing(h, h->devs[0]);
   h->np_resident = -1;
   return VPM_OK;
 }

@@ -93,3 +93,28 @@ def test_one_process_per_gpu_sharding(vpm, tmp_path):
     assert relerr(uj[0:3], ref[9:12, :n]) < TOL_FP64
     assert relerr(uj[3:12], ref[15:24, :n]) < TOL_FP64
     assert relerr(sfs, ref[39:42, :n]) < TOL_FP64
+
+
+@pytest.mark.parametrize("ncrit", [24, 300])
+def test_nearfield_leafpairs_multi_gpu(vpm, ncrit):
+    """Hook 3 with target leaves sharded over the devices of one handle"""
+    g = _ngpu()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    h = vpm.Handle(min(g, 4))
+    try:
+        pf = vpm.fields.cloud_field(6000, kernel=vpm.gaussianerf, seed=21)
+        ll = vpm.fields.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=ncrit, theta=0.4)
+        order = ll["sort_index"]
+        sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
+        rng = np.random.default_rng(1)
+        tb = np.asfortranarray(rng.standard_normal((16, pf.np)) * 1e-3)   # accumulate on previous values
+        tb[0:3] = pf.get_X()[:, order]
+        leaves = (ll["leaf_begin"], ll["leaf_end"])
+        ref = tb.copy(order="F")
+        oracle.direct_leafpairs(ref, sb, leaves, leaves, ll["direct_list"], "gaussianerf")
+        vpm.nearfield_device(tb, leaves, sb, leaves, ll["direct_list"], vpm.gaussianerf, handle=h)
+        assert relerr(tb[4:7], ref[4:7]) < TOL_FP64 and relerr(tb[7:16], ref[7:16]) < TOL_FP64
+        assert np.array_equal(tb[0:4], ref[0:4])
+    finally:
+        h.close()
