@@ -162,6 +162,67 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def rvpm_step_c2(vpm, h):
+    """BASELINE.json configs[1]: two leapfrogging rings (test/runtests_leapfrog.jl:42-46 geometry,
+    nc=6 -> 33 800 particles), RK3 + reformulated VPM (f=0, g=1/5) + SFS + Pedrizzetti relaxation.
+    The O(N) stage updates run on the host (numpy restatement in tests/physics.py -- in production
+    they stay in the reference's Julia code); every UJ / SFS evaluation is a host-API call to the
+    GPU, so this is the end-to-end time of one time step as the reference would see it."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import physics
+    R = 0.7906
+    pf = vpm.fields.ring_field(Nphi=100, nc=6, R=R, Rcross=0.1 * R, rings=2, dZ=0.7906, kernel=vpm.gaussianerf)
+    pf.particles[36, :pf.np] = 1.0  # constant SFS coefficient
+    P = pf.particles
+    h.check(h.lib.vpm_pin_host(h.ptr, P.ctypes.data, P.nbytes))
+    gpu_ms = [0.0]
+
+    def UJ(pfield, **kw):
+        vpm.UJ_direct(pfield, **kw)
+        gpu_ms[0] += h.timing()["total_ms"]
+
+    dt = 1e-3
+    zeta0 = 1.0 / (2 * np.pi) ** 1.5
+    physics.rk3_step(pf, dt, UJ, f=0.0, g=0.2, relax=True, sfs=True, zeta0=zeta0)
+    gpu_ms[0] = 0.0
+    k = 3
+    t = time.perf_counter()
+    for _ in range(k):
+        physics.rk3_step(pf, dt, UJ, f=0.0, g=0.2, relax=True, sfs=True, zeta0=zeta0)
+    wall = (time.perf_counter() - t) / k
+    h.check(h.lib.vpm_unpin_host(h.ptr, P.ctypes.data))
+    return {"n_particles": pf.np, "kernel": "gaussianerf", "ms_per_step": wall * 1e3, "gpu_ms_per_step": gpu_ms[0] / k,
+            "what": "3 x (U/J + SFS) + 1 x U/J (relaxation) through UJ_direct(pfield) with host buffers; "
+                    "O(N) RK3/rVPM/relaxation updates on the host in numpy; constant SFS coefficient "
+                    "(the dynamic procedure adds one more U/J + SFS call per step)"}
+
+
+def nearfield_extra(vpm, h, n):
+    """FMM near-field hook (BASELINE.json configs[4] shape at this N): uniform-octree leaves,
+    theta = 0.4 near-field list, one vpm_p2p_leafpairs call from host buffers."""
+    out = {}
+    pf = vpm.fields.cloud_field(n, kernel=vpm.winckelmans)
+    for ncrit in (128, 1024):
+        ll = vpm.fields.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=ncrit, theta=0.4)
+        order = ll["sort_index"]
+        sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
+        tb = np.zeros((16, n), order="F")
+        tb[0:3] = pf.get_X()[:, order]
+        leaves = (ll["leaf_begin"], ll["leaf_end"])
+        sizes = ll["leaf_end"] - ll["leaf_begin"]
+        dl = ll["direct_list"]
+        pairs = int((sizes[dl[:, 0]].astype(np.int64) * sizes[dl[:, 1]]).sum())
+        vpm.nearfield_device(tb, leaves, sb, leaves, dl, vpm.winckelmans)
+        t = time.perf_counter()
+        vpm.nearfield_device(tb, leaves, sb, leaves, dl, vpm.winckelmans)
+        dt = time.perf_counter() - t
+        tm = h.timing()
+        out[f"ncrit_{ncrit}"] = {"leaves": int(len(sizes)), "mean_leaf": float(sizes.mean()), "list_pairs": int(len(dl)),
+                                 "interactions": pairs, "kernel_interactions_per_s": pairs / (tm["uj_ms"] * 1e-3),
+                                 "e2e_interactions_per_s": pairs / dt}
+    return out
+
+
 # ------------------------------------------------------------------ B200 arm
 def main():
     args = parse()
@@ -331,6 +392,8 @@ def main():
         uj_ms = ms_per_step
         extras["rvpm_step_ms_estimate"] = {"value": 5 * uj_ms + 4 * extras["sfs"]["ms"],
                                            "what": "5 U/J + 4 SFS sweeps (RK3 + DynamicSFS + relaxation, SURVEY 3.1), O(N) host work excluded"}
+        extras["rvpm_step_c2"] = rvpm_step_c2(vpm, h)
+        extras["fmm_nearfield"] = nearfield_extra(vpm, h, n)
         line["extras"] = extras
         v, desc, cores = cpu_sample(n, args.kernel, args.cpu_seconds)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -17,6 +17,7 @@ SYMBOLS = [
     "vpm_upload_state", "vpm_eval", "vpm_download_results",
     "vpm_pin_host", "vpm_unpin_host",
     "vpm_p2p_buffers", "vpm_p2p_leafpairs", "vpm_estr_leafpairs",
+    "vpm_zeta_direct", "vpm_zeta_leafpairs",
     "vpm_uj_device", "vpm_sfs_device",
     "vpm_get_timing", "vpm_measure_dfma_peak", "vpm_test_math",
 ]
@@ -71,6 +72,8 @@ def load():
     lib.vpm_p2p_leafpairs.argtypes = [p, p, i64, i64, i32, i32, i32, p, i64, p, p, i64, p, p, i64,
                                       p, p, i64, i32, i32, i32]
     lib.vpm_estr_leafpairs.argtypes = [p, p, i64, i64, p, p, p, p, i64, p, p, i64, p, p, i64, i32, i32]
+    lib.vpm_zeta_direct.argtypes = [p, p, i64, i64, i32]
+    lib.vpm_zeta_leafpairs.argtypes = [p, p, i64, i64, p, p, p, i64, p, p, i64, i32]
     lib.vpm_uj_device.argtypes = [p, p, i64, i64, i64, p, i32, i32, p]
     lib.vpm_sfs_device.argtypes = [p, p, p, p, i64, i64, i64, p, i32, i32, p]
     lib.vpm_get_timing.argtypes = [p, P(VpmTiming)]

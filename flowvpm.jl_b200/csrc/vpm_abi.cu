@@ -188,16 +188,21 @@ void launch_uj(int kernel, const Plan &p, const UjArgs &a, cudaStream_t st) {
   }
 }
 template <int K>
-void launch_sfs_T(const Plan &p, const SfsArgs &a, cudaStream_t st) {
-  if (p.T == 2) sfs_pairs_kernel<K, 2><<<p.grid, kThreads, 0, st>>>(a);
-  else sfs_pairs_kernel<K, 1><<<p.grid, kThreads, 0, st>>>(a);
+void launch_sfs_T(const Plan &p, const SfsArgs &a, cudaStream_t st, int mode) {
+  if (mode == MODE_ZETA) {
+    if (p.T == 2) sfs_pairs_kernel<K, 2, MODE_ZETA><<<p.grid, kThreads, 0, st>>>(a);
+    else sfs_pairs_kernel<K, 1, MODE_ZETA><<<p.grid, kThreads, 0, st>>>(a);
+  } else {
+    if (p.T == 2) sfs_pairs_kernel<K, 2, MODE_SFS><<<p.grid, kThreads, 0, st>>>(a);
+    else sfs_pairs_kernel<K, 1, MODE_SFS><<<p.grid, kThreads, 0, st>>>(a);
+  }
 }
-void launch_sfs(int kernel, const Plan &p, const SfsArgs &a, cudaStream_t st) {
+void launch_sfs(int kernel, const Plan &p, const SfsArgs &a, cudaStream_t st, int mode = MODE_SFS) {
   switch (kernel) {
-    case K_SING: launch_sfs_T<K_SING>(p, a, st); break;
-    case K_GAUS: launch_sfs_T<K_GAUS>(p, a, st); break;
-    case K_GERF: launch_sfs_T<K_GERF>(p, a, st); break;
-    default: launch_sfs_T<K_WINCK>(p, a, st); break;
+    case K_SING: launch_sfs_T<K_SING>(p, a, st, mode); break;
+    case K_GAUS: launch_sfs_T<K_GAUS>(p, a, st, mode); break;
+    case K_GERF: launch_sfs_T<K_GERF>(p, a, st, mode); break;
+    default: launch_sfs_T<K_WINCK>(p, a, st, mode); break;
   }
 }
 
@@ -254,7 +259,8 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
 int sfs_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *tpos, int64_t tld,
               const double *tJ, int64_t jld, const int64_t *tindex, int64_t nt, SrcView src,
               const double *sJ, int64_t sjld, int sjoff, const double *stat, int64_t sld,
-              const int64_t *sindex, int64_t ns, int flags, Plan &plan, bool time_pairs = false) {
+              const int64_t *sindex, int64_t ns, int flags, Plan &plan, bool time_pairs = false,
+              int mode = MODE_SFS) {
   const int64_t ns_pad = round_up(std::max<int64_t>(ns, 1), kTile);
   TRY(ensure(h, d.srec, (size_t)ns_pad * kSfsRec * sizeof(double)));
   plan = make_plan(nt, ns, d.sm_count, PLAN_SFS);
@@ -273,7 +279,7 @@ int sfs_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *
     a.transposed = transposed;
     a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
     if (time_pairs) CK(h, cudaEventRecord(d.ev[6], st));
-    launch_sfs(kernel, plan, a, st);
+    launch_sfs(kernel, plan, a, st, mode);
     if (time_pairs) CK(h, cudaEventRecord(d.ev[7], st));
     h->launches++;
   } else {
@@ -625,15 +631,21 @@ int build_csr(vpm_handle *h, const char *fn, const int64_t *tb, const int64_t *t
     if (sb[l] < 0 || se[l] < sb[l] || se[l] > n_src)
       return fail(h, VPM_EINVAL, "%s: source leaf %lld range [%lld,%lld) outside 0..%lld", fn, (long long)l, (long long)sb[l], (long long)se[l], (long long)n_src);
   c.ptr.assign((size_t)ntl + 1, 0);
+  bool sorted = true;  // a list already grouped by target leaf needs no scatter
   for (int64_t k = 0; k < npairs; ++k) {
     if (pt[k] < 0 || pt[k] >= ntl || ps[k] < 0 || ps[k] >= nsl)
       return fail(h, VPM_EINVAL, "%s: pair %lld = (%d,%d) outside the leaf tables", fn, (long long)k, pt[k], ps[k]);
     c.ptr[(size_t)pt[k] + 1]++;
+    sorted = sorted && (k == 0 || pt[k] >= pt[k - 1]);
   }
   for (int64_t l = 0; l < ntl; ++l) c.ptr[(size_t)l + 1] += c.ptr[(size_t)l];
-  c.src.resize((size_t)npairs);
-  std::vector<int64_t> cur(c.ptr.begin(), c.ptr.end() - 1);
-  for (int64_t k = 0; k < npairs; ++k) c.src[(size_t)cur[(size_t)pt[k]]++] = ps[k];  // stable
+  if (sorted) {
+    c.src.assign(ps, ps + npairs);
+  } else {
+    c.src.resize((size_t)npairs);
+    std::vector<int64_t> cur(c.ptr.begin(), c.ptr.end() - 1);
+    for (int64_t k = 0; k < npairs; ++k) c.src[(size_t)cur[(size_t)pt[k]]++] = ps[k];  // stable
+  }
   // CTA width: minimise the padded lane-work  sum_leaf ceil(size/NT)*NT * (its source bodies)
   std::vector<int64_t> srcw((size_t)ntl, 0);
   for (int64_t k = 0; k < npairs; ++k) srcw[(size_t)pt[k]] += se[ps[k]] - sb[ps[k]];
@@ -722,19 +734,25 @@ void launch_uj_leaf(int kernel, int nt, unsigned nwi, const LeafUjArgs &a, cudaS
     default: launch_uj_leaf_K<K_WINCK>(nt, nwi, a, st); break;
   }
 }
-template <int K>
+template <int K, int MODE>
 void launch_sfs_leaf_K(int nt, unsigned nwi, const LeafSfsArgs &a, cudaStream_t st) {
-  if (nt == 32) sfs_leaf_kernel<K, 32, 64><<<nwi, 32, 0, st>>>(a);
-  else if (nt == 64) sfs_leaf_kernel<K, 64, 64><<<nwi, 64, 0, st>>>(a);
-  else sfs_leaf_kernel<K, 128, 128><<<nwi, 128, 0, st>>>(a);
+  if (nt == 32) sfs_leaf_kernel<K, 32, 64, MODE><<<nwi, 32, 0, st>>>(a);
+  else if (nt == 64) sfs_leaf_kernel<K, 64, 64, MODE><<<nwi, 64, 0, st>>>(a);
+  else sfs_leaf_kernel<K, 128, 128, MODE><<<nwi, 128, 0, st>>>(a);
 }
-void launch_sfs_leaf(int kernel, int nt, unsigned nwi, const LeafSfsArgs &a, cudaStream_t st) {
+template <int MODE>
+void launch_sfs_leaf_M(int kernel, int nt, unsigned nwi, const LeafSfsArgs &a, cudaStream_t st) {
   switch (kernel) {
-    case K_SING: launch_sfs_leaf_K<K_SING>(nt, nwi, a, st); break;
-    case K_GAUS: launch_sfs_leaf_K<K_GAUS>(nt, nwi, a, st); break;
-    case K_GERF: launch_sfs_leaf_K<K_GERF>(nt, nwi, a, st); break;
-    default: launch_sfs_leaf_K<K_WINCK>(nt, nwi, a, st); break;
+    case K_SING: launch_sfs_leaf_K<K_SING, MODE>(nt, nwi, a, st); break;
+    case K_GAUS: launch_sfs_leaf_K<K_GAUS, MODE>(nt, nwi, a, st); break;
+    case K_GERF: launch_sfs_leaf_K<K_GERF, MODE>(nt, nwi, a, st); break;
+    default: launch_sfs_leaf_K<K_WINCK, MODE>(nt, nwi, a, st); break;
   }
+}
+void launch_sfs_leaf(int kernel, int nt, unsigned nwi, const LeafSfsArgs &a, cudaStream_t st,
+                     int mode = MODE_SFS) {
+  if (mode == MODE_ZETA) launch_sfs_leaf_M<MODE_ZETA>(kernel, nt, nwi, a, st);
+  else launch_sfs_leaf_M<MODE_SFS>(kernel, nt, nwi, a, st);
 }
 
 int64_t count_pairs(const int64_t *tb, const int64_t *te, const int64_t *sb, const int64_t *se,
@@ -1220,11 +1238,10 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
   return VPM_OK;
 }
 
-int vpm_estr_leafpairs(vpm_handle *h, double *P, int64_t nf, int64_t np, const int64_t *tsort,
-                       const int64_t *ssort, const int64_t *tb, const int64_t *te, int64_t ntl,
-                       const int64_t *sb, const int64_t *se, int64_t nsl, const int32_t *pt,
-                       const int32_t *ps, int64_t npairs, int kernel, int flags) {
-  const char *fn = "vpm_estr_leafpairs";
+static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, int64_t nf, int64_t np,
+                           const int64_t *tsort, const int64_t *ssort, const int64_t *tb, const int64_t *te,
+                           int64_t ntl, const int64_t *sb, const int64_t *se, int64_t nsl, const int32_t *pt,
+                           const int32_t *ps, int64_t npairs, int kernel, int flags) {
   TRY(check_field(h, fn, P, nf, np, kernel));
   if (ntl < 0 || nsl < 0 || npairs < 0) return fail(h, VPM_EINVAL, "%s: negative size", fn);
   if (npairs == 0 || np == 0) return VPM_OK;
@@ -1249,7 +1266,8 @@ int vpm_estr_leafpairs(vpm_handle *h, double *P, int64_t nf, int64_t np, const i
                           (size_t)np, cudaMemcpyHostToDevice, st));
   CK(h, cudaMemcpy2DAsync(d.jbuf.p, 9 * sizeof(double), P + R_J, nf * sizeof(double), 9 * sizeof(double),
                           (size_t)np, cudaMemcpyHostToDevice, st));
-  CK(h, cudaMemcpy2DAsync(d.sfs3.p, 3 * sizeof(double), P + R_SFS, nf * sizeof(double), 3 * sizeof(double),
+  const int out_row = mode == MODE_ZETA ? R_J : R_SFS;
+  CK(h, cudaMemcpy2DAsync(d.sfs3.p, 3 * sizeof(double), P + out_row, nf * sizeof(double), 3 * sizeof(double),
                           (size_t)np, cudaMemcpyHostToDevice, st));
   LeafSfsArgs a;
   const int64_t *dts, *dss;
@@ -1268,16 +1286,76 @@ int vpm_estr_leafpairs(vpm_handle *h, double *P, int64_t nf, int64_t np, const i
   a.transposed = transposed;
   a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
   const unsigned nwi = (unsigned)c.wi_leaf.size();
-  launch_sfs_leaf(kernel, c.nt, nwi, a, st);
+  launch_sfs_leaf(kernel, c.nt, nwi, a, st, mode);
   h->launches++;
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(d.ev[4], st));
-  CK(h, cudaMemcpy2DAsync(P + R_SFS, nf * sizeof(double), d.sfs3.p, 3 * sizeof(double), 3 * sizeof(double),
+  CK(h, cudaMemcpy2DAsync(P + out_row, nf * sizeof(double), d.sfs3.p, 3 * sizeof(double), 3 * sizeof(double),
                           (size_t)np, cudaMemcpyDeviceToHost, st));
   CK(h, cudaEventRecord(d.ev[5], st));
   CK(h, cudaStreamSynchronize(st));
   h->timing.uj_pairs = 0;
   h->timing.sfs_pairs = count_pairs(tb, te, sb, se, pt, ps, npairs);
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+
+int vpm_estr_leafpairs(vpm_handle *h, double *P, int64_t nf, int64_t np, const int64_t *tsort,
+                       const int64_t *ssort, const int64_t *tb, const int64_t *te, int64_t ntl,
+                       const int64_t *sb, const int64_t *se, int64_t nsl, const int32_t *pt,
+                       const int32_t *ps, int64_t npairs, int kernel, int flags) {
+  return leafpairs_field(h, "vpm_estr_leafpairs", MODE_SFS, P, nf, np, tsort, ssort, tb, te, ntl, sb, se, nsl, pt,
+                         ps, npairs, kernel, flags);
+}
+
+int vpm_zeta_leafpairs(vpm_handle *h, double *P, int64_t nf, int64_t np, const int64_t *sort_index,
+                       const int64_t *lb, const int64_t *le, int64_t nl, const int32_t *pair_a,
+                       const int32_t *pair_b, int64_t npairs, int kernel) {
+  // zeta_fmm (src/FLOWVPM_viscous.jl:523-558): for a list entry (a, b) the bodies of leaf b
+  // RECEIVE Gamma_j zeta_j from the bodies j of leaf a -> receivers are indexed by the second
+  // element, givers by the first.
+  return leafpairs_field(h, "vpm_zeta_leafpairs", MODE_ZETA, P, nf, np, sort_index, sort_index, lb, le, nl, lb, le,
+                         nl, pair_b, pair_a, npairs, kernel, 0);
+}
+
+int vpm_zeta_direct(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel) {
+  TRY(check_field(h, "vpm_zeta_direct", P, nf, np, kernel));
+  if (np == 0) return VPM_OK;
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  TRY(ensure(h, d.in7, ((size_t)np * 7 + 16) * sizeof(double)));
+  TRY(ensure(h, d.sfs3, (size_t)np * 3 * sizeof(double)));
+  CK(h, cudaEventRecord(d.ev[0], st));
+  CK(h, cudaMemcpy2DAsync(d.in7.p, 7 * sizeof(double), P, nf * sizeof(double), 7 * sizeof(double), (size_t)np,
+                          cudaMemcpyHostToDevice, st));
+  CK(h, cudaEventRecord(d.ev[1], st));
+  CK(h, cudaEventRecord(d.ev[2], st));
+  CK(h, cudaEventRecord(d.ev[3], st));
+  SrcView src{(const double *)d.in7.p, 7, 0, 3, 6};
+  Plan sp;
+  // the J operand is unused in zeta mode: the record builder reads 9 doubles per source
+  // from it, so point it at in7 (stride 7; the allocation has 16 doubles of slack)
+  TRY(sfs_sweep(h, d, st, kernel, (const double *)d.in7.p, 7, (const double *)d.in7.p, 7, nullptr, np, src,
+                (const double *)d.in7.p, 7, 0, nullptr, 1, nullptr, np, VPM_FLAG_TRANSPOSED, sp, false, MODE_ZETA));
+  SfsFinishArgs f;
+  f.partial = (const double *)d.partial.p; f.pstride = sp.pstride; f.nsplit = sp.nsplit;
+  f.nt = np; f.tindex = nullptr; f.out = (double *)d.sfs3.p; f.ld = 3; f.row = 0;
+  f.accumulate = 0; f.reset = 0;  // zeta_direct zeroes J[1:3] of every particle first (:487-489)
+  f.filter_static = 0; f.stat = nullptr; f.sld = 1;
+  sfs_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(f);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(d.ev[4], st));
+  CK(h, cudaMemcpy2DAsync(P + R_J, nf * sizeof(double), d.sfs3.p, 3 * sizeof(double), 3 * sizeof(double),
+                          (size_t)np, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaEventRecord(d.ev[5], st));
+  CK(h, cudaStreamSynchronize(st));
+  h->timing.uj_pairs = 0;
+  h->timing.sfs_pairs = np * np;
   h1_fill_timing(h, d);
   h->np_resident = -1;
   return VPM_OK;

@@ -597,7 +597,10 @@ __global__ void uj_finish_kernel(const UjFinishArgs a) {
 
 // --------------------------------------------------------------- SFS pair sweep
 // One tile of SFS source records against the T targets of this thread.
-template <int K, int T>
+// MODE 0: SFS stretching term (Estr_direct).  MODE 1: basis-function sum
+// acc += zeta(r/sigma_s)/sigma_s^3 * Gamma_s  (zeta_direct, src/FLOWVPM_viscous.jl:488-515).
+constexpr int MODE_SFS = 0, MODE_ZETA = 1;
+template <int K, int T, int MODE = MODE_SFS>
 __device__ __forceinline__ void sfs_tile(const double2 *__restrict__ tile, int n,
                                          const double (&tx)[T], const double (&ty)[T],
                                          const double (&tz)[T], const double (&JT)[T][9],
@@ -623,6 +626,16 @@ __device__ __forceinline__ void sfs_tile(const double2 *__restrict__ tile, int n
     const double2 v2 = tile[j * 9 + 2];
     const double2 v3 = tile[j * 9 + 3];
     const double gx = v2.x, gy = v2.y, gz = v3.x, q1 = v3.y;
+    if constexpr (MODE == MODE_ZETA) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        double w = sfs_weight<K>(r2[t], q0, q1);
+        acc[t][0] = fma(w, gx, acc[t][0]);
+        acc[t][1] = fma(w, gy, acc[t][1]);
+        acc[t][2] = fma(w, gz, acc[t][2]);
+      }
+      continue;
+    }
     const double2 j0 = tile[j * 9 + 4], j1 = tile[j * 9 + 5], j2 = tile[j * 9 + 6],
                   j3 = tile[j * 9 + 7], j4 = tile[j * 9 + 8];
     const double JS[9] = {j0.x, j0.y, j1.x, j1.y, j2.x, j2.y, j3.x, j3.y, j4.x};
@@ -662,7 +675,7 @@ struct SfsArgs {
   int shortcut;
 };
 
-template <int K, int T>
+template <int K, int T, int MODE = MODE_SFS>
 __global__ void __launch_bounds__(kThreads) sfs_pairs_kernel(const SfsArgs a) {
   __shared__ __align__(128) double tiles[kStages][kTile * kSfsRec];
   __shared__ __align__(8) uint64_t full[kStages];
@@ -678,12 +691,18 @@ __global__ void __launch_bounds__(kThreads) sfs_pairs_kernel(const SfsArgs a) {
     int64_t c = a.tindex ? a.tindex[i] : i;
     const double *p = a.tpos + c * a.tld;
     tx[t] = p[0]; ty[t] = p[1]; tz[t] = p[2];
-    const double *j = a.tJ + c * a.jld;
     // same row-of-3 order as the source records (see prep_sfs_records)
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int m = 0; m < 3; ++m) JT[t][3 * k + m] = a.transposed ? j[3 * k + m] : j[k + 3 * m];
+      for (int m = 0; m < 3; ++m) {
+        if constexpr (MODE == MODE_SFS) {
+          const double *j = a.tJ + c * a.jld;
+          JT[t][3 * k + m] = a.transposed ? j[3 * k + m] : j[k + 3 * m];
+        } else {
+          JT[t][3 * k + m] = 0.0;
+        }
+      }
     acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
   }
 
@@ -719,7 +738,7 @@ __global__ void __launch_bounds__(kThreads) sfs_pairs_kernel(const SfsArgs a) {
     const int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
     const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
 
-    sfs_tile<K, T>(tile, n, tx, ty, tz, JT, acc, a.shortcut);
+    sfs_tile<K, T, MODE>(tile, n, tx, ty, tz, JT, acc, a.shortcut);
     __syncthreads();
     if (tid == 0 && it + kStages < ntl) issue(it + kStages);
   }

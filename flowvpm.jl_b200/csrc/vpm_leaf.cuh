@@ -146,7 +146,7 @@ struct LeafSfsArgs {
   int shortcut;
 };
 
-template <int K, int NT, int TILE>
+template <int K, int NT, int TILE, int MODE = MODE_SFS>
 __global__ void __launch_bounds__(NT) sfs_leaf_kernel(const LeafSfsArgs a) {
   __shared__ __align__(128) double tiles[kStages][TILE * kSfsRec];
   __shared__ __align__(8) uint64_t full[kStages];
@@ -161,11 +161,17 @@ __global__ void __launch_bounds__(NT) sfs_leaf_kernel(const LeafSfsArgs a) {
   const double *p = a.tpos + c * a.tld;
   double tx[1] = {p[0]}, ty[1] = {p[1]}, tz[1] = {p[2]};
   double JT[1][9], acc[1][3] = {{0.0, 0.0, 0.0}};
-  const double *j = a.tJ + c * a.jld;
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
-    for (int m = 0; m < 3; ++m) JT[0][3 * k + m] = a.transposed ? j[3 * k + m] : j[k + 3 * m];
+    for (int m = 0; m < 3; ++m) {
+      if constexpr (MODE == MODE_SFS) {
+        const double *j = a.tJ + c * a.jld;
+        JT[0][3 * k + m] = a.transposed ? j[3 * k + m] : j[k + 3 * m];
+      } else {
+        JT[0][3 * k + m] = 0.0;
+      }
+    }
 
   if (tid == 0) {
 #pragma unroll
@@ -197,8 +203,8 @@ __global__ void __launch_bounds__(NT) sfs_leaf_kernel(const LeafSfsArgs a) {
     if (n == 0) break;
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
-    sfs_tile<K, 1>(reinterpret_cast<const double2 *>(&tiles[st][0]), n, tx, ty, tz, JT, acc,
-                   a.shortcut);
+    sfs_tile<K, 1, MODE>(reinterpret_cast<const double2 *>(&tiles[st][0]), n, tx, ty, tz, JT, acc,
+                         a.shortcut);
     __syncthreads();
     if (tid == 0) issue();
   }

@@ -156,6 +156,30 @@ def Estr_fmm(pfield, target_sort_index, source_sort_index, target_leaves, source
         pt.ctypes.data, ps.ctypes.data, len(pt), pfield.kernel.id, flags))
 
 
+def zeta_direct(pfield, *, handle=None):
+    """zeta_direct(pfield) -- src/FLOWVPM_viscous.jl:488-515: J[1:3] of every particle <-
+    sum_j Gamma_j zeta_sigma_j(x_i - x_j) (the vorticity the particle field represents)."""
+    h = handle or get_handle()
+    P = pfield.particles
+    _check_matrix(P)
+    h.check(h.lib.vpm_zeta_direct(h.ptr, P.ctypes.data, P.shape[0], pfield.np, pfield.kernel.id))
+
+
+def zeta_fmm(pfield, sort_index, leaves, direct_list, *, handle=None):
+    """zeta_fmm(pfield) -- src/FLOWVPM_viscous.jl:523-558 given the tree's sort index, leaf
+    body ranges and near-field list (the tree itself is FastMultipole's, external)."""
+    h = handle or get_handle()
+    P = pfield.particles
+    _check_matrix(P)
+    si = _i64(sort_index)
+    lb, le = _i64(leaves[0]), _i64(leaves[1])
+    dl = np.asarray(direct_list)
+    pa, pb = _i32(dl[:, 0]), _i32(dl[:, 1])
+    h.check(h.lib.vpm_zeta_leafpairs(h.ptr, P.ctypes.data, P.shape[0], pfield.np, si.ctypes.data,
+                                     lb.ctypes.data, le.ctypes.data, len(lb), pa.ctypes.data,
+                                     pb.ctypes.data, len(pa), pfield.kernel.id))
+
+
 def source_system_to_buffer(pfield):
     """fmm.source_system_to_buffer! for every particle (src/FLOWVPM_fmm.jl:62-71) with the
     default rho/sigma = 1 (autotune_reg_error off); returns the 8 x np buffer."""

@@ -137,6 +137,19 @@ int vpm_estr_leafpairs(vpm_handle *h, double *particles, int64_t nfields, int64_
                        const int32_t *pair_tgt, const int32_t *pair_src, int64_t n_pairs,
                        int kernel_id, int flags);
 
+/* ---- second P2P of the reference: the basis-function (vorticity) sum -------- */
+/* zeta_direct(pfield): src/FLOWVPM_viscous.jl:488-515.  Rows 16:18 (J[1:3]) of EVERY
+ * particle (static included) <- sum_j Gamma_j zeta(|x_i-x_j|/sigma_j)/sigma_j^3 (self term
+ * included), overwriting them as the reference does. */
+int vpm_zeta_direct(vpm_handle *h, double *particles, int64_t nfields, int64_t np, int kernel_id);
+/* zeta_fmm(pfield): src/FLOWVPM_viscous.jl:523-558 -- the same sum restricted to the
+ * near-field list of one tree, ADDED to rows 16:18 (the caller zeroes them).  For a list
+ * entry (a, b) the bodies of leaf b receive from the bodies of leaf a, as in the reference. */
+int vpm_zeta_leafpairs(vpm_handle *h, double *particles, int64_t nfields, int64_t np,
+                       const int64_t *sort_index, const int64_t *leaf_begin, const int64_t *leaf_end,
+                       int64_t n_leaves, const int32_t *pair_a, const int32_t *pair_b, int64_t n_pairs,
+                       int kernel_id);
+
 /* ---- device-pointer entry points (one process per GPU; the caller owns the
  * collective, e.g. an NCCL all-gather of the 8 x N source buffer) ---------- */
 /* targets [t0,t1) of the same 8 x ns buffer; out12 is 12 x (t1-t0): U then J.

@@ -53,6 +53,10 @@ def lib():
         L.vpm_oracle_direct_leafpairs.restype = None
         L.vpm_oracle_estr_leafpairs.argtypes = [p, i64, p, p, p, p, p, p, p, p, i64, i32, i32]
         L.vpm_oracle_estr_leafpairs.restype = None
+        L.vpm_oracle_zeta_direct.argtypes = [p, i64, i64, i32, i32]
+        L.vpm_oracle_zeta_direct.restype = None
+        L.vpm_oracle_zeta_leafpairs.argtypes = [p, i64, p, p, p, p, p, i64, i32]
+        L.vpm_oracle_zeta_leafpairs.restype = None
         L.vpm_oracle_max_threads.restype = i32
         _lib = L
     return _lib
@@ -117,6 +121,20 @@ def direct_buffers(tgt, t0, t1, src, s0, s1, kernel, want_U=True, want_J=True, n
     lib().vpm_oracle_direct_buffers_mt(tgt.ctypes.data, tgt.shape[0], int(t0), int(t1), src.ctypes.data,
                                        int(s0), int(s1), _kid(kernel), int(want_U), int(want_J),
                                        int(nthreads))
+
+
+def zeta_direct(P, np_, kernel, nthreads=0):
+    _f(P)
+    lib().vpm_oracle_zeta_direct(P.ctypes.data, P.shape[0], int(np_), _kid(kernel), int(nthreads or max_threads()))
+
+
+def zeta_leafpairs(P, sort, leaves, direct_list, kernel):
+    _f(P)
+    si, lb, le = _i64(sort), _i64(leaves[0]), _i64(leaves[1])
+    dl = np.asarray(direct_list)
+    pt, ps = _i32(dl[:, 0]), _i32(dl[:, 1])
+    lib().vpm_oracle_zeta_leafpairs(P.ctypes.data, P.shape[0], si.ctypes.data, lb.ctypes.data, le.ctypes.data,
+                                    pt.ctypes.data, ps.ctypes.data, len(pt), _kid(kernel))
 
 
 def _i64(a):

@@ -403,6 +403,58 @@ void vpm_oracle_estr_leafpairs(double *P, int64_t nf, const int64_t *tsort, cons
 }
 
 /*
+ * zeta_direct(pfield): src/FLOWVPM_viscous.jl:488-515.  J[1:3] of every particle (static
+ * included) is zeroed, then J[1:3]_i += Gamma_j * (1/sigma_j^3 * zeta(r/sigma_j)) over all j
+ * in index order (self term included).
+ */
+void vpm_oracle_zeta_direct(double *P, int64_t nf, int64_t np, int kernel, int nthreads) {
+  init_consts();
+  for (int64_t i = 0; i < np; ++i)
+    for (int k = 0; k < 3; ++k) P[nf * i + R_J + k] = 0.0;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int64_t i = 0; i < np; ++i) {
+    double *pi = P + nf * i;
+    for (int64_t j = 0; j < np; ++j) {
+      const double *pj = P + nf * j;
+      double dX1 = pi[0] - pj[0], dX2 = pi[1] - pj[1], dX3 = pi[2] - pj[2];
+      double r = sqrt(dX1 * dX1 + dX2 * dX2 + dX3 * dX3);
+      double sg = pj[R_SIGMA];
+      double zeta_sgm = 1 / (sg * sg * sg) * zeta_fn(kernel, r / sg);
+      pi[R_J + 0] += pj[R_G + 0] * zeta_sgm;
+      pi[R_J + 1] += pj[R_G + 1] * zeta_sgm;
+      pi[R_J + 2] += pj[R_G + 2] * zeta_sgm;
+    }
+  }
+}
+
+/*
+ * zeta_fmm's list loop: src/FLOWVPM_viscous.jl:535-557.  For a list entry (i_target,
+ * i_source): Pi runs over the bodies of the SOURCE branch and receives, Pj over the bodies of
+ * the TARGET branch and gives (the reference's naming); no zeroing here.
+ */
+void vpm_oracle_zeta_leafpairs(double *P, int64_t nf, const int64_t *sort, const int64_t *lb,
+                               const int64_t *le, const int32_t *pair_t, const int32_t *pair_s,
+                               int64_t npairs, int kernel) {
+  init_consts();
+  for (int64_t k = 0; k < npairs; ++k) {
+    int32_t bt = pair_t[k], bs = pair_s[k];
+    for (int64_t is = lb[bs]; is < le[bs]; ++is) {
+      double *pi = P + nf * sort[is];
+      for (int64_t it = lb[bt]; it < le[bt]; ++it) {
+        const double *pj = P + nf * sort[it];
+        double dX1 = pi[0] - pj[0], dX2 = pi[1] - pj[1], dX3 = pi[2] - pj[2];
+        double r = sqrt(dX1 * dX1 + dX2 * dX2 + dX3 * dX3);
+        double sg = pj[R_SIGMA];
+        double zeta_sgm = 1 / (sg * sg * sg) * zeta_fn(kernel, r / sg);
+        pi[R_J + 0] += pj[R_G + 0] * zeta_sgm;
+        pi[R_J + 1] += pj[R_G + 1] * zeta_sgm;
+        pi[R_J + 2] += pj[R_G + 2] * zeta_sgm;
+      }
+    }
+  }
+}
+
+/*
  * Timing helper for bench.py's cpu_baseline / --impl reference legs: all ns
  * sources against the target slice [t0,t1) on `nthreads` threads, returning
  * nothing but the accumulated buffer (the caller times the call).

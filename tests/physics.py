@@ -45,20 +45,30 @@ def euler_step(pf, dt, UJ, f=0.0, g=0.0, relax=True):
         relax_pedrizzetti(P, n)
 
 
-def rk3_step(pf, dt, UJ, f=0.0, g=0.0, relax=True):
+def rk3_step(pf, dt, UJ, f=0.0, g=0.0, relax=True, sfs=False, zeta0=1.0):
+    """rungekutta3 for ReformulatedVPM{f,g}; with sfs=True the UJ call also evaluates the SFS
+    term and the per-particle coefficient C (row 37) multiplies it (ConstantSFS-style: the
+    dynamic procedure of src/FLOWVPM_subfilterscale.jl:447-673 is not restated)."""
     n = pf.np
     P = pf.particles
     M = P[27:36, :n]
     M[:] = 0
     for a, b in ((0.0, 1 / 3), (-5 / 9, 15 / 16), (-153 / 128, 8 / 15)):
-        UJ(pf, reset=True)
+        if sfs:
+            UJ(pf, reset=True, reset_sfs=True, sfs=True)
+        else:
+            UJ(pf, reset=True)
         G = P[3:6, :n]
         M[0:3] = a * M[0:3] + dt * P[9:12, :n]
         P[0:3, :n] += b * M[0:3]
         S = _stretch(P[15:24, :n], G, pf.transposed)
         Gn2 = (G * G).sum(axis=0)
-        Z = np.where(Gn2 > 0, (f + g) / (1 + 3 * f) * (S * G).sum(axis=0) / np.where(Gn2 > 0, Gn2, 1), 0.0)
-        M[3:6] = a * M[3:6] + dt * (S - 3 * Z * G)
+        eps_ = P[36, :n] * P[39:42, :n] * P[6, :n] ** 3 / zeta0 if sfs else 0.0
+        Z = (f + g) / (1 + 3 * f) * (S * G).sum(axis=0)
+        if sfs:
+            Z = Z - f / (1 + 3 * f) * (eps_ * G).sum(axis=0)
+        Z = np.where(Gn2 > 0, Z / np.where(Gn2 > 0, Gn2, 1), 0.0)
+        M[3:6] = a * M[3:6] + dt * (S - 3 * Z * G - eps_)
         M[7] = a * M[7] - dt * (P[6, :n] * Z)
         G += b * M[3:6]
         P[6, :n] += b * M[7]

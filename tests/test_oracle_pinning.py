@@ -151,6 +151,23 @@ def test_oracle_sfs_vs_golden(kernel, transposed):
     assert relerr(P[39:42, ~st] - 7.0, ref[:, ~st]) < 2e-13 if np.abs(ref).max() > 0 else True
 
 
+def test_oracle_zeta_direct_vs_mpmath():
+    P = make_field(16)
+    P[42, 3] = 1.0
+    oracle.zeta_direct(P, 16, "gaussianerf", nthreads=1)
+    import mpmath as mp
+    for i in (0, 3, 9):
+        acc = [mp.mpf(0)] * 3
+        for j in range(16):
+            d = [mp.mpf(float(P[k, i])) - mp.mpf(float(P[k, j])) for k in range(3)]
+            r = mp.sqrt(sum(v * v for v in d))
+            sg = mp.mpf(float(P[6, j]))
+            z = hp_oracle.zeta("gaussianerf", r / sg) / sg**3
+            for k in range(3):
+                acc[k] += mp.mpf(float(P[3 + k, j])) * z
+        assert relerr(P[15:18, i], [float(v) for v in acc]) < 1e-14
+
+
 # ------------------------------------------------- reset / static / accumulate
 def test_reset_and_static_rules():
     n = 12

@@ -285,6 +285,33 @@ def test_leafpairs_unsorted_list_and_empty_leaves(vpm, handle):
     assert relerr(tb[4:7], ref[4:7]) < TOL_FP64 and relerr(tb[7:16], ref[7:16]) < TOL_FP64
 
 
+# ------------------------- second P2P: zeta_direct / zeta_fmm (vorticity basis sum)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_zeta_direct(vpm, handle, kernel):
+    pf = vpm.fields.cloud_field(3333, kernel=vpm.KERNELS[kernel], static_fraction=0.1, seed=12)
+    vpm.fields.random_results(pf)
+    ref = pf.particles.copy(order="F")
+    oracle.zeta_direct(ref, pf.np, kernel)
+    vpm.zeta_direct(pf)
+    assert relerr(pf.particles[15:18], ref[15:18]) < TOL_FP64
+    keep = np.r_[0:15, 18:46]
+    assert np.array_equal(pf.particles[keep], ref[keep])   # only J[1:3] is written
+
+
+@pytest.mark.parametrize("kernel", ["gaussianerf", "winckelmans"])
+def test_zeta_fmm_list(vpm, handle, kernel):
+    pf = vpm.fields.cloud_field(4000, kernel=vpm.KERNELS[kernel], seed=13)
+    ll = vpm.fields.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=50, theta=0.4)
+    leaves = (ll["leaf_begin"], ll["leaf_end"])
+    dl = ll["direct_list"][::-1].copy()           # unsorted, asymmetric order
+    dl = dl[: len(dl) * 3 // 4]                   # and an asymmetric list
+    vpm.fields.random_results(pf, scale=1e-2)     # zeta_fmm accumulates on what is there
+    ref = pf.particles.copy(order="F")
+    oracle.zeta_leafpairs(ref, ll["sort_index"], leaves, dl, kernel)
+    vpm.zeta_fmm(pf, ll["sort_index"], leaves, dl)
+    assert relerr(pf.particles[15:18], ref[15:18]) < TOL_FP64
+
+
 # ------------------------------------------------------------ error behaviour
 def test_errors_are_codes_with_messages(vpm, handle):
     pf = vpm.fields.cloud_field(10)
