@@ -188,6 +188,14 @@ function Estr_cuda!(pfield::vpm.ParticleField{Float64}, target_tree, source_tree
     return nothing
 end
 
-export UJ_cuda
+"`zeta_direct(pfield)` (src/FLOWVPM_viscous.jl:488-515): J[1:3] <- sum_j Gamma_j zeta_sigma_j."
+function zeta_cuda(pfield::vpm.ParticleField{Float64})
+    P = pfield.particles
+    GC.@preserve P check(ccall((:vpm_zeta_direct, lib[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Cint),
+                               handle[], P, size(P, 1), pfield.np, kernel_id(pfield.kernel)))
+    return nothing
+end
+
+export UJ_cuda, zeta_cuda
 
 end # module
