@@ -424,18 +424,22 @@ void h1_fill_timing(vpm_handle *h, Dev &d) {
 typedef int (*nccl_comm_init_all_t)(void **comms, int ndev, const int *devlist);
 typedef int (*nccl_all_gather_t)(const void *send, void *recv, size_t count, int dtype, void *comm,
                                  cudaStream_t stream);
+typedef int (*nccl_broadcast_t)(const void *send, void *recv, size_t count, int dtype, int root, void *comm,
+                                cudaStream_t stream);
 typedef int (*nccl_group_t)(void);
 typedef int (*nccl_comm_destroy_t)(void *comm);
 typedef const char *(*nccl_err_t)(int);
 struct NcclApi {
   nccl_comm_init_all_t comm_init_all = nullptr;
   nccl_all_gather_t all_gather = nullptr;
+  nccl_broadcast_t broadcast = nullptr;
   nccl_group_t group_start = nullptr, group_end = nullptr;
   nccl_comm_destroy_t comm_destroy = nullptr;
   nccl_err_t err_string = nullptr;
 };
 NcclApi g_nccl;
 constexpr int kNcclFloat64 = 8;  // ncclDouble (nccl.h ncclDataType_t)
+constexpr int kNcclInt8 = 0;     // ncclChar
 
 int nccl_load(vpm_handle *h) {
   if (h->nccl_lib) return VPM_OK;
@@ -444,11 +448,12 @@ int nccl_load(vpm_handle *h) {
   if (!lib) return fail(h, VPM_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
   g_nccl.comm_init_all = (nccl_comm_init_all_t)dlsym(lib, "ncclCommInitAll");
   g_nccl.all_gather = (nccl_all_gather_t)dlsym(lib, "ncclAllGather");
+  g_nccl.broadcast = (nccl_broadcast_t)dlsym(lib, "ncclBroadcast");
   g_nccl.group_start = (nccl_group_t)dlsym(lib, "ncclGroupStart");
   g_nccl.group_end = (nccl_group_t)dlsym(lib, "ncclGroupEnd");
   g_nccl.comm_destroy = (nccl_comm_destroy_t)dlsym(lib, "ncclCommDestroy");
   g_nccl.err_string = (nccl_err_t)dlsym(lib, "ncclGetErrorString");
-  if (!g_nccl.comm_init_all || !g_nccl.all_gather || !g_nccl.group_start || !g_nccl.group_end ||
+  if (!g_nccl.comm_init_all || !g_nccl.all_gather || !g_nccl.broadcast || !g_nccl.group_start || !g_nccl.group_end ||
       !g_nccl.comm_destroy)
     return fail(h, VPM_ENCCL, "libnccl.so.2 lacks a required symbol");
   h->nccl_lib = lib;
@@ -463,6 +468,33 @@ int nccl_load(vpm_handle *h) {
                   g_nccl.err_string ? g_nccl.err_string(r_) : "nccl error");           \
   } while (0)
 
+int ensure_comms(vpm_handle *h) {
+  if (!h->comms.empty()) return VPM_OK;
+  TRY(nccl_load(h));
+  const int G = (int)h->devs.size();
+  std::vector<int> ids(G);
+  for (int g = 0; g < G; ++g) ids[g] = h->devs[g].id;
+  h->comms.assign(G, nullptr);
+  NCK(h, g_nccl.comm_init_all(h->comms.data(), G, ids.data()));
+  return VPM_OK;
+}
+
+// Replicate `bytes` of one buffer from device 0 to every device of the handle over NVLink
+// (ncclBroadcast on each device's stream): the host uploads a replicated input once
+// instead of G times over PCIe.
+int bcast_from_dev0(vpm_handle *h, Buf Dev::*member, size_t bytes) {
+  const int G = (int)h->devs.size();
+  if (G < 2 || bytes == 0) return VPM_OK;
+  TRY(ensure_comms(h));
+  NCK(h, g_nccl.group_start());
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    NCK(h, g_nccl.broadcast((h->devs[0].*member).p, (d.*member).p, bytes, kNcclInt8, 0, h->comms[g], d.stream));
+  }
+  NCK(h, g_nccl.group_end());
+  return VPM_OK;
+}
+
 // UJ_direct on G devices of this process: targets block-sharded, sources
 // replicated by the host upload; with SFS the final J of every shard is
 // all-gathered (NCCL over NVLink) before the second sweep.
@@ -470,13 +502,7 @@ int uj_direct_multi(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
   const int G = (int)h->devs.size();
   h->launches = 0;
   if (np == 0) return VPM_OK;
-  if (h->comms.empty()) {
-    TRY(nccl_load(h));
-    std::vector<int> ids(G);
-    for (int g = 0; g < G; ++g) ids[g] = h->devs[g].id;
-    h->comms.assign(G, nullptr);
-    NCK(h, g_nccl.comm_init_all(h->comms.data(), G, ids.data()));
-  }
+  TRY(ensure_comms(h));
   const bool reset = flags & VPM_FLAG_RESET;
   const bool do_sfs = flags & VPM_FLAG_SFS;
   const bool sfs_rows = do_sfs || (flags & VPM_FLAG_RESET_SFS);
@@ -496,22 +522,32 @@ int uj_direct_multi(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
   }
   const bool prior = !reset || has_static;
   std::vector<Plan> plans(G);
-  // upload + U/J sweep on every device
+  // sources (X, Gamma, sigma, static flags) go to device 0 once and are broadcast over NVLink
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    CK(h, cudaSetDevice(d.id));
+    TRY(ensure(h, d.in7, (size_t)np * 7 * sizeof(double)));
+    TRY(ensure(h, d.res18, (size_t)np_pad * RES_ROWS * sizeof(double)));
+    TRY(ensure(h, d.sfs3, (size_t)np_pad * 3 * sizeof(double)));
+    if (has_static) TRY(ensure(h, d.stat, (size_t)np * sizeof(double)));
+  }
+  {
+    Dev &d0 = h->devs[0];
+    CK(h, cudaSetDevice(d0.id));
+    CK(h, cudaEventRecord(d0.ev[0], d0.stream));
+    CK(h, cudaMemcpy2DAsync(d0.in7.p, 7 * sizeof(double), P, nf * sizeof(double), 7 * sizeof(double),
+                            (size_t)np, cudaMemcpyHostToDevice, d0.stream));
+    if (has_static)
+      CK(h, cudaMemcpyAsync(d0.stat.p, h->h_stat, (size_t)np * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
+  }
+  TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np * 7 * sizeof(double)));
+  if (has_static) TRY(bcast_from_dev0(h, &Dev::stat, (size_t)np * sizeof(double)));
+  // per-shard previous values + U/J sweep on every device
   for (int g = 0; g < G; ++g) {
     Dev &d = h->devs[g];
     cudaStream_t st = d.stream;
     const int64_t t0 = std::min(np, g * shard), t1 = std::min(np, t0 + shard), nt = t1 - t0;
     CK(h, cudaSetDevice(d.id));
-    TRY(ensure(h, d.in7, (size_t)np * 7 * sizeof(double)));
-    TRY(ensure(h, d.res18, (size_t)np_pad * RES_ROWS * sizeof(double)));
-    TRY(ensure(h, d.sfs3, (size_t)np_pad * 3 * sizeof(double)));
-    if (g == 0) CK(h, cudaEventRecord(d.ev[0], st));
-    CK(h, cudaMemcpy2DAsync(d.in7.p, 7 * sizeof(double), P, nf * sizeof(double), 7 * sizeof(double),
-                            (size_t)np, cudaMemcpyHostToDevice, st));
-    if (has_static) {
-      TRY(ensure(h, d.stat, (size_t)np * sizeof(double)));
-      CK(h, cudaMemcpyAsync(d.stat.p, h->h_stat, (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
-    }
     double *res = (double *)d.res18.p + t0 * RES_ROWS;
     double *sfs = (double *)d.sfs3.p + t0 * 3;
     if (nt > 0) {
@@ -1186,26 +1222,55 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
       cut[g] = std::lower_bound(w.begin(), w.end(), w[(size_t)nwi] * g / G) - w.begin();
   }
   const int64_t ns_pad = round_up(n_src, kTile);
+  // replicated inputs (source buffer, CSR tables): device 0 gets them from the host, the
+  // other devices over NVLink
+  std::vector<LeafCsr> csr(G);
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    CK(h, cudaSetDevice(d.id));
+    TRY(ensure(h, d.tbuf, (size_t)n_tgt * ld * sizeof(double)));
+    TRY(ensure(h, d.sbuf, (size_t)n_src * 8 * sizeof(double)));
+    TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
+  }
+  size_t csr_bytes = 0;
+  {
+    Dev &d0 = h->devs[0];
+    CK(h, cudaSetDevice(d0.id));
+    CK(h, cudaEventRecord(d0.ev[0], d0.stream));
+    CK(h, cudaMemcpyAsync(d0.sbuf.p, src, (size_t)n_src * 8 * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
+    const int64_t *dts, *dss;
+    TRY(upload_csr(h, d0, d0.stream, c, tb, te, ntl, sb, se, nsl, nullptr, 0, nullptr, 0, csr[0], dts, dss));
+    csr_bytes = (size_t)((const char *)csr[0].sleaf_end + (size_t)nsl * sizeof(int64_t) - (const char *)d0.ibuf.p);
+  }
+  for (int g = 1; g < G; ++g) {
+    // same carve-out on every device: rebase device 0's table pointers
+    Dev &d = h->devs[g];
+    CK(h, cudaSetDevice(d.id));
+    TRY(ensure(h, d.ibuf, h->devs[0].ibuf.cap));
+    const ptrdiff_t shift = (const char *)d.ibuf.p - (const char *)h->devs[0].ibuf.p;
+    auto rb = [shift](auto *p) { return (decltype(p))((const char *)p + shift); };
+    csr[g].wi_leaf = rb(csr[0].wi_leaf); csr[g].wi_off = rb(csr[0].wi_off);
+    csr[g].tleaf_begin = rb(csr[0].tleaf_begin); csr[g].tleaf_end = rb(csr[0].tleaf_end);
+    csr[g].csr_ptr = rb(csr[0].csr_ptr); csr[g].csr_src = rb(csr[0].csr_src);
+    csr[g].sleaf_begin = rb(csr[0].sleaf_begin); csr[g].sleaf_end = rb(csr[0].sleaf_end);
+  }
+  TRY(bcast_from_dev0(h, &Dev::sbuf, (size_t)n_src * 8 * sizeof(double)));
+  TRY(bcast_from_dev0(h, &Dev::ibuf, csr_bytes));
+  std::vector<std::pair<int64_t, int64_t>> cols(G, {0, 0});
   for (int g = 0; g < G; ++g) {
     Dev &d = h->devs[g];
     cudaStream_t st = d.stream;
     const int64_t k0 = cut[g], k1 = cut[g + 1];
     if (k1 <= k0) continue;
     CK(h, cudaSetDevice(d.id));
-    TRY(ensure(h, d.tbuf, (size_t)n_tgt * ld * sizeof(double)));
-    TRY(ensure(h, d.sbuf, (size_t)n_src * 8 * sizeof(double)));
-    TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
-    if (g == 0) CK(h, cudaEventRecord(d.ev[0], st));
     // this device's target columns: first target of its first item .. last target of its last
     const int lf = c.wi_leaf[(size_t)k0], ll = c.wi_leaf[(size_t)k1 - 1];
     const int64_t col0 = G == 1 ? 0 : tb[lf] + c.wi_off[(size_t)k0];
     const int64_t col1 = G == 1 ? n_tgt : std::min<int64_t>(te[ll], tb[ll] + c.wi_off[(size_t)k1 - 1] + c.nt);
     CK(h, cudaMemcpyAsync((double *)d.tbuf.p + col0 * ld, tgt + col0 * ld, (size_t)(col1 - col0) * ld * sizeof(double),
                           cudaMemcpyHostToDevice, st));
-    CK(h, cudaMemcpyAsync(d.sbuf.p, src, (size_t)n_src * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
     LeafUjArgs a;
-    const int64_t *dts, *dss;
-    TRY(upload_csr(h, d, st, c, tb, te, ntl, sb, se, nsl, nullptr, 0, nullptr, 0, a.csr, dts, dss));
+    a.csr = csr[g];
     a.csr.wi_leaf += k0;
     a.csr.wi_off += k0;
     if (g == 0) CK(h, cudaEventRecord(d.ev[1], st));
@@ -1223,9 +1288,18 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
       CK(h, cudaEventRecord(d.ev[3], st));
       CK(h, cudaEventRecord(d.ev[4], st));
     }
+    cols[g] = {col0, col1};
+  }
+  // downloads in a second pass: a D2H into pageable memory blocks the host, and every
+  // device must have its kernel in flight before that happens
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    if (cols[g].second <= cols[g].first) continue;
+    CK(h, cudaSetDevice(d.id));
+    const int64_t col0 = cols[g].first, col1 = cols[g].second;
     CK(h, cudaMemcpyAsync(tgt + col0 * ld, (double *)d.tbuf.p + col0 * ld, (size_t)(col1 - col0) * ld * sizeof(double),
-                          cudaMemcpyDeviceToHost, st));
-    if (g == 0) CK(h, cudaEventRecord(d.ev[5], st));
+                          cudaMemcpyDeviceToHost, d.stream));
+    if (g == 0) CK(h, cudaEventRecord(d.ev[5], d.stream));
   }
   for (int g = G - 1; g >= 0; --g) {
     CK(h, cudaSetDevice(h->devs[g].id));
