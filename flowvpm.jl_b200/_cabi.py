@@ -18,6 +18,7 @@ SYMBOLS = [
     "vpm_pin_host", "vpm_unpin_host",
     "vpm_p2p_buffers", "vpm_p2p_leafpairs", "vpm_estr_leafpairs",
     "vpm_zeta_direct", "vpm_zeta_leafpairs",
+    "vpm_field_upload", "vpm_field_download", "vpm_field_uj", "vpm_field_step",
     "vpm_uj_device", "vpm_sfs_device",
     "vpm_get_timing", "vpm_measure_dfma_peak", "vpm_test_math",
 ]
@@ -32,6 +33,14 @@ class VpmTiming(C.Structure):
                 ("h2d_ms", "prep_ms", "uj_ms", "sfs_ms", "finish_ms", "d2h_ms", "total_ms")] + \
                [("uj_pairs", C.c_int64), ("sfs_pairs", C.c_int64),
                 ("kernel_launches", C.c_int32), ("n_gpus", C.c_int32)]
+
+
+class VpmStepParams(C.Structure):
+    _fields_ = [("dt", C.c_double), ("f", C.c_double), ("g", C.c_double), ("Uinf", C.c_double * 3),
+                ("Cs", C.c_double), ("rlxf", C.c_double),
+                ("kernel_id", C.c_int32), ("integration", C.c_int32), ("relaxation", C.c_int32),
+                ("relax", C.c_int32), ("sfs", C.c_int32), ("clip_backscatter", C.c_int32),
+                ("transposed", C.c_int32), ("reserved", C.c_int32)]
 
 
 class VpmError(RuntimeError):
@@ -74,6 +83,10 @@ def load():
     lib.vpm_estr_leafpairs.argtypes = [p, p, i64, i64, p, p, p, p, i64, p, p, i64, p, p, i64, i32, i32]
     lib.vpm_zeta_direct.argtypes = [p, p, i64, i64, i32]
     lib.vpm_zeta_leafpairs.argtypes = [p, p, i64, i64, p, p, p, i64, p, p, i64, i32]
+    lib.vpm_field_upload.argtypes = [p, p, i64, i64]
+    lib.vpm_field_download.argtypes = [p, p, i64, i64]
+    lib.vpm_field_uj.argtypes = [p, i32, i32]
+    lib.vpm_field_step.argtypes = [p, P(VpmStepParams)]
     lib.vpm_uj_device.argtypes = [p, p, i64, i64, i64, p, i32, i32, p]
     lib.vpm_sfs_device.argtypes = [p, p, p, p, i64, i64, i64, p, i32, i32, p]
     lib.vpm_get_timing.argtypes = [p, P(VpmTiming)]

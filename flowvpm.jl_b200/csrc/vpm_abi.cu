@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -19,6 +20,7 @@
 
 #include "vpm_kernels.cuh"
 #include "vpm_leaf.cuh"
+#include "vpm_step.cuh"
 
 using namespace vpm;
 
@@ -42,7 +44,7 @@ struct Dev {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
-  Buf in7, stat, res18, sfs3, rec, srec, partial, tbuf, sbuf, ibuf, jbuf;
+  Buf in7, stat, res18, sfs3, rec, srec, partial, tbuf, sbuf, ibuf, jbuf, fld;
 };
 
 struct Plan {
@@ -67,6 +69,7 @@ struct vpm_handle {
   size_t h_stat_cap = 0;
   std::vector<void *> pinned;
   int launches = 0;
+  int64_t fld_nf = 0, fld_np = -1;  // device mirror of the whole particle matrix (vpm_field_*)
   int device_timing = 0;  // 1/2: ev[6..7] bracket the last _device U/J / SFS pair kernel
   // single-process multi-GPU (n_gpus > 1): NCCL communicators, one per device
   void *nccl_lib = nullptr;
@@ -798,6 +801,52 @@ int64_t count_pairs(const int64_t *tb, const int64_t *te, const int64_t *sb, con
   return n;
 }
 
+
+// ---- device-resident field: UJ_direct on the mirror of the whole matrix ----
+int field_uj(vpm_handle *h, Dev &d, int kernel, int flags) {
+  cudaStream_t st = d.stream;
+  double *F = (double *)d.fld.p;
+  const int64_t nf = h->fld_nf, np = h->fld_np;
+  if (np == 0) return VPM_OK;
+  const double *stat = F + R_STATIC;
+  SrcView src{F, nf, 0, 3, 6};
+  Plan plan;
+  TRY(uj_sweep(h, d, st, kernel, F, nf, np, src, 0, np, flags, plan));
+  UjFinishArgs f;
+  f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+  f.nt = np; f.out = F; f.ld = nf; f.urow = R_U; f.jrow = R_J; f.zrow0 = R_W; f.zrow1 = R_PSE;
+  f.want_U = 1; f.want_J = 1; f.accumulate = 1; f.reset = (flags & VPM_FLAG_RESET) ? 1 : 0;
+  f.stat = stat; f.sld = nf;
+  uj_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(f);
+  h->launches++;
+  if (flags & VPM_FLAG_SFS) {
+    Plan sp;
+    TRY(sfs_sweep(h, d, st, kernel, F, nf, F + R_J, nf, nullptr, np, src, F, nf, R_J, stat, nf, nullptr, np,
+                  flags, sp));
+    SfsFinishArgs g;
+    g.partial = (const double *)d.partial.p; g.pstride = sp.pstride; g.nsplit = sp.nsplit;
+    g.nt = np; g.tindex = nullptr; g.out = F; g.ld = nf; g.row = R_SFS; g.accumulate = 1;
+    g.reset = (flags & VPM_FLAG_RESET_SFS) ? 1 : 0; g.filter_static = 1; g.stat = stat; g.sld = nf;
+    sfs_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(g);
+    h->launches++;
+  } else if (flags & VPM_FLAG_RESET_SFS) {
+    zero_rows_kernel<<<blocks_for(np, 256), 256, 0, st>>>(F, nf, R_SFS, 3, np, stat, nf);
+    h->launches++;
+  }
+  CK(h, cudaGetLastError());
+  return VPM_OK;
+}
+
+double zeta0_of(int kernel) {  // kernel.zeta(0): src/FLOWVPM_kernel.jl:45,51,60,69-74
+  const double pi = 3.14159265358979323846;
+  switch (kernel) {
+    case K_SING: return 1.0;
+    case K_GAUS: return 3.0 / (4.0 * pi);
+    case K_GERF: return 1.0 / pow(2.0 * pi, 1.5);
+    default: return 1.0 / (4.0 * pi) * 7.5 / sqrt(1.0);
+  }
+}
+
 }  // namespace
 
 // ============================================================== C ABI
@@ -866,7 +915,7 @@ int vpm_destroy(vpm_handle *h) {
     cudaSetDevice(d.id);
     cudaStreamSynchronize(d.stream);
     for (Buf *b : {&d.in7, &d.stat, &d.res18, &d.sfs3, &d.rec, &d.srec, &d.partial, &d.tbuf, &d.sbuf,
-                   &d.ibuf, &d.jbuf})
+                   &d.ibuf, &d.jbuf, &d.fld})
       if (b->p) cudaFree(b->p);
     for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
     if (d.stream) cudaStreamDestroy(d.stream);
@@ -1432,6 +1481,100 @@ int vpm_zeta_direct(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
   h->timing.sfs_pairs = np * np;
   h1_fill_timing(h, d);
   h->np_resident = -1;
+  return VPM_OK;
+}
+
+int vpm_field_upload(vpm_handle *h, const double *P, int64_t nf, int64_t np) {
+  TRY(check_field(h, "vpm_field_upload", P, nf, np, 0));
+  Dev &d = h->devs[0];
+  CK(h, cudaSetDevice(d.id));
+  TRY(ensure(h, d.fld, (size_t)std::max<int64_t>(np, 1) * nf * sizeof(double)));
+  if (np > 0) CK(h, cudaMemcpyAsync(d.fld.p, P, (size_t)np * nf * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+  CK(h, cudaStreamSynchronize(d.stream));
+  h->fld_nf = nf;
+  h->fld_np = np;
+  return VPM_OK;
+}
+
+int vpm_field_download(vpm_handle *h, double *P, int64_t nf, int64_t np) {
+  TRY(check_field(h, "vpm_field_download", P, nf, np, 0));
+  if (h->fld_np != np || h->fld_nf != nf)
+    return fail(h, VPM_ESTATE, "vpm_field_download: a %lld x %lld field is resident, not %lld x %lld",
+                (long long)h->fld_nf, (long long)h->fld_np, (long long)nf, (long long)np);
+  Dev &d = h->devs[0];
+  CK(h, cudaSetDevice(d.id));
+  if (np > 0) CK(h, cudaMemcpyAsync(P, d.fld.p, (size_t)np * nf * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+  CK(h, cudaStreamSynchronize(d.stream));
+  return VPM_OK;
+}
+
+int vpm_field_uj(vpm_handle *h, int kernel, int flags) {
+  if (!h) return VPM_EINVAL;
+  if (h->fld_np < 0) return fail(h, VPM_ESTATE, "vpm_field_uj: no resident field (call vpm_field_upload first)");
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "vpm_field_uj: unknown kernel_id %d", kernel);
+  Dev &d = h->devs[0];
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  CK(h, cudaEventRecord(d.ev[0], d.stream));
+  CK(h, cudaEventRecord(d.ev[1], d.stream));
+  TRY(field_uj(h, d, kernel, flags));
+  for (int k = 2; k <= 5; ++k) CK(h, cudaEventRecord(d.ev[k], d.stream));
+  CK(h, cudaStreamSynchronize(d.stream));
+  h1_fill_timing(h, d);
+  h->timing.uj_ms = h->timing.total_ms;
+  return VPM_OK;
+}
+
+int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
+  if (!h || !sp) return VPM_EINVAL;
+  if (h->fld_np < 0) return fail(h, VPM_ESTATE, "vpm_field_step: no resident field (call vpm_field_upload first)");
+  if (!valid_kernel(sp->kernel_id)) return fail(h, VPM_EINVAL, "vpm_field_step: unknown kernel_id %d", sp->kernel_id);
+  if (sp->integration < 0 || sp->integration > 1 || sp->relaxation < 0 || sp->relaxation > 2)
+    return fail(h, VPM_EINVAL, "vpm_field_step: integration must be 0 (euler) or 1 (rungekutta3), relaxation 0..2");
+  if (h->fld_nf < 44) return fail(h, VPM_EINVAL, "vpm_field_step: the resident field needs >= 44 rows");
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  const int64_t np = h->fld_np;
+  if (np == 0) return VPM_OK;
+  StepArgs a;
+  a.P = (double *)d.fld.p; a.nf = h->fld_nf; a.np = np;
+  a.a = 1.0; a.b = 1.0; a.dt = sp->dt; a.Ux = sp->Uinf[0]; a.Uy = sp->Uinf[1]; a.Uz = sp->Uinf[2];
+  a.f = sp->f; a.g = sp->g; a.zeta0 = zeta0_of(sp->kernel_id); a.Cs = sp->Cs; a.rlxf = sp->rlxf;
+  a.transposed = sp->transposed; a.sfs = sp->sfs; a.clip = sp->clip_backscatter; a.relax_kind = sp->relaxation;
+  const int tr = sp->transposed ? VPM_FLAG_TRANSPOSED : 0;
+  const int uj_flags = VPM_FLAG_RESET | tr | (sp->sfs ? (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS) : 0);
+  const unsigned nb = blocks_for(np, 256);
+  CK(h, cudaEventRecord(d.ev[0], st));
+  CK(h, cudaEventRecord(d.ev[1], st));
+  if (sp->integration == 0) {  // euler: src/FLOWVPM_timeintegration.jl:23-37
+    TRY(field_uj(h, d, sp->kernel_id, uj_flags));
+    if (sp->sfs) { step_sfs_coeff<<<nb, 256, 0, st>>>(a); h->launches++; }
+    step_euler<<<nb, 256, 0, st>>>(a, sp->relax ? 1 : 0);
+    h->launches++;
+  } else {  // rungekutta3: src/FLOWVPM_timeintegration.jl:388-461
+    step_reset_M<<<nb, 256, 0, st>>>(a);
+    h->launches++;
+    const double ab[3][2] = {{0.0, 1.0 / 3}, {-5.0 / 9, 15.0 / 16}, {-153.0 / 128, 8.0 / 15}};
+    for (int k = 0; k < 3; ++k) {
+      a.a = ab[k][0]; a.b = ab[k][1];
+      TRY(field_uj(h, d, sp->kernel_id, uj_flags));
+      if (sp->sfs && k == 0) { step_sfs_coeff<<<nb, 256, 0, st>>>(a); h->launches++; }
+      step_rk_stage<<<nb, 256, 0, st>>>(a);
+      h->launches++;
+    }
+    if (sp->relax && sp->relaxation) {
+      TRY(field_uj(h, d, sp->kernel_id, VPM_FLAG_RESET | tr));
+      step_relax<<<nb, 256, 0, st>>>(a);
+      h->launches++;
+    }
+  }
+  CK(h, cudaGetLastError());
+  for (int k = 2; k <= 5; ++k) CK(h, cudaEventRecord(d.ev[k], st));
+  CK(h, cudaStreamSynchronize(st));
+  h1_fill_timing(h, d);
+  h->timing.uj_ms = h->timing.total_ms;
   return VPM_OK;
 }
 

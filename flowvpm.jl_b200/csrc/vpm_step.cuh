@@ -1,0 +1,161 @@
+// vpm_step.cuh -- SURVEY 8(f-1): the O(N) per-particle kernels around the sweeps, so that a
+// whole time step can run on a device-resident copy of ParticleField.particles.
+//
+// Reference being restated (FLOWVPM.jl v4.0.3):
+//   rungekutta3 / update_particle_states for ReformulatedVPM{f,g}  src/FLOWVPM_timeintegration.jl:388-534
+//   euler / _euler for ReformulatedVPM{f,g}                        src/FLOWVPM_timeintegration.jl:23-37,103-173
+//   relax_pedrizzetti / relax_correctedpedrizzetti                 src/FLOWVPM_relaxation.jl:62-142
+//   ConstantSFS AfterUJ hook + clipping_backscatter                src/FLOWVPM_subfilterscale.jl:110-135,287-296
+// Covered: cVPM / rVPM / any (f, g), NoSFS and ConstantSFS (optional backscatter clipping),
+// Inviscid, constant Uinf.  Not covered (stays in Julia): DynamicSFS procedure, viscous schemes.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vpm {
+
+struct StepArgs {
+  double *P;  // device mirror of ParticleField.particles, nf x np column-major
+  int64_t nf, np;
+  double a, b, dt;
+  double Ux, Uy, Uz;  // Uinf
+  double f, g, zeta0;
+  double Cs, rlxf;
+  int transposed, sfs, clip, relax_kind;  // relax_kind: 0 none, 1 pedrizzetti, 2 corrected
+};
+
+// rows, 0-based (src/FLOWVPM_particlefield.jl:239-252)
+enum { S_X = 0, S_G = 3, S_SIGMA = 6, S_U = 9, S_J = 15, S_M = 27, S_C = 36, S_SFS = 39, S_STATIC = 42 };
+
+__device__ __forceinline__ void stretching(const double *J, const double *G, int transposed, double &m1,
+                                           double &m2, double &m3) {
+  if (transposed) {
+    m1 = J[0] * G[0] + J[1] * G[1] + J[2] * G[2];
+    m2 = J[3] * G[0] + J[4] * G[1] + J[5] * G[2];
+    m3 = J[6] * G[0] + J[7] * G[1] + J[8] * G[2];
+  } else {
+    m1 = J[0] * G[0] + J[3] * G[1] + J[6] * G[2];
+    m2 = J[1] * G[0] + J[4] * G[1] + J[7] * G[2];
+    m3 = J[2] * G[0] + J[5] * G[1] + J[8] * G[2];
+  }
+}
+
+// relaxation(pfield, i): src/FLOWVPM_relaxation.jl:62-81 (kind 1), :117-142 (kind 2)
+__device__ __forceinline__ void relax_particle(double *p, double rlxf, int kind) {
+  const double *J = p + S_J;
+  double *G = p + S_G;
+  const double w1 = J[5] - J[7], w2 = J[6] - J[2], w3 = J[1] - J[3];
+  const double nrmw = sqrt(w1 * w1 + w2 * w2 + w3 * w3);
+  if (nrmw == 0.0) return;
+  const double nrmG = sqrt(G[0] * G[0] + G[1] * G[1] + G[2] * G[2]);
+  double b2 = 1.0;
+  if (kind == 2) b2 = 1 - 2 * (1 - rlxf) * rlxf * (1 - (G[0] * w1 + G[1] * w2 + G[2] * w3) / (nrmG * nrmw));
+  G[0] = (1 - rlxf) * G[0] + rlxf * nrmG * w1 / nrmw;
+  G[1] = (1 - rlxf) * G[1] + rlxf * nrmG * w2 / nrmw;
+  G[2] = (1 - rlxf) * G[2] + rlxf * nrmG * w3 / nrmw;
+  if (kind == 2) {
+    const double s = sqrt(b2);
+    G[0] /= s; G[1] /= s; G[2] /= s;
+  }
+}
+
+// zero the RK storage M of non-static particles (src/FLOWVPM_timeintegration.jl:402-414)
+__global__ void step_reset_M(StepArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) p[S_M + k] = 0.0;
+}
+
+// ConstantSFS AfterUJ at an Euler step or the first RK substep: C <- Cs, then backscatter
+// clipping C <- 0 where C (Gamma . SFS) < 0 (src/FLOWVPM_subfilterscale.jl:110-135,287-296)
+__global__ void step_sfs_coeff(StepArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+  double C = a.Cs;
+  if (a.clip) {
+    const double d = p[S_G] * p[S_SFS] + p[S_G + 1] * p[S_SFS + 1] + p[S_G + 2] * p[S_SFS + 2];
+    if (C * d < 0.0) C = 0.0;
+  }
+  p[S_C] = C;
+}
+
+// the Z and dGamma terms shared by the Euler and RK updates (:505-521, :145-160)
+__device__ __forceinline__ void rvpm_rates(const double *p, const StepArgs &a, double &m1, double &m2, double &m3,
+                                           double &m4, double &e1, double &e2, double &e3) {
+  const double *G = p + S_G, *SFS = p + S_SFS;
+  const double C = p[S_C], sg = p[S_SIGMA];
+  stretching(p + S_J, G, a.transposed, m1, m2, m3);
+  const double sigma3 = sg * sg * sg;
+  const double Gn2 = G[0] * G[0] + G[1] * G[1] + G[2] * G[2];
+  if (Gn2 > 0.0) {
+    m4 = (a.f + a.g) / (1 + 3 * a.f) * (m1 * G[0] + m2 * G[1] + m3 * G[2]);
+    m4 -= a.f / (1 + 3 * a.f) * (C * SFS[0] * G[0] + C * SFS[1] * G[1] + C * SFS[2] * G[2]) * sigma3 / a.zeta0;
+    m4 /= Gn2;
+  } else {
+    m4 = 0.0;
+  }
+  e1 = C * SFS[0] * sigma3 / a.zeta0;
+  e2 = C * SFS[1] * sigma3 / a.zeta0;
+  e3 = C * SFS[2] * sigma3 / a.zeta0;
+}
+
+// update_particle_states, ReformulatedVPM: src/FLOWVPM_timeintegration.jl:463-534
+__global__ void step_rk_stage(StepArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+  double *M = p + S_M, *G = p + S_G, *X = p + S_X;
+  const double *U = p + S_U;
+  M[0] = a.a * M[0] + a.dt * (U[0] + a.Ux);
+  M[1] = a.a * M[1] + a.dt * (U[1] + a.Uy);
+  M[2] = a.a * M[2] + a.dt * (U[2] + a.Uz);
+  X[0] += a.b * M[0];
+  X[1] += a.b * M[1];
+  X[2] += a.b * M[2];
+  double m1, m2, m3, m4, e1, e2, e3;
+  rvpm_rates(p, a, m1, m2, m3, m4, e1, e2, e3);
+  M[3] = a.a * M[3] + a.dt * (m1 - 3 * m4 * G[0] - e1);
+  M[4] = a.a * M[4] + a.dt * (m2 - 3 * m4 * G[1] - e2);
+  M[5] = a.a * M[5] + a.dt * (m3 - 3 * m4 * G[2] - e3);
+  M[7] = a.a * M[7] - a.dt * (p[S_SIGMA] * m4);
+  G[0] += a.b * M[3];
+  G[1] += a.b * M[4];
+  G[2] += a.b * M[5];
+  p[S_SIGMA] += a.b * M[7];
+}
+
+// _euler, ReformulatedVPM: src/FLOWVPM_timeintegration.jl:103-173 (relaxation inside the loop)
+__global__ void step_euler(StepArgs a, int relax) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+  double *G = p + S_G, *X = p + S_X;
+  const double *U = p + S_U;
+  X[0] += a.dt * (U[0] + a.Ux);
+  X[1] += a.dt * (U[1] + a.Uy);
+  X[2] += a.dt * (U[2] + a.Uz);
+  double m1, m2, m3, m4, e1, e2, e3;
+  rvpm_rates(p, a, m1, m2, m3, m4, e1, e2, e3);
+  G[0] += a.dt * (m1 - 3 * m4 * G[0] - e1);
+  G[1] += a.dt * (m2 - 3 * m4 * G[1] - e2);
+  G[2] += a.dt * (m3 - 3 * m4 * G[2] - e3);
+  p[S_SIGMA] -= a.dt * (p[S_SIGMA] * m4);
+  if (relax && a.relax_kind) relax_particle(p, a.rlxf, a.relax_kind);
+}
+
+__global__ void step_relax(StepArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+  relax_particle(p, a.rlxf, a.relax_kind);
+}
+
+}  // namespace vpm

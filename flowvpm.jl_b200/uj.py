@@ -180,6 +180,52 @@ def zeta_fmm(pfield, sort_index, leaves, direct_list, *, handle=None):
                                      pb.ctypes.data, len(pa), pfield.kernel.id))
 
 
+class ResidentField:
+    """Device-resident mirror of pfield.particles: the reference's `nextstep`
+    integration call (`euler` / `rungekutta3` for ReformulatedVPM{f,g}, NoSFS or ConstantSFS,
+    Pedrizzetti relaxations, Inviscid) runs on the GPU; the matrix crosses PCIe only on
+    upload() / download().  DynamicSFS and viscous schemes are not covered: use UJ_direct
+    in the UJ slot for those."""
+
+    INTEGRATIONS = {"euler": 0, "rungekutta3": 1}
+    RELAXATIONS = {None: 0, "none": 0, "pedrizzetti": 1, "correctedpedrizzetti": 2}
+
+    def __init__(self, pfield, handle=None):
+        self.pfield = pfield
+        self.h = handle or get_handle()
+        P = pfield.particles
+        _check_matrix(P)
+        if P.dtype != np.float64:
+            raise TypeError("ResidentField is FP64 only")
+        self.upload()
+
+    def upload(self):
+        P = self.pfield.particles
+        self.h.check(self.h.lib.vpm_field_upload(self.h.ptr, P.ctypes.data, P.shape[0], self.pfield.np))
+
+    def download(self):
+        P = self.pfield.particles
+        self.h.check(self.h.lib.vpm_field_download(self.h.ptr, P.ctypes.data, P.shape[0], self.pfield.np))
+
+    def UJ(self, *, sfs=False, reset=True, reset_sfs=False):
+        self.h.check(self.h.lib.vpm_field_uj(self.h.ptr, self.pfield.kernel.id,
+                                             _flags(self.pfield, sfs, reset, reset_sfs)))
+
+    def nextstep(self, dt, *, integration="rungekutta3", f=0.0, g=0.2, Uinf=(0.0, 0.0, 0.0), sfs=False, Cs=1.0,
+                 clip_backscatter=False, relaxation="pedrizzetti", relax=True, rlxf=0.3):
+        sp = _cabi.VpmStepParams()
+        sp.dt, sp.f, sp.g, sp.Cs, sp.rlxf = dt, f, g, Cs, rlxf
+        sp.Uinf[0], sp.Uinf[1], sp.Uinf[2] = Uinf
+        sp.kernel_id = self.pfield.kernel.id
+        sp.integration = self.INTEGRATIONS[integration]
+        sp.relaxation = self.RELAXATIONS[relaxation]
+        sp.relax, sp.sfs, sp.clip_backscatter = int(relax), int(sfs), int(clip_backscatter)
+        sp.transposed = int(self.pfield.transposed)
+        self.h.check(self.h.lib.vpm_field_step(self.h.ptr, C.byref(sp)))
+        self.pfield.t += dt
+        self.pfield.nt += 1
+
+
 def source_system_to_buffer(pfield):
     """fmm.source_system_to_buffer! for every particle (src/FLOWVPM_fmm.jl:62-71) with the
     default rho/sigma = 1 (autotune_reg_error off); returns the 8 x np buffer."""

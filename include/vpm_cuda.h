@@ -150,6 +150,37 @@ int vpm_zeta_leafpairs(vpm_handle *h, double *particles, int64_t nfields, int64_
                        int64_t n_leaves, const int32_t *pair_a, const int32_t *pair_b, int64_t n_pairs,
                        int kernel_id);
 
+/* ---- device-resident time step ------------------------------- */
+/* The whole particle matrix is mirrored on the device; a step runs the reference's
+ * integrator there, so the matrix only crosses PCIe when the caller wants it back.
+ *   rungekutta3 / update_particle_states, ReformulatedVPM{f,g}: src/FLOWVPM_timeintegration.jl:388-534
+ *   euler / _euler:                                             src/FLOWVPM_timeintegration.jl:23-37,103-173
+ *   relaxation (pedrizzetti / correctedpedrizzetti):            src/FLOWVPM_relaxation.jl:62-142
+ *   ConstantSFS hook + clipping_backscatter:                    src/FLOWVPM_subfilterscale.jl:110-135,287-296
+ * Covered: any (f, g) incl. cVPM (0,0) and rVPM (0,1/5); NoSFS / ConstantSFS; Inviscid; constant
+ * Uinf.  DynamicSFS and the viscous schemes stay in the reference's Julia code (use Hook 1). */
+typedef struct vpm_step_params {
+  double dt;
+  double f, g;        /* ReformulatedVPM{f,g}: src/FLOWVPM_formulation.jl:23-37 */
+  double Uinf[3];     /* pfield.Uinf(t), constant over the step */
+  double Cs;          /* ConstantSFS model coefficient */
+  double rlxf;        /* relaxation factor (0.3 in the reference's presets, src/FLOWVPM.jl:169-170) */
+  int32_t kernel_id;
+  int32_t integration;      /* 0 euler, 1 rungekutta3 */
+  int32_t relaxation;       /* 0 none, 1 pedrizzetti, 2 correctedpedrizzetti */
+  int32_t relax;            /* apply relaxation in this step (run_vpm!'s `relax`, src/FLOWVPM_utils.jl:94-96) */
+  int32_t sfs;              /* 0 NoSFS, 1 ConstantSFS */
+  int32_t clip_backscatter; /* ConstantSFS clippings = (clipping_backscatter,) */
+  int32_t transposed;       /* pfield.transposed */
+  int32_t reserved;
+} vpm_step_params;
+int vpm_field_upload(vpm_handle *h, const double *particles, int64_t nfields, int64_t np);
+int vpm_field_download(vpm_handle *h, double *particles, int64_t nfields, int64_t np);
+/* UJ_direct(pfield; ...) on the resident matrix (flags as vpm_uj_direct) */
+int vpm_field_uj(vpm_handle *h, int kernel_id, int flags);
+/* nextstep's integration call: one euler / rungekutta3 step on the resident matrix */
+int vpm_field_step(vpm_handle *h, const vpm_step_params *params);
+
 /* ---- device-pointer entry points (one process per GPU; the caller owns the
  * collective, e.g. an NCCL all-gather of the 8 x N source buffer) ---------- */
 /* targets [t0,t1) of the same 8 x ns buffer; out12 is 12 x (t1-t0): U then J.

@@ -57,6 +57,8 @@ def lib():
         L.vpm_oracle_zeta_direct.restype = None
         L.vpm_oracle_zeta_leafpairs.argtypes = [p, i64, p, p, p, p, p, i64, i32]
         L.vpm_oracle_zeta_leafpairs.restype = None
+        L.vpm_oracle_field_step.argtypes = [p, i64, i64, p, p, i32]
+        L.vpm_oracle_field_step.restype = i32
         L.vpm_oracle_max_threads.restype = i32
         _lib = L
     return _lib
@@ -121,6 +123,21 @@ def direct_buffers(tgt, t0, t1, src, s0, s1, kernel, want_U=True, want_J=True, n
     lib().vpm_oracle_direct_buffers_mt(tgt.ctypes.data, tgt.shape[0], int(t0), int(t1), src.ctypes.data,
                                        int(s0), int(s1), _kid(kernel), int(want_U), int(want_J),
                                        int(nthreads))
+
+
+def field_step(P, np_, kernel, dt, *, integration="rungekutta3", f=0.0, g=0.2, Uinf=(0.0, 0.0, 0.0), sfs=False,
+               Cs=1.0, clip_backscatter=False, relaxation="pedrizzetti", relax=True, rlxf=0.3, transposed=True,
+               nthreads=0):
+    """one euler / rungekutta3 step of ReformulatedVPM{f,g} on the 46 x N matrix, in place"""
+    _f(P)
+    dp = np.array([dt, f, g, Uinf[0], Uinf[1], Uinf[2], Cs, rlxf], dtype=np.float64)
+    ip = np.array([_kid(kernel), {"euler": 0, "rungekutta3": 1}[integration],
+                   {None: 0, "none": 0, "pedrizzetti": 1, "correctedpedrizzetti": 2}[relaxation], int(relax), int(sfs),
+                   int(clip_backscatter), int(transposed)], dtype=np.int32)
+    rc = lib().vpm_oracle_field_step(P.ctypes.data, P.shape[0], int(np_), dp.ctypes.data, ip.ctypes.data,
+                                     int(nthreads or max_threads()))
+    if rc != 0:
+        raise RuntimeError(f"oracle field_step failed ({rc})")
 
 
 def zeta_direct(P, np_, kernel, nthreads=0):

@@ -454,6 +454,131 @@ void vpm_oracle_zeta_leafpairs(double *P, int64_t nf, const int64_t *sort, const
   }
 }
 
+/* ===========================================================================
+ * Time step on the host (SURVEY 8 f-1 checker).  ReformulatedVPM{f,g} only.
+ *   rungekutta3            src/FLOWVPM_timeintegration.jl:388-461
+ *   update_particle_states src/FLOWVPM_timeintegration.jl:463-534
+ *   euler / _euler         src/FLOWVPM_timeintegration.jl:23-37,103-173
+ *   relaxation             src/FLOWVPM_relaxation.jl:62-142
+ *   ConstantSFS hook       src/FLOWVPM_subfilterscale.jl:110-135, clipping :287-296
+ * ========================================================================== */
+enum { R_M = 27, R_C = 36 };
+
+static void o_stretch(const double *J, const double *G, int transposed, double *m) {
+  if (transposed) {
+    m[0] = J[0] * G[0] + J[1] * G[1] + J[2] * G[2];
+    m[1] = J[3] * G[0] + J[4] * G[1] + J[5] * G[2];
+    m[2] = J[6] * G[0] + J[7] * G[1] + J[8] * G[2];
+  } else {
+    m[0] = J[0] * G[0] + J[3] * G[1] + J[6] * G[2];
+    m[1] = J[1] * G[0] + J[4] * G[1] + J[7] * G[2];
+    m[2] = J[2] * G[0] + J[5] * G[1] + J[8] * G[2];
+  }
+}
+
+static void o_relax(double *p, double rlxf, int kind) {
+  const double *J = p + R_J;
+  double *G = p + R_G;
+  double nrmw = sqrt((J[5] - J[7]) * (J[5] - J[7]) + (J[6] - J[2]) * (J[6] - J[2]) + (J[1] - J[3]) * (J[1] - J[3]));
+  if (nrmw != 0.0) {
+    double nrmGamma = sqrt(G[0] * G[0] + G[1] * G[1] + G[2] * G[2]);
+    double b2 = 1.0;
+    if (kind == 2)
+      b2 = 1 - 2 * (1 - rlxf) * rlxf *
+                   (1 - (G[0] * (J[5] - J[7]) + G[1] * (J[6] - J[2]) + G[2] * (J[1] - J[3])) / (nrmGamma * nrmw));
+    G[0] = (1 - rlxf) * G[0] + rlxf * nrmGamma * (J[5] - J[7]) / nrmw;
+    G[1] = (1 - rlxf) * G[1] + rlxf * nrmGamma * (J[6] - J[2]) / nrmw;
+    G[2] = (1 - rlxf) * G[2] + rlxf * nrmGamma * (J[1] - J[3]) / nrmw;
+    if (kind == 2) {
+      double sq = sqrt(b2);
+      G[0] /= sq; G[1] /= sq; G[2] /= sq;
+    }
+  }
+}
+
+static void o_sfs_coeff(double *P, int64_t nf, int64_t np, double Cs, int clip) {
+  for (int64_t i = 0; i < np; ++i) {
+    double *p = P + nf * i;
+    if (p[R_STATIC] != 0.0) continue;
+    p[R_C] = Cs;
+  }
+  if (clip)
+    for (int64_t i = 0; i < np; ++i) {
+      double *p = P + nf * i;
+      if (p[R_STATIC] != 0.0) continue;
+      if (p[R_C] * (p[R_G] * p[R_SFS] + p[R_G + 1] * p[R_SFS + 1] + p[R_G + 2] * p[R_SFS + 2]) < 0) p[R_C] = 0;
+    }
+}
+
+static void o_rates(const double *p, double f, double g, double zeta0, int transposed, double *MM, double *MM4,
+                    double *eps) {
+  const double *G = p + R_G;
+  double C = p[R_C], sg = p[R_SIGMA];
+  o_stretch(p + R_J, G, transposed, MM);
+  double Gnorm2 = G[0] * G[0] + G[1] * G[1] + G[2] * G[2];
+  if (Gnorm2 > 0) {
+    *MM4 = (f + g) / (1 + 3 * f) * (MM[0] * G[0] + MM[1] * G[1] + MM[2] * G[2]);
+    *MM4 -= f / (1 + 3 * f) * (C * p[R_SFS] * G[0] + C * p[R_SFS + 1] * G[1] + C * p[R_SFS + 2] * G[2]) *
+            (sg * sg * sg) / zeta0;
+    *MM4 /= Gnorm2;
+  } else {
+    *MM4 = 0;
+  }
+  for (int k = 0; k < 3; ++k) eps[k] = C * p[R_SFS + k] * (sg * sg * sg) / zeta0;
+}
+
+int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, const double *dp, const int *ip, int nthreads) {
+  init_consts();
+  const double dt = dp[0], f = dp[1], g = dp[2], Uinf[3] = {dp[3], dp[4], dp[5]}, Cs = dp[6], rlxf = dp[7];
+  const int kernel = ip[0], integration = ip[1], relaxation = ip[2], relax = ip[3], sfs = ip[4], clip = ip[5],
+            transposed = ip[6];
+  const double zeta0 = zeta_fn(kernel, 0.0);
+  const int tr = transposed ? VPM_FLAG_TRANSPOSED : 0;
+  const int uj_flags = VPM_FLAG_RESET | tr | (sfs ? (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS) : 0);
+  if (integration == 0) {
+    vpm_oracle_uj_direct(P, nf, np, kernel, uj_flags, nthreads);
+    if (sfs) o_sfs_coeff(P, nf, np, Cs, clip);
+    for (int64_t i = 0; i < np; ++i) {
+      double *p = P + nf * i;
+      if (p[R_STATIC] != 0.0) continue;
+      double *G = p + R_G, MM[3], MM4, eps[3];
+      for (int k = 0; k < 3; ++k) p[k] += dt * (p[R_U + k] + Uinf[k]);
+      o_rates(p, f, g, zeta0, transposed, MM, &MM4, eps);
+      for (int k = 0; k < 3; ++k) G[k] += dt * (MM[k] - 3 * MM4 * G[k] - eps[k]);
+      p[R_SIGMA] -= dt * (p[R_SIGMA] * MM4);
+      if (relax && relaxation) o_relax(p, rlxf, relaxation);
+    }
+    return 0;
+  }
+  for (int64_t i = 0; i < np; ++i)
+    if (P[nf * i + R_STATIC] == 0.0)
+      for (int k = 0; k < 9; ++k) P[nf * i + R_M + k] = 0.0;
+  const double ab[3][2] = {{0.0, 1.0 / 3}, {-5.0 / 9, 15.0 / 16}, {-153.0 / 128, 8.0 / 15}};
+  for (int s_ = 0; s_ < 3; ++s_) {
+    const double a = ab[s_][0], b = ab[s_][1];
+    vpm_oracle_uj_direct(P, nf, np, kernel, uj_flags, nthreads);
+    if (sfs && a == 0.0) o_sfs_coeff(P, nf, np, Cs, clip);
+    for (int64_t i = 0; i < np; ++i) {
+      double *p = P + nf * i;
+      if (p[R_STATIC] != 0.0) continue;
+      double *M = p + R_M, *G = p + R_G, MM[3], MM4, eps[3];
+      for (int k = 0; k < 3; ++k) M[k] = a * M[k] + dt * (p[R_U + k] + Uinf[k]);
+      for (int k = 0; k < 3; ++k) p[k] += b * M[k];
+      o_rates(p, f, g, zeta0, transposed, MM, &MM4, eps);
+      for (int k = 0; k < 3; ++k) M[3 + k] = a * M[3 + k] + dt * (MM[k] - 3 * MM4 * G[k] - eps[k]);
+      M[7] = a * M[7] - dt * (p[R_SIGMA] * MM4);
+      for (int k = 0; k < 3; ++k) G[k] += b * M[3 + k];
+      p[R_SIGMA] += b * M[7];
+    }
+  }
+  if (relax && relaxation) {
+    vpm_oracle_uj_direct(P, nf, np, kernel, VPM_FLAG_RESET | tr, nthreads);
+    for (int64_t i = 0; i < np; ++i)
+      if (P[nf * i + R_STATIC] == 0.0) o_relax(P + nf * i, rlxf, relaxation);
+  }
+  return 0;
+}
+
 /*
  * Timing helper for bench.py's cpu_baseline / --impl reference legs: all ns
  * sources against the target slice [t0,t1) on `nthreads` threads, returning

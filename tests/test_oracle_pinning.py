@@ -229,3 +229,18 @@ def test_single_ring_speed_within_2_percent(integration, vpm):
     U_vpm, U_ana = physics.run_single_ring(vpm, UJ, integration)
     err = (U_vpm - U_ana) / U_ana
     assert abs(err) < 0.02, (U_vpm, U_ana, err)  # test/runtests_singlevortexring.jl:143
+
+
+@pytest.mark.parametrize("integration", ["euler", "rungekutta3"])
+def test_oracle_step_equals_numpy_harness(integration, vpm):
+    """two independent restatements of the reference integrators (C in oracle/, numpy in
+    tests/physics.py) agree bit for bit"""
+    pf = vpm.fields.ring_field(Nphi=40, nc=1, kernel=vpm.winckelmans)
+    a = pf.particles.copy(order="F")
+
+    def UJ(p, reset=True, **kw):
+        oracle.uj_direct(p.particles, p.np, p.kernel.name, reset=reset, **kw)
+    step = physics.euler_step if integration == "euler" else physics.rk3_step
+    step(pf, 1e-2, UJ, f=0.0, g=0.2, relax=True)
+    oracle.field_step(a, pf.np, "winckelmans", 1e-2, integration=integration, f=0.0, g=0.2, relax=True)
+    assert np.array_equal(a[0:7], pf.particles[0:7])

@@ -1,0 +1,104 @@
+"""the device-resident time step (vpm_field_*) against the CPU restatement of
+the reference's euler / rungekutta3 (oracle.field_step), and the reference's own physics
+assertion (ring speed within 2 %, test/runtests_singlevortexring.jl:143) run entirely on the GPU."""
+import numpy as np
+import pytest
+
+from helpers import relerr
+from oracle import oracle
+import physics
+
+pytestmark = pytest.mark.gpu
+
+ROWS = {"X": slice(0, 3), "Gamma": slice(3, 6), "sigma": slice(6, 7), "U": slice(9, 12), "J": slice(15, 24),
+        "M": slice(27, 36), "C": slice(36, 37), "SFS": slice(39, 42)}
+
+
+def make_field(vpm, kernel):
+    pf = vpm.fields.ring_field(Nphi=60, nc=1, kernel=kernel, R=1.0, Rcross=0.15)
+    pf.particles[42, 5:pf.np:37] = 1.0          # a few static particles
+    pf.particles[36, :pf.np] = 0.3              # stale C values must be overwritten by ConstantSFS
+    return pf
+
+
+@pytest.mark.parametrize("integration", ["euler", "rungekutta3"])
+@pytest.mark.parametrize("sfs,clip", [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("relaxation", ["pedrizzetti", "correctedpedrizzetti", None])
+def test_step_matches_oracle(vpm, handle, integration, sfs, clip, relaxation):
+    kernel = vpm.gaussianerf if sfs else vpm.winckelmans
+    pf = make_field(vpm, kernel)
+    ref = pf.particles.copy(order="F")
+    kw = dict(integration=integration, f=0.0, g=0.2, Uinf=(0.01, -0.02, 0.03), sfs=sfs, Cs=0.8,
+              clip_backscatter=clip, relaxation=relaxation, relax=True, rlxf=0.3)
+    rf = vpm.ResidentField(pf)
+    dt = 2e-2
+    for _ in range(2):
+        rf.nextstep(dt, **kw)
+        oracle.field_step(ref, pf.np, kernel.name, dt, transposed=pf.transposed, **kw)
+    rf.download()
+    for name, rows in ROWS.items():
+        if not sfs and name in ("SFS", "C"):
+            assert np.array_equal(pf.particles[rows], ref[rows])
+            continue
+        assert relerr(pf.particles[rows, :pf.np], ref[rows, :pf.np]) < 1e-11, name
+    st = ref[42, :pf.np] != 0
+    assert np.array_equal(pf.particles[0:9, :pf.np][:, st], ref[0:9, :pf.np][:, st])  # static particles do not move
+
+
+def test_formulations_and_classic_scheme(vpm, handle):
+    for f, g, transposed in ((0.0, 0.0, True), (0.5, 0.0, True), (0.25, 0.25, False)):
+        pf = make_field(vpm, vpm.gaussianerf)
+        pf.transposed = transposed
+        ref = pf.particles.copy(order="F")
+        # (no clipping with the classic scheme on this symmetric ring: Gamma . SFS is zero to
+        # rounding there, so the sign test of clipping_backscatter is decided by noise)
+        kw = dict(integration="rungekutta3", f=f, g=g, sfs=True, Cs=1.0, clip_backscatter=transposed,
+                  relaxation="pedrizzetti", relax=True)
+        rf = vpm.ResidentField(pf)
+        rf.nextstep(1e-2, **kw)
+        oracle.field_step(ref, pf.np, "gaussianerf", 1e-2, transposed=transposed, **kw)
+        rf.download()
+        for name, rows in ROWS.items():
+            assert relerr(pf.particles[rows, :pf.np], ref[rows, :pf.np]) < 1e-11, (f, g, name)
+
+
+def test_resident_uj_equals_hook1(vpm, handle):
+    pf = vpm.fields.cloud_field(3000, kernel=vpm.winckelmans, static_fraction=0.1)
+    vpm.fields.random_results(pf, scale=1e-3)
+    a = pf.particles.copy(order="F")
+    rf = vpm.ResidentField(pf)
+    rf.UJ(sfs=True, reset=True, reset_sfs=True)
+    rf.download()
+    b = pf.particles.copy(order="F")
+    pf.particles[:] = a
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    assert np.array_equal(b, pf.particles)   # same kernels, same order: bit-identical
+
+
+@pytest.mark.parametrize("integration", ["euler", "rungekutta3"])
+def test_single_ring_speed_on_device(vpm, handle, integration):
+    """test/runtests_singlevortexring.jl rows 1-2, every step on the GPU"""
+    Nphi, nc, R, Rtot, beta, faux, nsteps = 100, 0, 1.0, 2.0, 0.5, 0.25, 50
+    Rcross = 0.15 * R
+    Uref = vpm.fields.Uring(1.0, R, Rcross, beta)
+    dt = (Rtot / Uref) / nsteps
+    pf = vpm.ParticleField(vpm.fields.number_particles(Nphi, nc), kernel=vpm.winckelmans)
+    vpm.fields.addvortexring(pf, 1.0, R, 1.0, faux * Rcross, Nphi, nc, Rcross)
+    rf = vpm.ResidentField(pf)
+    for _ in range(nsteps):
+        rf.nextstep(dt, integration=integration, f=0.0, g=0.0, relaxation="pedrizzetti", relax=True, rlxf=0.3)
+    rf.download()
+    U_vpm = np.linalg.norm(physics.ring_centroid_weighted(pf)) / (dt * nsteps)
+    assert abs((U_vpm - Uref) / Uref) < 0.02
+
+
+def test_step_needs_resident_field(vpm):
+    h = vpm.Handle(1)
+    try:
+        sp = vpm._cabi.VpmStepParams()
+        sp.kernel_id = 3
+        import ctypes
+        assert h.lib.vpm_field_step(h.ptr, ctypes.byref(sp)) == -6
+        assert b"vpm_field_upload" in h.lib.vpm_last_error(h.ptr)
+    finally:
+        h.close()
