@@ -191,7 +191,17 @@ def rvpm_step_c2(vpm, h):
         physics.rk3_step(pf, dt, UJ, f=0.0, g=0.2, relax=True, sfs=True, zeta0=zeta0)
     wall = (time.perf_counter() - t) / k
     h.check(h.lib.vpm_unpin_host(h.ptr, P.ctypes.data))
+    # the same step with the field resident on the device (vpm_field_step)
+    rf = vpm.ResidentField(pf, handle=h)
+    kw = dict(integration="rungekutta3", f=0.0, g=0.2, sfs=True, Cs=1.0, relaxation="pedrizzetti", relax=True)
+    rf.nextstep(dt, **kw)
+    t = time.perf_counter()
+    for _ in range(k):
+        rf.nextstep(dt, **kw)
+    dev_wall = (time.perf_counter() - t) / k
+    rf.download()
     return {"n_particles": pf.np, "kernel": "gaussianerf", "ms_per_step": wall * 1e3, "gpu_ms_per_step": gpu_ms[0] / k,
+            "device_resident_ms_per_step": dev_wall * 1e3,
             "what": "3 x (U/J + SFS) + 1 x U/J (relaxation) through UJ_direct(pfield) with host buffers; "
                     "O(N) RK3/rVPM/relaxation updates on the host in numpy; constant SFS coefficient "
                     "(the dynamic procedure adds one more U/J + SFS call per step)"}

@@ -196,6 +196,45 @@ function zeta_cuda(pfield::vpm.ParticleField{Float64})
     return nothing
 end
 
+# ------------------------------------------------------------------------------
+# Optional: the integrator on the device (include/vpm_cuda.h vpm_field_*).  Mirrors
+# `nextstep` (src/FLOWVPM_particlefield.jl:435-460) for ReformulatedVPM{f,g}, NoSFS /
+# ConstantSFS, Inviscid, relaxation pedrizzetti / correctedpedrizzetti.
+# ------------------------------------------------------------------------------
+struct StepParams
+    dt::Cdouble; f::Cdouble; g::Cdouble; Uinf::NTuple{3,Cdouble}; Cs::Cdouble; rlxf::Cdouble
+    kernel_id::Int32; integration::Int32; relaxation::Int32; relax::Int32
+    sfs::Int32; clip_backscatter::Int32; transposed::Int32; reserved::Int32
+end
+
+function upload!(pfield::vpm.ParticleField{Float64})
+    P = pfield.particles
+    GC.@preserve P check(ccall((:vpm_field_upload, lib[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64),
+                               handle[], P, size(P, 1), pfield.np))
+end
+
+function download!(pfield::vpm.ParticleField{Float64})
+    P = pfield.particles
+    GC.@preserve P check(ccall((:vpm_field_download, lib[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64),
+                               handle[], P, size(P, 1), pfield.np))
+end
+
+function nextstep_cuda!(pfield::vpm.ParticleField{Float64}, dt::Real; relax::Bool=false, Cs::Real=1.0,
+                        clip_backscatter::Bool=false)
+    form = pfield.formulation
+    rlx = pfield.relaxation
+    relaxation = rlx.relax === vpm.relax_pedrizzetti ? 1 : rlx.relax === vpm.relax_correctedpedrizzetti ? 2 : 0
+    integration = pfield.integration === vpm.rungekutta3 ? 1 : 0
+    Uinf = pfield.Uinf(pfield.t)
+    sp = Ref(StepParams(dt, form.f, form.g, (Uinf[1], Uinf[2], Uinf[3]), Cs, rlx.rlxf, kernel_id(pfield.kernel),
+                        integration, relaxation, relax, vpm.isSFSenabled(pfield.SFS), clip_backscatter,
+                        pfield.transposed, 0))
+    check(ccall((:vpm_field_step, lib[]), Cint, (Ptr{Cvoid}, Ref{StepParams}), handle[], sp))
+    pfield.t += dt
+    pfield.nt += 1
+    return nothing
+end
+
 export UJ_cuda, zeta_cuda
 
 end # module
