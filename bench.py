@@ -199,9 +199,19 @@ def rvpm_step_c2(vpm, h):
     for _ in range(k):
         rf.nextstep(dt, **kw)
     dev_wall = (time.perf_counter() - t) / k
+    # ... and with the DynamicSFS pseudo-3-level procedure (configs[1] as the reference runs it:
+    # 4 x (U/J + SFS) + 1 x U/J per step), also resident
+    kwd = dict(integration="rungekutta3", f=0.0, g=0.2, sfs="dynamic", clip_backscatter=True, alpha=0.999,
+               sfs_rlxf=0.005, minC=0.0, maxC=1.0, force_positive=True, relaxation="correctedpedrizzetti", relax=True)
+    rf.nextstep(dt, **kwd)
+    t = time.perf_counter()
+    for _ in range(k):
+        rf.nextstep(dt, **kwd)
+    dyn_wall = (time.perf_counter() - t) / k
     rf.download()
     return {"n_particles": pf.np, "kernel": "gaussianerf", "ms_per_step": wall * 1e3, "gpu_ms_per_step": gpu_ms[0] / k,
             "device_resident_ms_per_step": dev_wall * 1e3,
+            "device_resident_dynamic_sfs_ms_per_step": dyn_wall * 1e3,
             "what": "3 x (U/J + SFS) + 1 x U/J (relaxation) through UJ_direct(pfield) with host buffers; "
                     "O(N) RK3/rVPM/relaxation updates on the host in numpy; constant SFS coefficient "
                     "(the dynamic procedure adds one more U/J + SFS call per step)"}

@@ -1538,19 +1538,43 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
   CK(h, cudaSetDevice(d.id));
   const int64_t np = h->fld_np;
   if (np == 0) return VPM_OK;
+  const int tr = sp->transposed ? VPM_FLAG_TRANSPOSED : 0;
+  const int uj_flags = VPM_FLAG_RESET | tr | (sp->sfs ? (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS) : 0);
+  const unsigned nb = blocks_for(np, 256);
   StepArgs a;
   a.P = (double *)d.fld.p; a.nf = h->fld_nf; a.np = np;
   a.a = 1.0; a.b = 1.0; a.dt = sp->dt; a.Ux = sp->Uinf[0]; a.Uy = sp->Uinf[1]; a.Uz = sp->Uinf[2];
   a.f = sp->f; a.g = sp->g; a.zeta0 = zeta0_of(sp->kernel_id); a.Cs = sp->Cs; a.rlxf = sp->rlxf;
   a.transposed = sp->transposed; a.sfs = sp->sfs; a.clip = sp->clip_backscatter; a.relax_kind = sp->relaxation;
-  const int tr = sp->transposed ? VPM_FLAG_TRANSPOSED : 0;
-  const int uj_flags = VPM_FLAG_RESET | tr | (sp->sfs ? (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS) : 0);
-  const unsigned nb = blocks_for(np, 256);
+  a.alpha = sp->alpha; a.sfs_rlxf = sp->sfs_rlxf; a.minC = sp->minC; a.maxC = sp->maxC;
+  a.force_positive = sp->force_positive;
+  if (sp->sfs < 0 || sp->sfs > 2) return fail(h, VPM_EINVAL, "vpm_field_step: sfs must be 0 (none), 1 (constant) or 2 (dynamic)");
+  if (sp->sfs == 2 && (sp->minC < 0 || sp->maxC < 0 || sp->minC > sp->maxC || sp->alpha <= 0))
+    return fail(h, VPM_EINVAL, "vpm_field_step: invalid DynamicSFS parameters (minC=%g maxC=%g alpha=%g)", sp->minC, sp->maxC, sp->alpha);
+  TRY(ensure(h, d.ibuf, 4096));
+  a.nan_flag = (int *)d.ibuf.p;
+  CK(h, cudaMemsetAsync(a.nan_flag, 0, sizeof(int), st));
+  // the SFS hooks around a UJ evaluation at an Euler step / the first RK substep
+  // (src/FLOWVPM_subfilterscale.jl:110-135 ConstantSFS, :204-268 DynamicSFS)
+  auto sfs_before = [&]() -> int {
+    if (sp->sfs != 2) return VPM_OK;
+    step_scale_sigma<<<nb, 256, 0, st>>>(a, 0);
+    TRY(field_uj(h, d, sp->kernel_id, VPM_FLAG_RESET | VPM_FLAG_RESET_SFS | VPM_FLAG_SFS | tr));
+    step_dyn_store<<<nb, 256, 0, st>>>(a);
+    step_scale_sigma<<<nb, 256, 0, st>>>(a, 1);
+    h->launches += 3;
+    return VPM_OK;
+  };
+  auto sfs_after = [&]() {
+    if (sp->sfs == 1) { step_sfs_coeff<<<nb, 256, 0, st>>>(a); h->launches++; }
+    if (sp->sfs == 2) { step_dyn_coeff<<<nb, 256, 0, st>>>(a); h->launches++; }
+  };
   CK(h, cudaEventRecord(d.ev[0], st));
   CK(h, cudaEventRecord(d.ev[1], st));
   if (sp->integration == 0) {  // euler: src/FLOWVPM_timeintegration.jl:23-37
+    TRY(sfs_before());
     TRY(field_uj(h, d, sp->kernel_id, uj_flags));
-    if (sp->sfs) { step_sfs_coeff<<<nb, 256, 0, st>>>(a); h->launches++; }
+    sfs_after();
     step_euler<<<nb, 256, 0, st>>>(a, sp->relax ? 1 : 0);
     h->launches++;
   } else {  // rungekutta3: src/FLOWVPM_timeintegration.jl:388-461
@@ -1559,8 +1583,9 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
     const double ab[3][2] = {{0.0, 1.0 / 3}, {-5.0 / 9, 15.0 / 16}, {-153.0 / 128, 8.0 / 15}};
     for (int k = 0; k < 3; ++k) {
       a.a = ab[k][0]; a.b = ab[k][1];
+      if (k == 0) TRY(sfs_before());
       TRY(field_uj(h, d, sp->kernel_id, uj_flags));
-      if (sp->sfs && k == 0) { step_sfs_coeff<<<nb, 256, 0, st>>>(a); h->launches++; }
+      if (k == 0) sfs_after();
       step_rk_stage<<<nb, 256, 0, st>>>(a);
       h->launches++;
     }
@@ -1572,9 +1597,12 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
   }
   CK(h, cudaGetLastError());
   for (int k = 2; k <= 5; ++k) CK(h, cudaEventRecord(d.ev[k], st));
+  int nan_flag = 0;
+  CK(h, cudaMemcpyAsync(&nan_flag, a.nan_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(h, cudaStreamSynchronize(st));
   h1_fill_timing(h, d);
   h->timing.uj_ms = h->timing.total_ms;
+  if (nan_flag) return fail(h, VPM_ESTATE, "NaN in dynamicprocedure_pseudo3level_afterUJ");  // subfilterscale.jl:645-652
   return VPM_OK;
 }
 

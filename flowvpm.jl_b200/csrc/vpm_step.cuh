@@ -6,8 +6,11 @@
 //   euler / _euler for ReformulatedVPM{f,g}                        src/FLOWVPM_timeintegration.jl:23-37,103-173
 //   relax_pedrizzetti / relax_correctedpedrizzetti                 src/FLOWVPM_relaxation.jl:62-142
 //   ConstantSFS AfterUJ hook + clipping_backscatter                src/FLOWVPM_subfilterscale.jl:110-135,287-296
-// Covered: cVPM / rVPM / any (f, g), NoSFS and ConstantSFS (optional backscatter clipping),
-// Inviscid, constant Uinf.  Not covered (stays in Julia): DynamicSFS procedure, viscous schemes.
+//   DynamicSFS pseudo-3-level procedure (before / after UJ)         src/FLOWVPM_subfilterscale.jl:447-673
+// Covered: cVPM / rVPM / any (f, g); NoSFS, ConstantSFS and DynamicSFS (pseudo3level, optional
+// force_positive and backscatter clipping); Inviscid; constant Uinf.  Not covered (stays in
+// Julia): SFS control strategies (sigma / magnitude sensors), the sensor-function procedure,
+// viscous schemes.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -21,7 +24,10 @@ struct StepArgs {
   double Ux, Uy, Uz;  // Uinf
   double f, g, zeta0;
   double Cs, rlxf;
-  int transposed, sfs, clip, relax_kind;  // relax_kind: 0 none, 1 pedrizzetti, 2 corrected
+  double alpha, sfs_rlxf, minC, maxC;  // DynamicSFS (src/FLOWVPM_subfilterscale.jl:167-202)
+  int transposed, sfs, clip, relax_kind;  // sfs: 0 none, 1 constant, 2 dynamic; relax_kind: 0 none, 1 pedrizzetti, 2 corrected
+  int force_positive;
+  int *nan_flag;  // set when the dynamic procedure produces a NaN coefficient (:645-652)
 };
 
 // rows, 0-based (src/FLOWVPM_particlefield.jl:239-252)
@@ -82,6 +88,76 @@ __global__ void step_sfs_coeff(StepArgs a) {
     if (C * d < 0.0) C = 0.0;
   }
   p[S_C] = C;
+}
+
+// ---- DynamicSFS, pseudo-3-level procedure -------------------------------------------
+// sigma *= alpha (test filter) / sigma /= alpha (back to the domain filter), non-static only
+// (src/FLOWVPM_subfilterscale.jl:464-475, 525-536)
+__global__ void step_scale_sigma(StepArgs a, int divide) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+  if (divide) p[S_SIGMA] /= a.alpha; else p[S_SIGMA] *= a.alpha;
+}
+
+// after the test-filter UJ: M <- 0, M[1:3] <- stretching, M[4:6] <- SFS (:480-521)
+__global__ void step_dyn_store(StepArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+  double *M = p + S_M;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) M[k] = 0.0;
+  stretching(p + S_J, p + S_G, a.transposed, M[0], M[1], M[2]);
+  M[3] = p[S_SFS]; M[4] = p[S_SFS + 1]; M[5] = p[S_SFS + 2];
+}
+
+__device__ __forceinline__ double jl_sign(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : x); }
+
+// after the domain-filter UJ: differences, Lagrangian-averaged C = <Gamma.L>/<Gamma.m> with
+// clamps, M flushed (:556-670)
+__global__ void step_dyn_coeff(StepArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+  double *M = p + S_M, *Cp = p + S_C;
+  const double *G = p + S_G;
+  double m1, m2, m3;
+  stretching(p + S_J, G, a.transposed, m1, m2, m3);
+  M[0] -= m1; M[1] -= m2; M[2] -= m3;
+  M[3] -= p[S_SFS]; M[4] -= p[S_SFS + 1]; M[5] -= p[S_SFS + 2];
+  double nume = M[0] * G[0] + M[1] * G[1] + M[2] * G[2];
+  nume *= 3 * a.alpha - 2;
+  double deno = M[3] * G[0] + M[4] * G[1] + M[5] * G[2];
+  const double sg = p[S_SIGMA];
+  deno /= a.zeta0 / (sg * sg * sg);
+  if (Cp[2] == 0.0) {
+    Cp[2] = deno;
+    if (Cp[2] == 0.0) Cp[2] = 2.220446049250313e-16;  // eps()
+  }
+  nume = a.sfs_rlxf * nume + (1 - a.sfs_rlxf) * Cp[1];
+  deno = a.sfs_rlxf * deno + (1 - a.sfs_rlxf) * Cp[2];
+  if (fabs(nume / deno) > a.maxC) {
+    if (fabs(deno) < fabs(Cp[2])) deno = jl_sign(deno) * fabs(Cp[2]);
+    if (fabs(nume / deno) >= a.maxC) nume = jl_sign(nume) * fabs(deno) * a.maxC;
+  } else if (fabs(nume / deno) < a.minC) {
+    nume = jl_sign(nume) * fabs(deno) * a.minC;
+  }
+  Cp[1] = nume;
+  Cp[2] = deno;
+  double C = Cp[1] / Cp[2];
+  if (C != C) atomicExch(a.nan_flag, 1);
+  if (a.force_positive) C *= jl_sign(C);
+  if (a.clip) {
+    const double d = G[0] * p[S_SFS] + G[1] * p[S_SFS + 1] + G[2] * p[S_SFS + 2];
+    if (C * d < 0.0) C *= 0.0;
+  }
+  Cp[0] = C;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) M[k] = 0.0;
 }
 
 // the Z and dGamma terms shared by the Euler and RK updates (:505-521, :145-160)

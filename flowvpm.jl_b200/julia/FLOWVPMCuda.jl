@@ -199,12 +199,13 @@ end
 # ------------------------------------------------------------------------------
 # Optional: the integrator on the device (include/vpm_cuda.h vpm_field_*).  Mirrors
 # `nextstep` (src/FLOWVPM_particlefield.jl:435-460) for ReformulatedVPM{f,g}, NoSFS /
-# ConstantSFS, Inviscid, relaxation pedrizzetti / correctedpedrizzetti.
+# ConstantSFS / DynamicSFS (pseudo3level), Inviscid, relaxation pedrizzetti / correctedpedrizzetti.
 # ------------------------------------------------------------------------------
 struct StepParams
     dt::Cdouble; f::Cdouble; g::Cdouble; Uinf::NTuple{3,Cdouble}; Cs::Cdouble; rlxf::Cdouble
+    alpha::Cdouble; sfs_rlxf::Cdouble; minC::Cdouble; maxC::Cdouble
     kernel_id::Int32; integration::Int32; relaxation::Int32; relax::Int32
-    sfs::Int32; clip_backscatter::Int32; transposed::Int32; reserved::Int32
+    sfs::Int32; clip_backscatter::Int32; transposed::Int32; force_positive::Int32
 end
 
 function upload!(pfield::vpm.ParticleField{Float64})
@@ -219,16 +220,20 @@ function download!(pfield::vpm.ParticleField{Float64})
                                handle[], P, size(P, 1), pfield.np))
 end
 
-function nextstep_cuda!(pfield::vpm.ParticleField{Float64}, dt::Real; relax::Bool=false, Cs::Real=1.0,
-                        clip_backscatter::Bool=false)
+function nextstep_cuda!(pfield::vpm.ParticleField{Float64}, dt::Real; relax::Bool=false,
+                        clip_backscatter::Bool=false, force_positive::Bool=false)
     form = pfield.formulation
+    S = pfield.SFS
+    sfs = S isa vpm.DynamicSFS ? 2 : (vpm.isSFSenabled(S) ? 1 : 0)
+    Cs = S isa vpm.ConstantSFS ? S.Cs : 1.0
+    alpha, sfs_rlxf, minC, maxC = S isa vpm.DynamicSFS ? (S.alpha, S.rlxf, S.minC, S.maxC) : (0.667, 0.005, 0.0, 1.0)
     rlx = pfield.relaxation
     relaxation = rlx.relax === vpm.relax_pedrizzetti ? 1 : rlx.relax === vpm.relax_correctedpedrizzetti ? 2 : 0
     integration = pfield.integration === vpm.rungekutta3 ? 1 : 0
     Uinf = pfield.Uinf(pfield.t)
-    sp = Ref(StepParams(dt, form.f, form.g, (Uinf[1], Uinf[2], Uinf[3]), Cs, rlx.rlxf, kernel_id(pfield.kernel),
-                        integration, relaxation, relax, vpm.isSFSenabled(pfield.SFS), clip_backscatter,
-                        pfield.transposed, 0))
+    sp = Ref(StepParams(dt, form.f, form.g, (Uinf[1], Uinf[2], Uinf[3]), Cs, rlx.rlxf, alpha, sfs_rlxf, minC, maxC,
+                        kernel_id(pfield.kernel), integration, relaxation, relax, sfs, clip_backscatter,
+                        pfield.transposed, force_positive))
     check(ccall((:vpm_field_step, lib[]), Cint, (Ptr{Cvoid}, Ref{StepParams}), handle[], sp))
     pfield.t += dt
     pfield.nt += 1

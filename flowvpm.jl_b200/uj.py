@@ -211,15 +211,24 @@ class ResidentField:
         self.h.check(self.h.lib.vpm_field_uj(self.h.ptr, self.pfield.kernel.id,
                                              _flags(self.pfield, sfs, reset, reset_sfs)))
 
+    SFS_SCHEMES = {False: 0, None: 0, "none": 0, True: 1, "constant": 1, "dynamic": 2}
+
     def nextstep(self, dt, *, integration="rungekutta3", f=0.0, g=0.2, Uinf=(0.0, 0.0, 0.0), sfs=False, Cs=1.0,
-                 clip_backscatter=False, relaxation="pedrizzetti", relax=True, rlxf=0.3):
+                 clip_backscatter=False, relaxation="pedrizzetti", relax=True, rlxf=0.3, alpha=0.667,
+                 sfs_rlxf=0.005, minC=0.0, maxC=1.0, force_positive=False):
+        """sfs: False | "constant" (ConstantSFS, coefficient Cs) | "dynamic" (DynamicSFS with the
+        pseudo-3-level procedure: alpha, sfs_rlxf, minC, maxC, force_positive)"""
+        if minC < 0 or maxC < 0 or minC > maxC:
+            raise ValueError(f"Invalid C bounds: minC={minC}, maxC={maxC}")  # subfilterscale.jl:456-462
         sp = _cabi.VpmStepParams()
         sp.dt, sp.f, sp.g, sp.Cs, sp.rlxf = dt, f, g, Cs, rlxf
+        sp.alpha, sp.sfs_rlxf, sp.minC, sp.maxC = alpha, sfs_rlxf, minC, maxC
+        sp.force_positive = int(force_positive)
         sp.Uinf[0], sp.Uinf[1], sp.Uinf[2] = Uinf
         sp.kernel_id = self.pfield.kernel.id
         sp.integration = self.INTEGRATIONS[integration]
         sp.relaxation = self.RELAXATIONS[relaxation]
-        sp.relax, sp.sfs, sp.clip_backscatter = int(relax), int(sfs), int(clip_backscatter)
+        sp.relax, sp.sfs, sp.clip_backscatter = int(relax), self.SFS_SCHEMES[sfs], int(clip_backscatter)
         sp.transposed = int(self.pfield.transposed)
         self.h.check(self.h.lib.vpm_field_step(self.h.ptr, C.byref(sp)))
         self.pfield.t += dt

@@ -157,22 +157,27 @@ int vpm_zeta_leafpairs(vpm_handle *h, double *particles, int64_t nfields, int64_
  *   euler / _euler:                                             src/FLOWVPM_timeintegration.jl:23-37,103-173
  *   relaxation (pedrizzetti / correctedpedrizzetti):            src/FLOWVPM_relaxation.jl:62-142
  *   ConstantSFS hook + clipping_backscatter:                    src/FLOWVPM_subfilterscale.jl:110-135,287-296
- * Covered: any (f, g) incl. cVPM (0,0) and rVPM (0,1/5); NoSFS / ConstantSFS; Inviscid; constant
- * Uinf.  DynamicSFS and the viscous schemes stay in the reference's Julia code (use Hook 1). */
+ *   DynamicSFS pseudo-3-level procedure:                        src/FLOWVPM_subfilterscale.jl:447-673
+ * Covered: any (f, g) incl. cVPM (0,0) and rVPM (0,1/5); NoSFS / ConstantSFS / DynamicSFS
+ * (pseudo3level, force_positive, clipping_backscatter); Inviscid; constant Uinf.  SFS control
+ * strategies and the viscous schemes stay in the reference's Julia code (use Hook 1). */
 typedef struct vpm_step_params {
   double dt;
   double f, g;        /* ReformulatedVPM{f,g}: src/FLOWVPM_formulation.jl:23-37 */
   double Uinf[3];     /* pfield.Uinf(t), constant over the step */
   double Cs;          /* ConstantSFS model coefficient */
   double rlxf;        /* relaxation factor (0.3 in the reference's presets, src/FLOWVPM.jl:169-170) */
+  double alpha;       /* DynamicSFS: test-filter scaling (default 0.667) */
+  double sfs_rlxf;    /* DynamicSFS: Lagrangian-average relaxation (default 0.005) */
+  double minC, maxC;  /* DynamicSFS: bounds of |C| (defaults 0, 1) */
   int32_t kernel_id;
   int32_t integration;      /* 0 euler, 1 rungekutta3 */
   int32_t relaxation;       /* 0 none, 1 pedrizzetti, 2 correctedpedrizzetti */
   int32_t relax;            /* apply relaxation in this step (run_vpm!'s `relax`, src/FLOWVPM_utils.jl:94-96) */
-  int32_t sfs;              /* 0 NoSFS, 1 ConstantSFS */
-  int32_t clip_backscatter; /* ConstantSFS clippings = (clipping_backscatter,) */
+  int32_t sfs;              /* 0 NoSFS, 1 ConstantSFS, 2 DynamicSFS (pseudo3level) */
+  int32_t clip_backscatter; /* clippings = (clipping_backscatter,) */
   int32_t transposed;       /* pfield.transposed */
-  int32_t reserved;
+  int32_t force_positive;   /* DynamicSFS: pseudo3level_positive */
 } vpm_step_params;
 int vpm_field_upload(vpm_handle *h, const double *particles, int64_t nfields, int64_t np);
 int vpm_field_download(vpm_handle *h, double *particles, int64_t nfields, int64_t np);

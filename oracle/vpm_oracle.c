@@ -527,17 +527,91 @@ static void o_rates(const double *p, double f, double g, double zeta0, int trans
   for (int k = 0; k < 3; ++k) eps[k] = C * p[R_SFS + k] * (sg * sg * sg) / zeta0;
 }
 
+/* dynamicprocedure_pseudo3level_beforeUJ: src/FLOWVPM_subfilterscale.jl:447-539 */
+static void o_dyn_before(double *P, int64_t nf, int64_t np, int kernel, int transposed, double alpha, int nthreads) {
+  for (int64_t i = 0; i < np; ++i)
+    if (P[nf * i + R_STATIC] == 0.0) P[nf * i + R_SIGMA] *= alpha;
+  vpm_oracle_uj_direct(P, nf, np, kernel,
+                       VPM_FLAG_RESET | VPM_FLAG_RESET_SFS | VPM_FLAG_SFS | (transposed ? VPM_FLAG_TRANSPOSED : 0),
+                       nthreads);
+  for (int64_t i = 0; i < np; ++i) {
+    double *p = P + nf * i;
+    if (p[R_STATIC] != 0.0) continue;
+    double *M = p + R_M;
+    for (int k = 0; k < 9; ++k) M[k] = 0.0;
+    o_stretch(p + R_J, p + R_G, transposed, M);
+    M[3] = p[R_SFS]; M[4] = p[R_SFS + 1]; M[5] = p[R_SFS + 2];
+  }
+  for (int64_t i = 0; i < np; ++i)
+    if (P[nf * i + R_STATIC] == 0.0) P[nf * i + R_SIGMA] /= alpha;
+}
+
+/* dynamicprocedure_pseudo3level_afterUJ (:541-673) followed by the DynamicSFS clipping (:225-243) */
+static int o_dyn_after(double *P, int64_t nf, int64_t np, int kernel, int transposed, double alpha, double rlxf,
+                       double minC, double maxC, int force_positive, int clip) {
+  const double zeta0 = zeta_fn(kernel, 0.0);
+  for (int64_t i = 0; i < np; ++i) {
+    double *p = P + nf * i;
+    if (p[R_STATIC] != 0.0) continue;
+    double *M = p + R_M, MM[3];
+    o_stretch(p + R_J, p + R_G, transposed, MM);
+    M[0] -= MM[0]; M[1] -= MM[1]; M[2] -= MM[2];
+    M[3] -= p[R_SFS]; M[4] -= p[R_SFS + 1]; M[5] -= p[R_SFS + 2];
+  }
+  for (int64_t i = 0; i < np; ++i) {
+    double *p = P + nf * i;
+    if (p[R_STATIC] != 0.0) continue;
+    double *M = p + R_M, *C_p = p + R_C;
+    const double *Gamma = p + R_G;
+    double nume = M[0] * Gamma[0] + M[1] * Gamma[1] + M[2] * Gamma[2];
+    nume *= 3 * alpha - 2;
+    double deno = M[3] * Gamma[0] + M[4] * Gamma[1] + M[5] * Gamma[2];
+    deno /= zeta0 / (p[R_SIGMA] * p[R_SIGMA] * p[R_SIGMA]);
+    if (C_p[2] == 0) {
+      C_p[2] = deno;
+      if (C_p[2] == 0) C_p[2] = 2.220446049250313e-16;
+    }
+    nume = rlxf * nume + (1 - rlxf) * C_p[1];
+    deno = rlxf * deno + (1 - rlxf) * C_p[2];
+    if (fabs(nume / deno) > maxC) {
+      if (fabs(deno) < fabs(C_p[2])) deno = jl_sign(deno) * fabs(C_p[2]);
+      if (fabs(nume / deno) >= maxC) nume = jl_sign(nume) * fabs(deno) * maxC;
+    } else if (fabs(nume / deno) < minC) {
+      nume = jl_sign(nume) * fabs(deno) * minC;
+    }
+    C_p[1] = nume;
+    C_p[2] = deno;
+    C_p[0] = C_p[1] / C_p[2];
+    if (C_p[0] != C_p[0]) return -3;
+    if (force_positive) C_p[0] *= jl_sign(C_p[0]);
+  }
+  for (int64_t i = 0; i < np; ++i)
+    if (P[nf * i + R_STATIC] == 0.0)
+      for (int k = 0; k < 9; ++k) P[nf * i + R_M + k] = 0.0;
+  if (clip)
+    for (int64_t i = 0; i < np; ++i) {
+      double *p = P + nf * i;
+      if (p[R_STATIC] != 0.0) continue;
+      if (p[R_C] * (p[R_G] * p[R_SFS] + p[R_G + 1] * p[R_SFS + 1] + p[R_G + 2] * p[R_SFS + 2]) < 0) p[R_C] *= 0;
+    }
+  return 0;
+}
+
 int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, const double *dp, const int *ip, int nthreads) {
   init_consts();
   const double dt = dp[0], f = dp[1], g = dp[2], Uinf[3] = {dp[3], dp[4], dp[5]}, Cs = dp[6], rlxf = dp[7];
+  const double alpha = dp[8], sfs_rlxf = dp[9], minC = dp[10], maxC = dp[11];
   const int kernel = ip[0], integration = ip[1], relaxation = ip[2], relax = ip[3], sfs = ip[4], clip = ip[5],
-            transposed = ip[6];
+            transposed = ip[6], force_positive = ip[7];
   const double zeta0 = zeta_fn(kernel, 0.0);
   const int tr = transposed ? VPM_FLAG_TRANSPOSED : 0;
   const int uj_flags = VPM_FLAG_RESET | tr | (sfs ? (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS) : 0);
   if (integration == 0) {
+    if (sfs == 2) o_dyn_before(P, nf, np, kernel, transposed, alpha, nthreads);
     vpm_oracle_uj_direct(P, nf, np, kernel, uj_flags, nthreads);
-    if (sfs) o_sfs_coeff(P, nf, np, Cs, clip);
+    if (sfs == 1) o_sfs_coeff(P, nf, np, Cs, clip);
+    if (sfs == 2 && o_dyn_after(P, nf, np, kernel, transposed, alpha, sfs_rlxf, minC, maxC, force_positive, clip))
+      return -3;
     for (int64_t i = 0; i < np; ++i) {
       double *p = P + nf * i;
       if (p[R_STATIC] != 0.0) continue;
@@ -556,8 +630,12 @@ int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, const double *dp, c
   const double ab[3][2] = {{0.0, 1.0 / 3}, {-5.0 / 9, 15.0 / 16}, {-153.0 / 128, 8.0 / 15}};
   for (int s_ = 0; s_ < 3; ++s_) {
     const double a = ab[s_][0], b = ab[s_][1];
+    if (sfs == 2 && a == 0.0) o_dyn_before(P, nf, np, kernel, transposed, alpha, nthreads);
     vpm_oracle_uj_direct(P, nf, np, kernel, uj_flags, nthreads);
-    if (sfs && a == 0.0) o_sfs_coeff(P, nf, np, Cs, clip);
+    if (sfs == 1 && a == 0.0) o_sfs_coeff(P, nf, np, Cs, clip);
+    if (sfs == 2 && a == 0.0 &&
+        o_dyn_after(P, nf, np, kernel, transposed, alpha, sfs_rlxf, minC, maxC, force_positive, clip))
+      return -3;
     for (int64_t i = 0; i < np; ++i) {
       double *p = P + nf * i;
       if (p[R_STATIC] != 0.0) continue;

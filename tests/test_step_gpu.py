@@ -45,6 +45,27 @@ def test_step_matches_oracle(vpm, handle, integration, sfs, clip, relaxation):
     assert np.array_equal(pf.particles[0:9, :pf.np][:, st], ref[0:9, :pf.np][:, st])  # static particles do not move
 
 
+@pytest.mark.parametrize("integration", ["euler", "rungekutta3"])
+@pytest.mark.parametrize("force_positive,clip,alpha", [(False, False, 0.667), (True, True, 0.9), (False, True, 0.999)])
+def test_dynamic_sfs_step_matches_oracle(vpm, handle, integration, force_positive, clip, alpha):
+    """DynamicSFS pseudo-3-level procedure (src/FLOWVPM_subfilterscale.jl:447-673) on the device:
+    three steps so that the Lagrangian averages <Gamma.L>, <Gamma.m> (C rows 2:3) evolve"""
+    pf = vpm.fields.cloud_field(1500, kernel=vpm.gaussianerf, static_fraction=0.05, seed=31)
+    ref = pf.particles.copy(order="F")
+    kw = dict(integration=integration, f=0.0, g=0.2, sfs="dynamic", clip_backscatter=clip, relaxation="pedrizzetti",
+              relax=True, rlxf=0.3, alpha=alpha, sfs_rlxf=0.3, minC=0.0, maxC=1.0, force_positive=force_positive)
+    rf = vpm.ResidentField(pf)
+    dt = 1e-3
+    for _ in range(3):
+        rf.nextstep(dt, **kw)
+        oracle.field_step(ref, pf.np, "gaussianerf", dt, transposed=True, **kw)
+    rf.download()
+    rows = dict(ROWS, C=slice(36, 39))
+    for name, r in rows.items():
+        assert relerr(pf.particles[r, :pf.np], ref[r, :pf.np]) < 1e-9, name
+    assert np.abs(ref[36, :pf.np]).max() > 0 and np.abs(ref[36, :pf.np]).max() <= 1.0
+
+
 def test_formulations_and_classic_scheme(vpm, handle):
     for f, g, transposed in ((0.0, 0.0, True), (0.5, 0.0, True), (0.25, 0.25, False)):
         pf = make_field(vpm, vpm.gaussianerf)
