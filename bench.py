@@ -243,6 +243,19 @@ def nearfield_extra(vpm, h, n):
     return out
 
 
+def ncu_traffic(n, kernel, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the pair kernel from the committed ncu
+    --set full capture (profiles/uj_pairs_traffic.json), if it was taken at this size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "uj_pairs_traffic.json")) as fh:
+            t = json.load(fh)
+        if t["n_particles"] == n and t["kernel"] == kernel and world == 1:
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
+
+
 # ------------------------------------------------------------------ B200 arm
 def main():
     args = parse()
@@ -380,7 +393,9 @@ def main():
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "fp64_fma", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / peak_tflops, "traffic": None,
+                     "frac": achieved_tflops / peak_tflops, "traffic": ncu_traffic(n, args.kernel, world),
+                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum; algorithmic: "
+                                     "80 B/source record + 112 B/target per source split)",
                      "kernel": f"uj_pairs_kernel<{args.kernel}>", "kernel_ms": kernel_ms,
                      "flop_per_interaction": F_UJ[args.kernel],
                      "peak_source": "2 x DFMA/s measured live by vpm_measure_dfma_peak on this GPU "

@@ -15,4 +15,7 @@ from vpm_import import vpm
 pf = vpm.fields.cloud_field(131072, kernel=vpm.winckelmans)
 vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
 " > gpurun_out/ncu_sfs_$R.log 2>&1
+# full-size capture of the bench kernel for roofline.traffic (one launch, ~40 replays of 3 s)
+ncu --set full --clock-control none -k regex:uj_pairs -s 1 -c 1 -o gpurun_out/prof_uj_1M_$R -f \
+    python bench.py --steps 1 --warmup 3 --no-extras > gpurun_out/ncu_uj_1M_$R.log 2>&1
 ls -la gpurun_out
