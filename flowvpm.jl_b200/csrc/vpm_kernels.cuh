@@ -24,7 +24,7 @@ namespace vpm {
 enum { K_SING = 0, K_GAUS = 1, K_GERF = 2, K_WINCK = 3 };
 
 constexpr int kRec = 10;      // doubles per U/J source record (80 B, 5 x LDS.128)
-constexpr int kSfsRec = 18;   // doubles per SFS source record (144 B, 9 x LDS.128)
+constexpr int kSfsRec = 12;   // doubles per SFS source record (96 B, 6 x LDS.128)
 constexpr int kTile = 128;    // sources per shared-memory tile
 constexpr int kThreads = 128; // threads per CTA of the pair kernels
 constexpr int kAcc = 14;      // U(3) + J(8, J33 implied) + W(3) partial sums per target
@@ -118,8 +118,18 @@ __global__ void prep_uj_records(SrcView src, int64_t s0, int64_t ns, int64_t ns_
   r[7] = q1; r[8] = q2; r[9] = q3;
 }
 
-// SFS record of source i: [x y z q0 | Gx Gy Gz q1 | J(row-of-3 order) 0], q0 = 1/s^2,
-// q1 = zeta-prefactor / s^3 (0 for sources the sweep must ignore).
+// (J row k) . Gamma with explicitly rounded operations: the SFS sweep evaluates it for the
+// target per pair and the record builder for the source once; using the SAME instruction
+// sequence on both sides makes (JT - JS) Gamma exactly zero when JT == JS.
+__device__ __forceinline__ double row_dot(double a0, double a1, double a2, double gx, double gy, double gz) {
+  return __fma_rn(a2, gz, __fma_rn(a1, gy, __dmul_rn(a0, gx)));
+}
+
+// SFS record of source i: [x y z q0 | Gx Gy Gz q1 | (J Gamma)_1..3 0].
+//   q1 = zeta-prefactor / sigma^3 (0 for sources the sweep must ignore; winckelmans:
+//   prefactor * sigma^4 because its weight is written on b = r^2 + sigma^2), q0 = 1/sigma^2
+//   (winckelmans: sigma^2).  (J Gamma)_k = sum_m J[3k+m] G_m in the transposed scheme,
+//   sum_m J[k+3m] G_m in the classic one (src/FLOWVPM_subfilterscale_models.jl:24-31).
 // src_index (nullable) maps record i -> particle column (leaf-list form).
 __global__ void prep_sfs_records(SrcView src, const double *__restrict__ J, int64_t jld, int joff,
                                  const double *__restrict__ stat, int64_t sld,
@@ -136,24 +146,32 @@ __global__ void prep_sfs_records(SrcView src, const double *__restrict__ J, int6
   }
   int64_t c = src_index ? src_index[i] : i;
   const double *p = src.p + c * src.ld;
-  double isig = 1.0 / p[src.osig];
+  const double sigma = p[src.osig];
+  double isig = 1.0 / sigma;
   double isig3 = isig * isig * isig;
   double pref = kernel == K_WINCK  ? kConst4 * 7.5
                 : kernel == K_GERF ? kConst1
                 : kernel == K_GAUS ? kConst3
                                    : 1.0;
   bool is_static = stat != nullptr && stat[c * sld] != 0.0;
-  r[0] = p[src.ox]; r[1] = p[src.ox + 1]; r[2] = p[src.ox + 2]; r[3] = isig * isig;
-  r[4] = p[src.og]; r[5] = p[src.og + 1]; r[6] = p[src.og + 2];
-  r[7] = is_static ? 0.0 : pref * isig3;
-  // J is stored so that S_k = sum_m D[3k+m] G_m in both schemes: the classic
-  // scheme reads the transpose (src/FLOWVPM_subfilterscale_models.jl:24-31)
+  const double gx = p[src.og], gy = p[src.og + 1], gz = p[src.og + 2];
+  r[0] = p[src.ox]; r[1] = p[src.ox + 1]; r[2] = p[src.ox + 2];
+  r[4] = gx; r[5] = gy; r[6] = gz;
+  if (kernel == K_WINCK) {
+    const double s2 = sigma * sigma;
+    r[3] = s2;
+    r[7] = is_static ? 0.0 : pref * (s2 * s2);
+  } else {
+    r[3] = isig * isig;
+    r[7] = is_static ? 0.0 : pref * isig3;
+  }
   const double *j = J + c * jld + joff;
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
-#pragma unroll
-    for (int m = 0; m < 3; ++m) r[8 + 3 * k + m] = transposed ? j[3 * k + m] : j[k + 3 * m];
-  r[17] = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    r[8 + k] = transposed ? row_dot(j[3 * k], j[3 * k + 1], j[3 * k + 2], gx, gy, gz)
+                          : row_dot(j[k], j[k + 3], j[k + 6], gx, gy, gz);
+  }
+  r[11] = 0.0;
 }
 
 // ------------------------------------------------------- per-pair kernel math
@@ -253,8 +271,9 @@ __device__ __forceinline__ void ab_gaus(double r2, double q0, double q1, double 
 template <int K>
 __device__ __forceinline__ double sfs_weight(double r2, double q0, double q1) {
   if constexpr (K == K_WINCK) {
-    double a = fma(r2, q0, 1.0);
-    double y = rsqrt_fp64(a);
+    // r2 here is b = r^2 + sigma^2 (formed by the caller's FMA chain), q1 = prefactor sigma^4:
+    // zeta(s)/sigma^3 = prefactor (s^2+1)^-7/2 / sigma^3 = prefactor sigma^4 b^-7/2
+    double y = rsqrt_fp64(r2);
     double y2 = y * y;
     double y4 = y2 * y2;
     return q1 * (y4 * y2 * y);
@@ -607,14 +626,15 @@ __device__ __forceinline__ void sfs_tile(const double2 *__restrict__ tile, int n
                                          double (&acc)[T][3], int shortcut) {
 #pragma unroll 2
   for (int j = 0; j < n; ++j) {
-    const double2 v0 = tile[j * 9 + 0];
-    const double2 v1 = tile[j * 9 + 1];
+    const double2 v0 = tile[j * 6 + 0];
+    const double2 v1 = tile[j * 6 + 1];
     const double sx = v0.x, sy = v0.y, sz = v1.x, q0 = v1.y;
     double r2[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       double dx = sx - tx[t], dy = sy - ty[t], dz = sz - tz[t];
-      r2[t] = fma(dz, dz, fma(dy, dy, dx * dx));
+      if constexpr (K == K_WINCK) r2[t] = fma(dz, dz, fma(dy, dy, fma(dx, dx, q0)));  // b = r^2 + sigma^2
+      else r2[t] = fma(dz, dz, fma(dy, dy, dx * dx));
     }
     if constexpr (K == K_GERF || K == K_GAUS) {
       const double far_u = (K == K_GERF) ? kSfsFarU_gerf : kSfsFarU_gaus;
@@ -623,8 +643,8 @@ __device__ __forceinline__ void sfs_tile(const double2 *__restrict__ tile, int n
       for (int t = 0; t < T; ++t) near |= (r2[t] * q0 < far_u);
       if (!__any_sync(0xffffffffu, near)) continue;
     }
-    const double2 v2 = tile[j * 9 + 2];
-    const double2 v3 = tile[j * 9 + 3];
+    const double2 v2 = tile[j * 6 + 2];
+    const double2 v3 = tile[j * 6 + 3];
     const double gx = v2.x, gy = v2.y, gz = v3.x, q1 = v3.y;
     if constexpr (MODE == MODE_ZETA) {
 #pragma unroll
@@ -636,21 +656,18 @@ __device__ __forceinline__ void sfs_tile(const double2 *__restrict__ tile, int n
       }
       continue;
     }
-    const double2 j0 = tile[j * 9 + 4], j1 = tile[j * 9 + 5], j2 = tile[j * 9 + 6],
-                  j3 = tile[j * 9 + 7], j4 = tile[j * 9 + 8];
-    const double JS[9] = {j0.x, j0.y, j1.x, j1.y, j2.x, j2.y, j3.x, j3.y, j4.x};
+    // S_k = (JT - JS)_k . Gamma_s evaluated as (JT_k . Gamma_s) - (JS_k . Gamma_s): the source
+    // half comes precomputed in the record (row_dot, identical rounding), so the pair costs
+    // 9 + 3 instead of 9 + 9 FP64 instructions and a uniform gradient still gives exactly 0.
+    const double2 v4 = tile[j * 6 + 4];
+    const double2 v5 = tile[j * 6 + 5];
+    const double qs1 = v4.x, qs2 = v4.y, qs3 = v5.x;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       double w = sfs_weight<K>(r2[t], q0, q1);
-      double S1 = (JT[t][0] - JS[0]) * gx;
-      S1 = fma(JT[t][1] - JS[1], gy, S1);
-      S1 = fma(JT[t][2] - JS[2], gz, S1);
-      double S2 = (JT[t][3] - JS[3]) * gx;
-      S2 = fma(JT[t][4] - JS[4], gy, S2);
-      S2 = fma(JT[t][5] - JS[5], gz, S2);
-      double S3 = (JT[t][6] - JS[6]) * gx;
-      S3 = fma(JT[t][7] - JS[7], gy, S3);
-      S3 = fma(JT[t][8] - JS[8], gz, S3);
+      double S1 = __dsub_rn(row_dot(JT[t][0], JT[t][1], JT[t][2], gx, gy, gz), qs1);
+      double S2 = __dsub_rn(row_dot(JT[t][3], JT[t][4], JT[t][5], gx, gy, gz), qs2);
+      double S3 = __dsub_rn(row_dot(JT[t][6], JT[t][7], JT[t][8], gx, gy, gz), qs3);
       acc[t][0] = fma(w, S1, acc[t][0]);
       acc[t][1] = fma(w, S2, acc[t][1]);
       acc[t][2] = fma(w, S3, acc[t][2]);
@@ -850,7 +867,7 @@ __global__ void test_math_kernel(int op, int arg, const double *in, double *out,
     if (out2) out2[i] = B;
   } else if (op == 3) {
     double w;
-    if (arg == K_WINCK) w = sfs_weight<K_WINCK>(x, 1.0, kConst4 * 7.5);
+    if (arg == K_WINCK) w = sfs_weight<K_WINCK>(x + 1.0, 1.0, kConst4 * 7.5);
     else if (arg == K_GERF) w = sfs_weight<K_GERF>(x, 1.0, kConst1);
     else if (arg == K_GAUS) w = sfs_weight<K_GAUS>(x, 1.0, kConst3);
     else w = sfs_weight<K_SING>(x, 1.0, 1.0);
