@@ -67,6 +67,8 @@ struct vpm_handle {
   bool resident_prior = false;
   double *h_stat = nullptr;   // pinned staging for compact static flags
   size_t h_stat_cap = 0;
+  double *h_stage = nullptr;  // pinned staging for the strided rows of a pageable host matrix
+  size_t h_stage_cap = 0;     // (doubles)
   std::vector<void *> pinned;
   int launches = 0;
   int64_t fld_nf = 0, fld_np = -1;  // device mirror of the whole particle matrix (vpm_field_*)
@@ -132,18 +134,22 @@ enum PlanKind { PLAN_UJ = 0, PLAN_SFS = 1 };
 Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind) {
   Plan p;
   const int64_t ntiles = std::max<int64_t>(1, (ns + kTile - 1) / kTile);
-  p.T = nt >= 4096 ? 2 : 1;
+  // two targets per thread (5 % faster in steady state) only when that still leaves enough
+  // CTAs to fill the machine a few times; small fields take T = 1 and splits down to one tile
+  const int64_t nblk2 = std::max<int64_t>(1, (nt + 2 * kThreads - 1) / (2 * kThreads));
+  const bool big = nblk2 * std::max<int64_t>(1, ntiles / 4) >= (int64_t)sm_count * 4 * 4;
+  p.T = big ? 2 : 1;
   p.unroll = p.T == 2 ? 1 : 2;
   if (const char *v = getenv(kind == PLAN_UJ ? "VPM_UJ_VARIANT" : "VPM_SFS_VARIANT")) {
     int x = atoi(v);  // tuning aid: "<T><unroll>", e.g. 12, 21, 22
-    if (x / 10 >= 1 && x / 10 <= 4) { p.T = x / 10; p.unroll = x % 10; }
+    if (x / 10 >= 1 && x / 10 <= 2) { p.T = x / 10; p.unroll = x % 10; }
   }
-  if (kind == PLAN_SFS && p.T > 2) p.T = 2;
+  const int min_tiles = big ? 4 : 1;
   const int ctas_per_sm = p.T == 1 ? 6 : 4;
   const int64_t nblk = std::max<int64_t>(1, (nt + (int64_t)kThreads * p.T - 1) / ((int64_t)kThreads * p.T));
   const int64_t want_ctas = (int64_t)sm_count * ctas_per_sm * 16;
   int64_t nsplit = (want_ctas + nblk - 1) / nblk;
-  nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, std::max<int64_t>(1, ntiles / 4)));
+  nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, std::max<int64_t>(1, ntiles / min_tiles)));
   nsplit = std::min<int64_t>(nsplit, 1024);
   p.tiles_per_split = (int)((ntiles + nsplit - 1) / nsplit);
   p.nsplit = (int)((ntiles + p.tiles_per_split - 1) / p.tiles_per_split);
@@ -157,10 +163,7 @@ void launch_uj_T(const Plan &p, const UjArgs &a, cudaStream_t st) {
   switch (p.T * 10 + p.unroll) {
     case 11: uj_pairs_kernel<K, 1, 1><<<p.grid, kThreads, 0, st>>>(a); break;
     case 12: uj_pairs_kernel<K, 1, 2><<<p.grid, kThreads, 0, st>>>(a); break;
-    case 14: uj_pairs_kernel<K, 1, 4><<<p.grid, kThreads, 0, st>>>(a); break;
     case 21: uj_pairs_kernel<K, 2, 1><<<p.grid, kThreads, 0, st>>>(a); break;
-    case 41: uj_pairs_kernel<K, 4, 1><<<p.grid, kThreads, 0, st>>>(a); break;
-    case 31: uj_pairs_kernel<K, 3, 1><<<p.grid, kThreads, 0, st>>>(a); break;
     default: uj_pairs_kernel<K, 2, 2><<<p.grid, kThreads, 0, st>>>(a); break;
   }
 }
@@ -298,6 +301,40 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
+
+// ---- strided rows of the host matrix <-> compact device blocks ------------------------
+// A 2-D copy straight from/to pageable host memory is staged row by row by the driver
+// (measured: 37 ms up + 60 ms down for 262 144 particles against 2 + 1 ms from registered
+// memory).  If the caller has not page-locked the matrix (vpm_pin_host), the rows are
+// gathered into / scattered from one pinned staging block on the host instead, and the
+// transfers themselves are contiguous.
+bool host_is_pinned(const void *ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int ensure_stage(vpm_handle *h, size_t doubles) {
+  if (doubles <= h->h_stage_cap) return VPM_OK;
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  h->h_stage = nullptr;
+  h->h_stage_cap = 0;
+  const size_t want = doubles + doubles / 4;
+  CK(h, cudaMallocHost((void **)&h->h_stage, want * sizeof(double)));
+  h->h_stage_cap = want;
+  return VPM_OK;
+}
+
+void gather_rows(double *dst, const double *P, int64_t nf, int row0, int nrows, int64_t np) {
+  for (int64_t i = 0; i < np; ++i) memcpy(dst + i * nrows, P + nf * i + row0, (size_t)nrows * sizeof(double));
+}
+void scatter_rows(double *P, int64_t nf, int row0, int nrows, int64_t np, const double *src) {
+  for (int64_t i = 0; i < np; ++i) memcpy(P + nf * i + row0, src + i * nrows, (size_t)nrows * sizeof(double));
+}
+
 // ---- Hook 1 pieces (single device d; targets = all particles) ---------------
 
 // host -> device: X, Gamma, sigma rows; static flags (compacted on the host,
@@ -314,8 +351,17 @@ int h1_upload(vpm_handle *h, Dev &d, const double *P, int64_t nf, int64_t np, bo
   if (np == 0) return VPM_OK;
   for (int64_t i = 0; i < np; ++i)
     if (P[nf * i + R_STATIC] != 0.0) { has_static = true; break; }
-  CK(h, cudaMemcpy2DAsync(d.in7.p, 7 * sizeof(double), P, nf * sizeof(double), 7 * sizeof(double),
-                          (size_t)np, cudaMemcpyHostToDevice, st));
+  const bool pinned = host_is_pinned(P);
+  double *stg = nullptr;
+  if (!pinned) {
+    TRY(ensure_stage(h, (size_t)np * (7 + RES_ROWS + 3)));
+    stg = h->h_stage;
+    gather_rows(stg, P, nf, R_X, 7, np);
+    CK(h, cudaMemcpyAsync(d.in7.p, stg, (size_t)np * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else {
+    CK(h, cudaMemcpy2DAsync(d.in7.p, 7 * sizeof(double), P, nf * sizeof(double), 7 * sizeof(double),
+                            (size_t)np, cudaMemcpyHostToDevice, st));
+  }
   if (has_static) {
     if (h->h_stat_cap < (size_t)np) {
       if (h->h_stat) cudaFreeHost(h->h_stat);
@@ -329,12 +375,24 @@ int h1_upload(vpm_handle *h, Dev &d, const double *P, int64_t nf, int64_t np, bo
     CK(h, cudaMemcpyAsync(d.stat.p, h->h_stat, (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
   }
   if (need_prior || has_static) {
-    CK(h, cudaMemcpy2DAsync(d.res18.p, RES_ROWS * sizeof(double), P + R_U, nf * sizeof(double),
-                            RES_ROWS * sizeof(double), (size_t)np, cudaMemcpyHostToDevice, st));
+    if (!pinned) {
+      double *s18 = stg + (size_t)np * 7;
+      gather_rows(s18, P, nf, R_U, RES_ROWS, np);
+      CK(h, cudaMemcpyAsync(d.res18.p, s18, (size_t)np * RES_ROWS * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+      CK(h, cudaMemcpy2DAsync(d.res18.p, RES_ROWS * sizeof(double), P + R_U, nf * sizeof(double),
+                              RES_ROWS * sizeof(double), (size_t)np, cudaMemcpyHostToDevice, st));
+    }
   }
   if (need_sfs_rows) {
-    CK(h, cudaMemcpy2DAsync(d.sfs3.p, 3 * sizeof(double), P + R_SFS, nf * sizeof(double),
-                            3 * sizeof(double), (size_t)np, cudaMemcpyHostToDevice, st));
+    if (!pinned) {
+      double *s3 = stg + (size_t)np * (7 + RES_ROWS);
+      gather_rows(s3, P, nf, R_SFS, 3, np);
+      CK(h, cudaMemcpyAsync(d.sfs3.p, s3, (size_t)np * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+      CK(h, cudaMemcpy2DAsync(d.sfs3.p, 3 * sizeof(double), P + R_SFS, nf * sizeof(double),
+                              3 * sizeof(double), (size_t)np, cudaMemcpyHostToDevice, st));
+    }
   }
   return VPM_OK;
 }
@@ -396,10 +454,23 @@ int h1_eval(vpm_handle *h, Dev &d, int64_t np, int kernel, int flags, bool has_s
 int h1_download(vpm_handle *h, Dev &d, double *P, int64_t nf, int64_t np, int flags) {
   cudaStream_t st = d.stream;
   CK(h, cudaSetDevice(d.id));
+  const bool sfs_rows = flags & (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS);
+  if (np > 0 && !host_is_pinned(P)) {
+    // pageable matrix: contiguous D2H into the pinned staging block, then scatter on the host
+    TRY(ensure_stage(h, (size_t)np * (7 + RES_ROWS + 3)));
+    double *s18 = h->h_stage + (size_t)np * 7, *s3 = h->h_stage + (size_t)np * (7 + RES_ROWS);
+    CK(h, cudaMemcpyAsync(s18, d.res18.p, (size_t)np * RES_ROWS * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (sfs_rows) CK(h, cudaMemcpyAsync(s3, d.sfs3.p, (size_t)np * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaEventRecord(d.ev[5], st));
+    CK(h, cudaStreamSynchronize(st));
+    scatter_rows(P, nf, R_U, RES_ROWS, np, s18);
+    if (sfs_rows) scatter_rows(P, nf, R_SFS, 3, np, s3);
+    return VPM_OK;
+  }
   if (np > 0) {
     CK(h, cudaMemcpy2DAsync(P + R_U, nf * sizeof(double), d.res18.p, RES_ROWS * sizeof(double),
                             RES_ROWS * sizeof(double), (size_t)np, cudaMemcpyDeviceToHost, st));
-    if (flags & (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS))
+    if (sfs_rows)
       CK(h, cudaMemcpy2DAsync(P + R_SFS, nf * sizeof(double), d.sfs3.p, 3 * sizeof(double),
                               3 * sizeof(double), (size_t)np, cudaMemcpyDeviceToHost, st));
   }
@@ -921,6 +992,7 @@ int vpm_destroy(vpm_handle *h) {
     if (d.stream) cudaStreamDestroy(d.stream);
   }
   if (h->h_stat) cudaFreeHost(h->h_stat);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
   cudaGetLastError();
   delete h;
   return VPM_OK;
