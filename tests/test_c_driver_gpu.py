@@ -1,0 +1,38 @@
+"""The C ABI driven from plain C (tests/c_abi_driver.c, compiled with gcc against
+include/vpm_cuda.h and linked to libvpm_cuda.so) -- no Python, no torch on the product side."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import TOL_FP64, relerr
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("kernel_id,kernel", [(3, "winckelmans"), (2, "gaussianerf")])
+def test_plain_c_driver(tmp_path, kernel_id, kernel):
+    exe = str(tmp_path / "c_abi_driver")
+    libdir = os.path.join(ROOT, "flowvpm.jl_b200", "csrc")
+    subprocess.run(["/usr/bin/gcc", "-std=c11", "-O1", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi_driver.c"), "-L", libdir, "-lvpm_cuda", "-lm",
+                    f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    n = 300
+    out = subprocess.run([exe, str(n), str(kernel_id)], check=True, capture_output=True, text=True).stdout.splitlines()
+    assert out[0].startswith("abi 1 gpus 1")
+    got = np.array([[float(v) for v in line.split()] for line in out[1:]]).T   # 15 x n
+    i = np.arange(n)
+    t = 0.05 * i
+    P = np.zeros((46, n), order="F")
+    P[0], P[1], P[2] = np.cos(t), np.sin(t), 0.02 * t
+    P[3], P[4], P[5] = -0.01 * np.sin(t), 0.01 * np.cos(t), 0.001
+    P[6] = 0.08 + 0.01 * np.sin(3 * t)
+    P[42] = (i % 17 == 0).astype(float)
+    P[9] = 0.5
+    oracle.uj_direct(P, n, kernel, sfs=True, reset=True, reset_sfs=True)
+    assert relerr(got[0:3], P[9:12]) < TOL_FP64
+    assert relerr(got[3:12], P[15:24]) < TOL_FP64
+    assert relerr(got[12:15], P[39:42]) < TOL_FP64
