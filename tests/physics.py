@@ -99,3 +99,68 @@ def run_single_ring(vpm, UJ, integration, nsteps=50, Nphi=100, nc=0, R=1.0, Rtot
         t += dt
     Zc = ring_centroid_weighted(pf)
     return float(np.linalg.norm(Zc) / t), float(Uref)
+
+
+# ---------------------------------------------------------------------------------------
+# Leapfrogging rings: the analytic reference of test/runtests_leapfrog.jl
+# (examples/vortexrings/vortexrings_postprocessing.jl:190-305): Borisov, Kilin & Mamaev 2013
+# coaxial thin rings, forward Euler with dt = 1e-4, finite-difference dG/dR, dG/dZ (h = 1e-5),
+# dynamica = false, Delta = 0 (Winckelmans kernel).
+# ---------------------------------------------------------------------------------------
+def _G(z, r, zt, rt):
+    from scipy.special import ellipe, ellipk
+    k = np.sqrt(4 * r * rt / ((z - zt) ** 2 + (r + rt) ** 2))
+    return np.sqrt(r * rt) / (2 * np.pi) * ((2 / k - k) * ellipk(k * k) - 2 / k * ellipe(k * k))
+
+
+def analytic_coaxialrings(Gammas, Rs, Zs, a_s, tend, dt=1e-4, h=1e-5):
+    n = len(Gammas)
+    R, Z = np.array(Rs, dtype=float), np.array(Zs, dtype=float)
+    nst = int(np.floor(tend / dt + 1e-12))
+    steps = [dt] * nst + ([tend - nst * dt] if tend - nst * dt > 0 else [])
+    for this_dt in steps:
+        dR, dZ = np.zeros(n), np.zeros(n)
+        for i in range(n):
+            dZ[i] = Gammas[i] / (4 * np.pi * R[i]) * (np.log(8 * R[i] / a_s[i]) - 0.5)
+            for j in range(n):
+                if i == j:
+                    continue
+                g0 = _G(Z[i], R[i], Z[j], R[j])
+                dR[i] -= 1 / R[i] * Gammas[j] * (_G(Z[i] + h, R[i], Z[j], R[j]) - g0) / h
+                dZ[i] += 1 / R[i] * Gammas[j] * (_G(Z[i], R[i] + h, Z[j], R[j]) - g0) / h
+        R, Z = R + dR * this_dt, Z + dZ * this_dt
+    return R, Z
+
+
+def rings_weighted(pf, nrings, n_per_ring):
+    """calc_rings_weighted! (examples/vortexrings/vortexrings_functions.jl:284-322): centroid
+    and radius of each ring weighted by |Gamma|"""
+    out = []
+    for ri in range(nrings):
+        P = pf.particles[:, ri * n_per_ring:(ri + 1) * n_per_ring]
+        w = np.sqrt((P[3:6] ** 2).sum(axis=0))
+        Zc = (P[0:3] * w).sum(axis=1) / w.sum()
+        Rr = (w * np.sqrt(((P[0:3] - Zc[:, None]) ** 2).sum(axis=0))).sum() / w.sum()
+        out.append((Zc, Rr))
+    return out
+
+
+LEAPFROG = dict(nsteps=350, R=0.7906, dZ=0.7906, Nphi=100, nc=0, beta=0.5)
+
+
+def leapfrog_setup(vpm):
+    """test/runtests_leapfrog.jl:38-75: two coaxial rings, Rcross = 0.1 R, sigma = Rcross"""
+    c = LEAPFROG
+    Rcross = 0.10 * c["R"]
+    pf = vpm.fields.ring_field(Nphi=c["Nphi"], nc=c["nc"], R=c["R"], Rcross=Rcross, sigma=Rcross, rings=2, dZ=c["dZ"],
+                               kernel=vpm.winckelmans)
+    Uref = vpm.fields.Uring(1.0, c["R"], Rcross, c["beta"])
+    dt = ((c["nsteps"] / 1000) / Uref) / c["nsteps"]
+    return pf, dt, Rcross
+
+
+def leapfrog_errors(vpm, pf, tend, Rcross):
+    c = LEAPFROG
+    (Z1, R1), (Z2, R2) = rings_weighted(pf, 2, vpm.fields.number_particles(c["Nphi"], c["nc"]))
+    Ra, Za = analytic_coaxialrings([1.0, 1.0], [c["R"], c["R"]], [0.0, c["dZ"]], [Rcross, Rcross], tend)
+    return ((Z1[2] - Za[0]) / Za[0], (Z2[2] - Za[1]) / Za[1], (R1 - Ra[0]) / Ra[0], (R2 - Ra[1]) / Ra[1])

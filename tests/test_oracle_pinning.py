@@ -244,3 +244,18 @@ def test_oracle_step_equals_numpy_harness(integration, vpm):
     step(pf, 1e-2, UJ, f=0.0, g=0.2, relax=True)
     oracle.field_step(a, pf.np, "winckelmans", 1e-2, integration=integration, f=0.0, g=0.2, relax=True)
     assert np.array_equal(a[0:7], pf.particles[0:7])
+
+
+@pytest.mark.parametrize("f,g,sfs", [(0.0, 0.0, False), (0.0, 0.2, False), (0.0, 0.2, "dynamic")])
+def test_leapfrog_rings_vs_borisov_ode(vpm, f, g, sfs):
+    """test/runtests_leapfrog.jl rows 1-3 (cVPM, rVPM, rVPM + DynamicSFS; RK3, corrected
+    Pedrizzetti relaxation, 2 x 100 particles, 350 steps) with the oracle's integrator: end
+    state within the reference's own tolerances (:169) of the Borisov-2013 ODE solution.
+    (The reference runs these through UJ_fmm; here the sums are direct.)"""
+    pf, dt, Rcross = physics.leapfrog_setup(vpm)
+    for _ in range(physics.LEAPFROG["nsteps"]):
+        oracle.field_step(pf.particles, pf.np, "winckelmans", dt, integration="rungekutta3", f=f, g=g, sfs=sfs,
+                          relaxation="correctedpedrizzetti", relax=True, rlxf=0.3, alpha=0.667, sfs_rlxf=0.005,
+                          minC=0.0, maxC=1.0, nthreads=4)
+    Z1e, Z2e, R1e, R2e = physics.leapfrog_errors(vpm, pf, dt * physics.LEAPFROG["nsteps"], Rcross)
+    assert abs(Z1e) < 0.05 and abs(Z2e) < 0.03 and abs(R1e) < 0.03 and abs(R2e) < 0.03, (Z1e, Z2e, R1e, R2e)

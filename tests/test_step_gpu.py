@@ -123,3 +123,17 @@ def test_step_needs_resident_field(vpm):
         assert b"vpm_field_upload" in h.lib.vpm_last_error(h.ptr)
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("f,g,sfs", [(0.0, 0.0, False), (0.0, 0.2, False), (0.0, 0.2, "dynamic")])
+def test_leapfrog_rings_on_device(vpm, handle, f, g, sfs):
+    """test/runtests_leapfrog.jl rows 1-3 run entirely on the GPU (vpm_field_step): end state
+    within the reference's tolerances of the Borisov-2013 ODE solution (:169)"""
+    pf, dt, Rcross = physics.leapfrog_setup(vpm)
+    rf = vpm.ResidentField(pf)
+    for _ in range(physics.LEAPFROG["nsteps"]):
+        rf.nextstep(dt, integration="rungekutta3", f=f, g=g, sfs=sfs, relaxation="correctedpedrizzetti", relax=True,
+                    rlxf=0.3, alpha=0.667, sfs_rlxf=0.005, minC=0.0, maxC=1.0)
+    rf.download()
+    Z1e, Z2e, R1e, R2e = physics.leapfrog_errors(vpm, pf, dt * physics.LEAPFROG["nsteps"], Rcross)
+    assert abs(Z1e) < 0.05 and abs(Z2e) < 0.03 and abs(R1e) < 0.03 and abs(R2e) < 0.03, (Z1e, Z2e, R1e, R2e)
