@@ -300,7 +300,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed_steps(fn, k, w):
+    def timed_steps(fn, k, w, key="uj_ms"):
         """W warm-ups, then K steps each bracketed by CUDA events on the launching stream,
         L2 flushed between steps; returns (list of ms, list of pair-kernel ms)."""
         for _ in range(w):
@@ -317,8 +317,7 @@ def main():
             b.record()
             b.synchronize()
             ms.append(a.elapsed_time(b))
-            tm = h.timing()
-            kms.append(tm["uj_ms"] if tm["uj_ms"] > 0 else tm["sfs_ms"])
+            kms.append(h.timing()[key])
         sync_all()
         return ms, kms
 
@@ -407,7 +406,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_extras:
         extras = {}
         # SFS sweep over the J just computed
-        sms, skms = timed_steps(lambda: field.sfs(vpm._cabi.FLAG_TRANSPOSED), 1, 1)
+        sms, skms = timed_steps(lambda: field.sfs(vpm._cabi.FLAG_TRANSPOSED), 1, 1, key="sfs_ms")
         extras["sfs"] = {"interactions_per_s": n * n / (np.mean(sms) * 1e-3), "ms": float(np.mean(sms)),
                          "kernel": args.kernel,
                          "roofline_frac": n * n / (np.mean(skms) * 1e-3) * F_SFS[args.kernel] / 1e12 / peak_tflops}
