@@ -39,9 +39,11 @@ class VpmStepParams(C.Structure):
     _fields_ = [("dt", C.c_double), ("f", C.c_double), ("g", C.c_double), ("Uinf", C.c_double * 3),
                 ("Cs", C.c_double), ("rlxf", C.c_double),
                 ("alpha", C.c_double), ("sfs_rlxf", C.c_double), ("minC", C.c_double), ("maxC", C.c_double),
+                ("deltat", C.c_double),
                 ("kernel_id", C.c_int32), ("integration", C.c_int32), ("relaxation", C.c_int32),
                 ("relax", C.c_int32), ("sfs", C.c_int32), ("clip_backscatter", C.c_int32),
-                ("transposed", C.c_int32), ("force_positive", C.c_int32)]
+                ("transposed", C.c_int32), ("force_positive", C.c_int32), ("controls", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class VpmError(RuntimeError):

@@ -1620,6 +1620,7 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
   a.transposed = sp->transposed; a.sfs = sp->sfs; a.clip = sp->clip_backscatter; a.relax_kind = sp->relaxation;
   a.alpha = sp->alpha; a.sfs_rlxf = sp->sfs_rlxf; a.minC = sp->minC; a.maxC = sp->maxC;
   a.force_positive = sp->force_positive;
+  a.controls = sp->controls; a.deltat = sp->deltat;
   if (sp->sfs < 0 || sp->sfs > 2) return fail(h, VPM_EINVAL, "vpm_field_step: sfs must be 0 (none), 1 (constant) or 2 (dynamic)");
   if (sp->sfs == 2 && (sp->minC < 0 || sp->maxC < 0 || sp->minC > sp->maxC || sp->alpha <= 0))
     return fail(h, VPM_EINVAL, "vpm_field_step: invalid DynamicSFS parameters (minC=%g maxC=%g alpha=%g)", sp->minC, sp->maxC, sp->alpha);
@@ -1640,6 +1641,7 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
   auto sfs_after = [&]() {
     if (sp->sfs == 1) { step_sfs_coeff<<<nb, 256, 0, st>>>(a); h->launches++; }
     if (sp->sfs == 2) { step_dyn_coeff<<<nb, 256, 0, st>>>(a); h->launches++; }
+    if (sp->sfs && (sp->controls & 3)) { step_sfs_controls<<<nb, 256, 0, st>>>(a); h->launches++; }
   };
   CK(h, cudaEventRecord(d.ev[0], st));
   CK(h, cudaEventRecord(d.ev[1], st));

@@ -8,9 +8,8 @@
 //   ConstantSFS AfterUJ hook + clipping_backscatter                src/FLOWVPM_subfilterscale.jl:110-135,287-296
 //   DynamicSFS pseudo-3-level procedure (before / after UJ)         src/FLOWVPM_subfilterscale.jl:447-673
 // Covered: cVPM / rVPM / any (f, g); NoSFS, ConstantSFS and DynamicSFS (pseudo3level, optional
-// force_positive and backscatter clipping); Inviscid; constant Uinf.  Not covered (stays in
-// Julia): SFS control strategies (sigma / magnitude sensors), the sensor-function procedure,
-// viscous schemes.
+// force_positive, backscatter clipping, directional / magnitude controls); Inviscid; constant
+// Uinf.  Not covered (stays in Julia): the (stale) sensor-function procedure, viscous schemes.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -27,6 +26,8 @@ struct StepArgs {
   double alpha, sfs_rlxf, minC, maxC;  // DynamicSFS (src/FLOWVPM_subfilterscale.jl:167-202)
   int transposed, sfs, clip, relax_kind;  // sfs: 0 none, 1 constant, 2 dynamic; relax_kind: 0 none, 1 pedrizzetti, 2 corrected
   int force_positive;
+  int controls;     // bit 0: control_directional, bit 1: control_magnitude (applied in that order)
+  double deltat;    // pfield.t / pfield.nt for control_magnitude (<= 0: pfield.nt == 0, control skipped)
   int *nan_flag;  // set when the dynamic procedure produces a NaN coefficient (:645-652)
 };
 
@@ -88,6 +89,33 @@ __global__ void step_sfs_coeff(StepArgs a) {
     if (C * d < 0.0) C = 0.0;
   }
   p[S_C] = C;
+}
+
+// SFS control strategies, applied after the clippings at an Euler step / the first RK substep
+// (src/FLOWVPM_subfilterscale.jl:121-155,245-265): control_directional (:319-334) keeps only
+// the component of SFS along Gamma; control_magnitude (:367-397) limits forward scatter.
+__global__ void step_sfs_controls(StepArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+  const double G1 = p[S_G], G2 = p[S_G + 1], G3 = p[S_G + 2];
+  if (a.controls & 1) {
+    const double S1 = p[S_SFS], S2 = p[S_SFS + 1], S3 = p[S_SFS + 2];
+    double aux = S1 * G1 + S2 * G2 + S3 * G3;
+    aux /= (G1 * G1 + G2 * G2 + G3 * G3);
+    p[S_SFS] = aux * G1; p[S_SFS + 1] = aux * G2; p[S_SFS + 2] = aux * G3;
+  }
+  if ((a.controls & 2) && a.deltat > 0.0) {
+    const double C = p[S_C];
+    if (C != 0.0) {
+      const double S1 = p[S_SFS], S2 = p[S_SFS + 1], S3 = p[S_SFS + 2], sg = p[S_SIGMA];
+      double aux = S1 * G1 + S2 * G2 + S3 * G3;
+      aux /= (G1 * G1 + G2 * G2 + G3 * G3);
+      aux -= (1 + 3 * a.f) * (a.zeta0 / (sg * sg * sg)) / a.deltat / C;
+      if (aux > 0.0) { p[S_SFS] = -aux * G1; p[S_SFS + 1] = -aux * G2; p[S_SFS + 2] = -aux * G3; }
+    }
+  }
 }
 
 // ---- DynamicSFS, pseudo-3-level procedure -------------------------------------------

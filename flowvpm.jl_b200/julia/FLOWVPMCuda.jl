@@ -203,9 +203,10 @@ end
 # ------------------------------------------------------------------------------
 struct StepParams
     dt::Cdouble; f::Cdouble; g::Cdouble; Uinf::NTuple{3,Cdouble}; Cs::Cdouble; rlxf::Cdouble
-    alpha::Cdouble; sfs_rlxf::Cdouble; minC::Cdouble; maxC::Cdouble
+    alpha::Cdouble; sfs_rlxf::Cdouble; minC::Cdouble; maxC::Cdouble; deltat::Cdouble
     kernel_id::Int32; integration::Int32; relaxation::Int32; relax::Int32
     sfs::Int32; clip_backscatter::Int32; transposed::Int32; force_positive::Int32
+    controls::Int32; reserved::Int32
 end
 
 function upload!(pfield::vpm.ParticleField{Float64})
@@ -221,7 +222,8 @@ function download!(pfield::vpm.ParticleField{Float64})
 end
 
 function nextstep_cuda!(pfield::vpm.ParticleField{Float64}, dt::Real; relax::Bool=false,
-                        clip_backscatter::Bool=false, force_positive::Bool=false)
+                        clip_backscatter::Bool=false, force_positive::Bool=false,
+                        control_directional::Bool=false, control_magnitude::Bool=false)
     form = pfield.formulation
     S = pfield.SFS
     sfs = S isa vpm.DynamicSFS ? 2 : (vpm.isSFSenabled(S) ? 1 : 0)
@@ -231,9 +233,11 @@ function nextstep_cuda!(pfield::vpm.ParticleField{Float64}, dt::Real; relax::Boo
     relaxation = rlx.relax === vpm.relax_pedrizzetti ? 1 : rlx.relax === vpm.relax_correctedpedrizzetti ? 2 : 0
     integration = pfield.integration === vpm.rungekutta3 ? 1 : 0
     Uinf = pfield.Uinf(pfield.t)
+    deltat = pfield.nt > 0 ? pfield.t / pfield.nt : 0.0
     sp = Ref(StepParams(dt, form.f, form.g, (Uinf[1], Uinf[2], Uinf[3]), Cs, rlx.rlxf, alpha, sfs_rlxf, minC, maxC,
-                        kernel_id(pfield.kernel), integration, relaxation, relax, sfs, clip_backscatter,
-                        pfield.transposed, force_positive))
+                        deltat, kernel_id(pfield.kernel), integration, relaxation, relax, sfs, clip_backscatter,
+                        pfield.transposed, force_positive, Int32(control_directional) | (Int32(control_magnitude) << 1),
+                        0))
     check(ccall((:vpm_field_step, lib[]), Cint, (Ptr{Cvoid}, Ref{StepParams}), handle[], sp))
     pfield.t += dt
     pfield.nt += 1

@@ -215,7 +215,8 @@ class ResidentField:
 
     def nextstep(self, dt, *, integration="rungekutta3", f=0.0, g=0.2, Uinf=(0.0, 0.0, 0.0), sfs=False, Cs=1.0,
                  clip_backscatter=False, relaxation="pedrizzetti", relax=True, rlxf=0.3, alpha=0.667,
-                 sfs_rlxf=0.005, minC=0.0, maxC=1.0, force_positive=False):
+                 sfs_rlxf=0.005, minC=0.0, maxC=1.0, force_positive=False, control_directional=False,
+                 control_magnitude=False):
         """sfs: False | "constant" (ConstantSFS, coefficient Cs) | "dynamic" (DynamicSFS with the
         pseudo-3-level procedure: alpha, sfs_rlxf, minC, maxC, force_positive)"""
         if minC < 0 or maxC < 0 or minC > maxC:
@@ -224,6 +225,8 @@ class ResidentField:
         sp.dt, sp.f, sp.g, sp.Cs, sp.rlxf = dt, f, g, Cs, rlxf
         sp.alpha, sp.sfs_rlxf, sp.minC, sp.maxC = alpha, sfs_rlxf, minC, maxC
         sp.force_positive = int(force_positive)
+        sp.controls = int(control_directional) | (int(control_magnitude) << 1)
+        sp.deltat = self.pfield.t / self.pfield.nt if self.pfield.nt > 0 else 0.0   # subfilterscale.jl:344-347
         sp.Uinf[0], sp.Uinf[1], sp.Uinf[2] = Uinf
         sp.kernel_id = self.pfield.kernel.id
         sp.integration = self.INTEGRATIONS[integration]

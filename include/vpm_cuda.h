@@ -159,8 +159,8 @@ int vpm_zeta_leafpairs(vpm_handle *h, double *particles, int64_t nfields, int64_
  *   ConstantSFS hook + clipping_backscatter:                    src/FLOWVPM_subfilterscale.jl:110-135,287-296
  *   DynamicSFS pseudo-3-level procedure:                        src/FLOWVPM_subfilterscale.jl:447-673
  * Covered: any (f, g) incl. cVPM (0,0) and rVPM (0,1/5); NoSFS / ConstantSFS / DynamicSFS
- * (pseudo3level, force_positive, clipping_backscatter); Inviscid; constant Uinf.  SFS control
- * strategies and the viscous schemes stay in the reference's Julia code (use Hook 1). */
+ * (pseudo3level, force_positive, clipping_backscatter, control_directional, control_magnitude);
+ * Inviscid; constant Uinf.  The viscous schemes stay in the reference's Julia code (Hook 1). */
 typedef struct vpm_step_params {
   double dt;
   double f, g;        /* ReformulatedVPM{f,g}: src/FLOWVPM_formulation.jl:23-37 */
@@ -170,6 +170,7 @@ typedef struct vpm_step_params {
   double alpha;       /* DynamicSFS: test-filter scaling (default 0.667) */
   double sfs_rlxf;    /* DynamicSFS: Lagrangian-average relaxation (default 0.005) */
   double minC, maxC;  /* DynamicSFS: bounds of |C| (defaults 0, 1) */
+  double deltat;      /* pfield.t / pfield.nt, used by control_magnitude; <= 0 when pfield.nt == 0 */
   int32_t kernel_id;
   int32_t integration;      /* 0 euler, 1 rungekutta3 */
   int32_t relaxation;       /* 0 none, 1 pedrizzetti, 2 correctedpedrizzetti */
@@ -178,6 +179,9 @@ typedef struct vpm_step_params {
   int32_t clip_backscatter; /* clippings = (clipping_backscatter,) */
   int32_t transposed;       /* pfield.transposed */
   int32_t force_positive;   /* DynamicSFS: pseudo3level_positive */
+  int32_t controls;         /* SFS controls: bit 0 control_directional, bit 1 control_magnitude
+                               (src/FLOWVPM_subfilterscale.jl:300-397) */
+  int32_t reserved;
 } vpm_step_params;
 int vpm_field_upload(vpm_handle *h, const double *particles, int64_t nfields, int64_t np);
 int vpm_field_download(vpm_handle *h, double *particles, int64_t nfields, int64_t np);

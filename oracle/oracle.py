@@ -127,15 +127,18 @@ def direct_buffers(tgt, t0, t1, src, s0, s1, kernel, want_U=True, want_J=True, n
 
 def field_step(P, np_, kernel, dt, *, integration="rungekutta3", f=0.0, g=0.2, Uinf=(0.0, 0.0, 0.0), sfs=False,
                Cs=1.0, clip_backscatter=False, relaxation="pedrizzetti", relax=True, rlxf=0.3, transposed=True,
-               alpha=0.667, sfs_rlxf=0.005, minC=0.0, maxC=1.0, force_positive=False, nthreads=0):
+               alpha=0.667, sfs_rlxf=0.005, minC=0.0, maxC=1.0, force_positive=False, control_directional=False,
+               control_magnitude=False, deltat=0.0, nthreads=0):
     """one euler / rungekutta3 step of ReformulatedVPM{f,g} on the 46 x N matrix, in place;
     sfs: False | "constant" | "dynamic" (pseudo-3-level procedure)"""
     _f(P)
-    dp = np.array([dt, f, g, Uinf[0], Uinf[1], Uinf[2], Cs, rlxf, alpha, sfs_rlxf, minC, maxC], dtype=np.float64)
+    dp = np.array([dt, f, g, Uinf[0], Uinf[1], Uinf[2], Cs, rlxf, alpha, sfs_rlxf, minC, maxC, deltat],
+                  dtype=np.float64)
     ip = np.array([_kid(kernel), {"euler": 0, "rungekutta3": 1}[integration],
                    {None: 0, "none": 0, "pedrizzetti": 1, "correctedpedrizzetti": 2}[relaxation], int(relax),
                    {False: 0, None: 0, "none": 0, True: 1, "constant": 1, "dynamic": 2}[sfs],
-                   int(clip_backscatter), int(transposed), int(force_positive)], dtype=np.int32)
+                   int(clip_backscatter), int(transposed), int(force_positive),
+                   int(control_directional) | (int(control_magnitude) << 1)], dtype=np.int32)
     rc = lib().vpm_oracle_field_step(P.ctypes.data, P.shape[0], int(np_), dp.ctypes.data, ip.ctypes.data,
                                      int(nthreads or max_threads()))
     if rc != 0:

@@ -597,10 +597,38 @@ static int o_dyn_after(double *P, int64_t nf, int64_t np, int kernel, int transp
   return 0;
 }
 
+/* SFS control strategies after the clippings: control_directional (src/FLOWVPM_subfilterscale.jl:319-334),
+ * control_magnitude (:367-397), each applied to every non-static particle in turn (:245-265) */
+static void o_controls(double *P, int64_t nf, int64_t np, int controls, double f, double zeta0, double deltat) {
+  if (controls & 1)
+    for (int64_t i = 0; i < np; ++i) {
+      double *p = P + nf * i;
+      if (p[R_STATIC] != 0.0) continue;
+      double G1 = p[R_G], G2 = p[R_G + 1], G3 = p[R_G + 2], S1 = p[R_SFS], S2 = p[R_SFS + 1], S3 = p[R_SFS + 2];
+      double aux = S1 * G1 + S2 * G2 + S3 * G3;
+      aux /= (G1 * G1 + G2 * G2 + G3 * G3);
+      p[R_SFS] = aux * G1; p[R_SFS + 1] = aux * G2; p[R_SFS + 2] = aux * G3;
+    }
+  if ((controls & 2) && deltat > 0)
+    for (int64_t i = 0; i < np; ++i) {
+      double *p = P + nf * i;
+      if (p[R_STATIC] != 0.0) continue;
+      double C = p[R_C];
+      if (C != 0) {
+        double G1 = p[R_G], G2 = p[R_G + 1], G3 = p[R_G + 2], S1 = p[R_SFS], S2 = p[R_SFS + 1], S3 = p[R_SFS + 2];
+        double aux = S1 * G1 + S2 * G2 + S3 * G3;
+        aux /= (G1 * G1 + G2 * G2 + G3 * G3);
+        aux -= (1 + 3 * f) * (zeta0 / (p[R_SIGMA] * p[R_SIGMA] * p[R_SIGMA])) / deltat / C;
+        if (aux > 0) { p[R_SFS] = -aux * G1; p[R_SFS + 1] = -aux * G2; p[R_SFS + 2] = -aux * G3; }
+      }
+    }
+}
+
 int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, const double *dp, const int *ip, int nthreads) {
   init_consts();
   const double dt = dp[0], f = dp[1], g = dp[2], Uinf[3] = {dp[3], dp[4], dp[5]}, Cs = dp[6], rlxf = dp[7];
-  const double alpha = dp[8], sfs_rlxf = dp[9], minC = dp[10], maxC = dp[11];
+  const double alpha = dp[8], sfs_rlxf = dp[9], minC = dp[10], maxC = dp[11], deltat = dp[12];
+  const int controls = ip[8];
   const int kernel = ip[0], integration = ip[1], relaxation = ip[2], relax = ip[3], sfs = ip[4], clip = ip[5],
             transposed = ip[6], force_positive = ip[7];
   const double zeta0 = zeta_fn(kernel, 0.0);
@@ -612,6 +640,7 @@ int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, const double *dp, c
     if (sfs == 1) o_sfs_coeff(P, nf, np, Cs, clip);
     if (sfs == 2 && o_dyn_after(P, nf, np, kernel, transposed, alpha, sfs_rlxf, minC, maxC, force_positive, clip))
       return -3;
+    if (sfs) o_controls(P, nf, np, controls, f, zeta0, deltat);
     for (int64_t i = 0; i < np; ++i) {
       double *p = P + nf * i;
       if (p[R_STATIC] != 0.0) continue;
@@ -636,6 +665,7 @@ int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, const double *dp, c
     if (sfs == 2 && a == 0.0 &&
         o_dyn_after(P, nf, np, kernel, transposed, alpha, sfs_rlxf, minC, maxC, force_positive, clip))
       return -3;
+    if (sfs && a == 0.0) o_controls(P, nf, np, controls, f, zeta0, deltat);
     for (int64_t i = 0; i < np; ++i) {
       double *p = P + nf * i;
       if (p[R_STATIC] != 0.0) continue;

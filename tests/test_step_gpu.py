@@ -66,6 +66,25 @@ def test_dynamic_sfs_step_matches_oracle(vpm, handle, integration, force_positiv
     assert np.abs(ref[36, :pf.np]).max() > 0 and np.abs(ref[36, :pf.np]).max() <= 1.0
 
 
+@pytest.mark.parametrize("sfs", ["constant", "dynamic"])
+@pytest.mark.parametrize("directional,magnitude", [(True, False), (False, True), (True, True)])
+def test_sfs_controls_match_oracle(vpm, handle, sfs, directional, magnitude):
+    """control_directional / control_magnitude (src/FLOWVPM_subfilterscale.jl:300-397)"""
+    pf = vpm.fields.cloud_field(1200, kernel=vpm.gaussianerf, static_fraction=0.05, seed=41)
+    ref = pf.particles.copy(order="F")
+    kw = dict(integration="rungekutta3", f=0.1, g=0.2, sfs=sfs, Cs=0.7, clip_backscatter=True, relaxation=None,
+              relax=False, alpha=0.9, sfs_rlxf=0.4, control_directional=directional, control_magnitude=magnitude)
+    rf = vpm.ResidentField(pf)
+    dt = 1e-3
+    for k in range(3):
+        deltat = pf.t / pf.nt if pf.nt > 0 else 0.0
+        rf.nextstep(dt, **kw)
+        oracle.field_step(ref, pf.np, "gaussianerf", dt, transposed=True, deltat=deltat, **kw)
+    rf.download()
+    for name, r in dict(ROWS, C=slice(36, 39)).items():
+        assert relerr(pf.particles[r, :pf.np], ref[r, :pf.np]) < 1e-9, name
+
+
 def test_formulations_and_classic_scheme(vpm, handle):
     for f, g, transposed in ((0.0, 0.0, True), (0.5, 0.0, True), (0.25, 0.25, False)):
         pf = make_field(vpm, vpm.gaussianerf)
