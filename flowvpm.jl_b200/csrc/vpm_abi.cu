@@ -874,37 +874,89 @@ int64_t count_pairs(const int64_t *tb, const int64_t *te, const int64_t *sb, con
 
 
 // ---- device-resident field: UJ_direct on the mirror of the whole matrix ----
-int field_uj(vpm_handle *h, Dev &d, int kernel, int flags) {
-  cudaStream_t st = d.stream;
-  double *F = (double *)d.fld.p;
+// With G devices every device holds the whole mirror (np_pad = G * shard columns); device g
+// sweeps the targets of its shard and the shards' columns are all-gathered in place over
+// NVLink (columns = particles are contiguous in the column-major matrix), so all mirrors
+// stay identical and the O(N) step kernels simply run on every device.
+int64_t field_shard(const vpm_handle *h) {
+  const int64_t G = (int64_t)h->devs.size();
+  return (h->fld_np + G - 1) / G;
+}
+
+int field_allgather(vpm_handle *h) {
+  const int G = (int)h->devs.size();
+  if (G < 2) return VPM_OK;
+  TRY(ensure_comms(h));
+  const size_t count = (size_t)field_shard(h) * h->fld_nf;
+  NCK(h, g_nccl.group_start());
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    double *F = (double *)d.fld.p;
+    NCK(h, g_nccl.all_gather(F + (size_t)g * count, F, count, kNcclFloat64, h->comms[g], d.stream));
+  }
+  NCK(h, g_nccl.group_end());
+  return VPM_OK;
+}
+
+int field_uj(vpm_handle *h, int kernel, int flags) {
   const int64_t nf = h->fld_nf, np = h->fld_np;
   if (np == 0) return VPM_OK;
-  const double *stat = F + R_STATIC;
-  SrcView src{F, nf, 0, 3, 6};
-  Plan plan;
-  TRY(uj_sweep(h, d, st, kernel, F, nf, np, src, 0, np, flags, plan));
-  UjFinishArgs f;
-  f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
-  f.nt = np; f.out = F; f.ld = nf; f.urow = R_U; f.jrow = R_J; f.zrow0 = R_W; f.zrow1 = R_PSE;
-  f.want_U = 1; f.want_J = 1; f.accumulate = 1; f.reset = (flags & VPM_FLAG_RESET) ? 1 : 0;
-  f.stat = stat; f.sld = nf;
-  uj_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(f);
-  h->launches++;
-  if (flags & VPM_FLAG_SFS) {
-    Plan sp;
-    TRY(sfs_sweep(h, d, st, kernel, F, nf, F + R_J, nf, nullptr, np, src, F, nf, R_J, stat, nf, nullptr, np,
-                  flags, sp));
-    SfsFinishArgs g;
-    g.partial = (const double *)d.partial.p; g.pstride = sp.pstride; g.nsplit = sp.nsplit;
-    g.nt = np; g.tindex = nullptr; g.out = F; g.ld = nf; g.row = R_SFS; g.accumulate = 1;
-    g.reset = (flags & VPM_FLAG_RESET_SFS) ? 1 : 0; g.filter_static = 1; g.stat = stat; g.sld = nf;
-    sfs_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(g);
-    h->launches++;
-  } else if (flags & VPM_FLAG_RESET_SFS) {
-    zero_rows_kernel<<<blocks_for(np, 256), 256, 0, st>>>(F, nf, R_SFS, 3, np, stat, nf);
-    h->launches++;
+  const int G = (int)h->devs.size();
+  const int64_t shard = field_shard(h);
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    cudaStream_t st = d.stream;
+    CK(h, cudaSetDevice(d.id));
+    double *F = (double *)d.fld.p;
+    const int64_t t0 = std::min(np, g * shard), t1 = std::min(np, t0 + shard), nt = t1 - t0;
+    SrcView src{F, nf, 0, 3, 6};
+    Plan plan;
+    TRY(uj_sweep(h, d, st, kernel, F + t0 * nf, nf, nt, src, 0, np, flags, plan));
+    if (nt > 0) {
+      UjFinishArgs f;
+      f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+      f.nt = nt; f.out = F + t0 * nf; f.ld = nf; f.urow = R_U; f.jrow = R_J; f.zrow0 = R_W; f.zrow1 = R_PSE;
+      f.want_U = 1; f.want_J = 1; f.accumulate = 1; f.reset = (flags & VPM_FLAG_RESET) ? 1 : 0;
+      f.stat = F + t0 * nf + R_STATIC; f.sld = nf;
+      uj_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+      h->launches++;
+      CK(h, cudaGetLastError());
+    }
   }
-  CK(h, cudaGetLastError());
+  TRY(field_allgather(h));
+  if (flags & VPM_FLAG_SFS) {
+    for (int g = 0; g < G; ++g) {
+      Dev &d = h->devs[g];
+      cudaStream_t st = d.stream;
+      CK(h, cudaSetDevice(d.id));
+      double *F = (double *)d.fld.p;
+      const int64_t t0 = std::min(np, g * shard), t1 = std::min(np, t0 + shard), nt = t1 - t0;
+      SrcView src{F, nf, 0, 3, 6};
+      Plan sp;
+      TRY(sfs_sweep(h, d, st, kernel, F + t0 * nf, nf, F + t0 * nf + R_J, nf, nullptr, nt, src, F, nf, R_J,
+                    F + R_STATIC, nf, nullptr, np, flags, sp));
+      if (nt > 0) {
+        SfsFinishArgs q;
+        q.partial = (const double *)d.partial.p; q.pstride = sp.pstride; q.nsplit = sp.nsplit;
+        q.nt = nt; q.tindex = nullptr; q.out = F + t0 * nf; q.ld = nf; q.row = R_SFS; q.accumulate = 1;
+        q.reset = (flags & VPM_FLAG_RESET_SFS) ? 1 : 0; q.filter_static = 1;
+        q.stat = F + t0 * nf + R_STATIC; q.sld = nf;
+        sfs_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(q);
+        h->launches++;
+        CK(h, cudaGetLastError());
+      }
+    }
+    TRY(field_allgather(h));
+  } else if (flags & VPM_FLAG_RESET_SFS) {
+    for (int g = 0; g < G; ++g) {  // O(N): every device does all particles, no exchange needed
+      Dev &d = h->devs[g];
+      CK(h, cudaSetDevice(d.id));
+      double *F = (double *)d.fld.p;
+      zero_rows_kernel<<<blocks_for(np, 256), 256, 0, d.stream>>>(F, nf, R_SFS, 3, np, F + R_STATIC, nf);
+      h->launches++;
+      CK(h, cudaGetLastError());
+    }
+  }
   return VPM_OK;
 }
 
@@ -1558,13 +1610,24 @@ int vpm_zeta_direct(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
 
 int vpm_field_upload(vpm_handle *h, const double *P, int64_t nf, int64_t np) {
   TRY(check_field(h, "vpm_field_upload", P, nf, np, 0));
-  Dev &d = h->devs[0];
-  CK(h, cudaSetDevice(d.id));
-  TRY(ensure(h, d.fld, (size_t)std::max<int64_t>(np, 1) * nf * sizeof(double)));
-  if (np > 0) CK(h, cudaMemcpyAsync(d.fld.p, P, (size_t)np * nf * sizeof(double), cudaMemcpyHostToDevice, d.stream));
-  CK(h, cudaStreamSynchronize(d.stream));
+  const int G = (int)h->devs.size();
+  const int64_t shard = (np + G - 1) / G, np_pad = std::max<int64_t>(shard * G, 1);
+  for (Dev &d : h->devs) {
+    CK(h, cudaSetDevice(d.id));
+    TRY(ensure(h, d.fld, (size_t)np_pad * nf * sizeof(double)));
+  }
+  Dev &d0 = h->devs[0];
+  CK(h, cudaSetDevice(d0.id));
+  if (np_pad > np)
+    CK(h, cudaMemsetAsync((double *)d0.fld.p + np * nf, 0, (size_t)(np_pad - np) * nf * sizeof(double), d0.stream));
+  if (np > 0) CK(h, cudaMemcpyAsync(d0.fld.p, P, (size_t)np * nf * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
   h->fld_nf = nf;
   h->fld_np = np;
+  TRY(bcast_from_dev0(h, &Dev::fld, (size_t)np_pad * nf * sizeof(double)));
+  for (int g = G - 1; g >= 0; --g) {
+    CK(h, cudaSetDevice(h->devs[g].id));
+    CK(h, cudaStreamSynchronize(h->devs[g].stream));
+  }
   return VPM_OK;
 }
 
@@ -1580,6 +1643,14 @@ int vpm_field_download(vpm_handle *h, double *P, int64_t nf, int64_t np) {
   return VPM_OK;
 }
 
+static int field_sync_all(vpm_handle *h) {
+  for (int g = (int)h->devs.size() - 1; g >= 0; --g) {
+    CK(h, cudaSetDevice(h->devs[g].id));
+    CK(h, cudaStreamSynchronize(h->devs[g].stream));
+  }
+  return VPM_OK;
+}
+
 int vpm_field_uj(vpm_handle *h, int kernel, int flags) {
   if (!h) return VPM_EINVAL;
   if (h->fld_np < 0) return fail(h, VPM_ESTATE, "vpm_field_uj: no resident field (call vpm_field_upload first)");
@@ -1589,9 +1660,10 @@ int vpm_field_uj(vpm_handle *h, int kernel, int flags) {
   CK(h, cudaSetDevice(d.id));
   CK(h, cudaEventRecord(d.ev[0], d.stream));
   CK(h, cudaEventRecord(d.ev[1], d.stream));
-  TRY(field_uj(h, d, kernel, flags));
+  TRY(field_uj(h, kernel, flags));
+  CK(h, cudaSetDevice(d.id));
   for (int k = 2; k <= 5; ++k) CK(h, cudaEventRecord(d.ev[k], d.stream));
-  CK(h, cudaStreamSynchronize(d.stream));
+  TRY(field_sync_all(h));
   h1_fill_timing(h, d);
   h->timing.uj_ms = h->timing.total_ms;
   return VPM_OK;
@@ -1604,77 +1676,90 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
   if (sp->integration < 0 || sp->integration > 1 || sp->relaxation < 0 || sp->relaxation > 2)
     return fail(h, VPM_EINVAL, "vpm_field_step: integration must be 0 (euler) or 1 (rungekutta3), relaxation 0..2");
   if (h->fld_nf < 44) return fail(h, VPM_EINVAL, "vpm_field_step: the resident field needs >= 44 rows");
-  Dev &d = h->devs[0];
-  cudaStream_t st = d.stream;
-  h->launches = 0;
-  CK(h, cudaSetDevice(d.id));
-  const int64_t np = h->fld_np;
-  if (np == 0) return VPM_OK;
-  const int tr = sp->transposed ? VPM_FLAG_TRANSPOSED : 0;
-  const int uj_flags = VPM_FLAG_RESET | tr | (sp->sfs ? (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS) : 0);
-  const unsigned nb = blocks_for(np, 256);
-  StepArgs a;
-  a.P = (double *)d.fld.p; a.nf = h->fld_nf; a.np = np;
-  a.a = 1.0; a.b = 1.0; a.dt = sp->dt; a.Ux = sp->Uinf[0]; a.Uy = sp->Uinf[1]; a.Uz = sp->Uinf[2];
-  a.f = sp->f; a.g = sp->g; a.zeta0 = zeta0_of(sp->kernel_id); a.Cs = sp->Cs; a.rlxf = sp->rlxf;
-  a.transposed = sp->transposed; a.sfs = sp->sfs; a.clip = sp->clip_backscatter; a.relax_kind = sp->relaxation;
-  a.alpha = sp->alpha; a.sfs_rlxf = sp->sfs_rlxf; a.minC = sp->minC; a.maxC = sp->maxC;
-  a.force_positive = sp->force_positive;
-  a.controls = sp->controls; a.deltat = sp->deltat;
   if (sp->sfs < 0 || sp->sfs > 2) return fail(h, VPM_EINVAL, "vpm_field_step: sfs must be 0 (none), 1 (constant) or 2 (dynamic)");
   if (sp->sfs == 2 && (sp->minC < 0 || sp->maxC < 0 || sp->minC > sp->maxC || sp->alpha <= 0))
     return fail(h, VPM_EINVAL, "vpm_field_step: invalid DynamicSFS parameters (minC=%g maxC=%g alpha=%g)", sp->minC, sp->maxC, sp->alpha);
-  TRY(ensure(h, d.ibuf, 4096));
-  a.nan_flag = (int *)d.ibuf.p;
-  CK(h, cudaMemsetAsync(a.nan_flag, 0, sizeof(int), st));
+  h->launches = 0;
+  const int64_t np = h->fld_np;
+  if (np == 0) return VPM_OK;
+  const int G = (int)h->devs.size();
+  const int tr = sp->transposed ? VPM_FLAG_TRANSPOSED : 0;
+  const int uj_flags = VPM_FLAG_RESET | tr | (sp->sfs ? (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS) : 0);
+  const unsigned nb = blocks_for(np, 256);
+  std::vector<StepArgs> args(G);
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    CK(h, cudaSetDevice(d.id));
+    StepArgs &a = args[g];
+    a.P = (double *)d.fld.p; a.nf = h->fld_nf; a.np = np;
+    a.a = 1.0; a.b = 1.0; a.dt = sp->dt; a.Ux = sp->Uinf[0]; a.Uy = sp->Uinf[1]; a.Uz = sp->Uinf[2];
+    a.f = sp->f; a.g = sp->g; a.zeta0 = zeta0_of(sp->kernel_id); a.Cs = sp->Cs; a.rlxf = sp->rlxf;
+    a.transposed = sp->transposed; a.sfs = sp->sfs; a.clip = sp->clip_backscatter; a.relax_kind = sp->relaxation;
+    a.alpha = sp->alpha; a.sfs_rlxf = sp->sfs_rlxf; a.minC = sp->minC; a.maxC = sp->maxC;
+    a.force_positive = sp->force_positive;
+    a.controls = sp->controls; a.deltat = sp->deltat;
+    TRY(ensure(h, d.ibuf, 4096));
+    a.nan_flag = (int *)d.ibuf.p;
+    CK(h, cudaMemsetAsync(a.nan_flag, 0, sizeof(int), d.stream));
+  }
+  // an O(N) kernel on every device's mirror (all mirrors hold the same data)
+  auto on_all = [&](auto launch) -> int {
+    for (int g = 0; g < G; ++g) {
+      CK(h, cudaSetDevice(h->devs[g].id));
+      launch(args[g], h->devs[g].stream);
+      h->launches++;
+    }
+    CK(h, cudaGetLastError());
+    return VPM_OK;
+  };
   // the SFS hooks around a UJ evaluation at an Euler step / the first RK substep
   // (src/FLOWVPM_subfilterscale.jl:110-135 ConstantSFS, :204-268 DynamicSFS)
   auto sfs_before = [&]() -> int {
     if (sp->sfs != 2) return VPM_OK;
-    step_scale_sigma<<<nb, 256, 0, st>>>(a, 0);
-    TRY(field_uj(h, d, sp->kernel_id, VPM_FLAG_RESET | VPM_FLAG_RESET_SFS | VPM_FLAG_SFS | tr));
-    step_dyn_store<<<nb, 256, 0, st>>>(a);
-    step_scale_sigma<<<nb, 256, 0, st>>>(a, 1);
-    h->launches += 3;
+    TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_scale_sigma<<<nb, 256, 0, st>>>(a, 0); }));
+    TRY(field_uj(h, sp->kernel_id, VPM_FLAG_RESET | VPM_FLAG_RESET_SFS | VPM_FLAG_SFS | tr));
+    TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_dyn_store<<<nb, 256, 0, st>>>(a); }));
+    TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_scale_sigma<<<nb, 256, 0, st>>>(a, 1); }));
     return VPM_OK;
   };
-  auto sfs_after = [&]() {
-    if (sp->sfs == 1) { step_sfs_coeff<<<nb, 256, 0, st>>>(a); h->launches++; }
-    if (sp->sfs == 2) { step_dyn_coeff<<<nb, 256, 0, st>>>(a); h->launches++; }
-    if (sp->sfs && (sp->controls & 3)) { step_sfs_controls<<<nb, 256, 0, st>>>(a); h->launches++; }
+  auto sfs_after = [&]() -> int {
+    if (sp->sfs == 1) TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_sfs_coeff<<<nb, 256, 0, st>>>(a); }));
+    if (sp->sfs == 2) TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_dyn_coeff<<<nb, 256, 0, st>>>(a); }));
+    if (sp->sfs && (sp->controls & 3))
+      TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_sfs_controls<<<nb, 256, 0, st>>>(a); }));
+    return VPM_OK;
   };
-  CK(h, cudaEventRecord(d.ev[0], st));
-  CK(h, cudaEventRecord(d.ev[1], st));
+  Dev &d0 = h->devs[0];
+  CK(h, cudaSetDevice(d0.id));
+  CK(h, cudaEventRecord(d0.ev[0], d0.stream));
+  CK(h, cudaEventRecord(d0.ev[1], d0.stream));
   if (sp->integration == 0) {  // euler: src/FLOWVPM_timeintegration.jl:23-37
     TRY(sfs_before());
-    TRY(field_uj(h, d, sp->kernel_id, uj_flags));
-    sfs_after();
-    step_euler<<<nb, 256, 0, st>>>(a, sp->relax ? 1 : 0);
-    h->launches++;
+    TRY(field_uj(h, sp->kernel_id, uj_flags));
+    TRY(sfs_after());
+    const int relax = sp->relax ? 1 : 0;
+    TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_euler<<<nb, 256, 0, st>>>(a, relax); }));
   } else {  // rungekutta3: src/FLOWVPM_timeintegration.jl:388-461
-    step_reset_M<<<nb, 256, 0, st>>>(a);
-    h->launches++;
+    TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_reset_M<<<nb, 256, 0, st>>>(a); }));
     const double ab[3][2] = {{0.0, 1.0 / 3}, {-5.0 / 9, 15.0 / 16}, {-153.0 / 128, 8.0 / 15}};
     for (int k = 0; k < 3; ++k) {
-      a.a = ab[k][0]; a.b = ab[k][1];
+      for (StepArgs &a : args) { a.a = ab[k][0]; a.b = ab[k][1]; }
       if (k == 0) TRY(sfs_before());
-      TRY(field_uj(h, d, sp->kernel_id, uj_flags));
-      if (k == 0) sfs_after();
-      step_rk_stage<<<nb, 256, 0, st>>>(a);
-      h->launches++;
+      TRY(field_uj(h, sp->kernel_id, uj_flags));
+      if (k == 0) TRY(sfs_after());
+      TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_rk_stage<<<nb, 256, 0, st>>>(a); }));
     }
     if (sp->relax && sp->relaxation) {
-      TRY(field_uj(h, d, sp->kernel_id, VPM_FLAG_RESET | tr));
-      step_relax<<<nb, 256, 0, st>>>(a);
-      h->launches++;
+      TRY(field_uj(h, sp->kernel_id, VPM_FLAG_RESET | tr));
+      TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_relax<<<nb, 256, 0, st>>>(a); }));
     }
   }
-  CK(h, cudaGetLastError());
-  for (int k = 2; k <= 5; ++k) CK(h, cudaEventRecord(d.ev[k], st));
+  CK(h, cudaSetDevice(d0.id));
+  for (int k = 2; k <= 5; ++k) CK(h, cudaEventRecord(d0.ev[k], d0.stream));
   int nan_flag = 0;
-  CK(h, cudaMemcpyAsync(&nan_flag, a.nan_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(h, cudaStreamSynchronize(st));
-  h1_fill_timing(h, d);
+  CK(h, cudaMemcpyAsync(&nan_flag, args[0].nan_flag, sizeof(int), cudaMemcpyDeviceToHost, d0.stream));
+  TRY(field_sync_all(h));
+  h1_fill_timing(h, d0);
   h->timing.uj_ms = h->timing.total_ms;
   if (nan_flag) return fail(h, VPM_ESTATE, "NaN in dynamicprocedure_pseudo3level_afterUJ");  // subfilterscale.jl:645-652
   return VPM_OK;

@@ -118,3 +118,32 @@ def test_nearfield_leafpairs_multi_gpu(vpm, ncrit):
         assert np.array_equal(tb[0:4], ref[0:4])
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("sfs", [False, "dynamic"])
+def test_resident_step_multi_gpu(vpm, sfs):
+    """vpm_field_step with the mirror replicated on every device of the handle: targets sharded,
+    whole particle columns all-gathered after each sweep (NCCL), O(N) kernels run everywhere"""
+    g = _ngpu()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    h = vpm.Handle(min(g, 4))
+    try:
+        pf = vpm.fields.cloud_field(3001, kernel=vpm.gaussianerf, static_fraction=0.05, seed=51)
+        ref = pf.particles.copy(order="F")
+        kw = dict(integration="rungekutta3", f=0.0, g=0.2, sfs=sfs, clip_backscatter=bool(sfs), relaxation="pedrizzetti",
+                  relax=True, rlxf=0.3, alpha=0.9, sfs_rlxf=0.3)
+        rf = vpm.ResidentField(pf, handle=h)
+        for _ in range(2):
+            rf.nextstep(1e-3, **kw)
+            oracle.field_step(ref, pf.np, "gaussianerf", 1e-3, transposed=True, **kw)
+        rf.download()
+        for rows in (slice(0, 7), slice(9, 12), slice(15, 24), slice(27, 42)):
+            assert relerr(pf.particles[rows, :pf.np], ref[rows, :pf.np]) < 1e-9, rows
+        # UJ_direct on the resident field across devices
+        rf.UJ(sfs=True, reset=True, reset_sfs=True)
+        oracle.uj_direct(ref, pf.np, "gaussianerf", sfs=True, reset=True, reset_sfs=True)
+        rf.download()
+        assert_parity(pf.particles, ref, pf.np, tol=1e-9)
+    finally:
+        h.close()
