@@ -427,6 +427,17 @@ def main():
         extras["rvpm_step_ms_estimate"] = {"value": 5 * uj_ms + 4 * extras["sfs"]["ms"],
                                            "what": "5 U/J + 4 SFS sweeps (RK3 + DynamicSFS + relaxation, SURVEY 3.1), O(N) host work excluded"}
         extras["rvpm_step_c2"] = rvpm_step_c2(vpm, h)
+        # the metric's second half at the bench size: one whole rVPM time step on the device
+        # (RK3 + reformulated VPM + DynamicSFS + relaxation = 5 U/J + 4 SFS sweeps, vpm_field_step)
+        rf = vpm.ResidentField(pf, handle=h)
+        tw = time.perf_counter()
+        rf.nextstep(1e-4, integration="rungekutta3", f=0.0, g=0.2, sfs="dynamic", clip_backscatter=True,
+                    force_positive=True, alpha=0.999, relaxation="correctedpedrizzetti", relax=True)
+        extras["rvpm_step"] = {"n_particles": n, "kernel": args.kernel, "s_per_step": time.perf_counter() - tw,
+                               "what": "one device-resident step: rungekutta3 + rVPM (f=0, g=1/5) + DynamicSFS "
+                                       "(pseudo3level_positive, clipping_backscatter) + correctedpedrizzetti "
+                                       "relaxation = 5 U/J + 4 SFS sweeps (9 N^2 pair visits); 8 GPUs: "
+                                       "profiles/r1_rvpm_step_1M_8gpu.json"}
         extras["fmm_nearfield"] = nearfield_extra(vpm, h, n)
         line["extras"] = extras
         v, desc, cores = cpu_sample(n, args.kernel, args.cpu_seconds)
