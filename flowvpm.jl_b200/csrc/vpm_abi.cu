@@ -548,8 +548,9 @@ int ensure_comms(vpm_handle *h) {
   const int G = (int)h->devs.size();
   std::vector<int> ids(G);
   for (int g = 0; g < G; ++g) ids[g] = h->devs[g].id;
-  h->comms.assign(G, nullptr);
-  NCK(h, g_nccl.comm_init_all(h->comms.data(), G, ids.data()));
+  std::vector<void *> comms(G, nullptr);
+  NCK(h, g_nccl.comm_init_all(comms.data(), G, ids.data()));
+  h->comms = comms;  // only a fully initialised set is kept
   return VPM_OK;
 }
 
@@ -595,6 +596,10 @@ int uj_direct_multi(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
     for (int64_t i = 0; i < np; ++i) h->h_stat[i] = P[nf * i + R_STATIC];
   }
   const bool prior = !reset || has_static;
+  const bool pinned = host_is_pinned(P);
+  if (!pinned) TRY(ensure_stage(h, (size_t)np * (7 + RES_ROWS + 3)));
+  double *stg18 = pinned ? nullptr : h->h_stage + (size_t)np * 7;
+  double *stg3 = pinned ? nullptr : h->h_stage + (size_t)np * (7 + RES_ROWS);
   std::vector<Plan> plans(G);
   // sources (X, Gamma, sigma, static flags) go to device 0 once and are broadcast over NVLink
   for (int g = 0; g < G; ++g) {
@@ -609,8 +614,16 @@ int uj_direct_multi(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
     Dev &d0 = h->devs[0];
     CK(h, cudaSetDevice(d0.id));
     CK(h, cudaEventRecord(d0.ev[0], d0.stream));
-    CK(h, cudaMemcpy2DAsync(d0.in7.p, 7 * sizeof(double), P, nf * sizeof(double), 7 * sizeof(double),
-                            (size_t)np, cudaMemcpyHostToDevice, d0.stream));
+    if (pinned) {
+      CK(h, cudaMemcpy2DAsync(d0.in7.p, 7 * sizeof(double), P, nf * sizeof(double), 7 * sizeof(double),
+                              (size_t)np, cudaMemcpyHostToDevice, d0.stream));
+    } else {  // pageable matrix: gather the strided rows into the pinned staging block (see h1_upload)
+      TRY(ensure_stage(h, (size_t)np * (7 + RES_ROWS + 3)));
+      gather_rows(h->h_stage, P, nf, R_X, 7, np);
+      CK(h, cudaMemcpyAsync(d0.in7.p, h->h_stage, (size_t)np * 7 * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
+      if (prior) gather_rows(stg18, P, nf, R_U, RES_ROWS, np);
+      if (sfs_rows) gather_rows(stg3, P, nf, R_SFS, 3, np);
+    }
     if (has_static)
       CK(h, cudaMemcpyAsync(d0.stat.p, h->h_stat, (size_t)np * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
   }
@@ -625,14 +638,18 @@ int uj_direct_multi(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
     double *res = (double *)d.res18.p + t0 * RES_ROWS;
     double *sfs = (double *)d.sfs3.p + t0 * 3;
     if (nt > 0) {
-      if (prior)
+      if (prior && pinned)
         CK(h, cudaMemcpy2DAsync(res, RES_ROWS * sizeof(double), P + nf * t0 + R_U, nf * sizeof(double),
                                 RES_ROWS * sizeof(double), (size_t)nt, cudaMemcpyHostToDevice, st));
+      else if (prior)
+        CK(h, cudaMemcpyAsync(res, stg18 + t0 * RES_ROWS, (size_t)nt * RES_ROWS * sizeof(double), cudaMemcpyHostToDevice, st));
       else
         CK(h, cudaMemsetAsync(res, 0, (size_t)nt * RES_ROWS * sizeof(double), st));
-      if (sfs_rows)
+      if (sfs_rows && pinned)
         CK(h, cudaMemcpy2DAsync(sfs, 3 * sizeof(double), P + nf * t0 + R_SFS, nf * sizeof(double),
                                 3 * sizeof(double), (size_t)nt, cudaMemcpyHostToDevice, st));
+      else if (sfs_rows)
+        CK(h, cudaMemcpyAsync(sfs, stg3 + t0 * 3, (size_t)nt * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     }
     if (g == 0) CK(h, cudaEventRecord(d.ev[1], st));
     SrcView src{(const double *)d.in7.p, 7, 0, 3, 6};
@@ -705,19 +722,31 @@ int uj_direct_multi(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
     const int64_t t0 = std::min(np, g * shard), t1 = std::min(np, t0 + shard), nt = t1 - t0;
     if (nt == 0) continue;
     CK(h, cudaSetDevice(d.id));
-    CK(h, cudaMemcpy2DAsync(P + nf * t0 + R_U, nf * sizeof(double), (double *)d.res18.p + t0 * RES_ROWS,
-                            RES_ROWS * sizeof(double), RES_ROWS * sizeof(double), (size_t)nt,
-                            cudaMemcpyDeviceToHost, d.stream));
-    if (sfs_rows)
-      CK(h, cudaMemcpy2DAsync(P + nf * t0 + R_SFS, nf * sizeof(double), (double *)d.sfs3.p + t0 * 3,
-                              3 * sizeof(double), 3 * sizeof(double), (size_t)nt, cudaMemcpyDeviceToHost,
-                              d.stream));
+    if (pinned) {
+      CK(h, cudaMemcpy2DAsync(P + nf * t0 + R_U, nf * sizeof(double), (double *)d.res18.p + t0 * RES_ROWS,
+                              RES_ROWS * sizeof(double), RES_ROWS * sizeof(double), (size_t)nt,
+                              cudaMemcpyDeviceToHost, d.stream));
+      if (sfs_rows)
+        CK(h, cudaMemcpy2DAsync(P + nf * t0 + R_SFS, nf * sizeof(double), (double *)d.sfs3.p + t0 * 3,
+                                3 * sizeof(double), 3 * sizeof(double), (size_t)nt, cudaMemcpyDeviceToHost,
+                                d.stream));
+    } else {  // contiguous D2H of each shard into the pinned staging block, scattered below
+      CK(h, cudaMemcpyAsync(stg18 + t0 * RES_ROWS, (double *)d.res18.p + t0 * RES_ROWS,
+                            (size_t)nt * RES_ROWS * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+      if (sfs_rows)
+        CK(h, cudaMemcpyAsync(stg3 + t0 * 3, (double *)d.sfs3.p + t0 * 3, (size_t)nt * 3 * sizeof(double),
+                              cudaMemcpyDeviceToHost, d.stream));
+    }
   }
   for (int g = G - 1; g >= 0; --g) {
     Dev &d = h->devs[g];
     CK(h, cudaSetDevice(d.id));
     if (g == 0) CK(h, cudaEventRecord(d.ev[5], d.stream));
     CK(h, cudaStreamSynchronize(d.stream));
+  }
+  if (!pinned) {
+    scatter_rows(P, nf, R_U, RES_ROWS, np, stg18);
+    if (sfs_rows) scatter_rows(P, nf, R_SFS, 3, np, stg3);
   }
   h1_fill_timing(h, h->devs[0]);
   h->np_resident = -1;
