@@ -18,7 +18,8 @@ SYMBOLS = [
     "vpm_pin_host", "vpm_unpin_host",
     "vpm_p2p_buffers", "vpm_p2p_leafpairs", "vpm_estr_leafpairs",
     "vpm_zeta_direct", "vpm_zeta_leafpairs",
-    "vpm_field_upload", "vpm_field_download", "vpm_field_uj", "vpm_field_step",
+    "vpm_field_upload", "vpm_field_download", "vpm_field_uj", "vpm_field_step", "vpm_field_rbf",
+    "vpm_field_tsgm",
     "vpm_uj_device", "vpm_sfs_device",
     "vpm_get_timing", "vpm_measure_dfma_peak", "vpm_test_math",
 ]
@@ -39,11 +40,12 @@ class VpmStepParams(C.Structure):
     _fields_ = [("dt", C.c_double), ("f", C.c_double), ("g", C.c_double), ("Uinf", C.c_double * 3),
                 ("Cs", C.c_double), ("rlxf", C.c_double),
                 ("alpha", C.c_double), ("sfs_rlxf", C.c_double), ("minC", C.c_double), ("maxC", C.c_double),
-                ("deltat", C.c_double),
+                ("deltat", C.c_double), ("nu", C.c_double), ("sgm0", C.c_double), ("cs_beta", C.c_double),
+                ("cs_tol", C.c_double),
                 ("kernel_id", C.c_int32), ("integration", C.c_int32), ("relaxation", C.c_int32),
                 ("relax", C.c_int32), ("sfs", C.c_int32), ("clip_backscatter", C.c_int32),
                 ("transposed", C.c_int32), ("force_positive", C.c_int32), ("controls", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("viscous", C.c_int32), ("cs_itmax", C.c_int32), ("cs_iterror", C.c_int32)]
 
 
 class VpmError(RuntimeError):
@@ -90,6 +92,8 @@ def load():
     lib.vpm_field_download.argtypes = [p, p, i64, i64]
     lib.vpm_field_uj.argtypes = [p, i32, i32]
     lib.vpm_field_step.argtypes = [p, P(VpmStepParams)]
+    lib.vpm_field_rbf.argtypes = [p, i32, i32, dbl, i32, P(i32), P(dbl)]
+    lib.vpm_field_tsgm.argtypes = [p, P(dbl), i32]
     lib.vpm_uj_device.argtypes = [p, p, i64, i64, i64, p, i32, i32, p]
     lib.vpm_sfs_device.argtypes = [p, p, p, p, i64, i64, i64, p, i32, i32, p]
     lib.vpm_get_timing.argtypes = [p, P(VpmTiming)]

@@ -72,6 +72,7 @@ struct vpm_handle {
   std::vector<void *> pinned;
   int launches = 0;
   int64_t fld_nf = 0, fld_np = -1;  // device mirror of the whole particle matrix (vpm_field_*)
+  double fld_t_sgm = 0.0;           // CoreSpreading.t_sgm of the resident field
   int device_timing = 0;  // 1/2: ev[6..7] bracket the last _device U/J / SFS pair kernel
   // single-process multi-GPU (n_gpus > 1): NCCL communicators, one per device
   void *nccl_lib = nullptr;
@@ -989,6 +990,141 @@ int field_uj(vpm_handle *h, int kernel, int flags) {
   return VPM_OK;
 }
 
+
+// zeta_direct on the resident mirror(s): J[1:3] of every particle <- sum_j Gamma_j zeta_sigma_j
+int field_zeta(vpm_handle *h, int kernel) {
+  const int64_t nf = h->fld_nf, np = h->fld_np;
+  if (np == 0) return VPM_OK;
+  const int G = (int)h->devs.size();
+  const int64_t shard = field_shard(h);
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    cudaStream_t st = d.stream;
+    CK(h, cudaSetDevice(d.id));
+    double *F = (double *)d.fld.p;
+    const int64_t t0 = std::min(np, g * shard), t1 = std::min(np, t0 + shard), nt = t1 - t0;
+    SrcView src{F, nf, 0, 3, 6};
+    Plan sp;
+    TRY(sfs_sweep(h, d, st, kernel, F + t0 * nf, nf, F + t0 * nf + R_J, nf, nullptr, nt, src, F, nf, R_J, nullptr, 1,
+                  nullptr, np, VPM_FLAG_TRANSPOSED, sp, false, MODE_ZETA));
+    if (nt > 0) {
+      SfsFinishArgs q;
+      q.partial = (const double *)d.partial.p; q.pstride = sp.pstride; q.nsplit = sp.nsplit;
+      q.nt = nt; q.tindex = nullptr; q.out = F + t0 * nf; q.ld = nf; q.row = R_J; q.accumulate = 0; q.reset = 0;
+      q.filter_static = 0; q.stat = nullptr; q.sld = 1;
+      sfs_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(q);
+      h->launches++;
+      CK(h, cudaGetLastError());
+    }
+  }
+  return field_allgather(h);
+}
+
+StepArgs step_args_of(vpm_handle *h, Dev &d) {
+  StepArgs a{};
+  a.P = (double *)d.fld.p; a.nf = h->fld_nf; a.np = h->fld_np;
+  return a;
+}
+
+// launch one O(N) kernel on every device's mirror
+template <class L>
+int field_on_all(vpm_handle *h, L launch) {
+  for (Dev &d : h->devs) {
+    CK(h, cudaSetDevice(d.id));
+    launch(d);
+    h->launches++;
+  }
+  CK(h, cudaGetLastError());
+  return VPM_OK;
+}
+
+// sum over the non-static particles of r_k^2 (mode 0) or Gamma_k J_k (mode 1), from device 0
+int field_reduce3(vpm_handle *h, int mode, double out[3]) {
+  Dev &d = h->devs[0];
+  CK(h, cudaSetDevice(d.id));
+  TRY(ensure(h, d.jbuf, (size_t)(kRedBlocks * 3 + 3) * sizeof(double)));
+  double *partial = (double *)d.jbuf.p, *res = partial + kRedBlocks * 3;
+  rbf_reduce_partial<<<kRedBlocks, 256, 0, d.stream>>>(step_args_of(h, d), mode, partial);
+  rbf_reduce_final<<<1, kRedBlocks, 0, d.stream>>>(partial, res);
+  h->launches += 2;
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(out, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+  CK(h, cudaStreamSynchronize(d.stream));
+  return VPM_OK;
+}
+
+// rbf_conjugategradient (src/FLOWVPM_viscous.jl:309-478) with cs.zeta = zeta_direct
+int field_rbf(vpm_handle *h, int kernel, int itmax, double tol, int iterror, int *iterations, double *residuals) {
+  const double eps = 2.220446049250313e-16;
+  const unsigned nb = blocks_for(h->fld_np, 256);
+  auto stage = [&](int st, const double c[3]) {
+    return field_on_all(h, [&](Dev &d) { rbf_stage<<<nb, 256, 0, d.stream>>>(step_args_of(h, d), st, c[0], c[1], c[2]); });
+  };
+  const double zero3[3] = {0, 0, 0};
+  double rr0s[3], rrs[3], prev_rrs[3], pAps[3], alphas[3], betas[3];
+  bool flags[3];
+  TRY(stage(0, zero3));
+  TRY(field_zeta(h, kernel));
+  TRY(stage(1, zero3));
+  TRY(field_reduce3(h, 0, rr0s));
+  for (int k = 0; k < 3; ++k) {
+    rrs[k] = rr0s[k];
+    flags[k] = sqrt(rr0s[k]) > tol || sqrt(rrs[k] / rr0s[k]) > tol;
+  }
+  int it_done = 0;
+  bool failed = false;
+  for (int it = 1; it <= itmax; ++it) {
+    if (!(flags[0] || flags[1] || flags[2])) break;
+    it_done = it;
+    TRY(field_zeta(h, kernel));
+    TRY(field_reduce3(h, 1, pAps));
+    for (int k = 0; k < 3; ++k) {
+      alphas[k] = flags[k] ? rrs[k] / pAps[k] : 0.0;  // Julia: x * false == 0 (strong zero)
+      prev_rrs[k] = rrs[k];
+    }
+    TRY(stage(2, alphas));
+    TRY(field_reduce3(h, 0, rrs));
+    for (int k = 0; k < 3; ++k) {
+      betas[k] = rrs[k] / prev_rrs[k];
+      if (fabs(prev_rrs[k]) <= 2 * eps) betas[k] = 1;
+    }
+    TRY(stage(3, betas));
+    for (int k = 0; k < 3; ++k)
+      flags[k] = flags[k] && (fabs(rr0s[k]) <= 2 * eps ? false : sqrt(rrs[k] / rr0s[k]) > tol);
+    if (it == itmax && (flags[0] || flags[1] || flags[2])) failed = true;
+  }
+  TRY(stage(4, zero3));
+  if (iterations) *iterations = it_done;
+  if (residuals)
+    for (int k = 0; k < 3; ++k) residuals[k] = rr0s[k] > 0 ? sqrt(rrs[k] / rr0s[k]) : 0.0;
+  if (failed && iterror)
+    return fail(h, VPM_ESTATE, "Maximum number of iterations %d reached before convergence. Errors: %g %g %g, tolerance: %g",
+                itmax, sqrt(rrs[0] / rr0s[0]), sqrt(rrs[1] / rr0s[1]), sqrt(rrs[2] / rr0s[2]), tol);
+  return VPM_OK;
+}
+
+// viscousdiffusion(pfield, CoreSpreading, dt; aux1, aux2): src/FLOWVPM_viscous.jl:152-223
+int field_corespreading(vpm_handle *h, const vpm_step_params *sp, double aux1, double aux2) {
+  const unsigned nb = blocks_for(h->fld_np, 256);
+  const int rk = sp->integration == 1;
+  TRY(field_on_all(h, [&](Dev &d) {
+    StepArgs a = step_args_of(h, d);
+    a.a = aux1; a.b = aux2; a.dt = sp->dt;
+    cs_spread<<<nb, 256, 0, d.stream>>>(a, sp->nu, rk);
+  }));
+  const bool proceed = !rk || fabs(aux2 - 8.0 / 15) <= 1e-7;
+  if (!proceed) return VPM_OK;
+  h->fld_t_sgm += sp->dt;
+  const double beta_cur = sqrt(2 * sp->nu * h->fld_t_sgm / (sp->sgm0 * sp->sgm0) + 1);
+  if (beta_cur >= sp->cs_beta) {
+    TRY(field_zeta(h, sp->kernel_id));
+    TRY(field_on_all(h, [&](Dev &d) { cs_reset<<<nb, 256, 0, d.stream>>>(step_args_of(h, d), sp->sgm0); }));
+    TRY(field_rbf(h, sp->kernel_id, sp->cs_itmax, sp->cs_tol, sp->cs_iterror, nullptr, nullptr));
+    h->fld_t_sgm = 0.0;
+  }
+  return VPM_OK;
+}
+
 double zeta0_of(int kernel) {  // kernel.zeta(0): src/FLOWVPM_kernel.jl:45,51,60,69-74
   const double pi = 3.14159265358979323846;
   switch (kernel) {
@@ -1652,6 +1788,7 @@ int vpm_field_upload(vpm_handle *h, const double *P, int64_t nf, int64_t np) {
   if (np > 0) CK(h, cudaMemcpyAsync(d0.fld.p, P, (size_t)np * nf * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
   h->fld_nf = nf;
   h->fld_np = np;
+  h->fld_t_sgm = 0.0;
   TRY(bcast_from_dev0(h, &Dev::fld, (size_t)np_pad * nf * sizeof(double)));
   for (int g = G - 1; g >= 0; --g) {
     CK(h, cudaSetDevice(h->devs[g].id));
@@ -1708,6 +1845,11 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
   if (sp->sfs < 0 || sp->sfs > 2) return fail(h, VPM_EINVAL, "vpm_field_step: sfs must be 0 (none), 1 (constant) or 2 (dynamic)");
   if (sp->sfs == 2 && (sp->minC < 0 || sp->maxC < 0 || sp->minC > sp->maxC || sp->alpha <= 0))
     return fail(h, VPM_EINVAL, "vpm_field_step: invalid DynamicSFS parameters (minC=%g maxC=%g alpha=%g)", sp->minC, sp->maxC, sp->alpha);
+  if (sp->viscous < 0 || sp->viscous > 1) return fail(h, VPM_EINVAL, "vpm_field_step: viscous must be 0 (Inviscid) or 1 (CoreSpreading)");
+  if (sp->viscous == 1 && sp->kernel_id != K_GERF)
+    return fail(h, VPM_EINVAL, "vpm_field_step: kernel %d is not compatible with viscous scheme CoreSpreading; compatible kernels are gaussianerf", sp->kernel_id);  // src/FLOWVPM_utils.jl:58-64
+  if (sp->viscous == 1 && (sp->sgm0 <= 0 || sp->nu < 0 || sp->cs_itmax < 0))
+    return fail(h, VPM_EINVAL, "vpm_field_step: invalid CoreSpreading parameters (nu=%g sgm0=%g itmax=%d)", sp->nu, sp->sgm0, sp->cs_itmax);
   h->launches = 0;
   const int64_t np = h->fld_np;
   if (np == 0) return VPM_OK;
@@ -1768,6 +1910,7 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
     TRY(sfs_after());
     const int relax = sp->relax ? 1 : 0;
     TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_euler<<<nb, 256, 0, st>>>(a, relax); }));
+    if (sp->viscous) TRY(field_corespreading(h, sp, 0.0, 0.0));
   } else {  // rungekutta3: src/FLOWVPM_timeintegration.jl:388-461
     TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_reset_M<<<nb, 256, 0, st>>>(a); }));
     const double ab[3][2] = {{0.0, 1.0 / 3}, {-5.0 / 9, 15.0 / 16}, {-153.0 / 128, 8.0 / 15}};
@@ -1777,6 +1920,7 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
       TRY(field_uj(h, sp->kernel_id, uj_flags));
       if (k == 0) TRY(sfs_after());
       TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_rk_stage<<<nb, 256, 0, st>>>(a); }));
+      if (sp->viscous) TRY(field_corespreading(h, sp, ab[k][0], ab[k][1]));
     }
     if (sp->relax && sp->relaxation) {
       TRY(field_uj(h, sp->kernel_id, VPM_FLAG_RESET | tr));
@@ -1791,6 +1935,26 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
   h1_fill_timing(h, d0);
   h->timing.uj_ms = h->timing.total_ms;
   if (nan_flag) return fail(h, VPM_ESTATE, "NaN in dynamicprocedure_pseudo3level_afterUJ");  // subfilterscale.jl:645-652
+  return VPM_OK;
+}
+
+int vpm_field_rbf(vpm_handle *h, int kernel, int itmax, double tol, int iterror, int *iterations, double *residuals) {
+  if (!h) return VPM_EINVAL;
+  if (h->fld_np < 0) return fail(h, VPM_ESTATE, "vpm_field_rbf: no resident field (call vpm_field_upload first)");
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "vpm_field_rbf: unknown kernel_id %d", kernel);
+  if (itmax < 0 || !(tol >= 0)) return fail(h, VPM_EINVAL, "vpm_field_rbf: itmax >= 0 and tol >= 0 required");
+  h->launches = 0;
+  if (iterations) *iterations = 0;
+  if (h->fld_np == 0) return VPM_OK;
+  int rc = field_rbf(h, kernel, itmax, tol, iterror, iterations, residuals);
+  int rs = field_sync_all(h);
+  h->timing.kernel_launches = h->launches;
+  return rc != VPM_OK ? rc : rs;
+}
+
+int vpm_field_tsgm(vpm_handle *h, double *t_sgm, int set) {
+  if (!h || !t_sgm) return VPM_EINVAL;
+  if (set) h->fld_t_sgm = *t_sgm; else *t_sgm = h->fld_t_sgm;
   return VPM_OK;
 }
 

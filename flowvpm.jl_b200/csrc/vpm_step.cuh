@@ -262,4 +262,94 @@ __global__ void step_relax(StepArgs a) {
   relax_particle(p, a.rlxf, a.relax_kind);
 }
 
+// ---- CoreSpreading viscous scheme (src/FLOWVPM_viscous.jl:152-223) and the RBF conjugate-
+// gradient re-discretisation it triggers (:309-478).  The scalar recurrences of the CG
+// (alphas, betas, convergence flags) run on the host; these are its O(N) pieces.
+enum { S_VOL = 7 };
+
+// sigma <- sqrt(sigma^2 + 2 nu dt) (Euler) / the low-storage RK form with M[7] (:159-175)
+__global__ void cs_spread(StepArgs a, double nu, int rk) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+  if (rk) {
+    p[S_M + 6] = a.a * p[S_M + 6] + a.dt * 2 * nu;
+    p[S_SIGMA] = sqrt(p[S_SIGMA] * p[S_SIGMA] + a.b * p[S_M + 6]);
+  } else {
+    p[S_SIGMA] = sqrt(p[S_SIGMA] * p[S_SIGMA] + 2 * nu * a.dt);
+  }
+}
+
+// overgrown cores: target vorticity M[7:9] <- J[1:3] (basis evaluation), sigma <- sgm0 (:205-212)
+__global__ void cs_reset(StepArgs a, double sgm0) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) p[S_M + 6 + k] = p[S_J + k];
+  p[S_SIGMA] = sgm0;
+}
+
+// stage 0: initial guess Gamma = omega_targ * vol (:334-341); stage 1: r0 = omega_targ - omega_cur,
+// p0 = r0 (:346-357); stage 2: x += alpha p, r -= alpha A p (:392-398); stage 3: p = r + beta p
+// (:410-414); stage 4: Gamma <- solution (:449-453)
+__global__ void rbf_stage(StepArgs a, int stage, double c0, double c1, double c2) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+  double *M = p + S_M, *G = p + S_G;
+  const double *J = p + S_J;
+  const double c[3] = {c0, c1, c2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (stage == 0) { M[k] = M[6 + k] * p[S_VOL]; G[k] = M[k]; }
+    else if (stage == 1) { M[3 + k] = M[6 + k] - J[k]; G[k] = M[3 + k]; }
+    else if (stage == 2) { M[k] += c[k] * G[k]; M[3 + k] -= c[k] * J[k]; }
+    else if (stage == 3) { G[k] = M[3 + k] + c[k] * G[k]; }
+    else { G[k] = M[k]; }
+  }
+}
+
+// deterministic 3-component reductions over the non-static particles:
+// mode 0: sum r_k^2 (r = M[4:6]); mode 1: sum Gamma_k J_k (the pAp product).
+// Fixed launch shape (kRedBlocks x 256) and fixed tree order => run-to-run identical.
+constexpr int kRedBlocks = 256;
+__global__ void rbf_reduce_partial(StepArgs a, int mode, double *partial) {
+  __shared__ double sh[3][256];
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.np; i += (int64_t)gridDim.x * blockDim.x) {
+    const double *p = a.P + i * a.nf;
+    if (p[S_STATIC] != 0.0) continue;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      acc[k] += mode == 0 ? p[S_M + 3 + k] * p[S_M + 3 + k] : p[S_G + k] * p[S_J + k];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) partial[blockIdx.x * 3 + threadIdx.x] = sh[threadIdx.x][0];
+}
+__global__ void rbf_reduce_final(const double *partial, double *out) {
+  __shared__ double sh[3][kRedBlocks];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] = partial[threadIdx.x * 3 + k];
+  __syncthreads();
+  for (int s = kRedBlocks / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) out[threadIdx.x] = sh[threadIdx.x][0];
+}
+
 }  // namespace vpm

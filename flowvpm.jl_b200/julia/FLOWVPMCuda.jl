@@ -199,14 +199,16 @@ end
 # ------------------------------------------------------------------------------
 # Optional: the integrator on the device (include/vpm_cuda.h vpm_field_*).  Mirrors
 # `nextstep` (src/FLOWVPM_particlefield.jl:435-460) for ReformulatedVPM{f,g}, NoSFS /
-# ConstantSFS / DynamicSFS (pseudo3level), Inviscid, relaxation pedrizzetti / correctedpedrizzetti.
+# ConstantSFS / DynamicSFS (pseudo3level), Inviscid or CoreSpreading, relaxation pedrizzetti /
+# correctedpedrizzetti.
 # ------------------------------------------------------------------------------
 struct StepParams
     dt::Cdouble; f::Cdouble; g::Cdouble; Uinf::NTuple{3,Cdouble}; Cs::Cdouble; rlxf::Cdouble
     alpha::Cdouble; sfs_rlxf::Cdouble; minC::Cdouble; maxC::Cdouble; deltat::Cdouble
+    nu::Cdouble; sgm0::Cdouble; cs_beta::Cdouble; cs_tol::Cdouble
     kernel_id::Int32; integration::Int32; relaxation::Int32; relax::Int32
     sfs::Int32; clip_backscatter::Int32; transposed::Int32; force_positive::Int32
-    controls::Int32; reserved::Int32
+    controls::Int32; viscous::Int32; cs_itmax::Int32; cs_iterror::Int32
 end
 
 function upload!(pfield::vpm.ParticleField{Float64})
@@ -234,11 +236,23 @@ function nextstep_cuda!(pfield::vpm.ParticleField{Float64}, dt::Real; relax::Boo
     integration = pfield.integration === vpm.rungekutta3 ? 1 : 0
     Uinf = pfield.Uinf(pfield.t)
     deltat = pfield.nt > 0 ? pfield.t / pfield.nt : 0.0
+    V = pfield.viscous
+    cs = V isa vpm.CoreSpreading          # evaluated with zeta_direct on the device
+    nu, sgm0, cs_beta, cs_tol = cs ? (V.nu, V.sgm0, V.beta, V.tol) : (0.0, 1.0, 1.5, 1e-3)
+    if cs
+        t_sgm = Ref{Cdouble}(V.t_sgm)
+        check(ccall((:vpm_field_tsgm, lib[]), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Cint), handle[], t_sgm, 1))
+    end
     sp = Ref(StepParams(dt, form.f, form.g, (Uinf[1], Uinf[2], Uinf[3]), Cs, rlx.rlxf, alpha, sfs_rlxf, minC, maxC,
-                        deltat, kernel_id(pfield.kernel), integration, relaxation, relax, sfs, clip_backscatter,
-                        pfield.transposed, force_positive, Int32(control_directional) | (Int32(control_magnitude) << 1),
-                        0))
+                        deltat, nu, sgm0, cs_beta, cs_tol, kernel_id(pfield.kernel), integration, relaxation, relax,
+                        sfs, clip_backscatter, pfield.transposed, force_positive,
+                        Int32(control_directional) | (Int32(control_magnitude) << 1),
+                        cs, cs ? V.itmax : 15, cs ? V.iterror : true))
     check(ccall((:vpm_field_step, lib[]), Cint, (Ptr{Cvoid}, Ref{StepParams}), handle[], sp))
+    if cs
+        check(ccall((:vpm_field_tsgm, lib[]), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Cint), handle[], t_sgm, 0))
+        V.t_sgm = t_sgm[]
+    end
     pfield.t += dt
     pfield.nt += 1
     return nothing

@@ -213,12 +213,34 @@ class ResidentField:
 
     SFS_SCHEMES = {False: 0, None: 0, "none": 0, True: 1, "constant": 1, "dynamic": 2}
 
+    def rbf_conjugategradient(self, itmax=15, tol=1e-3, iterror=True):
+        """rbf_conjugategradient(pfield, cs) with cs.zeta = zeta_direct (src/FLOWVPM_viscous.jl:309-478):
+        target vorticity in M[7:9]; returns (iterations, final relative residuals)"""
+        it = C.c_int32(0)
+        res = (C.c_double * 3)()
+        self.h.check(self.h.lib.vpm_field_rbf(self.h.ptr, self.pfield.kernel.id, int(itmax), float(tol), int(iterror),
+                                              C.byref(it), res))
+        return it.value, np.array(res[:])
+
+    @property
+    def t_sgm(self):
+        v = C.c_double(0.0)
+        self.h.check(self.h.lib.vpm_field_tsgm(self.h.ptr, C.byref(v), 0))
+        return v.value
+
+    @t_sgm.setter
+    def t_sgm(self, value):
+        v = C.c_double(float(value))
+        self.h.check(self.h.lib.vpm_field_tsgm(self.h.ptr, C.byref(v), 1))
+
     def nextstep(self, dt, *, integration="rungekutta3", f=0.0, g=0.2, Uinf=(0.0, 0.0, 0.0), sfs=False, Cs=1.0,
                  clip_backscatter=False, relaxation="pedrizzetti", relax=True, rlxf=0.3, alpha=0.667,
                  sfs_rlxf=0.005, minC=0.0, maxC=1.0, force_positive=False, control_directional=False,
-                 control_magnitude=False):
+                 control_magnitude=False, viscous=None):
         """sfs: False | "constant" (ConstantSFS, coefficient Cs) | "dynamic" (DynamicSFS with the
-        pseudo-3-level procedure: alpha, sfs_rlxf, minC, maxC, force_positive)"""
+        pseudo-3-level procedure: alpha, sfs_rlxf, minC, maxC, force_positive);
+        viscous: None (Inviscid) | dict(nu=, sgm0=, beta=1.5, itmax=15, tol=1e-3, iterror=True) for
+        CoreSpreading(nu, sgm0, zeta_direct) (src/FLOWVPM_viscous.jl:63-223)"""
         if minC < 0 or maxC < 0 or minC > maxC:
             raise ValueError(f"Invalid C bounds: minC={minC}, maxC={maxC}")  # subfilterscale.jl:456-462
         sp = _cabi.VpmStepParams()
@@ -233,6 +255,11 @@ class ResidentField:
         sp.relaxation = self.RELAXATIONS[relaxation]
         sp.relax, sp.sfs, sp.clip_backscatter = int(relax), self.SFS_SCHEMES[sfs], int(clip_backscatter)
         sp.transposed = int(self.pfield.transposed)
+        if viscous is not None:
+            sp.viscous = 1
+            sp.nu, sp.sgm0 = viscous["nu"], viscous["sgm0"]
+            sp.cs_beta, sp.cs_tol = viscous.get("beta", 1.5), viscous.get("tol", 1e-3)
+            sp.cs_itmax, sp.cs_iterror = int(viscous.get("itmax", 15)), int(viscous.get("iterror", True))
         self.h.check(self.h.lib.vpm_field_step(self.h.ptr, C.byref(sp)))
         self.pfield.t += dt
         self.pfield.nt += 1

@@ -160,7 +160,8 @@ int vpm_zeta_leafpairs(vpm_handle *h, double *particles, int64_t nfields, int64_
  *   DynamicSFS pseudo-3-level procedure:                        src/FLOWVPM_subfilterscale.jl:447-673
  * Covered: any (f, g) incl. cVPM (0,0) and rVPM (0,1/5); NoSFS / ConstantSFS / DynamicSFS
  * (pseudo3level, force_positive, clipping_backscatter, control_directional, control_magnitude);
- * Inviscid; constant Uinf.  The viscous schemes stay in the reference's Julia code (Hook 1). */
+ * Inviscid or CoreSpreading (with zeta_direct as its basis evaluation); constant Uinf.
+ * ParticleStrengthExchange stays in the reference's Julia code (it needs the FMM tree). */
 typedef struct vpm_step_params {
   double dt;
   double f, g;        /* ReformulatedVPM{f,g}: src/FLOWVPM_formulation.jl:23-37 */
@@ -171,6 +172,9 @@ typedef struct vpm_step_params {
   double sfs_rlxf;    /* DynamicSFS: Lagrangian-average relaxation (default 0.005) */
   double minC, maxC;  /* DynamicSFS: bounds of |C| (defaults 0, 1) */
   double deltat;      /* pfield.t / pfield.nt, used by control_magnitude; <= 0 when pfield.nt == 0 */
+  double nu, sgm0;    /* CoreSpreading(nu, sgm0, zeta_direct): src/FLOWVPM_viscous.jl:63-141 */
+  double cs_beta;     /* maximum core growth sigma/sgm0 before the RBF reset (default 1.5) */
+  double cs_tol;      /* RBF tolerance (default 1e-3) */
   int32_t kernel_id;
   int32_t integration;      /* 0 euler, 1 rungekutta3 */
   int32_t relaxation;       /* 0 none, 1 pedrizzetti, 2 correctedpedrizzetti */
@@ -181,7 +185,10 @@ typedef struct vpm_step_params {
   int32_t force_positive;   /* DynamicSFS: pseudo3level_positive */
   int32_t controls;         /* SFS controls: bit 0 control_directional, bit 1 control_magnitude
                                (src/FLOWVPM_subfilterscale.jl:300-397) */
-  int32_t reserved;
+  int32_t viscous;          /* 0 Inviscid, 1 CoreSpreading (requires the gaussianerf kernel,
+                               src/FLOWVPM.jl:265-267) */
+  int32_t cs_itmax;         /* maximum RBF iterations (default 15) */
+  int32_t cs_iterror;       /* fail when the RBF does not converge (default 1) */
 } vpm_step_params;
 int vpm_field_upload(vpm_handle *h, const double *particles, int64_t nfields, int64_t np);
 int vpm_field_download(vpm_handle *h, double *particles, int64_t nfields, int64_t np);
@@ -189,6 +196,14 @@ int vpm_field_download(vpm_handle *h, double *particles, int64_t nfields, int64_
 int vpm_field_uj(vpm_handle *h, int kernel_id, int flags);
 /* nextstep's integration call: one euler / rungekutta3 step on the resident matrix */
 int vpm_field_step(vpm_handle *h, const vpm_step_params *params);
+/* rbf_conjugategradient(pfield, cs) with cs.zeta = zeta_direct on the resident matrix
+ * (src/FLOWVPM_viscous.jl:309-478): target vorticity in M[7:9], new strengths in Gamma.
+ * iterations / residuals (3) may be NULL. */
+int vpm_field_rbf(vpm_handle *h, int kernel_id, int itmax, double tol, int iterror, int *iterations,
+                  double *residuals);
+/* CoreSpreading.t_sgm (time since the last core reset) kept with the resident field:
+ * set != 0 stores *t_sgm, otherwise it is returned; vpm_field_upload resets it to 0 */
+int vpm_field_tsgm(vpm_handle *h, double *t_sgm, int set);
 
 /* ---- device-pointer entry points (one process per GPU; the caller owns the
  * collective, e.g. an NCCL all-gather of the 8 x N source buffer) ---------- */

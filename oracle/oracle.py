@@ -59,6 +59,8 @@ def lib():
         L.vpm_oracle_zeta_leafpairs.restype = None
         L.vpm_oracle_field_step.argtypes = [p, i64, i64, p, p, i32]
         L.vpm_oracle_field_step.restype = i32
+        L.vpm_oracle_rbf_cg.argtypes = [p, i64, i64, i32, i32, dbl, i32, p, i32]
+        L.vpm_oracle_rbf_cg.restype = i32
         L.vpm_oracle_max_threads.restype = i32
         _lib = L
     return _lib
@@ -128,21 +130,37 @@ def direct_buffers(tgt, t0, t1, src, s0, s1, kernel, want_U=True, want_J=True, n
 def field_step(P, np_, kernel, dt, *, integration="rungekutta3", f=0.0, g=0.2, Uinf=(0.0, 0.0, 0.0), sfs=False,
                Cs=1.0, clip_backscatter=False, relaxation="pedrizzetti", relax=True, rlxf=0.3, transposed=True,
                alpha=0.667, sfs_rlxf=0.005, minC=0.0, maxC=1.0, force_positive=False, control_directional=False,
-               control_magnitude=False, deltat=0.0, nthreads=0):
+               control_magnitude=False, deltat=0.0, viscous=None, nthreads=0):
     """one euler / rungekutta3 step of ReformulatedVPM{f,g} on the 46 x N matrix, in place;
     sfs: False | "constant" | "dynamic" (pseudo-3-level procedure)"""
     _f(P)
-    dp = np.array([dt, f, g, Uinf[0], Uinf[1], Uinf[2], Cs, rlxf, alpha, sfs_rlxf, minC, maxC, deltat],
+    v = viscous or {}
+    dp = np.array([dt, f, g, Uinf[0], Uinf[1], Uinf[2], Cs, rlxf, alpha, sfs_rlxf, minC, maxC, deltat,
+                   v.get("nu", 0.0), v.get("sgm0", 1.0), v.get("beta", 1.5), v.get("tol", 1e-3), v.get("t_sgm", 0.0)],
                   dtype=np.float64)
     ip = np.array([_kid(kernel), {"euler": 0, "rungekutta3": 1}[integration],
                    {None: 0, "none": 0, "pedrizzetti": 1, "correctedpedrizzetti": 2}[relaxation], int(relax),
                    {False: 0, None: 0, "none": 0, True: 1, "constant": 1, "dynamic": 2}[sfs],
                    int(clip_backscatter), int(transposed), int(force_positive),
-                   int(control_directional) | (int(control_magnitude) << 1)], dtype=np.int32)
+                   int(control_directional) | (int(control_magnitude) << 1),
+                   int(viscous is not None), int(v.get("itmax", 15)), int(v.get("iterror", True))], dtype=np.int32)
     rc = lib().vpm_oracle_field_step(P.ctypes.data, P.shape[0], int(np_), dp.ctypes.data, ip.ctypes.data,
                                      int(nthreads or max_threads()))
     if rc != 0:
         raise RuntimeError(f"oracle field_step failed ({rc})")
+    if viscous is not None:
+        viscous["t_sgm"] = float(dp[17])   # CoreSpreading.t_sgm: time since the last core reset
+
+
+def rbf_conjugategradient(P, np_, kernel, itmax=15, tol=1e-3, iterror=True, nthreads=0):
+    """rbf_conjugategradient with cs.zeta = zeta_direct; returns (iterations, final relative residuals)"""
+    _f(P)
+    info = np.zeros(3)
+    rc = lib().vpm_oracle_rbf_cg(P.ctypes.data, P.shape[0], int(np_), _kid(kernel), int(itmax), float(tol),
+                                 int(iterror), info.ctypes.data, int(nthreads or max_threads()))
+    if rc < 0:
+        raise RuntimeError("Maximum number of iterations reached before convergence")
+    return rc, info
 
 
 def zeta_direct(P, np_, kernel, nthreads=0):

@@ -624,8 +624,136 @@ static void o_controls(double *P, int64_t nf, int64_t np, int controls, double f
     }
 }
 
-int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, const double *dp, const int *ip, int nthreads) {
+/*
+ * rbf_conjugategradient(pfield, cs): src/FLOWVPM_viscous.jl:309-478 with cs.zeta = zeta_direct.
+ * Target vorticity in M[7:9], solution built in M[1:3], residual in M[4:6], search direction in
+ * Gamma, basis evaluation in J[1:3]; updates over iterator(pfield) (non-static), zeta over all.
+ * Returns the number of CG iterations, or -4 when itmax is reached without convergence and
+ * iterror is set (the reference throws).  info[0:3] = final sqrt(rrs/rr0s).
+ */
+enum { R_VOL = 7 };
+int vpm_oracle_rbf_cg(double *P, int64_t nf, int64_t np, int kernel, int itmax, double tol, int iterror,
+                      double *info, int nthreads) {
   init_consts();
+  const double eps = 2.220446049250313e-16;
+  double rr0s[3] = {0, 0, 0}, rrs[3], prev_rrs[3], pAps[3], alphas[3], betas[3];
+  int flags[3];
+  for (int64_t i = 0; i < np; ++i) {
+    double *p = P + nf * i;
+    if (p[R_STATIC] != 0.0) continue;
+    for (int k = 0; k < 3; ++k) {
+      p[R_M + k] = p[R_M + 6 + k] * p[R_VOL];
+      p[R_G + k] = p[R_M + k];
+    }
+  }
+  vpm_oracle_zeta_direct(P, nf, np, kernel, nthreads);
+  for (int64_t i = 0; i < np; ++i) {
+    double *p = P + nf * i;
+    if (p[R_STATIC] != 0.0) continue;
+    for (int k = 0; k < 3; ++k) {
+      p[R_M + 3 + k] = p[R_M + 6 + k] - p[R_J + k];
+      p[R_G + k] = p[R_M + 3 + k];
+      rr0s[k] += p[R_M + 3 + k] * p[R_M + 3 + k];
+    }
+  }
+  for (int k = 0; k < 3; ++k) {
+    rrs[k] = rr0s[k];
+    flags[k] = sqrt(rr0s[k]) > tol || sqrt(rrs[k] / rr0s[k]) > tol;
+  }
+  int it_done = 0, failed = 0;
+  for (int it = 1; it <= itmax; ++it) {
+    if (!(flags[0] || flags[1] || flags[2])) break;
+    it_done = it;
+    vpm_oracle_zeta_direct(P, nf, np, kernel, nthreads);
+    for (int k = 0; k < 3; ++k) pAps[k] = 0;
+    for (int64_t i = 0; i < np; ++i) {
+      const double *p = P + nf * i;
+      if (p[R_STATIC] != 0.0) continue;
+      for (int k = 0; k < 3; ++k) pAps[k] += p[R_G + k] * p[R_J + k];
+    }
+    for (int k = 0; k < 3; ++k) {
+      alphas[k] = flags[k] ? rrs[k] / pAps[k] : 0.0; /* Julia: x * false == 0 even for NaN (strong zero) */
+      prev_rrs[k] = rrs[k];
+      rrs[k] = 0;
+    }
+    for (int64_t i = 0; i < np; ++i) {
+      double *p = P + nf * i;
+      if (p[R_STATIC] != 0.0) continue;
+      for (int k = 0; k < 3; ++k) {
+        p[R_M + k] += alphas[k] * p[R_G + k];
+        p[R_M + 3 + k] -= alphas[k] * p[R_J + k];
+        rrs[k] += p[R_M + 3 + k] * p[R_M + 3 + k];
+      }
+    }
+    for (int k = 0; k < 3; ++k) {
+      betas[k] = rrs[k] / prev_rrs[k];
+      if (fabs(prev_rrs[k]) <= 2 * eps) betas[k] = 1;
+    }
+    for (int64_t i = 0; i < np; ++i) {
+      double *p = P + nf * i;
+      if (p[R_STATIC] != 0.0) continue;
+      for (int k = 0; k < 3; ++k) p[R_G + k] = p[R_M + 3 + k] + betas[k] * p[R_G + k];
+    }
+    for (int k = 0; k < 3; ++k)
+      flags[k] = flags[k] && (fabs(rr0s[k]) <= 2 * eps ? 0 : sqrt(rrs[k] / rr0s[k]) > tol);
+    if (it == itmax && (flags[0] || flags[1] || flags[2])) failed = 1;
+  }
+  for (int64_t i = 0; i < np; ++i) {
+    double *p = P + nf * i;
+    if (p[R_STATIC] != 0.0) continue;
+    for (int k = 0; k < 3; ++k) p[R_G + k] = p[R_M + k];
+  }
+  if (info)
+    for (int k = 0; k < 3; ++k) info[k] = rr0s[k] > 0 ? sqrt(rrs[k] / rr0s[k]) : 0.0;
+  if (failed && iterror) return -4;
+  return it_done;
+}
+
+/* viscousdiffusion(pfield, CoreSpreading, dt; aux1, aux2): src/FLOWVPM_viscous.jl:152-223.
+ * vis[0..4] = nu, sgm0, beta, tol, t_sgm (in/out); returns < 0 on RBF failure. */
+static int o_corespreading(double *P, int64_t nf, int64_t np, int kernel, int integration, double dt, double aux1,
+                           double aux2, double *vis, int itmax, int iterror, int nthreads) {
+  const double nu = vis[0], sgm0 = vis[1], beta = vis[2], tol = vis[3];
+  int proceed = 0;
+  if (integration == 0) {
+    for (int64_t i = 0; i < np; ++i) {
+      double *p = P + nf * i;
+      if (p[R_STATIC] != 0.0) continue;
+      p[R_SIGMA] = sqrt(p[R_SIGMA] * p[R_SIGMA] + 2 * nu * dt);
+    }
+    proceed = 1;
+  } else {
+    for (int64_t i = 0; i < np; ++i) {
+      double *p = P + nf * i;
+      if (p[R_STATIC] != 0.0) continue;
+      p[R_M + 6] = aux1 * p[R_M + 6] + dt * 2 * nu;
+      p[R_SIGMA] = sqrt(p[R_SIGMA] * p[R_SIGMA] + aux2 * p[R_M + 6]);
+    }
+    if (fabs(aux2 - 8.0 / 15) <= 1e-7) proceed = 1;
+  }
+  if (proceed) {
+    vis[4] += dt;
+    double beta_cur = sqrt(2 * nu * vis[4] / (sgm0 * sgm0) + 1);
+    if (beta_cur >= beta) {
+      vpm_oracle_zeta_direct(P, nf, np, kernel, nthreads);
+      for (int64_t i = 0; i < np; ++i) {
+        double *p = P + nf * i;
+        if (p[R_STATIC] != 0.0) continue;
+        for (int k = 0; k < 3; ++k) p[R_M + 6 + k] = p[R_J + k];
+        p[R_SIGMA] = sgm0;
+      }
+      int rc = vpm_oracle_rbf_cg(P, nf, np, kernel, itmax, tol, iterror, NULL, nthreads);
+      if (rc < 0) return rc;
+      vis[4] = 0;
+    }
+  }
+  return 0;
+}
+
+int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, double *dp, const int *ip, int nthreads) {
+  init_consts();
+  const int viscous = ip[9], itmax = ip[10], iterror = ip[11];
+  double *vis = dp + 13; /* nu, sgm0, beta, tol, t_sgm (in/out) */
   const double dt = dp[0], f = dp[1], g = dp[2], Uinf[3] = {dp[3], dp[4], dp[5]}, Cs = dp[6], rlxf = dp[7];
   const double alpha = dp[8], sfs_rlxf = dp[9], minC = dp[10], maxC = dp[11], deltat = dp[12];
   const int controls = ip[8];
@@ -651,6 +779,7 @@ int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, const double *dp, c
       p[R_SIGMA] -= dt * (p[R_SIGMA] * MM4);
       if (relax && relaxation) o_relax(p, rlxf, relaxation);
     }
+    if (viscous) return o_corespreading(P, nf, np, kernel, 0, dt, 0.0, 0.0, vis, itmax, iterror, nthreads);
     return 0;
   }
   for (int64_t i = 0; i < np; ++i)
@@ -677,6 +806,10 @@ int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, const double *dp, c
       M[7] = a * M[7] - dt * (p[R_SIGMA] * MM4);
       for (int k = 0; k < 3; ++k) G[k] += b * M[3 + k];
       p[R_SIGMA] += b * M[7];
+    }
+    if (viscous) {
+      int rc = o_corespreading(P, nf, np, kernel, 1, dt, a, b, vis, itmax, iterror, nthreads);
+      if (rc < 0) return rc;
     }
   }
   if (relax && relaxation) {

@@ -259,3 +259,19 @@ def test_leapfrog_rings_vs_borisov_ode(vpm, f, g, sfs):
                           minC=0.0, maxC=1.0, nthreads=4)
     Z1e, Z2e, R1e, R2e = physics.leapfrog_errors(vpm, pf, dt * physics.LEAPFROG["nsteps"], Rcross)
     assert abs(Z1e) < 0.05 and abs(Z2e) < 0.03 and abs(R1e) < 0.03 and abs(R2e) < 0.03, (Z1e, Z2e, R1e, R2e)
+
+
+def test_oracle_rbf_recovers_strengths(vpm):
+    """rbf_conjugategradient restatement (src/FLOWVPM_viscous.jl:309-478): fed the vorticity the
+    field represents, the CG converges and returns the original strengths"""
+    pf = vpm.fields.ring_field(Nphi=60, nc=1, kernel=vpm.gaussianerf, R=1.0, Rcross=0.15, sigma=0.12)
+    n, P = pf.np, pf.particles
+    G0 = P[3:6, :n].copy()
+    oracle.zeta_direct(P, n, "gaussianerf")
+    W = P[15:18, :n].copy()
+    P[33:36, :n] = W
+    it, res = oracle.rbf_conjugategradient(P, n, "gaussianerf", itmax=30, tol=1e-6)
+    assert 2 <= it < 30 and res.max() < 1e-6
+    assert relerr(P[3:6, :n], G0) < 1e-4
+    oracle.zeta_direct(P, n, "gaussianerf")
+    assert relerr(P[15:18, :n], W) < 1e-6

@@ -85,6 +85,62 @@ def test_sfs_controls_match_oracle(vpm, handle, sfs, directional, magnitude):
         assert relerr(pf.particles[r, :pf.np], ref[r, :pf.np]) < 1e-9, name
 
 
+def _vorticity_ring(vpm):
+    # no static particles: their fixed strengths enter every basis evaluation of the CG, which
+    # makes the reference's RBF system inhomogeneous (it does not converge there either)
+    return vpm.fields.ring_field(Nphi=60, nc=1, kernel=vpm.gaussianerf, R=1.0, Rcross=0.15, sigma=0.12)
+
+
+def test_rbf_conjugategradient_matches_oracle(vpm, handle):
+    """rbf_conjugategradient (src/FLOWVPM_viscous.jl:309-478) with zeta_direct: the target is the
+    vorticity the field itself represents, so the CG must give the strengths back"""
+    pf = _vorticity_ring(vpm)
+    n = pf.np
+    G0 = pf.particles[3:6, :n].copy()
+    oracle.zeta_direct(pf.particles, n, "gaussianerf")
+    pf.particles[33:36, :n] = pf.particles[15:18, :n]      # M[7:9] <- target vorticity
+    ref = pf.particles.copy(order="F")
+    it_ref, res_ref = oracle.rbf_conjugategradient(ref, n, "gaussianerf", itmax=30, tol=1e-6)
+    rf = vpm.ResidentField(pf)
+    it, res = rf.rbf_conjugategradient(itmax=30, tol=1e-6)
+    rf.download()
+    assert it == it_ref and it >= 2
+    assert relerr(pf.particles[3:6, :n], ref[3:6, :n]) < 1e-9
+    assert relerr(pf.particles[27:33, :n], ref[27:33, :n]) < 1e-7          # solution and residual rows of M
+    assert relerr(pf.particles[3:6, :n], G0) < 1e-4                        # strengths recovered
+    with pytest.raises(vpm.VpmError):                                      # the reference throws when it does not converge
+        rf.upload()
+        rf.rbf_conjugategradient(itmax=1, tol=1e-12, iterror=True)
+
+
+@pytest.mark.parametrize("integration", ["euler", "rungekutta3"])
+def test_corespreading_step_matches_oracle(vpm, handle, integration):
+    """viscousdiffusion(pfield, CoreSpreading, dt) (src/FLOWVPM_viscous.jl:152-223): core growth every
+    stage, and an RBF reset when sigma/sgm0 reaches beta (forced every second step here)"""
+    pf = _vorticity_ring(vpm)
+    pf.particles[7, :pf.np] = 4 / 3 * np.pi * 0.05**3      # particle volumes feed the RBF initial guess
+    ref = pf.particles.copy(order="F")
+    vis = dict(nu=2e-3, sgm0=0.12, beta=1.02, itmax=20, tol=1e-4, iterror=True)
+    vis_ref = dict(vis, t_sgm=0.0)
+    kw = dict(integration=integration, f=0.0, g=0.2, sfs=False, relaxation="pedrizzetti", relax=True)
+    rf = vpm.ResidentField(pf)
+    resets = 0
+    for k in range(4):
+        rf.nextstep(5e-2, viscous=vis, **kw)
+        oracle.field_step(ref, pf.np, "gaussianerf", 5e-2, transposed=True, viscous=vis_ref, **kw)
+        assert abs(rf.t_sgm - vis_ref["t_sgm"]) < 1e-15
+        resets += vis_ref["t_sgm"] == 0.0
+    assert 1 <= resets < 4
+    rf.download()
+    for name, r in ROWS.items():
+        if name in ("SFS", "C"):
+            continue
+        assert relerr(pf.particles[r, :pf.np], ref[r, :pf.np]) < 1e-8, name
+    with pytest.raises(vpm.VpmError):   # CoreSpreading is only compatible with gaussianerf (src/FLOWVPM.jl:265-267)
+        pf.kernel = vpm.winckelmans
+        rf.nextstep(5e-2, viscous=vis, **kw)
+
+
 def test_formulations_and_classic_scheme(vpm, handle):
     for f, g, transposed in ((0.0, 0.0, True), (0.5, 0.0, True), (0.25, 0.25, False)):
         pf = make_field(vpm, vpm.gaussianerf)
