@@ -147,3 +147,28 @@ def test_resident_step_multi_gpu(vpm, sfs):
         assert_parity(pf.particles, ref, pf.np, tol=1e-9)
     finally:
         h.close()
+
+
+def test_corespreading_rbf_multi_gpu(vpm):
+    """CoreSpreading + RBF conjugate gradient with the mirror replicated on several devices
+    (zeta sweeps sharded + all-gathered, CG reductions read from device 0)"""
+    g = _ngpu()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    h = vpm.Handle(2)
+    try:
+        pf = vpm.fields.ring_field(Nphi=60, nc=1, kernel=vpm.gaussianerf, R=1.0, Rcross=0.15, sigma=0.12)
+        pf.particles[7, :pf.np] = 4 / 3 * np.pi * 0.05**3
+        ref = pf.particles.copy(order="F")
+        vis = dict(nu=2e-3, sgm0=0.12, beta=1.02, itmax=20, tol=1e-4, iterror=True)
+        vis_ref = dict(vis, t_sgm=0.0)
+        kw = dict(integration="rungekutta3", f=0.0, g=0.2, sfs=False, relaxation="pedrizzetti", relax=True)
+        rf = vpm.ResidentField(pf, handle=h)
+        for _ in range(2):
+            rf.nextstep(5e-2, viscous=vis, **kw)
+            oracle.field_step(ref, pf.np, "gaussianerf", 5e-2, transposed=True, viscous=vis_ref, **kw)
+        rf.download()
+        for rows in (slice(0, 7), slice(9, 12), slice(15, 24), slice(27, 36)):
+            assert relerr(pf.particles[rows, :pf.np], ref[rows, :pf.np]) < 1e-8, rows
+    finally:
+        h.close()
