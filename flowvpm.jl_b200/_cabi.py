@@ -21,12 +21,13 @@ SYMBOLS = [
     "vpm_field_upload", "vpm_field_download", "vpm_field_uj", "vpm_field_step", "vpm_field_rbf",
     "vpm_field_tsgm",
     "vpm_uj_device", "vpm_sfs_device",
-    "vpm_get_timing", "vpm_measure_dfma_peak", "vpm_test_math",
+    "vpm_get_timing", "vpm_measure_dfma_peak", "vpm_measure_ffma_peak", "vpm_test_math",
 ]
 
 VPM_OK = 0
 KERNEL_SINGULAR, KERNEL_GAUSSIAN, KERNEL_GAUSSIANERF, KERNEL_WINCKELMANS = 0, 1, 2, 3
 FLAG_RESET, FLAG_RESET_SFS, FLAG_SFS, FLAG_TRANSPOSED, FLAG_NO_FARFIELD_SHORTCUT = 1, 2, 4, 8, 16
+FLAG_FP32 = 32
 
 
 class VpmTiming(C.Structure):
@@ -98,6 +99,7 @@ def load():
     lib.vpm_sfs_device.argtypes = [p, p, p, p, i64, i64, i64, p, i32, i32, p]
     lib.vpm_get_timing.argtypes = [p, P(VpmTiming)]
     lib.vpm_measure_dfma_peak.argtypes = [p, P(dbl), P(dbl)]
+    lib.vpm_measure_ffma_peak.argtypes = [p, i32, P(dbl), P(dbl)]
     lib.vpm_test_math.argtypes = [p, i32, i32, p, p, p, i64]
     for name in SYMBOLS:
         fn = getattr(lib, name)

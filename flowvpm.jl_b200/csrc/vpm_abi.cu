@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "vpm_kernels.cuh"
+#include "vpm_kernels_f32.cuh"
 #include "vpm_leaf.cuh"
 #include "vpm_step.cuh"
 
@@ -131,7 +132,7 @@ bool valid_kernel(int k) { return k >= 0 && k <= 3; }
 // The grid is sized to ~16 waves of resident CTAs so that the tail of the last wave is a
 // few percent at most; when the target count alone cannot provide that, the sources are
 // split (>= 4 tiles per split) and the finish kernel adds the splits in order.
-enum PlanKind { PLAN_UJ = 0, PLAN_SFS = 1 };
+enum PlanKind { PLAN_UJ = 0, PLAN_SFS = 1, PLAN_UJ_F32 = 2 };
 Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind) {
   Plan p;
   const int64_t ntiles = std::max<int64_t>(1, (ns + kTile - 1) / kTile);
@@ -141,10 +142,11 @@ Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind) {
   const bool big = nblk2 * std::max<int64_t>(1, ntiles / 4) >= (int64_t)sm_count * 4 * 4;
   p.T = big ? 2 : 1;
   p.unroll = p.T == 2 ? 1 : 2;
-  if (const char *v = getenv(kind == PLAN_UJ ? "VPM_UJ_VARIANT" : "VPM_SFS_VARIANT")) {
+  if (const char *v = getenv(kind == PLAN_SFS ? "VPM_SFS_VARIANT" : "VPM_UJ_VARIANT")) {
     int x = atoi(v);  // tuning aid: "<T><unroll>", e.g. 12, 21, 22
     if (x / 10 >= 1 && x / 10 <= 2) { p.T = x / 10; p.unroll = x % 10; }
   }
+  if (kind == PLAN_UJ_F32) p.T = 2;  // the FP32 sweep packs the two targets of a thread into f32x2
   const int min_tiles = big ? 4 : 1;
   const int ctas_per_sm = p.T == 1 ? 6 : 4;
   const int64_t nblk = std::max<int64_t>(1, (nt + (int64_t)kThreads * p.T - 1) / ((int64_t)kThreads * p.T));
@@ -194,6 +196,15 @@ void launch_uj(int kernel, const Plan &p, const UjArgs &a, cudaStream_t st) {
     default: launch_uj_T<K_WINCK>(p, a, st); break;
   }
 }
+void launch_uj_f32(int kernel, const Plan &p, const UjArgsF &a, cudaStream_t st) {
+  const bool u1 = p.unroll == 1;
+  switch (kernel) {
+    case K_SING: u1 ? uj_pairs_kernel_f32<K_SING, 1><<<p.grid, kThreads, 0, st>>>(a) : uj_pairs_kernel_f32<K_SING, 2><<<p.grid, kThreads, 0, st>>>(a); break;
+    case K_GAUS: uj_pairs_kernel_f32<K_GAUS, 1><<<p.grid, kThreads, 0, st>>>(a); break;
+    case K_GERF: uj_pairs_kernel_f32<K_GERF, 1><<<p.grid, kThreads, 0, st>>>(a); break;
+    default: u1 ? uj_pairs_kernel_f32<K_WINCK, 1><<<p.grid, kThreads, 0, st>>>(a) : uj_pairs_kernel_f32<K_WINCK, 2><<<p.grid, kThreads, 0, st>>>(a); break;
+  }
+}
 template <int K>
 void launch_sfs_T(const Plan &p, const SfsArgs &a, cudaStream_t st, int mode) {
   if (mode == MODE_ZETA) {
@@ -221,6 +232,31 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
              int64_t nt, SrcView src, int64_t s0, int64_t ns, int flags, Plan &plan,
              bool time_pairs = false) {
   const int64_t ns_pad = round_up(std::max<int64_t>(ns, 1), kTile);
+  if (flags & VPM_FLAG_FP32) {
+    // optional FP32-arithmetic sweep (vpm_kernels_f32.cuh): FP32 records, FP64 partial sums in
+    // the same layout, so the finish kernels are shared with the FP64 sweep
+    TRY(ensure(h, d.rec, (size_t)ns_pad * kRecF * sizeof(float)));
+    plan = make_plan(nt, ns, d.sm_count, PLAN_UJ_F32);
+    TRY(ensure(h, d.partial, (size_t)plan.nsplit * kAcc * plan.pstride * sizeof(double)));
+    prep_uj_records_f32<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, s0, ns, ns_pad, kernel, (float *)d.rec.p);
+    h->launches++;
+    if (nt > 0 && ns > 0) {
+      UjArgsF a;
+      a.tpos = tpos; a.tld = tld; a.nt = nt;
+      a.rec = (const float *)d.rec.p; a.ns = ns;
+      a.tiles_per_split = plan.tiles_per_split;
+      a.partial = (double *)d.partial.p; a.pstride = plan.pstride;
+      a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
+      if (time_pairs) CK(h, cudaEventRecord(d.ev[6], st));
+      launch_uj_f32(kernel, plan, a, st);
+      if (time_pairs) CK(h, cudaEventRecord(d.ev[7], st));
+      h->launches++;
+    } else {
+      plan.nsplit = 0;
+    }
+    CK(h, cudaGetLastError());
+    return VPM_OK;
+  }
   TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
   plan = make_plan(nt, ns, d.sm_count, PLAN_UJ);
   TRY(ensure(h, d.partial, (size_t)plan.nsplit * kAcc * plan.pstride * sizeof(double)));
@@ -1992,6 +2028,39 @@ int vpm_measure_dfma_peak(vpm_handle *h, double *dfma_per_s, double *elapsed_ms)
   }
   const double n = (double)blocks * threads * (double)iters * 16.0 * 8.0;
   *dfma_per_s = n / (best * 1e-3);
+  if (elapsed_ms) *elapsed_ms = best;
+  return VPM_OK;
+}
+
+int vpm_measure_ffma_peak(vpm_handle *h, int mode, double *fma_per_s, double *elapsed_ms) {
+  if (!h || !fma_per_s || mode < 0 || mode > 3) return VPM_EINVAL;
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  TRY(ensure(h, d.ibuf, 4096));
+  const int threads = 256, blocks = d.sm_count * 8, iters = 4096;
+  auto run = [&](int it) {
+    float *o = (float *)d.ibuf.p;
+    switch (mode) {
+      case 0: ffma_peak_kernel<0><<<blocks, threads, 0, st>>>(o, it, 1.0f); break;
+      case 1: ffma_peak_kernel<1><<<blocks, threads, 0, st>>>(o, it, 1.0f); break;
+      case 2: ffma_peak_kernel<2><<<blocks, threads, 0, st>>>(o, it, 1.0f); break;
+      default: ffma_peak_kernel<3><<<blocks, threads, 0, st>>>(o, it, 1.0f); break;
+    }
+  };
+  run(64);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(h, cudaEventRecord(d.ev[6], st));
+    run(iters);
+    CK(h, cudaEventRecord(d.ev[7], st));
+    CK(h, cudaStreamSynchronize(st));
+    CK(h, cudaGetLastError());
+    best = std::min(best, ev_ms(d.ev[6], d.ev[7]));
+  }
+  // scalar FMAs per second: 8 chains x 16 x 2 lanes per thread and iteration in every mode
+  const double n = (double)blocks * threads * (double)iters * 16.0 * 8.0 * 2.0;
+  *fma_per_s = n / (best * 1e-3);
   if (elapsed_ms) *elapsed_ms = best;
   return VPM_OK;
 }

@@ -1,0 +1,138 @@
+// vpm_csr.cuh -- device-side regrouping of FastMultipole's direct_list (Hook 3).
+//
+// The near-field kernels of vpm_leaf.cuh want the (target leaf, source leaf) list as a CSR
+// by target leaf (list order kept inside a group), a table of work items (<= NT targets of
+// one leaf each) and, with several GPUs, cuts of that table with balanced pair counts.  For
+// the lists of SURVEY config C5 (2^24 particles, 2e7..9e7 list entries) doing this with host
+// loops costs more than the pair kernel itself, so every O(n_pairs) step runs here:
+//   count + validate + sortedness  ->  exclusive scan  ->  stable sort by target leaf (only
+//   if the list is not already grouped)  ->  CTA-width choice  ->  work items  ->  cuts.
+// All reductions are integer (atomicAdd on 64-bit counters), so the outcome is deterministic.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+namespace vpm {
+
+typedef unsigned long long u64;
+
+// slots of the small statistics block read back by the host
+enum { CS_BAD = 0,       // 1 + index of an out-of-range list entry (0 = none)
+       CS_UNSORTED = 1,  // != 0 when the list is not grouped by target leaf already
+       CS_W128 = 2, CS_W64 = 3, CS_W32 = 4,  // padded lane-work for the three CTA widths
+       CS_PAIRS = 5,     // sum over list entries of nt * ns (pair visits)
+       CS_NWI = 6,       // number of work items
+       CS_SLOTS = 8 };
+
+// one thread per list entry: counts per target leaf (cnt[l + 1]), source bodies per target
+// leaf (srcw[l]), validation and sortedness
+__global__ void csr_count_kernel(const int32_t *__restrict__ pt, const int32_t *__restrict__ ps, int64_t npairs,
+                                 int64_t ntl, int64_t nsl, const int64_t *__restrict__ sb,
+                                 const int64_t *__restrict__ se, u64 *__restrict__ cnt, u64 *__restrict__ srcw,
+                                 u64 *__restrict__ stats) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= npairs) return;
+  const int32_t t = pt[k], s = ps[k];
+  if (t < 0 || t >= ntl || s < 0 || s >= nsl) {
+    atomicMin(&stats[CS_BAD], (u64)k + 1);
+    return;
+  }
+  atomicAdd(&cnt[t + 1], 1ull);
+  atomicAdd(&srcw[t], (u64)(se[s] - sb[s]));
+  if (k > 0 && pt[k - 1] > t) stats[CS_UNSORTED] = 1;
+}
+
+// one thread per target leaf: padded lane-work of the three candidate CTA widths and the
+// number of pair visits
+__global__ void csr_cand_kernel(const int64_t *__restrict__ tb, const int64_t *__restrict__ te, int64_t ntl,
+                                const u64 *__restrict__ srcw, u64 *__restrict__ stats) {
+  const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  u64 w128 = 0, w64 = 0, w32 = 0, pairs = 0;
+  if (l < ntl) {
+    const u64 sz = (u64)(te[l] - tb[l]), w = srcw[l];
+    w128 = (sz + 127) / 128 * 128 * w;
+    w64 = (sz + 63) / 64 * 64 * w;
+    w32 = (sz + 31) / 32 * 32 * w;
+    pairs = sz * w;
+  }
+  // warp reduction, then one atomic per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    w128 += __shfl_down_sync(0xffffffffu, w128, o);
+    w64 += __shfl_down_sync(0xffffffffu, w64, o);
+    w32 += __shfl_down_sync(0xffffffffu, w32, o);
+    pairs += __shfl_down_sync(0xffffffffu, pairs, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (w128) atomicAdd(&stats[CS_W128], w128);
+    if (w64) atomicAdd(&stats[CS_W64], w64);
+    if (w32) atomicAdd(&stats[CS_W32], w32);
+    if (pairs) atomicAdd(&stats[CS_PAIRS], pairs);
+  }
+}
+
+// work items of leaf l: ceil(size / nt) when the leaf has list entries, else none
+__global__ void csr_wi_count_kernel(const int64_t *__restrict__ tb, const int64_t *__restrict__ te, int64_t ntl,
+                                    const u64 *__restrict__ ptr, int nt, u64 *__restrict__ wcnt) {
+  const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= ntl) return;
+  const int64_t sz = te[l] - tb[l];
+  wcnt[l] = ptr[l + 1] > ptr[l] ? (u64)((sz + nt - 1) / nt) : 0ull;
+}
+
+// fill the work items of leaf l at wofs[l].. and their pair counts (for the multi-GPU cuts)
+__global__ void csr_wi_fill_kernel(const int64_t *__restrict__ tb, const int64_t *__restrict__ te, int64_t ntl,
+                                   const u64 *__restrict__ wofs, const u64 *__restrict__ wcnt,
+                                   const u64 *__restrict__ srcw, int nt, int32_t *__restrict__ wi_leaf,
+                                   int32_t *__restrict__ wi_off, u64 *__restrict__ wi_w, u64 *__restrict__ stats) {
+  const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= ntl) return;
+  const u64 n = wcnt[l], o = wofs[l];
+  const int64_t sz = te[l] - tb[l];
+  for (u64 j = 0; j < n; ++j) {
+    const int64_t off = (int64_t)j * nt;
+    wi_leaf[o + j] = (int32_t)l;
+    wi_off[o + j] = (int32_t)off;
+    const int64_t c = sz - off < nt ? sz - off : nt;
+    wi_w[o + j] = (u64)c * srcw[l];
+  }
+  if (l == ntl - 1) stats[CS_NWI] = o + n;
+}
+
+// cut g (1 <= g < G): first work item whose inclusive pair-count prefix reaches total * g / G.
+// out[3g..3g+2] = (item, its leaf, its offset); out[0..2] describes item 0, out[3G..] the last item.
+__global__ void csr_cut_kernel(const u64 *__restrict__ wsum /* inclusive */, const int32_t *__restrict__ wi_leaf,
+                               const int32_t *__restrict__ wi_off, int64_t nwi, int G, int64_t *__restrict__ out) {
+  const int g = threadIdx.x;
+  if (g > G || nwi <= 0) return;
+  int64_t k;
+  if (g == 0) k = 0;
+  else if (g == G) k = nwi;
+  else {
+    // lower_bound over the exclusive prefix w[k] = wsum[k - 1]: first k with w[k] >= target
+    const double target = (double)wsum[nwi - 1] * g / G;
+    int64_t lo = 0, hi = nwi;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) / 2;
+      const double w = mid == 0 ? 0.0 : (double)wsum[mid - 1];
+      if (w < target) lo = mid + 1; else hi = mid;
+    }
+    k = lo;
+  }
+  out[3 * g] = k;
+  const int64_t kk = k < nwi ? k : nwi - 1;  // the entry after the end describes the last item
+  out[3 * g + 1] = wi_leaf[kk];
+  out[3 * g + 2] = wi_off[kk];
+}
+
+__global__ void csr_zero_kernel(u64 *p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0ull;
+}
+__global__ void csr_init_stats_kernel(u64 *stats) {
+  if (threadIdx.x < CS_SLOTS) stats[threadIdx.x] = threadIdx.x == CS_BAD ? ~0ull : 0ull;
+}
+
+}  // namespace vpm

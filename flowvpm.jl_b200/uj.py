@@ -30,7 +30,7 @@ def set_handle(handle):
     _default_handle = handle
 
 
-def _flags(pfield, sfs, reset, reset_sfs, no_shortcut=False):
+def _flags(pfield, sfs, reset, reset_sfs, no_shortcut=False, fp32=False):
     f = 0
     if reset:
         f |= _cabi.FLAG_RESET
@@ -42,6 +42,8 @@ def _flags(pfield, sfs, reset, reset_sfs, no_shortcut=False):
         f |= _cabi.FLAG_TRANSPOSED
     if no_shortcut:
         f |= _cabi.FLAG_NO_FARFIELD_SHORTCUT
+    if fp32:
+        f |= _cabi.FLAG_FP32
     return f
 
 
@@ -51,11 +53,12 @@ def _check_matrix(P):
 
 
 def UJ_direct(pfield, target=None, *, rbf=False, sfs=False, reset=True, reset_sfs=False,
-              handle=None, no_farfield_shortcut=False, **optargs):
+              handle=None, no_farfield_shortcut=False, fp32=False, **optargs):
     """UJ_direct(pfield; rbf, sfs, reset=true, reset_sfs=false)  -- src/FLOWVPM_UJ.jl:21-37
     UJ_direct(source, target)                                    -- src/FLOWVPM_UJ.jl:48-50
 
-    `rbf` is accepted and ignored, as in the reference."""
+    `rbf` is accepted and ignored, as in the reference.  `fp32=True` (library-only) runs
+    the U/J sweep in FP32 arithmetic (VPM_FLAG_FP32, 1e-5 bar); the default is FP64."""
     h = handle or get_handle()
     if target is not None:
         src = pfield
@@ -69,7 +72,7 @@ def UJ_direct(pfield, target=None, *, rbf=False, sfs=False, reset=True, reset_sf
         return None
     P = pfield.particles
     _check_matrix(P)
-    flags = _flags(pfield, sfs, reset, reset_sfs, no_farfield_shortcut)
+    flags = _flags(pfield, sfs, reset, reset_sfs, no_farfield_shortcut, fp32)
     if P.dtype == np.float64:
         fn = h.lib.vpm_uj_direct
     elif P.dtype == np.float32:

@@ -57,6 +57,10 @@ extern "C" {
 #define VPM_FLAG_NO_FARFIELD_SHORTCUT 16 /* gaussian/gaussianerf: evaluate exp/erf for
                                             every pair instead of g==1 beyond the cutoff */
 
+#define VPM_FLAG_FP32 32  /* optional FP32-arithmetic U/J sweep (north star: <= 1e-5): hi/lo split
+                             positions, packed f32x2 pair loop, FP64 sums across tiles; the SFS
+                             sweep stays FP64.  Without it every entry point computes in FP64. */
+
 typedef struct vpm_handle vpm_handle;
 
 /* ---- lifetime ---------------------------------------------------------- */
@@ -231,6 +235,10 @@ int vpm_get_timing(const vpm_handle *h, vpm_timing *out);
 /* FP64 FMA pipe peak of device 0, measured with a dependent-chain-free DFMA
  * loop: the roofline denominator. */
 int vpm_measure_dfma_peak(vpm_handle *h, double *dfma_per_s, double *elapsed_ms);
+/* FP32 FMA issue rate of device 0 (scalar FMAs/s), the roofline denominator of VPM_FLAG_FP32:
+ * mode 0 FFMA2 with loop-invariant operands, 1 FFMA2 reading three distinct registers,
+ * 2 / 3 the same with scalar FFMA. */
+int vpm_measure_ffma_peak(vpm_handle *h, int mode, double *fma_per_s, double *elapsed_ms);
 /* evaluate one device math routine on an array (accuracy tests):
  * op 0 rsqrt, 1 exp, 2 (g, dg) of kernel `arg` at s, 3 zeta of kernel `arg` */
 int vpm_test_math(vpm_handle *h, int op, int arg, const double *in, double *out, double *out2,
