@@ -18,6 +18,7 @@ SYMBOLS = [
     "vpm_pin_host", "vpm_unpin_host",
     "vpm_p2p_buffers", "vpm_p2p_leafpairs", "vpm_estr_leafpairs",
     "vpm_zeta_direct", "vpm_zeta_leafpairs",
+    "vpm_leaflists_build", "vpm_leaflists_get", "vpm_uj_nearfield",
     "vpm_field_upload", "vpm_field_download", "vpm_field_uj", "vpm_field_step", "vpm_field_rbf",
     "vpm_field_tsgm",
     "vpm_uj_device", "vpm_sfs_device",
@@ -89,6 +90,9 @@ def load():
     lib.vpm_estr_leafpairs.argtypes = [p, p, i64, i64, p, p, p, p, i64, p, p, i64, p, p, i64, i32, i32]
     lib.vpm_zeta_direct.argtypes = [p, p, i64, i64, i32]
     lib.vpm_zeta_leafpairs.argtypes = [p, p, i64, i64, p, p, p, i64, p, p, i64, i32]
+    lib.vpm_leaflists_build.argtypes = [p, p, i64, i64, i64, dbl, P(i64), P(i64)]
+    lib.vpm_leaflists_get.argtypes = [p, p, p, p, p, p]
+    lib.vpm_uj_nearfield.argtypes = [p, p, i64, i64, i32, i32]
     lib.vpm_field_upload.argtypes = [p, p, i64, i64]
     lib.vpm_field_download.argtypes = [p, p, i64, i64]
     lib.vpm_field_uj.argtypes = [p, i32, i32]

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libvpm_cuda.so")
 SOURCES = ["vpm_abi.cu"]
-HEADERS = ["vpm_kernels.cuh", "vpm_kernels_f32.cuh", "vpm_leaf.cuh", "vpm_math.cuh", "vpm_coeffs.cuh", "vpm_step.cuh",
+HEADERS = ["vpm_kernels.cuh", "vpm_kernels_f32.cuh", "vpm_leaf.cuh", "vpm_csr.cuh", "vpm_tree.cuh", "vpm_math.cuh", "vpm_coeffs.cuh", "vpm_step.cuh",
            os.path.join("..", "..", "include", "vpm_cuda.h")]
 
 

@@ -21,6 +21,8 @@
 #include "vpm_kernels.cuh"
 #include "vpm_kernels_f32.cuh"
 #include "vpm_leaf.cuh"
+#include "vpm_csr.cuh"
+#include "vpm_tree.cuh"
 #include "vpm_step.cuh"
 
 using namespace vpm;
@@ -44,8 +46,8 @@ struct Dev {
   int id = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[8] = {};
-  Buf in7, stat, res18, sfs3, rec, srec, partial, tbuf, sbuf, ibuf, jbuf, fld;
+  cudaEvent_t ev[10] = {};  // 0..5 phases of a call, 6..7 pair kernel, 8..9 cross-device ordering
+  Buf in7, stat, res18, sfs3, rec, srec, partial, tbuf, sbuf, ibuf, jbuf, fld, scr, scr2, cubtmp, tree, tlist;
 };
 
 struct Plan {
@@ -75,6 +77,8 @@ struct vpm_handle {
   int64_t fld_nf = 0, fld_np = -1;  // device mirror of the whole particle matrix (vpm_field_*)
   double fld_t_sgm = 0.0;           // CoreSpreading.t_sgm of the resident field
   int device_timing = 0;  // 1/2: ev[6..7] bracket the last _device U/J / SFS pair kernel
+  // device-built leaf lists (vpm_leaflists_build), resident on device 0
+  int64_t tree_np = -1, tree_nl = 0, tree_npairs = 0;
   // single-process multi-GPU (n_gpus > 1): NCCL communicators, one per device
   void *nccl_lib = nullptr;
   std::vector<void *> comms;
@@ -790,64 +794,8 @@ int uj_direct_multi(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
   return VPM_OK;
 }
 
-// ---- leaf-pair list (Hook 3) host side: CSR by target leaf -------------------
-struct HostCsr {
-  std::vector<int64_t> ptr;
-  std::vector<int32_t> src, wi_leaf, wi_off;
-  int nt = kThreads;  // threads per CTA (targets per work item): 32, 64 or 128
-};
-
-int build_csr(vpm_handle *h, const char *fn, const int64_t *tb, const int64_t *te, int64_t ntl,
-              int64_t n_tgt, const int64_t *sb, const int64_t *se, int64_t nsl, int64_t n_src,
-              const int32_t *pt, const int32_t *ps, int64_t npairs, HostCsr &c) {
-  for (int64_t l = 0; l < ntl; ++l)
-    if (tb[l] < 0 || te[l] < tb[l] || te[l] > n_tgt)
-      return fail(h, VPM_EINVAL, "%s: target leaf %lld range [%lld,%lld) outside 0..%lld", fn, (long long)l, (long long)tb[l], (long long)te[l], (long long)n_tgt);
-  for (int64_t l = 0; l < nsl; ++l)
-    if (sb[l] < 0 || se[l] < sb[l] || se[l] > n_src)
-      return fail(h, VPM_EINVAL, "%s: source leaf %lld range [%lld,%lld) outside 0..%lld", fn, (long long)l, (long long)sb[l], (long long)se[l], (long long)n_src);
-  c.ptr.assign((size_t)ntl + 1, 0);
-  bool sorted = true;  // a list already grouped by target leaf needs no scatter
-  for (int64_t k = 0; k < npairs; ++k) {
-    if (pt[k] < 0 || pt[k] >= ntl || ps[k] < 0 || ps[k] >= nsl)
-      return fail(h, VPM_EINVAL, "%s: pair %lld = (%d,%d) outside the leaf tables", fn, (long long)k, pt[k], ps[k]);
-    c.ptr[(size_t)pt[k] + 1]++;
-    sorted = sorted && (k == 0 || pt[k] >= pt[k - 1]);
-  }
-  for (int64_t l = 0; l < ntl; ++l) c.ptr[(size_t)l + 1] += c.ptr[(size_t)l];
-  if (sorted) {
-    c.src.assign(ps, ps + npairs);
-  } else {
-    c.src.resize((size_t)npairs);
-    std::vector<int64_t> cur(c.ptr.begin(), c.ptr.end() - 1);
-    for (int64_t k = 0; k < npairs; ++k) c.src[(size_t)cur[(size_t)pt[k]]++] = ps[k];  // stable
-  }
-  // CTA width: minimise the padded lane-work  sum_leaf ceil(size/NT)*NT * (its source bodies)
-  std::vector<int64_t> srcw((size_t)ntl, 0);
-  for (int64_t k = 0; k < npairs; ++k) srcw[(size_t)pt[k]] += se[ps[k]] - sb[ps[k]];
-  double best = -1.0;
-  for (int cand : {128, 64, 32}) {
-    double w = 0.0;
-    for (int64_t l = 0; l < ntl; ++l) {
-      const int64_t sz = te[l] - tb[l];
-      w += (double)((sz + cand - 1) / cand * cand) * (double)srcw[(size_t)l];
-    }
-    // wider CTAs amortise the tile traffic better: require a 10 % gain to go narrower
-    if (best < 0.0 || w < 0.9 * best) { best = w; c.nt = cand; }
-  }
-  c.wi_leaf.clear();
-  c.wi_off.clear();
-  for (int64_t l = 0; l < ntl; ++l) {
-    if (c.ptr[(size_t)l + 1] == c.ptr[(size_t)l]) continue;
-    for (int64_t off = 0; off < te[l] - tb[l]; off += c.nt) {
-      c.wi_leaf.push_back((int32_t)l);
-      c.wi_off.push_back((int32_t)off);
-    }
-  }
-  return VPM_OK;
-}
-
-// carve aligned sub-arrays out of one device allocation and fill them
+// ---- leaf-pair list (Hook 3): CSR by target leaf, built on device 0 (vpm_csr.cuh) ----
+// carve aligned sub-arrays out of one device allocation
 struct Carver {
   char *base;
   size_t off = 0;
@@ -861,38 +809,288 @@ struct Carver {
   }
 };
 
-int upload_csr(vpm_handle *h, Dev &d, cudaStream_t st, const HostCsr &c, const int64_t *tb,
-               const int64_t *te, int64_t ntl, const int64_t *sb, const int64_t *se, int64_t nsl,
-               const int64_t *tsort, int64_t n_tsort, const int64_t *ssort, int64_t n_ssort,
-               LeafCsr &out, const int64_t *&d_tsort, const int64_t *&d_ssort) {
-  size_t bytes = 16 * 12 + c.wi_leaf.size() * 8 + (size_t)ntl * 16 + c.ptr.size() * 8 +
-                 c.src.size() * 4 + (size_t)nsl * 16 + (size_t)(n_tsort + n_ssort) * 8;
-  TRY(ensure(h, d.ibuf, bytes));
+struct DevCsr {
+  LeafCsr csr;              // pointers into device 0's ibuf
+  size_t bcast_bytes = 0;   // leading bytes of ibuf every device needs (tables + sort indices)
+  int nt = kThreads;        // CTA width (targets per work item): 32, 64 or 128
+  int64_t nwi = 0;          // work items
+  int64_t pairs = 0;        // pair visits of the whole list
+  std::vector<int64_t> cut;                     // [G + 1] work-item cuts
+  std::vector<int64_t> first_leaf, first_off;   // [G + 1] item cut[g]     (first item of device g)
+  std::vector<int64_t> last_leaf, last_off;     // [G + 1] item cut[g] - 1 (last item of device g - 1)
+  const int64_t *d_tsort = nullptr, *d_ssort = nullptr;
+};
+
+// rebase the table pointers of device 0 onto another device's copy of ibuf
+LeafCsr rebase_csr(const LeafCsr &c, const void *from, const void *to) {
+  const ptrdiff_t shift = (const char *)to - (const char *)from;
+  auto rb = [shift](auto *p) { return (decltype(p))((const char *)p + shift); };
+  LeafCsr r;
+  r.wi_leaf = rb(c.wi_leaf); r.wi_off = rb(c.wi_off);
+  r.tleaf_begin = rb(c.tleaf_begin); r.tleaf_end = rb(c.tleaf_end);
+  r.csr_ptr = rb(c.csr_ptr); r.csr_src = rb(c.csr_src);
+  r.sleaf_begin = rb(c.sleaf_begin); r.sleaf_end = rb(c.sleaf_end);
+  return r;
+}
+
+int build_csr_device(vpm_handle *h, const char *fn, const int64_t *tb, const int64_t *te, int64_t ntl,
+                     int64_t n_tgt, const int64_t *sb, const int64_t *se, int64_t nsl, int64_t n_src,
+                     const int32_t *pt, const int32_t *ps, int64_t npairs, int G, const int64_t *tsort,
+                     int64_t n_tsort, const int64_t *ssort, int64_t n_ssort, DevCsr &out, bool dev_in = false) {
+  // O(leaves) checks stay on the host; everything O(list entries) runs on the device.
+  // dev_in: the tables are device arrays produced by vpm_leaflists_build (already valid).
+  int64_t max_wi = dev_in ? n_tgt / 32 + ntl : 0;
+  for (int64_t l = 0; l < ntl && !dev_in; ++l) {
+    if (tb[l] < 0 || te[l] < tb[l] || te[l] > n_tgt)
+      return fail(h, VPM_EINVAL, "%s: target leaf %lld range [%lld,%lld) outside 0..%lld", fn, (long long)l, (long long)tb[l], (long long)te[l], (long long)n_tgt);
+    max_wi += (te[l] - tb[l] + 31) / 32;
+  }
+  for (int64_t l = 0; l < nsl && !dev_in; ++l)
+    if (sb[l] < 0 || se[l] < sb[l] || se[l] > n_src)
+      return fail(h, VPM_EINVAL, "%s: source leaf %lld range [%lld,%lld) outside 0..%lld", fn, (long long)l, (long long)sb[l], (long long)se[l], (long long)n_src);
+  max_wi = std::max<int64_t>(max_wi, 1);
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  // replicated tables (ibuf) ...
+  const size_t ibytes = 16 * 12 + (size_t)max_wi * 8 + (size_t)ntl * 16 + ((size_t)ntl + 1) * 8 + (size_t)npairs * 4 +
+                        (size_t)nsl * 16 + (size_t)(n_tsort + n_ssort) * 8;
+  TRY(ensure(h, d.ibuf, ibytes));
   Carver cv(d.ibuf.p);
-  auto put = [&](auto *dst, const auto *srcp, size_t n) -> cudaError_t {
-    if (n == 0) return cudaSuccess;
-    return cudaMemcpyAsync((void *)dst, (const void *)srcp, n * sizeof(*srcp), cudaMemcpyHostToDevice, st);
-  };
-  int32_t *wl = cv.take<int32_t>(c.wi_leaf.size());
-  int32_t *wo = cv.take<int32_t>(c.wi_off.size());
+  int32_t *wl = cv.take<int32_t>((size_t)max_wi), *wo = cv.take<int32_t>((size_t)max_wi);
   int64_t *dtb = cv.take<int64_t>((size_t)ntl), *dte = cv.take<int64_t>((size_t)ntl);
-  int64_t *dptr = cv.take<int64_t>(c.ptr.size());
-  int32_t *dsrc = cv.take<int32_t>(c.src.size());
+  u64 *dptr = cv.take<u64>((size_t)ntl + 1);
+  int32_t *dsrc = cv.take<int32_t>((size_t)npairs);
   int64_t *dsb = cv.take<int64_t>((size_t)nsl), *dse = cv.take<int64_t>((size_t)nsl);
   int64_t *dts = cv.take<int64_t>((size_t)n_tsort), *dss = cv.take<int64_t>((size_t)n_ssort);
-  CK(h, put(wl, c.wi_leaf.data(), c.wi_leaf.size()));
-  CK(h, put(wo, c.wi_off.data(), c.wi_off.size()));
+  out.bcast_bytes = cv.off;
+  // ... and device-0 scratch
+  const size_t sbytes = 16 * 8 + (size_t)npairs * 4 + (size_t)ntl * 8 * 3 + (size_t)max_wi * 8 + CS_SLOTS * 8 + (size_t)(G + 1) * 40;
+  TRY(ensure(h, d.scr, sbytes));
+  Carver sc(d.scr.p);
+  int32_t *dpt = sc.take<int32_t>((size_t)npairs);
+  u64 *srcw = sc.take<u64>((size_t)ntl), *wcnt = sc.take<u64>((size_t)ntl), *wofs = sc.take<u64>((size_t)ntl);
+  u64 *wiw = sc.take<u64>((size_t)max_wi);
+  u64 *stats = sc.take<u64>(CS_SLOTS);
+  int64_t *dcut = sc.take<int64_t>((size_t)(G + 1) * 5);
+  // cub temporary storage: the largest of the four calls below
+  const int key_bits = std::max(1, (int)std::ceil(std::log2((double)std::max<int64_t>(ntl, 2))));
+  size_t tmp = 0, t1 = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, t1, dptr, dptr, (int64_t)ntl + 1, st); tmp = std::max(tmp, t1);
+  cub::DeviceScan::ExclusiveSum(nullptr, t1, wcnt, wofs, (int64_t)ntl, st); tmp = std::max(tmp, t1);
+  cub::DeviceScan::InclusiveSum(nullptr, t1, wiw, wiw, max_wi, st); tmp = std::max(tmp, t1);
+  cub::DeviceRadixSort::SortPairs(nullptr, t1, (const int32_t *)nullptr, (int32_t *)nullptr, (const int32_t *)nullptr,
+                                  (int32_t *)nullptr, npairs, 0, key_bits, st);
+  tmp = std::max(tmp, t1);
+  TRY(ensure(h, d.cubtmp, tmp + 16));
+
+  auto put = [&](auto *dst, const auto *srcp, size_t n) -> cudaError_t {
+    if (n == 0) return cudaSuccess;
+    return cudaMemcpyAsync((void *)dst, (const void *)srcp, n * sizeof(*srcp), cudaMemcpyDefault, st);
+  };
   CK(h, put(dtb, tb, (size_t)ntl));
   CK(h, put(dte, te, (size_t)ntl));
-  CK(h, put(dptr, c.ptr.data(), c.ptr.size()));
-  CK(h, put(dsrc, c.src.data(), c.src.size()));
   CK(h, put(dsb, sb, (size_t)nsl));
   CK(h, put(dse, se, (size_t)nsl));
+  CK(h, put(dpt, pt, (size_t)npairs));
+  CK(h, put(dsrc, ps, (size_t)npairs));  // already the CSR column array when the list is grouped
   if (n_tsort) CK(h, put(dts, tsort, (size_t)n_tsort));
   if (n_ssort) CK(h, put(dss, ssort, (size_t)n_ssort));
-  out.wi_leaf = wl; out.wi_off = wo; out.tleaf_begin = dtb; out.tleaf_end = dte;
-  out.csr_ptr = dptr; out.csr_src = dsrc; out.sleaf_begin = dsb; out.sleaf_end = dse;
-  d_tsort = dts; d_ssort = dss;
+  csr_init_stats_kernel<<<1, 32, 0, st>>>(stats);
+  csr_zero_kernel<<<blocks_for(ntl + 1, 256), 256, 0, st>>>(dptr, ntl + 1);
+  csr_zero_kernel<<<blocks_for(ntl, 256), 256, 0, st>>>(srcw, ntl);
+  csr_count_kernel<<<blocks_for(npairs, 256), 256, 0, st>>>(dpt, dsrc, npairs, ntl, nsl, dsb, dse, dptr, srcw, stats);
+  csr_cand_kernel<<<blocks_for(ntl, 256), 256, 0, st>>>(dtb, dte, ntl, srcw, stats);
+  t1 = d.cubtmp.cap;
+  CK(h, cub::DeviceScan::InclusiveSum(d.cubtmp.p, t1, dptr, dptr, (int64_t)ntl + 1, st));
+  h->launches += 6;
+  u64 hs[CS_SLOTS];
+  CK(h, cudaMemcpyAsync(hs, stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  CK(h, cudaGetLastError());
+  if (hs[CS_BAD] != ~0ull) {
+    const int64_t k = (int64_t)hs[CS_BAD] - 1;
+    return fail(h, VPM_EINVAL, "%s: pair %lld = (%d,%d) outside the leaf tables", fn, (long long)k,
+                dev_in ? -1 : pt[k], dev_in ? -1 : ps[k]);
+  }
+  // CTA width: minimise the padded lane-work  sum_leaf ceil(size/NT)*NT * (its source bodies);
+  // wider CTAs amortise the tile traffic better: require a 10 % gain to go narrower
+  double best = -1.0;
+  const int cands[3] = {128, 64, 32};
+  const u64 wsum[3] = {hs[CS_W128], hs[CS_W64], hs[CS_W32]};
+  for (int c = 0; c < 3; ++c)
+    if (best < 0.0 || (double)wsum[c] < 0.9 * best) { best = (double)wsum[c]; out.nt = cands[c]; }
+  out.pairs = (int64_t)hs[CS_PAIRS];
+  if (hs[CS_UNSORTED]) {
+    // stable radix sort by target leaf keeps the list order inside each group
+    TRY(ensure(h, d.scr2, (size_t)npairs * 8 + 32));
+    Carver s2(d.scr2.p);
+    int32_t *keys_out = s2.take<int32_t>((size_t)npairs), *vals_out = s2.take<int32_t>((size_t)npairs);
+    t1 = d.cubtmp.cap;
+    CK(h, cub::DeviceRadixSort::SortPairs(d.cubtmp.p, t1, (const int32_t *)dpt, keys_out, (const int32_t *)dsrc, vals_out,
+                                          npairs, 0, key_bits, st));
+    CK(h, cudaMemcpyAsync(dsrc, vals_out, (size_t)npairs * 4, cudaMemcpyDeviceToDevice, st));
+    h->launches += 1;
+  }
+  csr_wi_count_kernel<<<blocks_for(ntl, 256), 256, 0, st>>>(dtb, dte, ntl, dptr, out.nt, wcnt);
+  t1 = d.cubtmp.cap;
+  CK(h, cub::DeviceScan::ExclusiveSum(d.cubtmp.p, t1, wcnt, wofs, (int64_t)ntl, st));
+  csr_zero_kernel<<<blocks_for(max_wi, 256), 256, 0, st>>>(wiw, max_wi);
+  csr_wi_fill_kernel<<<blocks_for(ntl, 256), 256, 0, st>>>(dtb, dte, ntl, wofs, wcnt, srcw, out.nt, wl, wo, wiw, stats);
+  t1 = d.cubtmp.cap;
+  CK(h, cub::DeviceScan::InclusiveSum(d.cubtmp.p, t1, wiw, wiw, max_wi, st));
+  h->launches += 5;
+  CK(h, cudaMemcpyAsync(hs, stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  out.nwi = (int64_t)hs[CS_NWI];
+  out.cut.assign((size_t)G + 1, out.nwi);
+  out.cut[0] = 0;
+  for (auto *v : {&out.first_leaf, &out.first_off, &out.last_leaf, &out.last_off}) v->assign((size_t)G + 1, 0);
+  if (out.nwi > 0) {
+    if (G + 1 > 32) return fail(h, VPM_EINVAL, "%s: more than 31 devices", fn);
+    csr_cut_kernel<<<1, 32, 0, st>>>(wiw, wl, wo, out.nwi, G, dcut);
+    h->launches += 1;
+    std::vector<int64_t> hc((size_t)(G + 1) * 5);
+    CK(h, cudaMemcpyAsync(hc.data(), dcut, hc.size() * 8, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    for (int g = 0; g <= G; ++g) {
+      const int64_t *c = &hc[(size_t)5 * g];
+      out.cut[(size_t)g] = c[0];
+      out.first_leaf[(size_t)g] = c[1]; out.first_off[(size_t)g] = c[2];
+      out.last_leaf[(size_t)g] = c[3]; out.last_off[(size_t)g] = c[4];
+    }
+  }
+  CK(h, cudaGetLastError());
+  out.csr.wi_leaf = wl; out.csr.wi_off = wo; out.csr.tleaf_begin = dtb; out.csr.tleaf_end = dte;
+  out.csr.csr_ptr = (const int64_t *)dptr; out.csr.csr_src = dsrc; out.csr.sleaf_begin = dsb; out.csr.sleaf_end = dse;
+  out.d_tsort = dts; out.d_ssort = dss;
+  return VPM_OK;
+}
+
+
+// ---- device-built leaf lists (vpm_tree.cuh) --------------------------------------
+// Builds sort index, leaf ranges and the near-field list from the rows X (3) and sigma of a
+// device-resident column-major matrix view.  Results stay on device 0 (d.tree, d.tlist).
+struct TreeView {
+  int64_t *sidx, *lbegin, *lend;  // [np], [nl], [nl]
+  int32_t *pt, *ps;               // [npairs]
+};
+TreeView tree_view(vpm_handle *h) {
+  Dev &d = h->devs[0];
+  TreeView v;
+  Carver cv(d.tree.p);
+  const size_t n = (size_t)std::max<int64_t>(h->tree_np, 1);
+  v.sidx = cv.take<int64_t>(n); v.lbegin = cv.take<int64_t>(n); v.lend = cv.take<int64_t>(n);
+  Carver cl(d.tlist.p);
+  const size_t m = (size_t)std::max<int64_t>(h->tree_npairs, 1);
+  v.pt = cl.take<int32_t>(m); v.ps = cl.take<int32_t>(m);
+  return v;
+}
+
+int tree_build(vpm_handle *h, const double *d_P, int64_t ld, int osig, int64_t np, int64_t ncrit, double theta) {
+  const char *fn = "vpm_leaflists_build";
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  h->tree_np = -1;
+  const size_t n = (size_t)np;
+  TRY(ensure(h, d.tree, 3 * n * 8 + 64));
+  // scratch: bb[8] | keys | idx | skeys | rank (u64) | lkey | ctr[3] | rad | cnt | ofs
+  TRY(ensure(h, d.scr, 16 * 16 + 8 * 8 + n * 8 * 11));
+  Carver sc(d.scr.p);
+  long long *bb = sc.take<long long>(8);
+  int64_t *keys = sc.take<int64_t>(n), *idx0 = sc.take<int64_t>(n), *skeys = sc.take<int64_t>(n);
+  u64 *rank = sc.take<u64>(n);
+  int64_t *lkey = sc.take<int64_t>(n);
+  double *ctr = sc.take<double>(3 * n), *rad = sc.take<double>(n);
+  u64 *cnt = sc.take<u64>(n), *ofs = sc.take<u64>(n);
+  Carver tv(d.tree.p);
+  int64_t *sidx = tv.take<int64_t>(n), *lbegin = tv.take<int64_t>(n), *lend = tv.take<int64_t>(n);
+
+  tree_bbox_init_kernel<<<1, 32, 0, st>>>(bb);
+  tree_bbox_kernel<<<blocks_for(np, 256), 256, 0, st>>>(d_P, ld, np, bb);
+  h->launches += 2;
+  long long hb[8];
+  CK(h, cudaMemcpyAsync(hb, bb, sizeof hb, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  CK(h, cudaGetLastError());
+  // grid: cell size for a mean occupancy of ncrit/2; thin directions are padded to 1e-3 of
+  // the largest extent so that planar / linear fields do not explode the cell count
+  TreeGrid g;
+  double ext[3], emax = 0.0;
+  for (int a = 0; a < 3; ++a) {
+    g.lo[a] = ordered_to_dbl(hb[a]);
+    ext[a] = ordered_to_dbl(hb[3 + a]) - g.lo[a];
+    if (!std::isfinite(ext[a])) return fail(h, VPM_EINVAL, "%s: non-finite particle positions", fn);
+    emax = std::max(emax, ext[a]);
+  }
+  for (int a = 0; a < 3; ++a) ext[a] = std::max(std::max(ext[a], 1e-3 * emax), 1e-300);
+  const double vol = ext[0] * ext[1] * ext[2];
+  g.h = std::pow(vol * ((double)ncrit / 2.0) / (double)np, 1.0 / 3.0);
+  if (!(g.h > 0.0) || !std::isfinite(g.h)) g.h = 1.0;
+  double ncell_d = 1.0;
+  for (int a = 0; a < 3; ++a) {
+    const double c = std::max(1.0, std::ceil(ext[a] / g.h));
+    g.dims[a] = (int64_t)c;
+    ncell_d *= c;
+  }
+  if (ncell_d > 2.0e9) return fail(h, VPM_EINVAL, "%s: %.3g grid cells (field too anisotropic for ncrit = %lld)", fn, ncell_d, (long long)ncrit);
+  g.theta = theta;
+  const int64_t ncell = g.dims[0] * g.dims[1] * g.dims[2];
+  TRY(ensure(h, d.scr2, (size_t)ncell * 4 + 64));
+  int32_t *cell_to_leaf = (int32_t *)d.scr2.p;
+  const int key_bits = std::max(1, (int)std::ceil(std::log2((double)std::max<int64_t>(ncell, 2))));
+  size_t tmp = 0, t1 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t1, (const int64_t *)nullptr, (int64_t *)nullptr, (const int64_t *)nullptr,
+                                  (int64_t *)nullptr, np, 0, key_bits, st);
+  tmp = std::max(tmp, t1);
+  cub::DeviceScan::InclusiveSum(nullptr, t1, rank, rank, np, st); tmp = std::max(tmp, t1);
+  cub::DeviceScan::ExclusiveSum(nullptr, t1, cnt, ofs, np, st); tmp = std::max(tmp, t1);
+  TRY(ensure(h, d.cubtmp, tmp + 16));
+
+  tree_keys_kernel<<<blocks_for(np, 256), 256, 0, st>>>(d_P, ld, np, g, keys, idx0);
+  t1 = d.cubtmp.cap;
+  CK(h, cub::DeviceRadixSort::SortPairs(d.cubtmp.p, t1, (const int64_t *)keys, skeys, (const int64_t *)idx0, sidx, np, 0,
+                                        key_bits, st));
+  tree_heads_kernel<<<blocks_for(np, 256), 256, 0, st>>>(skeys, np, rank);
+  t1 = d.cubtmp.cap;
+  CK(h, cub::DeviceScan::InclusiveSum(d.cubtmp.p, t1, rank, rank, np, st));
+  tree_fill_i32_kernel<<<blocks_for(ncell, 256), 256, 0, st>>>(cell_to_leaf, ncell, -1);
+  tree_leaves_kernel<<<blocks_for(np, 256), 256, 0, st>>>(skeys, rank, np, lbegin, lend, lkey, cell_to_leaf);
+  h->launches += 6;
+  u64 nl64 = 0;
+  CK(h, cudaMemcpyAsync(&nl64, rank + (np - 1), 8, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  const int64_t nl = (int64_t)nl64;
+  tree_spheres_kernel<<<blocks_for(nl * 32, 256), 256, 0, st>>>(d_P, ld, osig, sidx, lbegin, lend, nl, ctr, rad, bb);
+  h->launches++;
+  CK(h, cudaMemcpyAsync(hb, bb, sizeof hb, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  CK(h, cudaGetLastError());
+  const double rmax = ordered_to_dbl(hb[6]);
+  if (!std::isfinite(rmax)) return fail(h, VPM_EINVAL, "%s: non-finite leaf radius (core sizes)", fn);
+  const double reach_d = std::ceil(2.0 * rmax / (theta * g.h)) + 1.0;
+  int reach = (int)std::min(reach_d, 1.0e6);
+  // no leaf is further than the grid itself
+  reach = (int)std::min<int64_t>(reach, std::max(std::max(g.dims[0], g.dims[1]), g.dims[2]));
+  tree_list_kernel<0><<<blocks_for(nl * 32, 256), 256, 0, st>>>(g, reach, lkey, cell_to_leaf, ctr, rad, nl, cnt, nullptr,
+                                                            nullptr, nullptr);
+  t1 = d.cubtmp.cap;
+  CK(h, cub::DeviceScan::ExclusiveSum(d.cubtmp.p, t1, cnt, ofs, nl, st));
+  h->launches += 2;
+  u64 last[2] = {0, 0};
+  CK(h, cudaMemcpyAsync(&last[0], cnt + (nl - 1), 8, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaMemcpyAsync(&last[1], ofs + (nl - 1), 8, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  const int64_t npairs = (int64_t)(last[0] + last[1]);
+  TRY(ensure(h, d.tlist, (size_t)std::max<int64_t>(npairs, 1) * 8 + 64));
+  Carver cl(d.tlist.p);
+  int32_t *pt = cl.take<int32_t>((size_t)std::max<int64_t>(npairs, 1)), *ps = cl.take<int32_t>((size_t)std::max<int64_t>(npairs, 1));
+  tree_list_kernel<1><<<blocks_for(nl * 32, 256), 256, 0, st>>>(g, reach, lkey, cell_to_leaf, ctr, rad, nl, cnt, ofs, pt, ps);
+  h->launches++;
+  CK(h, cudaStreamSynchronize(st));
+  CK(h, cudaGetLastError());
+  h->tree_np = np; h->tree_nl = nl; h->tree_npairs = npairs;
   return VPM_OK;
 }
 
@@ -931,12 +1129,6 @@ void launch_sfs_leaf(int kernel, int nt, unsigned nwi, const LeafSfsArgs &a, cud
   else launch_sfs_leaf_M<MODE_SFS>(kernel, nt, nwi, a, st);
 }
 
-int64_t count_pairs(const int64_t *tb, const int64_t *te, const int64_t *sb, const int64_t *se,
-                    const int32_t *pt, const int32_t *ps, int64_t npairs) {
-  int64_t n = 0;
-  for (int64_t k = 0; k < npairs; ++k) n += (te[pt[k]] - tb[pt[k]]) * (se[ps[k]] - sb[ps[k]]);
-  return n;
-}
 
 
 // ---- device-resident field: UJ_direct on the mirror of the whole matrix ----
@@ -1239,7 +1431,7 @@ int vpm_destroy(vpm_handle *h) {
     cudaSetDevice(d.id);
     cudaStreamSynchronize(d.stream);
     for (Buf *b : {&d.in7, &d.stat, &d.res18, &d.sfs3, &d.rec, &d.srec, &d.partial, &d.tbuf, &d.sbuf,
-                   &d.ibuf, &d.jbuf, &d.fld})
+                   &d.ibuf, &d.jbuf, &d.fld, &d.scr, &d.scr2, &d.cubtmp, &d.tree, &d.tlist})
       if (b->p) cudaFree(b->p);
     for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
     if (d.stream) cudaStreamDestroy(d.stream);
@@ -1569,36 +1761,15 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
     return fail(h, VPM_EINVAL, "%s: row offsets outside the %lld-row target buffer", fn, (long long)ld);
   if (npairs == 0 || n_tgt == 0 || n_src == 0 || (!want_U && !want_J)) return VPM_OK;
   if (!tgt || !src || !tb || !te || !sb || !se || !pt || !ps) return fail(h, VPM_EINVAL, "%s: NULL argument", fn);
-  HostCsr c;
-  TRY(build_csr(h, fn, tb, te, ntl, n_tgt, sb, se, nsl, n_src, pt, ps, npairs, c));
-  if (c.wi_leaf.empty()) return VPM_OK;
   h->launches = 0;
-  const int64_t nwi = (int64_t)c.wi_leaf.size();
   // Multi-GPU: target leaves are sharded into G contiguous runs of work items
-  // with balanced  sum nt*ns ; sources are replicated by the host upload.  Needs the leaves
-  // in increasing, non-overlapping body order (tree-sorted buffers) so that a device's
-  // targets are one contiguous column range; otherwise device 0 does everything.
+  // with balanced  sum nt*ns ; sources are replicated.  Needs the leaves in increasing,
+  // non-overlapping body order (tree-sorted buffers) so that a device's targets are one
+  // contiguous column range; otherwise device 0 does everything.
   int G = (int)h->devs.size();
   for (int64_t l = 0; l + 1 < ntl && G > 1; ++l)
     if (tb[l + 1] < te[l]) G = 1;
-  std::vector<int64_t> cut(G + 1, nwi);
-  cut[0] = 0;
-  if (G > 1) {
-    std::vector<double> w((size_t)nwi + 1, 0.0);
-    std::vector<int64_t> srcw((size_t)ntl, 0);
-    for (int64_t k = 0; k < npairs; ++k) srcw[(size_t)pt[k]] += se[ps[k]] - sb[ps[k]];
-    for (int64_t k = 0; k < nwi; ++k) {
-      const int l = c.wi_leaf[(size_t)k];
-      const int64_t cnt = std::min<int64_t>(c.nt, te[l] - tb[l] - c.wi_off[(size_t)k]);
-      w[(size_t)k + 1] = w[(size_t)k] + (double)cnt * (double)srcw[(size_t)l];
-    }
-    for (int g = 1; g < G; ++g)
-      cut[g] = std::lower_bound(w.begin(), w.end(), w[(size_t)nwi] * g / G) - w.begin();
-  }
   const int64_t ns_pad = round_up(n_src, kTile);
-  // replicated inputs (source buffer, CSR tables): device 0 gets them from the host, the
-  // other devices over NVLink
-  std::vector<LeafCsr> csr(G);
   for (int g = 0; g < G; ++g) {
     Dev &d = h->devs[g];
     CK(h, cudaSetDevice(d.id));
@@ -1606,41 +1777,36 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
     TRY(ensure(h, d.sbuf, (size_t)n_src * 8 * sizeof(double)));
     TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
   }
-  size_t csr_bytes = 0;
-  {
-    Dev &d0 = h->devs[0];
-    CK(h, cudaSetDevice(d0.id));
-    CK(h, cudaEventRecord(d0.ev[0], d0.stream));
-    CK(h, cudaMemcpyAsync(d0.sbuf.p, src, (size_t)n_src * 8 * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
-    const int64_t *dts, *dss;
-    TRY(upload_csr(h, d0, d0.stream, c, tb, te, ntl, sb, se, nsl, nullptr, 0, nullptr, 0, csr[0], dts, dss));
-    csr_bytes = (size_t)((const char *)csr[0].sleaf_end + (size_t)nsl * sizeof(int64_t) - (const char *)d0.ibuf.p);
-  }
+  // replicated inputs (source buffer, CSR tables): device 0 gets them from the host, the
+  // other devices over NVLink.  The list is regrouped on device 0 (vpm_csr.cuh).
+  Dev &d0 = h->devs[0];
+  CK(h, cudaSetDevice(d0.id));
+  CK(h, cudaEventRecord(d0.ev[0], d0.stream));
+  CK(h, cudaMemcpyAsync(d0.sbuf.p, src, (size_t)n_src * 8 * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
+  DevCsr c;
+  TRY(build_csr_device(h, fn, tb, te, ntl, n_tgt, sb, se, nsl, n_src, pt, ps, npairs, G, nullptr, 0, nullptr, 0, c));
+  if (c.nwi == 0) return VPM_OK;
+  std::vector<LeafCsr> csr(G);
+  csr[0] = c.csr;
   for (int g = 1; g < G; ++g) {
-    // same carve-out on every device: rebase device 0's table pointers
     Dev &d = h->devs[g];
     CK(h, cudaSetDevice(d.id));
     TRY(ensure(h, d.ibuf, h->devs[0].ibuf.cap));
-    const ptrdiff_t shift = (const char *)d.ibuf.p - (const char *)h->devs[0].ibuf.p;
-    auto rb = [shift](auto *p) { return (decltype(p))((const char *)p + shift); };
-    csr[g].wi_leaf = rb(csr[0].wi_leaf); csr[g].wi_off = rb(csr[0].wi_off);
-    csr[g].tleaf_begin = rb(csr[0].tleaf_begin); csr[g].tleaf_end = rb(csr[0].tleaf_end);
-    csr[g].csr_ptr = rb(csr[0].csr_ptr); csr[g].csr_src = rb(csr[0].csr_src);
-    csr[g].sleaf_begin = rb(csr[0].sleaf_begin); csr[g].sleaf_end = rb(csr[0].sleaf_end);
+    csr[g] = rebase_csr(c.csr, h->devs[0].ibuf.p, d.ibuf.p);
   }
   TRY(bcast_from_dev0(h, &Dev::sbuf, (size_t)n_src * 8 * sizeof(double)));
-  TRY(bcast_from_dev0(h, &Dev::ibuf, csr_bytes));
+  TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
   std::vector<std::pair<int64_t, int64_t>> cols(G, {0, 0});
   for (int g = 0; g < G; ++g) {
     Dev &d = h->devs[g];
     cudaStream_t st = d.stream;
-    const int64_t k0 = cut[g], k1 = cut[g + 1];
+    const int64_t k0 = c.cut[g], k1 = c.cut[g + 1];
     if (k1 <= k0) continue;
     CK(h, cudaSetDevice(d.id));
     // this device's target columns: first target of its first item .. last target of its last
-    const int lf = c.wi_leaf[(size_t)k0], ll = c.wi_leaf[(size_t)k1 - 1];
-    const int64_t col0 = G == 1 ? 0 : tb[lf] + c.wi_off[(size_t)k0];
-    const int64_t col1 = G == 1 ? n_tgt : std::min<int64_t>(te[ll], tb[ll] + c.wi_off[(size_t)k1 - 1] + c.nt);
+    const int64_t lf = c.first_leaf[g], ll = c.last_leaf[g + 1];
+    const int64_t col0 = G == 1 ? 0 : tb[lf] + c.first_off[g];
+    const int64_t col1 = G == 1 ? n_tgt : std::min<int64_t>(te[ll], tb[ll] + c.last_off[g + 1] + c.nt);
     CK(h, cudaMemcpyAsync((double *)d.tbuf.p + col0 * ld, tgt + col0 * ld, (size_t)(col1 - col0) * ld * sizeof(double),
                           cudaMemcpyHostToDevice, st));
     LeafUjArgs a;
@@ -1679,7 +1845,7 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
     CK(h, cudaSetDevice(h->devs[g].id));
     CK(h, cudaStreamSynchronize(h->devs[g].stream));
   }
-  h->timing.uj_pairs = count_pairs(tb, te, sb, se, pt, ps, npairs);
+  h->timing.uj_pairs = c.pairs;
   h->timing.sfs_pairs = 0;
   h1_fill_timing(h, h->devs[0]);
   h->np_resident = -1;
@@ -1697,9 +1863,6 @@ static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, i
   for (int64_t i = 0; i < np; ++i)
     if (tsort[i] < 0 || tsort[i] >= np || ssort[i] < 0 || ssort[i] >= np)
       return fail(h, VPM_EINVAL, "%s: sort index %lld out of range", fn, (long long)i);
-  HostCsr c;
-  TRY(build_csr(h, fn, tb, te, ntl, np, sb, se, nsl, np, pt, ps, npairs, c));
-  if (c.wi_leaf.empty()) return VPM_OK;
   Dev &d = h->devs[0];
   cudaStream_t st = d.stream;
   h->launches = 0;
@@ -1718,8 +1881,11 @@ static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, i
   CK(h, cudaMemcpy2DAsync(d.sfs3.p, 3 * sizeof(double), P + out_row, nf * sizeof(double), 3 * sizeof(double),
                           (size_t)np, cudaMemcpyHostToDevice, st));
   LeafSfsArgs a;
-  const int64_t *dts, *dss;
-  TRY(upload_csr(h, d, st, c, tb, te, ntl, sb, se, nsl, tsort, np, ssort, np, a.csr, dts, dss));
+  DevCsr c;
+  TRY(build_csr_device(h, fn, tb, te, ntl, np, sb, se, nsl, np, pt, ps, npairs, 1, tsort, np, ssort, np, c));
+  if (c.nwi == 0) return VPM_OK;
+  a.csr = c.csr;
+  const int64_t *dts = c.d_tsort, *dss = c.d_ssort;
   CK(h, cudaEventRecord(d.ev[1], st));
   CK(h, cudaEventRecord(d.ev[2], st));
   CK(h, cudaEventRecord(d.ev[3], st));
@@ -1733,8 +1899,7 @@ static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, i
   a.tindex = dts; a.rec = (const double *)d.srec.p; a.out = (double *)d.sfs3.p; a.old = 3; a.orow = 0;
   a.transposed = transposed;
   a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
-  const unsigned nwi = (unsigned)c.wi_leaf.size();
-  launch_sfs_leaf(kernel, c.nt, nwi, a, st, mode);
+  launch_sfs_leaf(kernel, c.nt, (unsigned)c.nwi, a, st, mode);
   h->launches++;
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(d.ev[4], st));
@@ -1743,7 +1908,7 @@ static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, i
   CK(h, cudaEventRecord(d.ev[5], st));
   CK(h, cudaStreamSynchronize(st));
   h->timing.uj_pairs = 0;
-  h->timing.sfs_pairs = count_pairs(tb, te, sb, se, pt, ps, npairs);
+  h->timing.sfs_pairs = c.pairs;
   h1_fill_timing(h, d);
   h->np_resident = -1;
   return VPM_OK;
@@ -1805,6 +1970,162 @@ int vpm_zeta_direct(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
   h->timing.uj_pairs = 0;
   h->timing.sfs_pairs = np * np;
   h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+int vpm_leaflists_build(vpm_handle *h, const double *P, int64_t nf, int64_t np, int64_t ncrit, double theta,
+                        int64_t *n_leaves, int64_t *n_pairs) {
+  TRY(check_field(h, "vpm_leaflists_build", P, nf, np, 0));
+  if (ncrit < 1 || !(theta > 0.0)) return fail(h, VPM_EINVAL, "vpm_leaflists_build: ncrit >= 1 and theta > 0 required");
+  h->launches = 0;
+  h->tree_np = -1;
+  if (n_leaves) *n_leaves = 0;
+  if (n_pairs) *n_pairs = 0;
+  if (np == 0) { h->tree_np = 0; h->tree_nl = 0; h->tree_npairs = 0; return VPM_OK; }
+  Dev &d = h->devs[0];
+  bool has_static = false;
+  CK(h, cudaSetDevice(d.id));
+  CK(h, cudaEventRecord(d.ev[0], d.stream));
+  TRY(h1_upload(h, d, P, nf, np, false, false, has_static));
+  CK(h, cudaEventRecord(d.ev[1], d.stream));
+  TRY(tree_build(h, (const double *)d.in7.p, 7, 6, np, ncrit, theta));
+  for (int e = 2; e <= 5; ++e) CK(h, cudaEventRecord(d.ev[e], d.stream));
+  CK(h, cudaStreamSynchronize(d.stream));
+  h->timing.uj_pairs = 0; h->timing.sfs_pairs = 0;
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  if (n_leaves) *n_leaves = h->tree_nl;
+  if (n_pairs) *n_pairs = h->tree_npairs;
+  return VPM_OK;
+}
+
+int vpm_leaflists_get(vpm_handle *h, int64_t *sort_index, int64_t *leaf_begin, int64_t *leaf_end, int32_t *pair_tgt,
+                      int32_t *pair_src) {
+  if (!h) return VPM_EINVAL;
+  if (h->tree_np < 0) return fail(h, VPM_ESTATE, "vpm_leaflists_get: no leaf lists (call vpm_leaflists_build first)");
+  if (h->tree_np == 0) return VPM_OK;
+  Dev &d = h->devs[0];
+  CK(h, cudaSetDevice(d.id));
+  const TreeView v = tree_view(h);
+  if (sort_index) CK(h, cudaMemcpyAsync(sort_index, v.sidx, (size_t)h->tree_np * 8, cudaMemcpyDeviceToHost, d.stream));
+  if (leaf_begin) CK(h, cudaMemcpyAsync(leaf_begin, v.lbegin, (size_t)h->tree_nl * 8, cudaMemcpyDeviceToHost, d.stream));
+  if (leaf_end) CK(h, cudaMemcpyAsync(leaf_end, v.lend, (size_t)h->tree_nl * 8, cudaMemcpyDeviceToHost, d.stream));
+  if (pair_tgt && h->tree_npairs) CK(h, cudaMemcpyAsync(pair_tgt, v.pt, (size_t)h->tree_npairs * 4, cudaMemcpyDeviceToHost, d.stream));
+  if (pair_src && h->tree_npairs) CK(h, cudaMemcpyAsync(pair_src, v.ps, (size_t)h->tree_npairs * 4, cudaMemcpyDeviceToHost, d.stream));
+  CK(h, cudaStreamSynchronize(d.stream));
+  return VPM_OK;
+}
+
+int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel, int flags) {
+  const char *fn = "vpm_uj_nearfield";
+  TRY(check_field(h, fn, P, nf, np, kernel));
+  if (h->tree_np != np) return fail(h, VPM_ESTATE, "%s: leaf lists were built for %lld particles, field has %lld (call vpm_leaflists_build)", fn, (long long)h->tree_np, (long long)np);
+  if (np == 0) return VPM_OK;
+  h->launches = 0;
+  const int G = (int)h->devs.size();
+  Dev &d0 = h->devs[0];
+  CK(h, cudaSetDevice(d0.id));
+  CK(h, cudaEventRecord(d0.ev[0], d0.stream));
+  const bool reset = flags & VPM_FLAG_RESET;
+  bool has_static = false;
+  TRY(h1_upload(h, d0, P, nf, np, !reset, false, has_static));
+  const bool prior = !reset || has_static;
+  if (!prior) CK(h, cudaMemsetAsync(d0.res18.p, 0, (size_t)np * RES_ROWS * sizeof(double), d0.stream));
+  const TreeView tv = tree_view(h);
+  DevCsr c;
+  TRY(build_csr_device(h, fn, tv.lbegin, tv.lend, h->tree_nl, np, tv.lbegin, tv.lend, h->tree_nl, np, tv.pt, tv.ps,
+                       h->tree_npairs, G, nullptr, 0, nullptr, 0, c, true));
+  CK(h, cudaEventRecord(d0.ev[1], d0.stream));
+  const int64_t ns_pad = round_up(np, kTile);
+  std::vector<LeafCsr> csr(G);
+  csr[0] = c.csr;
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    CK(h, cudaSetDevice(d.id));
+    TRY(ensure(h, d.tbuf, (size_t)np * 16 * sizeof(double)));
+    TRY(ensure(h, d.sbuf, (size_t)np * 8 * sizeof(double)));
+    TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
+    if (g > 0) {
+      TRY(ensure(h, d.in7, (size_t)np * 7 * sizeof(double)));
+      TRY(ensure(h, d.tree, h->devs[0].tree.cap));
+      TRY(ensure(h, d.ibuf, h->devs[0].ibuf.cap));
+      csr[g] = rebase_csr(c.csr, h->devs[0].ibuf.p, d.ibuf.p);
+    }
+  }
+  // replicate state, sort index and list tables over NVLink; every device gathers its own
+  // tree-sorted buffers
+  TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np * 7 * sizeof(double)));
+  TRY(bcast_from_dev0(h, &Dev::tree, (size_t)np * 8));
+  TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
+  std::vector<std::pair<int64_t, int64_t>> cols(G, {0, 0});
+  // leaf tables on the host are not available (device-built): the column range of a device is
+  // [begin of its first item, end of its last item), read from the cut records
+  std::vector<int64_t> hb((size_t)h->tree_nl), he((size_t)h->tree_nl);
+  if (G > 1) {
+    CK(h, cudaSetDevice(d0.id));
+    CK(h, cudaMemcpyAsync(hb.data(), tv.lbegin, hb.size() * 8, cudaMemcpyDeviceToHost, d0.stream));
+    CK(h, cudaMemcpyAsync(he.data(), tv.lend, he.size() * 8, cudaMemcpyDeviceToHost, d0.stream));
+    CK(h, cudaStreamSynchronize(d0.stream));
+  }
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    cudaStream_t st = d.stream;
+    const int64_t k0 = c.cut[g], k1 = c.cut[g + 1];
+    if (k1 <= k0) continue;
+    CK(h, cudaSetDevice(d.id));
+    const int64_t lf = c.first_leaf[g], ll = c.last_leaf[g + 1];
+    const int64_t col0 = G == 1 ? 0 : hb[(size_t)lf] + c.first_off[g];
+    const int64_t col1 = G == 1 ? np : std::min<int64_t>(he[(size_t)ll], hb[(size_t)ll] + c.last_off[g + 1] + c.nt);
+    tree_gather_kernel<<<blocks_for(np, 256), 256, 0, st>>>((const double *)d.in7.p, 7, 0, 3, 6, (const int64_t *)d.tree.p,
+                                                            np, (double *)d.sbuf.p, (double *)d.tbuf.p);
+    // device 0 initialises every column of its sorted buffer: peers may only write their
+    // columns into it after that
+    if (g == 0) CK(h, cudaEventRecord(d.ev[8], st));
+    else CK(h, cudaStreamWaitEvent(st, d0.ev[8], 0));
+    SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
+    prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, np, ns_pad, kernel, (double *)d.rec.p);
+    LeafUjArgs a;
+    a.csr = csr[g];
+    a.csr.wi_leaf += k0;
+    a.csr.wi_off += k0;
+    a.tpos = (const double *)d.tbuf.p; a.tld = 16; a.rec = (const double *)d.rec.p;
+    a.out = (double *)d.tbuf.p; a.urow = 4; a.jrow = 7; a.want_U = 1; a.want_J = 1;
+    a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
+    if (g == 0) CK(h, cudaEventRecord(d.ev[6], st));
+    launch_uj_leaf(kernel, c.nt, (unsigned)(k1 - k0), a, st);
+    if (g == 0) CK(h, cudaEventRecord(d.ev[7], st));
+    h->launches += 3;
+    CK(h, cudaGetLastError());
+    cols[g] = {col0, col1};
+    if (g > 0) {
+      // return this device's columns of the sorted result to device 0
+      CK(h, cudaMemcpyPeerAsync((double *)d0.tbuf.p + col0 * 16, d0.id, (const double *)d.tbuf.p + col0 * 16, d.id,
+                                (size_t)(col1 - col0) * 16 * sizeof(double), st));
+      CK(h, cudaEventRecord(d.ev[5], st));
+    }
+  }
+  CK(h, cudaSetDevice(d0.id));
+  for (int g = 1; g < G; ++g)
+    if (cols[g].second > cols[g].first) CK(h, cudaStreamWaitEvent(d0.stream, h->devs[g].ev[5], 0));
+  CK(h, cudaEventRecord(d0.ev[2], d0.stream));
+  tree_scatter_kernel<<<blocks_for(np, 256), 256, 0, d0.stream>>>((const double *)d0.tbuf.p, (const int64_t *)d0.tree.p, np,
+                                                                 (double *)d0.res18.p, RES_ROWS, RES_U, RES_J, RES_W,
+                                                                 RES_PSE, reset ? 1 : 0,
+                                                                 has_static ? (const double *)d0.stat.p : nullptr, 1);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(d0.ev[3], d0.stream));
+  CK(h, cudaEventRecord(d0.ev[4], d0.stream));
+  TRY(h1_download(h, d0, P, nf, np, 0));
+  for (int g = G - 1; g >= 0; --g) {
+    CK(h, cudaSetDevice(h->devs[g].id));
+    CK(h, cudaStreamSynchronize(h->devs[g].stream));
+  }
+  h->timing.uj_pairs = c.pairs;
+  h->timing.sfs_pairs = 0;
+  h1_fill_timing(h, d0);
+  h->timing.uj_ms = ev_ms(d0.ev[6], d0.ev[7]);  // the pair kernel of device 0 alone
   h->np_resident = -1;
   return VPM_OK;
 }

@@ -101,8 +101,9 @@ __global__ void csr_wi_fill_kernel(const int64_t *__restrict__ tb, const int64_t
   if (l == ntl - 1) stats[CS_NWI] = o + n;
 }
 
-// cut g (1 <= g < G): first work item whose inclusive pair-count prefix reaches total * g / G.
-// out[3g..3g+2] = (item, its leaf, its offset); out[0..2] describes item 0, out[3G..] the last item.
+// cut g (0 <= g <= G): first work item k whose exclusive pair-count prefix reaches total * g / G
+// (cut 0 = 0, cut G = nwi).  out[5g..5g+4] = (k, leaf and offset of item k, leaf and offset of
+// item k - 1): the host turns them into the contiguous target-column range of each device.
 __global__ void csr_cut_kernel(const u64 *__restrict__ wsum /* inclusive */, const int32_t *__restrict__ wi_leaf,
                                const int32_t *__restrict__ wi_off, int64_t nwi, int G, int64_t *__restrict__ out) {
   const int g = threadIdx.x;
@@ -111,7 +112,6 @@ __global__ void csr_cut_kernel(const u64 *__restrict__ wsum /* inclusive */, con
   if (g == 0) k = 0;
   else if (g == G) k = nwi;
   else {
-    // lower_bound over the exclusive prefix w[k] = wsum[k - 1]: first k with w[k] >= target
     const double target = (double)wsum[nwi - 1] * g / G;
     int64_t lo = 0, hi = nwi;
     while (lo < hi) {
@@ -121,10 +121,12 @@ __global__ void csr_cut_kernel(const u64 *__restrict__ wsum /* inclusive */, con
     }
     k = lo;
   }
-  out[3 * g] = k;
-  const int64_t kk = k < nwi ? k : nwi - 1;  // the entry after the end describes the last item
-  out[3 * g + 1] = wi_leaf[kk];
-  out[3 * g + 2] = wi_off[kk];
+  const int64_t ka = k < nwi ? k : nwi - 1, kb = k > 0 ? k - 1 : 0;
+  out[5 * g] = k;
+  out[5 * g + 1] = wi_leaf[ka];
+  out[5 * g + 2] = wi_off[ka];
+  out[5 * g + 3] = wi_leaf[kb];
+  out[5 * g + 4] = wi_off[kb];
 }
 
 __global__ void csr_zero_kernel(u64 *p, int64_t n) {

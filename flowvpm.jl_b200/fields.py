@@ -164,69 +164,16 @@ def random_results(pfield, seed=3, scale=1.0):
 
 
 # ----------------------------------------------------------------- leaf lists
-def build_leaf_lists(X, sigma, ncrit=64, theta=0.4):
-    """Uniform-octree stand-in for FastMultipole's tree.
-
-    Returns dict(sort_index, leaf_begin, leaf_end, direct_list): bodies are
-    sorted by leaf; leaves hold <= ~ncrit bodies on average; (i, j) is in the
-    near-field direct_list when the MAC (r_i + r_j) / d <= theta fails, with leaf radii
-    padded by the regularisation radius (max sigma in the leaf)."""
-    X = np.asarray(X)
-    N = X.shape[1]
-    lo, hi = X.min(axis=1), X.max(axis=1)
-    ext = np.maximum(hi - lo, 1e-300)
-    # cell size so that the average occupancy is ~ncrit/2
-    vol = float(np.prod(ext))
-    h = (vol * (ncrit / 2) / N) ** (1.0 / 3.0)
-    dims = np.maximum(1, np.ceil(ext / h).astype(np.int64))
-    cell = np.minimum(((X - lo[:, None]) / h).astype(np.int64), (dims - 1)[:, None])
-    key = (cell[0] * dims[1] + cell[1]) * dims[2] + cell[2]
-    order = np.argsort(key, kind="stable")
-    skey = key[order]
-    uniq, begin = np.unique(skey, return_index=True)
-    end = np.append(begin[1:], N)
-    nl = len(uniq)
-    Xs = X[:, order]
-    ssig = np.asarray(sigma)[order]
-    centers = np.empty((3, nl))
-    radii = np.empty(nl)
-    for l in range(nl):
-        pts = Xs[:, begin[l]:end[l]]
-        c = 0.5 * (pts.min(axis=1) + pts.max(axis=1))
-        centers[:, l] = c
-        radii[l] = np.sqrt(((pts - c[:, None]) ** 2).sum(axis=0).max()) + ssig[begin[l]:end[l]].max()
-    # candidate neighbours through the cell grid, one vectorised pass per cell offset
-    cz = uniq % dims[2]
-    cy = (uniq // dims[2]) % dims[1]
-    cx = uniq // (dims[1] * dims[2])
-    ncell = int(np.prod(dims))
-    cell_to_leaf = np.full(ncell, -1, dtype=np.int64)
-    cell_to_leaf[uniq] = np.arange(nl)
-    reach = int(np.ceil(2 * radii.max() / (theta * h))) + 1
-    leaves = np.arange(nl)
-    pairs = []
-    for ddx in range(-reach, reach + 1):
-        x = cx + ddx
-        okx = (x >= 0) & (x < dims[0])
-        for ddy in range(-reach, reach + 1):
-            y = cy + ddy
-            okxy = okx & (y >= 0) & (y < dims[1])
-            if not okxy.any():
-                continue
-            for ddz in range(-reach, reach + 1):
-                z = cz + ddz
-                ok = okxy & (z >= 0) & (z < dims[2])
-                if not ok.any():
-                    continue
-                l = leaves[ok]
-                m = cell_to_leaf[(x[ok] * dims[1] + y[ok]) * dims[2] + z[ok]]
-                has = m >= 0
-                l, m = l[has], m[has]
-                dist = np.sqrt(((centers[:, l] - centers[:, m]) ** 2).sum(axis=0))
-                near = (dist == 0) | ((radii[l] + radii[m]) > theta * dist)
-                pairs.append(np.stack([l[near], m[near]], axis=1))
-    pairs = np.concatenate(pairs) if pairs else np.zeros((0, 2), dtype=np.int64)
-    pairs = pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]
-    direct_list = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
-    return dict(sort_index=order.astype(np.int64), leaf_begin=begin.astype(np.int64),
-                leaf_end=end.astype(np.int64), direct_list=direct_list)
+def build_leaf_lists(X, sigma, ncrit=64, theta=0.4, handle=None):
+    """Leaf lists for the FMM near-field hook, built ON THE GPU (vpm_leaflists_build, csrc/vpm_tree.cuh):
+    dict(sort_index, leaf_begin, leaf_end, direct_list).  Stand-in for FastMultipole's tree
+    (src/FLOWVPM_UJ.jl:90-101) when only positions and core sizes are at hand."""
+    from .particlefield import ParticleField
+    from .uj import leaf_lists
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[1]
+    pf = ParticleField(max(n, 1))
+    pf.particles[0:3, :n] = X
+    pf.particles[6, :n] = np.asarray(sigma, dtype=np.float64)
+    pf.np = n
+    return leaf_lists(pf, ncrit=ncrit, theta=theta, handle=handle)

@@ -159,6 +159,38 @@ def Estr_fmm(pfield, target_sort_index, source_sort_index, target_leaves, source
         pt.ctypes.data, ps.ctypes.data, len(pt), pfield.kernel.id, flags))
 
 
+def leaf_lists(pfield, ncrit=64, theta=0.4, *, handle=None, fetch=True):
+    """Device-built leaf lists of `pfield` (vpm_leaflists_build): sort index, leaf ranges and the
+    near-field direct_list by the theta-MAC; they stay resident for `UJ_nearfield`.  With
+    fetch=True they are also returned as dict(sort_index, leaf_begin, leaf_end, direct_list)."""
+    h = handle or get_handle()
+    P = pfield.particles
+    _check_matrix(P)
+    nl, npairs = C.c_int64(), C.c_int64()
+    h.check(h.lib.vpm_leaflists_build(h.ptr, P.ctypes.data, P.shape[0], pfield.np, int(ncrit), float(theta),
+                                      C.byref(nl), C.byref(npairs)))
+    if not fetch:
+        return dict(n_leaves=nl.value, n_pairs=npairs.value)
+    sort_index = np.empty(pfield.np, dtype=np.int64)
+    lb, le = np.empty(nl.value, dtype=np.int64), np.empty(nl.value, dtype=np.int64)
+    pt, ps = np.empty(npairs.value, dtype=np.int32), np.empty(npairs.value, dtype=np.int32)
+    h.check(h.lib.vpm_leaflists_get(h.ptr, sort_index.ctypes.data, lb.ctypes.data, le.ctypes.data,
+                                    pt.ctypes.data, ps.ctypes.data))
+    return dict(sort_index=sort_index, leaf_begin=lb, leaf_end=le,
+                direct_list=np.ascontiguousarray(np.stack([pt, ps], axis=1)))
+
+
+def UJ_nearfield(pfield, *, reset=True, handle=None, no_farfield_shortcut=False):
+    """Near-field half of UJ_fmm (src/FLOWVPM_UJ.jl:62-129) over the leaf lists last built by
+    `leaf_lists(pfield, ...)`, entirely on the device(s); adds to rows U, J (after
+    _reset_particles when reset=True)."""
+    h = handle or get_handle()
+    P = pfield.particles
+    _check_matrix(P)
+    flags = (_cabi.FLAG_RESET if reset else 0) | (_cabi.FLAG_NO_FARFIELD_SHORTCUT if no_farfield_shortcut else 0)
+    h.check(h.lib.vpm_uj_nearfield(h.ptr, P.ctypes.data, P.shape[0], pfield.np, pfield.kernel.id, flags))
+
+
 def zeta_direct(pfield, *, handle=None):
     """zeta_direct(pfield) -- src/FLOWVPM_viscous.jl:488-515: J[1:3] of every particle <-
     sum_j Gamma_j zeta_sigma_j(x_i - x_j) (the vorticity the particle field represents)."""

