@@ -222,8 +222,22 @@ def nearfield_extra(vpm, h, n):
     theta = 0.4 near-field list, one vpm_p2p_leafpairs call from host buffers."""
     out = {}
     pf = vpm.fields.cloud_field(n, kernel=vpm.winckelmans)
+    h.check(h.lib.vpm_pin_host(h.ptr, pf.particles.ctypes.data, pf.particles.nbytes))
     for ncrit in (128, 1024):
-        ll = vpm.fields.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=ncrit, theta=0.4)
+        # f-3: tree + theta-MAC list built on the device, near field over the resident lists
+        vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, fetch=False)
+        t = time.perf_counter()
+        vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, fetch=False)
+        t_tree = time.perf_counter() - t
+        vpm.UJ_nearfield(pf, reset=True)
+        t = time.perf_counter()
+        vpm.UJ_nearfield(pf, reset=True)
+        t_near = time.perf_counter() - t
+        f3 = {"device_tree_ms": t_tree * 1e3, "nearfield_call_ms": t_near * 1e3,
+              "e2e_interactions_per_s": h.timing()["uj_pairs"] / (t_tree + t_near),
+              "what": "vpm_leaflists_build + vpm_uj_nearfield from the pinned host matrix (tree, list, near field on the device)"}
+        # Hook 3: the same lists handed in by the caller, as FastMultipole would
+        ll = vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4)
         order = ll["sort_index"]
         sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
         tb = np.zeros((16, n), order="F")
@@ -239,7 +253,8 @@ def nearfield_extra(vpm, h, n):
         tm = h.timing()
         out[f"ncrit_{ncrit}"] = {"leaves": int(len(sizes)), "mean_leaf": float(sizes.mean()), "list_pairs": int(len(dl)),
                                  "interactions": pairs, "kernel_interactions_per_s": pairs / (tm["uj_ms"] * 1e-3),
-                                 "e2e_interactions_per_s": pairs / dt}
+                                 "e2e_interactions_per_s": pairs / dt, "device_lists": f3}
+    h.check(h.lib.vpm_unpin_host(h.ptr, pf.particles.ctypes.data))
     return out
 
 
@@ -423,6 +438,17 @@ def main():
                 by[name]["no_farfield_shortcut_interactions_per_s"] = n * n / (np.mean(m2) * 1e-3)
         field.kernel_id = kernel.id
         extras["by_kernel"] = by
+        # optional FP32-arithmetic sweep (VPM_FLAG_FP32, north star's 1e-5 mode) against the FP32 FMA pipe
+        import ctypes as C
+        fv, fms = C.c_double(), C.c_double()
+        h.check(lib.vpm_measure_ffma_peak(h.ptr, 0, C.byref(fv), C.byref(fms)))
+        m, km = timed_steps(lambda: field.uj(vpm._cabi.FLAG_FP32), 2, 1)
+        extras["fp32_mode"] = {"interactions_per_s": n * n / (np.mean(m) * 1e-3), "kernel": args.kernel,
+                               "ffma_per_s_measured": fv.value,
+                               "fp32_lane_ops_per_interaction": 46,
+                               "frac_of_ffma_issue_peak": n * n / (np.mean(km) * 1e-3) * 46 / fv.value,
+                               "what": "uj_pairs_kernel_f32: hi/lo split positions, packed f32x2 pair loop (23 FFMA2/FMUL2/"
+                                       "FADD2 per pair), FP64 flush per 128-source tile; parity bar 1e-5 (tests/test_fp32_gpu.py)"}
         uj_ms = ms_per_step
         extras["rvpm_step_ms_estimate"] = {"value": 5 * uj_ms + 4 * extras["sfs"]["ms"],
                                            "what": "5 U/J + 4 SFS sweeps (RK3 + DynamicSFS + relaxation, SURVEY 3.1), O(N) host work excluded"}

@@ -541,6 +541,7 @@ typedef int (*nccl_all_gather_t)(const void *send, void *recv, size_t count, int
                                  cudaStream_t stream);
 typedef int (*nccl_broadcast_t)(const void *send, void *recv, size_t count, int dtype, int root, void *comm,
                                 cudaStream_t stream);
+typedef int (*nccl_sendrecv_t)(void *buf, size_t count, int dtype, int peer, void *comm, cudaStream_t stream);
 typedef int (*nccl_group_t)(void);
 typedef int (*nccl_comm_destroy_t)(void *comm);
 typedef const char *(*nccl_err_t)(int);
@@ -548,6 +549,7 @@ struct NcclApi {
   nccl_comm_init_all_t comm_init_all = nullptr;
   nccl_all_gather_t all_gather = nullptr;
   nccl_broadcast_t broadcast = nullptr;
+  nccl_sendrecv_t send = nullptr, recv = nullptr;
   nccl_group_t group_start = nullptr, group_end = nullptr;
   nccl_comm_destroy_t comm_destroy = nullptr;
   nccl_err_t err_string = nullptr;
@@ -564,12 +566,14 @@ int nccl_load(vpm_handle *h) {
   g_nccl.comm_init_all = (nccl_comm_init_all_t)dlsym(lib, "ncclCommInitAll");
   g_nccl.all_gather = (nccl_all_gather_t)dlsym(lib, "ncclAllGather");
   g_nccl.broadcast = (nccl_broadcast_t)dlsym(lib, "ncclBroadcast");
+  g_nccl.send = (nccl_sendrecv_t)dlsym(lib, "ncclSend");
+  g_nccl.recv = (nccl_sendrecv_t)dlsym(lib, "ncclRecv");
   g_nccl.group_start = (nccl_group_t)dlsym(lib, "ncclGroupStart");
   g_nccl.group_end = (nccl_group_t)dlsym(lib, "ncclGroupEnd");
   g_nccl.comm_destroy = (nccl_comm_destroy_t)dlsym(lib, "ncclCommDestroy");
   g_nccl.err_string = (nccl_err_t)dlsym(lib, "ncclGetErrorString");
   if (!g_nccl.comm_init_all || !g_nccl.all_gather || !g_nccl.broadcast || !g_nccl.group_start || !g_nccl.group_end ||
-      !g_nccl.comm_destroy)
+      !g_nccl.comm_destroy || !g_nccl.send || !g_nccl.recv)
     return fail(h, VPM_ENCCL, "libnccl.so.2 lacks a required symbol");
   h->nccl_lib = lib;
   return VPM_OK;
@@ -2079,10 +2083,6 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
     const int64_t col1 = G == 1 ? np : std::min<int64_t>(he[(size_t)ll], hb[(size_t)ll] + c.last_off[g + 1] + c.nt);
     tree_gather_kernel<<<blocks_for(np, 256), 256, 0, st>>>((const double *)d.in7.p, 7, 0, 3, 6, (const int64_t *)d.tree.p,
                                                             np, (double *)d.sbuf.p, (double *)d.tbuf.p);
-    // device 0 initialises every column of its sorted buffer: peers may only write their
-    // columns into it after that
-    if (g == 0) CK(h, cudaEventRecord(d.ev[8], st));
-    else CK(h, cudaStreamWaitEvent(st, d0.ev[8], 0));
     SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
     prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, np, ns_pad, kernel, (double *)d.rec.p);
     LeafUjArgs a;
@@ -2098,16 +2098,23 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
     h->launches += 3;
     CK(h, cudaGetLastError());
     cols[g] = {col0, col1};
-    if (g > 0) {
-      // return this device's columns of the sorted result to device 0
-      CK(h, cudaMemcpyPeerAsync((double *)d0.tbuf.p + col0 * 16, d0.id, (const double *)d.tbuf.p + col0 * 16, d.id,
-                                (size_t)(col1 - col0) * 16 * sizeof(double), st));
-      CK(h, cudaEventRecord(d.ev[5], st));
+  }
+  // the devices return their columns of the sorted result to device 0 over NVLink
+  // (ncclSend / ncclRecv; the receives are ordered on device 0's stream after its own
+  // gather + pair kernel and before the scatter)
+  if (G > 1) {
+    NCK(h, g_nccl.group_start());
+    for (int g = 1; g < G; ++g) {
+      const int64_t col0 = cols[g].first, col1 = cols[g].second;
+      if (col1 <= col0) continue;
+      Dev &d = h->devs[g];
+      const size_t cnt = (size_t)(col1 - col0) * 16;
+      NCK(h, g_nccl.send((double *)d.tbuf.p + col0 * 16, cnt, kNcclFloat64, 0, h->comms[g], d.stream));
+      NCK(h, g_nccl.recv((double *)d0.tbuf.p + col0 * 16, cnt, kNcclFloat64, g, h->comms[0], d0.stream));
     }
+    NCK(h, g_nccl.group_end());
   }
   CK(h, cudaSetDevice(d0.id));
-  for (int g = 1; g < G; ++g)
-    if (cols[g].second > cols[g].first) CK(h, cudaStreamWaitEvent(d0.stream, h->devs[g].ev[5], 0));
   CK(h, cudaEventRecord(d0.ev[2], d0.stream));
   tree_scatter_kernel<<<blocks_for(np, 256), 256, 0, d0.stream>>>((const double *)d0.tbuf.p, (const int64_t *)d0.tree.p, np,
                                                                  (double *)d0.res18.p, RES_ROWS, RES_U, RES_J, RES_W,

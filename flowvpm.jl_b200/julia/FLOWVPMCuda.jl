@@ -31,6 +31,8 @@ const FLAG_RESET = Cint(1)
 const FLAG_RESET_SFS = Cint(2)
 const FLAG_SFS = Cint(4)
 const FLAG_TRANSPOSED = Cint(8)
+const FLAG_NO_FARFIELD_SHORTCUT = Cint(16)
+const FLAG_FP32 = Cint(32)   # library-only: FP32-arithmetic U/J sweep (1e-5 bar); default is FP64
 
 const lib = Ref{String}("libvpm_cuda.so")
 const handle = Ref{Ptr{Cvoid}}(C_NULL)
@@ -98,12 +100,13 @@ particles never reset, SFS sweep after the final J).  `rbf` is accepted and igno
 as in the reference.
 """
 function UJ_cuda(pfield::vpm.ParticleField{Float64}; rbf::Bool=false, sfs::Bool=false,
-                 reset::Bool=true, reset_sfs::Bool=false, optargs...)
+                 reset::Bool=true, reset_sfs::Bool=false, fp32::Bool=false, optargs...)
     P = pfield.particles
+    # fp32=true (library-only keyword): U/J sweep in FP32 arithmetic, 1e-5 instead of 1e-12
     GC.@preserve P check(ccall((:vpm_uj_direct, lib[]), Cint,
                                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Cint, Cint),
                                handle[], P, size(P, 1), pfield.np, kernel_id(pfield.kernel),
-                               flags(pfield; sfs, reset, reset_sfs)))
+                               flags(pfield; sfs, reset, reset_sfs) | (fp32 ? FLAG_FP32 : Cint(0))))
     return nothing
 end
 
@@ -193,6 +196,38 @@ function zeta_cuda(pfield::vpm.ParticleField{Float64})
     P = pfield.particles
     GC.@preserve P check(ccall((:vpm_zeta_direct, lib[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Cint),
                                handle[], P, size(P, 1), pfield.np, kernel_id(pfield.kernel)))
+    return nothing
+end
+
+# ------------------------------------------------------------------------------
+# Optional: leaf lists built on the device (include/vpm_cuda.h vpm_leaflists_*, SURVEY 8 f-3).
+# `leaflists_cuda!` replaces the host tree of the near field when FastMultipole's own tree is
+# not needed (near-field-only evaluations, or as the source of `direct_list` for the hooks
+# above); `UJ_nearfield_cuda!` is the near-field half of UJ_fmm (src/FLOWVPM_UJ.jl:62-129)
+# over those resident lists.
+# ------------------------------------------------------------------------------
+function leaflists_cuda!(pfield::vpm.ParticleField{Float64}; ncrit::Integer=50, theta::Real=pfield.fmm.theta,
+                         fetch::Bool=false)
+    P = pfield.particles
+    nl, npairs = Ref{Int64}(0), Ref{Int64}(0)
+    GC.@preserve P check(ccall((:vpm_leaflists_build, lib[]), Cint,
+                               (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Cdouble, Ref{Int64}, Ref{Int64}),
+                               handle[], P, size(P, 1), pfield.np, ncrit, theta, nl, npairs))
+    fetch || return (n_leaves=nl[], n_pairs=npairs[])
+    sort_index = Vector{Int64}(undef, pfield.np)
+    lb, le = Vector{Int64}(undef, nl[]), Vector{Int64}(undef, nl[])
+    pt, ps = Vector{Int32}(undef, npairs[]), Vector{Int32}(undef, npairs[])
+    GC.@preserve sort_index lb le pt ps check(ccall((:vpm_leaflists_get, lib[]), Cint,
+        (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}), handle[], sort_index, lb, le, pt, ps))
+    # 0-based, half-open on the C side -> 1-based Julia ranges
+    return (sort_index=sort_index .+ 1, leaves=[(lb[i]+1):le[i] for i in 1:nl[]],
+            direct_list=[(pt[k] + 1, ps[k] + 1) for k in 1:npairs[]])
+end
+
+function UJ_nearfield_cuda!(pfield::vpm.ParticleField{Float64}; reset::Bool=true)
+    P = pfield.particles
+    GC.@preserve P check(ccall((:vpm_uj_nearfield, lib[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Cint, Cint),
+                               handle[], P, size(P, 1), pfield.np, kernel_id(pfield.kernel), reset ? FLAG_RESET : Cint(0)))
     return nothing
 end
 

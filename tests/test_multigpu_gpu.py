@@ -120,6 +120,43 @@ def test_nearfield_leafpairs_multi_gpu(vpm, ncrit):
         h.close()
 
 
+@pytest.mark.parametrize("ncrit", [24, 300])
+def test_uj_nearfield_device_lists_multi_gpu(vpm, ncrit):
+    """f-3 on several devices: lists built on device 0, work items cut over the devices, sorted
+    results returned to device 0 over NVLink; must equal the single-list oracle evaluation and
+    the single-GPU result bit for bit (same per-target summation order)"""
+    g = _ngpu()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    hm, h1 = vpm.Handle(min(g, 4)), vpm.Handle(1)
+    try:
+        pf = vpm.fields.cloud_field(7000, kernel=vpm.winckelmans, static_fraction=0.05, seed=23)
+        vpm.fields.random_results(pf, scale=1e-3)
+        before = pf.particles.copy(order="F")
+        ll = vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, handle=hm)
+        ref_ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=ncrit, theta=0.4)
+        assert all(np.array_equal(ll[k], ref_ll[k]) for k in ll)
+        vpm.UJ_nearfield(pf, reset=False, handle=hm)
+        multi = pf.particles.copy(order="F")
+        pf.particles[:] = before
+        vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, handle=h1, fetch=False)
+        vpm.UJ_nearfield(pf, reset=False, handle=h1)
+        assert np.array_equal(multi, pf.particles)
+        order = ll["sort_index"]
+        sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
+        tb = np.zeros((16, pf.np), order="F")
+        tb[0:3] = pf.get_X()[:, order]
+        leaves = (ll["leaf_begin"], ll["leaf_end"])
+        oracle.direct_leafpairs(tb, sb, leaves, leaves, ll["direct_list"], "winckelmans")
+        near = np.zeros((12, pf.np))
+        near[:, order] = tb[4:16]
+        assert relerr(multi[9:12] - before[9:12], near[0:3]) < TOL_FP64
+        assert relerr(multi[15:24] - before[15:24], near[3:12]) < 1e-11
+    finally:
+        hm.close()
+        h1.close()
+
+
 @pytest.mark.parametrize("sfs", [False, "dynamic"])
 def test_resident_step_multi_gpu(vpm, sfs):
     """vpm_field_step with the mirror replicated on every device of the handle: targets sharded,

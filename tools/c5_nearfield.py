@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """One-off measurement (GPU box): BASELINE.json configs[4] -- FMM near-field offload on a
-2^24-particle cloud: uniform-octree leaves, theta = 0.4 near-field list built on the host,
-evaluated by vpm_p2p_leafpairs (all GPUs of the handle).  usage: c5_nearfield.py [log2N] [ncrit] [ngpu]"""
+2^24-particle cloud.  Two paths through the C ABI, both from host buffers:
+  hook3 : lists handed in by the caller (as FastMultipole would) -> vpm_p2p_leafpairs
+  f3    : vpm_leaflists_build (tree + theta = 0.4 list on the device) -> vpm_uj_nearfield
+usage: c5_nearfield.py [log2N] [ncrit] [ngpu]"""
 import json
 import os
 import sys
@@ -14,45 +16,69 @@ from vpm_import import load  # noqa: E402
 
 vpm = load()
 logn = int(sys.argv[1]) if len(sys.argv) > 1 else 24
-ncrit = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+ncrits = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [512]
 ngpu = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 n = 1 << logn
 h = vpm.Handle(ngpu)
-t = time.perf_counter()
-X, Gamma, sigma = vpm.fields.cloud_arrays(n)
-ll = vpm.fields.build_leaf_lists(X, sigma, ncrit=ncrit, theta=0.4)
-t_build = time.perf_counter() - t
-order = ll["sort_index"]
+pf = vpm.fields.cloud_field(n, kernel=vpm.winckelmans)
+
+
+def pin(a):
+    h.check(h.lib.vpm_pin_host(h.ptr, a.ctypes.data, a.nbytes))
+
+
+pin(pf.particles)  # as a Julia caller would page-lock pfield.particles once
 sb = np.zeros((8, n), order="F")
-sb[0:3], sb[4:7], sb[3], sb[7] = X[:, order], Gamma[:, order], sigma[order], sigma[order]
 tb = np.zeros((16, n), order="F")
-tb[0:3] = X[:, order]
-del X, Gamma
-leaves = (ll["leaf_begin"], ll["leaf_end"])
-sizes = ll["leaf_end"] - ll["leaf_begin"]
-dl = ll["direct_list"]
-pairs = int((sizes[dl[:, 0]].astype(np.int64) * sizes[dl[:, 1]]).sum())
-res = {"n": n, "ncrit": ncrit, "gpus": ngpu, "leaves": int(len(sizes)), "mean_leaf": float(sizes.mean()),
-       "list_pairs": int(len(dl)), "interactions": pairs, "host_tree_s": t_build}
-for rep in range(2):
-    tb[4:] = 0
-    t = time.perf_counter()
-    vpm.nearfield_device(tb, leaves, sb, leaves, dl, vpm.winckelmans, handle=h)
-    dt = time.perf_counter() - t
-tm = h.timing()
-res.update(call_s=dt, kernel_ms_dev0=tm["uj_ms"], h2d_ms=tm["h2d_ms"], d2h_ms=tm["d2h_ms"],
-           e2e_interactions_per_s=pairs / dt, finite=bool(np.isfinite(tb[4:]).all()))
-# parity on a slice: three target leaves recomputed by the CPU oracle (test infrastructure)
-from oracle import oracle  # noqa: E402
-worst = 0.0
-for leaf in (0, len(sizes) // 2, len(sizes) - 1):
-    sel = dl[dl[:, 0] == leaf]
-    ref = np.zeros((16, n), order="F") if False else None
-    b, e = int(ll["leaf_begin"][leaf]), int(ll["leaf_end"][leaf])
-    loc = np.zeros((16, e - b), order="F")
-    loc[0:3] = tb[0:3, b:e]
-    for _, sl in sel:
-        oracle.direct_buffers(loc, 0, e - b, sb, int(ll["leaf_begin"][sl]), int(ll["leaf_end"][sl]), "winckelmans")
-    worst = max(worst, float(np.abs(loc[4:] - tb[4:, b:e]).max() / np.abs(loc[4:]).max()))
-res["slice_parity_rel_err"] = worst
-print(json.dumps(res))
+pin(sb)
+pin(tb)
+for ncrit in ncrits:
+  res = {"n": n, "ncrit": ncrit, "gpus": ngpu}
+  # ---- f-3: tree and list on the device
+  for rep in range(2):
+      t = time.perf_counter()
+      info = vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, handle=h, fetch=False)
+      t_build = time.perf_counter() - t
+  res.update(leaves=info["n_leaves"], list_pairs=info["n_pairs"], device_tree_s=t_build,
+             device_tree_h2d_ms=h.timing()["h2d_ms"], device_tree_total_ms=h.timing()["total_ms"])
+  for rep in range(2):
+      t = time.perf_counter()
+      vpm.UJ_nearfield(pf, reset=True, handle=h)
+      dt = time.perf_counter() - t
+  tm = h.timing()
+  res.update(f3_call_s=dt, f3_kernel_ms_dev0=tm["uj_ms"], f3_h2d_ms=tm["h2d_ms"], f3_d2h_ms=tm["d2h_ms"],
+             interactions=tm["uj_pairs"], f3_e2e_interactions_per_s=tm["uj_pairs"] / dt,
+             f3_tree_plus_nearfield_interactions_per_s=tm["uj_pairs"] / (dt + t_build))
+  U_f3 = pf.particles[9:12].copy()
+  # ---- Hook 3: the same lists fetched to the host and handed back like FastMultipole's
+  t = time.perf_counter()
+  ll = vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, handle=h)
+  res["device_tree_with_fetch_s"] = time.perf_counter() - t
+  order = ll["sort_index"]
+  sb[0:3], sb[4:7], sb[3], sb[7] = pf.get_X()[:, order], pf.get_Gamma()[:, order], pf.get_sigma()[order], pf.get_sigma()[order]
+  tb[0:3] = sb[0:3]
+  leaves = (ll["leaf_begin"], ll["leaf_end"])
+  dl = ll["direct_list"]
+  for rep in range(2):
+      tb[4:] = 0
+      t = time.perf_counter()
+      vpm.nearfield_device(tb, leaves, sb, leaves, dl, vpm.winckelmans, handle=h)
+      dt = time.perf_counter() - t
+  tm = h.timing()
+  res.update(hook3_call_s=dt, hook3_kernel_ms_dev0=tm["uj_ms"], hook3_h2d_ms=tm["h2d_ms"], hook3_d2h_ms=tm["d2h_ms"],
+             hook3_e2e_interactions_per_s=tm["uj_pairs"] / dt, finite=bool(np.isfinite(tb[4:]).all()))
+  res["f3_equals_hook3"] = bool(np.array_equal(U_f3[:, order], tb[4:7]))
+  # parity on a slice: three target leaves recomputed by the CPU oracle (test infrastructure)
+  from oracle import oracle  # noqa: E402
+  worst = 0.0
+  sizes = ll["leaf_end"] - ll["leaf_begin"]
+  for leaf in (0, len(sizes) // 2, len(sizes) - 1):
+      sel = dl[dl[:, 0] == leaf]
+      b, e = int(ll["leaf_begin"][leaf]), int(ll["leaf_end"][leaf])
+      loc = np.zeros((16, e - b), order="F")
+      loc[0:3] = tb[0:3, b:e]
+      for _, sl in sel:
+          oracle.direct_buffers(loc, 0, e - b, sb, int(ll["leaf_begin"][sl]), int(ll["leaf_end"][sl]), "winckelmans")
+      worst = max(worst, float(np.abs(loc[4:] - tb[4:, b:e]).max() / np.abs(loc[4:]).max()))
+  res["slice_parity_rel_err"] = worst
+  print(json.dumps(res), flush=True)
