@@ -1870,12 +1870,22 @@ static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, i
   Dev &d = h->devs[0];
   cudaStream_t st = d.stream;
   h->launches = 0;
-  CK(h, cudaSetDevice(d.id));
-  TRY(ensure(h, d.in7, (size_t)np * 7 * sizeof(double)));
-  TRY(ensure(h, d.jbuf, (size_t)np * 9 * sizeof(double)));
-  TRY(ensure(h, d.sfs3, (size_t)np * 3 * sizeof(double)));
+  // Multi-GPU: as Hook 3 -- target leaves sharded over the devices in contiguous runs of work
+  // items; needs increasing, non-overlapping target leaves (tree-sorted), else device 0 alone
+  int G = (int)h->devs.size();
+  for (int64_t l = 0; l + 1 < ntl && G > 1; ++l)
+    if (tb[l + 1] < te[l]) G = 1;
   const int64_t ns_pad = round_up(np, kTile);
-  TRY(ensure(h, d.srec, (size_t)ns_pad * kSfsRec * sizeof(double)));
+  for (int g = 0; g < G; ++g) {
+    Dev &dg = h->devs[g];
+    CK(h, cudaSetDevice(dg.id));
+    TRY(ensure(h, dg.in7, (size_t)np * 7 * sizeof(double)));
+    TRY(ensure(h, dg.jbuf, (size_t)np * 9 * sizeof(double)));
+    TRY(ensure(h, dg.srec, (size_t)ns_pad * kSfsRec * sizeof(double)));
+    if (G > 1) TRY(ensure(h, dg.tbuf, (size_t)np * 3 * sizeof(double)));
+  }
+  CK(h, cudaSetDevice(d.id));
+  TRY(ensure(h, d.sfs3, (size_t)np * 3 * sizeof(double)));
   CK(h, cudaEventRecord(d.ev[0], st));
   CK(h, cudaMemcpy2DAsync(d.in7.p, 7 * sizeof(double), P, nf * sizeof(double), 7 * sizeof(double),
                           (size_t)np, cudaMemcpyHostToDevice, st));
@@ -1884,33 +1894,86 @@ static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, i
   const int out_row = mode == MODE_ZETA ? R_J : R_SFS;
   CK(h, cudaMemcpy2DAsync(d.sfs3.p, 3 * sizeof(double), P + out_row, nf * sizeof(double), 3 * sizeof(double),
                           (size_t)np, cudaMemcpyHostToDevice, st));
-  LeafSfsArgs a;
   DevCsr c;
-  TRY(build_csr_device(h, fn, tb, te, ntl, np, sb, se, nsl, np, pt, ps, npairs, 1, tsort, np, ssort, np, c));
+  TRY(build_csr_device(h, fn, tb, te, ntl, np, sb, se, nsl, np, pt, ps, npairs, G, tsort, np, ssort, np, c));
   if (c.nwi == 0) return VPM_OK;
-  a.csr = c.csr;
-  const int64_t *dts = c.d_tsort, *dss = c.d_ssort;
   CK(h, cudaEventRecord(d.ev[1], st));
   CK(h, cudaEventRecord(d.ev[2], st));
   CK(h, cudaEventRecord(d.ev[3], st));
+  for (int g = 1; g < G; ++g) {
+    CK(h, cudaSetDevice(h->devs[g].id));
+    TRY(ensure(h, h->devs[g].ibuf, d.ibuf.cap));
+  }
+  TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np * 7 * sizeof(double)));
+  TRY(bcast_from_dev0(h, &Dev::jbuf, (size_t)np * 9 * sizeof(double)));
+  TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
   const int transposed = (flags & VPM_FLAG_TRANSPOSED) ? 1 : 0;
-  SrcView sv{(const double *)d.in7.p, 7, 0, 3, 6};
-  prep_sfs_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, (const double *)d.jbuf.p, 9, 0, nullptr, 1,
-                                                            dss, np, ns_pad, kernel, transposed,
-                                                            (double *)d.srec.p);
-  h->launches++;
-  a.tpos = (const double *)d.in7.p; a.tld = 7; a.tJ = (const double *)d.jbuf.p; a.jld = 9;
-  a.tindex = dts; a.rec = (const double *)d.srec.p; a.out = (double *)d.sfs3.p; a.old = 3; a.orow = 0;
-  a.transposed = transposed;
-  a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
-  launch_sfs_leaf(kernel, c.nt, (unsigned)c.nwi, a, st, mode);
-  h->launches++;
-  CK(h, cudaGetLastError());
+  std::vector<std::pair<int64_t, int64_t>> cols(G, {0, 0});
+  for (int g = 0; g < G; ++g) {
+    Dev &dg = h->devs[g];
+    cudaStream_t sg = dg.stream;
+    const int64_t k0 = c.cut[g], k1 = c.cut[g + 1];
+    if (k1 <= k0) continue;
+    CK(h, cudaSetDevice(dg.id));
+    const ptrdiff_t shift = (const char *)dg.ibuf.p - (const char *)d.ibuf.p;
+    const int64_t *dts = (const int64_t *)((const char *)c.d_tsort + shift);
+    const int64_t *dss = (const int64_t *)((const char *)c.d_ssort + shift);
+    SrcView sv{(const double *)dg.in7.p, 7, 0, 3, 6};
+    prep_sfs_records<<<blocks_for(ns_pad, 256), 256, 0, sg>>>(sv, (const double *)dg.jbuf.p, 9, 0, nullptr, 1, dss, np,
+                                                              ns_pad, kernel, transposed, (double *)dg.srec.p);
+    LeafSfsArgs a;
+    a.csr = g == 0 ? c.csr : rebase_csr(c.csr, d.ibuf.p, dg.ibuf.p);
+    a.csr.wi_leaf += k0;
+    a.csr.wi_off += k0;
+    a.tpos = (const double *)dg.in7.p; a.tld = 7; a.tJ = (const double *)dg.jbuf.p; a.jld = 9;
+    a.tindex = dts; a.rec = (const double *)dg.srec.p; a.old = 3; a.orow = 0;
+    a.transposed = transposed;
+    a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
+    if (G == 1) {
+      a.out = (double *)dg.sfs3.p;  // particle-indexed, accumulated in place
+    } else {
+      // sums land in a zeroed buffer indexed by sorted body; the columns return to device 0
+      const int64_t lf = c.first_leaf[g], ll = c.last_leaf[g + 1];
+      const int64_t col0 = tb[lf] + c.first_off[g];
+      const int64_t col1 = std::min<int64_t>(te[ll], tb[ll] + c.last_off[g + 1] + c.nt);
+      cols[g] = {col0, col1};
+      CK(h, cudaMemsetAsync((double *)dg.tbuf.p + col0 * 3, 0, (size_t)(col1 - col0) * 3 * sizeof(double), sg));
+      a.out = (double *)dg.tbuf.p;
+      a.obody = 1;
+    }
+    launch_sfs_leaf(kernel, c.nt, (unsigned)(k1 - k0), a, sg, mode);
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+  }
+  if (G > 1) {
+    NCK(h, g_nccl.group_start());
+    for (int g = 1; g < G; ++g) {
+      const int64_t col0 = cols[g].first, col1 = cols[g].second;
+      if (col1 <= col0) continue;
+      const size_t cnt = (size_t)(col1 - col0) * 3;
+      NCK(h, g_nccl.send((double *)h->devs[g].tbuf.p + col0 * 3, cnt, kNcclFloat64, 0, h->comms[g], h->devs[g].stream));
+      NCK(h, g_nccl.recv((double *)d.tbuf.p + col0 * 3, cnt, kNcclFloat64, g, h->comms[0], st));
+    }
+    NCK(h, g_nccl.group_end());
+    CK(h, cudaSetDevice(d.id));
+    for (int g = 0; g < G; ++g) {
+      const int64_t col0 = cols[g].first, col1 = cols[g].second;
+      if (col1 <= col0) continue;
+      add_sorted3_kernel<<<blocks_for(col1 - col0, 256), 256, 0, st>>>((const double *)d.tbuf.p, c.d_tsort, col0, col1,
+                                                                      (double *)d.sfs3.p);
+      h->launches++;
+    }
+    CK(h, cudaGetLastError());
+  }
+  CK(h, cudaSetDevice(d.id));
   CK(h, cudaEventRecord(d.ev[4], st));
   CK(h, cudaMemcpy2DAsync(P + out_row, nf * sizeof(double), d.sfs3.p, 3 * sizeof(double), 3 * sizeof(double),
                           (size_t)np, cudaMemcpyDeviceToHost, st));
   CK(h, cudaEventRecord(d.ev[5], st));
-  CK(h, cudaStreamSynchronize(st));
+  for (int g = G - 1; g >= 0; --g) {
+    CK(h, cudaSetDevice(h->devs[g].id));
+    CK(h, cudaStreamSynchronize(h->devs[g].stream));
+  }
   h->timing.uj_pairs = 0;
   h->timing.sfs_pairs = c.pairs;
   h1_fill_timing(h, d);

@@ -144,6 +144,7 @@ struct LeafSfsArgs {
   int orow;
   int transposed;
   int shortcut;
+  int obody = 0;       // 1: out is indexed by sorted body (multi-GPU: columns return to device 0)
 };
 
 template <int K, int NT, int TILE, int MODE = MODE_SFS>
@@ -210,11 +211,22 @@ __global__ void __launch_bounds__(NT) sfs_leaf_kernel(const LeafSfsArgs a) {
   }
 
   if (valid) {
-    double *o = a.out + c * a.old + a.orow;
+    double *o = a.out + (a.obody ? i : c) * a.old + a.orow;
     o[0] += acc[0][0];
     o[1] += acc[0][1];
     o[2] += acc[0][2];
   }
+}
+
+// out[tindex[i]] += sorted[i] for sorted bodies [i0, i1)  (3 values per body)
+__global__ void add_sorted3_kernel(const double *__restrict__ sorted, const int64_t *__restrict__ tindex, int64_t i0,
+                                   int64_t i1, double *__restrict__ out) {
+  const int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i1) return;
+  const int64_t c = tindex[i];
+  out[c * 3] += sorted[i * 3];
+  out[c * 3 + 1] += sorted[i * 3 + 1];
+  out[c * 3 + 2] += sorted[i * 3 + 2];
 }
 
 }  // namespace vpm

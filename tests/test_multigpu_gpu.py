@@ -157,6 +157,43 @@ def test_uj_nearfield_device_lists_multi_gpu(vpm, ncrit):
         h1.close()
 
 
+def test_estr_and_zeta_leafpairs_multi_gpu(vpm):
+    """Estr_fmm! / zeta_fmm over a list with the target leaves sharded over the devices: equal to
+    the oracle and bit-identical to the single-device evaluation"""
+    g = _ngpu()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    hm, h1 = vpm.Handle(min(g, 4)), vpm.Handle(1)
+    try:
+        pf = vpm.fields.cloud_field(5000, kernel=vpm.gaussianerf, seed=29)
+        vpm.fields.random_results(pf, scale=1e-2)
+        ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=40, theta=0.4)
+        order, leaves = ll["sort_index"], (ll["leaf_begin"], ll["leaf_end"])
+        dl = ll["direct_list"][::-1].copy()   # unsorted list
+        before = pf.particles.copy(order="F")
+        ref = before.copy(order="F")
+        oracle.estr_leafpairs(ref, order, order, leaves, leaves, dl, "gaussianerf", True)
+        vpm.Estr_fmm(pf, order, order, leaves, leaves, dl, handle=hm)
+        multi = pf.particles.copy(order="F")
+        pf.particles[:] = before
+        vpm.Estr_fmm(pf, order, order, leaves, leaves, dl, handle=h1)
+        assert np.array_equal(multi, pf.particles)
+        assert relerr(multi[39:42], ref[39:42]) < TOL_FP64
+        # zeta_fmm
+        pf.particles[:] = before
+        ref = before.copy(order="F")
+        oracle.zeta_leafpairs(ref, order, leaves, dl, "gaussianerf")
+        vpm.zeta_fmm(pf, order, leaves, dl, handle=hm)
+        multi = pf.particles.copy(order="F")
+        pf.particles[:] = before
+        vpm.zeta_fmm(pf, order, leaves, dl, handle=h1)
+        assert np.array_equal(multi, pf.particles)
+        assert relerr(multi[15:18], ref[15:18]) < TOL_FP64
+    finally:
+        hm.close()
+        h1.close()
+
+
 @pytest.mark.parametrize("sfs", [False, "dynamic"])
 def test_resident_step_multi_gpu(vpm, sfs):
     """vpm_field_step with the mirror replicated on every device of the handle: targets sharded,
