@@ -187,7 +187,7 @@ __global__ void prep_sfs_records(SrcView src, const double *__restrict__ J, int6
 // i.e. the reference's aux/r^3 after cancelling dg/(sigma r) against 3g/r^2
 // analytically: no 1/r, no cancellation, regular at r = 0, and the singular
 // kernel is recovered for sigma -> 0.  b comes out of the same FMA chain that
-// forms r^2 (13 FP64 instructions for A and B instead of 6 divisions + 2 sqrt).
+// forms r^2 (12 FP64 instructions for A and B instead of 6 divisions + 2 sqrt).
 // The reference skips r2 == 0 (src/FLOWVPM_fmm.jl:118); c and dx vanish there so
 // only the W term needs A masked (done by the caller on the integer pipe).
 __device__ __forceinline__ void ab_winck(double b, double q1, double q2, double &A, double &B) {
@@ -195,9 +195,8 @@ __device__ __forceinline__ void ab_winck(double b, double q1, double q2, double 
   double y2 = y * y;
   double y3 = y2 * y;
   double y5 = y3 * y2;
-  double y7 = y5 * y2;
   A = fma(q1, y5, y3);
-  B = fma(q2, y7, -3.0 * y5);
+  B = fma(q2, y2, -3.0) * y5;  // -3 y^5 + q2 y^7 without forming y^7: 12 FP64 instructions for A and B
 }
 
 // singular (src/FLOWVPM_kernel.jl:48): g = 1, dg = 0  ->  A = 1/r^3, B = -3/r^5
@@ -324,7 +323,7 @@ __device__ __forceinline__ void load_rec(const double2 *__restrict__ tile, int j
 // acc[0..2] U, acc[3..10] J without its last diagonal entry (c is orthogonal to dx,
 // so sum_i J_ii == 0 and J33 is rebuilt as -(J11 + J22) when the sums are
 // finished), acc[11..13] W = sum A G' (the Kronecker-delta term, folded into J at
-// the end).  FP64-pipe instructions per pair: 41 (winckelmans), 38 (singular).
+// the end).  FP64-pipe instructions per pair: 40 (winckelmans), 38 (singular).
 template <int K, int T, int UNROLL, bool CONST = false>
 __device__ __forceinline__ void uj_tile(const double2 *__restrict__ tile, int n,
                                         const double (&tx)[T], const double (&ty)[T],
