@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + SOURCES + ["-ldl"]
+           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + SOURCES + ["-ldl", "-lpthread"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     # the image exports CC/CXX wrappers that lack libgomp specs; nvcc only needs a host g++
