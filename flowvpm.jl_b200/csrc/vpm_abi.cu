@@ -1068,40 +1068,58 @@ int tree_build(vpm_handle *h, const double *d_P, int64_t ld, int osig, int64_t n
   const double vol = ext[0] * ext[1] * ext[2];
   g.h = std::pow(vol * ((double)ncrit / 2.0) / (double)np, 1.0 / 3.0);
   if (!(g.h > 0.0) || !std::isfinite(g.h)) g.h = 1.0;
-  double ncell_d = 1.0;
-  for (int a = 0; a < 3; ++a) {
-    const double c = std::max(1.0, std::ceil(ext[a] / g.h));
-    g.dims[a] = (int64_t)c;
-    ncell_d *= c;
-  }
-  if (ncell_d > 2.0e9) return fail(h, VPM_EINVAL, "%s: %.3g grid cells (field too anisotropic for ncrit = %lld)", fn, ncell_d, (long long)ncrit);
   g.theta = theta;
-  const int64_t ncell = g.dims[0] * g.dims[1] * g.dims[2];
-  TRY(ensure(h, d.scr2, (size_t)ncell * 4 + 64));
-  int32_t *cell_to_leaf = (int32_t *)d.scr2.p;
-  const int key_bits = std::max(1, (int)std::ceil(std::log2((double)std::max<int64_t>(ncell, 2))));
+  auto dims_of = [&](double hh, int64_t dims[3]) {
+    double ncell_d = 1.0;
+    for (int a = 0; a < 3; ++a) {
+      const double c = std::max(1.0, std::ceil(ext[a] / hh));
+      dims[a] = (int64_t)std::min(c, 4.0e18);
+      ncell_d *= c;
+    }
+    return ncell_d;
+  };
+  if (dims_of(g.h, g.dims) > 1.0e9)
+    return fail(h, VPM_EINVAL, "%s: too many grid cells (field too anisotropic for ncrit = %lld)", fn, (long long)ncrit);
   size_t tmp = 0, t1 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, t1, (const int64_t *)nullptr, (int64_t *)nullptr, (const int64_t *)nullptr,
-                                  (int64_t *)nullptr, np, 0, key_bits, st);
+                                  (int64_t *)nullptr, np, 0, 64, st);
   tmp = std::max(tmp, t1);
   cub::DeviceScan::InclusiveSum(nullptr, t1, rank, rank, np, st); tmp = std::max(tmp, t1);
   cub::DeviceScan::ExclusiveSum(nullptr, t1, cnt, ofs, np, st); tmp = std::max(tmp, t1);
   TRY(ensure(h, d.cubtmp, tmp + 16));
-
-  tree_keys_kernel<<<blocks_for(np, 256), 256, 0, st>>>(d_P, ld, np, g, keys, idx0);
-  t1 = d.cubtmp.cap;
-  CK(h, cub::DeviceRadixSort::SortPairs(d.cubtmp.p, t1, (const int64_t *)keys, skeys, (const int64_t *)idx0, sidx, np, 0,
-                                        key_bits, st));
-  tree_heads_kernel<<<blocks_for(np, 256), 256, 0, st>>>(skeys, np, rank);
-  t1 = d.cubtmp.cap;
-  CK(h, cub::DeviceScan::InclusiveSum(d.cubtmp.p, t1, rank, rank, np, st));
+  // The first cell size assumes the field fills its bounding box.  Fields that do not (rings,
+  // jets) leave most cells empty and the occupied ones overfull: shrink the cells by the
+  // cube root of the overfill and sort again (at most twice; a sort is ~1 ms per million).
+  int64_t nl = 0, ncell = 0;
+  for (int iter = 0;; ++iter) {
+    ncell = g.dims[0] * g.dims[1] * g.dims[2];
+    const int key_bits = std::max(1, (int)std::ceil(std::log2((double)std::max<int64_t>(ncell, 2))));
+    tree_keys_kernel<<<blocks_for(np, 256), 256, 0, st>>>(d_P, ld, np, g, keys, idx0);
+    t1 = d.cubtmp.cap;
+    CK(h, cub::DeviceRadixSort::SortPairs(d.cubtmp.p, t1, (const int64_t *)keys, skeys, (const int64_t *)idx0, sidx, np,
+                                          0, key_bits, st));
+    tree_heads_kernel<<<blocks_for(np, 256), 256, 0, st>>>(skeys, np, rank);
+    t1 = d.cubtmp.cap;
+    CK(h, cub::DeviceScan::InclusiveSum(d.cubtmp.p, t1, rank, rank, np, st));
+    h->launches += 4;
+    u64 nl64 = 0;
+    CK(h, cudaMemcpyAsync(&nl64, rank + (np - 1), 8, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    nl = (int64_t)nl64;
+    const double occ = (double)np / (double)nl;
+    if (iter >= 2 || occ <= 0.75 * (double)ncrit) break;
+    const double h2 = g.h * std::pow(((double)ncrit / 2.0) / occ, 1.0 / 3.0);
+    int64_t dims2[3];
+    const double ncell2 = dims_of(h2, dims2);
+    if (!(h2 > 0.0) || ncell2 > 1.0e9 || ncell2 > 64.0 * (double)np + 4096.0) break;
+    g.h = h2;
+    for (int a = 0; a < 3; ++a) g.dims[a] = dims2[a];
+  }
+  TRY(ensure(h, d.scr2, (size_t)ncell * 4 + 64));
+  int32_t *cell_to_leaf = (int32_t *)d.scr2.p;
   tree_fill_i32_kernel<<<blocks_for(ncell, 256), 256, 0, st>>>(cell_to_leaf, ncell, -1);
   tree_leaves_kernel<<<blocks_for(np, 256), 256, 0, st>>>(skeys, rank, np, lbegin, lend, lkey, cell_to_leaf);
-  h->launches += 6;
-  u64 nl64 = 0;
-  CK(h, cudaMemcpyAsync(&nl64, rank + (np - 1), 8, cudaMemcpyDeviceToHost, st));
-  CK(h, cudaStreamSynchronize(st));
-  const int64_t nl = (int64_t)nl64;
+  h->launches += 2;
   tree_spheres_kernel<<<blocks_for(nl * 32, 256), 256, 0, st>>>(d_P, ld, osig, sidx, lbegin, lend, nl, ctr, rad, bb);
   h->launches++;
   CK(h, cudaMemcpyAsync(hb, bb, sizeof hb, cudaMemcpyDeviceToHost, st));
@@ -1113,6 +1131,15 @@ int tree_build(vpm_handle *h, const double *d_P, int64_t ld, int osig, int64_t n
   int reach = (int)std::min(reach_d, 1.0e6);
   // no leaf is further than the grid itself
   reach = (int)std::min<int64_t>(reach, std::max(std::max(g.dims[0], g.dims[1]), g.dims[2]));
+  {
+    // the stencil search costs nl * prod_a min(2 reach + 1, dims_a) MAC tests: refuse fields whose
+    // leaf radii (core sizes) are so large against the cell size that this would run for minutes
+    double cand = (double)nl;
+    for (int a = 0; a < 3; ++a) cand *= (double)std::min<int64_t>(2 * (int64_t)reach + 1, 2 * g.dims[a] - 1);
+    if (cand > 1.0e11)
+      return fail(h, VPM_EINVAL, "%s: %.2g leaf-pair tests (largest leaf radius %.3g against cell size %.3g): "
+                  "core sizes too large for ncrit = %lld, use a larger ncrit", fn, cand, rmax, g.h, (long long)ncrit);
+  }
   tree_list_kernel<0><<<blocks_for(nl * 32, 256), 256, 0, st>>>(g, reach, lkey, cell_to_leaf, ctr, rad, nl, cnt, nullptr,
                                                             nullptr, nullptr);
   t1 = d.cubtmp.cap;

@@ -8,7 +8,8 @@ work) and (ii) that ANY valid list evaluated by the near-field kernels equals th
 fmm.direct! arithmetic over the same list (tests/test_tree_gpu.py).
 
 Recipe: uniform cell grid with mean occupancy ~ncrit/2 (thin directions padded to 1e-3 of the
-largest extent), stable sort by cell key, one leaf per occupied cell, leaf sphere = middle of
+largest extent; cells shrunk up to twice when the field does not fill its bounding box), stable
+sort by cell key, one leaf per occupied cell, leaf sphere = middle of
 the leaf's bounding box + largest distance + largest sigma, near-field list = leaf pairs failing
 the MAC (r_i + r_j) <= theta * d (theta = 0.4: src/FLOWVPM_particlefield.jl:28-36), emitted in
 (target, source) lexicographic order."""
@@ -17,7 +18,14 @@ import math
 import numpy as np
 
 
-def grid_of(X, ncrit):
+def _dims(ext, h):
+    c = np.maximum(1.0, np.ceil(ext / h))
+    return c.astype(np.int64), float(c[0] * c[1] * c[2])
+
+
+def grid_and_sort(X, ncrit):
+    """cell size, grid dimensions and the stable sort by cell key; the cells shrink (at most twice)
+    while the occupied ones hold more than 1.5 x the target ncrit/2 bodies on average"""
     N = X.shape[1]
     lo, hi = X.min(axis=1), X.max(axis=1)
     ext = hi - lo
@@ -27,8 +35,24 @@ def grid_of(X, ncrit):
     h = math.pow(vol * (ncrit / 2.0) / N, 1.0 / 3.0)
     if not (h > 0.0 and math.isfinite(h)):
         h = 1.0
-    dims = np.maximum(1, np.ceil(ext / h)).astype(np.int64)
-    return lo, h, dims
+    dims, _ = _dims(ext, h)
+    it = 0
+    while True:
+        cell = np.minimum(((X - lo[:, None]) / h).astype(np.int64), (dims - 1)[:, None])
+        key = (cell[0] * dims[1] + cell[1]) * dims[2] + cell[2]
+        order = np.argsort(key, kind="stable")
+        skey = key[order]
+        nl = 1 + int(np.count_nonzero(skey[1:] != skey[:-1]))
+        occ = N / nl
+        if it >= 2 or occ <= 0.75 * ncrit:
+            break
+        h2 = h * math.pow((ncrit / 2.0) / occ, 1.0 / 3.0)
+        dims2, ncell2 = _dims(ext, h2)
+        if not (h2 > 0.0) or ncell2 > 1.0e9 or ncell2 > 64.0 * N + 4096.0:
+            break
+        h, dims = h2, dims2
+        it += 1
+    return lo, h, dims, order, skey
 
 
 def build_leaf_lists(X, sigma, ncrit=64, theta=0.4):
@@ -36,11 +60,7 @@ def build_leaf_lists(X, sigma, ncrit=64, theta=0.4):
     X = np.asarray(X, dtype=np.float64)
     sigma = np.asarray(sigma, dtype=np.float64)
     N = X.shape[1]
-    lo, h, dims = grid_of(X, ncrit)
-    cell = np.minimum(((X - lo[:, None]) / h).astype(np.int64), (dims - 1)[:, None])
-    key = (cell[0] * dims[1] + cell[1]) * dims[2] + cell[2]
-    order = np.argsort(key, kind="stable")
-    skey = key[order]
+    lo, h, dims, order, skey = grid_and_sort(X, ncrit)
     uniq, begin = np.unique(skey, return_index=True)
     end = np.append(begin[1:], N)
     nl = len(uniq)
