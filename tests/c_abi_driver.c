@@ -11,6 +11,7 @@
 int main(int argc, char **argv) {
   const int64_t nf = 46, np = argc > 1 ? atoll(argv[1]) : 300;
   const int kernel = argc > 2 ? atoi(argv[2]) : VPM_KERNEL_WINCKELMANS;
+  const int mode = argc > 3 ? atoi(argv[3]) : 0; /* 0: vpm_uj_direct; 1: device leaf lists + near field */
   double *P = calloc((size_t)(nf * np), sizeof(double));
   if (!P) return 2;
   /* a deterministic helix of particles: no RNG so that the Python side can rebuild it */
@@ -26,8 +27,27 @@ int main(int argc, char **argv) {
   vpm_handle *h = NULL;
   int rc = vpm_create(&h, 1, NULL);
   if (rc != VPM_OK) { fprintf(stderr, "vpm_create: %d %s\n", rc, vpm_last_error(NULL)); return 3; }
-  rc = vpm_uj_direct(h, P, nf, np, kernel, VPM_FLAG_RESET | VPM_FLAG_RESET_SFS | VPM_FLAG_SFS | VPM_FLAG_TRANSPOSED);
-  if (rc != VPM_OK) { fprintf(stderr, "vpm_uj_direct: %d %s\n", rc, vpm_last_error(h)); return 4; }
+  if (mode == 1) {
+    /* f-3: tree + near-field list on the device, then the near-field half of UJ_fmm over them */
+    int64_t nl = 0, npairs = 0;
+    rc = vpm_uj_nearfield(h, P, nf, np, kernel, VPM_FLAG_RESET);
+    if (rc != VPM_ESTATE) { fprintf(stderr, "expected VPM_ESTATE before vpm_leaflists_build\n"); return 6; }
+    rc = vpm_leaflists_build(h, P, nf, np, 16, 0.4, &nl, &npairs);
+    if (rc != VPM_OK) { fprintf(stderr, "vpm_leaflists_build: %d %s\n", rc, vpm_last_error(h)); return 7; }
+    int64_t *sidx = malloc((size_t)np * 8), *lb = malloc((size_t)nl * 8), *le = malloc((size_t)nl * 8);
+    int32_t *pt = malloc((size_t)npairs * 4), *ps = malloc((size_t)npairs * 4);
+    rc = vpm_leaflists_get(h, sidx, lb, le, pt, ps);
+    if (rc != VPM_OK) { fprintf(stderr, "vpm_leaflists_get: %d %s\n", rc, vpm_last_error(h)); return 8; }
+    int64_t covered = 0;
+    for (int64_t l = 0; l < nl; ++l) covered += le[l] - lb[l];
+    printf("lists %lld %lld %lld\n", (long long)nl, (long long)npairs, (long long)covered);
+    free(sidx); free(lb); free(le); free(pt); free(ps);
+    rc = vpm_uj_nearfield(h, P, nf, np, kernel, VPM_FLAG_RESET);
+    if (rc != VPM_OK) { fprintf(stderr, "vpm_uj_nearfield: %d %s\n", rc, vpm_last_error(h)); return 9; }
+  } else {
+    rc = vpm_uj_direct(h, P, nf, np, kernel, VPM_FLAG_RESET | VPM_FLAG_RESET_SFS | VPM_FLAG_SFS | VPM_FLAG_TRANSPOSED);
+    if (rc != VPM_OK) { fprintf(stderr, "vpm_uj_direct: %d %s\n", rc, vpm_last_error(h)); return 4; }
+  }
   /* error path: an unknown kernel id must come back as a code with a message, not abort */
   rc = vpm_uj_direct(h, P, nf, np, 42, 0);
   if (rc != VPM_EINVAL || vpm_last_error(h)[0] == 0) { fprintf(stderr, "expected VPM_EINVAL\n"); return 5; }

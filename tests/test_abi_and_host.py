@@ -119,6 +119,24 @@ def test_leaf_lists_cover_all_near_pairs(vpm):
     assert all((j, i) in s for (i, j) in list(s)[:2000])  # MAC is symmetric
 
 
+def test_leaf_lists_refine_cells_for_sparse_fields(vpm):
+    """a ring fills a small part of its bounding box: the restated builder shrinks the cells until
+    the occupied ones hold about ncrit/2 bodies, and the lists stay complete and symmetric"""
+    r = vpm.fields.ring_field(Nphi=100, nc=3)
+    ll = leaflists.build_leaf_lists(r.get_X(), r.get_sigma(), ncrit=32, theta=0.4)
+    sizes = ll["leaf_end"] - ll["leaf_begin"]
+    assert sizes.sum() == r.np and 8 <= sizes.mean() <= 24
+    s = set(map(tuple, ll["direct_list"]))
+    assert all((i, i) in s for i in range(len(sizes))) and all((j, i) in s for (i, j) in s)
+    # every pair of bodies closer than the smaller of their core sizes is covered by the list
+    X, order = r.get_X(), ll["sort_index"]
+    leaf_of = np.empty(r.np, dtype=np.int64)
+    leaf_of[order] = np.repeat(np.arange(len(sizes)), sizes)
+    from scipy.spatial import cKDTree
+    for i, j in cKDTree(X.T).query_pairs(float(r.get_sigma().min())):
+        assert (leaf_of[i], leaf_of[j]) in s
+
+
 def test_sharding_bounds(vpm):
     from flowvpm_jl_b200 import sharding
     for n, w in ((10, 4), (1 << 20, 8), (7, 8), (0, 2)):
