@@ -324,13 +324,27 @@ __device__ __forceinline__ void load_rec(const double2 *__restrict__ tile, int j
 // so sum_i J_ii == 0 and J33 is rebuilt as -(J11 + J22) when the sums are
 // finished), acc[11..13] W = sum A G' (the Kronecker-delta term, folded into J at
 // the end).  FP64-pipe instructions per pair: 40 (winckelmans), 38 (singular).
-template <int K, int T, int UNROLL, bool CONST = false>
+// SPLIT (leaf-list kernels, warps with <= 16 live targets): the lanes of a warp form `nsplit`
+// groups that own the same targets and take the records j = phase, phase + nsplit, ... of the
+// tile; every lane runs the same trip count (the votes below need the whole warp) and a lane
+// past the end of the tile re-reads the last record with A = B = 0.  The groups' sums are
+// added by the caller with warp shuffles.
+template <int K, int T, int UNROLL, bool CONST = false, bool SPLIT = false>
 __device__ __forceinline__ void uj_tile(const double2 *__restrict__ tile, int n,
                                         const double (&tx)[T], const double (&ty)[T],
                                         const double (&tz)[T], double (&acc)[T][kAcc],
-                                        int shortcut, const double2 *__restrict__ gtab = nullptr) {
+                                        int shortcut, const double2 *__restrict__ gtab = nullptr,
+                                        int nsplit = 1, int phase = 0) {
+  const int trips = SPLIT ? (n + nsplit - 1) / nsplit : n;
 #pragma unroll UNROLL
-  for (int j = 0; j < n; ++j) {
+  for (int jj = 0; jj < trips; ++jj) {
+    int j = jj;
+    bool live = true;
+    if constexpr (SPLIT) {
+      j = jj * nsplit + phase;
+      live = j < n;
+      j = live ? j : n - 1;
+    }
     double sx, sy, sz, q0, gx, gy, gz, q1, q2, q3;
     load_rec<CONST>(tile, j, sx, sy, sz, q0, gx, gy, gz, q1, q2, q3);
 
@@ -389,6 +403,13 @@ __device__ __forceinline__ void uj_tile(const double2 *__restrict__ tile, int n,
 #pragma unroll
           for (int t = 0; t < T; ++t) ab_sing(r2[t], A[t], B[t]);
         }
+      }
+    }
+    if constexpr (SPLIT) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        A[t] = select_zero(!live, A[t]);
+        B[t] = select_zero(!live, B[t]);
       }
     }
 #pragma unroll

@@ -23,7 +23,12 @@ struct LeafCsr {
   const int64_t *sleaf_end;
 };
 
-// walks the source bodies of one target leaf tile by tile
+// Walks the source bodies of one target leaf tile by tile.  A tile is filled with up to `tile`
+// bodies taken in list order and may span several source leaves (small leaves -- ncrit ~ 64 means
+// ~30 bodies -- would otherwise make tiles of a quarter of their capacity, each paying a
+// barrier round trip and an exposed TMA latency).  seg(first, n, filled) is called for every
+// contiguous piece; the producer issues one bulk copy per piece, the consumers only need the
+// total.  The per-target summation order is the list order either way.
 struct LeafTileIter {
   int64_t li, le;    // position / end in csr_src
   int64_t cur, end;  // remaining sorted-body range of the current source leaf
@@ -32,19 +37,26 @@ struct LeafTileIter {
     le = c.csr_ptr[leaf + 1];
     cur = end = 0;
   }
-  // next tile [first, first+n) of at most `tile` bodies; n == 0 when the list is exhausted
-  __device__ __forceinline__ int next(const LeafCsr &c, int64_t &first, int tile) {
-    while (cur >= end) {
-      if (li >= le) return 0;
-      int s = c.csr_src[li++];
-      cur = c.sleaf_begin[s];
-      end = c.sleaf_end[s];
+  template <class F>
+  __device__ __forceinline__ int next(const LeafCsr &c, int tile, F seg) {
+    int filled = 0;
+    while (filled < tile) {
+      while (cur >= end) {
+        if (li >= le) return filled;
+        const int s = c.csr_src[li++];
+        cur = c.sleaf_begin[s];
+        end = c.sleaf_end[s];
+      }
+      int64_t n = end - cur;
+      if (n > tile - filled) n = tile - filled;
+      seg(cur, (int)n, filled);
+      cur += n;
+      filled += (int)n;
     }
-    first = cur;
-    int64_t n = end - cur;
-    if (n > tile) n = tile;
-    cur += n;
-    return (int)n;
+    return filled;
+  }
+  __device__ __forceinline__ int next(const LeafCsr &c, int tile) {
+    return next(c, tile, [](int64_t, int, int) {});
   }
 };
 
@@ -73,7 +85,14 @@ __global__ void __launch_bounds__(NT) uj_leaf_kernel(const LeafUjArgs a) {
   const int64_t tb = a.csr.tleaf_begin[leaf] + a.csr.wi_off[blockIdx.x];
   int64_t te = a.csr.tleaf_end[leaf];
   if (te > tb + NT) te = tb + NT;
-  const int64_t i = tb + tid;
+  // A warp with <= 16 live targets (the tail of a leaf, or a whole small leaf: CPU-style trees
+  // have ncrit 10..50) would idle most of its lanes: its lanes form nsplit groups that own the
+  // same targets and share the sources of every tile between them (uj_tile<SPLIT>).
+  const int wbase = (tid >> 5) << 5, lane = tid & 31;
+  const int64_t wlive = te - (tb + wbase);  // live targets of this warp (may be <= 0 when NT > 32)
+  const int nsplit = wlive > 16 ? 1 : wlive > 8 ? 2 : wlive > 4 ? 4 : 8;
+  const int glanes = 32 / nsplit, phase = lane / glanes;
+  const int64_t i = tb + wbase + (lane % glanes);
   const bool valid = i < te;
   const double *p = a.tpos + (valid ? i : te - 1) * a.tld;
   double tx[1] = {p[0]}, ty[1] = {p[1]}, tz[1] = {p[2]};
@@ -93,30 +112,37 @@ __global__ void __launch_bounds__(NT) uj_leaf_kernel(const LeafUjArgs a) {
   cons.init(a.csr, leaf);
   int issued = 0;
   auto issue = [&]() {
-    int64_t first;
-    int n = prod.next(a.csr, first, TILE);
+    LeafTileIter dry = prod;  // total first (the barrier wants the byte count up front), copies second
+    const int n = dry.next(a.csr, TILE);
     if (n == 0) return;
-    uint32_t bytes = (uint32_t)n * kRec * sizeof(double);
-    int st = issued % kStages;
-    mbar_expect_tx(&full[st], bytes);
-    tma_bulk_g2s(&tiles[st][0], a.rec + first * kRec, bytes, &full[st]);
+    const int st = issued % kStages;
+    mbar_expect_tx(&full[st], (uint32_t)n * kRec * sizeof(double));
+    prod.next(a.csr, TILE, [&](int64_t first, int cnt, int filled) {
+      tma_bulk_g2s(&tiles[st][filled * kRec], a.rec + first * kRec, (uint32_t)cnt * kRec * sizeof(double), &full[st]);
+    });
     ++issued;
   };
   if (tid == 0)
     for (int s = 0; s < kStages; ++s) issue();
 
   for (int it = 0;; ++it) {
-    int64_t first;
-    const int n = cons.next(a.csr, first, TILE);
+    const int n = cons.next(a.csr, TILE);
     if (n == 0) break;
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
-    uj_tile<K, 1, 2>(reinterpret_cast<const double2 *>(&tiles[st][0]), n, tx, ty, tz, acc, a.shortcut, gtab);
+    const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
+    if (nsplit == 1) uj_tile<K, 1, 2>(tile, n, tx, ty, tz, acc, a.shortcut, gtab);
+    else uj_tile<K, 1, 2, false, true>(tile, n, tx, ty, tz, acc, a.shortcut, gtab, nsplit, phase);
     __syncthreads();
     if (tid == 0) issue();
   }
+  // add the groups' sums (fixed order: deterministic); afterwards every group holds the total
+  for (int o = glanes; o < 32; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc[0][k] += __shfl_xor_sync(0xffffffffu, acc[0][k], o);
+  }
 
-  if (valid) {
+  if (valid && phase == 0) {
     double U[3], J[9];
     finish_sums(acc[0], U, J);
     double *o = a.out + i * a.tld;
@@ -186,21 +212,22 @@ __global__ void __launch_bounds__(NT) sfs_leaf_kernel(const LeafSfsArgs a) {
   cons.init(a.csr, leaf);
   int issued = 0;
   auto issue = [&]() {
-    int64_t first;
-    int n = prod.next(a.csr, first, TILE);
+    LeafTileIter dry = prod;
+    const int n = dry.next(a.csr, TILE);
     if (n == 0) return;
-    uint32_t bytes = (uint32_t)n * kSfsRec * sizeof(double);
-    int st = issued % kStages;
-    mbar_expect_tx(&full[st], bytes);
-    tma_bulk_g2s(&tiles[st][0], a.rec + first * kSfsRec, bytes, &full[st]);
+    const int st = issued % kStages;
+    mbar_expect_tx(&full[st], (uint32_t)n * kSfsRec * sizeof(double));
+    prod.next(a.csr, TILE, [&](int64_t first, int cnt, int filled) {
+      tma_bulk_g2s(&tiles[st][filled * kSfsRec], a.rec + first * kSfsRec, (uint32_t)cnt * kSfsRec * sizeof(double),
+                   &full[st]);
+    });
     ++issued;
   };
   if (tid == 0)
     for (int s = 0; s < kStages; ++s) issue();
 
   for (int it = 0;; ++it) {
-    int64_t first;
-    const int n = cons.next(a.csr, first, TILE);
+    const int n = cons.next(a.csr, TILE);
     if (n == 0) break;
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
