@@ -639,13 +639,21 @@ __global__ void uj_finish_kernel(const UjFinishArgs a) {
 // MODE 0: SFS stretching term (Estr_direct).  MODE 1: basis-function sum
 // acc += zeta(r/sigma_s)/sigma_s^3 * Gamma_s  (zeta_direct, src/FLOWVPM_viscous.jl:488-515).
 constexpr int MODE_SFS = 0, MODE_ZETA = 1;
-template <int K, int T, int MODE = MODE_SFS>
+template <int K, int T, int MODE = MODE_SFS, bool SPLIT = false>
 __device__ __forceinline__ void sfs_tile(const double2 *__restrict__ tile, int n,
                                          const double (&tx)[T], const double (&ty)[T],
                                          const double (&tz)[T], const double (&JT)[T][9],
-                                         double (&acc)[T][3], int shortcut) {
+                                         double (&acc)[T][3], int shortcut, int nsplit = 1, int phase = 0) {
+  const int trips = SPLIT ? (n + nsplit - 1) / nsplit : n;  // SPLIT: see uj_tile
 #pragma unroll 2
-  for (int j = 0; j < n; ++j) {
+  for (int jj = 0; jj < trips; ++jj) {
+    int j = jj;
+    bool live = true;
+    if constexpr (SPLIT) {
+      j = jj * nsplit + phase;
+      live = j < n;
+      j = live ? j : n - 1;
+    }
     const double2 v0 = tile[j * 6 + 0];
     const double2 v1 = tile[j * 6 + 1];
     const double sx = v0.x, sy = v0.y, sz = v1.x, q0 = v1.y;
@@ -670,6 +678,7 @@ __device__ __forceinline__ void sfs_tile(const double2 *__restrict__ tile, int n
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         double w = sfs_weight<K>(r2[t], q0, q1);
+        if constexpr (SPLIT) w = select_zero(!live, w);
         acc[t][0] = fma(w, gx, acc[t][0]);
         acc[t][1] = fma(w, gy, acc[t][1]);
         acc[t][2] = fma(w, gz, acc[t][2]);
@@ -685,6 +694,7 @@ __device__ __forceinline__ void sfs_tile(const double2 *__restrict__ tile, int n
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       double w = sfs_weight<K>(r2[t], q0, q1);
+      if constexpr (SPLIT) w = select_zero(!live, w);
       double S1 = __dsub_rn(row_dot(JT[t][0], JT[t][1], JT[t][2], gx, gy, gz), qs1);
       double S2 = __dsub_rn(row_dot(JT[t][3], JT[t][4], JT[t][5], gx, gy, gz), qs2);
       double S3 = __dsub_rn(row_dot(JT[t][6], JT[t][7], JT[t][8], gx, gy, gz), qs3);

@@ -182,7 +182,12 @@ __global__ void __launch_bounds__(NT) sfs_leaf_kernel(const LeafSfsArgs a) {
   const int64_t tb = a.csr.tleaf_begin[leaf] + a.csr.wi_off[blockIdx.x];
   int64_t te = a.csr.tleaf_end[leaf];
   if (te > tb + NT) te = tb + NT;
-  const int64_t i = tb + tid;
+  // sparse warps share the sources of a tile between lane groups, as in uj_leaf_kernel
+  const int wbase = (tid >> 5) << 5, lane = tid & 31;
+  const int64_t wlive = te - (tb + wbase);
+  const int nsplit = wlive > 16 ? 1 : wlive > 8 ? 2 : wlive > 4 ? 4 : 8;
+  const int glanes = 32 / nsplit, phase = lane / glanes;
+  const int64_t i = tb + wbase + (lane % glanes);
   const bool valid = i < te;
   const int64_t c = a.tindex[valid ? i : te - 1];
   const double *p = a.tpos + c * a.tld;
@@ -231,13 +236,18 @@ __global__ void __launch_bounds__(NT) sfs_leaf_kernel(const LeafSfsArgs a) {
     if (n == 0) break;
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
-    sfs_tile<K, 1, MODE>(reinterpret_cast<const double2 *>(&tiles[st][0]), n, tx, ty, tz, JT, acc,
-                         a.shortcut);
+    const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
+    if (nsplit == 1) sfs_tile<K, 1, MODE>(tile, n, tx, ty, tz, JT, acc, a.shortcut);
+    else sfs_tile<K, 1, MODE, true>(tile, n, tx, ty, tz, JT, acc, a.shortcut, nsplit, phase);
     __syncthreads();
     if (tid == 0) issue();
   }
+  for (int o = glanes; o < 32; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[0][k] += __shfl_xor_sync(0xffffffffu, acc[0][k], o);
+  }
 
-  if (valid) {
+  if (valid && phase == 0) {
     double *o = a.out + (a.obody ? i : c) * a.old + a.orow;
     o[0] += acc[0][0];
     o[1] += acc[0][1];
