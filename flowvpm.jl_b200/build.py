@@ -7,7 +7,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libvpm_cuda.so")
 SOURCES = ["vpm_abi.cu"]
-HEADERS = ["vpm_kernels.cuh", "vpm_kernels_f32.cuh", "vpm_leaf.cuh", "vpm_csr.cuh", "vpm_tree.cuh", "vpm_math.cuh", "vpm_coeffs.cuh", "vpm_step.cuh",
+HEADERS = ["vpm_kernels.cuh", "vpm_kernels_f32.cuh", "vpm_leaf.cuh", "vpm_csr.cuh", "vpm_tree.cuh", "vpm_math.cuh",
+           "vpm_coeffs.cuh", "vpm_step.cuh",
+           # host side: parts of the single translation unit vpm_abi.cu
+           "vpm_host_base.cuh", "vpm_host_sweeps.cuh", "vpm_host_hook1.cuh", "vpm_host_multi.cuh",
+           "vpm_host_lists.cuh", "vpm_host_field.cuh", "vpm_abi_core.cuh", "vpm_abi_lists.cuh",
+           "vpm_abi_field.cuh", "vpm_abi_instr.cuh",
            os.path.join("..", "..", "include", "vpm_cuda.h")]
 
 

@@ -1,0 +1,380 @@
+// vpm_abi_core.cuh -- exports: lifetime, Hook 1 (UJ slot), Hook 2 (fmm.direct! buffers), device-pointer entry points.
+// Part of the single translation unit vpm_abi.cu (included there in order; not a standalone header).
+#pragma once
+extern "C" {
+
+
+int vpm_abi_version(void) { return VPM_ABI_VERSION; }
+
+const char *vpm_last_error(const vpm_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vpm_num_devices(const vpm_handle *h) { return h ? (int)h->devs.size() : 0; }
+
+int vpm_create(vpm_handle **out, int n_gpus, const int *device_ids) {
+  if (!out) return fail(nullptr, VPM_EINVAL, "vpm_create: out is NULL");
+  *out = nullptr;
+  if (n_gpus < 1 || n_gpus > 64) return fail(nullptr, VPM_EINVAL, "vpm_create: n_gpus=%d", n_gpus);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count < 1) {
+    cudaGetLastError();
+    return fail(nullptr, VPM_ENODEV, "vpm_create: no usable CUDA device (%s); there is no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  vpm_handle *h = new (std::nothrow) vpm_handle();
+  if (!h) return fail(nullptr, VPM_ENOMEM, "vpm_create: out of host memory");
+  for (int g = 0; g < n_gpus; ++g) {
+    Dev d;
+    d.id = device_ids ? device_ids[g] : g;
+    if (d.id < 0 || d.id >= count) {
+      int rc = fail(nullptr, VPM_ENODEV, "vpm_create: device %d not present (%d visible)", d.id, count);
+      delete h;
+      return rc;
+    }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(d.id) != cudaSuccess || cudaGetDeviceProperties(&prop, d.id) != cudaSuccess) {
+      int rc = fail(nullptr, VPM_ECUDA, "vpm_create: cannot open device %d: %s", d.id,
+                    cudaGetErrorString(cudaGetLastError()));
+      delete h;
+      return rc;
+    }
+    if (prop.major < 10) {
+      int rc = fail(nullptr, VPM_ENODEV,
+                    "vpm_create: device %d is sm_%d%d; libvpm_cuda is built for sm_100a only", d.id,
+                    prop.major, prop.minor);
+      delete h;
+      return rc;
+    }
+    d.sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) {
+      int rc = fail(nullptr, VPM_ECUDA, "vpm_create: stream: %s", cudaGetErrorString(cudaGetLastError()));
+      delete h;
+      return rc;
+    }
+    for (auto &ev : d.ev) cudaEventCreate(&ev);
+    h->devs.push_back(d);
+  }
+  *out = h;
+  return VPM_OK;
+}
+
+int vpm_destroy(vpm_handle *h) {
+  if (!h) return VPM_OK;
+  for (auto &p : h->pinned) cudaHostUnregister(p.first);
+  if (g_nccl.comm_destroy)
+    for (void *c : h->comms) if (c) g_nccl.comm_destroy(c);
+  for (Dev &d : h->devs) {
+    cudaSetDevice(d.id);
+    cudaStreamSynchronize(d.stream);
+    for (Buf *b : {&d.in7, &d.stat, &d.res18, &d.sfs3, &d.rec, &d.srec, &d.partial, &d.tbuf, &d.sbuf,
+                   &d.ibuf, &d.jbuf, &d.fld, &d.scr, &d.scr2, &d.cubtmp, &d.tree, &d.tlist})
+      if (b->p) cudaFree(b->p);
+    for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
+    if (d.stream) cudaStreamDestroy(d.stream);
+  }
+  if (h->h_stat) cudaFreeHost(h->h_stat);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  cudaGetLastError();
+  delete h;
+  return VPM_OK;
+}
+
+int vpm_pin_host(vpm_handle *h, void *ptr, size_t bytes) {
+  if (!h || !ptr || bytes == 0) return fail(h, VPM_EINVAL, "vpm_pin_host: bad argument");
+  CK(h, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  h->pinned.push_back({ptr, bytes});
+  return VPM_OK;
+}
+
+int vpm_unpin_host(vpm_handle *h, void *ptr) {
+  if (!h || !ptr) return fail(h, VPM_EINVAL, "vpm_unpin_host: bad argument");
+  auto it = std::find_if(h->pinned.begin(), h->pinned.end(), [ptr](const std::pair<void *, size_t> &r) { return r.first == ptr; });
+  if (it == h->pinned.end()) return fail(h, VPM_EINVAL, "vpm_unpin_host: pointer was not pinned by this handle");
+  CK(h, cudaHostUnregister(ptr));
+  h->pinned.erase(it);
+  return VPM_OK;
+}
+
+static int check_field(vpm_handle *h, const char *fn, const void *P, int64_t nf, int64_t np, int kernel) {
+  if (!h) return VPM_EINVAL;
+  if (np < 0 || nf < MIN_FIELDS) return fail(h, VPM_EINVAL, "%s: need nfields >= 43 and np >= 0 (got %lld, %lld)", fn, (long long)nf, (long long)np);
+  if (!P && np > 0) return fail(h, VPM_EINVAL, "%s: particles is NULL", fn);
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "%s: unknown kernel_id %d", fn, kernel);
+  return VPM_OK;
+}
+
+int vpm_uj_direct(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel, int flags) {
+  TRY(check_field(h, "vpm_uj_direct", P, nf, np, kernel));
+  if (h->devs.size() > 1) return uj_direct_multi(h, P, nf, np, kernel, flags);
+  Dev &d = h->devs[0];
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  CK(h, cudaEventRecord(d.ev[0], d.stream));
+  const bool reset = flags & VPM_FLAG_RESET;
+  const bool sfs_rows = (flags & VPM_FLAG_SFS) || (flags & VPM_FLAG_RESET_SFS);
+  bool has_static = false;
+  // previous SFS rows are needed unless every one of them is overwritten
+  TRY(h1_upload(h, d, P, nf, np, !reset, sfs_rows, has_static));
+  TRY(h1_eval(h, d, np, kernel, flags, has_static, !reset || has_static));
+  TRY(h1_download(h, d, P, nf, np, flags));
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+
+int vpm_uj_direct_f32(vpm_handle *h, float *P, int64_t nf, int64_t np, int kernel, int flags) {
+  TRY(check_field(h, "vpm_uj_direct_f32", P, nf, np, kernel));
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  CK(h, cudaEventRecord(d.ev[0], st));
+  const bool reset = flags & VPM_FLAG_RESET;
+  const bool sfs_rows = (flags & VPM_FLAG_SFS) || (flags & VPM_FLAG_RESET_SFS);
+  const size_t n = (size_t)std::max<int64_t>(np, 1);
+  TRY(ensure(h, d.in7, n * 7 * sizeof(double)));
+  TRY(ensure(h, d.res18, n * RES_ROWS * sizeof(double)));
+  TRY(ensure(h, d.sfs3, n * 3 * sizeof(double)));
+  TRY(ensure(h, d.jbuf, n * (7 + RES_ROWS + 3) * sizeof(float) + 64));
+  float *f_in7 = (float *)d.jbuf.p, *f_res = f_in7 + n * 7, *f_sfs = f_res + n * RES_ROWS;
+  bool has_static = false;
+  has_static = any_static(P, nf, np);
+  const bool prior = !reset || has_static;
+  if (np > 0) {
+    CK(h, cudaMemcpy2DAsync(f_in7, 7 * sizeof(float), P, nf * sizeof(float), 7 * sizeof(float), (size_t)np,
+                            cudaMemcpyHostToDevice, st));
+    cvt_f32_to_f64_kernel<<<blocks_for(np * 7, 256), 256, 0, st>>>(f_in7, (double *)d.in7.p, np * 7);
+    h->launches++;
+    if (has_static) {
+      if (h->h_stat_cap < (size_t)np) {
+        if (h->h_stat) cudaFreeHost(h->h_stat);
+        h->h_stat = nullptr; h->h_stat_cap = 0;
+        CK(h, cudaMallocHost((void **)&h->h_stat, (size_t)np * sizeof(double)));
+        h->h_stat_cap = (size_t)np;
+      }
+      for (int64_t i = 0; i < np; ++i) h->h_stat[i] = (double)P[nf * i + R_STATIC];
+      TRY(ensure(h, d.stat, (size_t)np * sizeof(double)));
+      CK(h, cudaMemcpyAsync(d.stat.p, h->h_stat, (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (prior) {
+      CK(h, cudaMemcpy2DAsync(f_res, RES_ROWS * sizeof(float), P + R_U, nf * sizeof(float),
+                              RES_ROWS * sizeof(float), (size_t)np, cudaMemcpyHostToDevice, st));
+      cvt_f32_to_f64_kernel<<<blocks_for(np * RES_ROWS, 256), 256, 0, st>>>(f_res, (double *)d.res18.p, np * RES_ROWS);
+      h->launches++;
+    }
+    if (sfs_rows) {
+      CK(h, cudaMemcpy2DAsync(f_sfs, 3 * sizeof(float), P + R_SFS, nf * sizeof(float), 3 * sizeof(float),
+                              (size_t)np, cudaMemcpyHostToDevice, st));
+      cvt_f32_to_f64_kernel<<<blocks_for(np * 3, 256), 256, 0, st>>>(f_sfs, (double *)d.sfs3.p, np * 3);
+      h->launches++;
+    }
+    CK(h, cudaGetLastError());
+  }
+  TRY(h1_eval(h, d, np, kernel, flags, has_static, prior));
+  if (np > 0) {
+    cvt_f64_to_f32_kernel<<<blocks_for(np * RES_ROWS, 256), 256, 0, st>>>((const double *)d.res18.p, f_res, np * RES_ROWS);
+    h->launches++;
+    CK(h, cudaMemcpy2DAsync(P + R_U, nf * sizeof(float), f_res, RES_ROWS * sizeof(float),
+                            RES_ROWS * sizeof(float), (size_t)np, cudaMemcpyDeviceToHost, st));
+    if (sfs_rows) {
+      cvt_f64_to_f32_kernel<<<blocks_for(np * 3, 256), 256, 0, st>>>((const double *)d.sfs3.p, f_sfs, np * 3);
+      h->launches++;
+      CK(h, cudaMemcpy2DAsync(P + R_SFS, nf * sizeof(float), f_sfs, 3 * sizeof(float), 3 * sizeof(float),
+                              (size_t)np, cudaMemcpyDeviceToHost, st));
+    }
+    CK(h, cudaGetLastError());
+  }
+  CK(h, cudaEventRecord(d.ev[5], st));
+  CK(h, cudaStreamSynchronize(st));
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+int vpm_upload_state(vpm_handle *h, const double *P, int64_t nf, int64_t np) {
+  TRY(check_field(h, "vpm_upload_state", P, nf, np, 0));
+  Dev &d = h->devs[0];
+  CK(h, cudaSetDevice(d.id));
+  CK(h, cudaEventRecord(d.ev[0], d.stream));
+  bool has_static = false;
+  TRY(h1_upload(h, d, P, nf, np, true, true, has_static));
+  CK(h, cudaStreamSynchronize(d.stream));
+  h->np_resident = np;
+  h->resident_static = has_static;
+  h->resident_prior = true;
+  return VPM_OK;
+}
+
+int vpm_eval(vpm_handle *h, int kernel, int flags) {
+  if (!h) return VPM_EINVAL;
+  if (h->np_resident < 0) return fail(h, VPM_ESTATE, "vpm_eval: no resident state (call vpm_upload_state first)");
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "vpm_eval: unknown kernel_id %d", kernel);
+  Dev &d = h->devs[0];
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  CK(h, cudaEventRecord(d.ev[0], d.stream));
+  TRY(h1_eval(h, d, h->np_resident, kernel, flags, h->resident_static, true));
+  CK(h, cudaEventRecord(d.ev[5], d.stream));
+  CK(h, cudaStreamSynchronize(d.stream));
+  h1_fill_timing(h, d);
+  return VPM_OK;
+}
+
+int vpm_download_results(vpm_handle *h, double *P, int64_t nf, int64_t np, int flags) {
+  TRY(check_field(h, "vpm_download_results", P, nf, np, 0));
+  if (h->np_resident != np) return fail(h, VPM_ESTATE, "vpm_download_results: np=%lld but %lld particles are resident", (long long)np, (long long)h->np_resident);
+  return h1_download(h, h->devs[0], P, nf, np, flags | VPM_FLAG_SFS);
+}
+
+int vpm_uj_direct_st(vpm_handle *h, const double *S, int64_t nfs, int64_t nps, double *Tg, int64_t nft,
+                     int64_t npt, int kernel) {
+  TRY(check_field(h, "vpm_uj_direct_st(source)", S, nfs, nps, kernel));
+  TRY(check_field(h, "vpm_uj_direct_st(target)", Tg, nft, npt, kernel));
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  if (npt == 0) return VPM_OK;
+  TRY(ensure(h, d.in7, (size_t)std::max<int64_t>(nps, 1) * 7 * sizeof(double)));
+  TRY(ensure(h, d.tbuf, (size_t)npt * 3 * sizeof(double)));
+  TRY(ensure(h, d.res18, (size_t)npt * RES_ROWS * sizeof(double)));
+  CK(h, cudaEventRecord(d.ev[0], st));
+  if (nps > 0)
+    TRY(h2d_rows(h, st, (double *)d.in7.p, S, nfs, 7, nps));
+  TRY(h2d_rows(h, st, (double *)d.tbuf.p, Tg, nft, 3, npt));
+  TRY(h2d_rows(h, st, (double *)d.res18.p, Tg + R_U, nft, RES_ROWS, npt));
+  CK(h, cudaEventRecord(d.ev[1], st));
+  SrcView src{(const double *)d.in7.p, 7, 0, 3, 6};
+  Plan plan;
+  TRY(uj_sweep(h, d, st, kernel, (const double *)d.tbuf.p, 3, npt, src, 0, nps, 0, plan));
+  CK(h, cudaEventRecord(d.ev[2], st));
+  UjFinishArgs f;
+  f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+  f.nt = npt; f.out = (double *)d.res18.p; f.ld = RES_ROWS; f.urow = RES_U; f.jrow = RES_J;
+  f.zrow0 = -1; f.zrow1 = -1; f.want_U = 1; f.want_J = 1; f.accumulate = 1; f.reset = 0;
+  f.stat = nullptr; f.sld = 1;
+  uj_finish_kernel<<<blocks_for(npt, 256), 256, 0, st>>>(f);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(d.ev[3], st));
+  CK(h, cudaEventRecord(d.ev[4], st));
+  CK(h, cudaMemcpy2DAsync(Tg + R_U, nft * sizeof(double), d.res18.p, RES_ROWS * sizeof(double),
+                          RES_ROWS * sizeof(double), (size_t)npt, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaEventRecord(d.ev[5], st));
+  CK(h, cudaStreamSynchronize(st));
+  h->timing.uj_pairs = nps * npt;
+  h->timing.sfs_pairs = 0;
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+int vpm_p2p_buffers(vpm_handle *h, double *tgt, int64_t ld, int64_t t0, int64_t t1, int row_pos,
+                    int row_grad, int row_hess, const double *src, int64_t s0, int64_t s1, int kernel,
+                    int want_U, int want_J) {
+  if (!h) return VPM_EINVAL;
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "vpm_p2p_buffers: unknown kernel_id %d", kernel);
+  if (t0 < 0 || t1 < t0 || s0 < 0 || s1 < s0 || ld < 3)
+    return fail(h, VPM_EINVAL, "vpm_p2p_buffers: bad ranges [%lld,%lld) [%lld,%lld) ld=%lld", (long long)t0, (long long)t1, (long long)s0, (long long)s1, (long long)ld);
+  if (row_pos < 0 || row_pos + 3 > ld || (want_U && (row_grad < 0 || row_grad + 3 > ld)) ||
+      (want_J && (row_hess < 0 || row_hess + 9 > ld)))
+    return fail(h, VPM_EINVAL, "vpm_p2p_buffers: row offsets outside the %lld-row target buffer", (long long)ld);
+  const int64_t nt = t1 - t0, ns = s1 - s0;
+  if (nt == 0 || ns == 0 || (!want_U && !want_J)) return VPM_OK;
+  if (!tgt || !src) return fail(h, VPM_EINVAL, "vpm_p2p_buffers: NULL buffer");
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  TRY(ensure(h, d.tbuf, (size_t)nt * ld * sizeof(double)));
+  TRY(ensure(h, d.sbuf, (size_t)ns * 8 * sizeof(double)));
+  CK(h, cudaEventRecord(d.ev[0], st));
+  CK(h, cudaMemcpyAsync(d.tbuf.p, tgt + t0 * ld, (size_t)nt * ld * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(h, cudaMemcpyAsync(d.sbuf.p, src + s0 * 8, (size_t)ns * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(h, cudaEventRecord(d.ev[1], st));
+  SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
+  Plan plan;
+  TRY(uj_sweep(h, d, st, kernel, (const double *)d.tbuf.p + row_pos, ld, nt, sv, 0, ns, 0, plan));
+  CK(h, cudaEventRecord(d.ev[2], st));
+  UjFinishArgs f;
+  f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+  f.nt = nt; f.out = (double *)d.tbuf.p; f.ld = ld; f.urow = row_grad; f.jrow = row_hess;
+  f.zrow0 = -1; f.zrow1 = -1; f.want_U = want_U; f.want_J = want_J; f.accumulate = 1; f.reset = 0;
+  f.stat = nullptr; f.sld = 1;
+  uj_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(d.ev[3], st));
+  CK(h, cudaEventRecord(d.ev[4], st));
+  CK(h, cudaMemcpyAsync(tgt + t0 * ld, d.tbuf.p, (size_t)nt * ld * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaEventRecord(d.ev[5], st));
+  CK(h, cudaStreamSynchronize(st));
+  h->timing.uj_pairs = nt * ns;
+  h->timing.sfs_pairs = 0;
+  h1_fill_timing(h, d);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
+int vpm_uj_device(vpm_handle *h, const double *d_src8, int64_t ns, int64_t t0, int64_t t1,
+                  double *d_out12, int kernel, int flags, void *stream) {
+  if (!h) return VPM_EINVAL;
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "vpm_uj_device: unknown kernel_id %d", kernel);
+  if (ns < 0 || t0 < 0 || t1 < t0 || t1 > ns) return fail(h, VPM_EINVAL, "vpm_uj_device: bad target range [%lld,%lld) of %lld", (long long)t0, (long long)t1, (long long)ns);
+  const int64_t nt = t1 - t0;
+  if (nt == 0) return VPM_OK;
+  if (!d_src8 || !d_out12) return fail(h, VPM_EINVAL, "vpm_uj_device: NULL device pointer");
+  Dev &d = h->devs[0];
+  cudaStream_t st = (cudaStream_t)stream;  // as given: NULL is CUDA's default stream
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  SrcView sv{d_src8, 8, 0, 4, 7};
+  Plan plan;
+  TRY(uj_sweep(h, d, st, kernel, d_src8 + t0 * 8, 8, nt, sv, 0, ns, flags, plan, true));
+  h->device_timing = 1;
+  UjFinishArgs f;
+  f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+  f.nt = nt; f.out = d_out12; f.ld = 12; f.urow = 0; f.jrow = 3;
+  f.zrow0 = -1; f.zrow1 = -1; f.want_U = 1; f.want_J = 1; f.accumulate = 0; f.reset = 0;
+  f.stat = nullptr; f.sld = 1;
+  uj_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  h->timing.uj_pairs = nt * ns;
+  h->timing.kernel_launches = h->launches;
+  return VPM_OK;
+}
+
+int vpm_sfs_device(vpm_handle *h, const double *d_src8, const double *d_J9, const double *d_static,
+                   int64_t ns, int64_t t0, int64_t t1, double *d_out3, int kernel, int flags,
+                   void *stream) {
+  if (!h) return VPM_EINVAL;
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "vpm_sfs_device: unknown kernel_id %d", kernel);
+  if (ns < 0 || t0 < 0 || t1 < t0 || t1 > ns) return fail(h, VPM_EINVAL, "vpm_sfs_device: bad target range");
+  const int64_t nt = t1 - t0;
+  if (nt == 0) return VPM_OK;
+  if (!d_src8 || !d_J9 || !d_out3) return fail(h, VPM_EINVAL, "vpm_sfs_device: NULL device pointer");
+  Dev &d = h->devs[0];
+  cudaStream_t st = (cudaStream_t)stream;  // as given: NULL is CUDA's default stream
+  h->launches = 0;
+  CK(h, cudaSetDevice(d.id));
+  SrcView sv{d_src8, 8, 0, 4, 7};
+  Plan plan;
+  TRY(sfs_sweep(h, d, st, kernel, d_src8 + t0 * 8, 8, d_J9 + t0 * 9, 9, nullptr, nt, sv, d_J9, 9, 0,
+                d_static, 1, nullptr, ns, flags, plan, true));
+  h->device_timing = 2;
+  SfsFinishArgs f;
+  f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+  f.nt = nt; f.tindex = nullptr; f.out = d_out3; f.ld = 3; f.row = 0; f.accumulate = 0; f.reset = 0;
+  f.filter_static = 0;  // static targets get an (ignored) value; the caller masks them
+  f.stat = nullptr; f.sld = 1;
+  sfs_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  h->timing.sfs_pairs = nt * ns;
+  h->timing.kernel_launches = h->launches;
+  return VPM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// vpm_host_base.cuh -- handle, per-device buffers, error plumbing of the C ABI host side.
+// Part of the single translation unit vpm_abi.cu (included there in order; not a standalone header).
+#pragma once
+namespace {
+
+thread_local std::string g_create_error;
+
+// rows of ParticleField.particles, 0-based (src/FLOWVPM_particlefield.jl:239-252)
+enum { R_X = 0, R_G = 3, R_SIGMA = 6, R_U = 9, R_W = 12, R_J = 15, R_PSE = 24, R_SFS = 39,
+       R_STATIC = 42, MIN_FIELDS = 43 };
+// rows inside the device-side result block res18 = particle rows 9..26
+enum { RES_ROWS = 18, RES_U = 0, RES_W = 3, RES_J = 6, RES_PSE = 15 };
+
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct Dev {
+  int id = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[10] = {};  // 0..5 phases of a call, 6..7 pair kernel, 8..9 cross-device ordering
+  Buf in7, stat, res18, sfs3, rec, srec, partial, tbuf, sbuf, ibuf, jbuf, fld, scr, scr2, cubtmp, tree, tlist;
+};
+
+struct Plan {
+  int T = 1;
+  int unroll = 2;
+  int nsplit = 1;
+  int tiles_per_split = 1;
+  int64_t pstride = 0;
+  dim3 grid;
+};
+
+}  // namespace
+
+struct vpm_handle {
+  std::vector<Dev> devs;
+  std::string err;
+  vpm_timing timing{};
+  int64_t np_resident = -1;   // particles held by the staged API
+  bool resident_static = false;
+  bool resident_prior = false;
+  double *h_stat = nullptr;   // pinned staging for compact static flags
+  size_t h_stat_cap = 0;
+  double *h_stage = nullptr;  // pinned staging for the strided rows of a pageable host matrix
+  size_t h_stage_cap = 0;     // (doubles)
+  std::vector<std::pair<void *, size_t>> pinned;  // ranges page-locked by vpm_pin_host
+  int launches = 0;
+  int64_t fld_nf = 0, fld_np = -1;  // device mirror of the whole particle matrix (vpm_field_*)
+  double fld_t_sgm = 0.0;           // CoreSpreading.t_sgm of the resident field
+  int device_timing = 0;  // 1/2: ev[6..7] bracket the last _device U/J / SFS pair kernel
+  // device-built leaf lists (vpm_leaflists_build), resident on device 0
+  int64_t tree_np = -1, tree_nl = 0, tree_npairs = 0;
+  // single-process multi-GPU (n_gpus > 1): NCCL communicators, one per device
+  void *nccl_lib = nullptr;
+  std::vector<void *> comms;
+};
+
+namespace {
+
+int fail(vpm_handle *h, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(h, call)                                                                        \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(h, e_ == cudaErrorMemoryAllocation ? VPM_ENOMEM : VPM_ECUDA,             \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define TRY(expr)            \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_ != VPM_OK) return rc_; \
+  } while (0)
+
+int ensure(vpm_handle *h, Buf &b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return VPM_OK;
+  if (b.p) CK(h, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = std::max<size_t>(bytes + bytes / 4, 4096);
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&b.p, want);
+  }
+  if (e != cudaSuccess)
+    return fail(h, VPM_ENOMEM, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+  b.cap = want;
+  return VPM_OK;
+}
+
+int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+bool valid_kernel(int k) { return k >= 0 && k <= 3; }
+
+}  // namespace

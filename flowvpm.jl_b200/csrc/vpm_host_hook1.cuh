@@ -1,0 +1,235 @@
+// vpm_host_hook1.cuh -- host <-> device row copies and the pieces of Hook 1 (UJ slot) on one device.
+// Part of the single translation unit vpm_abi.cu (included there in order; not a standalone header).
+#pragma once
+namespace {
+
+// ---- strided rows of the host matrix <-> compact device blocks ------------------------
+// A 2-D copy straight from/to pageable host memory is staged row by row by the driver
+// (measured: 37 ms up + 60 ms down for 262 144 particles against 2 + 1 ms from registered
+// memory).  If the caller has not page-locked the matrix (vpm_pin_host), the rows are
+// gathered into / scattered from one pinned staging block on the host instead, and the
+// transfers themselves are contiguous.
+bool host_is_pinned(const void *ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int ensure_stage(vpm_handle *h, size_t doubles) {
+  if (doubles <= h->h_stage_cap) return VPM_OK;
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  h->h_stage = nullptr;
+  h->h_stage_cap = 0;
+  const size_t want = doubles + doubles / 4;
+  CK(h, cudaMallocHost((void **)&h->h_stage, want * sizeof(double)));
+  h->h_stage_cap = want;
+  return VPM_OK;
+}
+
+// The O(N) host loops over the particle matrix (strided gathers / scatters, the static-flag
+// scan) are memory-latency bound on one core: at 2^24 particles they cost 0.1 s each.  Split
+// them over a few threads (chunks of >= 64 Ki particles; small fields stay on the caller's thread).
+template <class F>
+void parallel_chunks(int64_t n, F fn) {
+  const int64_t min_chunk = 1 << 16;
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, 8), n / min_chunk);
+  if (nt <= 1) { fn((int64_t)0, n); return; }
+  std::vector<std::thread> th;
+  const int64_t chunk = (n + nt - 1) / nt;
+  for (int t = 1; t < nt; ++t) th.emplace_back([=] { fn(t * chunk, std::min<int64_t>(n, (t + 1) * chunk)); });
+  fn((int64_t)0, std::min<int64_t>(n, chunk));
+  for (auto &t : th) t.join();
+}
+void gather_rows(double *dst, const double *P, int64_t nf, int row0, int nrows, int64_t np) {
+  parallel_chunks(np, [=](int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; ++i) memcpy(dst + i * nrows, P + nf * i + row0, (size_t)nrows * sizeof(double));
+  });
+}
+void scatter_rows(double *P, int64_t nf, int row0, int nrows, int64_t np, const double *src) {
+  parallel_chunks(np, [=](int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; ++i) memcpy(P + nf * i + row0, src + i * nrows, (size_t)nrows * sizeof(double));
+  });
+}
+// any particle with a non-zero static flag (row 43)?
+template <class R>
+bool any_static(const R *P, int64_t nf, int64_t np) {
+  std::atomic<bool> found{false};
+  parallel_chunks(np, [&](int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; ++i) {
+      if (P[nf * i + R_STATIC] != (R)0) { found.store(true, std::memory_order_relaxed); return; }
+      if ((i & 4095) == 0 && found.load(std::memory_order_relaxed)) return;
+    }
+  });
+  return found.load();
+}
+
+// Strided rows [row.., row+nrows) of `np` columns of a host matrix (leading dimension nf)
+// -> compact device block: a 2-D DMA.  (Measured alternative: page-locking the matrix as
+// mapped memory and gathering the rows with a kernel reading host memory directly gave the
+// same 13.8 GB/s for the 56-byte rows at N = 2^22, so the plain copy stays.)
+int h2d_rows(vpm_handle *h, cudaStream_t st, double *dst, const double *src, int64_t nf, int nrows, int64_t np) {
+  if (np <= 0) return VPM_OK;
+  CK(h, cudaMemcpy2DAsync(dst, nrows * sizeof(double), src, nf * sizeof(double), nrows * sizeof(double), (size_t)np,
+                          cudaMemcpyHostToDevice, st));
+  return VPM_OK;
+}
+
+// ---- Hook 1 pieces (single device d; targets = all particles) ---------------
+
+// host -> device: X, Gamma, sigma rows; static flags (compacted on the host,
+// only if any is set); previous U..PSE and SFS rows when they are accumulated on.
+int h1_upload(vpm_handle *h, Dev &d, const double *P, int64_t nf, int64_t np, bool need_prior,
+              bool need_sfs_rows, bool &has_static) {
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  const size_t n = (size_t)std::max<int64_t>(np, 1);
+  TRY(ensure(h, d.in7, n * 7 * sizeof(double)));
+  TRY(ensure(h, d.res18, n * RES_ROWS * sizeof(double)));
+  TRY(ensure(h, d.sfs3, n * 3 * sizeof(double)));
+  has_static = false;
+  if (np == 0) return VPM_OK;
+  has_static = any_static(P, nf, np);
+  const bool pinned = host_is_pinned(P);
+  double *stg = nullptr;
+  if (!pinned) {
+    TRY(ensure_stage(h, (size_t)np * (7 + RES_ROWS + 3)));
+    stg = h->h_stage;
+    gather_rows(stg, P, nf, R_X, 7, np);
+    CK(h, cudaMemcpyAsync(d.in7.p, stg, (size_t)np * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else {
+    TRY(h2d_rows(h, st, (double *)d.in7.p, P, nf, 7, np));
+  }
+  if (has_static) {
+    if (h->h_stat_cap < (size_t)np) {
+      if (h->h_stat) cudaFreeHost(h->h_stat);
+      h->h_stat = nullptr;
+      h->h_stat_cap = 0;
+      CK(h, cudaMallocHost((void **)&h->h_stat, (size_t)np * sizeof(double)));
+      h->h_stat_cap = (size_t)np;
+    }
+    for (int64_t i = 0; i < np; ++i) h->h_stat[i] = P[nf * i + R_STATIC];
+    TRY(ensure(h, d.stat, (size_t)np * sizeof(double)));
+    CK(h, cudaMemcpyAsync(d.stat.p, h->h_stat, (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  if (need_prior || has_static) {
+    if (!pinned) {
+      double *s18 = stg + (size_t)np * 7;
+      gather_rows(s18, P, nf, R_U, RES_ROWS, np);
+      CK(h, cudaMemcpyAsync(d.res18.p, s18, (size_t)np * RES_ROWS * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+      TRY(h2d_rows(h, st, (double *)d.res18.p, P + R_U, nf, RES_ROWS, np));
+    }
+  }
+  if (need_sfs_rows) {
+    if (!pinned) {
+      double *s3 = stg + (size_t)np * (7 + RES_ROWS);
+      gather_rows(s3, P, nf, R_SFS, 3, np);
+      CK(h, cudaMemcpyAsync(d.sfs3.p, s3, (size_t)np * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+      TRY(h2d_rows(h, st, (double *)d.sfs3.p, P + R_SFS, nf, 3, np));
+    }
+  }
+  return VPM_OK;
+}
+
+// device-resident evaluation: U/J sweep (+ SFS sweep) over all particles.
+// `prior` says res18/sfs3 hold previous values that must be accumulated on.
+int h1_eval(vpm_handle *h, Dev &d, int64_t np, int kernel, int flags, bool has_static, bool prior) {
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  const double *stat = has_static ? (const double *)d.stat.p : nullptr;
+  SrcView src{(const double *)d.in7.p, 7, 0, 3, 6};
+  Plan plan;
+  CK(h, cudaEventRecord(d.ev[1], st));
+  TRY(uj_sweep(h, d, st, kernel, (const double *)d.in7.p, 7, np, src, 0, np, flags, plan));
+  CK(h, cudaEventRecord(d.ev[2], st));
+  if (np > 0) {
+    UjFinishArgs f;
+    f.partial = (const double *)d.partial.p; f.pstride = plan.pstride; f.nsplit = plan.nsplit;
+    f.nt = np; f.out = (double *)d.res18.p; f.ld = RES_ROWS; f.urow = RES_U; f.jrow = RES_J;
+    f.zrow0 = RES_W; f.zrow1 = RES_PSE; f.want_U = 1; f.want_J = 1;
+    f.accumulate = prior ? 1 : 0;
+    f.reset = (flags & VPM_FLAG_RESET) ? 1 : 0;
+    f.stat = stat; f.sld = 1;
+    if (!prior) {
+      // nothing uploaded: vorticity / PSE rows of the block must still be defined
+      CK(h, cudaMemsetAsync(d.res18.p, 0, (size_t)np * RES_ROWS * sizeof(double), st));
+    }
+    uj_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(f);
+    h->launches++;
+    CK(h, cudaGetLastError());
+  }
+  CK(h, cudaEventRecord(d.ev[3], st));
+  h->timing.uj_pairs = np * np;
+  h->timing.sfs_pairs = 0;
+  if (np > 0 && (flags & VPM_FLAG_SFS)) {
+    Plan sp;
+    const double *J = (const double *)d.res18.p + RES_J;
+    TRY(sfs_sweep(h, d, st, kernel, (const double *)d.in7.p, 7, J, RES_ROWS, nullptr, np, src, J,
+                  RES_ROWS, 0, stat, 1, nullptr, np, flags, sp));
+    SfsFinishArgs f;
+    f.partial = (const double *)d.partial.p; f.pstride = sp.pstride; f.nsplit = sp.nsplit;
+    f.nt = np; f.tindex = nullptr; f.out = (double *)d.sfs3.p; f.ld = 3; f.row = 0;
+    f.accumulate = 1;  // sfs3 holds either the uploaded rows or (below) zeros
+    f.reset = (flags & VPM_FLAG_RESET_SFS) ? 1 : 0;
+    f.filter_static = 1; f.stat = stat; f.sld = 1;
+    sfs_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(f);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    h->timing.sfs_pairs = np * np;
+  } else if (np > 0 && (flags & VPM_FLAG_RESET_SFS)) {
+    zero_rows_kernel<<<blocks_for(np, 256), 256, 0, st>>>((double *)d.sfs3.p, 3, 0, 3, np, stat, 1);
+    h->launches++;
+    CK(h, cudaGetLastError());
+  }
+  CK(h, cudaEventRecord(d.ev[4], st));
+  return VPM_OK;
+}
+
+int h1_download(vpm_handle *h, Dev &d, double *P, int64_t nf, int64_t np, int flags) {
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  const bool sfs_rows = flags & (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS);
+  if (np > 0 && !host_is_pinned(P)) {
+    // pageable matrix: contiguous D2H into the pinned staging block, then scatter on the host
+    TRY(ensure_stage(h, (size_t)np * (7 + RES_ROWS + 3)));
+    double *s18 = h->h_stage + (size_t)np * 7, *s3 = h->h_stage + (size_t)np * (7 + RES_ROWS);
+    CK(h, cudaMemcpyAsync(s18, d.res18.p, (size_t)np * RES_ROWS * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (sfs_rows) CK(h, cudaMemcpyAsync(s3, d.sfs3.p, (size_t)np * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaEventRecord(d.ev[5], st));
+    CK(h, cudaStreamSynchronize(st));
+    scatter_rows(P, nf, R_U, RES_ROWS, np, s18);
+    if (sfs_rows) scatter_rows(P, nf, R_SFS, 3, np, s3);
+    return VPM_OK;
+  }
+  if (np > 0) {
+    CK(h, cudaMemcpy2DAsync(P + R_U, nf * sizeof(double), d.res18.p, RES_ROWS * sizeof(double),
+                            RES_ROWS * sizeof(double), (size_t)np, cudaMemcpyDeviceToHost, st));
+    if (sfs_rows)
+      CK(h, cudaMemcpy2DAsync(P + R_SFS, nf * sizeof(double), d.sfs3.p, 3 * sizeof(double),
+                              3 * sizeof(double), (size_t)np, cudaMemcpyDeviceToHost, st));
+  }
+  CK(h, cudaEventRecord(d.ev[5], st));
+  CK(h, cudaStreamSynchronize(st));
+  return VPM_OK;
+}
+
+void h1_fill_timing(vpm_handle *h, Dev &d) {
+  vpm_timing &t = h->timing;
+  h->device_timing = 0;
+  t.h2d_ms = ev_ms(d.ev[0], d.ev[1]);
+  t.uj_ms = ev_ms(d.ev[1], d.ev[2]);
+  t.finish_ms = ev_ms(d.ev[2], d.ev[3]);
+  t.sfs_ms = ev_ms(d.ev[3], d.ev[4]);
+  t.d2h_ms = ev_ms(d.ev[4], d.ev[5]);
+  t.total_ms = ev_ms(d.ev[0], d.ev[5]);
+  t.prep_ms = 0.0;
+  t.kernel_launches = h->launches;
+  t.n_gpus = (int32_t)h->devs.size();
+}
+
+}  // namespace
