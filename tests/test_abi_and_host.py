@@ -137,6 +137,22 @@ def test_leaf_lists_refine_cells_for_sparse_fields(vpm):
         assert (leaf_of[i], leaf_of[j]) in s
 
 
+def test_direct_list_forms(vpm):
+    """the list-taking wrappers accept the reference's (n, 2) direct_list or a tuple of its columns"""
+    from flowvpm_jl_b200 import uj
+    dl = np.array([[0, 1], [2, 3], [4, 5]], dtype=np.int64)
+    a, b = uj._pairs(dl), uj._pairs((dl[:, 0], dl[:, 1]))
+    for x, y in zip(a, b):
+        assert x.dtype == np.int32 and x.flags.c_contiguous and np.array_equal(x, y)
+    assert [v.tolist() for v in uj._pairs([[0, 1], [2, 3]])] == [[0, 2], [1, 3]]   # a list is an (n, 2) list
+    cols = (np.arange(4, dtype=np.int32), np.arange(4, dtype=np.int32))
+    assert uj._pairs(cols)[0] is cols[0]                                            # no copy
+    with pytest.raises(ValueError):
+        uj._pairs(np.zeros((3, 3)))
+    with pytest.raises(ValueError):
+        uj._pairs((np.arange(3), np.arange(4)))
+
+
 def test_sharding_bounds(vpm):
     from flowvpm_jl_b200 import sharding
     for n, w in ((10, 4), (1 << 20, 8), (7, 8), (0, 2)):

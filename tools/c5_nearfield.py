@@ -59,10 +59,11 @@ for ncrit in ncrits:
   tb[0:3] = sb[0:3]
   leaves = (ll["leaf_begin"], ll["leaf_end"])
   dl = ll["direct_list"]
+  pairs = (ll["pair_tgt"], ll["pair_src"])   # contiguous columns: no de-interleaving copy in the wrapper
   for rep in range(2):
       tb[4:] = 0
       t = time.perf_counter()
-      vpm.nearfield_device(tb, leaves, sb, leaves, dl, vpm.winckelmans, handle=h)
+      vpm.nearfield_device(tb, leaves, sb, leaves, pairs, vpm.winckelmans, handle=h)
       dt = time.perf_counter() - t
   tm = h.timing()
   res.update(hook3_call_s=dt, hook3_kernel_ms_dev0=tm["uj_ms"], hook3_h2d_ms=tm["h2d_ms"], hook3_d2h_ms=tm["d2h_ms"],
