@@ -135,7 +135,7 @@ def test_uj_nearfield_device_lists_multi_gpu(vpm, ncrit):
         before = pf.particles.copy(order="F")
         ll = vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, handle=hm)
         ref_ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=ncrit, theta=0.4)
-        assert all(np.array_equal(ll[k], ref_ll[k]) for k in ll)
+        assert all(np.array_equal(ll[k], ref_ll[k]) for k in ref_ll)
         vpm.UJ_nearfield(pf, reset=False, handle=hm)
         multi = pf.particles.copy(order="F")
         pf.particles[:] = before
