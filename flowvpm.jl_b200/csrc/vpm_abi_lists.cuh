@@ -70,14 +70,10 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
     a.csr.wi_leaf += k0;
     a.csr.wi_off += k0;
     if (g == 0) CK(h, cudaEventRecord(d.ev[1], st));
-    SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
-    prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (double *)d.rec.p);
-    h->launches++;
     a.tpos = (const double *)d.tbuf.p + row_pos; a.tld = ld; a.rec = (const double *)d.rec.p;
     a.out = (double *)d.tbuf.p; a.urow = row_grad; a.jrow = row_hess; a.want_U = want_U; a.want_J = want_J;
     a.shortcut = 1;
-    launch_uj_leaf(kernel, c.nt, (unsigned)(k1 - k0), a, st);
-    h->launches++;
+    launch_uj_leaf_any(h, d, st, kernel, c.nt, (unsigned)(k1 - k0), a, (const double *)d.sbuf.p, n_src, ns_pad);
     CK(h, cudaGetLastError());
     if (g == 0) {
       CK(h, cudaEventRecord(d.ev[2], st));
@@ -394,8 +390,6 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
     const int64_t col1 = G == 1 ? np : std::min<int64_t>(he[(size_t)ll], hb[(size_t)ll] + c.last_off[g + 1] + c.nt);
     tree_gather_kernel<<<blocks_for(np, 256), 256, 0, st>>>((const double *)d.in7.p, 7, 0, 3, 6, (const int64_t *)d.tree.p,
                                                             np, (double *)d.sbuf.p, (double *)d.tbuf.p);
-    SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
-    prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, np, ns_pad, kernel, (double *)d.rec.p);
     LeafUjArgs a;
     a.csr = csr[g];
     a.csr.wi_leaf += k0;
@@ -404,9 +398,9 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
     a.out = (double *)d.tbuf.p; a.urow = 4; a.jrow = 7; a.want_U = 1; a.want_J = 1;
     a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
     if (g == 0) CK(h, cudaEventRecord(d.ev[6], st));
-    launch_uj_leaf(kernel, c.nt, (unsigned)(k1 - k0), a, st);
+    launch_uj_leaf_any(h, d, st, kernel, c.nt, (unsigned)(k1 - k0), a, (const double *)d.sbuf.p, np, ns_pad);
     if (g == 0) CK(h, cudaEventRecord(d.ev[7], st));
-    h->launches += 3;
+    h->launches += 1;
     CK(h, cudaGetLastError());
     cols[g] = {col0, col1};
   }

@@ -361,6 +361,36 @@ void launch_uj_leaf(int kernel, int nt, unsigned nwi, const LeafUjArgs &a, cudaS
     default: launch_uj_leaf_K<K_WINCK>(nt, nwi, a, st); break;
   }
 }
+template <int K>
+void launch_uj_leaf_f32_K(int nt, unsigned nwi, const LeafUjArgsF &a, cudaStream_t st) {
+  if (nt == 32) uj_leaf_kernel_f32<K, 32, 64><<<nwi, 32, 0, st>>>(a);
+  else if (nt == 64) uj_leaf_kernel_f32<K, 64, 64><<<nwi, 64, 0, st>>>(a);
+  else uj_leaf_kernel_f32<K, 128, 128><<<nwi, 128, 0, st>>>(a);
+}
+void launch_uj_leaf_f32(int kernel, int nt, unsigned nwi, const LeafUjArgsF &a, cudaStream_t st) {
+  switch (kernel) {
+    case K_SING: launch_uj_leaf_f32_K<K_SING>(nt, nwi, a, st); break;
+    case K_GAUS: launch_uj_leaf_f32_K<K_GAUS>(nt, nwi, a, st); break;
+    case K_GERF: launch_uj_leaf_f32_K<K_GERF>(nt, nwi, a, st); break;
+    default: launch_uj_leaf_f32_K<K_WINCK>(nt, nwi, a, st); break;
+  }
+}
+// records + leaf kernel of one device's share of the work items, FP64 or (option) FP32 arithmetic
+void launch_uj_leaf_any(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, int nt, unsigned nwi, const LeafUjArgs &a,
+                        const double *sbuf8, int64_t n_src, int64_t ns_pad) {
+  SrcView sv{sbuf8, 8, 0, 4, 7};
+  if (h->opt_nearfield_fp32) {
+    prep_uj_records_f32s<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (float *)d.rec.p);
+    LeafUjArgsF f;
+    f.csr = a.csr; f.tpos = a.tpos; f.tld = a.tld; f.rec = (const float *)d.rec.p; f.out = a.out;
+    f.urow = a.urow; f.jrow = a.jrow; f.want_U = a.want_U; f.want_J = a.want_J; f.shortcut = a.shortcut;
+    launch_uj_leaf_f32(kernel, nt, nwi, f, st);
+  } else {
+    prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (double *)d.rec.p);
+    launch_uj_leaf(kernel, nt, nwi, a, st);
+  }
+  h->launches += 2;
+}
 template <int K, int MODE>
 void launch_sfs_leaf_K(int nt, unsigned nwi, const LeafSfsArgs &a, cudaStream_t st) {
   if (nt == 32) sfs_leaf_kernel<K, 32, 64, MODE><<<nwi, 32, 0, st>>>(a);
