@@ -15,7 +15,7 @@ SYMBOLS = [
     "vpm_create", "vpm_destroy", "vpm_last_error", "vpm_abi_version", "vpm_num_devices",
     "vpm_uj_direct", "vpm_uj_direct_f32", "vpm_uj_direct_st",
     "vpm_upload_state", "vpm_eval", "vpm_download_results",
-    "vpm_pin_host", "vpm_unpin_host",
+    "vpm_pin_host", "vpm_unpin_host", "vpm_set_option",
     "vpm_p2p_buffers", "vpm_p2p_leafpairs", "vpm_estr_leafpairs",
     "vpm_zeta_direct", "vpm_zeta_leafpairs",
     "vpm_leaflists_build", "vpm_leaflists_get", "vpm_uj_nearfield",
@@ -29,6 +29,7 @@ VPM_OK = 0
 KERNEL_SINGULAR, KERNEL_GAUSSIAN, KERNEL_GAUSSIANERF, KERNEL_WINCKELMANS = 0, 1, 2, 3
 FLAG_RESET, FLAG_RESET_SFS, FLAG_SFS, FLAG_TRANSPOSED, FLAG_NO_FARFIELD_SHORTCUT = 1, 2, 4, 8, 16
 FLAG_FP32 = 32
+OPT_NEARFIELD_FP32 = 1
 
 
 class VpmTiming(C.Structure):
@@ -82,6 +83,7 @@ def load():
     lib.vpm_upload_state.argtypes = [p, p, i64, i64]
     lib.vpm_eval.argtypes = [p, i32, i32]
     lib.vpm_download_results.argtypes = [p, p, i64, i64, i32]
+    lib.vpm_set_option.argtypes = [p, i32, i32]
     lib.vpm_pin_host.argtypes = [p, p, C.c_size_t]
     lib.vpm_unpin_host.argtypes = [p, p]
     lib.vpm_p2p_buffers.argtypes = [p, p, i64, i64, i64, i32, i32, i32, p, i64, i64, i32, i32, i32]
@@ -136,6 +138,9 @@ class Handle:
     def check(self, rc):
         if rc != VPM_OK:
             raise VpmError(rc, self.lib.vpm_last_error(self._h).decode())
+
+    def set_option(self, option, value):
+        self.check(self.lib.vpm_set_option(self._h, int(option), int(value)))
 
     def timing(self):
         t = VpmTiming()

@@ -79,6 +79,14 @@ int vpm_destroy(vpm_handle *h) {
   return VPM_OK;
 }
 
+int vpm_set_option(vpm_handle *h, int option, int value) {
+  if (!h) return VPM_EINVAL;
+  switch (option) {
+    case VPM_OPT_NEARFIELD_FP32: h->opt_nearfield_fp32 = value != 0; return VPM_OK;
+  }
+  return fail(h, VPM_EINVAL, "vpm_set_option: unknown option %d", option);
+}
+
 int vpm_pin_host(vpm_handle *h, void *ptr, size_t bytes) {
   if (!h || !ptr || bytes == 0) return fail(h, VPM_EINVAL, "vpm_pin_host: bad argument");
   CK(h, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));

@@ -24,8 +24,6 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
   // non-overlapping body order (tree-sorted buffers) so that a device's targets are one
   // contiguous column range; otherwise device 0 does everything.
   int G = (int)h->devs.size();
-  for (int64_t l = 0; l + 1 < ntl && G > 1; ++l)
-    if (tb[l + 1] < te[l]) G = 1;
   const int64_t ns_pad = round_up(n_src, kTile);
   for (int g = 0; g < G; ++g) {
     Dev &d = h->devs[g];
@@ -43,6 +41,7 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
   DevCsr c;
   TRY(build_csr_device(h, fn, tb, te, ntl, n_tgt, sb, se, nsl, n_src, pt, ps, npairs, G, nullptr, 0, nullptr, 0, c));
   if (c.nwi == 0) return VPM_OK;
+  G = c.G_eff;  // 1 when the target leaves that carry work overlap
   std::vector<LeafCsr> csr(G);
   csr[0] = c.csr;
   for (int g = 1; g < G; ++g) {
@@ -51,8 +50,8 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
     TRY(ensure(h, d.ibuf, h->devs[0].ibuf.cap));
     csr[g] = rebase_csr(c.csr, h->devs[0].ibuf.p, d.ibuf.p);
   }
-  TRY(bcast_from_dev0(h, &Dev::sbuf, (size_t)n_src * 8 * sizeof(double)));
-  TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
+  if (G > 1) TRY(bcast_from_dev0(h, &Dev::sbuf, (size_t)n_src * 8 * sizeof(double)));
+  if (G > 1) TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
   std::vector<std::pair<int64_t, int64_t>> cols(G, {0, 0});
   for (int g = 0; g < G; ++g) {
     Dev &d = h->devs[g];
@@ -71,14 +70,10 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
     a.csr.wi_leaf += k0;
     a.csr.wi_off += k0;
     if (g == 0) CK(h, cudaEventRecord(d.ev[1], st));
-    SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
-    prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (double *)d.rec.p);
-    h->launches++;
     a.tpos = (const double *)d.tbuf.p + row_pos; a.tld = ld; a.rec = (const double *)d.rec.p;
     a.out = (double *)d.tbuf.p; a.urow = row_grad; a.jrow = row_hess; a.want_U = want_U; a.want_J = want_J;
     a.shortcut = 1;
-    launch_uj_leaf(kernel, c.nt, (unsigned)(k1 - k0), a, st);
-    h->launches++;
+    launch_uj_leaf_any(h, d, st, kernel, c.nt, (unsigned)(k1 - k0), a, (const double *)d.sbuf.p, n_src, ns_pad);
     CK(h, cudaGetLastError());
     if (g == 0) {
       CK(h, cudaEventRecord(d.ev[2], st));
@@ -126,8 +121,6 @@ static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, i
   // Multi-GPU: as Hook 3 -- target leaves sharded over the devices in contiguous runs of work
   // items; needs increasing, non-overlapping target leaves (tree-sorted), else device 0 alone
   int G = (int)h->devs.size();
-  for (int64_t l = 0; l + 1 < ntl && G > 1; ++l)
-    if (tb[l + 1] < te[l]) G = 1;
   const int64_t ns_pad = round_up(np, kTile);
   for (int g = 0; g < G; ++g) {
     Dev &dg = h->devs[g];
@@ -147,6 +140,7 @@ static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, i
   DevCsr c;
   TRY(build_csr_device(h, fn, tb, te, ntl, np, sb, se, nsl, np, pt, ps, npairs, G, tsort, np, ssort, np, c));
   if (c.nwi == 0) return VPM_OK;
+  G = c.G_eff;
   CK(h, cudaEventRecord(d.ev[1], st));
   CK(h, cudaEventRecord(d.ev[2], st));
   CK(h, cudaEventRecord(d.ev[3], st));
@@ -154,9 +148,9 @@ static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, i
     CK(h, cudaSetDevice(h->devs[g].id));
     TRY(ensure(h, h->devs[g].ibuf, d.ibuf.cap));
   }
-  TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np * 7 * sizeof(double)));
-  TRY(bcast_from_dev0(h, &Dev::jbuf, (size_t)np * 9 * sizeof(double)));
-  TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
+  if (G > 1) TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np * 7 * sizeof(double)));
+  if (G > 1) TRY(bcast_from_dev0(h, &Dev::jbuf, (size_t)np * 9 * sizeof(double)));
+  if (G > 1) TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
   const int transposed = (flags & VPM_FLAG_TRANSPOSED) ? 1 : 0;
   std::vector<std::pair<int64_t, int64_t>> cols(G, {0, 0});
   for (int g = 0; g < G; ++g) {
@@ -339,7 +333,7 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
   if (h->tree_np != np) return fail(h, VPM_ESTATE, "%s: leaf lists were built for %lld particles, field has %lld (call vpm_leaflists_build)", fn, (long long)h->tree_np, (long long)np);
   if (np == 0) return VPM_OK;
   h->launches = 0;
-  const int G = (int)h->devs.size();
+  int G = (int)h->devs.size();
   Dev &d0 = h->devs[0];
   CK(h, cudaSetDevice(d0.id));
   CK(h, cudaEventRecord(d0.ev[0], d0.stream));
@@ -352,6 +346,7 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
   DevCsr c;
   TRY(build_csr_device(h, fn, tv.lbegin, tv.lend, h->tree_nl, np, tv.lbegin, tv.lend, h->tree_nl, np, tv.pt, tv.ps,
                        h->tree_npairs, G, nullptr, 0, nullptr, 0, c, true));
+  G = c.G_eff;
   CK(h, cudaEventRecord(d0.ev[1], d0.stream));
   const int64_t ns_pad = round_up(np, kTile);
   std::vector<LeafCsr> csr(G);
@@ -371,9 +366,9 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
   }
   // replicate state, sort index and list tables over NVLink; every device gathers its own
   // tree-sorted buffers
-  TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np * 7 * sizeof(double)));
-  TRY(bcast_from_dev0(h, &Dev::tree, (size_t)np * 8));
-  TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
+  if (G > 1) TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np * 7 * sizeof(double)));
+  if (G > 1) TRY(bcast_from_dev0(h, &Dev::tree, (size_t)np * 8));
+  if (G > 1) TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
   std::vector<std::pair<int64_t, int64_t>> cols(G, {0, 0});
   // leaf tables on the host are not available (device-built): the column range of a device is
   // [begin of its first item, end of its last item), read from the cut records
@@ -395,8 +390,6 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
     const int64_t col1 = G == 1 ? np : std::min<int64_t>(he[(size_t)ll], hb[(size_t)ll] + c.last_off[g + 1] + c.nt);
     tree_gather_kernel<<<blocks_for(np, 256), 256, 0, st>>>((const double *)d.in7.p, 7, 0, 3, 6, (const int64_t *)d.tree.p,
                                                             np, (double *)d.sbuf.p, (double *)d.tbuf.p);
-    SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
-    prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, np, ns_pad, kernel, (double *)d.rec.p);
     LeafUjArgs a;
     a.csr = csr[g];
     a.csr.wi_leaf += k0;
@@ -405,9 +398,9 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
     a.out = (double *)d.tbuf.p; a.urow = 4; a.jrow = 7; a.want_U = 1; a.want_J = 1;
     a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
     if (g == 0) CK(h, cudaEventRecord(d.ev[6], st));
-    launch_uj_leaf(kernel, c.nt, (unsigned)(k1 - k0), a, st);
+    launch_uj_leaf_any(h, d, st, kernel, c.nt, (unsigned)(k1 - k0), a, (const double *)d.sbuf.p, np, ns_pad);
     if (g == 0) CK(h, cudaEventRecord(d.ev[7], st));
-    h->launches += 3;
+    h->launches += 1;
     CK(h, cudaGetLastError());
     cols[g] = {col0, col1};
   }

@@ -24,6 +24,7 @@ enum { CS_BAD = 0,       // 1 + index of an out-of-range list entry (0 = none)
        CS_W128 = 2, CS_W64 = 3, CS_W32 = 4,  // padded lane-work for the three CTA widths
        CS_PAIRS = 5,     // sum over list entries of nt * ns (pair visits)
        CS_NWI = 6,       // number of work items
+       CS_OVERLAP = 7,   // != 0 when target leaves that carry work overlap or are out of body order
        CS_SLOTS = 8 };
 
 // one thread per list entry: counts per target leaf (cnt[l + 1]), source bodies per target
@@ -73,23 +74,32 @@ __global__ void csr_cand_kernel(const int64_t *__restrict__ tb, const int64_t *_
   }
 }
 
-// work items of leaf l: ceil(size / nt) when the leaf has list entries, else none
+// Work items are laid out in BODY order (rank r = position of a leaf when the target leaves are
+// sorted by their first body; ord[r] = leaf), not in leaf-index order: the caller's leaf table
+// may be level-ordered and contain interior branches (FastMultipole's branch array), but a
+// device's share of the items must still be one contiguous range of target columns.
+// work items of the leaf of rank r: ceil(size / nt) when the leaf has list entries, else none
 __global__ void csr_wi_count_kernel(const int64_t *__restrict__ tb, const int64_t *__restrict__ te, int64_t ntl,
-                                    const u64 *__restrict__ ptr, int nt, u64 *__restrict__ wcnt) {
-  const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= ntl) return;
+                                    const u64 *__restrict__ ptr, const int32_t *__restrict__ ord, int nt,
+                                    u64 *__restrict__ wcnt) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= ntl) return;
+  const int64_t l = ord[r];
   const int64_t sz = te[l] - tb[l];
-  wcnt[l] = ptr[l + 1] > ptr[l] ? (u64)((sz + nt - 1) / nt) : 0ull;
+  wcnt[r] = ptr[l + 1] > ptr[l] ? (u64)((sz + nt - 1) / nt) : 0ull;
 }
 
-// fill the work items of leaf l at wofs[l].. and their pair counts (for the multi-GPU cuts)
+// fill the work items of the leaf of rank r at wofs[r].. and their pair counts (for the multi-GPU
+// cuts); flag leaves with work whose body range starts before the previous such leaf ended
 __global__ void csr_wi_fill_kernel(const int64_t *__restrict__ tb, const int64_t *__restrict__ te, int64_t ntl,
                                    const u64 *__restrict__ wofs, const u64 *__restrict__ wcnt,
-                                   const u64 *__restrict__ srcw, int nt, int32_t *__restrict__ wi_leaf,
-                                   int32_t *__restrict__ wi_off, u64 *__restrict__ wi_w, u64 *__restrict__ stats) {
-  const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= ntl) return;
-  const u64 n = wcnt[l], o = wofs[l];
+                                   const u64 *__restrict__ srcw, const int32_t *__restrict__ ord, int nt,
+                                   int32_t *__restrict__ wi_leaf, int32_t *__restrict__ wi_off,
+                                   u64 *__restrict__ wi_w, u64 *__restrict__ stats) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= ntl) return;
+  const int64_t l = ord[r];
+  const u64 n = wcnt[r], o = wofs[r];
   const int64_t sz = te[l] - tb[l];
   for (u64 j = 0; j < n; ++j) {
     const int64_t off = (int64_t)j * nt;
@@ -98,7 +108,21 @@ __global__ void csr_wi_fill_kernel(const int64_t *__restrict__ tb, const int64_t
     const int64_t c = sz - off < nt ? sz - off : nt;
     wi_w[o + j] = (u64)c * srcw[l];
   }
-  if (l == ntl - 1) stats[CS_NWI] = o + n;
+  if (n > 0) {
+    // previous leaf with work, in body order
+    for (int64_t q = r - 1; q >= 0; --q) {
+      if (wcnt[q] > 0) {
+        if (te[ord[q]] > tb[l]) stats[CS_OVERLAP] = 1;
+        break;
+      }
+    }
+  }
+  if (r == ntl - 1) stats[CS_NWI] = o + n;
+}
+
+__global__ void csr_iota_kernel(int32_t *p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)i;
 }
 
 // cut g (0 <= g <= G): first work item k whose exclusive pair-count prefix reaches total * g / G

@@ -48,6 +48,7 @@ struct vpm_handle {
   size_t h_stage_cap = 0;     // (doubles)
   std::vector<std::pair<void *, size_t>> pinned;  // ranges page-locked by vpm_pin_host
   int launches = 0;
+  int opt_nearfield_fp32 = 0;  // VPM_OPT_NEARFIELD_FP32
   int64_t fld_nf = 0, fld_np = -1;  // device mirror of the whole particle matrix (vpm_field_*)
   double fld_t_sgm = 0.0;           // CoreSpreading.t_sgm of the resident field
   int device_timing = 0;  // 1/2: ev[6..7] bracket the last _device U/J / SFS pair kernel

@@ -24,6 +24,8 @@ struct DevCsr {
   int nt = kThreads;        // CTA width (targets per work item): 32, 64 or 128
   int64_t nwi = 0;          // work items
   int64_t pairs = 0;        // pair visits of the whole list
+  int G_eff = 1;            // devices the work items are cut over: G, or 1 when the target leaves that
+                            // carry work overlap (a device's targets must be one contiguous column range)
   std::vector<int64_t> cut;                     // [G + 1] work-item cuts
   std::vector<int64_t> first_leaf, first_off;   // [G + 1] item cut[g]     (first item of device g)
   std::vector<int64_t> last_leaf, last_off;     // [G + 1] item cut[g] - 1 (last item of device g - 1)
@@ -74,7 +76,8 @@ int build_csr_device(vpm_handle *h, const char *fn, const int64_t *tb, const int
   int64_t *dts = cv.take<int64_t>((size_t)n_tsort), *dss = cv.take<int64_t>((size_t)n_ssort);
   out.bcast_bytes = cv.off;
   // ... and device-0 scratch
-  const size_t sbytes = 16 * 8 + (size_t)npairs * 4 + (size_t)ntl * 8 * 3 + (size_t)max_wi * 8 + CS_SLOTS * 8 + (size_t)(G + 1) * 40;
+  const size_t sbytes = 16 * 12 + (size_t)npairs * 4 + (size_t)ntl * 8 * 3 + (size_t)max_wi * 8 + CS_SLOTS * 8 +
+                        (size_t)(G + 1) * 40 + (size_t)ntl * 16;
   TRY(ensure(h, d.scr, sbytes));
   Carver sc(d.scr.p);
   int32_t *dpt = sc.take<int32_t>((size_t)npairs);
@@ -82,6 +85,8 @@ int build_csr_device(vpm_handle *h, const char *fn, const int64_t *tb, const int
   u64 *wiw = sc.take<u64>((size_t)max_wi);
   u64 *stats = sc.take<u64>(CS_SLOTS);
   int64_t *dcut = sc.take<int64_t>((size_t)(G + 1) * 5);
+  int64_t *tb_sorted = sc.take<int64_t>((size_t)ntl);
+  int32_t *iota = sc.take<int32_t>((size_t)ntl), *ord = sc.take<int32_t>((size_t)ntl);
   // cub temporary storage: the largest of the four calls below
   const int key_bits = std::max(1, (int)std::ceil(std::log2((double)std::max<int64_t>(ntl, 2))));
   size_t tmp = 0, t1 = 0;
@@ -90,6 +95,9 @@ int build_csr_device(vpm_handle *h, const char *fn, const int64_t *tb, const int
   cub::DeviceScan::InclusiveSum(nullptr, t1, wiw, wiw, max_wi, st); tmp = std::max(tmp, t1);
   cub::DeviceRadixSort::SortPairs(nullptr, t1, (const int32_t *)nullptr, (int32_t *)nullptr, (const int32_t *)nullptr,
                                   (int32_t *)nullptr, npairs, 0, key_bits, st);
+  tmp = std::max(tmp, t1);
+  cub::DeviceRadixSort::SortPairs(nullptr, t1, (const int64_t *)nullptr, (int64_t *)nullptr, (const int32_t *)nullptr,
+                                  (int32_t *)nullptr, ntl, 0, 64, st);
   tmp = std::max(tmp, t1);
   TRY(ensure(h, d.cubtmp, tmp + 16));
 
@@ -141,17 +149,26 @@ int build_csr_device(vpm_handle *h, const char *fn, const int64_t *tb, const int
     CK(h, cudaMemcpyAsync(dsrc, vals_out, (size_t)npairs * 4, cudaMemcpyDeviceToDevice, st));
     h->launches += 1;
   }
-  csr_wi_count_kernel<<<blocks_for(ntl, 256), 256, 0, st>>>(dtb, dte, ntl, dptr, out.nt, wcnt);
+  // target leaves in body order (stable: leaves with the same first body keep their index order)
+  csr_iota_kernel<<<blocks_for(ntl, 256), 256, 0, st>>>(iota, ntl);
+  t1 = d.cubtmp.cap;
+  CK(h, cub::DeviceRadixSort::SortPairs(d.cubtmp.p, t1, (const int64_t *)dtb, tb_sorted, (const int32_t *)iota, ord, ntl, 0,
+                                        64, st));
+  csr_wi_count_kernel<<<blocks_for(ntl, 256), 256, 0, st>>>(dtb, dte, ntl, dptr, ord, out.nt, wcnt);
   t1 = d.cubtmp.cap;
   CK(h, cub::DeviceScan::ExclusiveSum(d.cubtmp.p, t1, wcnt, wofs, (int64_t)ntl, st));
   csr_zero_kernel<<<blocks_for(max_wi, 256), 256, 0, st>>>(wiw, max_wi);
-  csr_wi_fill_kernel<<<blocks_for(ntl, 256), 256, 0, st>>>(dtb, dte, ntl, wofs, wcnt, srcw, out.nt, wl, wo, wiw, stats);
+  csr_wi_fill_kernel<<<blocks_for(ntl, 256), 256, 0, st>>>(dtb, dte, ntl, wofs, wcnt, srcw, ord, out.nt, wl, wo, wiw,
+                                                          stats);
+  h->launches += 2;
   t1 = d.cubtmp.cap;
   CK(h, cub::DeviceScan::InclusiveSum(d.cubtmp.p, t1, wiw, wiw, max_wi, st));
   h->launches += 5;
   CK(h, cudaMemcpyAsync(hs, stats, sizeof hs, cudaMemcpyDeviceToHost, st));
   CK(h, cudaStreamSynchronize(st));
   out.nwi = (int64_t)hs[CS_NWI];
+  out.G_eff = hs[CS_OVERLAP] ? 1 : G;
+  G = out.G_eff;
   out.cut.assign((size_t)G + 1, out.nwi);
   out.cut[0] = 0;
   for (auto *v : {&out.first_leaf, &out.first_off, &out.last_leaf, &out.last_off}) v->assign((size_t)G + 1, 0);
@@ -343,6 +360,36 @@ void launch_uj_leaf(int kernel, int nt, unsigned nwi, const LeafUjArgs &a, cudaS
     case K_GERF: launch_uj_leaf_K<K_GERF>(nt, nwi, a, st); break;
     default: launch_uj_leaf_K<K_WINCK>(nt, nwi, a, st); break;
   }
+}
+template <int K>
+void launch_uj_leaf_f32_K(int nt, unsigned nwi, const LeafUjArgsF &a, cudaStream_t st) {
+  if (nt == 32) uj_leaf_kernel_f32<K, 32, 64><<<nwi, 32, 0, st>>>(a);
+  else if (nt == 64) uj_leaf_kernel_f32<K, 64, 64><<<nwi, 64, 0, st>>>(a);
+  else uj_leaf_kernel_f32<K, 128, 128><<<nwi, 128, 0, st>>>(a);
+}
+void launch_uj_leaf_f32(int kernel, int nt, unsigned nwi, const LeafUjArgsF &a, cudaStream_t st) {
+  switch (kernel) {
+    case K_SING: launch_uj_leaf_f32_K<K_SING>(nt, nwi, a, st); break;
+    case K_GAUS: launch_uj_leaf_f32_K<K_GAUS>(nt, nwi, a, st); break;
+    case K_GERF: launch_uj_leaf_f32_K<K_GERF>(nt, nwi, a, st); break;
+    default: launch_uj_leaf_f32_K<K_WINCK>(nt, nwi, a, st); break;
+  }
+}
+// records + leaf kernel of one device's share of the work items, FP64 or (option) FP32 arithmetic
+void launch_uj_leaf_any(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, int nt, unsigned nwi, const LeafUjArgs &a,
+                        const double *sbuf8, int64_t n_src, int64_t ns_pad) {
+  SrcView sv{sbuf8, 8, 0, 4, 7};
+  if (h->opt_nearfield_fp32) {
+    prep_uj_records_f32s<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (float *)d.rec.p);
+    LeafUjArgsF f;
+    f.csr = a.csr; f.tpos = a.tpos; f.tld = a.tld; f.rec = (const float *)d.rec.p; f.out = a.out;
+    f.urow = a.urow; f.jrow = a.jrow; f.want_U = a.want_U; f.want_J = a.want_J; f.shortcut = a.shortcut;
+    launch_uj_leaf_f32(kernel, nt, nwi, f, st);
+  } else {
+    prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (double *)d.rec.p);
+    launch_uj_leaf(kernel, nt, nwi, a, st);
+  }
+  h->launches += 2;
 }
 template <int K, int MODE>
 void launch_sfs_leaf_K(int nt, unsigned nwi, const LeafSfsArgs &a, cudaStream_t st) {

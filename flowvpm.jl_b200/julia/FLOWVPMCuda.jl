@@ -224,6 +224,11 @@ function leaflists_cuda!(pfield::vpm.ParticleField{Float64}; ncrit::Integer=50, 
             direct_list=[(pt[k] + 1, ps[k] + 1) for k in 1:npairs[]])
 end
 
+"Run the U/J leaf-list kernels (Hook 3, `UJ_nearfield_cuda!`) in FP32 arithmetic (errors ~1e-6, below FMM truncation)."
+function nearfield_fp32!(on::Bool=true)
+    check(ccall((:vpm_set_option, lib[]), Cint, (Ptr{Cvoid}, Cint, Cint), handle[], Cint(1), Cint(on)))
+end
+
 function UJ_nearfield_cuda!(pfield::vpm.ParticleField{Float64}; reset::Bool=true)
     P = pfield.particles
     GC.@preserve P check(ccall((:vpm_uj_nearfield, lib[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Cint, Cint),

@@ -75,6 +75,13 @@ const char *vpm_last_error(const vpm_handle *h);
 int vpm_abi_version(void);
 int vpm_num_devices(const vpm_handle *h);
 
+/* handle options (library-only) */
+#define VPM_OPT_NEARFIELD_FP32 1 /* value != 0: the U/J leaf-list kernels (vpm_p2p_leafpairs, vpm_uj_nearfield)
+                                    compute in FP32 arithmetic (split-precision positions, FP64 sums across
+                                    tiles; errors ~1e-6 of the field maximum): the near field of UJ_fmm is added
+                                    to a far field FastMultipole truncates at 1e-3..1e-6 anyway.  Default 0. */
+int vpm_set_option(vpm_handle *h, int option, int value);
+
 /* ---- Hook 1: the UJ slot ---------------------------------------------- */
 /* UJ_direct(pfield; sfs, reset, reset_sfs): src/FLOWVPM_UJ.jl:21-37.
  * Uploads rows X, Gamma, sigma (+ static, + previous U/J/SFS when they must be

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from helpers import KERNELS, TOL_FP32, relerr, stretching, U_ROWS, J_ROWS
-from oracle import oracle
+from oracle import leaflists, oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -87,3 +87,39 @@ def test_fp32_large_field_slice(vpm, handle, kernel):
     eu, ej = relerr(pf.get_U()[:, idx], tb[4:7]), relerr(pf.get_J()[:, idx], tb[7:16])
     print(kernel, "U", eu, "J", ej)
     assert eu <= TOL_FP32 and ej <= TOL_FP32
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("ncrit", [20, 300])
+def test_fp32_nearfield_option(vpm, kernel, ncrit):
+    """VPM_OPT_NEARFIELD_FP32: the leaf-list kernels in FP32 arithmetic against the FP64 oracle over
+    the same lists (Hook 3 with caller lists, and the device-built lists of f-3)"""
+    h = vpm.Handle(1)
+    try:
+        h.set_option(vpm._cabi.OPT_NEARFIELD_FP32, 1)
+        pf = vpm.fields.cloud_field(5000, kernel=vpm.KERNELS[kernel], seed=41)
+        ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=ncrit, theta=0.4)
+        order = ll["sort_index"]
+        sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
+        tb = np.zeros((16, pf.np), order="F")
+        tb[0:3] = pf.get_X()[:, order]
+        leaves = (ll["leaf_begin"], ll["leaf_end"])
+        ref = tb.copy(order="F")
+        oracle.direct_leafpairs(ref, sb, leaves, leaves, ll["direct_list"], kernel)
+        vpm.nearfield_device(tb, leaves, sb, leaves, ll["direct_list"], vpm.KERNELS[kernel], handle=h)
+        eu, ej = relerr(tb[4:7], ref[4:7]), relerr(tb[7:16], ref[7:16])
+        print(kernel, ncrit, "U", eu, "J", ej)
+        assert eu <= TOL_FP32 and ej <= TOL_FP32
+        assert eu > 1e-12   # it really ran in FP32
+        vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, handle=h, fetch=False)
+        vpm.UJ_nearfield(pf, reset=True, handle=h)
+        near = np.zeros((12, pf.np))
+        near[:, order] = ref[4:16]
+        assert relerr(pf.particles[9:12], near[0:3]) <= TOL_FP32 and relerr(pf.particles[15:24], near[3:12]) <= TOL_FP32
+        h.set_option(vpm._cabi.OPT_NEARFIELD_FP32, 0)
+        vpm.UJ_nearfield(pf, reset=True, handle=h)
+        assert relerr(pf.particles[9:12], near[0:3]) < 1e-12
+        with pytest.raises(vpm.VpmError):
+            h.set_option(99, 1)
+    finally:
+        h.close()

@@ -157,6 +157,38 @@ def test_uj_nearfield_device_lists_multi_gpu(vpm, ncrit):
         h1.close()
 
 
+def test_leafpairs_level_ordered_branch_table_multi_gpu(vpm):
+    """Hook 3 with a leaf table as a level-ordered tree hands it over (interior branches, leaves not
+    in body order): the work items are laid out in body order on the device, so the devices still
+    share the work (and overlapping WORK leaves fall back to one device); result = oracle"""
+    from test_parity_gpu import branch_table_like_fastmultipole
+    g = _ngpu()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    h = vpm.Handle(min(g, 4))
+    try:
+        pf = vpm.fields.cloud_field(6000, kernel=vpm.gaussianerf, seed=33)
+        ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=30)
+        lb, le, dl = branch_table_like_fastmultipole(ll, pf.np)
+        order = ll["sort_index"]
+        sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
+        tb = np.zeros((16, pf.np), order="F")
+        tb[0:3] = pf.get_X()[:, order]
+        ref = tb.copy(order="F")
+        oracle.direct_leafpairs(ref, sb, (lb, le), (lb, le), dl, "gaussianerf")
+        vpm.nearfield_device(tb, (lb, le), sb, (lb, le), dl, vpm.gaussianerf, handle=h)
+        assert relerr(tb[4:7], ref[4:7]) < TOL_FP64 and relerr(tb[7:16], ref[7:16]) < TOL_FP64
+        # overlapping leaves that carry work: the root is also a target -> one device, still right
+        dl2 = np.vstack([dl, [[0, len(lb) - 1]]]).astype(np.int32)
+        tb[4:] = 0
+        ref = tb.copy(order="F")
+        oracle.direct_leafpairs(ref, sb, (lb, le), (lb, le), dl2, "gaussianerf")
+        vpm.nearfield_device(tb, (lb, le), sb, (lb, le), dl2, vpm.gaussianerf, handle=h)
+        assert relerr(tb[4:7], ref[4:7]) < TOL_FP64 and relerr(tb[7:16], ref[7:16]) < TOL_FP64
+    finally:
+        h.close()
+
+
 def test_estr_and_zeta_leafpairs_multi_gpu(vpm):
     """Estr_fmm! / zeta_fmm over a list with the target leaves sharded over the devices: equal to
     the oracle and bit-identical to the single-device evaluation"""

@@ -285,6 +285,38 @@ def test_leafpairs_unsorted_list_and_empty_leaves(vpm, handle):
     assert relerr(tb[4:7], ref[4:7]) < TOL_FP64 and relerr(tb[7:16], ref[7:16]) < TOL_FP64
 
 
+def branch_table_like_fastmultipole(ll, n, seed=0):
+    """a leaf table as a level-ordered tree would hand it over: interior branches first (root and
+    a few unions of leaves, never referenced by the list), then the leaves in shuffled order"""
+    rng = np.random.default_rng(seed)
+    nl = len(ll["leaf_begin"])
+    perm = rng.permutation(nl)
+    interior_b = [0] + [int(ll["leaf_begin"][k]) for k in range(0, nl, 7)]
+    interior_e = [n] + [int(ll["leaf_end"][min(k + 6, nl - 1)]) for k in range(0, nl, 7)]
+    ni = len(interior_b)
+    lb = np.array(interior_b + ll["leaf_begin"][perm].tolist(), dtype=np.int64)
+    le = np.array(interior_e + ll["leaf_end"][perm].tolist(), dtype=np.int64)
+    new_id = np.empty(nl, dtype=np.int64)
+    new_id[perm] = ni + np.arange(nl)
+    dl = new_id[ll["direct_list"]].astype(np.int32)
+    return lb, le, dl[rng.permutation(len(dl))]
+
+
+def test_leafpairs_level_ordered_branch_table(vpm, handle):
+    """leaf table not in body order and with interior branches: same result as the oracle"""
+    pf = vpm.fields.cloud_field(3000, kernel=vpm.winckelmans, seed=14)
+    ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=20)
+    lb, le, dl = branch_table_like_fastmultipole(ll, pf.np)
+    order = ll["sort_index"]
+    sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
+    tb = np.zeros((16, pf.np), order="F")
+    tb[0:3] = pf.get_X()[:, order]
+    ref = tb.copy(order="F")
+    oracle.direct_leafpairs(ref, sb, (lb, le), (lb, le), dl, "winckelmans")
+    vpm.nearfield_device(tb, (lb, le), sb, (lb, le), dl, vpm.winckelmans)
+    assert relerr(tb[4:7], ref[4:7]) < TOL_FP64 and relerr(tb[7:16], ref[7:16]) < TOL_FP64
+
+
 # ------------------------- second P2P: zeta_direct / zeta_fmm (vorticity basis sum)
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_zeta_direct(vpm, handle, kernel):
