@@ -103,12 +103,14 @@ class ClockSampler:
 # -------------------------------------------------------------- reference arm
 def cpu_sample(n, kernel, seconds, threads=None, repeats=1):
     """The CPU restatement of the reference's UJ_direct pair loop (oracle port: Julia is not
-    available on this box) on all host cores: all n sources x a target slice sized to
-    about `seconds` of work.  Returns (interactions/s, description, cores)."""
+    available on this box) on ALL host cores (omp_get_num_procs -- not OMP_NUM_THREADS, which
+    torchrun sets to 1): all n sources x a target slice sized to about `seconds` of work, cut
+    into >= 4 contiguous target blocks per thread.  ONE sampling policy for both CPU legs
+    (`cpu_baseline` and `--impl reference`).  Returns (interactions/s, description, cores)."""
     from vpm_import import load
     from oracle import oracle
     vpm = load()
-    threads = threads or oracle.max_threads()
+    threads = threads or oracle.num_procs()
     pf = vpm.fields.cloud_field(n, kernel=vpm.KERNELS[kernel])
     sb = vpm.source_system_to_buffer(pf)
 
@@ -119,11 +121,11 @@ def cpu_sample(n, kernel, seconds, threads=None, repeats=1):
         oracle.direct_buffers(tb, 0, nt, sb, 0, n, kernel, True, True, threads)
         return time.perf_counter() - t
 
+    g = 8 * threads  # every thread gets whole blocks
     probe = min(n, 64 * threads)
-    run(min(n, 8 * threads))  # spin the thread pool up
+    run(min(n, g))  # spin the thread pool up
     dt = run(probe)
     rate = probe * n / dt
-    g = 32 * threads
     nt = int(min(n, max(probe, seconds * rate / n // g * g)))
     best = run(nt)
     if best < 0.6 * seconds and nt < n:  # the probe under-estimated the rate: size once more
@@ -131,17 +133,19 @@ def cpu_sample(n, kernel, seconds, threads=None, repeats=1):
         best = run(nt)
     for _ in range(repeats - 1):
         best = min(best, run(nt))
-    return nt * n / best, f"all {n} sources x first {nt} targets of the same cloud ({nt * n:.3g} interactions, {best:.1f} s)", threads
+    return nt * n / best, f"all {n} sources x first {nt} targets of the same cloud ({nt * n:.3g} interactions, {best:.1f} s, {threads} threads)", threads
 
 
 def reference_arm(args):
+    """--impl reference: the CPU restatement on all host cores, rank 0 only, same workload,
+    metric and sampling policy as the b200 arm's cpu_baseline leg."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle
-    threads = oracle.max_threads()
-    times, inter = [], 0
-    per_step_seconds = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    threads = oracle.num_procs()
+    times = []
+    per_step_seconds = max(4.0, min(15.0, 90.0 / max(1, args.steps + args.warmup)))
     desc = ""
     for i in range(args.warmup + args.steps):
         v, desc, _ = cpu_sample(args.n, args.kernel, per_step_seconds, threads)
@@ -152,14 +156,23 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": args.n * args.n / value * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_particles": args.n, "kernel": args.kernel,
-                   "note": "ms_per_step is the full N^2 sweep extrapolated from the bounded sample"},
+        "config": bench_config(args.n, args.kernel, args.gpus),
+        "note": "ms_per_step is the full N^2 sweep extrapolated from the bounded sample; the CPU arm uses "
+                "the host's cores whatever --gpus says",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": desc + "; reference-equivalent C restatement (oracle/), Julia not available"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def bench_config(n, kernel, world):
+    """the `config` object, identical in both arms (same keys, same workload)"""
+    return {"workload": WORKLOAD, "n_particles": n, "kernel": kernel,
+            "parallelism": f"targets block-sharded over {world} GPU(s), all-gather of the 8xN source buffer per sweep",
+            "l2": "flushed between timed steps (256 MiB write); per-step CUDA events, max over ranks",
+            "interaction": "one ordered (source,target) pair visit of the U+J loop; N^2 per step"}
 
 
 def rvpm_step_c2(vpm, h):
@@ -397,10 +410,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_particles": n, "kernel": args.kernel,
-                   "parallelism": f"targets block-sharded over {world} GPU(s), all-gather of the 8xN source buffer per sweep",
-                   "l2": "flushed between timed steps (256 MiB write); per-step CUDA events, max over ranks",
-                   "interaction": "one ordered (source,target) pair visit of the U+J loop; N^2 per step"},
+        "config": bench_config(n, args.kernel, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_k, "api": "UJ_direct(pfield) -> vpm_uj_direct (pinned host matrix)" if world == 1
                 else "sharding.ShardedField.uj with pinned H2D/D2H of the local shard"},

@@ -62,6 +62,7 @@ def lib():
         L.vpm_oracle_rbf_cg.argtypes = [p, i64, i64, i32, i32, dbl, i32, p, i32]
         L.vpm_oracle_rbf_cg.restype = i32
         L.vpm_oracle_max_threads.restype = i32
+        L.vpm_oracle_num_procs.restype = i32
         _lib = L
     return _lib
 
@@ -80,6 +81,11 @@ def _f(P):
 
 def max_threads():
     return int(lib().vpm_oracle_max_threads())
+
+
+def num_procs():
+    """host cores available to this process, ignoring OMP_NUM_THREADS (bench.py's CPU legs)"""
+    return int(lib().vpm_oracle_num_procs())
 
 
 def erf64(x):

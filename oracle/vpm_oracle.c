@@ -244,8 +244,13 @@ void vpm_oracle_direct_buffers_mt(double *tgt, int64_t ld, int64_t t0, int64_t t
   }
   init_consts();
   int64_t nt = t1 - t0;
-  /* blocks small enough that a block of targets stays in L1/L2 while sources stream */
-  int64_t blk = 256;
+  /* contiguous target blocks, at least four per thread so that every thread is busy even on
+   * a short target slice (one block per thread is the reference's split,
+   * src/FLOWVPM_subfilterscale_models.jl:51-59; smaller blocks only balance the tail), and at
+   * most 256 targets so that a block stays in L1/L2 while the sources stream */
+  int64_t blk = (nt + 4 * (int64_t)nthreads - 1) / (4 * (int64_t)nthreads);
+  if (blk > 256) blk = 256;
+  if (blk < 1) blk = 1;
   int64_t nblk = (nt + blk - 1) / blk;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
   for (int64_t b = 0; b < nblk; ++b) {
@@ -828,6 +833,15 @@ int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, double *dp, const i
 int vpm_oracle_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+/* cores this process may run on, whatever OMP_NUM_THREADS says (torchrun exports
+ * OMP_NUM_THREADS=1 to its workers; the CPU baseline must still use the whole host) */
+int vpm_oracle_num_procs(void) {
+#ifdef _OPENMP
+  return omp_get_num_procs();
 #else
   return 1;
 #endif
