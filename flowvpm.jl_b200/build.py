@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libvpm_cuda.so")
 SOURCES = ["vpm_abi.cu"]
-HEADERS = ["vpm_kernels.cuh", "vpm_kernels_f32.cuh", "vpm_leaf.cuh", "vpm_leaf_f32.cuh", "vpm_csr.cuh", "vpm_tree.cuh", "vpm_math.cuh",
+HEADERS = ["vpm_kernels.cuh", "vpm_kernels_f32.cuh", "vpm_kernels_tab.cuh", "vpm_tab_coeffs.cuh", "vpm_leaf.cuh", "vpm_leaf_f32.cuh", "vpm_csr.cuh", "vpm_tree.cuh", "vpm_math.cuh",
            "vpm_coeffs.cuh", "vpm_step.cuh",
            # host side: parts of the single translation unit vpm_abi.cu
            "vpm_host_base.cuh", "vpm_host_sweeps.cuh", "vpm_host_hook1.cuh", "vpm_host_multi.cuh",

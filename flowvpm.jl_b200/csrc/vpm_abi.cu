@@ -22,6 +22,7 @@
 
 #include "vpm_kernels.cuh"
 #include "vpm_kernels_f32.cuh"
+#include "vpm_kernels_tab.cuh"
 #include "vpm_leaf.cuh"
 #include "vpm_leaf_f32.cuh"
 #include "vpm_csr.cuh"

@@ -83,6 +83,23 @@ int vpm_set_option(vpm_handle *h, int option, int value) {
   if (!h) return VPM_EINVAL;
   switch (option) {
     case VPM_OPT_NEARFIELD_FP32: h->opt_nearfield_fp32 = value != 0; return VPM_OK;
+    case VPM_OPT_UJ_VARIANT:
+      if (value != 0 && value != 11 && value != 12 && value != 21 && value != 22 && value != 31 && value != 32 &&
+          value != 41 && value != 42)
+        return fail(h, VPM_EINVAL, "vpm_set_option: VPM_OPT_UJ_VARIANT must be 0, 11, 12, 21, 22, 31, 32, 41 or 42 (got %d)", value);
+      h->opt_uj_variant = value;
+      return VPM_OK;
+    case VPM_OPT_SFS_VARIANT:
+      if (value != 0 && value != 10 && value != 20)
+        return fail(h, VPM_EINVAL, "vpm_set_option: VPM_OPT_SFS_VARIANT must be 0, 10 or 20 (got %d)", value);
+      h->opt_sfs_variant = value;
+      return VPM_OK;
+    case VPM_OPT_UJ_CONST: h->opt_uj_const = value != 0; return VPM_OK;
+    case VPM_OPT_UJ_TABLE:
+      if (value < 0 || value > 2)
+        return fail(h, VPM_EINVAL, "vpm_set_option: VPM_OPT_UJ_TABLE must be 0, 1 or 2 (got %d)", value);
+      h->opt_uj_table = value;
+      return VPM_OK;
   }
   return fail(h, VPM_EINVAL, "vpm_set_option: unknown option %d", option);
 }

@@ -84,7 +84,19 @@ int vpm_test_math(vpm_handle *h, int op, int arg, const double *in, double *out,
   TRY(ensure(h, d.sbuf, (size_t)n * 2 * sizeof(double)));
   CK(h, cudaMemcpyAsync(d.tbuf.p, in, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
   double *o1 = (double *)d.sbuf.p, *o2 = o1 + n;
-  test_math_kernel<<<blocks_for(n, 256), 256, 0, st>>>(op, arg, (const double *)d.tbuf.p, o1, o2, n);
+  if (op == 4) {  // (A, B) of the bank-replicated table path (vpm_kernels_tab.cuh), arg = K_GAUS or K_GERF
+    if (arg != K_GERF && arg != K_GAUS) return fail(h, VPM_EINVAL, "vpm_test_math: op 4 needs arg 1 or 2");
+    const size_t smem = arg == K_GERF ? tab_smem_bytes<K_GERF>() : tab_smem_bytes<K_GAUS>();
+    if (arg == K_GERF) {
+      CK(h, cudaFuncSetAttribute(test_tab_kernel<K_GERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      test_tab_kernel<K_GERF><<<blocks_for(n, 256), 256, smem, st>>>((const double *)d.tbuf.p, o1, o2, n);
+    } else {
+      CK(h, cudaFuncSetAttribute(test_tab_kernel<K_GAUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      test_tab_kernel<K_GAUS><<<blocks_for(n, 256), 256, smem, st>>>((const double *)d.tbuf.p, o1, o2, n);
+    }
+  } else {
+    test_math_kernel<<<blocks_for(n, 256), 256, 0, st>>>(op, arg, (const double *)d.tbuf.p, o1, o2, n);
+  }
   CK(h, cudaGetLastError());
   CK(h, cudaMemcpyAsync(out, o1, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (out2) CK(h, cudaMemcpyAsync(out2, o2, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -25,6 +25,7 @@ struct Dev {
 };
 
 struct Plan {
+  int tab = 0;  // != 0: uj_pairs_tab_kernel with `tab` threads x 2 targets per CTA
   int T = 1;
   int unroll = 2;
   int nsplit = 1;
@@ -49,6 +50,10 @@ struct vpm_handle {
   std::vector<std::pair<void *, size_t>> pinned;  // ranges page-locked by vpm_pin_host
   int launches = 0;
   int opt_nearfield_fp32 = 0;  // VPM_OPT_NEARFIELD_FP32
+  int opt_uj_variant = 0;      // VPM_OPT_UJ_VARIANT  (0 = automatic)
+  int opt_sfs_variant = 0;     // VPM_OPT_SFS_VARIANT
+  int opt_uj_const = 0;        // VPM_OPT_UJ_CONST
+  int opt_uj_table = 0;        // VPM_OPT_UJ_TABLE
   int64_t fld_nf = 0, fld_np = -1;  // device mirror of the whole particle matrix (vpm_field_*)
   double fld_t_sgm = 0.0;           // CoreSpreading.t_sgm of the resident field
   int device_timing = 0;  // 1/2: ev[6..7] bracket the last _device U/J / SFS pair kernel

@@ -8,7 +8,9 @@ namespace {
 // few percent at most; when the target count alone cannot provide that, the sources are
 // split (>= 4 tiles per split) and the finish kernel adds the splits in order.
 enum PlanKind { PLAN_UJ = 0, PLAN_SFS = 1, PLAN_UJ_F32 = 2 };
-Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind) {
+// `variant`: 0 = automatic, else the validated value of VPM_OPT_UJ_VARIANT / VPM_OPT_SFS_VARIANT
+// ("<T><unroll>"; the plan is built FROM it, so grid and kernel always agree).
+Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind, int variant = 0) {
   Plan p;
   const int64_t ntiles = std::max<int64_t>(1, (ns + kTile - 1) / kTile);
   // two targets per thread (5 % faster in steady state) only when that still leaves enough
@@ -17,9 +19,9 @@ Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind) {
   const bool big = nblk2 * std::max<int64_t>(1, ntiles / 4) >= (int64_t)sm_count * 4 * 4;
   p.T = big ? 2 : 1;
   p.unroll = p.T == 2 ? 1 : 2;
-  if (const char *v = getenv(kind == PLAN_SFS ? "VPM_SFS_VARIANT" : "VPM_UJ_VARIANT")) {
-    int x = atoi(v);  // tuning aid: "<T><unroll>", e.g. 12, 21, 22
-    if (x / 10 >= 1 && x / 10 <= 2) { p.T = x / 10; p.unroll = x % 10; }
+  if (variant / 10 >= 1 && variant / 10 <= 2) {
+    p.T = variant / 10;
+    if (variant % 10 >= 1 && variant % 10 <= 2) p.unroll = variant % 10;
   }
   if (kind == PLAN_UJ_F32) p.T = 2;  // the FP32 sweep packs the two targets of a thread into f32x2
   const int min_tiles = big ? 4 : 1;
@@ -34,6 +36,49 @@ Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind) {
   p.pstride = round_up(std::max<int64_t>(nt, 1), 32);
   p.grid = dim3((unsigned)nblk, (unsigned)p.nsplit, 1);
   return p;
+}
+
+// Plan of the table kernel (vpm_kernels_tab.cuh): one CTA per SM, 512 (or 384) threads x 2 targets.
+// `fills` tells whether the field is large enough to give every SM >= 8 CTAs even at one
+// source tile per CTA -- below that the 128-thread kernels balance better.
+// variant (VPM_OPT_UJ_VARIANT): 41 / 42 = 512 threads, unroll 1 / 2;  31 / 32 = 384 threads.
+Plan make_plan_tab(int64_t nt, int64_t ns, int sm_count, bool *fills, int variant = 0) {
+  Plan p;
+  p.tab = (variant / 10 == 3) ? 384 : kTabThreads;
+  p.T = kTabT;
+  p.unroll = (variant % 10 == 2) ? 2 : 1;
+  const int64_t per = (int64_t)p.tab * kTabT;
+  const int64_t ntiles = std::max<int64_t>(1, (ns + kTile - 1) / kTile);
+  const int64_t nblk = std::max<int64_t>(1, (nt + per - 1) / per);
+  if (fills) *fills = nblk * ntiles >= (int64_t)sm_count * 8;
+  const bool big = nblk * std::max<int64_t>(1, ntiles / 4) >= (int64_t)sm_count * 16;
+  const int min_tiles = big ? 4 : 1;
+  const int64_t want_ctas = (int64_t)sm_count * 16;
+  int64_t nsplit = (want_ctas + nblk - 1) / nblk;
+  nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, std::max<int64_t>(1, ntiles / min_tiles)));
+  nsplit = std::min<int64_t>(nsplit, 1024);
+  p.tiles_per_split = (int)((ntiles + nsplit - 1) / nsplit);
+  p.nsplit = (int)((ntiles + p.tiles_per_split - 1) / p.tiles_per_split);
+  p.pstride = round_up(std::max<int64_t>(nt, 1), 32);
+  p.grid = dim3((unsigned)nblk, (unsigned)p.nsplit, 1);
+  return p;
+}
+
+template <int K, int THREADS, int UNROLL>
+cudaError_t launch_uj_tab_V(const Plan &p, const UjArgs &a, cudaStream_t st) {
+  const size_t smem = tab_smem_bytes<K>();
+  cudaError_t e = cudaFuncSetAttribute(uj_pairs_tab_kernel<K, THREADS, UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  uj_pairs_tab_kernel<K, THREADS, UNROLL><<<p.grid, THREADS, smem, st>>>(a);
+  return cudaSuccess;
+}
+template <int K>
+cudaError_t launch_uj_tab_K(const Plan &p, const UjArgs &a, cudaStream_t st) {
+  if (p.tab == 384) return p.unroll == 2 ? launch_uj_tab_V<K, 384, 2>(p, a, st) : launch_uj_tab_V<K, 384, 1>(p, a, st);
+  return p.unroll == 2 ? launch_uj_tab_V<K, 512, 2>(p, a, st) : launch_uj_tab_V<K, 512, 1>(p, a, st);
+}
+cudaError_t launch_uj_tab(int kernel, const Plan &p, const UjArgs &a, cudaStream_t st) {
+  return kernel == K_GERF ? launch_uj_tab_K<K_GERF>(p, a, st) : launch_uj_tab_K<K_GAUS>(p, a, st);
 }
 
 template <int K>
@@ -111,7 +156,7 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
     // optional FP32-arithmetic sweep (vpm_kernels_f32.cuh): FP32 records, FP64 partial sums in
     // the same layout, so the finish kernels are shared with the FP64 sweep
     TRY(ensure(h, d.rec, (size_t)ns_pad * kRecF * sizeof(float)));
-    plan = make_plan(nt, ns, d.sm_count, PLAN_UJ_F32);
+    plan = make_plan(nt, ns, d.sm_count, PLAN_UJ_F32, h->opt_uj_variant);
     TRY(ensure(h, d.partial, (size_t)plan.nsplit * kAcc * plan.pstride * sizeof(double)));
     prep_uj_records_f32<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, s0, ns, ns_pad, kernel, (float *)d.rec.p);
     h->launches++;
@@ -133,15 +178,22 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
     return VPM_OK;
   }
   TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
-  plan = make_plan(nt, ns, d.sm_count, PLAN_UJ);
+  const bool use_const = h->opt_uj_const != 0;
+  bool use_tab = false;
+  if ((kernel == K_GERF || kernel == K_GAUS) && !use_const && h->opt_uj_table != 2) {
+    bool fills = false;
+    Plan pt = make_plan_tab(nt, ns, d.sm_count, &fills, h->opt_uj_variant);
+    if (fills || h->opt_uj_table == 1) { plan = pt; use_tab = true; }
+  }
+  if (!use_tab) plan = make_plan(nt, ns, d.sm_count, PLAN_UJ, h->opt_uj_variant < 30 ? h->opt_uj_variant : 0);
+  if (use_const) plan.nsplit = 1;  // the constant-bank form keeps ONE set of sums across its launches
   TRY(ensure(h, d.partial, (size_t)plan.nsplit * kAcc * plan.pstride * sizeof(double)));
-  prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, s0, ns, ns_pad, kernel,
-                                                           (double *)d.rec.p);
+  if (use_tab)
+    prep_uj_records_tab<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, s0, ns, ns_pad, kernel, (double *)d.rec.p);
+  else
+    prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, s0, ns, ns_pad, kernel, (double *)d.rec.p);
   h->launches++;
-  const char *cenv = getenv("VPM_UJ_CONST");
-  const bool use_const = cenv && atoi(cenv) != 0;
   if (nt > 0 && ns > 0 && use_const) {
-    plan.nsplit = 1;
     UjConstArgs a;
     a.tpos = tpos; a.tld = tld; a.nt = nt;
     a.partial = (double *)d.partial.p; a.pstride = plan.pstride;
@@ -164,7 +216,8 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
     a.partial = (double *)d.partial.p; a.pstride = plan.pstride;
     a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
     if (time_pairs) CK(h, cudaEventRecord(d.ev[6], st));
-    launch_uj(kernel, plan, a, st);
+    if (use_tab) CK(h, launch_uj_tab(kernel, plan, a, st));
+    else launch_uj(kernel, plan, a, st);
     if (time_pairs) CK(h, cudaEventRecord(d.ev[7], st));
     h->launches++;
   } else {
@@ -181,7 +234,7 @@ int sfs_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *
               int mode = MODE_SFS) {
   const int64_t ns_pad = round_up(std::max<int64_t>(ns, 1), kTile);
   TRY(ensure(h, d.srec, (size_t)ns_pad * kSfsRec * sizeof(double)));
-  plan = make_plan(nt, ns, d.sm_count, PLAN_SFS);
+  plan = make_plan(nt, ns, d.sm_count, PLAN_SFS, h->opt_sfs_variant);
   TRY(ensure(h, d.partial, (size_t)std::max(1, plan.nsplit) * kAcc * plan.pstride * sizeof(double)));
   const int transposed = (flags & VPM_FLAG_TRANSPOSED) ? 1 : 0;
   prep_sfs_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, sJ, sjld, sjoff, stat, sld, sindex,

@@ -80,6 +80,17 @@ int vpm_num_devices(const vpm_handle *h);
                                     compute in FP32 arithmetic (split-precision positions, FP64 sums across
                                     tiles; errors ~1e-6 of the field maximum): the near field of UJ_fmm is added
                                     to a far field FastMultipole truncates at 1e-3..1e-6 anyway.  Default 0. */
+#define VPM_OPT_UJ_VARIANT 2      /* tuning aid: launch variant "<T><unroll>" of the FP64 U/J pair kernel, one of
+                                    11, 12, 21, 22 (T targets per thread, unroll of the source loop), or of the
+                                    table kernel of the gaussian families: 31, 32 (384 threads per CTA, unroll 1 / 2),
+                                    41, 42 (512 threads); 0 = automatic (default).  Any other value: VPM_EINVAL. */
+#define VPM_OPT_SFS_VARIANT 3     /* the same for the SFS pair kernel: 10, 20 or 0 (T only) */
+#define VPM_OPT_UJ_CONST 4        /* value != 0: constant-bank form of the U/J sweep (records copied 768 at a time
+                                    into __constant__ memory, one launch per chunk).  Default 0. */
+#define VPM_OPT_UJ_TABLE 5        /* gaussianerf / gaussian U/J sweep: 0 = automatic (default: the bank-replicated
+                                    log-spaced table kernel, csrc/vpm_kernels_tab.cuh, when the field is large
+                                    enough to fill the GPU with 1024-target CTAs), 1 = always, 2 = never (the
+                                    round-1 kernels). */
 int vpm_set_option(vpm_handle *h, int option, int value);
 
 /* ---- Hook 1: the UJ slot ---------------------------------------------- */

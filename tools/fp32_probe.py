@@ -28,9 +28,7 @@ src8 = torch.from_numpy(np.ascontiguousarray(vpm.source_system_to_buffer(pf).T))
 for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["winckelmans", "singular", "gaussianerf", "gaussian"]):
     f = sharding.ShardedField(h, src8, n, 0, 1, vpm.KERNELS[k].id)
     for flags, label in ((0, "fp64"), (32, "fp32 unroll1"), (32, "fp32 unroll2")):
-        os.environ["VPM_UJ_VARIANT"] = "22" if label.endswith("2") else "21"
-        if flags == 0:
-            os.environ.pop("VPM_UJ_VARIANT")
+        h.set_option(vpm._cabi.OPT_UJ_VARIANT, 0 if flags == 0 else (22 if label.endswith("2") else 21))
         f.uj(flags)
         torch.cuda.synchronize()
         best = 1e30

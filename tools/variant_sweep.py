@@ -21,7 +21,7 @@ src8 = torch.from_numpy(np.ascontiguousarray(vpm.source_system_to_buffer(pf).T))
 for k in kernels:
     f = sharding.ShardedField(h, src8, n, 0, 1, vpm.KERNELS[k].id)
     for v in variants:
-        os.environ["VPM_UJ_VARIANT"] = v
+        h.set_option(vpm._cabi.OPT_UJ_VARIANT, int(v))
         f.uj(0)
         torch.cuda.synchronize()
         best = 1e30
@@ -32,7 +32,7 @@ for k in kernels:
         print(f"{k:12s} variant {v}: {best:9.3f} ms  {n * n / best / 1e6:8.1f} G/s", flush=True)
     if len(sys.argv) > 4:
         for v in variants:
-            os.environ["VPM_SFS_VARIANT"] = v
+            h.set_option(vpm._cabi.OPT_SFS_VARIANT, int(v) // 10 * 10)
             f.sfs(8)
             torch.cuda.synchronize()
             best = 1e30
