@@ -271,6 +271,130 @@ def nearfield_extra(vpm, h, n):
     return out
 
 
+def near_fraction(pf, cutoff_s, samples=400000, seed=1):
+    """fraction of ordered pairs with r / sigma_source < cutoff_s (sampled)"""
+    n = pf.np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    i, j = rng.integers(0, n, samples), rng.integers(0, n, samples)
+    X, sig = pf.get_X()[:, :n], pf.particles[6, :n]
+    s = np.linalg.norm(X[:, i] - X[:, j], axis=0) / sig[j]
+    return float(np.mean(s < cutoff_s))
+
+
+FAR_CUTOFF = {"gaussianerf": 9.0, "gaussian": 3.45}
+
+
+def family_rates(vpm, h, pf, peak_tflops, kernels, reps=2):
+    """pair-kernel rate of each family on the field pf, far-field shortcut on and off.  roofline_frac for the
+    shortcut-OFF run credits the family's flops to every pair (every pair took the regularised evaluation);
+    for the shortcut-ON run the flops are credited per branch: the sampled fraction of pairs inside the
+    regularised range gets the family's count, the rest the singular kernel's 68 (a LOWER bound of the work
+    done: the branch is per warp, so some far pairs of mixed warps also took the regularised path)."""
+    import torch
+    from flowvpm_jl_b200 import sharding
+    n = pf.np
+    src8 = torch.from_numpy(np.ascontiguousarray(vpm.source_system_to_buffer(pf).T)).cuda()
+    out = {}
+    for name in kernels:
+        f = sharding.ShardedField(h, src8, n, 0, 1, vpm.KERNELS[name].id)
+        row = {}
+        for flags, tag in ((0, "shortcut_on"), (vpm._cabi.FLAG_NO_FARFIELD_SHORTCUT, "shortcut_off")):
+            if flags and name not in FAR_CUTOFF:
+                continue
+            f.uj(flags)
+            torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(reps):
+                f.uj(flags)
+                torch.cuda.synchronize()
+                best = min(best, h.timing()["uj_ms"])
+            rate = n * n / (best * 1e-3)
+            if name in FAR_CUTOFF and not flags:
+                fn = near_fraction(pf, FAR_CUTOFF[name])
+                flop = fn * F_UJ[name] + (1 - fn) * F_UJ["singular"]
+                row["pairs_inside_cutoff"] = fn
+            else:
+                flop = F_UJ[name]
+            row[tag] = {"interactions_per_s": rate, "kernel_ms": best, "flop_credited_per_pair": flop,
+                        "roofline_frac": rate * flop / 1e12 / peak_tflops}
+        out[name] = row
+    del src8
+    return out
+
+
+def dense_fields(vpm, h, peak_tflops):
+    """fields where a large share of the pairs is INSIDE the regularised range (the configurations that
+    actually use gaussianerf: CoreSpreading requires it, src/FLOWVPM.jl:265-267), next to the sparse C4 cloud
+    of the headline: BASELINE config 2 (two rings, 33 800 particles) and a compact blob (65 536 particles in
+    a unit cube, sigma = 3 lattice spacings)."""
+    R = 0.7906
+    c2 = vpm.fields.ring_field(Nphi=100, nc=6, R=R, Rcross=0.1 * R, rings=2, dZ=0.7906)
+    rng = np.random.Generator(np.random.PCG64(5))
+    n = 65536
+    blob = vpm.ParticleField(n)
+    blob.particles[0:3, :n] = rng.random((3, n))
+    blob.particles[3:6, :n] = rng.standard_normal((3, n)) / n
+    blob.particles[6, :n] = 3.0 / 40 * (1 + 0.1 * (rng.random(n) - 0.5))
+    blob.np = n
+    out = {}
+    for name, pf in (("c2_two_rings_33800", c2), ("blob_65536", blob)):
+        out[name] = {"n_particles": pf.np, "pairs_with_s_below_9": near_fraction(pf, 9.0),
+                     "by_kernel": family_rates(vpm, h, pf, peak_tflops, ["gaussianerf", "gaussian", "winckelmans"])}
+    return out
+
+
+def single_process_handle(vpm, n, kernel, ngpu):
+    """the deployment north_star describes: ONE process (the Julia caller) drives all GPUs through one handle.
+    UJ_direct(pfield; sfs=true) on the page-locked 46 x N host matrix: uploads rows X, Gamma, sigma, U/J + SFS
+    sweeps sharded over the devices (NCCL broadcast of the sources, all-gather of J), rows 10:27 and 40:42
+    written back -- everything inside the timed call."""
+    h = vpm.Handle(device_ids=list(range(ngpu)))
+    try:
+        pf = vpm.fields.cloud_field(n, kernel=vpm.KERNELS[kernel])
+        P = pf.particles
+        h.check(h.lib.vpm_pin_host(h.ptr, P.ctypes.data, P.nbytes))
+        out = {"n_gpus": ngpu, "n_particles": n, "kernel": kernel}
+        for sfs, tag in ((False, "uj"), (True, "uj_sfs")):
+            vpm.UJ_direct(pf, sfs=sfs, reset=True, reset_sfs=sfs, handle=h)
+            t = time.perf_counter()
+            vpm.UJ_direct(pf, sfs=sfs, reset=True, reset_sfs=sfs, handle=h)
+            dt = time.perf_counter() - t
+            out[tag] = {"s_per_call": dt, "interactions_per_s": (2 if sfs else 1) * n * n / dt,
+                        "h2d_bytes": n * 7 * 8, "d2h_bytes": n * (18 + (3 if sfs else 0)) * 8}
+        h.check(h.lib.vpm_unpin_host(h.ptr, P.ctypes.data))
+        out["what"] = "vpm.Handle(device_ids=range(N)) in rank 0's process; UJ_direct(pfield) on the pinned host matrix"
+        return out
+    finally:
+        h.close()
+
+
+def c5_nearfield(vpm, ngpu, logn=24, ncrits=(128, 512)):
+    """BASELINE config 5: 2^24 particles, leaf lists + near field on `ngpu` GPUs from one process"""
+    h = vpm.Handle(device_ids=list(range(ngpu)))
+    try:
+        n = 1 << logn
+        pf = vpm.fields.cloud_field(n, kernel=vpm.winckelmans)
+        h.check(h.lib.vpm_pin_host(h.ptr, pf.particles.ctypes.data, pf.particles.nbytes))
+        out = {"n_particles": n, "n_gpus": ngpu}
+        for ncrit in ncrits:
+            vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, handle=h, fetch=False)
+            t = time.perf_counter()
+            info = vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, handle=h, fetch=False)
+            t_tree = time.perf_counter() - t
+            vpm.UJ_nearfield(pf, reset=True, handle=h)
+            t = time.perf_counter()
+            vpm.UJ_nearfield(pf, reset=True, handle=h)
+            dt = time.perf_counter() - t
+            tm = h.timing()
+            out[f"ncrit_{ncrit}"] = {"leaves": info["n_leaves"], "list_pairs": info["n_pairs"], "interactions": tm["uj_pairs"],
+                                     "device_tree_s": t_tree, "nearfield_call_s": dt, "pair_kernel_ms_dev0": tm["uj_ms"],
+                                     "e2e_interactions_per_s": tm["uj_pairs"] / dt}
+        h.check(h.lib.vpm_unpin_host(h.ptr, pf.particles.ctypes.data))
+        return out
+    finally:
+        h.close()
+
+
 def ncu_traffic(n, kernel, world):
     """dram__bytes_read.sum + dram__bytes_write.sum of the pair kernel from the committed ncu
     --set full capture (profiles/uj_pairs_traffic.json), if it was taken at this size."""
@@ -435,19 +559,13 @@ def main():
         extras["sfs"] = {"interactions_per_s": n * n / (np.mean(sms) * 1e-3), "ms": float(np.mean(sms)),
                          "kernel": args.kernel,
                          "roofline_frac": n * n / (np.mean(skms) * 1e-3) * F_SFS[args.kernel] / 1e12 / peak_tflops}
-        by = {}
-        for name in sorted(F_UJ):
-            if name == args.kernel:
-                continue
-            field.kernel_id = vpm.KERNELS[name].id
-            m, km = timed_steps(lambda: field.uj(0), 1, 1)
-            by[name] = {"interactions_per_s": n * n / (np.mean(m) * 1e-3),
-                        "roofline_frac": n * n / (np.mean(km) * 1e-3) * F_UJ[name] / 1e12 / peak_tflops}
-            if name in ("gaussian", "gaussianerf"):
-                m2, km2 = timed_steps(lambda: field.uj(vpm._cabi.FLAG_NO_FARFIELD_SHORTCUT), 1, 0)
-                by[name]["no_farfield_shortcut_interactions_per_s"] = n * n / (np.mean(m2) * 1e-3)
-        field.kernel_id = kernel.id
-        extras["by_kernel"] = by
+        extras["by_kernel"] = family_rates(vpm, h, pf, peak_tflops, [k for k in sorted(F_UJ) if k != args.kernel])
+        extras["dense_fields"] = dense_fields(vpm, h, peak_tflops)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import smalln_bench
+        extras["small_n_latency"] = {"what": "one UJ_direct(pfield; sfs=true, reset=true, reset_sfs=true) call, wall clock "
+                                             "per call (us), host matrix pageable / page-locked, next to the CPU port on all cores",
+                                     "gaussianerf": smalln_bench.measure(h, "gaussianerf")}
         # optional FP32-arithmetic sweep (VPM_FLAG_FP32, north star's 1e-5 mode) against the FP32 FMA pipe
         import ctypes as C
         fv, fms = C.c_double(), C.c_double()
@@ -481,6 +599,26 @@ def main():
                                 "sample": desc + "; reference-equivalent C restatement (oracle/), Julia not available"}
     elif rank == 0:
         line["cpu_baseline"] = None
+
+    if world > 1:
+        # single-process legs: rank 0 alone drives all GPUs through ONE handle while the other ranks wait
+        # on the HOST (a key in torch.distributed's store): an NCCL barrier would leave a spinning kernel on
+        # every other GPU, time-slicing against rank 0's kernels there
+        sync_all()
+        import datetime
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            extras = {}
+            try:
+                extras["single_process_handle"] = single_process_handle(vpm, n, args.kernel, world)
+                if world >= 8 and not args.no_extras:
+                    extras["c5_nearfield_2p24"] = c5_nearfield(vpm, world)
+            except Exception as exc:  # noqa: BLE001 -- an extra must not take the headline line down
+                extras["single_process_error"] = repr(exc)
+            line["extras"] = extras
+            store.set("single_process_legs_done", "1")
+        else:
+            store.wait(["single_process_legs_done"], datetime.timedelta(minutes=30))
 
     if rank == 0:
         print(json.dumps(line))

@@ -14,7 +14,7 @@ from .particlefield import (ParticleField, Kernel, KERNELS, NFIELDS, kernel_defa
                             _reset_particles, _reset_particles_sfs,
                             X_INDEX, GAMMA_INDEX, SIGMA_INDEX, U_INDEX, VORTICITY_INDEX, J_INDEX,
                             PSE_INDEX, M_INDEX, C_INDEX, SFS_INDEX, STATIC_INDEX)
-from .uj import (ResidentField, UJ_direct, UJ_nearfield, leaf_lists, direct_buffers, nearfield_device, Estr_fmm, zeta_direct, zeta_fmm, get_handle,
+from .uj import (ResidentField, UJ_direct, UJ_nearfield, leaf_lists, direct_buffers, nearfield_device, fmm_nearfield_device, Estr_fmm, zeta_direct, zeta_fmm, get_handle,
                  set_handle,
                  source_system_to_buffer, buffer_to_target_system, ROW_POS, ROW_GRAD, ROW_HESS)
 from . import fields

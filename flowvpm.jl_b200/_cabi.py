@@ -15,7 +15,7 @@ SYMBOLS = [
     "vpm_create", "vpm_destroy", "vpm_last_error", "vpm_abi_version", "vpm_num_devices",
     "vpm_uj_direct", "vpm_uj_direct_f32", "vpm_uj_direct_st",
     "vpm_upload_state", "vpm_eval", "vpm_download_results",
-    "vpm_pin_host", "vpm_unpin_host", "vpm_set_option",
+    "vpm_pin_host", "vpm_unpin_host", "vpm_set_option", "vpm_nearfield_ranges",
     "vpm_p2p_buffers", "vpm_p2p_leafpairs", "vpm_estr_leafpairs",
     "vpm_zeta_direct", "vpm_zeta_leafpairs",
     "vpm_leaflists_build", "vpm_leaflists_get", "vpm_uj_nearfield",
@@ -85,6 +85,7 @@ def load():
     lib.vpm_eval.argtypes = [p, i32, i32]
     lib.vpm_download_results.argtypes = [p, p, i64, i64, i32]
     lib.vpm_set_option.argtypes = [p, i32, i32]
+    lib.vpm_nearfield_ranges.argtypes = [p, p, i64, i64, p, p, i64, p, i64, i64, p, p, p, i32, i32, i32]
     lib.vpm_pin_host.argtypes = [p, p, C.c_size_t]
     lib.vpm_unpin_host.argtypes = [p, p]
     lib.vpm_p2p_buffers.argtypes = [p, p, i64, i64, i64, i32, i32, i32, p, i64, i64, i32, i32, i32]

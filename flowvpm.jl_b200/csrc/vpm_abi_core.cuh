@@ -70,6 +70,7 @@ int vpm_destroy(vpm_handle *h) {
                    &d.ibuf, &d.jbuf, &d.fld, &d.scr, &d.scr2, &d.cubtmp, &d.tree, &d.tlist})
       if (b->p) cudaFree(b->p);
     for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
+    if (d.scratch_ev) cudaEventDestroy(d.scratch_ev);
     if (d.stream) cudaStreamDestroy(d.stream);
   }
   if (h->h_stat) cudaFreeHost(h->h_stat);
@@ -366,6 +367,7 @@ int vpm_uj_device(vpm_handle *h, const double *d_src8, int64_t ns, int64_t t0, i
   uj_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
   h->launches++;
   CK(h, cudaGetLastError());
+  TRY(scratch_release_async(h, d, st));
   h->timing.uj_pairs = nt * ns;
   h->timing.kernel_launches = h->launches;
   return VPM_OK;
@@ -397,6 +399,7 @@ int vpm_sfs_device(vpm_handle *h, const double *d_src8, const double *d_J9, cons
   sfs_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
   h->launches++;
   CK(h, cudaGetLastError());
+  TRY(scratch_release_async(h, d, st));
   h->timing.sfs_pairs = nt * ns;
   h->timing.kernel_launches = h->launches;
   return VPM_OK;

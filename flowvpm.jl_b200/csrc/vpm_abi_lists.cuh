@@ -104,6 +104,122 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
   return VPM_OK;
 }
 
+// Hook 3 in the call shape the reference shows (src/FLOWVPM_gpu.jl:637-643, helpers :554-602):
+//   fmm.nearfield_device!(target_system, target_indices::Vector{UnitRange}, switch, source_system, source_indices)
+// Both systems are ParticleFields (46 x N matrices, columns in the order the ranges index); the k-th target
+// range receives the sources of the source ranges src_offsets[k] .. src_offsets[k+1]-1 (what
+// combine_source_indices / expand_source_indices produced per target leaf).  U (rows 10:12) and J (rows 16:24)
+// of the targets are ACCUMULATED on (no reset: UJ_fmm resets before calling fmm!, src/FLOWVPM_UJ.jl:75-80).
+// Sources are replicated over the devices, target ranges are cut into contiguous runs of equal work and every
+// device moves its own target columns over its own PCIe link.
+int vpm_nearfield_ranges(vpm_handle *h, double *TP, int64_t nf_t, int64_t np_t, const int64_t *tb, const int64_t *te,
+                         int64_t ntr, const double *SP, int64_t nf_s, int64_t np_s, const int64_t *sb,
+                         const int64_t *se, const int64_t *soff, int kernel, int want_U, int want_J) {
+  const char *fn = "vpm_nearfield_ranges";
+  if (!h) return VPM_EINVAL;
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "%s: unknown kernel_id %d", fn, kernel);
+  if (np_t < 0 || np_s < 0 || ntr < 0 || nf_t < MIN_FIELDS - 19 || nf_s < 7)
+    return fail(h, VPM_EINVAL, "%s: negative size, target matrix with < 24 rows or source matrix with < 7 rows", fn);
+  if (ntr == 0 || np_t == 0 || np_s == 0 || (!want_U && !want_J)) return VPM_OK;
+  if (!TP || !SP || !tb || !te || !sb || !se || !soff) return fail(h, VPM_EINVAL, "%s: NULL argument", fn);
+  if (soff[0] != 0) return fail(h, VPM_EINVAL, "%s: src_offsets[0] must be 0", fn);
+  for (int64_t k = 0; k < ntr; ++k)
+    if (soff[k + 1] < soff[k]) return fail(h, VPM_EINVAL, "%s: src_offsets not non-decreasing at %lld", fn, (long long)k);
+  const int64_t nsr = soff[ntr];
+  if (nsr == 0) return VPM_OK;
+  if (nsr > INT32_MAX || ntr > INT32_MAX) return fail(h, VPM_EINVAL, "%s: more than 2^31 ranges", fn);
+  // the (target range, source range) list: entry i <-> (k, i) for soff[k] <= i < soff[k+1]
+  std::vector<int32_t> pt((size_t)nsr), ps((size_t)nsr);
+  for (int64_t k = 0; k < ntr; ++k)
+    for (int64_t i = soff[k]; i < soff[k + 1]; ++i) { pt[(size_t)i] = (int32_t)k; ps[(size_t)i] = (int32_t)i; }
+  h->launches = 0;
+  int G = (int)h->devs.size();
+  const int TLD = 18;  // device target buffer: rows 0:3 X, rows 3:18 = particle rows 10:24 (U, vorticity, J)
+  const int64_t ns_pad = round_up(np_s, kTile);
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    CK(h, cudaSetDevice(d.id));
+    TRY(ensure(h, d.tbuf, (size_t)np_t * TLD * sizeof(double)));
+    TRY(ensure(h, d.in7, (size_t)np_s * 7 * sizeof(double)));
+    TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
+  }
+  Dev &d0 = h->devs[0];
+  CK(h, cudaSetDevice(d0.id));
+  CK(h, cudaEventRecord(d0.ev[0], d0.stream));
+  TRY(h2d_rows(h, d0.stream, (double *)d0.in7.p, SP, nf_s, 7, np_s));
+  DevCsr c;
+  TRY(build_csr_device(h, fn, tb, te, ntr, np_t, sb, se, nsr, np_s, pt.data(), ps.data(), nsr, G, nullptr, 0, nullptr, 0, c));
+  if (c.nwi == 0) return VPM_OK;
+  G = c.G_eff;
+  std::vector<LeafCsr> csr(G);
+  csr[0] = c.csr;
+  for (int g = 1; g < G; ++g) {
+    Dev &d = h->devs[g];
+    CK(h, cudaSetDevice(d.id));
+    TRY(ensure(h, d.ibuf, h->devs[0].ibuf.cap));
+    csr[g] = rebase_csr(c.csr, h->devs[0].ibuf.p, d.ibuf.p);
+  }
+  if (G > 1) TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np_s * 7 * sizeof(double)));
+  if (G > 1) TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
+  std::vector<std::pair<int64_t, int64_t>> cols(G, {0, 0});
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    cudaStream_t st = d.stream;
+    const int64_t k0 = c.cut[g], k1 = c.cut[g + 1];
+    if (k1 <= k0) continue;
+    CK(h, cudaSetDevice(d.id));
+    const int64_t lf = c.first_leaf[g], ll = c.last_leaf[g + 1];
+    const int64_t col0 = G == 1 ? 0 : tb[lf] + c.first_off[g];
+    const int64_t col1 = G == 1 ? np_t : std::min<int64_t>(te[ll], tb[ll] + c.last_off[g + 1] + c.nt);
+    const size_t ncol = (size_t)(col1 - col0);
+    double *dt = (double *)d.tbuf.p + col0 * TLD;
+    CK(h, cudaMemcpy2DAsync(dt, TLD * sizeof(double), TP + col0 * nf_t + R_X, nf_t * sizeof(double), 3 * sizeof(double),
+                            ncol, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpy2DAsync(dt + 3, TLD * sizeof(double), TP + col0 * nf_t + R_U, nf_t * sizeof(double), 15 * sizeof(double),
+                            ncol, cudaMemcpyHostToDevice, st));
+    LeafUjArgs a;
+    a.csr = csr[g];
+    a.csr.wi_leaf += k0;
+    a.csr.wi_off += k0;
+    if (g == 0) CK(h, cudaEventRecord(d.ev[1], st));
+    a.tpos = (const double *)d.tbuf.p; a.tld = TLD; a.rec = (const double *)d.rec.p;
+    a.out = (double *)d.tbuf.p; a.urow = 3; a.jrow = 3 + (R_J - R_U); a.want_U = want_U; a.want_J = want_J;
+    a.shortcut = 1;
+    if (g == 0) CK(h, cudaEventRecord(d.ev[6], st));
+    launch_uj_leaf_any(h, d, st, kernel, c.nt, (unsigned)(k1 - k0), a, SrcView{(const double *)d.in7.p, 7, 0, 3, 6}, np_s, ns_pad);
+    if (g == 0) CK(h, cudaEventRecord(d.ev[7], st));
+    CK(h, cudaGetLastError());
+    if (g == 0) {
+      CK(h, cudaEventRecord(d.ev[2], st));
+      CK(h, cudaEventRecord(d.ev[3], st));
+      CK(h, cudaEventRecord(d.ev[4], st));
+    }
+    cols[g] = {col0, col1};
+  }
+  // downloads in a second pass (a D2H into pageable memory blocks the host: every device must have its
+  // kernel in flight before that happens)
+  for (int g = 0; g < G; ++g) {
+    Dev &d = h->devs[g];
+    if (cols[g].second <= cols[g].first) continue;
+    CK(h, cudaSetDevice(d.id));
+    const int64_t col0 = cols[g].first;
+    const size_t ncol = (size_t)(cols[g].second - col0);
+    CK(h, cudaMemcpy2DAsync(TP + col0 * nf_t + R_U, nf_t * sizeof(double), (double *)d.tbuf.p + col0 * TLD + 3,
+                            TLD * sizeof(double), 15 * sizeof(double), ncol, cudaMemcpyDeviceToHost, d.stream));
+    if (g == 0) CK(h, cudaEventRecord(d.ev[5], d.stream));
+  }
+  for (int g = G - 1; g >= 0; --g) {
+    CK(h, cudaSetDevice(h->devs[g].id));
+    CK(h, cudaStreamSynchronize(h->devs[g].stream));
+  }
+  h->timing.uj_pairs = c.pairs;
+  h->timing.sfs_pairs = 0;
+  h1_fill_timing(h, h->devs[0]);
+  h->timing.uj_ms = ev_ms(d0.ev[6], d0.ev[7]);
+  h->np_resident = -1;
+  return VPM_OK;
+}
+
 static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, int64_t nf, int64_t np,
                            const int64_t *tsort, const int64_t *ssort, const int64_t *tb, const int64_t *te,
                            int64_t ntl, const int64_t *sb, const int64_t *se, int64_t nsl, const int32_t *pt,
@@ -127,6 +243,7 @@ static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, i
     CK(h, cudaSetDevice(dg.id));
     TRY(ensure(h, dg.in7, (size_t)np * 7 * sizeof(double)));
     TRY(ensure(h, dg.jbuf, (size_t)np * 9 * sizeof(double)));
+    TRY(scratch_acquire(h, dg, dg.stream));
     TRY(ensure(h, dg.srec, (size_t)ns_pad * kSfsRec * sizeof(double)));
     if (G > 1) TRY(ensure(h, dg.tbuf, (size_t)np * 3 * sizeof(double)));
   }

@@ -21,6 +21,12 @@ struct Dev {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[10] = {};  // 0..5 phases of a call, 6..7 pair kernel, 8..9 cross-device ordering
+  // The sweep scratch (rec, srec, partial) is shared by every entry point.  The synchronous ones run on
+  // `stream` and return with it idle; vpm_uj_device / vpm_sfs_device run on the CALLER's stream and
+  // return without synchronising.  scratch_ev is recorded after their last kernel, and whoever touches
+  // the scratch next -- on any stream -- waits on it first (scratch_acquire).
+  cudaEvent_t scratch_ev = nullptr;
+  bool scratch_pending = false;
   Buf in7, stat, res18, sfs3, rec, srec, partial, tbuf, sbuf, ibuf, jbuf, fld, scr, scr2, cubtmp, tree, tlist;
 };
 
@@ -109,6 +115,19 @@ int ensure(vpm_handle *h, Buf &b, size_t bytes) {
 }
 
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// order stream `st` after the last stream-ordered (_device) use of the sweep scratch of `d`
+int scratch_acquire(vpm_handle *h, Dev &d, cudaStream_t st) {
+  if (d.scratch_pending) CK(h, cudaStreamWaitEvent(st, d.scratch_ev, 0));
+  return VPM_OK;
+}
+// the _device entry points: the scratch is in use on `st` until here
+int scratch_release_async(vpm_handle *h, Dev &d, cudaStream_t st) {
+  if (!d.scratch_ev) CK(h, cudaEventCreateWithFlags(&d.scratch_ev, cudaEventDisableTiming));
+  CK(h, cudaEventRecord(d.scratch_ev, st));
+  d.scratch_pending = true;
+  return VPM_OK;
+}
 
 bool valid_kernel(int k) { return k >= 0 && k <= 3; }
 

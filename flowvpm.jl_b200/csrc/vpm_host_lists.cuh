@@ -377,8 +377,8 @@ void launch_uj_leaf_f32(int kernel, int nt, unsigned nwi, const LeafUjArgsF &a, 
 }
 // records + leaf kernel of one device's share of the work items, FP64 or (option) FP32 arithmetic
 void launch_uj_leaf_any(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, int nt, unsigned nwi, const LeafUjArgs &a,
-                        const double *sbuf8, int64_t n_src, int64_t ns_pad) {
-  SrcView sv{sbuf8, 8, 0, 4, 7};
+                        SrcView sv, int64_t n_src, int64_t ns_pad) {
+  if (d.scratch_pending) cudaStreamWaitEvent(st, d.scratch_ev, 0);  // d.rec may still be read by a _device sweep
   if (h->opt_nearfield_fp32) {
     prep_uj_records_f32s<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (float *)d.rec.p);
     LeafUjArgsF f;
@@ -390,6 +390,11 @@ void launch_uj_leaf_any(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, int 
     launch_uj_leaf(kernel, nt, nwi, a, st);
   }
   h->launches += 2;
+}
+// the same for FastMultipole's 8-row source buffer [x y z rho Gx Gy Gz sigma]
+void launch_uj_leaf_any(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, int nt, unsigned nwi, const LeafUjArgs &a,
+                        const double *sbuf8, int64_t n_src, int64_t ns_pad) {
+  launch_uj_leaf_any(h, d, st, kernel, nt, nwi, a, SrcView{sbuf8, 8, 0, 4, 7}, n_src, ns_pad);
 }
 template <int K, int MODE>
 void launch_sfs_leaf_K(int nt, unsigned nwi, const LeafSfsArgs &a, cudaStream_t st) {

@@ -152,6 +152,7 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
              int64_t nt, SrcView src, int64_t s0, int64_t ns, int flags, Plan &plan,
              bool time_pairs = false) {
   const int64_t ns_pad = round_up(std::max<int64_t>(ns, 1), kTile);
+  TRY(scratch_acquire(h, d, st));
   if (flags & VPM_FLAG_FP32) {
     // optional FP32-arithmetic sweep (vpm_kernels_f32.cuh): FP32 records, FP64 partial sums in
     // the same layout, so the finish kernels are shared with the FP64 sweep
@@ -233,6 +234,7 @@ int sfs_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *
               const int64_t *sindex, int64_t ns, int flags, Plan &plan, bool time_pairs = false,
               int mode = MODE_SFS) {
   const int64_t ns_pad = round_up(std::max<int64_t>(ns, 1), kTile);
+  TRY(scratch_acquire(h, d, st));
   TRY(ensure(h, d.srec, (size_t)ns_pad * kSfsRec * sizeof(double)));
   plan = make_plan(nt, ns, d.sm_count, PLAN_SFS, h->opt_sfs_variant);
   TRY(ensure(h, d.partial, (size_t)std::max(1, plan.nsplit) * kAcc * plan.pstride * sizeof(double)));

@@ -151,9 +151,74 @@ end
 # ------------------------------------------------------------------------------
 # Hook 3 -- the FMM near-field device hook.  With `useGPU>0`, UJ_fmm passes
 # `nearfield_device=true` (src/FLOWVPM_UJ.jl:97) and FastMultipole calls
-# `nearfield_device!`; the whole direct_list goes to the GPU in one call instead of one
-# launch per target leaf (the removed CUDA.jl path, src/FLOWVPM_gpu.jl:554-643).
+# `fmm.nearfield_device!`.  The method below has the only call shape the reference shows
+# (src/FLOWVPM_gpu.jl:637-643): both systems are ParticleFields, `target_indices[k]` is the body
+# range of a target leaf and `source_indices[k]` the source range -- or the vector of source
+# ranges gathered for that leaf (combine_source_indices, :554-580).  The whole list goes to the
+# GPU(s) in ONE call (vpm_nearfield_ranges) instead of one launch per target leaf.
 # ------------------------------------------------------------------------------
+function fmm.nearfield_device!(target_system::vpm.ParticleField{Float64}, target_indices::AbstractVector{<:UnitRange},
+                               ::fmm.DerivativesSwitch{PS,VS,GS}, source_system::vpm.ParticleField{Float64},
+                               source_indices::AbstractVector) where {PS,VS,GS}
+    ntr = length(target_indices)
+    length(source_indices) == ntr || error("nearfield_device!: one source entry per target leaf expected")
+    tb = Int64[first(r) - 1 for r in target_indices]     # 0-based, half-open on the C side
+    te = Int64[last(r) for r in target_indices]
+    soff = zeros(Int64, ntr + 1)
+    sb, se = Int64[], Int64[]
+    for k in 1:ntr
+        g = source_indices[k]
+        for r in (g isa UnitRange ? (g,) : g)
+            push!(sb, first(r) - 1); push!(se, last(r))
+        end
+        soff[k + 1] = length(sb)
+    end
+    TP, SP = target_system.particles, source_system.particles
+    GC.@preserve TP SP tb te sb se soff check(ccall((:vpm_nearfield_ranges, lib[]), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int64,
+         Ptr{Float64}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Cint, Cint, Cint),
+        handle[], TP, size(TP, 1), target_system.np, tb, te, ntr,
+        SP, size(SP, 1), source_system.np, sb, se, soff, kernel_id(source_system.kernel), VS, GS))
+    return nothing
+end
+
+"""
+    UJ_fmm_cuda(pfield; verbose, rbf, sfs, reset, reset_sfs, autotune)
+
+`UJ_fmm` (src/FLOWVPM_UJ.jl:62-129) with the near field and the SFS term on the GPU(s) and
+NO edit of the reference: the reset rules (:75-80), the `fmm.fmm!` call with
+`nearfield_device=true` (:90-101; FastMultipole then calls `fmm.nearfield_device!` above), the
+autotune bookkeeping (:104-118) are restated; `Estr_fmm!` (:125) becomes `Estr_cuda!`.
+Install it in the slot: `ParticleField(maxp; UJ=FLOWVPMCuda.UJ_fmm_cuda, ...)`.
+"""
+function UJ_fmm_cuda(pfield::vpm.ParticleField{Float64}; verbose::Bool=false, rbf::Bool=false, sfs::Bool=false,
+                     sfs_type::Int=-1, transposed_sfs::Bool=true, reset::Bool=true, reset_sfs::Bool=false,
+                     autotune::Bool=true, optargs...)
+    reset && vpm._reset_particles(pfield)
+    (reset_sfs || sfs) && vpm._reset_particles_sfs(pfield)
+    o = pfield.fmm
+    if rbf
+        vpm.zeta_fmm(pfield)
+    else
+        args = fmm.fmm!(pfield; expansion_order=o.p - 1, leaf_size_source=max(o.ncrit, o.min_ncrit),
+                        multipole_acceptance=o.theta,
+                        error_tolerance=fmm.PowerRelativeGradient{o.relative_tolerance, o.absolute_tolerance, true}(),
+                        tune=true, shrink_recenter=o.shrink_recenter, nearfield_device=true,
+                        scalar_potential=false, hessian=true, silence_warnings=!verbose)
+        tuned, cache, target_tree, source_tree, m2l_list, direct_list, _ = args
+        if autotune
+            new_p = o.autotune_p ? tuned.expansion_order + 1 : o.p
+            new_ncrit = o.autotune_ncrit ? tuned.leaf_size_source[1] : o.ncrit
+            pfield.fmm = vpm.FMM(new_p, new_ncrit, o.theta, o.shrink_recenter, o.relative_tolerance,
+                                 o.absolute_tolerance, o.autotune_p, o.autotune_ncrit, o.autotune_reg_error,
+                                 o.default_rho_over_sigma, o.min_ncrit)
+        end
+        sfs && Estr_cuda!(pfield, target_tree, source_tree, direct_list)
+    end
+    return nothing
+end
+
+"The whole direct_list on FastMultipole's own (tree-sorted) buffers in one call (vpm_p2p_leafpairs)."
 function nearfield_cuda!(target_buffer::Matrix{Float64}, target_branches, source_system::vpm.ParticleField,
                          source_buffer::Matrix{Float64}, source_branches, direct_list;
                          velocity::Bool=true, velocity_gradient::Bool=true)
@@ -267,6 +332,10 @@ function nextstep_cuda!(pfield::vpm.ParticleField{Float64}, dt::Real; relax::Boo
                         clip_backscatter::Bool=false, force_positive::Bool=false,
                         control_directional::Bool=false, control_magnitude::Bool=false)
     form = pfield.formulation
+    # ClassicVPM{R} is an empty struct (src/FLOWVPM_formulation.jl:23) and its integrators pass
+    # reset_sfs=true on every substep: only the reformulated family is mirrored on the device
+    # (cVPM as ReformulatedVPM(0, 0), the reference's own `formulation_cVPM`)
+    form isa vpm.ReformulatedVPM || error("nextstep_cuda!: use ReformulatedVPM{R}(f, g) (cVPM = ReformulatedVPM(0, 0)); ClassicVPM stays on the host integrators")
     S = pfield.SFS
     sfs = S isa vpm.DynamicSFS ? 2 : (vpm.isSFSenabled(S) ? 1 : 0)
     Cs = S isa vpm.ConstantSFS ? S.Cs : 1.0
@@ -298,6 +367,6 @@ function nextstep_cuda!(pfield::vpm.ParticleField{Float64}, dt::Real; relax::Boo
     return nothing
 end
 
-export UJ_cuda, zeta_cuda
+export UJ_cuda, UJ_fmm_cuda, zeta_cuda
 
 end # module

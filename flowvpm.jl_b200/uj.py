@@ -152,6 +152,37 @@ def nearfield_device(target_buffer, target_leaves, source_buffer, source_leaves,
         pt.ctypes.data, ps.ctypes.data, len(pt), kernel.id, int(want_U), int(want_J)))
 
 
+def fmm_nearfield_device(target_system, target_indices, derivatives_switch, source_system, source_indices,
+                         *, handle=None):
+    """fmm.nearfield_device!(target_system, target_indices, switch, source_system, source_indices) in the
+    call shape the reference shows (src/FLOWVPM_gpu.jl:637-643; reached from UJ_fmm with useGPU > 0,
+    src/FLOWVPM_UJ.jl:97).  Both systems are ParticleFields; `target_indices[k]` is a `range` of particle
+    columns (0-based here, 1-based UnitRange in Julia), `source_indices[k]` the source range -- or the list
+    of source ranges that combine_source_indices (src/FLOWVPM_gpu.jl:554-580) gathered for that target
+    leaf.  `derivatives_switch` = (PS, VS, GS) as in fmm.DerivativesSwitch{PS,VS,GS}.  Accumulates U and J
+    of the target particles (no reset)."""
+    h = handle or get_handle()
+    TP, SP = target_system.particles, source_system.particles
+    _check_matrix(TP)
+    _check_matrix(SP)
+    if len(target_indices) != len(source_indices):
+        raise ValueError("target_indices and source_indices must have one entry per target leaf")
+    _, VS, GS = derivatives_switch
+    tb = _i64([r.start for r in target_indices])
+    te = _i64([r.stop for r in target_indices])
+    groups = [[g] if isinstance(g, range) else list(g) for g in source_indices]
+    for r in list(target_indices) + [r for g in groups for r in g]:
+        if r.step != 1:
+            raise ValueError("index ranges must have unit step")
+    soff = _i64(np.concatenate([[0], np.cumsum([len(g) for g in groups])]))
+    sb = _i64([r.start for g in groups for r in g])
+    se = _i64([r.stop for g in groups for r in g])
+    h.check(h.lib.vpm_nearfield_ranges(
+        h.ptr, TP.ctypes.data, TP.shape[0], target_system.np, tb.ctypes.data, te.ctypes.data, len(tb),
+        SP.ctypes.data, SP.shape[0], source_system.np, sb.ctypes.data, se.ctypes.data, soff.ctypes.data,
+        source_system.kernel.id, int(bool(VS)), int(bool(GS))))
+
+
 def Estr_fmm(pfield, target_sort_index, source_sort_index, target_leaves, source_leaves,
              direct_list, *, handle=None, no_farfield_shortcut=False):
     """Estr_fmm!(target_pfield, source_pfield, target_tree, source_tree, direct_list)

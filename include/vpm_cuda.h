@@ -136,11 +136,24 @@ int vpm_p2p_buffers(vpm_handle *h, double *tgt_buf, int64_t tgt_ld, int64_t t0, 
                     int64_t s1, int kernel_id, int want_U, int want_J);
 
 /* ---- Hook 3: FMM near-field device hook -------------------------------- */
-/* nearfield_device!(target_system, target_indices, switch, source_system,
- * source_indices) as reached from UJ_fmm with useGPU>0: src/FLOWVPM_UJ.jl:97,
- * call shape src/FLOWVPM_gpu.jl:637-643.  Buffers as in Hook 2, tree-sorted;
- * leaves are half-open body ranges; pair k = (pair_tgt[k], pair_src[k]) is the
- * direct_list.  Every listed pair is evaluated with fmm.direct!'s arithmetic. */
+/* fmm.nearfield_device!(target_system, target_indices::Vector{UnitRange}, switch, source_system,
+ * source_indices) in the ONLY call shape the reference shows (src/FLOWVPM_gpu.jl:637-643, reached from
+ * UJ_fmm with useGPU > 0, src/FLOWVPM_UJ.jl:97): both systems are ParticleFields, i.e. 46 x N matrices
+ * whose columns the ranges index; target range k = [tgt_begin[k], tgt_end[k]) (0-based, half-open)
+ * receives the sources of the source ranges src_offsets[k] .. src_offsets[k+1]-1, which is what the
+ * reference's combine_source_indices / expand_source_indices (:554-602) produced per target leaf.
+ * U (rows 10:12) and J (rows 16:24) of the target columns are accumulated on -- UJ_fmm has reset them
+ * before (src/FLOWVPM_UJ.jl:75-80).  want_U / want_J are the VS / GS switches of `switch`.
+ * Multi-GPU handles cut the target ranges into contiguous runs of equal work (they must then be
+ * increasing and non-overlapping, as tree leaves are; otherwise device 0 does everything). */
+int vpm_nearfield_ranges(vpm_handle *h, double *target_particles, int64_t nfields_t, int64_t np_t,
+                         const int64_t *tgt_begin, const int64_t *tgt_end, int64_t n_tgt_ranges,
+                         const double *source_particles, int64_t nfields_s, int64_t np_s,
+                         const int64_t *src_begin, const int64_t *src_end, const int64_t *src_offsets,
+                         int kernel_id, int want_U, int want_J);
+/* The same near field on FastMultipole's own buffers (as in Hook 2, tree-sorted) with the whole
+ * direct_list in one call: leaves are half-open body ranges; pair k = (pair_tgt[k], pair_src[k]).
+ * Every listed pair is evaluated with fmm.direct!'s arithmetic. */
 int vpm_p2p_leafpairs(vpm_handle *h, double *tgt_buf, int64_t tgt_ld, int64_t n_tgt,
                       int row_pos, int row_grad, int row_hess, const double *src_buf,
                       int64_t n_src, const int64_t *tgt_leaf_begin, const int64_t *tgt_leaf_end,
@@ -254,7 +267,12 @@ int vpm_field_tsgm(vpm_handle *h, double *t_sgm, int set);
 /* targets [t0,t1) of the same 8 x ns buffer; out12 is 12 x (t1-t0): U then J.
  * All pointers are device memory on the handle's first device; `stream` is a
  * cudaStream_t used as given (NULL = CUDA's default stream, e.g. torch's current
- * stream handle 0).  Overwrites out12. */
+ * stream handle 0).  Overwrites out12.
+ * Stream ordering: these two calls are asynchronous (they return once the kernels are queued on
+ * `stream`).  They use scratch buffers of the handle; the library records an event after the last
+ * kernel and makes the next user of that scratch -- another _device call on ANY stream, or any of
+ * the synchronous entry points -- wait on it, so calls may be issued on different streams without
+ * a synchronisation in between.  Outputs are valid once `stream` has reached this call's kernels. */
 int vpm_uj_device(vpm_handle *h, const double *d_src8, int64_t ns, int64_t t0, int64_t t1,
                   double *d_out12, int kernel_id, int flags, void *stream);
 /* SFS sweep for targets [t0,t1): d_J9 is 9 x ns (final J of every particle),

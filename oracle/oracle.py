@@ -41,12 +41,18 @@ def lib():
         L.vpm_oracle_zeta.restype = dbl
         L.vpm_oracle_direct_buffers.argtypes = [p, i64, i64, i64, p, i64, i64, i32, i32, i32]
         L.vpm_oracle_direct_buffers.restype = None
+        L.vpm_oracle_erf32.argtypes = [C.c_float]
+        L.vpm_oracle_erf32.restype = dbl
+        L.vpm_oracle_direct_buffers_f32.argtypes = [p, i64, i64, i64, p, i64, i64, i32, i32, i32]
+        L.vpm_oracle_direct_buffers_f32.restype = None
         L.vpm_oracle_direct_buffers_mt.argtypes = [p, i64, i64, i64, p, i64, i64, i32, i32, i32, i32]
         L.vpm_oracle_direct_buffers_mt.restype = None
         L.vpm_oracle_reset_particles.argtypes = [p, i64, i64]
         L.vpm_oracle_reset_particles_sfs.argtypes = [p, i64, i64]
         L.vpm_oracle_estr_direct.argtypes = [p, i64, i64, i32, i32, i32]
         L.vpm_oracle_estr_direct.restype = None
+        L.vpm_oracle_estr_direct_targets.argtypes = [p, i64, i64, p, i64, i32, i32, i32]
+        L.vpm_oracle_estr_direct_targets.restype = None
         L.vpm_oracle_uj_direct.argtypes = [p, i64, i64, i32, i32, i32]
         L.vpm_oracle_uj_direct.restype = i32
         L.vpm_oracle_direct_leafpairs.argtypes = [p, i64, p, p, p, p, p, p, p, i64, i32, i32, i32]
@@ -92,6 +98,19 @@ def erf64(x):
     return float(lib().vpm_oracle_erf64(float(x)))
 
 
+def erf32(x):
+    """custom_erf32 (Float32 in; the last branch returns a Float64, as in the reference)"""
+    return float(lib().vpm_oracle_erf32(C.c_float(float(x))))
+
+
+def direct_buffers_f32(tgt, t0, t1, src, s0, s1, kernel, want_U=True, want_J=True):
+    """fmm.direct! on Float32 buffers with Julia's promotion rules (a ParticleField{Float32}), in place"""
+    assert tgt.dtype == np.float32 and src.dtype == np.float32 and tgt.flags.f_contiguous and src.flags.f_contiguous
+    assert src.shape[0] == 8 and tgt.shape[0] >= 16
+    lib().vpm_oracle_direct_buffers_f32(tgt.ctypes.data, tgt.shape[0], int(t0), int(t1), src.ctypes.data,
+                                        int(s0), int(s1), _kid(kernel), int(want_U), int(want_J))
+
+
 def g_dgdr(kernel, s):
     g, dg = C.c_double(), C.c_double()
     lib().vpm_oracle_g_dgdr(_kid(kernel), float(s), C.byref(g), C.byref(dg))
@@ -121,6 +140,39 @@ def estr_direct(P, np_, kernel, transposed=True, nthreads=0):
     _f(P)
     lib().vpm_oracle_estr_direct(P.ctypes.data, P.shape[0], int(np_), _kid(kernel), int(transposed),
                                  int(nthreads or max_threads()))
+
+
+def estr_direct_targets(P, np_, targets, kernel, transposed=True, nthreads=0):
+    """Estr_direct for the listed target particles only (all non-static sources); adds into P's SFS rows."""
+    _f(P)
+    t = np.ascontiguousarray(targets, dtype=np.int64)
+    lib().vpm_oracle_estr_direct_targets(P.ctypes.data, P.shape[0], int(np_), t.ctypes.data, t.size, _kid(kernel),
+                                         int(transposed), int(nthreads or max_threads()))
+
+
+def uj_slice(P, np_, targets, kernel, *, sfs=True, transposed=True, nthreads=0):
+    """Reference values of U, J (and SFS) for the listed targets of the field P, every particle of P being a
+    source: U, J by fmm.direct! on buffers; SFS by Estr_direct over P AS IT STANDS (the J rows of P are the
+    velocity gradients the sweep reads -- the caller passes the field whose J the GPU just computed, so that
+    the SFS comparison is on identical inputs).  Returns (U[3,k], J[9,k], SFS[3,k])."""
+    _f(P)
+    t = np.ascontiguousarray(targets, dtype=np.int64)
+    nthreads = nthreads or num_procs()
+    src = np.zeros((8, np_), order="F")
+    src[0:3], src[4:7], src[7] = P[0:3, :np_], P[3:6, :np_], P[6, :np_]
+    src[3] = P[6, :np_]
+    tb = np.zeros((16, t.size), order="F")
+    tb[0:3] = P[0:3, t]
+    direct_buffers(tb, 0, t.size, src, 0, np_, kernel, True, True, nthreads)
+    sfs_out = None
+    if sfs:
+        Q = P  # in place on the SFS rows of the targets only (restored below)
+        before = Q[39:42, t].copy()
+        Q[39:42, t] = 0.0
+        estr_direct_targets(Q, np_, t, kernel, transposed, nthreads)
+        sfs_out = Q[39:42, t].copy()
+        Q[39:42, t] = before
+    return tb[4:7].copy(), tb[7:16].copy(), sfs_out
 
 
 def direct_buffers(tgt, t0, t1, src, s0, s1, kernel, want_U=True, want_J=True, nthreads=1):

@@ -229,6 +229,130 @@ void vpm_oracle_direct_buffers(double *tgt, int64_t ld, int64_t t0, int64_t t1,
 }
 
 /*
+ * ---- Float32 fields (ParticleField(n, Float32): R is a type parameter, src/FLOWVPM_particlefield.jl:120,134) ----
+ * Julia's promotion rules applied line by line to the SAME source: Float32 op Float32 stays Float32, an
+ * Int literal keeps the other operand's type, a Float64 constant or literal (const4, const2, sqr2, 2.5,
+ * 7.5, 3.0 ...) promotes to Float64; stores into the Float32 buffers round.  Below `float` expressions are
+ * Float32 arithmetic and `double` ones Float64 (gcc -O2 without -ffast-math / FLT_EVAL_METHOD 0 on x86-64).
+ *
+ * custom_erf32, src/FLOWVPM_gpu_erf.jl:124-156, coefficients :2-60 (the Float32 roundings of the Float64
+ * table, written here as casts).  Quirk restated: the last branch uses the Float64 `sb7` (:150), so S, the
+ * exponent and the result of that branch are Float64.  NOTE: g_dgdr_gauserf calls custom_erf(r/sqr2) with
+ * the Float64 constant sqr2, so a Float32 field reaches custom_erf64, not this function; it is restated
+ * because it is part of the reference's file and is checked against libm in tests/test_oracle_pinning.py.
+ */
+double vpm_oracle_erf32(float x) {
+  const float xabs = fabsf(x), sgn = x > 0.f ? 1.f : (x < 0.f ? -1.f : x), oneval = 1.f;
+  float val = sgn * oneval;
+#define F(c) ((float)(c))
+  if (xabs < 0.84375f) {
+    float z = x * x;
+    float r = F(pp0) + z * (F(pp1) + z * (F(pp2) + z * (F(pp3) + z * F(pp4))));
+    float s = oneval + z * (F(qq1) + z * (F(qq2) + z * (F(qq3) + z * (F(qq4) + z * F(qq5)))));
+    float y = r / s;
+    val = sgn * (xabs + xabs * y);
+  } else if (xabs < 1.25f) {
+    float s = xabs - oneval;
+    float P = F(pa0) + s * (F(pa1) + s * (F(pa2) + s * (F(pa3) + s * (F(pa4) + s * (F(pa5) + s * F(pa6))))));
+    float Q = oneval + s * (F(qa1) + s * (F(qa2) + s * (F(qa3) + s * (F(qa4) + s * (F(qa5) + s * F(qa6))))));
+    val = sgn * (F(erx) + P / Q);
+  } else if (xabs < 2.857142857142857f) {
+    float s = oneval / (x * x);
+    float R = F(ra0) + s * (F(ra1) + s * (F(ra2) + s * (F(ra3) + s * (F(ra4) + s * (F(ra5) + s * (F(ra6) + s * F(ra7)))))));
+    float S = oneval + s * (F(sa1) + s * (F(sa2) + s * (F(sa3) + s * (F(sa4) + s * (F(sa5) + s * (F(sa6) + s * (F(sa7) + s * F(sa8))))))));
+    float r = expf(-x * x - 0.5625f + R / S);
+    val = sgn * (oneval - r / xabs);
+  } else if (xabs < 6.0f) {
+    float s = oneval / (x * x);
+    float R = F(rb0) + s * (F(rb1) + s * (F(rb2) + s * (F(rb3) + s * (F(rb4) + s * (F(rb5) + s * F(rb6))))));
+    /* s*sb7 with the Float64 sb7 (:150): everything outward of it is Float64 */
+    double S = (double)oneval + (double)s * ((double)F(sb1) + (double)s * ((double)F(sb2) + (double)s * ((double)F(sb3) +
+               (double)s * ((double)F(sb4) + (double)s * ((double)F(sb5) + (double)s * ((double)F(sb6) + (double)s * sb7))))));
+    double r = exp((double)(-x * x - 0.5625f) + (double)R / S);
+    return (double)sgn * ((double)oneval - r / (double)xabs);
+  }
+#undef F
+  return (double)val;
+}
+
+/* g_dgdr(r::Float32) of the four families with Julia's promotion (src/FLOWVPM_kernel.jl:44-84) */
+static inline void g_dgdr_f32(int kernel, float r, double *g, double *dg) {
+  switch (kernel) {
+    case VPM_KERNEL_SINGULAR: *g = 1.0; *dg = 0.0; return;
+    case VPM_KERNEL_GAUSSIANERF: { /* const2, sqr2 are Float64; -r*r/2 and its exp are Float32 */
+      float e = expf(-r * r / 2);
+      double aux = c_const2 * (double)r * (double)e;
+      *g = vpm_oracle_erf64((double)r / c_sqr2) - aux;
+      *dg = (double)r * aux;
+      return;
+    }
+    case VPM_KERNEL_GAUSSIAN: { /* integer literals only: everything stays Float32 */
+      float aux = expf(-r * r * r);
+      *g = (double)(1 - aux);
+      *dg = (double)(3 * r * r * aux);
+      return;
+    }
+    default: { /* winckelmans: aux0 chain Float32, the literals 2.5 and 7.5 promote */
+      float aux0 = r * r + 1;
+      float aux02 = aux0 * aux0;
+      aux0 = aux02 * aux02 * aux0;
+      aux0 = sqrtf(aux0);
+      *g = (double)(r * r * r) * ((double)(r * r) + 2.5) / (double)aux0;
+      *dg = 7.5 * (double)r * (double)r / (double)(aux0 * (r * r + 1));
+      return;
+    }
+  }
+}
+
+/*
+ * fmm.direct! (src/FLOWVPM_fmm.jl:102-168) on Float32 buffers: dx, r2, r, r3inv and the cross-product
+ * factors are Float32; -const4 promotes crss, U, aux2 and the J entries to Float64; every setter adds
+ * in Float64 and rounds into the Float32 buffer (`buffer[i] += val`).
+ */
+void vpm_oracle_direct_buffers_f32(float *tgt, int64_t ld, int64_t t0, int64_t t1, const float *src,
+                                   int64_t s0, int64_t s1, int kernel, int want_U, int want_J) {
+  init_consts();
+  for (int64_t is = s0; is < s1; ++is) {
+    const float *S = src + 8 * is;
+    const float gamma_x = S[4], gamma_y = S[5], gamma_z = S[6];
+    const float source_x = S[0], source_y = S[1], source_z = S[2];
+    const float sigma = S[7];
+    for (int64_t jt = t0; jt < t1; ++jt) {
+      float *T = tgt + ld * jt;
+      float dx = T[0] - source_x, dy = T[1] - source_y, dz = T[2] - source_z;
+      float r2 = dx * dx + dy * dy + dz * dz;
+      if (r2 != 0.0f) {
+        float r = sqrtf(r2);
+        double g_sgm, dg_sgmdr;
+        g_dgdr_f32(kernel, r / sigma, &g_sgm, &dg_sgmdr);
+        float r3inv = 1.0f / (r2 * r);
+        double crss1 = -c_const4 * (double)r3inv * (double)(dy * gamma_z - dz * gamma_y);
+        double crss2 = -c_const4 * (double)r3inv * (double)(dz * gamma_x - dx * gamma_z);
+        double crss3 = -c_const4 * (double)r3inv * (double)(dx * gamma_y - dy * gamma_x);
+        if (want_U) {
+          T[4] = (float)((double)T[4] + g_sgm * crss1);
+          T[5] = (float)((double)T[5] + g_sgm * crss2);
+          T[6] = (float)((double)T[6] + g_sgm * crss3);
+        }
+        if (want_J) {
+          double aux = dg_sgmdr / (double)(sigma * r) - 3 * g_sgm / (double)r2;
+          double aux2 = -c_const4 * g_sgm * (double)r3inv;
+          T[7] = (float)((double)T[7] + (aux * crss1 * (double)dx));
+          T[8] = (float)((double)T[8] + (aux * crss2 * (double)dx - aux2 * (double)gamma_z));
+          T[9] = (float)((double)T[9] + (aux * crss3 * (double)dx + aux2 * (double)gamma_y));
+          T[10] = (float)((double)T[10] + (aux * crss1 * (double)dy + aux2 * (double)gamma_z));
+          T[11] = (float)((double)T[11] + (aux * crss2 * (double)dy));
+          T[12] = (float)((double)T[12] + (aux * crss3 * (double)dy - aux2 * (double)gamma_x));
+          T[13] = (float)((double)T[13] + (aux * crss1 * (double)dz - aux2 * (double)gamma_y));
+          T[14] = (float)((double)T[14] + (aux * crss2 * (double)dz + aux2 * (double)gamma_x));
+          T[15] = (float)((double)T[15] + (aux * crss3 * (double)dz));
+        }
+      }
+    }
+  }
+}
+
+/*
  * Threaded form: contiguous target blocks per thread, every block sees all
  * sources in index order -- the per-target accumulation order is therefore the
  * same as the serial loop (FastMultipole's threaded driver is not under
@@ -310,6 +434,29 @@ void vpm_oracle_estr_direct(double *P, int64_t nf, int64_t np, int kernel, int t
 #pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 0 ? nthreads : 1)
   for (int64_t it = 0; it < np; ++it) {
     double *tp = P + nf * it;
+    if (tp[R_STATIC] != 0.0) continue;
+    double tx = tp[0], ty = tp[1], tz = tp[2];
+    for (int64_t is = 0; is < np; ++is) {
+      const double *sp = P + nf * is;
+      if (sp[R_STATIC] != 0.0) continue;
+      double dx = sp[0] - tx, dy = sp[1] - ty, dz = sp[2] - tz;
+      double r = sqrt(dx * dx + dy * dy + dz * dz);
+      estr_pair(tp, sp, r, kernel, transposed);
+    }
+  }
+}
+
+/*
+ * The same sweep for a LIST of targets only (full-size parity tests: the GPU does the whole
+ * field, the oracle re-does a few hundred targets against all sources).  `targets[k]` are
+ * particle indices; the sums are added into P's own SFS rows of those particles.
+ */
+void vpm_oracle_estr_direct_targets(double *P, int64_t nf, int64_t np, const int64_t *targets,
+                                    int64_t ntargets, int kernel, int transposed, int nthreads) {
+  init_consts();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int64_t k = 0; k < ntargets; ++k) {
+    double *tp = P + nf * targets[k];
     if (tp[R_STATIC] != 0.0) continue;
     double tx = tp[0], ty = tp[1], tz = tp[2];
     for (int64_t is = 0; is < np; ++is) {

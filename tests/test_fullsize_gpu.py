@@ -13,20 +13,63 @@ from oracle import oracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("kernel", ["winckelmans", "gaussianerf"])
-def test_full_size_slice_parity(vpm, handle, kernel):
+def slice_targets(n, k_head=96, k_rand=160, seed=0):
+    rng = np.random.default_rng(seed)
+    return np.unique(np.concatenate([np.arange(min(n, k_head)), rng.choice(n, min(n, k_rand), replace=False),
+                                     [n - 1]])).astype(np.int64)
+
+
+def check_slice(pf, idx, kernel, what, sfs=True):
+    """GPU did the whole field in pf.particles; the oracle re-does the targets `idx` against all sources
+    (SFS over the J rows the GPU produced: identical inputs for the second sweep)."""
+    P, n = pf.particles, pf.np
+    U, J, S = oracle.uj_slice(P, n, idx, kernel, sfs=sfs, transposed=pf.transposed)
+    errs = {"U": relerr(P[9:12, idx], U), "J": relerr(P[15:24, idx], J)}
+    if sfs:
+        errs["SFS"] = relerr(P[39:42, idx], S)
+        assert np.abs(S).max() > 0
+    assert all(v < TOL_FP64 for v in errs.values()), (what, errs)
+    assert np.all(np.isfinite(P[9:27, :n])) and np.all(np.isfinite(P[39:42, :n]))
+    return errs
+
+
+@pytest.mark.parametrize("kernel", ["singular", "gaussian", "gaussianerf", "winckelmans"])
+def test_c4_full_size_slice_parity_with_sfs(vpm, handle, kernel):
+    """BASELINE config 4 at N = 2^20: U, J AND SFS of the whole cloud on the GPU, 257 targets re-done by the oracle"""
     n = 1 << 20
     pf = vpm.fields.cloud_field(n, kernel=vpm.KERNELS[kernel])
-    vpm.UJ_direct(pf, reset=True)
-    sb = vpm.source_system_to_buffer(pf)
-    rng = np.random.default_rng(0)
-    idx = np.concatenate([np.arange(96), rng.choice(n, 160, replace=False)])
-    tb = np.zeros((16, len(idx)), order="F")
-    tb[0:3] = pf.get_X()[:, idx]
-    oracle.direct_buffers(tb, 0, len(idx), sb, 0, n, kernel, True, True, oracle.max_threads())
-    assert relerr(pf.get_U()[:, idx], tb[4:7]) < TOL_FP64
-    assert relerr(pf.get_J()[:, idx], tb[7:16]) < TOL_FP64
-    assert np.all(np.isfinite(pf.get_U())) and np.all(np.isfinite(pf.get_J()))
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    print(kernel, check_slice(pf, slice_targets(n), kernel, f"C4/{kernel}"))
+
+
+@pytest.mark.parametrize("kernel", ["gaussianerf", "winckelmans"])
+def test_c2_leapfrog_full_field(vpm, handle, kernel):
+    """BASELINE config 2 at its full size: two rings, Nphi = 100, nc = 6 -> 33 800 particles
+    (test/runtests_leapfrog.jl:42-46 geometry), the WHOLE field against the oracle, SFS included"""
+    R = 0.7906
+    pf = vpm.fields.ring_field(Nphi=100, nc=6, R=R, Rcross=0.1 * R, rings=2, dZ=0.7906, kernel=vpm.KERNELS[kernel])
+    assert pf.np == 33800
+    ref = pf.particles.copy(order="F")
+    oracle.uj_direct(ref, pf.np, kernel, sfs=True, reset=True, reset_sfs=True, nthreads=oracle.num_procs())
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    from helpers import assert_parity, stretching
+    print(kernel, assert_parity(pf.particles, ref, pf.np, what=f"C2/{kernel}"))
+    assert relerr(stretching(pf.particles, pf.np), stretching(ref, pf.np)) < TOL_FP64
+
+
+@pytest.mark.parametrize("kernel", ["gaussianerf", "winckelmans"])
+def test_c3_jet_slice_with_static_and_sfs(vpm, handle, kernel):
+    """BASELINE config 3 shape at its size: jet column of ~3e5 particles, 10 % static inflow, U/J + SFS;
+    a slice of targets (static and free ones) re-done by the oracle"""
+    pf = vpm.fields.jet_field(n_target=300_000, kernel=vpm.KERNELS[kernel])
+    n = pf.np
+    st = pf.get_static() != 0
+    assert n >= 299_000 and 0.05 < st.mean() < 0.15
+    vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True)
+    idx = slice_targets(n, k_head=64, k_rand=192, seed=3)
+    assert st[idx].any() and (~st[idx]).any()
+    print(kernel, check_slice(pf, idx, kernel, f"C3/{kernel}"))
+    assert np.all(pf.particles[39:42, :n][:, st] == 0)   # static particles take no part in the SFS sweep
 
 
 def test_linearity_and_superposition(vpm, handle):

@@ -278,3 +278,27 @@ def test_corespreading_rbf_multi_gpu(vpm):
             assert relerr(pf.particles[rows, :pf.np], ref[rows, :pf.np]) < 1e-8, rows
     finally:
         h.close()
+
+
+def test_nearfield_device_call_shape_multi_gpu(vpm):
+    """Hook 3 in the reference's call shape (vpm_nearfield_ranges) on a multi-GPU handle: target ranges cut
+    over the devices, every device moving its own columns; bit-identical to one device"""
+    g = _ngpu()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from test_hook3_shape_gpu import combine_source_indices, sorted_system, reference, SWITCH_UJ
+    pf = vpm.fields.cloud_field(20000, kernel=vpm.winckelmans, seed=17)
+    ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=64, theta=0.4)
+    ti, si = combine_source_indices(ll["direct_list"], ll["leaf_begin"], ll["leaf_end"])
+    outs = []
+    for ng in (1, min(g, 4)):
+        h = vpm.Handle(ng)
+        try:
+            s = sorted_system(vpm, pf, ll["sort_index"])
+            vpm.fmm_nearfield_device(s, ti, SWITCH_UJ, s, si, handle=h)
+            outs.append(s.particles.copy(order="F"))
+        finally:
+            h.close()
+    U, J = reference(sorted_system(vpm, pf, ll["sort_index"]), ll, "winckelmans")
+    assert relerr(outs[0][9:12, :pf.np], U) < TOL_FP64 and relerr(outs[0][15:24, :pf.np], J) < TOL_FP64
+    assert np.array_equal(outs[0], outs[1])

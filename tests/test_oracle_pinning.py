@@ -47,6 +47,33 @@ def _tail_tol(v, eps):
     return 1e-300 if v == 0 else eps * v * (1 + abs(math.log(v))) + 1e-300
 
 
+def test_erf32_restatement_matches_libm():
+    """custom_erf32 (src/FLOWVPM_gpu_erf.jl:124-156) in Float32 arithmetic, Float64 `sb7` quirk included"""
+    xs = np.concatenate([np.linspace(-7, 7, 8001), [0.84374, 0.84376, 1.2499, 1.2501, 2.857, 2.858, 5.99, 6.01]])
+    worst = max(abs(oracle.erf32(np.float32(x)) - math.erf(float(np.float32(x)))) for x in xs)
+    assert worst < 2e-7, worst
+    assert oracle.erf32(0.0) == 0.0 and oracle.erf32(7.0) == 1.0 and oracle.erf32(-7.0) == -1.0
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_float32_field_semantics_close_to_float64(kernel, vpm):
+    """fmm.direct! on Float32 buffers under Julia's promotion rules (ParticleField{Float32}) against the
+    Float64 restatement on the same (Float32-rounded) inputs: 1e-5 is the north star's FP32 bar.  Compact
+    field (positions O(1), neighbour distances O(0.1)): the Float32 dx of the reference carries 1e-6."""
+    pf = vpm.fields.cloud_field(600, kernel=vpm.KERNELS[kernel], seed=2)
+    pf.particles[0:3] *= np.array([[1.0], [1.0], [1.0 / 7]])   # unit cube
+    src32 = np.asfortranarray(vpm.source_system_to_buffer(pf).astype(np.float32))
+    tb32 = np.zeros((16, pf.np), dtype=np.float32, order="F")
+    tb32[0:3] = src32[0:3]
+    oracle.direct_buffers_f32(tb32, 0, pf.np, src32, 0, pf.np, kernel)
+    src64 = np.asfortranarray(src32.astype(np.float64))
+    tb64 = np.zeros((16, pf.np), order="F")
+    tb64[0:3] = src64[0:3]
+    oracle.direct_buffers(tb64, 0, pf.np, src64, 0, pf.np, kernel)
+    assert relerr(tb32[4:7], tb64[4:7]) < 1e-5 and relerr(tb32[7:16], tb64[7:16]) < 1e-5
+    assert relerr(tb32[4:7], tb64[4:7]) > 1e-9   # it IS a Float32 evaluation
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_g_dgdr_zeta_vs_mpmath(kernel):
     for s in [1e-3, 0.01, 0.1, 0.3, 0.7, 1.0, 1.5, 2.5, 4.0, 6.0, 8.4, 8.6, 12.0, 40.0]:

@@ -225,6 +225,20 @@ def test_uj_direct_f32(vpm, handle, kernel):
     assert_parity(pf32.particles, ref, pf32.np, tol=TOL_FP32)
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_uj_direct_f32_vs_float32_field_semantics(vpm, handle, kernel):
+    """the Matrix{Float32} entry point against the reference's OWN Float32 behaviour (Julia promotion rules
+    restated in oracle.direct_buffers_f32): both are within 1e-5 of each other on a compact field"""
+    pf32 = vpm.fields.cloud_field(2000, kernel=vpm.KERNELS[kernel], seed=6, R=np.float32)
+    pf32.particles[2] /= 7.0   # unit cube: positions O(1), so the reference's Float32 dx keeps ~1e-6
+    src32 = np.asfortranarray(pf32.particles[[0, 1, 2, 6, 3, 4, 5, 6]][:, :pf32.np])
+    tb32 = np.zeros((16, pf32.np), dtype=np.float32, order="F")
+    tb32[0:3] = src32[0:3]
+    oracle.direct_buffers_f32(tb32, 0, pf32.np, src32, 0, pf32.np, kernel)
+    vpm.UJ_direct(pf32, reset=True)
+    assert relerr(pf32.get_U(), tb32[4:7]) < TOL_FP32 and relerr(pf32.get_J(), tb32[7:16]) < TOL_FP32
+
+
 # ------------------------------------------------ Hook 2: fmm.direct! buffers
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("want_U,want_J", [(True, True), (True, False), (False, True)])

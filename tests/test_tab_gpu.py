@@ -153,3 +153,33 @@ def test_option_validation(vpm, handle):
             handle.set_option(opt, bad)
     for v in (11, 12, 21, 22, 31, 32, 41, 42, 0):
         handle.set_option(vpm._cabi.OPT_UJ_VARIANT, v)
+
+
+def test_device_entry_points_on_two_streams(vpm, handle):
+    """vpm_uj_device / vpm_sfs_device return without synchronising and share the handle's scratch: two calls
+    on DIFFERENT streams back to back (and a synchronous call right after) must not corrupt each other"""
+    import torch
+    n1, n2 = 40000, 3000
+    f1 = vpm.fields.cloud_field(n1, kernel=vpm.winckelmans, seed=41)
+    f2 = vpm.fields.cloud_field(n2, kernel=vpm.gaussianerf, seed=42)
+    s1 = torch.from_numpy(np.ascontiguousarray(vpm.source_system_to_buffer(f1).T)).cuda()
+    s2 = torch.from_numpy(np.ascontiguousarray(vpm.source_system_to_buffer(f2).T)).cuda()
+    o1 = torch.zeros((n1, 12), dtype=torch.float64, device="cuda")
+    o2 = torch.zeros((n2, 12), dtype=torch.float64, device="cuda")
+    # references, one at a time
+    r1, r2 = torch.zeros_like(o1), torch.zeros_like(o2)
+    st0 = torch.cuda.current_stream().cuda_stream
+    handle.check(handle.lib.vpm_uj_device(handle.ptr, s1.data_ptr(), n1, 0, n1, r1.data_ptr(), 3, 0, st0))
+    torch.cuda.synchronize()
+    handle.check(handle.lib.vpm_uj_device(handle.ptr, s2.data_ptr(), n2, 0, n2, r2.data_ptr(), 2, 0, st0))
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        o1.zero_(); o2.zero_()
+        torch.cuda.synchronize()
+        handle.check(handle.lib.vpm_uj_device(handle.ptr, s1.data_ptr(), n1, 0, n1, o1.data_ptr(), 3, 0, a.cuda_stream))
+        handle.check(handle.lib.vpm_uj_device(handle.ptr, s2.data_ptr(), n2, 0, n2, o2.data_ptr(), 2, 0, b.cuda_stream))
+        vpm.UJ_direct(f2, reset=True)          # synchronous entry point on the handle's own stream
+        torch.cuda.synchronize()
+        assert torch.equal(o1, r1) and torch.equal(o2, r2)
+        assert np.array_equal(f2.get_U(), r2[:, 0:3].cpu().numpy().T)

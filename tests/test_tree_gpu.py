@@ -125,3 +125,37 @@ def test_leafpairs_run_to_run_bit_identical(vpm, handle):
         vpm.nearfield_device(tb, leaves, sb, leaves, dl, vpm.gaussianerf)
         outs.append(tb)
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_c5_nearfield_2p24_slice_parity(vpm, handle):
+    """BASELINE config 5 at its size: 2^24 particles, leaf lists (ncrit 128, theta = 0.4) and the near field
+    of UJ_fmm on the device; five target leaves (first, last, three inside) re-done by the CPU oracle over
+    the same list (fmm.direct! arithmetic per (target leaf, source leaf) entry, list order)."""
+    n = 1 << 24
+    pf = vpm.fields.cloud_field(n, kernel=vpm.winckelmans)
+    ll = vpm.leaf_lists(pf, ncrit=128, theta=0.4)
+    lb, le, pt, ps, order = ll["leaf_begin"], ll["leaf_end"], ll["pair_tgt"], ll["pair_src"], ll["sort_index"]
+    nl = len(lb)
+    assert nl > 100_000 and len(pt) > 10_000_000
+    assert np.all(pt[1:] >= pt[:-1])                       # grouped by target leaf
+    assert le[-1] == n and np.array_equal(lb[1:], le[:-1])  # leaves tile the sorted order
+    vpm.UJ_nearfield(pf, reset=True)
+    tm = handle.timing()
+    sizes = (le - lb).astype(np.int64)
+    assert tm["uj_pairs"] == int((sizes[pt] * sizes[ps]).sum())
+    starts = np.searchsorted(pt, np.arange(nl + 1))
+    X, G, sg = pf.get_X(), pf.get_Gamma(), pf.get_sigma()
+    worst = 0.0
+    for leaf in (0, nl // 3, nl // 2, (2 * nl) // 3, nl - 1):
+        tcols = order[lb[leaf]:le[leaf]]
+        tb = np.zeros((16, len(tcols)), order="F")
+        tb[0:3] = X[:, tcols]
+        for sl in ps[starts[leaf]:starts[leaf + 1]]:
+            scols = order[lb[sl]:le[sl]]
+            sb = np.zeros((8, len(scols)), order="F")
+            sb[0:3], sb[4:7], sb[3], sb[7] = X[:, scols], G[:, scols], sg[scols], sg[scols]
+            oracle.direct_buffers(tb, 0, len(tcols), sb, 0, len(scols), "winckelmans")
+        got = np.vstack([pf.particles[9:12, tcols], pf.particles[15:24, tcols]])
+        worst = max(worst, relerr(got[0:3], tb[4:7]), relerr(got[3:12], tb[7:16]))
+    assert worst < TOL_FP64, worst
+    assert np.all(np.isfinite(pf.particles[9:24, :n]))
