@@ -18,3 +18,5 @@ from .uj import (ResidentField, UJ_direct, UJ_nearfield, leaf_lists, direct_buff
                  set_handle,
                  source_system_to_buffer, buffer_to_target_system, ROW_POS, ROW_GRAD, ROW_HESS)
 from . import fields
+from . import io
+from .io import save

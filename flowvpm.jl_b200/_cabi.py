@@ -30,7 +30,7 @@ KERNEL_SINGULAR, KERNEL_GAUSSIAN, KERNEL_GAUSSIANERF, KERNEL_WINCKELMANS = 0, 1,
 FLAG_RESET, FLAG_RESET_SFS, FLAG_SFS, FLAG_TRANSPOSED, FLAG_NO_FARFIELD_SHORTCUT = 1, 2, 4, 8, 16
 FLAG_FP32 = 32
 OPT_NEARFIELD_FP32 = 1
-OPT_UJ_VARIANT, OPT_SFS_VARIANT, OPT_UJ_CONST, OPT_UJ_TABLE = 2, 3, 4, 5
+OPT_UJ_VARIANT, OPT_SFS_VARIANT, OPT_UJ_CONST, OPT_UJ_TABLE, OPT_SMALL_GRAPH = 2, 3, 4, 5, 6
 
 
 class VpmTiming(C.Structure):

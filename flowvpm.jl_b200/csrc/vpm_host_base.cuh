@@ -60,6 +60,21 @@ struct vpm_handle {
   int opt_sfs_variant = 0;     // VPM_OPT_SFS_VARIANT
   int opt_uj_const = 0;        // VPM_OPT_UJ_CONST
   int opt_uj_table = 0;        // VPM_OPT_UJ_TABLE
+  int opt_graph = 0;           // VPM_OPT_SMALL_GRAPH
+  // small-field path of vpm_uj_direct: captured CUDA graphs of the device half of a call, keyed by
+  // everything the captured nodes depend on; dropped whenever a buffer they point into moves
+  struct GraphEntry {
+    const double *P = nullptr;
+    int64_t nf = 0, np = 0;
+    int kernel = 0, flags = 0;
+    bool has_static = false, pinned = false;
+    int seen = 0;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+  };
+  std::vector<GraphEntry> graphs;
+  bool capturing = false;  // a stream capture of the small-field path is in progress
+  uint64_t alloc_epoch = 0, graphs_epoch = 0;  // alloc_epoch: bumped by every (re)allocation
   int64_t fld_nf = 0, fld_np = -1;  // device mirror of the whole particle matrix (vpm_field_*)
   double fld_t_sgm = 0.0;           // CoreSpreading.t_sgm of the resident field
   int device_timing = 0;  // 1/2: ev[6..7] bracket the last _device U/J / SFS pair kernel
@@ -98,6 +113,7 @@ int fail(vpm_handle *h, int code, const char *fmt, ...) {
 
 int ensure(vpm_handle *h, Buf &b, size_t bytes) {
   if (bytes <= b.cap && b.p) return VPM_OK;
+  if (h) h->alloc_epoch++;
   if (b.p) CK(h, cudaFree(b.p));
   b.p = nullptr;
   b.cap = 0;
@@ -116,8 +132,14 @@ int ensure(vpm_handle *h, Buf &b, size_t bytes) {
 
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+void drop_graphs(vpm_handle *h) {
+  for (auto &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
 // order stream `st` after the last stream-ordered (_device) use of the sweep scratch of `d`
 int scratch_acquire(vpm_handle *h, Dev &d, cudaStream_t st) {
+  if (h->capturing) return VPM_OK;  // ordered before the capture began / before every replay instead
   if (d.scratch_pending) CK(h, cudaStreamWaitEvent(st, d.scratch_ev, 0));
   return VPM_OK;
 }

@@ -24,6 +24,7 @@ int ensure_stage(vpm_handle *h, size_t doubles) {
   h->h_stage = nullptr;
   h->h_stage_cap = 0;
   const size_t want = doubles + doubles / 4;
+  h->alloc_epoch++;
   CK(h, cudaMallocHost((void **)&h->h_stage, want * sizeof(double)));
   h->h_stage_cap = want;
   return VPM_OK;
@@ -82,58 +83,77 @@ int h2d_rows(vpm_handle *h, cudaStream_t st, double *dst, const double *src, int
 
 // host -> device: X, Gamma, sigma rows; static flags (compacted on the host,
 // only if any is set); previous U..PSE and SFS rows when they are accumulated on.
-int h1_upload(vpm_handle *h, Dev &d, const double *P, int64_t nf, int64_t np, bool need_prior,
-              bool need_sfs_rows, bool &has_static) {
+// Split in a host half (gathers into the pinned staging block / the static-flag block) and a device
+// half (the asynchronous copies) so that a captured CUDA graph of the device half can be replayed
+// with only the host half redone (small-field path of vpm_uj_direct).
+struct H1Rows {
+  bool pinned = false, has_static = false, need_prior = false, need_sfs_rows = false;
+};
+
+int h1_upload_host(vpm_handle *h, const double *P, int64_t nf, int64_t np, const H1Rows &r) {
+  if (np == 0) return VPM_OK;
+  if (!r.pinned) {
+    TRY(ensure_stage(h, (size_t)np * (7 + RES_ROWS + 3)));
+    double *stg = h->h_stage;
+    gather_rows(stg, P, nf, R_X, 7, np);
+    if (r.need_prior || r.has_static) gather_rows(stg + (size_t)np * 7, P, nf, R_U, RES_ROWS, np);
+    if (r.need_sfs_rows) gather_rows(stg + (size_t)np * (7 + RES_ROWS), P, nf, R_SFS, 3, np);
+  }
+  if (r.has_static) {
+    if (h->h_stat_cap < (size_t)np) {
+      if (h->h_stat) cudaFreeHost(h->h_stat);
+      h->h_stat = nullptr;
+      h->h_stat_cap = 0;
+      h->alloc_epoch++;
+      CK(h, cudaMallocHost((void **)&h->h_stat, (size_t)np * sizeof(double)));
+      h->h_stat_cap = (size_t)np;
+    }
+    for (int64_t i = 0; i < np; ++i) h->h_stat[i] = P[nf * i + R_STATIC];
+  }
+  return VPM_OK;
+}
+
+int h1_upload_dev(vpm_handle *h, Dev &d, const double *P, int64_t nf, int64_t np, const H1Rows &r) {
   cudaStream_t st = d.stream;
   CK(h, cudaSetDevice(d.id));
   const size_t n = (size_t)std::max<int64_t>(np, 1);
   TRY(ensure(h, d.in7, n * 7 * sizeof(double)));
   TRY(ensure(h, d.res18, n * RES_ROWS * sizeof(double)));
   TRY(ensure(h, d.sfs3, n * 3 * sizeof(double)));
-  has_static = false;
   if (np == 0) return VPM_OK;
-  has_static = any_static(P, nf, np);
-  const bool pinned = host_is_pinned(P);
-  double *stg = nullptr;
-  if (!pinned) {
-    TRY(ensure_stage(h, (size_t)np * (7 + RES_ROWS + 3)));
-    stg = h->h_stage;
-    gather_rows(stg, P, nf, R_X, 7, np);
-    CK(h, cudaMemcpyAsync(d.in7.p, stg, (size_t)np * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
-  } else {
-    TRY(h2d_rows(h, st, (double *)d.in7.p, P, nf, 7, np));
-  }
-  if (has_static) {
-    if (h->h_stat_cap < (size_t)np) {
-      if (h->h_stat) cudaFreeHost(h->h_stat);
-      h->h_stat = nullptr;
-      h->h_stat_cap = 0;
-      CK(h, cudaMallocHost((void **)&h->h_stat, (size_t)np * sizeof(double)));
-      h->h_stat_cap = (size_t)np;
-    }
-    for (int64_t i = 0; i < np; ++i) h->h_stat[i] = P[nf * i + R_STATIC];
+  const double *stg = h->h_stage;
+  if (!r.pinned) CK(h, cudaMemcpyAsync(d.in7.p, stg, (size_t)np * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+  else TRY(h2d_rows(h, st, (double *)d.in7.p, P, nf, 7, np));
+  if (r.has_static) {
     TRY(ensure(h, d.stat, (size_t)np * sizeof(double)));
     CK(h, cudaMemcpyAsync(d.stat.p, h->h_stat, (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
   }
-  if (need_prior || has_static) {
-    if (!pinned) {
-      double *s18 = stg + (size_t)np * 7;
-      gather_rows(s18, P, nf, R_U, RES_ROWS, np);
-      CK(h, cudaMemcpyAsync(d.res18.p, s18, (size_t)np * RES_ROWS * sizeof(double), cudaMemcpyHostToDevice, st));
-    } else {
+  if (r.need_prior || r.has_static) {
+    if (!r.pinned)
+      CK(h, cudaMemcpyAsync(d.res18.p, stg + (size_t)np * 7, (size_t)np * RES_ROWS * sizeof(double), cudaMemcpyHostToDevice, st));
+    else
       TRY(h2d_rows(h, st, (double *)d.res18.p, P + R_U, nf, RES_ROWS, np));
-    }
   }
-  if (need_sfs_rows) {
-    if (!pinned) {
-      double *s3 = stg + (size_t)np * (7 + RES_ROWS);
-      gather_rows(s3, P, nf, R_SFS, 3, np);
-      CK(h, cudaMemcpyAsync(d.sfs3.p, s3, (size_t)np * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-    } else {
+  if (r.need_sfs_rows) {
+    if (!r.pinned)
+      CK(h, cudaMemcpyAsync(d.sfs3.p, stg + (size_t)np * (7 + RES_ROWS), (size_t)np * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    else
       TRY(h2d_rows(h, st, (double *)d.sfs3.p, P + R_SFS, nf, 3, np));
-    }
   }
   return VPM_OK;
+}
+
+int h1_upload(vpm_handle *h, Dev &d, const double *P, int64_t nf, int64_t np, bool need_prior,
+              bool need_sfs_rows, bool &has_static) {
+  H1Rows r;
+  r.need_prior = need_prior; r.need_sfs_rows = need_sfs_rows;
+  has_static = false;
+  if (np > 0) {
+    r.has_static = has_static = any_static(P, nf, np);
+    r.pinned = host_is_pinned(P);
+  }
+  TRY(h1_upload_host(h, P, nf, np, r));
+  return h1_upload_dev(h, d, P, nf, np, r);
 }
 
 // device-resident evaluation: U/J sweep (+ SFS sweep) over all particles.
@@ -190,23 +210,18 @@ int h1_eval(vpm_handle *h, Dev &d, int64_t np, int kernel, int flags, bool has_s
   return VPM_OK;
 }
 
-int h1_download(vpm_handle *h, Dev &d, double *P, int64_t nf, int64_t np, int flags) {
+// device -> host of rows 10:27 (+ 40:42): the asynchronous half (into the staging block for a pageable
+// matrix) and, after the stream has been synchronised, the host half (scatter from the staging block)
+int h1_download_dev(vpm_handle *h, Dev &d, double *P, int64_t nf, int64_t np, int flags, bool pinned) {
   cudaStream_t st = d.stream;
   CK(h, cudaSetDevice(d.id));
   const bool sfs_rows = flags & (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS);
-  if (np > 0 && !host_is_pinned(P)) {
-    // pageable matrix: contiguous D2H into the pinned staging block, then scatter on the host
+  if (np > 0 && !pinned) {
     TRY(ensure_stage(h, (size_t)np * (7 + RES_ROWS + 3)));
     double *s18 = h->h_stage + (size_t)np * 7, *s3 = h->h_stage + (size_t)np * (7 + RES_ROWS);
     CK(h, cudaMemcpyAsync(s18, d.res18.p, (size_t)np * RES_ROWS * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (sfs_rows) CK(h, cudaMemcpyAsync(s3, d.sfs3.p, (size_t)np * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(h, cudaEventRecord(d.ev[5], st));
-    CK(h, cudaStreamSynchronize(st));
-    scatter_rows(P, nf, R_U, RES_ROWS, np, s18);
-    if (sfs_rows) scatter_rows(P, nf, R_SFS, 3, np, s3);
-    return VPM_OK;
-  }
-  if (np > 0) {
+  } else if (np > 0) {
     CK(h, cudaMemcpy2DAsync(P + R_U, nf * sizeof(double), d.res18.p, RES_ROWS * sizeof(double),
                             RES_ROWS * sizeof(double), (size_t)np, cudaMemcpyDeviceToHost, st));
     if (sfs_rows)
@@ -214,7 +229,19 @@ int h1_download(vpm_handle *h, Dev &d, double *P, int64_t nf, int64_t np, int fl
                               3 * sizeof(double), (size_t)np, cudaMemcpyDeviceToHost, st));
   }
   CK(h, cudaEventRecord(d.ev[5], st));
-  CK(h, cudaStreamSynchronize(st));
+  return VPM_OK;
+}
+void h1_download_host(vpm_handle *h, double *P, int64_t nf, int64_t np, int flags, bool pinned) {
+  if (np <= 0 || pinned) return;
+  const bool sfs_rows = flags & (VPM_FLAG_SFS | VPM_FLAG_RESET_SFS);
+  scatter_rows(P, nf, R_U, RES_ROWS, np, h->h_stage + (size_t)np * 7);
+  if (sfs_rows) scatter_rows(P, nf, R_SFS, 3, np, h->h_stage + (size_t)np * (7 + RES_ROWS));
+}
+int h1_download(vpm_handle *h, Dev &d, double *P, int64_t nf, int64_t np, int flags) {
+  const bool pinned = np > 0 && host_is_pinned(P);
+  TRY(h1_download_dev(h, d, P, nf, np, flags, pinned));
+  CK(h, cudaStreamSynchronize(d.stream));
+  h1_download_host(h, P, nf, np, flags, pinned);
   return VPM_OK;
 }
 

@@ -378,7 +378,7 @@ void launch_uj_leaf_f32(int kernel, int nt, unsigned nwi, const LeafUjArgsF &a, 
 // records + leaf kernel of one device's share of the work items, FP64 or (option) FP32 arithmetic
 void launch_uj_leaf_any(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, int nt, unsigned nwi, const LeafUjArgs &a,
                         SrcView sv, int64_t n_src, int64_t ns_pad) {
-  if (d.scratch_pending) cudaStreamWaitEvent(st, d.scratch_ev, 0);  // d.rec may still be read by a _device sweep
+  if (d.scratch_pending && !h->capturing) cudaStreamWaitEvent(st, d.scratch_ev, 0);  // d.rec may still be read by a _device sweep
   if (h->opt_nearfield_fp32) {
     prep_uj_records_f32s<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (float *)d.rec.p);
     LeafUjArgsF f;

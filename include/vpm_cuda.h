@@ -91,6 +91,11 @@ int vpm_num_devices(const vpm_handle *h);
                                     log-spaced table kernel, csrc/vpm_kernels_tab.cuh, when the field is large
                                     enough to fill the GPU with 1024-target CTAs), 1 = always, 2 = never (the
                                     round-1 kernels). */
+#define VPM_OPT_SMALL_GRAPH 6      /* value != 0: vpm_uj_direct on one device replays a captured CUDA graph for fields of
+                                    <= 16 384 particles (the second call with the same matrix, np, kernel and flags
+                                    captures it): one launch + one synchronisation per call instead of ~20 API calls.
+                                    The per-phase times of vpm_get_timing are 0 for replayed calls (total_ms is the
+                                    wall time of the call). */
 int vpm_set_option(vpm_handle *h, int option, int value);
 
 /* ---- Hook 1: the UJ slot ---------------------------------------------- */

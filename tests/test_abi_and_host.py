@@ -160,3 +160,26 @@ def test_sharding_bounds(vpm):
         assert segs[0][0] == 0 and segs[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
         assert all(t1 - t0 <= sharding.shard_size(n, w) for t0, t1 in segs)
+
+
+def test_save_xdmf_binary_roundtrip(vpm, tmp_path):
+    """f-4: `save` (src/FLOWVPM_utils.jl:148-371) as XDMF + raw binary: names, shapes and values survive"""
+    import numpy as np
+    pf = vpm.fields.cloud_field(257, static_fraction=0.2, seed=3)
+    vpm.fields.random_results(pf)
+    pf.nt, pf.t = 7, 0.125
+    ret = vpm.save(pf, "pfield", path=str(tmp_path))
+    assert ret == "pfield.7.xmf;"
+    got = vpm.io.read(str(tmp_path / "pfield.7.xmf"))
+    n, P = pf.np, pf.particles
+    assert (got["np"], got["nt"], got["t"]) == (n, 7, 0.125)
+    assert np.array_equal(got["X"], P[0:3, :n].T) and np.array_equal(got["Gamma"], P[3:6, :n].T)
+    assert np.array_equal(got["sigma"], P[6, :n]) and np.array_equal(got["static"], P[42, :n])
+    assert np.array_equal(got["velocity"], P[9:12, :n].T) and np.array_equal(got["vorticity"], P[12:15, :n].T)
+    assert np.array_equal(got["velocity_gradient_x"], P[15:18, :n].T)
+    assert np.array_equal(got["velocity_gradient_z"], P[21:24, :n].T) and np.array_equal(got["C"], P[36:39, :n].T)
+    # empty field -> one dummy particle, explicit number, no number
+    empty = vpm.ParticleField(4)
+    assert vpm.save(empty, "e", path=str(tmp_path), num=3) == "e.3.xmf;"
+    assert vpm.io.read(str(tmp_path / "e.3.xmf"))["np"] == 1
+    assert vpm.save(pf, "plain", path=str(tmp_path / "sub"), add_num=False, createpath=True) == "plain.xmf;"

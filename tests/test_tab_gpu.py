@@ -183,3 +183,44 @@ def test_device_entry_points_on_two_streams(vpm, handle):
         torch.cuda.synchronize()
         assert torch.equal(o1, r1) and torch.equal(o2, r2)
         assert np.array_equal(f2.get_U(), r2[:, 0:3].cpu().numpy().T)
+
+
+@pytest.mark.parametrize("kernel", ["winckelmans", "gaussianerf"])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_small_field_graph_replay(vpm, kernel, pinned):
+    """VPM_OPT_SMALL_GRAPH: the third and later calls with the same (matrix, np, kernel, flags) replay a
+    captured CUDA graph; the field changes between calls (positions move, results accumulate, static flags
+    appear) and every call must match the oracle like the ordinary path does"""
+    h = vpm.Handle(1)
+    try:
+        h.set_option(vpm._cabi.OPT_SMALL_GRAPH, 1)
+        pf = vpm.fields.cloud_field(900, kernel=vpm.KERNELS[kernel], seed=19)
+        P = pf.particles
+        if pinned:
+            h.check(h.lib.vpm_pin_host(h.ptr, P.ctypes.data, P.nbytes))
+        rng = np.random.default_rng(0)
+        for call in range(6):
+            P[0:3, :pf.np] += 1e-3 * rng.standard_normal((3, pf.np))
+            if call == 4:
+                P[42, 5:50:3] = 1.0          # static particles appear: a different key, captured separately
+            ref = P.copy(order="F")
+            kw = dict(sfs=True, reset=call % 2 == 0, reset_sfs=True)
+            oracle.uj_direct(ref, pf.np, kernel, **kw)
+            vpm.UJ_direct(pf, handle=h, **kw)
+            assert_parity(P, ref, pf.np, rows=("U", "J", "SFS", "W", "PSE"), what=f"call {call}")
+            assert h.timing()["kernel_launches"] > 0 and h.timing()["uj_pairs"] == pf.np ** 2
+        # same field through a handle without the option: bit-identical
+        h2 = vpm.Handle(1)
+        try:
+            a = P.copy(order="F")
+            vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True, handle=h)
+            b = P.copy(order="F")
+            P[:] = a
+            vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True, handle=h2)
+            assert np.array_equal(P, b)
+        finally:
+            h2.close()
+        if pinned:
+            h.check(h.lib.vpm_unpin_host(h.ptr, P.ctypes.data))
+    finally:
+        h.close()
