@@ -83,6 +83,7 @@ int vpm_destroy(vpm_handle *h) {
 
 int vpm_set_option(vpm_handle *h, int option, int value) {
   if (!h) return VPM_EINVAL;
+  drop_graphs(h);  // captured small-field graphs embed the launch plan the options shape
   switch (option) {
     case VPM_OPT_NEARFIELD_FP32: h->opt_nearfield_fp32 = value != 0; return VPM_OK;
     case VPM_OPT_UJ_VARIANT:
@@ -140,7 +141,7 @@ static int check_field(vpm_handle *h, const char *fn, const void *P, int64_t nf,
 // CUDA graph the second time the same (matrix, np, kernel, flags, static?, pinned?) combination is seen and
 // replayed from then on: one cudaGraphLaunch + one synchronisation per call, only the host half
 // (row gathers / scatters of a pageable matrix, the static-flag block) is redone.
-constexpr int64_t kGraphMaxNp = 16384;
+constexpr int64_t kGraphMaxNp = 8192;  // below the size at which the table kernel (and its sampling sync) can be chosen
 
 int vpm_uj_direct(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel, int flags) {
   TRY(check_field(h, "vpm_uj_direct", P, nf, np, kernel));

@@ -128,10 +128,30 @@ int vpm_nearfield_ranges(vpm_handle *h, double *TP, int64_t nf_t, int64_t np_t, 
   const int64_t nsr = soff[ntr];
   if (nsr == 0) return VPM_OK;
   if (nsr > INT32_MAX || ntr > INT32_MAX) return fail(h, VPM_EINVAL, "%s: more than 2^31 ranges", fn);
-  // the (target range, source range) list: entry i <-> (k, i) for soff[k] <= i < soff[k+1]
+  // One owner per target column: the k-th range's CTAs add into its columns without atomics, so target
+  // ranges that carry work must not overlap.  IDENTICAL ranges (the reference's own example of the call,
+  // warmup_gpu at src/FLOWVPM_gpu.jl:637-643, lists `1:n` once per GPU) are merged: the later entries'
+  // source ranges join the first one's list, in order.  Partial overlaps are refused.
+  std::vector<int64_t> owner((size_t)ntr);
+  {
+    std::vector<int64_t> ord;
+    for (int64_t k = 0; k < ntr; ++k) {
+      owner[(size_t)k] = k;
+      if (soff[k + 1] > soff[k] && te[k] > tb[k]) ord.push_back(k);
+    }
+    std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return tb[a] != tb[b] ? tb[a] < tb[b] : te[a] < te[b]; });
+    for (size_t i = 1; i < ord.size(); ++i) {
+      const int64_t a = ord[i - 1], b = ord[i];
+      if (tb[a] == tb[b] && te[a] == te[b]) owner[(size_t)b] = owner[(size_t)a];
+      else if (tb[b] < te[a])
+        return fail(h, VPM_EINVAL, "%s: target ranges %lld [%lld,%lld) and %lld [%lld,%lld) overlap", fn, (long long)a,
+                    (long long)tb[a], (long long)te[a], (long long)b, (long long)tb[b], (long long)te[b]);
+    }
+  }
+  // the (target range, source range) list: entry i <-> (owner of k, i) for soff[k] <= i < soff[k+1]
   std::vector<int32_t> pt((size_t)nsr), ps((size_t)nsr);
   for (int64_t k = 0; k < ntr; ++k)
-    for (int64_t i = soff[k]; i < soff[k + 1]; ++i) { pt[(size_t)i] = (int32_t)k; ps[(size_t)i] = (int32_t)i; }
+    for (int64_t i = soff[k]; i < soff[k + 1]; ++i) { pt[(size_t)i] = (int32_t)owner[(size_t)k]; ps[(size_t)i] = (int32_t)i; }
   h->launches = 0;
   int G = (int)h->devs.size();
   const int TLD = 18;  // device target buffer: rows 0:3 X, rows 3:18 = particle rows 10:24 (U, vorticity, J)

@@ -60,7 +60,8 @@ struct vpm_handle {
   int opt_sfs_variant = 0;     // VPM_OPT_SFS_VARIANT
   int opt_uj_const = 0;        // VPM_OPT_UJ_CONST
   int opt_uj_table = 0;        // VPM_OPT_UJ_TABLE
-  int opt_graph = 0;           // VPM_OPT_SMALL_GRAPH
+  int opt_graph = 1;           // VPM_OPT_SMALL_GRAPH (on by default)
+  double last_near_fraction = -1.0;  // sampled by the last automatic gaussianerf kernel choice
   // small-field path of vpm_uj_direct: captured CUDA graphs of the device half of a call, keyed by
   // everything the captured nodes depend on; dropped whenever a buffer they point into moves
   struct GraphEntry {

@@ -320,6 +320,30 @@ __global__ void __launch_bounds__(THREADS, 1) uj_pairs_tab_kernel(const UjArgs a
   }
 }
 
+// Fraction of (target, source) pairs inside the regularised range, from 65 536 pseudo-random pairs
+// (a fixed hash of the sample index: the same field gives the same count, so the kernel choice that
+// depends on it is deterministic).  out[0] += pairs with r^2 < cutoff_u * sigma_source^2.
+__global__ void sample_near_kernel(SrcView src, int64_t s0, int64_t ns, const double *__restrict__ tpos, int64_t tld,
+                                   int64_t nt, double cutoff_u, unsigned int *out) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  auto mix = [](unsigned long long x) {  // splitmix64 finaliser
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+  };
+  const int64_t i = (int64_t)(mix(2ull * k) % (unsigned long long)nt);
+  const int64_t j = (int64_t)(mix(2ull * k + 1) % (unsigned long long)ns);
+  const double *t = tpos + i * tld;
+  const double *p = src.p + (s0 + j) * src.ld;
+  const double dx = t[0] - p[src.ox], dy = t[1] - p[src.ox + 1], dz = t[2] - p[src.ox + 2];
+  const double sg = p[src.osig];
+  const bool near = dx * dx + dy * dy + dz * dz < cutoff_u * sg * sg;
+  const unsigned m = __ballot_sync(0xffffffffu, near);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, (unsigned)__popc(m));
+}
+constexpr int kSampleBlocks = 256, kSampleThreads = 256;
+
 // device-math test hook (vpm_test_math op 4): (A, B) of the table path at r2 = in[i], sigma = 1
 template <int K>
 __global__ void test_tab_kernel(const double *in, double *out, double *out2, int64_t n) {

@@ -112,3 +112,6 @@ def test_nearfield_device_edge_cases(vpm, handle):
         vpm.fmm_nearfield_device(pf, [range(0, 400)], SWITCH_UJ, pf, [[range(0, 300)]])   # outside the field
     with pytest.raises(ValueError):
         vpm.fmm_nearfield_device(pf, [range(0, 10)], SWITCH_UJ, pf, [])
+    with pytest.raises(vpm.VpmError):   # partially overlapping target ranges have no single owner per column
+        vpm.fmm_nearfield_device(pf, [range(0, 100), range(50, 150)], SWITCH_UJ, pf, [[range(0, 300)], [range(0, 300)]])
+    assert np.array_equal(pf.particles, base)

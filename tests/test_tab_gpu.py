@@ -126,24 +126,33 @@ def test_forced_table_coincident_and_static(vpm, tab_forced, kernel):
     assert_parity(pf.particles, ref, pf.np, rows=("U", "J", "SFS", "W", "PSE"))
 
 
-@pytest.mark.parametrize("kernel", FAMILIES)
-def test_automatic_choice_takes_the_table_kernel(vpm, handle, kernel):
-    """20 000 particles: 20 x 157 (target block, source tile) pairs fill the GPU, so the automatic
-    plan takes the table kernel (timing.plan_T == 2 with 512-thread CTAs is not visible from here;
-    agreement with the forced run to the last bit is)."""
-    pf = vpm.fields.cloud_field(20000, kernel=vpm.KERNELS[kernel], seed=77)
-    base = pf.particles.copy(order="F")
-    ref = oracle_uj(pf, reset=True)
-    vpm.UJ_direct(pf, reset=True)
-    auto = pf.particles.copy(order="F")
-    assert_parity(auto, ref, pf.np, rows=("U", "J"))
+def _run_with(vpm, handle, pf, base, opt):
     pf.particles[:] = base
-    handle.set_option(vpm._cabi.OPT_UJ_TABLE, 1)
+    handle.set_option(vpm._cabi.OPT_UJ_TABLE, opt)
     try:
         vpm.UJ_direct(pf, reset=True)
     finally:
         handle.set_option(vpm._cabi.OPT_UJ_TABLE, 0)
-    assert np.array_equal(auto[9:24], pf.particles[9:24])
+    return pf.particles[9:24].copy()
+
+
+def test_automatic_choice_follows_the_sampled_near_fraction(vpm, handle):
+    """20 000 particles fill the GPU with 1024-target CTAs, so gaussianerf is a candidate for the table kernel;
+    the automatic plan takes it only when a deterministic sample of pairs finds >= 30 % of them inside s < 9:
+    a dense field (sigma x 4: every pair inside) runs the table kernel, the sparse C4 cloud the round-1
+    kernel -- seen from outside as bit-identity with the forced runs.  The gaussian family never takes it
+    automatically.  Every variant is in parity with the oracle."""
+    for kernel, scale, expect in (("gaussianerf", 8.0, 1), ("gaussianerf", 1.0, 2), ("gaussian", 8.0, 2)):
+        pf = vpm.fields.cloud_field(20000, kernel=vpm.KERNELS[kernel], seed=77)
+        pf.particles[0:3] *= np.array([[1.0], [1.0], [1.0 / 7.0]])   # unit cube
+        pf.particles[6] *= scale
+        base = pf.particles.copy(order="F")
+        ref = oracle_uj(pf, reset=True)
+        auto = _run_with(vpm, handle, pf, base, 0)
+        assert_parity(pf.particles, ref, pf.np, rows=("U", "J"), what=f"auto {kernel} x{scale}")
+        forced = {opt: _run_with(vpm, handle, pf, base, opt) for opt in (1, 2)}
+        assert not np.array_equal(forced[1], forced[2])          # the two kernels round differently
+        assert np.array_equal(auto, forced[expect]), (kernel, scale)
 
 
 def test_option_validation(vpm, handle):
@@ -209,8 +218,9 @@ def test_small_field_graph_replay(vpm, kernel, pinned):
             vpm.UJ_direct(pf, handle=h, **kw)
             assert_parity(P, ref, pf.np, rows=("U", "J", "SFS", "W", "PSE"), what=f"call {call}")
             assert h.timing()["kernel_launches"] > 0 and h.timing()["uj_pairs"] == pf.np ** 2
-        # same field through a handle without the option: bit-identical
+        # same field through a handle with the graph path switched off: bit-identical
         h2 = vpm.Handle(1)
+        h2.set_option(vpm._cabi.OPT_SMALL_GRAPH, 0)
         try:
             a = P.copy(order="F")
             vpm.UJ_direct(pf, sfs=True, reset=True, reset_sfs=True, handle=h)

@@ -63,5 +63,7 @@ def measure(h, kname="gaussianerf", sizes=(200, 900, 4900, 33800), reps=30):
 
 if __name__ == "__main__":
     h = vpm.Handle(1)
+    if os.environ.get("SMALL_GRAPH"):
+        h.set_option(vpm._cabi.OPT_SMALL_GRAPH, int(os.environ["SMALL_GRAPH"]))
     for r in measure(h, sys.argv[1] if len(sys.argv) > 1 else "gaussianerf"):
         print(r, flush=True)
