@@ -29,7 +29,7 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
     Dev &d = h->devs[g];
     CK(h, cudaSetDevice(d.id));
     TRY(ensure(h, d.tbuf, (size_t)n_tgt * ld * sizeof(double)));
-    TRY(ensure(h, d.sbuf, (size_t)n_src * 8 * sizeof(double)));
+    TRY(ensure(h, d.sbuf, (size_t)((n_src + G - 1) / G * G) * 8 * sizeof(double)));
     TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
   }
   // replicated inputs (source buffer, CSR tables): device 0 gets them from the host, the
@@ -37,7 +37,15 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
   Dev &d0 = h->devs[0];
   CK(h, cudaSetDevice(d0.id));
   CK(h, cudaEventRecord(d0.ev[0], d0.stream));
-  CK(h, cudaMemcpyAsync(d0.sbuf.p, src, (size_t)n_src * 8 * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
+  // page-locked source buffer on a multi-GPU handle: every device pulls 1/G of it over its own PCIe link and
+  // an all-gather over NVLink completes the copies (h2d_rows_sharded); otherwise device 0 + broadcast
+  const bool src_sharded = G > 1 && host_is_pinned(src);
+  if (src_sharded) {
+    TRY(h2d_rows_sharded(h, &Dev::sbuf, src, 8, 8, n_src));
+    CK(h, cudaSetDevice(d0.id));
+  } else {
+    CK(h, cudaMemcpyAsync(d0.sbuf.p, src, (size_t)n_src * 8 * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
+  }
   DevCsr c;
   TRY(build_csr_device(h, fn, tb, te, ntl, n_tgt, sb, se, nsl, n_src, pt, ps, npairs, G, nullptr, 0, nullptr, 0, c));
   if (c.nwi == 0) return VPM_OK;
@@ -50,7 +58,7 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
     TRY(ensure(h, d.ibuf, h->devs[0].ibuf.cap));
     csr[g] = rebase_csr(c.csr, h->devs[0].ibuf.p, d.ibuf.p);
   }
-  if (G > 1) TRY(bcast_from_dev0(h, &Dev::sbuf, (size_t)n_src * 8 * sizeof(double)));
+  if (G > 1 && !src_sharded) TRY(bcast_from_dev0(h, &Dev::sbuf, (size_t)n_src * 8 * sizeof(double)));
   if (G > 1) TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
   std::vector<std::pair<int64_t, int64_t>> cols(G, {0, 0});
   for (int g = 0; g < G; ++g) {
@@ -160,13 +168,16 @@ int vpm_nearfield_ranges(vpm_handle *h, double *TP, int64_t nf_t, int64_t np_t, 
     Dev &d = h->devs[g];
     CK(h, cudaSetDevice(d.id));
     TRY(ensure(h, d.tbuf, (size_t)np_t * TLD * sizeof(double)));
-    TRY(ensure(h, d.in7, (size_t)np_s * 7 * sizeof(double)));
+    TRY(ensure(h, d.in7, (size_t)((np_s + G - 1) / G * G) * 7 * sizeof(double)));
     TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
   }
   Dev &d0 = h->devs[0];
   CK(h, cudaSetDevice(d0.id));
   CK(h, cudaEventRecord(d0.ev[0], d0.stream));
-  TRY(h2d_rows(h, d0.stream, (double *)d0.in7.p, SP, nf_s, 7, np_s));
+  const bool src_sharded = G > 1 && host_is_pinned(SP);
+  if (src_sharded) TRY(h2d_rows_sharded(h, &Dev::in7, SP, nf_s, 7, np_s));
+  else TRY(h2d_rows(h, d0.stream, (double *)d0.in7.p, SP, nf_s, 7, np_s));
+  CK(h, cudaSetDevice(d0.id));
   DevCsr c;
   TRY(build_csr_device(h, fn, tb, te, ntr, np_t, sb, se, nsr, np_s, pt.data(), ps.data(), nsr, G, nullptr, 0, nullptr, 0, c));
   if (c.nwi == 0) return VPM_OK;
@@ -179,7 +190,7 @@ int vpm_nearfield_ranges(vpm_handle *h, double *TP, int64_t nf_t, int64_t np_t, 
     TRY(ensure(h, d.ibuf, h->devs[0].ibuf.cap));
     csr[g] = rebase_csr(c.csr, h->devs[0].ibuf.p, d.ibuf.p);
   }
-  if (G > 1) TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np_s * 7 * sizeof(double)));
+  if (G > 1 && !src_sharded) TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np_s * 7 * sizeof(double)));
   if (G > 1) TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
   std::vector<std::pair<int64_t, int64_t>> cols(G, {0, 0});
   for (int g = 0; g < G; ++g) {
@@ -434,7 +445,18 @@ int vpm_leaflists_build(vpm_handle *h, const double *P, int64_t nf, int64_t np, 
   bool has_static = false;
   CK(h, cudaSetDevice(d.id));
   CK(h, cudaEventRecord(d.ev[0], d.stream));
-  TRY(h1_upload(h, d, P, nf, np, false, false, has_static));
+  const int G = (int)h->devs.size();
+  if (G > 1 && host_is_pinned(P)) {
+    // every device pulls 1/G of the rows over its own PCIe link, all-gather over NVLink (h2d_rows_sharded)
+    for (int g = 0; g < G; ++g) {
+      CK(h, cudaSetDevice(h->devs[g].id));
+      TRY(ensure(h, h->devs[g].in7, (size_t)((np + G - 1) / G * G) * 7 * sizeof(double)));
+    }
+    TRY(h2d_rows_sharded(h, &Dev::in7, P, nf, 7, np));
+    CK(h, cudaSetDevice(d.id));
+  } else {
+    TRY(h1_upload(h, d, P, nf, np, false, false, has_static));
+  }
   CK(h, cudaEventRecord(d.ev[1], d.stream));
   TRY(tree_build(h, (const double *)d.in7.p, 7, 6, np, ncrit, theta));
   for (int e = 2; e <= 5; ++e) CK(h, cudaEventRecord(d.ev[e], d.stream));
@@ -475,10 +497,27 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
   CK(h, cudaSetDevice(d0.id));
   CK(h, cudaEventRecord(d0.ev[0], d0.stream));
   const bool reset = flags & VPM_FLAG_RESET;
-  bool has_static = false;
-  TRY(h1_upload(h, d0, P, nf, np, !reset, false, has_static));
+  bool has_static = any_static(P, nf, np);
   const bool prior = !reset || has_static;
-  if (!prior) CK(h, cudaMemsetAsync(d0.res18.p, 0, (size_t)np * RES_ROWS * sizeof(double), d0.stream));
+  // Sharded transfers (multi-GPU handle, page-locked matrix, nothing to accumulate on): every device pulls
+  // its 1/G of X, Gamma, sigma over its own PCIe link (+ one all-gather over NVLink) and, at the end, pushes
+  // its 1/G of the result rows itself; otherwise everything goes through device 0.
+  bool sharded = G > 1 && !prior && host_is_pinned(P);
+  const int64_t shard = (np + G - 1) / G;
+  if (sharded) {
+    for (int g = 0; g < G; ++g) {
+      Dev &d = h->devs[g];
+      CK(h, cudaSetDevice(d.id));
+      TRY(ensure(h, d.in7, (size_t)shard * G * 7 * sizeof(double)));
+      TRY(ensure(h, d.res18, (size_t)np * RES_ROWS * sizeof(double)));
+      CK(h, cudaMemsetAsync(d.res18.p, 0, (size_t)np * RES_ROWS * sizeof(double), d.stream));
+    }
+    TRY(h2d_rows_sharded(h, &Dev::in7, P, nf, 7, np));
+    CK(h, cudaSetDevice(d0.id));
+  } else {
+    TRY(h1_upload(h, d0, P, nf, np, !reset, false, has_static));
+    if (!prior) CK(h, cudaMemsetAsync(d0.res18.p, 0, (size_t)np * RES_ROWS * sizeof(double), d0.stream));
+  }
   const TreeView tv = tree_view(h);
   DevCsr c;
   TRY(build_csr_device(h, fn, tv.lbegin, tv.lend, h->tree_nl, np, tv.lbegin, tv.lend, h->tree_nl, np, tv.pt, tv.ps,
@@ -495,7 +534,7 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
     TRY(ensure(h, d.sbuf, (size_t)np * 8 * sizeof(double)));
     TRY(ensure(h, d.rec, (size_t)ns_pad * kRec * sizeof(double)));
     if (g > 0) {
-      TRY(ensure(h, d.in7, (size_t)np * 7 * sizeof(double)));
+      if (!sharded) TRY(ensure(h, d.in7, (size_t)np * 7 * sizeof(double)));
       TRY(ensure(h, d.tree, h->devs[0].tree.cap));
       TRY(ensure(h, d.ibuf, h->devs[0].ibuf.cap));
       csr[g] = rebase_csr(c.csr, h->devs[0].ibuf.p, d.ibuf.p);
@@ -503,7 +542,8 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
   }
   // replicate state, sort index and list tables over NVLink; every device gathers its own
   // tree-sorted buffers
-  if (G > 1) TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np * 7 * sizeof(double)));
+  if (G < (int)h->devs.size()) sharded = false;  // the cuts did not use every device: return through device 0
+  if (G > 1 && !sharded) TRY(bcast_from_dev0(h, &Dev::in7, (size_t)np * 7 * sizeof(double)));
   if (G > 1) TRY(bcast_from_dev0(h, &Dev::tree, (size_t)np * 8));
   if (G > 1) TRY(bcast_from_dev0(h, &Dev::ibuf, c.bcast_bytes));
   std::vector<std::pair<int64_t, int64_t>> cols(G, {0, 0});
@@ -541,6 +581,43 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
     CK(h, cudaGetLastError());
     cols[g] = {col0, col1};
   }
+  if (sharded) {
+    // every device receives every device's columns of the sorted result (one ncclBroadcast per owner),
+    // scatters the whole field into its own result block and writes its 1/G of the rows to the host
+    NCK(h, g_nccl.group_start());
+    for (int r = 0; r < G; ++r) {
+      const int64_t col0 = cols[r].first, col1 = cols[r].second;
+      if (col1 <= col0) continue;
+      const size_t cnt = (size_t)(col1 - col0) * 16;
+      for (int g = 0; g < G; ++g) {
+        Dev &d = h->devs[g];
+        NCK(h, g_nccl.broadcast((double *)h->devs[r].tbuf.p + col0 * 16, (double *)d.tbuf.p + col0 * 16, cnt, kNcclFloat64, r,
+                                h->comms[g], d.stream));
+      }
+    }
+    NCK(h, g_nccl.group_end());
+    CK(h, cudaSetDevice(d0.id));
+    CK(h, cudaEventRecord(d0.ev[2], d0.stream));
+    for (int g = 0; g < G; ++g) {
+      Dev &d = h->devs[g];
+      CK(h, cudaSetDevice(d.id));
+      tree_scatter_kernel<<<blocks_for(np, 256), 256, 0, d.stream>>>((const double *)d.tbuf.p, (const int64_t *)d.tree.p, np,
+                                                                   (double *)d.res18.p, RES_ROWS, RES_U, RES_J, RES_W,
+                                                                   RES_PSE, 1, nullptr, 1);
+      CK(h, cudaGetLastError());
+      if (g == 0) {
+        h->launches++;
+        CK(h, cudaEventRecord(d.ev[3], d.stream));
+        CK(h, cudaEventRecord(d.ev[4], d.stream));
+      }
+      const int64_t c0 = std::min<int64_t>(np, g * shard), c1 = std::min<int64_t>(np, (g + 1) * shard);
+      if (c1 > c0)
+        CK(h, cudaMemcpy2DAsync(P + c0 * nf + R_U, nf * sizeof(double), (double *)d.res18.p + c0 * RES_ROWS,
+                                RES_ROWS * sizeof(double), RES_ROWS * sizeof(double), (size_t)(c1 - c0),
+                                cudaMemcpyDeviceToHost, d.stream));
+      if (g == 0) CK(h, cudaEventRecord(d.ev[5], d.stream));
+    }
+  } else {
   // the devices return their columns of the sorted result to device 0 over NVLink
   // (ncclSend / ncclRecv; the receives are ordered on device 0's stream after its own
   // gather + pair kernel and before the scatter)
@@ -567,6 +644,7 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
   CK(h, cudaEventRecord(d0.ev[3], d0.stream));
   CK(h, cudaEventRecord(d0.ev[4], d0.stream));
   TRY(h1_download(h, d0, P, nf, np, 0));
+  }
   for (int g = G - 1; g >= 0; --g) {
     CK(h, cudaSetDevice(h->devs[g].id));
     CK(h, cudaStreamSynchronize(h->devs[g].stream));

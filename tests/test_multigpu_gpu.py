@@ -302,3 +302,51 @@ def test_nearfield_device_call_shape_multi_gpu(vpm):
     U, J = reference(sorted_system(vpm, pf, ll["sort_index"]), ll, "winckelmans")
     assert relerr(outs[0][9:12, :pf.np], U) < TOL_FP64 and relerr(outs[0][15:24, :pf.np], J) < TOL_FP64
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("ncrit", [24, 200])
+def test_sharded_transfers_pinned_matrix_multi_gpu(vpm, ncrit):
+    """page-locked matrix + reset + no static particles: every device pulls its 1/G of X, Gamma, sigma over its
+    own PCIe link (all-gather over NVLink) for vpm_leaflists_build / vpm_uj_nearfield / vpm_nearfield_ranges and
+    writes its 1/G of the result rows itself; results bit-identical to the single-GPU handle, untouched rows
+    untouched"""
+    g = _ngpu()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from test_hook3_shape_gpu import combine_source_indices, sorted_system, SWITCH_UJ
+    hm, h1 = vpm.Handle(min(g, 4)), vpm.Handle(1)
+    try:
+        pf = vpm.fields.cloud_field(9001, kernel=vpm.winckelmans, seed=29)   # not a multiple of the device count
+        vpm.fields.random_results(pf, scale=1e-3)
+        before = pf.particles.copy(order="F")
+        P = pf.particles
+        hm.check(hm.lib.vpm_pin_host(hm.ptr, P.ctypes.data, P.nbytes))
+        ll = vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, handle=hm)
+        vpm.UJ_nearfield(pf, reset=True, handle=hm)
+        multi = P.copy(order="F")
+        hm.check(hm.lib.vpm_unpin_host(hm.ptr, P.ctypes.data))
+        P[:] = before
+        ll1 = vpm.leaf_lists(pf, ncrit=ncrit, theta=0.4, handle=h1)
+        assert all(np.array_equal(ll[k], ll1[k]) for k in ("sort_index", "leaf_begin", "leaf_end", "direct_list"))
+        vpm.UJ_nearfield(pf, reset=True, handle=h1)
+        assert np.array_equal(multi, P)
+        for rows in (slice(0, 9), slice(27, 46)):
+            assert np.array_equal(P[rows], before[rows])
+        # Hook 3 call shape with a page-locked source system
+        ti, si = combine_source_indices(ll["direct_list"], ll["leaf_begin"], ll["leaf_end"])
+        outs = []
+        for h in (hm, h1):
+            s = sorted_system(vpm, pf, ll["sort_index"])
+            s.particles[9:27] = 0
+            if h is hm:
+                h.check(h.lib.vpm_pin_host(h.ptr, s.particles.ctypes.data, s.particles.nbytes))
+            vpm.fmm_nearfield_device(s, ti, SWITCH_UJ, s, si, handle=h)
+            if h is hm:
+                h.check(h.lib.vpm_unpin_host(h.ptr, s.particles.ctypes.data))
+            outs.append(s.particles.copy(order="F"))
+        assert np.array_equal(outs[0], outs[1])
+        order = ll["sort_index"]
+        assert np.array_equal(outs[1][9:12, :pf.np], P[9:12, order]) and np.array_equal(outs[1][15:24, :pf.np], P[15:24, order])
+    finally:
+        hm.close()
+        h1.close()
