@@ -158,8 +158,10 @@ int vpm_nearfield_ranges(vpm_handle *h, double *TP, int64_t nf_t, int64_t np_t, 
   }
   // the (target range, source range) list: entry i <-> (owner of k, i) for soff[k] <= i < soff[k+1]
   std::vector<int32_t> pt((size_t)nsr), ps((size_t)nsr);
-  for (int64_t k = 0; k < ntr; ++k)
-    for (int64_t i = soff[k]; i < soff[k + 1]; ++i) { pt[(size_t)i] = (int32_t)owner[(size_t)k]; ps[(size_t)i] = (int32_t)i; }
+  parallel_chunks(ntr, [&](int64_t k0, int64_t k1) {
+    for (int64_t k = k0; k < k1; ++k)
+      for (int64_t i = soff[k]; i < soff[k + 1]; ++i) { pt[(size_t)i] = (int32_t)owner[(size_t)k]; ps[(size_t)i] = (int32_t)i; }
+  });
   h->launches = 0;
   int G = (int)h->devs.size();
   const int TLD = 18;  // device target buffer: rows 0:3 X, rows 3:18 = particle rows 10:24 (U, vorticity, J)

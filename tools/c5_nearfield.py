@@ -69,6 +69,30 @@ for ncrit in ncrits:
   res.update(hook3_call_s=dt, hook3_kernel_ms_dev0=tm["uj_ms"], hook3_h2d_ms=tm["h2d_ms"], hook3_d2h_ms=tm["d2h_ms"],
              hook3_e2e_interactions_per_s=tm["uj_pairs"] / dt, finite=bool(np.isfinite(tb[4:]).all()))
   res["f3_equals_hook3"] = bool(np.array_equal(U_f3[:, order], tb[4:7]))
+  # ---- Hook 3 in the reference's call shape (vpm_nearfield_ranges): the tree-sorted SYSTEM (46 x N matrix,
+  # page-locked) and per-target-leaf source ranges; the range tables are built vectorised here (a Julia
+  # caller builds them from FastMultipole's branches), the call itself is the ctypes call of the ABI
+  import ctypes as C
+  S = np.asfortranarray(pf.particles[:, order])
+  S[9:27] = 0.0
+  pin(S)
+  lb, le = ll["leaf_begin"], ll["leaf_end"]
+  pt, ps = ll["pair_tgt"], ll["pair_src"]            # grouped by target leaf
+  nl = len(lb)
+  soff = np.searchsorted(pt, np.arange(nl + 1)).astype(np.int64)
+  sbeg, send = np.ascontiguousarray(lb[ps]), np.ascontiguousarray(le[ps])
+  for rep in range(2):
+      S[9:27] = 0.0
+      t = time.perf_counter()
+      h.check(h.lib.vpm_nearfield_ranges(h.ptr, S.ctypes.data, S.shape[0], n, lb.ctypes.data, le.ctypes.data, nl,
+                                         S.ctypes.data, S.shape[0], n, sbeg.ctypes.data, send.ctypes.data,
+                                         soff.ctypes.data, vpm.winckelmans.id, 1, 1))
+      dt = time.perf_counter() - t
+  tm = h.timing()
+  res.update(ranges_call_s=dt, ranges_kernel_ms_dev0=tm["uj_ms"], ranges_e2e_interactions_per_s=tm["uj_pairs"] / dt,
+             ranges_equals_hook3=bool(np.array_equal(S[9:12], tb[4:7]) and np.array_equal(S[15:24], tb[7:16])))
+  h.check(h.lib.vpm_unpin_host(h.ptr, S.ctypes.data))
+  del S
   # parity on a slice: three target leaves recomputed by the CPU oracle (test infrastructure)
   from oracle import oracle  # noqa: E402
   worst = 0.0
