@@ -59,7 +59,17 @@ extern "C" {
 
 #define VPM_FLAG_FP32 32  /* optional FP32-arithmetic U/J sweep (north star: <= 1e-5): hi/lo split
                              positions, packed f32x2 pair loop, FP64 sums across tiles; the SFS
-                             sweep stays FP64.  Without it every entry point computes in FP64. */
+                             sweep stays FP64.  Without it every entry point computes in FP64.
+                             Accuracy contract (tests/test_fp32_gpu.py; errors relative to the field
+                             maximum against the FP64 oracle): U, J and the stretching term (Gamma.grad')U
+                             <= 1e-5 for the three regularised families on every tested field (measured
+                             2e-7 .. 1e-6).  STATED DEVIATIONS from the 1e-5 bar:
+                              * the SFS term of the same call is computed in FP64 but FROM the FP32-mode J;
+                                (JT - JS).Gamma cancels, so it inherits J's error amplified: asserted at
+                                1e-4 (measured ~2e-5), not 1e-5;
+                              * the singular kernel on overlapping cores (a ring of unregularised particles,
+                                outside any reference use): J 5.6e-6 but stretching 1.7e-5, asserted at 5e-5.
+                             Callers that need 1e-5 on SFS use the default FP64 sweep. */
 
 typedef struct vpm_handle vpm_handle;
 
