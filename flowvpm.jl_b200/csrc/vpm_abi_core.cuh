@@ -242,9 +242,21 @@ int vpm_uj_direct(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel, 
     }
   }
   if (rc != VPM_OK) return rc;
+  const int launches = h->launches;
   CK(h, cudaStreamSynchronize(d.stream));
   h1_download_host(h, P, nf, np, flags, r.pinned);
-  h1_fill_timing(h, d);
+  if (capture && ge && ge->exec) {
+    // events recorded inside the capture carry no timestamps (cudaEventElapsedTime would fail on them)
+    vpm_timing &t = h->timing;
+    t = vpm_timing{};
+    t.uj_pairs = np * np;
+    t.sfs_pairs = (flags & VPM_FLAG_SFS) ? np * np : 0;
+    t.kernel_launches = launches;
+    t.n_gpus = 1;
+    h->device_timing = 0;
+  } else {
+    h1_fill_timing(h, d);
+  }
   h->np_resident = -1;
   return VPM_OK;
 }

@@ -75,7 +75,9 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
   if (sp->sfs < 0 || sp->sfs > 2) return fail(h, VPM_EINVAL, "vpm_field_step: sfs must be 0 (none), 1 (constant) or 2 (dynamic)");
   if (sp->sfs == 2 && (sp->minC < 0 || sp->maxC < 0 || sp->minC > sp->maxC || sp->alpha <= 0))
     return fail(h, VPM_EINVAL, "vpm_field_step: invalid DynamicSFS parameters (minC=%g maxC=%g alpha=%g)", sp->minC, sp->maxC, sp->alpha);
-  if (sp->viscous < 0 || sp->viscous > 1) return fail(h, VPM_EINVAL, "vpm_field_step: viscous must be 0 (Inviscid) or 1 (CoreSpreading)");
+  if (sp->viscous < 0 || sp->viscous > 3)
+    return fail(h, VPM_EINVAL, "vpm_field_step: viscous must be 0 (Inviscid), 1 (CoreSpreading), 2 or 3 (ParticleStrengthExchange with / without recalculate_vols)");
+  if (sp->viscous >= 2 && sp->nu < 0) return fail(h, VPM_EINVAL, "vpm_field_step: ParticleStrengthExchange needs nu >= 0");
   if (sp->viscous == 1 && sp->kernel_id != K_GERF)
     return fail(h, VPM_EINVAL, "vpm_field_step: kernel %d is not compatible with viscous scheme CoreSpreading; compatible kernels are gaussianerf", sp->kernel_id);  // src/FLOWVPM_utils.jl:58-64
   if (sp->viscous == 1 && (sp->sgm0 <= 0 || sp->nu < 0 || sp->cs_itmax < 0))
@@ -140,7 +142,7 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
     TRY(sfs_after());
     const int relax = sp->relax ? 1 : 0;
     TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_euler<<<nb, 256, 0, st>>>(a, relax); }));
-    if (sp->viscous) TRY(field_corespreading(h, sp, 0.0, 0.0));
+    if (sp->viscous) TRY(field_viscous(h, sp, 0.0, 0.0));
   } else {  // rungekutta3: src/FLOWVPM_timeintegration.jl:388-461
     TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_reset_M<<<nb, 256, 0, st>>>(a); }));
     const double ab[3][2] = {{0.0, 1.0 / 3}, {-5.0 / 9, 15.0 / 16}, {-153.0 / 128, 8.0 / 15}};
@@ -150,7 +152,7 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
       TRY(field_uj(h, sp->kernel_id, uj_flags));
       if (k == 0) TRY(sfs_after());
       TRY(on_all([&](StepArgs &a, cudaStream_t st) { step_rk_stage<<<nb, 256, 0, st>>>(a); }));
-      if (sp->viscous) TRY(field_corespreading(h, sp, ab[k][0], ab[k][1]));
+      if (sp->viscous) TRY(field_viscous(h, sp, ab[k][0], ab[k][1]));
     }
     if (sp->relax && sp->relaxation) {
       TRY(field_uj(h, sp->kernel_id, VPM_FLAG_RESET | tr));

@@ -225,6 +225,21 @@ int field_corespreading(vpm_handle *h, const vpm_step_params *sp, double aux1, d
   return VPM_OK;
 }
 
+// viscousdiffusion(pfield, ParticleStrengthExchange, dt; aux1, aux2): src/FLOWVPM_viscous.jl:257-298
+// (viscous = 2: recalculate_vols = true, the default; 3: false)
+int field_pse(vpm_handle *h, const vpm_step_params *sp, double aux1, double aux2) {
+  const unsigned nb = blocks_for(h->fld_np, 256);
+  const int rk = sp->integration == 1;
+  return field_on_all(h, [&](Dev &d) {
+    StepArgs a = step_args_of(h, d);
+    a.a = aux1; a.b = aux2; a.dt = sp->dt;
+    pse_update<<<nb, 256, 0, d.stream>>>(a, sp->nu, rk, sp->viscous == 2);
+  });
+}
+int field_viscous(vpm_handle *h, const vpm_step_params *sp, double aux1, double aux2) {
+  return sp->viscous == 1 ? field_corespreading(h, sp, aux1, aux2) : field_pse(h, sp, aux1, aux2);
+}
+
 double zeta0_of(int kernel) {  // kernel.zeta(0): src/FLOWVPM_kernel.jl:45,51,60,69-74
   const double pi = 3.14159265358979323846;
   switch (kernel) {

@@ -281,6 +281,33 @@ __global__ void cs_spread(StepArgs a, double nu, int rk) {
   }
 }
 
+// ParticleStrengthExchange, the per-particle part of viscousdiffusion (src/FLOWVPM_viscous.jl:257-298):
+// optionally vol <- 4/3 pi sigma^3, then Gamma += dt nu PSE (Euler) resp. M[4:6] += dt nu PSE,
+// Gamma += aux2 dt nu PSE (RK3), over the non-static particles.  In v4.0.3 nothing ever accumulates
+// into the PSE rows 25:27 (src/FLOWVPM_particlefield.jl:482-489 only zero them), so the strength update
+// adds zeros for every particle that has been reset; it is restated as written.
+enum { S_PSE = 24 };
+__global__ void pse_update(StepArgs a, double nu, int rk, int recalculate_vols) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.np) return;
+  double *p = a.P + i * a.nf;
+  if (p[S_STATIC] != 0.0) return;
+  if (recalculate_vols) {
+    const double sg = p[S_SIGMA];
+    p[S_VOL] = __dmul_rn(__dmul_rn(4.0 / 3.0, 3.14159265358979323846), __dmul_rn(__dmul_rn(sg, sg), sg));
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double q = __dmul_rn(__dmul_rn(a.dt, nu), p[S_PSE + k]);
+    if (rk) {
+      p[S_M + 3 + k] = __dadd_rn(p[S_M + 3 + k], q);
+      p[S_G + k] = __dadd_rn(p[S_G + k], __dmul_rn(__dmul_rn(__dmul_rn(a.b, a.dt), nu), p[S_PSE + k]));
+    } else {
+      p[S_G + k] = __dadd_rn(p[S_G + k], q);
+    }
+  }
+}
+
 // overgrown cores: target vorticity M[7:9] <- J[1:3] (basis evaluation), sigma <- sgm0 (:205-212)
 __global__ void cs_reset(StepArgs a, double sgm0) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

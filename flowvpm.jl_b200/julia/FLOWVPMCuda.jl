@@ -347,7 +347,8 @@ function nextstep_cuda!(pfield::vpm.ParticleField{Float64}, dt::Real; relax::Boo
     deltat = pfield.nt > 0 ? pfield.t / pfield.nt : 0.0
     V = pfield.viscous
     cs = V isa vpm.CoreSpreading          # evaluated with zeta_direct on the device
-    nu, sgm0, cs_beta, cs_tol = cs ? (V.nu, V.sgm0, V.beta, V.tol) : (0.0, 1.0, 1.5, 1e-3)
+    pse = V isa vpm.ParticleStrengthExchange   # per-particle part only (src/FLOWVPM_viscous.jl:257-298)
+    nu, sgm0, cs_beta, cs_tol = cs ? (V.nu, V.sgm0, V.beta, V.tol) : (pse ? V.nu : 0.0, 1.0, 1.5, 1e-3)
     if cs
         t_sgm = Ref{Cdouble}(V.t_sgm)
         check(ccall((:vpm_field_tsgm, lib[]), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Cint), handle[], t_sgm, 1))
@@ -356,7 +357,7 @@ function nextstep_cuda!(pfield::vpm.ParticleField{Float64}, dt::Real; relax::Boo
                         deltat, nu, sgm0, cs_beta, cs_tol, kernel_id(pfield.kernel), integration, relaxation, relax,
                         sfs, clip_backscatter, pfield.transposed, force_positive,
                         Int32(control_directional) | (Int32(control_magnitude) << 1),
-                        cs, cs ? V.itmax : 15, cs ? V.iterror : true))
+                        cs ? 1 : (pse ? (V.recalculate_vols ? 2 : 3) : 0), cs ? V.itmax : 15, cs ? V.iterror : true))
     check(ccall((:vpm_field_step, lib[]), Cint, (Ptr{Cvoid}, Ref{StepParams}), handle[], sp))
     if cs
         check(ccall((:vpm_field_tsgm, lib[]), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Cint), handle[], t_sgm, 0))

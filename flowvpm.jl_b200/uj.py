@@ -319,7 +319,8 @@ class ResidentField:
         """sfs: False | "constant" (ConstantSFS, coefficient Cs) | "dynamic" (DynamicSFS with the
         pseudo-3-level procedure: alpha, sfs_rlxf, minC, maxC, force_positive);
         viscous: None (Inviscid) | dict(nu=, sgm0=, beta=1.5, itmax=15, tol=1e-3, iterror=True) for
-        CoreSpreading(nu, sgm0, zeta_direct) (src/FLOWVPM_viscous.jl:63-223)"""
+        CoreSpreading(nu, sgm0, zeta_direct) (src/FLOWVPM_viscous.jl:63-223) |
+        dict(scheme="pse", nu=, recalculate_vols=True) for ParticleStrengthExchange (:228-298)"""
         if minC < 0 or maxC < 0 or minC > maxC:
             raise ValueError(f"Invalid C bounds: minC={minC}, maxC={maxC}")  # subfilterscale.jl:456-462
         sp = _cabi.VpmStepParams()
@@ -334,7 +335,11 @@ class ResidentField:
         sp.relaxation = self.RELAXATIONS[relaxation]
         sp.relax, sp.sfs, sp.clip_backscatter = int(relax), self.SFS_SCHEMES[sfs], int(clip_backscatter)
         sp.transposed = int(self.pfield.transposed)
-        if viscous is not None:
+        if viscous is not None and viscous.get("scheme", "corespreading") == "pse":
+            # ParticleStrengthExchange(nu; recalculate_vols): the per-particle part, src/FLOWVPM_viscous.jl:257-298
+            sp.viscous = 2 if viscous.get("recalculate_vols", True) else 3
+            sp.nu = viscous["nu"]
+        elif viscous is not None:
             sp.viscous = 1
             sp.nu, sp.sgm0 = viscous["nu"], viscous["sgm0"]
             sp.cs_beta, sp.cs_tol = viscous.get("beta", 1.5), viscous.get("tol", 1e-3)

@@ -261,7 +261,10 @@ typedef struct vpm_step_params {
   int32_t controls;         /* SFS controls: bit 0 control_directional, bit 1 control_magnitude
                                (src/FLOWVPM_subfilterscale.jl:300-397) */
   int32_t viscous;          /* 0 Inviscid, 1 CoreSpreading (requires the gaussianerf kernel,
-                               src/FLOWVPM.jl:265-267) */
+                               src/FLOWVPM.jl:265-267), 2 / 3 ParticleStrengthExchange(nu) with / without
+                               recalculate_vols: the per-particle part of src/FLOWVPM_viscous.jl:257-298 (the
+                               reference's scheme errors unless UJ == UJ_fmm and, in v4.0.3, nothing ever
+                               accumulates into the PSE rows it reads) */
   int32_t cs_itmax;         /* maximum RBF iterations (default 15) */
   int32_t cs_iterror;       /* fail when the RBF does not converge (default 1) */
 } vpm_step_params;

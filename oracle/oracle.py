@@ -185,6 +185,16 @@ def direct_buffers(tgt, t0, t1, src, s0, s1, kernel, want_U=True, want_J=True, n
                                        int(nthreads))
 
 
+def _viscous_id(viscous):
+    """None -> 0 Inviscid; dict without "scheme" or scheme="corespreading" -> 1; scheme="pse" -> 2 (3 when
+    recalculate_vols=False)"""
+    if viscous is None:
+        return 0
+    if viscous.get("scheme", "corespreading") == "pse":
+        return 2 if viscous.get("recalculate_vols", True) else 3
+    return 1
+
+
 def field_step(P, np_, kernel, dt, *, integration="rungekutta3", f=0.0, g=0.2, Uinf=(0.0, 0.0, 0.0), sfs=False,
                Cs=1.0, clip_backscatter=False, relaxation="pedrizzetti", relax=True, rlxf=0.3, transposed=True,
                alpha=0.667, sfs_rlxf=0.005, minC=0.0, maxC=1.0, force_positive=False, control_directional=False,
@@ -201,12 +211,12 @@ def field_step(P, np_, kernel, dt, *, integration="rungekutta3", f=0.0, g=0.2, U
                    {False: 0, None: 0, "none": 0, True: 1, "constant": 1, "dynamic": 2}[sfs],
                    int(clip_backscatter), int(transposed), int(force_positive),
                    int(control_directional) | (int(control_magnitude) << 1),
-                   int(viscous is not None), int(v.get("itmax", 15)), int(v.get("iterror", True))], dtype=np.int32)
+                   _viscous_id(viscous), int(v.get("itmax", 15)), int(v.get("iterror", True))], dtype=np.int32)
     rc = lib().vpm_oracle_field_step(P.ctypes.data, P.shape[0], int(np_), dp.ctypes.data, ip.ctypes.data,
                                      int(nthreads or max_threads()))
     if rc != 0:
         raise RuntimeError(f"oracle field_step failed ({rc})")
-    if viscous is not None:
+    if viscous is not None and _viscous_id(viscous) == 1:
         viscous["t_sgm"] = float(dp[17])   # CoreSpreading.t_sgm: time since the last core reset
 
 

@@ -902,6 +902,26 @@ static int o_corespreading(double *P, int64_t nf, int64_t np, int kernel, int in
   return 0;
 }
 
+/* viscousdiffusion(pfield, ParticleStrengthExchange, dt; aux1, aux2): src/FLOWVPM_viscous.jl:257-298 (the
+ * `pfield.UJ != UJ_fmm` error of :259-262 is the caller's business: this is the per-particle part) */
+static void o_pse(double *P, int64_t nf, int64_t np, int integration, double dt, double aux2, double nu,
+                  int recalculate_vols) {
+  const double pi = 3.14159265358979323846;
+  for (int64_t i = 0; i < np; ++i) {
+    double *p = P + nf * i;
+    if (p[R_STATIC] != 0.0) continue;
+    if (recalculate_vols) p[7] = 4.0 / 3.0 * pi * (p[R_SIGMA] * p[R_SIGMA] * p[R_SIGMA]); /* 4/3*pi*sigma^3 */
+    for (int k = 0; k < 3; ++k) {
+      if (integration == 0) {
+        p[R_G + k] += dt * nu * p[R_PSE + k];
+      } else {
+        p[R_M + 3 + k] += dt * nu * p[R_PSE + k];
+        p[R_G + k] += aux2 * dt * nu * p[R_PSE + k];
+      }
+    }
+  }
+}
+
 int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, double *dp, const int *ip, int nthreads) {
   init_consts();
   const int viscous = ip[9], itmax = ip[10], iterror = ip[11];
@@ -931,7 +951,8 @@ int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, double *dp, const i
       p[R_SIGMA] -= dt * (p[R_SIGMA] * MM4);
       if (relax && relaxation) o_relax(p, rlxf, relaxation);
     }
-    if (viscous) return o_corespreading(P, nf, np, kernel, 0, dt, 0.0, 0.0, vis, itmax, iterror, nthreads);
+    if (viscous == 1) return o_corespreading(P, nf, np, kernel, 0, dt, 0.0, 0.0, vis, itmax, iterror, nthreads);
+    if (viscous >= 2) o_pse(P, nf, np, 0, dt, 0.0, vis[0], viscous == 2);
     return 0;
   }
   for (int64_t i = 0; i < np; ++i)
@@ -959,9 +980,11 @@ int vpm_oracle_field_step(double *P, int64_t nf, int64_t np, double *dp, const i
       for (int k = 0; k < 3; ++k) G[k] += b * M[3 + k];
       p[R_SIGMA] += b * M[7];
     }
-    if (viscous) {
+    if (viscous == 1) {
       int rc = o_corespreading(P, nf, np, kernel, 1, dt, a, b, vis, itmax, iterror, nthreads);
       if (rc < 0) return rc;
+    } else if (viscous >= 2) {
+      o_pse(P, nf, np, 1, dt, b, vis[0], viscous == 2);
     }
   }
   if (relax && relaxation) {

@@ -302,3 +302,17 @@ def test_oracle_rbf_recovers_strengths(vpm):
     assert relerr(P[3:6, :n], G0) < 1e-4
     oracle.zeta_direct(P, n, "gaussianerf")
     assert relerr(P[15:18, :n], W) < 1e-6
+
+
+def test_oracle_pse_is_inviscid_plus_volumes(vpm):
+    """in v4.0.3 nothing accumulates into the PSE rows (src/FLOWVPM_particlefield.jl:482-489 only zero them), so a
+    step with ParticleStrengthExchange equals the inviscid step except for the recomputed volumes
+    (src/FLOWVPM_viscous.jl:264-268)"""
+    pf = vpm.fields.ring_field(Nphi=40, nc=1, kernel=vpm.winckelmans)
+    a, b = pf.particles.copy(order="F"), pf.particles.copy(order="F")
+    kw = dict(integration="rungekutta3", f=0.0, g=0.2, sfs=False, relaxation="pedrizzetti", relax=True)
+    oracle.field_step(a, pf.np, "winckelmans", 1e-2, viscous=dict(scheme="pse", nu=0.5), **kw)
+    oracle.field_step(b, pf.np, "winckelmans", 1e-2, **kw)
+    rows = [r for r in range(46) if r != 7]
+    assert np.array_equal(a[rows], b[rows])
+    assert np.allclose(a[7, :pf.np], 4 / 3 * np.pi * a[6, :pf.np] ** 3, rtol=1e-15) and not np.array_equal(a[7], b[7])

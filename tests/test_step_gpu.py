@@ -141,6 +141,38 @@ def test_corespreading_step_matches_oracle(vpm, handle, integration):
         rf.nextstep(5e-2, viscous=vis, **kw)
 
 
+@pytest.mark.parametrize("integration", ["euler", "rungekutta3"])
+@pytest.mark.parametrize("recalculate_vols", [True, False])
+def test_pse_step_matches_oracle(vpm, handle, integration, recalculate_vols):
+    """viscousdiffusion(pfield, ParticleStrengthExchange, dt) (src/FLOWVPM_viscous.jl:257-298), the per-particle
+    part: volumes recomputed from sigma, strengths updated with nu * PSE rows (static particles keep whatever
+    their never-reset PSE rows hold and are skipped by the iterator)"""
+    pf = make_field(vpm, vpm.winckelmans)
+    pf.particles[42, 3:pf.np:11] = 1.0
+    pf.particles[24:27, :pf.np] = 0.3            # visible only if the reset rules were wrong
+    pf.particles[7, :pf.np] = 1.0
+    ref = pf.particles.copy(order="F")
+    vis = dict(scheme="pse", nu=1e-2, recalculate_vols=recalculate_vols)
+    kw = dict(integration=integration, f=0.0, g=0.2, sfs=False, relaxation="pedrizzetti", relax=True)
+    rf = vpm.ResidentField(pf)
+    for _ in range(2):
+        rf.nextstep(2e-2, viscous=vis, **kw)
+        oracle.field_step(ref, pf.np, "winckelmans", 2e-2, transposed=True, viscous=vis, **kw)
+    rf.download()
+    free = pf.particles[42, :pf.np] == 0
+    for name, r in ROWS.items():
+        if name in ("SFS", "C"):
+            continue
+        assert relerr(pf.particles[r, :pf.np], ref[r, :pf.np]) < 1e-11, name
+    assert relerr(pf.particles[7, :pf.np], ref[7, :pf.np]) < 1e-11    # volumes follow sigma, itself at 1e-12
+    sg = pf.particles[6, :pf.np][free]
+    if recalculate_vols:
+        assert np.allclose(pf.particles[7, :pf.np][free], 4 / 3 * np.pi * sg**3, rtol=1e-15)
+    else:
+        assert np.all(pf.particles[7, :pf.np] == 1.0)
+    assert np.all(pf.particles[7, :pf.np][~free] == 1.0)
+
+
 def test_formulations_and_classic_scheme(vpm, handle):
     for f, g, transposed in ((0.0, 0.0, True), (0.5, 0.0, True), (0.25, 0.25, False)):
         pf = make_field(vpm, vpm.gaussianerf)
