@@ -38,7 +38,7 @@ Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind, int variant 
   return p;
 }
 
-constexpr double kTabNearFraction = 0.30;  // automatic choice: table kernel from this share of near pairs on
+constexpr double kTabNearFraction = 0.40;  // automatic choice: table kernel from this share of sampled warps with a near pair on
 
 // Plan of the table kernel (vpm_kernels_tab.cuh): one CTA per SM, 512 (or 384) threads x 2 targets.
 // `fills` tells whether the field is large enough to give every SM >= 8 CTAs even at one
@@ -186,25 +186,24 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
   if ((kernel == K_GERF || kernel == K_GAUS) && !use_const && h->opt_uj_table != 2 && nt > 0 && ns > 0) {
     bool fills = false;
     Plan pt = make_plan_tab(nt, ns, d.sm_count, &fills, h->opt_uj_variant);
-    if (h->opt_uj_table == 1 || (fills && kernel == K_GERF && (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT))) {
+    if (h->opt_uj_table == 1 || (fills && (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT))) {
       plan = pt; use_tab = true;  // forced, or every pair is to take the regularised evaluation anyway
-    } else if (fills && kernel == K_GERF) {
-      // Automatic choice.  The table kernel wins where a large share of the pairs is inside the
-      // regularised range (warps that mix near and far lanes run one code path, conflict-free
-      // gathers); where nearly every warp is entirely in the far field the round-1 kernel's smaller
-      // CTAs are ~4 % faster.  Decide on a sample of 65 536 pairs (deterministic hash; one small
-      // kernel and an 8-byte read-back, i.e. one synchronisation of `st` -- only reached for sweeps
-      // of >= 1e8 pairs).  The gaussian family gains nothing from the table kernel (its s = r/sigma
-      // needs the rsqrt either way) and stays on the round-1 kernel unless forced.
+    } else if (fills) {
+      // Automatic choice.  The table kernel wins where most WARPS see pairs inside the regularised range
+      // (lanes that mix near and far run one code path, conflict-free gathers); where most warps are
+      // entirely in the far field the round-1 kernel's smaller CTAs are ~5-10 % faster.  Decide on 2048
+      // sampled (32 consecutive targets, source) warps (deterministic hash; one small kernel and a 4-byte
+      // read-back, i.e. one synchronisation of `st` -- only reached for sweeps of >= 1e8 pairs).
       TRY(ensure(h, d.cubtmp, 256));
       unsigned int *cnt = (unsigned int *)d.cubtmp.p;
       CK(h, cudaMemsetAsync(cnt, 0, sizeof(unsigned int), st));
-      sample_near_kernel<<<kSampleBlocks, kSampleThreads, 0, st>>>(src, s0, ns, tpos, tld, nt, kFarU_gerf, cnt);
+      sample_near_kernel<<<kSampleBlocks, kSampleThreads, 0, st>>>(src, s0, ns, tpos, tld, nt,
+                                                                   kernel == K_GERF ? kFarU_gerf : kFarU_gaus, cnt);
       unsigned int near = 0;
       CK(h, cudaMemcpyAsync(&near, cnt, sizeof near, cudaMemcpyDeviceToHost, st));
       CK(h, cudaStreamSynchronize(st));
       h->launches++;
-      h->last_near_fraction = (double)near / (double)(kSampleBlocks * kSampleThreads);
+      h->last_near_fraction = (double)near / (double)(kSampleBlocks * kSampleThreads / 32);
       if (h->last_near_fraction >= kTabNearFraction) { plan = pt; use_tab = true; }
     }
   }

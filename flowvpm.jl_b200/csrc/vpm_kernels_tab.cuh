@@ -10,8 +10,8 @@
 // inside the regularised range the lanes of a warp hit different rows, the gathers bank-conflict
 // (ncu: shared-memory wavefronts 94 % of peak, FP64 pipe 67 % active, 205 G pairs/s = 0.44 of the
 // FP64 roofline -- profiles/r2_gerf_dense_before_ncu_summary.txt).  This version
-//   * tabulates G on intervals uniform in the BITS of t = v + c (v = u for gaussianerf, v = s for
-//     gaussian; 2^LOGN intervals per octave of t): the row index and the in-interval coordinate
+//   * tabulates G(u), u = s^2, on intervals uniform in the BITS of t = u + c (c = 4 for gaussianerf; c = 0 and
+//     rows from u = 1/4 for gaussian, whose G is not analytic at u = 0; 2^LOGN intervals per octave of t): the row index and the in-interval coordinate
 //     xi in [-1/2, 1/2) come from the exponent/mantissa fields of t on the integer pipe -- no
 //     FP64 magic-number rounding, and the relative interval width follows the function's scale;
 //   * evaluates value and derivative with one joint Horner pass of degree 7 whose three highest
@@ -38,11 +38,13 @@ constexpr int kTabRowBytes = kTabRowChunks * 8 * 16;   // one row of all eight c
 
 template <int K> struct TabOf;
 template <> struct TabOf<K_GERF> {
-  static constexpr int kappa = kTabGerfKappa, logn = kTabGerfLogN, near = kTabGerfRows, far = kTabGerfFarRows, rows = near + far;
+  static constexpr int offset = kTabGerfOffset, emin = kTabGerfEmin, logn = kTabGerfLogN, near = kTabGerfRows,
+                       far = kTabGerfFarRows, rows = near + far;
   static __device__ __forceinline__ const uint64_t *words() { return kTabGerf; }
 };
 template <> struct TabOf<K_GAUS> {
-  static constexpr int kappa = kTabGausKappa, logn = kTabGausLogN, near = kTabGausRows, far = kTabGausFarRows, rows = near + far;
+  static constexpr int offset = kTabGausOffset, emin = kTabGausEmin, logn = kTabGausLogN, near = kTabGausRows,
+                       far = kTabGausFarRows, rows = near + far;
   static __device__ __forceinline__ const uint64_t *words() { return kTabGaus; }
 };
 
@@ -74,9 +76,8 @@ __device__ __forceinline__ double2 lds_v2(uint32_t addr) {
   return v;
 }
 
-// Records (prep_uj_records_tab):  [x y z q0 | G'x G'y G'z q1 | q2 q3]
-//   gaussianerf: q0 = 1/sigma^2, q1 = 1/sigma^3, q2 = far cut-off in r^2, q3 = 2/sigma^5
-//   gaussian:    q0 = 1/sigma^3, q1 = 1/sigma,   q2 = far cut-off in r^2, q3 = 1/sigma^4
+// Records (prep_uj_records_tab), the same for both families:  [x y z q0 | G'x G'y G'z q1 | q2 q3],
+//   q0 = 1/sigma^2 (u = r^2 q0), q1 = 1/sigma^3 (A = q1 G), q2 = far cut-off in r^2, q3 = 2/sigma^5 (B = q3 dG/du)
 __global__ void prep_uj_records_tab(SrcView src, int64_t s0, int64_t ns, int64_t ns_pad, int kernel,
                                     double *__restrict__ rec) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,15 +95,11 @@ __global__ void prep_uj_records_tab(SrcView src, int64_t s0, int64_t ns, int64_t
   const double isig = 1.0 / sigma;
   const double isig2 = isig * isig;
   const double isig3 = isig2 * isig;
-  double q0, q1, q2, q3;
-  if (kernel == K_GERF) {
-    q0 = isig2; q1 = isig3; q2 = kFarU_gerf * (sigma * sigma); q3 = 2.0 * isig3 * isig2;
-  } else {
-    q0 = isig3; q1 = isig; q2 = kFarU_gaus * (sigma * sigma); q3 = isig2 * isig2;
-  }
-  r[0] = p[src.ox]; r[1] = p[src.ox + 1]; r[2] = p[src.ox + 2]; r[3] = q0;
+  r[0] = p[src.ox]; r[1] = p[src.ox + 1]; r[2] = p[src.ox + 2]; r[3] = isig2;
   r[4] = -kConst4 * p[src.og]; r[5] = -kConst4 * p[src.og + 1]; r[6] = -kConst4 * p[src.og + 2];
-  r[7] = q1; r[8] = q2; r[9] = q3;
+  r[7] = isig3;
+  r[8] = (kernel == K_GERF ? kFarU_gerf : kFarU_gaus) * (sigma * sigma);
+  r[9] = 2.0 * isig3 * isig2;
 }
 
 // Value p and xi-derivative dp of the polynomial of row `row` at the in-interval coordinate
@@ -135,56 +132,80 @@ __device__ __forceinline__ void tab_poly(int hi, unsigned lo, unsigned row, uint
   dp = d;
 }
 
-// A = G/sigma^3 (gaussianerf: q1 = 1/sigma^3) and B = 2 dG/du / sigma^5 resp. (dG/ds)/(s sigma^5) of one
-// pair; `far` = the pair is beyond the regularised range (g == 1, dg == 0).
-//   table rows [0, 128): the power law (far lanes): t = v, row = exponent parity bit (v^-3/2 only) and
-//     the top mantissa bits of t; the rest of the power of two is an exponent shift of qA and q3;
-//   rows [128, 128 + near): regularised range: t = v + 2^KAPPA, row from exponent + top LOGN mantissa bits.
-// G = p 2^ka, dG/dv = dp 2^(LOGN - e + ka) with t = m 2^e; ka = 0 (near), -3 (e >> 1) (v^-3/2), -3 e (v^-3).
+// A = G/sigma^3 = q1 G and B = 2 dG/du / sigma^5 = q3 dG/du of one pair from the table of its family;
+// `far` = the pair is beyond the regularised range (g == 1, dg == 0); `t` = u + offset for a near lane,
+// u for a far lane (u = r^2 / sigma^2); no square root anywhere.
+//   table rows [0, 128): the power law u^-3/2 (far lanes): row = exponent parity bit and the top mantissa bits
+//     of t; the rest of the power of two is an exponent shift of q1 and q3;
+//   rows [128, 128 + near): regularised range: row from exponent + top LOGN mantissa bits of t.
+// G = p 2^ka, dG/du = dp 2^(LOGN - e + ka) with t = m 2^e; ka = 0 (near), -3 (e >> 1) (far).
 // All of that is integer arithmetic on the high words (E = biased exponent field of t, in place):
-//   kq = ka << 20 + C,  C = (1023 + LOGN) << 20;   hi(qA) += kq - C;   hi(q3) += kq - (E << 20).
-// gaussianerf needs no square root at all; gaussian needs s = r/sigma, r = r2 * rsqrt(r2).
+//   kq = ka << 20 + C,  C = (1023 + LOGN) << 20;   hi(q1) += kq - C;   hi(q3) += kq - (E << 20).
 // r2 == 0 (the reference skips those pairs, src/FLOWVPM_fmm.jl:118; c = dx x G' = 0 there, so only the
 // W sums need A = 0): A's scale factor gets a zero high word, i.e. A ~ 1e-320 (an exact 0 to any
 // tolerance); decided on the high word of r2 alone, so pairs closer than ~1e-154 count as coincident.
 template <int K>
-__device__ __forceinline__ void ab_tab(double r2, bool far, double q0, double q1, double q3,
+__device__ __forceinline__ void ab_tab(double t, double r2, bool far, double q1, double q3,
                                        uint32_t lane_tab, double &A, double &B) {
   using TB = TabOf<K>;
   constexpr int LOGN = TB::logn, MB = 20 - LOGN;
   static_assert(TB::far == 128, "far rows are indexed with a 7-bit mask");
   constexpr unsigned C = (unsigned)(1023 + LOGN) << 20;
   const bool z = __double2hiint(r2) == 0;
-  const double c = far ? 0.0 : (double)(1 << TB::kappa);
-  double t, rinv = 0.0;
-  if constexpr (K == K_GERF) {
-    t = fma(r2, q0, c);
-  } else {
-    // r2 == 0 -> 1 so that everything stays finite (B is multiplied by c = 0 for such a pair)
-    const double r2s = __hiloint2double(z ? 0x3ff00000 : __double2hiint(r2), __double2loint(r2));
-    rinv = rsqrt_fp64(r2s);
-    t = fma(r2 * rinv, q1, c);
-  }
   const int hi = __double2hiint(t);
   const unsigned lo = (unsigned)__double2loint(t);
   const int top = hi >> MB;  // biased exponent and the top LOGN mantissa bits
-  // t >= 2^KAPPA, so the difference is >= 0 for every finite near t; the unsigned compare also sends
-  // NaN (CUDA's canonical NaN has the sign bit set) and anything past the range to the last near row
-  const unsigned row_near = min((unsigned)(top - ((1023 + TB::kappa) << LOGN) + TB::far), (unsigned)(TB::rows - 1));
+  // t >= 2^EMIN for every finite near lane the table serves, so the difference is >= 0; the unsigned compare
+  // also sends NaN (CUDA's canonical NaN has the sign bit set), anything past the range and the gaussian
+  // family's u < 2^EMIN lanes (handled by the caller's rare path) to the last near row
+  const unsigned row_near = min((unsigned)(top - ((1023 + TB::emin) << LOGN) + TB::far), (unsigned)(TB::rows - 1));
   const unsigned row = far ? (unsigned)(top & (TB::far - 1)) : row_near;
   double p, dp;
   tab_poly<LOGN>(hi, lo, row, lane_tab, p, dp);
   const unsigned em = (unsigned)hi & 0xfff00000u;  // E << 20
-  unsigned kq;
-  if constexpr (K == K_GERF) kq = ((unsigned)(hi + 0x100000) >> 21) * (unsigned)(-3 << 20) + ((1536u << 20) + C);  // -3 ((E - 1023) >> 1)
-  else kq = em * (unsigned)(-3) + ((3069u << 20) + C);                                                          // -3 (E - 1023)
+  unsigned kq = ((unsigned)(hi + 0x100000) >> 21) * (unsigned)(-3 << 20) + ((1536u << 20) + C);  // -3 ((E - 1023) >> 1)
   kq = far ? kq : C;
-  const double qA = K == K_GERF ? q1 : q0;
-  const unsigned hA = (unsigned)__double2hiint(qA) + kq - C;
-  A = __hiloint2double((int)(z ? 0u : hA), __double2loint(qA)) * p;
-  const double q3s = __hiloint2double((int)((unsigned)__double2hiint(q3) + kq - em), __double2loint(q3));
-  if constexpr (K == K_GERF) B = q3s * dp;
-  else B = (dp * rinv) * q3s;
+  const unsigned hA = (unsigned)__double2hiint(q1) + kq - C;
+  A = __hiloint2double((int)(z ? 0u : hA), __double2loint(q1)) * p;
+  B = __hiloint2double((int)((unsigned)__double2hiint(q3) + kq - em), __double2loint(q3)) * dp;
+}
+
+// The gaussian family off its table (some lane of the warp has a pair closer than s = 1/2, the self pair
+// included), for every lane of that warp-iteration.  With v = s^3:  G = g/s^3 = phi(v),  phi = (1 - e^-v)/v,  and
+// 2 dG/du = 3 (e^-v v - (1 - e^-v))/s^5 = 3 s psi(v),  psi = (e^-v v - 1 + e^-v)/v^2.  For v >= 1/32 these are
+// evaluated through exp as the reference does (src/FLOWVPM_kernel.jl:63-66; its 1 - e^-v loses at most five bits
+// there); below, where the reference's form cancels (g == 0 for s < 1e-5), from their Taylor series
+//   phi = sum_k (-v)^k / (k+1)!,   psi = sum_k (-1)^(k+1) (k+1)/(k+2)! v^k   (nine terms: < 1e-20 at v = 1/32).
+// Rare: one pair per target and sweep plus physically overlapping neighbours.
+__device__ __forceinline__ void ab_gaus_u(double r2, bool far, double q0, double q1, double q3, double &A, double &B) {
+  const bool z = __double2hiint(r2) == 0;
+  const double u0 = r2 * q0;
+  const double u = __hiloint2double(z ? 0x3ff00000 : __double2hiint(u0), __double2loint(u0));  // 0 -> 1: finite
+  const double y = rsqrt_fp64(u);      // 1/s
+  const double s = u * y;
+  const double v = u * s;
+  const double y2 = y * y, y3 = y2 * y, y5 = y3 * y2;
+  double G, H;                         // G and 2 dG/du
+  if (far) {
+    G = y3; H = -3.0 * y5;
+  } else if (v < 0.03125) {
+    double ph = 1.0 / 362880.0, ps = -9.0 / 3628800.0;  // k = 8
+    ph = fma(ph, -v, 1.0 / 40320.0);  ps = fma(ps, -v, -8.0 / 362880.0);
+    ph = fma(ph, -v, 1.0 / 5040.0);   ps = fma(ps, -v, -7.0 / 40320.0);
+    ph = fma(ph, -v, 1.0 / 720.0);    ps = fma(ps, -v, -6.0 / 5040.0);
+    ph = fma(ph, -v, 1.0 / 120.0);    ps = fma(ps, -v, -5.0 / 720.0);
+    ph = fma(ph, -v, 1.0 / 24.0);     ps = fma(ps, -v, -4.0 / 120.0);
+    ph = fma(ph, -v, 1.0 / 6.0);      ps = fma(ps, -v, -3.0 / 24.0);
+    ph = fma(ph, -v, 1.0 / 2.0);      ps = fma(ps, -v, -2.0 / 6.0);
+    ph = fma(ph, -v, 1.0);            ps = fma(ps, -v, -1.0 / 2.0);
+    G = ph; H = 3.0 * s * ps;
+  } else {
+    const double E = exp_neg_fp64(v);
+    const double g = 1.0 - E;
+    G = g * y3; H = 3.0 * (E * v - g) * y5;
+  }
+  A = select_zero(z, q1 * G);
+  B = select_zero(z, (0.5 * q3) * H);
 }
 
 template <int K, int UNROLL>
@@ -210,9 +231,22 @@ __device__ __forceinline__ void uj_tile_tab(const double2 *__restrict__ tile, in
     for (int t = 0; t < T; ++t) near |= __double2hiint(r2[t]) <= far_hi;
     if (__any_sync(0xffffffffu, near)) {
       // one code path for the whole warp: lanes beyond the cut-off read the power-law rows
+      using TB = TabOf<K>;
+      double tt[T];
+      bool far[T], rare = false;
 #pragma unroll
-      for (int t = 0; t < T; ++t)
-        ab_tab<K>(r2[t], __double2hiint(r2[t]) > far_hi, q0, q1, q3, lane_tab, A[t], B[t]);
+      for (int t = 0; t < T; ++t) {
+        far[t] = __double2hiint(r2[t]) > far_hi;
+        tt[t] = fma(r2[t], q0, far[t] ? 0.0 : (double)TB::offset);
+        if constexpr (K == K_GAUS) rare |= !far[t] && __double2hiint(tt[t]) < ((1023 + TB::emin) << 20);
+      }
+      if (K == K_GAUS && __any_sync(0xffffffffu, rare)) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) ab_gaus_u(r2[t], far[t], q0, q1, q3, A[t], B[t]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < T; ++t) ab_tab<K>(tt[t], r2[t], far[t], q1, q3, lane_tab, A[t], B[t]);
+      }
     } else {
       // every pair of the warp is in the far field: g = 1, dg = 0 (cheaper than the table)
 #pragma unroll
@@ -320,19 +354,25 @@ __global__ void __launch_bounds__(THREADS, 1) uj_pairs_tab_kernel(const UjArgs a
   }
 }
 
-// Fraction of (target, source) pairs inside the regularised range, from 65 536 pseudo-random pairs
-// (a fixed hash of the sample index: the same field gives the same count, so the kernel choice that
-// depends on it is deterministic).  out[0] += pairs with r^2 < cutoff_u * sigma_source^2.
+// How often does a warp of the sweep see a pair inside the regularised range?  2048 samples, each one warp
+// = 32 CONSECUTIVE targets against one pseudo-random source (a fixed hash of the sample index: the same
+// field gives the same count, so the kernel choice that depends on it is deterministic).
+// out[0] += samples in which at least one of the 32 pairs has r^2 < cutoff_u * sigma_source^2.
+// It is the warp-level share that matters, not the pair-level one: in a spatially ordered field (rings,
+// sorted clouds) near pairs come in whole warps and the far-field shortcut still serves most warps, in an
+// unordered dense field nearly every warp mixes near and far lanes.
 __global__ void sample_near_kernel(SrcView src, int64_t s0, int64_t ns, const double *__restrict__ tpos, int64_t tld,
                                    int64_t nt, double cutoff_u, unsigned int *out) {
-  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   auto mix = [](unsigned long long x) {  // splitmix64 finaliser
     x += 0x9e3779b97f4a7c15ull;
     x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
     x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
     return x ^ (x >> 31);
   };
-  const int64_t i = (int64_t)(mix(2ull * k) % (unsigned long long)nt);
+  const int64_t nblk = (nt + 31) / 32;
+  int64_t i = (int64_t)(mix(2ull * k) % (unsigned long long)nblk) * 32 + lane;
+  if (i >= nt) i = nt - 1;
   const int64_t j = (int64_t)(mix(2ull * k + 1) % (unsigned long long)ns);
   const double *t = tpos + i * tld;
   const double *p = src.p + (s0 + j) * src.ld;
@@ -340,9 +380,9 @@ __global__ void sample_near_kernel(SrcView src, int64_t s0, int64_t ns, const do
   const double sg = p[src.osig];
   const bool near = dx * dx + dy * dy + dz * dz < cutoff_u * sg * sg;
   const unsigned m = __ballot_sync(0xffffffffu, near);
-  if ((threadIdx.x & 31) == 0) atomicAdd(out, (unsigned)__popc(m));
+  if (lane == 0 && m != 0) atomicAdd(out, 1u);
 }
-constexpr int kSampleBlocks = 256, kSampleThreads = 256;
+constexpr int kSampleBlocks = 256, kSampleThreads = 256;  // 2048 warps
 
 // device-math test hook (vpm_test_math op 4): (A, B) of the table path at r2 = in[i], sigma = 1
 template <int K>
@@ -353,9 +393,11 @@ __global__ void test_tab_kernel(const double *in, double *out, double *out2, int
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double A, B;
-  const double x = in[i];
+  const double x = in[i];  // r2 at sigma = 1: q0 = 1, q1 = 1, q3 = 2
   const bool far = x > (K == K_GERF ? kFarU_gerf : kFarU_gaus);
-  ab_tab<K>(x, far, 1.0, 1.0, K == K_GERF ? 2.0 : 1.0, smem_u32(smem) + 16 * (threadIdx.x & 7), A, B);
+  const double t = fma(x, 1.0, far ? 0.0 : (double)TabOf<K>::offset);
+  if (K == K_GAUS && !far && __double2hiint(t) < ((1023 + TabOf<K>::emin) << 20)) ab_gaus_u(x, far, 1.0, 1.0, 2.0, A, B);
+  else ab_tab<K>(t, x, far, 1.0, 2.0, smem_u32(smem) + 16 * (threadIdx.x & 7), A, B);
   out[i] = A;
   if (out2) out2[i] = B;
 }

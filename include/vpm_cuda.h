@@ -97,12 +97,12 @@ int vpm_num_devices(const vpm_handle *h);
 #define VPM_OPT_SFS_VARIANT 3     /* the same for the SFS pair kernel: 10, 20 or 0 (T only) */
 #define VPM_OPT_UJ_CONST 4        /* value != 0: constant-bank form of the U/J sweep (records copied 768 at a time
                                     into __constant__ memory, one launch per chunk).  Default 0. */
-#define VPM_OPT_UJ_TABLE 5        /* gaussianerf / gaussian U/J sweep: 0 = automatic (default: gaussianerf takes the
-                                    bank-replicated log-spaced table kernel, csrc/vpm_kernels_tab.cuh, when the field
-                                    is large enough to fill the GPU with 1024-target CTAs AND a deterministic sample
-                                    of 65 536 pairs finds >= 30 % of them inside the regularised range; that costs one
-                                    small kernel and one stream synchronisation per sweep of >= 1e8 pairs),
-                                    1 = always (both families), 2 = never (the round-1 kernels). */
+#define VPM_OPT_UJ_TABLE 5        /* gaussianerf / gaussian U/J sweep: 0 = automatic (default: the bank-replicated
+                                    log-spaced table kernel, csrc/vpm_kernels_tab.cuh, when the field is large enough
+                                    to fill the GPU with 1024-target CTAs AND, of 2048 deterministically sampled warps
+                                    (32 consecutive targets x one source), >= 40 % see a pair inside the regularised
+                                    range; that costs one small kernel and one stream synchronisation per sweep of
+                                    >= 1e8 pairs), 1 = always, 2 = never (the round-1 kernels). */
 #define VPM_OPT_SMALL_GRAPH 6      /* value != 0 (default): vpm_uj_direct on one device replays a captured CUDA graph for fields of
                                     <= 8 192 particles (the second call with the same matrix, np, kernel and flags
                                     captures it): one launch + one synchronisation per call instead of ~20 API calls.

@@ -55,7 +55,9 @@ def test_table_scalars_vs_mpmath(handle, kernel, kid, smax):
         else:
             worstB = max(worstB, float(abs((mp.mpf(float(B[i])) - Bm) / Bm)))
     assert worstA < 2e-15, worstA
-    assert worstB < 2e-14, worstB
+    # gaussian below s = 1/2 is off the table: there the device restates the reference's own formula, whose
+    # E s^3 - g cancels like the reference's does
+    assert worstB < (2e-13 if kernel == "gaussian" else 2e-14), worstB
 
 
 @pytest.mark.parametrize("kid", [1, 2])
@@ -137,12 +139,12 @@ def _run_with(vpm, handle, pf, base, opt):
 
 
 def test_automatic_choice_follows_the_sampled_near_fraction(vpm, handle):
-    """20 000 particles fill the GPU with 1024-target CTAs, so gaussianerf is a candidate for the table kernel;
-    the automatic plan takes it only when a deterministic sample of pairs finds >= 30 % of them inside s < 9:
-    a dense field (sigma x 4: every pair inside) runs the table kernel, the sparse C4 cloud the round-1
-    kernel -- seen from outside as bit-identity with the forced runs.  The gaussian family never takes it
-    automatically.  Every variant is in parity with the oracle."""
-    for kernel, scale, expect in (("gaussianerf", 8.0, 1), ("gaussianerf", 1.0, 2), ("gaussian", 8.0, 2)):
+    """20 000 particles fill the GPU with 1024-target CTAs, so the gaussian families are candidates for the table
+    kernel; the automatic plan takes it only when >= 40 % of a deterministic sample of warps (32 consecutive
+    targets x one source) see a pair inside the regularised range: a dense field (sigma x 8) runs the table
+    kernel, the sparse cloud the round-1 kernel -- seen from outside as bit-identity with the forced runs.
+    Every variant is in parity with the oracle."""
+    for kernel, scale, expect in (("gaussianerf", 8.0, 1), ("gaussianerf", 0.4, 2), ("gaussian", 8.0, 1), ("gaussian", 0.4, 2)):
         pf = vpm.fields.cloud_field(20000, kernel=vpm.KERNELS[kernel], seed=77)
         pf.particles[0:3] *= np.array([[1.0], [1.0], [1.0 / 7.0]])   # unit cube
         pf.particles[6] *= scale

@@ -5,9 +5,12 @@
 For a family with regularising function g(s) (src/FLOWVPM_kernel.jl:51-66) the pair loop needs
     A = g/r^3 = G/sigma^3            G(s) = g(s)/s^3
     B = (dg/(sigma r) - 3g/r^2)/r^3 = (1/s) dG/ds / sigma^5 = 2 dG/du / sigma^5,   u = s^2.
-G is tabulated as a function of v (v = u for gaussianerf, where G is analytic in u; v = s for
-gaussian, where it is not) on intervals that are uniform in the bits of t = v + c: interval
-`row` = the top (11 + LOGN) bits of t minus those of c, i.e. 2^LOGN intervals per octave of t.
+G is tabulated as a function of u = s^2 on intervals that are uniform in the bits of t = u + c:
+interval `row` = the top (11 + LOGN) bits of t minus those of 2^EMIN, i.e. 2^LOGN intervals per
+octave of t.  gaussianerf: G is analytic in u, c = 4 = 2^EMIN, rows from u = 0.  gaussian:
+G = (1 - exp(-u^1.5))/u^1.5 is NOT analytic at u = 0, so c = 0 (pure log spacing: every interval is
+narrow relative to its distance from 0, where the u^1.5 terms are smooth) and the rows start at
+u = 2^EMIN = 1/4; the rare pairs closer than s = 1/2 take an exp-based evaluation on the device.
 On each interval G(v) ~ p(xi), xi = (t - t_lo)/width - 1/2 in [-1/2, 1/2), a degree-7 polynomial
 (Chebyshev interpolant computed at 60 digits); the device evaluates p and dp/dxi with one
 joint Horner pass: c0..c4 in FP64, the three highest coefficients in FP32 (their terms are
@@ -15,11 +18,10 @@ joint Horner pass: c0..c4 in FP64, the three highest coefficients in FP32 (their
     [c0 c1] [c2 c3] [c4* (t5,t6)]     c4*: the low 20 bits of c4's mantissa hold t7 as
                                       sign + 8 exponent + 11 mantissa bits (t7 = float(bits << 12))
 Beyond the regularised range (g == 1 to < 2e-16: s >= 9 resp. 3.45) G is the pure power law
-v^-3/2 resp. v^-3.  NFAR rows stored in front of the others tabulate that power law on the mantissa of v itself (t = v, no
-offset): 2^LOGN rows per octave; for v^-3/2 two octaves [1, 4) so that the odd/even exponent
-parity is a row-index bit and the remaining scale 2^(-3 (e >> 1)) is an exponent shift; for v^-3
-one octave and the shift 2^(-3 e).  With them a warp whose lanes straddle the cut-off evaluates
-ONE code path (no second rsqrt-based evaluation).
+u^-3/2.  128 rows stored in front of the others tabulate it on the mantissa of u itself (t = u, no
+offset), 2^LOGN rows per octave over the two octaves [1, 4): the odd/even exponent parity is a
+row-index bit and the remaining scale 2^(-3 (e >> 1)) is an exponent shift.  With them a warp whose
+lanes straddle the cut-off evaluates ONE code path (no second rsqrt-based evaluation).
 The error quoted in the header is that of the PACKED row evaluated the way the device does
 (FP32 tail emulated with numpy float32), against mpmath.
 """
@@ -53,6 +55,15 @@ def gerf_dG(u):  # dG/du = H/2, H = (sqrt(2/pi) e^{-u/2} - 3G)/u
     return (C2 * mp.exp(-u / 2) - 3 * gerf_G(u)) / (2 * u)
 
 
+def gaus_Gu(u):
+    return gaus_G(mp.sqrt(mp.mpf(u)))
+
+
+def gaus_dGu(u):
+    s = mp.sqrt(mp.mpf(u))
+    return gaus_dG(s) / (2 * s)
+
+
 def gaus_G(s):
     s = mp.mpf(s)
     if s < mp.mpf("0.3"):
@@ -70,9 +81,9 @@ def gaus_dG(s):
 
 
 FAMILIES = {
-    # name: (G, dG/dv, log2(c), LOGN, largest v the table must cover)
-    "Gerf": (gerf_G, gerf_dG, 2, 6, 81.0),       # v = u = s^2; far field (g == 1) from s = 9
-    "Gaus": (gaus_G, gaus_dG, 0, 7, 3.45),       # v = s;       far field from s = 3.45
+    # name: (G(u), dG/du, offset c, EMIN = exponent of the first row's t, LOGN, largest u the table must cover)
+    "Gerf": (gerf_G, gerf_dG, 4, 2, 6, 81.0),          # far field (g == 1) from s = 9
+    "Gaus": (gaus_Gu, gaus_dGu, 0, -2, 6, 11.9025),    # far field from s = 3.45; u < 1/4 off the table
 }
 DEG = 7
 NHEAD = 5
@@ -144,16 +155,13 @@ def eval_packed(words, xi):
     return b, d
 
 
-FAR_POWER = {"Gerf": mp.mpf(-3) / 2, "Gaus": mp.mpf(-3)}
-
-
 def far_rows(name, logn):
-    """power-law rows: t in [1, 4) (two octaves, parity) for v^-3/2, t in [1, 2) for v^-3; the row
+    """power-law rows u^-3/2 for t = u in [1, 4) (two octaves: the exponent parity is a row bit); the row
     order follows the index bits the device uses: (E & 1) << LOGN | mantissa bits, E the BIASED
     exponent -- an odd biased exponent is an even true exponent."""
-    pw = FAR_POWER[name]
+    pw = mp.mpf(-3) / 2
     n = 1 << logn
-    octaves = [1, 0] if name == "Gerf" else [0]   # true-exponent parity of the first / second block of rows
+    octaves = [1, 0]   # true-exponent parity of the first / second block of rows
     rows, errG, errD = [], mp.mpf(0), mp.mpf(0)
     for par in octaves:
         for j in range(n):
@@ -173,15 +181,16 @@ def far_rows(name, logn):
 
 
 def family_rows(name):
-    G, dG, kappa, logn, vmax = FAMILIES[name]
-    c = mp.mpf(2) ** kappa
+    G, dG, c, emin, logn, vmax = FAMILIES[name]
+    c = mp.mpf(c)
+    first = mp.mpf(2) ** emin
     n = 1 << logn
-    nrows = int(mp.ceil(mp.log((vmax + c) / c, 2) * n))
+    nrows = int(mp.ceil(mp.log((vmax + c) / first, 2) * n))
     rows, errG, errD = [], mp.mpf(0), mp.mpf(0)
     for row in range(nrows):
         e, j = divmod(row, n)
-        t0 = c * 2 ** e * (1 + mp.mpf(j) / n)
-        w = c * 2 ** e / n
+        t0 = first * 2 ** e * (1 + mp.mpf(j) / n)
+        w = first * 2 ** e / n
         mid = t0 + w / 2
         co = cheb_mono(lambda xi: G(mid + xi * w - c), DEG)
         words = pack_row(co)
@@ -193,15 +202,10 @@ def family_rows(name):
             b, d = eval_packed(words, float(xi))
             tg, td = G(v), dG(v)
             errG = max(errG, abs((mp.mpf(b) - tg) / tg))
-            # derivative error relative to the size of the B term it feeds: |dG/dv| (gaussianerf), for the
-            # gaussian family |dG/ds|/s with an absolute floor where that quantity goes to zero (s -> 0)
-            if name == "Gaus":
-                errD = max(errD, abs(mp.mpf(d) / w - td) / v / max(abs(td) / v, mp.mpf("0.05")))
-            else:
-                errD = max(errD, abs((mp.mpf(d) / w - td) / td))
+            errD = max(errD, abs((mp.mpf(d) / w - td) / td))
     frows, ferrG, ferrD = far_rows(name, logn)
     # device row order: the power-law rows first (their index is a bit mask), then the regularised range
-    return dict(kappa=kappa, logn=logn, nrows=nrows, rows=frows + rows, errG=errG, errD=errD,
+    return dict(offset=int(c), emin=emin, logn=logn, nrows=nrows, rows=frows + rows, errG=errG, errD=errD,
                 nfar=len(frows), ferrG=ferrG, ferrD=ferrD)
 
 
@@ -214,10 +218,11 @@ def main():
         r = family_rows(name)
         print(name, "rows", r["nrows"], "errG", mp.nstr(r["errG"], 3), "errD", mp.nstr(r["errD"], 3),
               "far rows", r["nfar"], "errG", mp.nstr(r["ferrG"], 3), "errD", mp.nstr(r["ferrD"], 3), flush=True)
-        out.append(f"// {name}: t = v + 2^{r['kappa']}, 2^{r['logn']} intervals per octave, {r['nrows']} rows; max rel err of the packed rows")
-        out.append(f"// evaluated as on the device: G {mp.nstr(r['errG'], 3)}, dG/dv {mp.nstr(r['errD'], 3)};")
-        out.append(f"// before them (rows 0..{r['nfar'] - 1}) the power-law rows (t = v): G {mp.nstr(r['ferrG'], 3)}, dG/dv {mp.nstr(r['ferrD'], 3)}")
-        out.append(f"constexpr int kTab{name}Kappa = {r['kappa']};")
+        out.append(f"// {name}: t = u + {r['offset']}, first row at t = 2^{r['emin']}, 2^{r['logn']} intervals per octave, {r['nrows']} rows; max rel err of the packed rows")
+        out.append(f"// evaluated as on the device: G {mp.nstr(r['errG'], 3)}, dG/du {mp.nstr(r['errD'], 3)};")
+        out.append(f"// before them (rows 0..{r['nfar'] - 1}) the power-law rows u^-3/2 (t = u): G {mp.nstr(r['ferrG'], 3)}, dG/du {mp.nstr(r['ferrD'], 3)}")
+        out.append(f"constexpr int kTab{name}Offset = {r['offset']};")
+        out.append(f"constexpr int kTab{name}Emin = {r['emin']};")
         out.append(f"constexpr int kTab{name}LogN = {r['logn']};")
         out.append(f"constexpr int kTab{name}Rows = {r['nrows']};     // regularised range")
         out.append(f"constexpr int kTab{name}FarRows = {r['nfar']};  // power-law rows, stored first")
