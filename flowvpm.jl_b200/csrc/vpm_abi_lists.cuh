@@ -520,6 +520,15 @@ int vpm_uj_nearfield(vpm_handle *h, double *P, int64_t nf, int64_t np, int kerne
     TRY(h1_upload(h, d0, P, nf, np, !reset, false, has_static));
     if (!prior) CK(h, cudaMemsetAsync(d0.res18.p, 0, (size_t)np * RES_ROWS * sizeof(double), d0.stream));
   }
+  // The resident lists (sort index, leaf ranges, near-field list) are functions of X and sigma as they were at
+  // vpm_leaflists_build: once particles have moved the leaf spheres no longer bound their bodies and near pairs
+  // would be dropped silently.  Compare the fingerprint of the rows just uploaded with the build's.
+  {
+    unsigned long long fp = 0;
+    TRY(tree_fingerprint(h, d0, (const double *)d0.in7.p, 7, 6, np, &fp));
+    if (fp != h->tree_fingerprint)
+      return fail(h, VPM_ESTATE, "%s: positions or core sizes changed since vpm_leaflists_build; rebuild the leaf lists (they are valid for one particle configuration)", fn);
+  }
   const TreeView tv = tree_view(h);
   DevCsr c;
   TRY(build_csr_device(h, fn, tv.lbegin, tv.lend, h->tree_nl, np, tv.lbegin, tv.lend, h->tree_nl, np, tv.pt, tv.ps,

@@ -81,6 +81,7 @@ struct vpm_handle {
   int device_timing = 0;  // 1/2: ev[6..7] bracket the last _device U/J / SFS pair kernel
   // device-built leaf lists (vpm_leaflists_build), resident on device 0
   int64_t tree_np = -1, tree_nl = 0, tree_npairs = 0;
+  unsigned long long tree_fingerprint = 0;  // of the X and sigma rows the lists were built from
   // single-process multi-GPU (n_gpus > 1): NCCL communicators, one per device
   void *nccl_lib = nullptr;
   std::vector<void *> comms;

@@ -213,6 +213,17 @@ TreeView tree_view(vpm_handle *h) {
   return v;
 }
 
+// fingerprint of X and sigma of a device copy of the rows (compact 7-row layout: ld = 7, sigma at 6)
+int tree_fingerprint(vpm_handle *h, Dev &d, const double *d_P, int64_t ld, int osig, int64_t np, unsigned long long *out) {
+  TRY(ensure(h, d.cubtmp, 256));
+  unsigned long long *acc = (unsigned long long *)d.cubtmp.p + 8;  // (the first words serve the near-fraction sample)
+  CK(h, cudaMemsetAsync(acc, 0, sizeof *acc, d.stream));
+  tree_fingerprint_kernel<<<blocks_for(np, 256), 256, 0, d.stream>>>(d_P, ld, 0, osig, np, acc);
+  CK(h, cudaMemcpyAsync(out, acc, sizeof *out, cudaMemcpyDeviceToHost, d.stream));
+  CK(h, cudaStreamSynchronize(d.stream));
+  return VPM_OK;
+}
+
 int tree_build(vpm_handle *h, const double *d_P, int64_t ld, int osig, int64_t np, int64_t ncrit, double theta) {
   const char *fn = "vpm_leaflists_build";
   Dev &d = h->devs[0];
@@ -343,6 +354,7 @@ int tree_build(vpm_handle *h, const double *d_P, int64_t ld, int osig, int64_t n
   h->launches++;
   CK(h, cudaStreamSynchronize(st));
   CK(h, cudaGetLastError());
+  TRY(tree_fingerprint(h, d, d_P, ld, osig, np, &h->tree_fingerprint));
   h->tree_np = np; h->tree_nl = nl; h->tree_npairs = npairs;
   return VPM_OK;
 }

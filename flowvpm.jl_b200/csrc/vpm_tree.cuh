@@ -238,6 +238,27 @@ __global__ void tree_scatter_kernel(const double *__restrict__ tgt16, const int6
   }
 }
 
+// Order-independent 64-bit fingerprint of the rows the leaf lists depend on (X and sigma of every particle):
+// the lists stay valid only while these do not change.  out[0] += mix(x, y, z, sigma, i) over all particles.
+__global__ void tree_fingerprint_kernel(const double *__restrict__ P, int64_t ld, int ox, int osig, int64_t n,
+                                        unsigned long long *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v = 0;
+  if (i < n) {
+    const double *p = P + i * ld;
+    auto bits = [](double x) { return (unsigned long long)__double_as_longlong(x); };
+    auto rot = [](unsigned long long x, int k) { return (x << k) | (x >> (64 - k)); };
+    unsigned long long x = bits(p[ox]) ^ rot(bits(p[ox + 1]), 13) ^ rot(bits(p[ox + 2]), 29) ^ rot(bits(p[osig]), 47);
+    x += 0x9e3779b97f4a7c15ull * (unsigned long long)(i + 1);
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    v = x ^ (x >> 31);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
 __global__ void tree_fill_i32_kernel(int32_t *p, int64_t n, int32_t v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

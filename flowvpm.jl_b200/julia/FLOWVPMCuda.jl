@@ -294,6 +294,10 @@ function nearfield_fp32!(on::Bool=true)
     check(ccall((:vpm_set_option, lib[]), Cint, (Ptr{Cvoid}, Cint, Cint), handle[], Cint(1), Cint(on)))
 end
 
+"""
+The lists built by `leaflists_cuda!` are valid for one particle configuration: after positions or core sizes
+change (every RK substep) call `leaflists_cuda!` again; the library checks a fingerprint and errors otherwise.
+"""
 function UJ_nearfield_cuda!(pfield::vpm.ParticleField{Float64}; reset::Bool=true)
     P = pfield.particles
     GC.@preserve P check(ccall((:vpm_uj_nearfield, lib[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Cint, Cint),

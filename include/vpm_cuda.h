@@ -209,7 +209,10 @@ int vpm_leaflists_get(vpm_handle *h, int64_t *sort_index, int64_t *leaf_begin, i
 /* near-field half of UJ_fmm (src/FLOWVPM_UJ.jl:62-129) over the resident lists, entirely on the
  * device(s): rows 10:12 and 16:24 of every particle receive the sum over the sources of its
  * near-field leaves (RESET: _reset_particles first; otherwise added to what is there, e.g. a
- * far field evaluated by the host).  Flags: VPM_FLAG_RESET, VPM_FLAG_NO_FARFIELD_SHORTCUT. */
+ * far field evaluated by the host).  Flags: VPM_FLAG_RESET, VPM_FLAG_NO_FARFIELD_SHORTCUT.
+ * The lists are valid for ONE particle configuration: the call compares a fingerprint of the X and sigma
+ * rows it uploads with the one taken by vpm_leaflists_build and returns VPM_ESTATE when they differ
+ * (strengths may change freely; after particles have moved, rebuild -- 23 ms at 2^24 on 8 GPUs). */
 int vpm_uj_nearfield(vpm_handle *h, double *particles, int64_t nfields, int64_t np, int kernel_id, int flags);
 
 /* ---- second P2P of the reference: the basis-function (vorticity) sum -------- */
@@ -293,7 +296,11 @@ int vpm_field_tsgm(vpm_handle *h, double *t_sgm, int set);
  * `stream`).  They use scratch buffers of the handle; the library records an event after the last
  * kernel and makes the next user of that scratch -- another _device call on ANY stream, or any of
  * the synchronous entry points -- wait on it, so calls may be issued on different streams without
- * a synchronisation in between.  Outputs are valid once `stream` has reached this call's kernels. */
+ * a synchronisation in between.  Outputs are valid once `stream` has reached this call's kernels.
+ * Exception: with the gaussian / gaussianerf kernels on fields large enough for the table kernel
+ * (VPM_OPT_UJ_TABLE = 0, >= ~12 500 targets) vpm_uj_device synchronises `stream` once to read the 4-byte
+ * sample its kernel choice depends on -- set VPM_OPT_UJ_TABLE to 1 or 2 to keep it fully asynchronous
+ * (e.g. inside a stream capture). */
 int vpm_uj_device(vpm_handle *h, const double *d_src8, int64_t ns, int64_t t0, int64_t t1,
                   double *d_out12, int kernel_id, int flags, void *stream);
 /* SFS sweep for targets [t0,t1): d_J9 is 9 x ns (final J of every particle),

@@ -159,3 +159,21 @@ def test_c5_nearfield_2p24_slice_parity(vpm, handle):
         worst = max(worst, relerr(got[0:3], tb[4:7]), relerr(got[3:12], tb[7:16]))
     assert worst < TOL_FP64, worst
     assert np.all(np.isfinite(pf.particles[9:24, :n]))
+
+
+def test_nearfield_refuses_stale_lists(vpm, handle):
+    """the resident lists are functions of X and sigma at build time: moving a particle (or changing a core size)
+    without rebuilding must fail loudly, not drop near pairs silently; strengths may change freely"""
+    pf = vpm.fields.cloud_field(3000, kernel=vpm.winckelmans, seed=8)
+    vpm.leaf_lists(pf, ncrit=32, theta=0.4, fetch=False)
+    vpm.UJ_nearfield(pf, reset=True)
+    pf.particles[3:6, :pf.np] *= 2.0                    # strengths: fine
+    vpm.UJ_nearfield(pf, reset=True)
+    pf.particles[0, 17] += 1e-9                         # one particle moved by 1e-9
+    with pytest.raises(vpm.VpmError, match="changed since vpm_leaflists_build"):
+        vpm.UJ_nearfield(pf, reset=True)
+    vpm.leaf_lists(pf, ncrit=32, theta=0.4, fetch=False)
+    vpm.UJ_nearfield(pf, reset=True)
+    pf.particles[6, 5] *= 1.0000001
+    with pytest.raises(vpm.VpmError):
+        vpm.UJ_nearfield(pf, reset=True)
