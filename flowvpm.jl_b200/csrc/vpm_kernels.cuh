@@ -358,7 +358,10 @@ __device__ __forceinline__ void uj_tile(const double2 *__restrict__ tile, int n,
       for (int t = 0; t < T; ++t) {
         double b = fma(dz[t], dz[t], fma(dy[t], dy[t], fma(dx[t], dx[t], q0)));
         ab_winck(b, q1, q2, A[t], B[t]);
-        // r2 == 0 <=> dx == dy == dz == 0 (differences of equal numbers are +0)
+        // r2 == 0 <=> dx == dy == dz == 0.  All six words are ORed and the result shifted left by one: that
+        // drops the SIGN bit of the high words (x - x can be -0 when the inputs are zeros of opposite sign)
+        // and, as a side effect, bit 31 of the low words -- a difference that has only that bit set is
+        // ~1e-314, whose square underflows to r2 == 0 in the reference as well, so the skip rule agrees.
         bool z = ((__double2hiint(dx[t]) | __double2loint(dx[t]) | __double2hiint(dy[t]) |
                    __double2loint(dy[t]) | __double2hiint(dz[t]) | __double2loint(dz[t])) << 1) == 0;
         A[t] = select_zero(z, A[t]);

@@ -78,8 +78,13 @@ template <int K, int NT, int TILE>
 __global__ void __launch_bounds__(NT) uj_leaf_kernel(const LeafUjArgs a) {
   __shared__ __align__(128) double tiles[kStages][TILE * kRec];
   __shared__ __align__(8) uint64_t full[kStages];
-  __shared__ __align__(16) double2 gtab[K == K_GERF ? kGerfIntervals * kGerfCoeffs / 2 : 1];
-  if constexpr (K == K_GERF) load_gerf_table(gtab);  // visible after the __syncthreads below
+  // gaussianerf: the 13 KB G(u) table is staged in shared memory only by CTAs wide enough to amortise the
+  // copy; a one- or two-warp CTA of a small leaf reads it through L1 instead (its whole work item is a few
+  // thousand pairs: the copy alone cost a third of the kernel at ncrit 24: 101 -> 139 G pairs/s)
+  constexpr bool kTabInSmem = K == K_GERF && NT >= 128;
+  __shared__ __align__(16) double2 gtab_s[kTabInSmem ? kGerfIntervals * kGerfCoeffs / 2 : 1];
+  if constexpr (kTabInSmem) load_gerf_table(gtab_s);  // visible after the __syncthreads below
+  const double2 *gtab = kTabInSmem ? gtab_s : reinterpret_cast<const double2 *>(kGerfTable);
   const int tid = threadIdx.x;
   const int leaf = a.csr.wi_leaf[blockIdx.x];
   const int64_t tb = a.csr.tleaf_begin[leaf] + a.csr.wi_off[blockIdx.x];
