@@ -361,7 +361,7 @@ int tree_build(vpm_handle *h, const double *d_P, int64_t ld, int osig, int64_t n
 
 template <int K>
 void launch_uj_leaf_K(int nt, unsigned nwi, const LeafUjArgs &a, cudaStream_t st) {
-  if (nt == 32) uj_leaf_kernel<K, 32, 64><<<nwi, 32, 0, st>>>(a);
+  if (nt == 32) uj_leaf1w_kernel<K, 64><<<nwi, 32, 0, st>>>(a);
   else if (nt == 64) uj_leaf_kernel<K, 64, 64><<<nwi, 64, 0, st>>>(a);
   else uj_leaf_kernel<K, 128, 128><<<nwi, 128, 0, st>>>(a);
 }
