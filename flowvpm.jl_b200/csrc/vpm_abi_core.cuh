@@ -71,6 +71,10 @@ int vpm_destroy(vpm_handle *h) {
       if (b->p) cudaFree(b->p);
     for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
     if (d.scratch_ev) cudaEventDestroy(d.scratch_ev);
+    for (int b = 0; b < 2; ++b) {
+      if (d.ring[b]) cudaFreeHost(d.ring[b]);
+      if (d.ring_ev[b]) cudaEventDestroy(d.ring_ev[b]);
+    }
     if (d.stream) cudaStreamDestroy(d.stream);
   }
   if (h->h_stat) cudaFreeHost(h->h_stat);
@@ -281,8 +285,7 @@ int vpm_uj_direct_f32(vpm_handle *h, float *P, int64_t nf, int64_t np, int kerne
   has_static = any_static(P, nf, np);
   const bool prior = !reset || has_static;
   if (np > 0) {
-    CK(h, cudaMemcpy2DAsync(f_in7, 7 * sizeof(float), P, nf * sizeof(float), 7 * sizeof(float), (size_t)np,
-                            cudaMemcpyHostToDevice, st));
+    TRY(h2d_strided(h, st, f_in7, 7 * sizeof(float), P, nf * sizeof(float), 7 * sizeof(float), np));
     cvt_f32_to_f64_kernel<<<blocks_for(np * 7, 256), 256, 0, st>>>(f_in7, (double *)d.in7.p, np * 7);
     h->launches++;
     if (has_static) {
@@ -297,14 +300,12 @@ int vpm_uj_direct_f32(vpm_handle *h, float *P, int64_t nf, int64_t np, int kerne
       CK(h, cudaMemcpyAsync(d.stat.p, h->h_stat, (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
     }
     if (prior) {
-      CK(h, cudaMemcpy2DAsync(f_res, RES_ROWS * sizeof(float), P + R_U, nf * sizeof(float),
-                              RES_ROWS * sizeof(float), (size_t)np, cudaMemcpyHostToDevice, st));
+      TRY(h2d_strided(h, st, f_res, RES_ROWS * sizeof(float), P + R_U, nf * sizeof(float), RES_ROWS * sizeof(float), np));
       cvt_f32_to_f64_kernel<<<blocks_for(np * RES_ROWS, 256), 256, 0, st>>>(f_res, (double *)d.res18.p, np * RES_ROWS);
       h->launches++;
     }
     if (sfs_rows) {
-      CK(h, cudaMemcpy2DAsync(f_sfs, 3 * sizeof(float), P + R_SFS, nf * sizeof(float), 3 * sizeof(float),
-                              (size_t)np, cudaMemcpyHostToDevice, st));
+      TRY(h2d_strided(h, st, f_sfs, 3 * sizeof(float), P + R_SFS, nf * sizeof(float), 3 * sizeof(float), np));
       cvt_f32_to_f64_kernel<<<blocks_for(np * 3, 256), 256, 0, st>>>(f_sfs, (double *)d.sfs3.p, np * 3);
       h->launches++;
     }
@@ -314,13 +315,11 @@ int vpm_uj_direct_f32(vpm_handle *h, float *P, int64_t nf, int64_t np, int kerne
   if (np > 0) {
     cvt_f64_to_f32_kernel<<<blocks_for(np * RES_ROWS, 256), 256, 0, st>>>((const double *)d.res18.p, f_res, np * RES_ROWS);
     h->launches++;
-    CK(h, cudaMemcpy2DAsync(P + R_U, nf * sizeof(float), f_res, RES_ROWS * sizeof(float),
-                            RES_ROWS * sizeof(float), (size_t)np, cudaMemcpyDeviceToHost, st));
+    TRY(d2h_strided(h, st, P + R_U, nf * sizeof(float), f_res, RES_ROWS * sizeof(float), RES_ROWS * sizeof(float), np));
     if (sfs_rows) {
       cvt_f64_to_f32_kernel<<<blocks_for(np * 3, 256), 256, 0, st>>>((const double *)d.sfs3.p, f_sfs, np * 3);
       h->launches++;
-      CK(h, cudaMemcpy2DAsync(P + R_SFS, nf * sizeof(float), f_sfs, 3 * sizeof(float), 3 * sizeof(float),
-                              (size_t)np, cudaMemcpyDeviceToHost, st));
+      TRY(d2h_strided(h, st, P + R_SFS, nf * sizeof(float), f_sfs, 3 * sizeof(float), 3 * sizeof(float), np));
     }
     CK(h, cudaGetLastError());
   }
@@ -398,8 +397,7 @@ int vpm_uj_direct_st(vpm_handle *h, const double *S, int64_t nfs, int64_t nps, d
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(d.ev[3], st));
   CK(h, cudaEventRecord(d.ev[4], st));
-  CK(h, cudaMemcpy2DAsync(Tg + R_U, nft * sizeof(double), d.res18.p, RES_ROWS * sizeof(double),
-                          RES_ROWS * sizeof(double), (size_t)npt, cudaMemcpyDeviceToHost, st));
+  TRY(d2h_rows(h, st, Tg + R_U, nft, (const double *)d.res18.p, RES_ROWS, npt));
   CK(h, cudaEventRecord(d.ev[5], st));
   CK(h, cudaStreamSynchronize(st));
   h->timing.uj_pairs = nps * npt;

@@ -206,10 +206,9 @@ int vpm_nearfield_ranges(vpm_handle *h, double *TP, int64_t nf_t, int64_t np_t, 
     const int64_t col1 = G == 1 ? np_t : std::min<int64_t>(te[ll], tb[ll] + c.last_off[g + 1] + c.nt);
     const size_t ncol = (size_t)(col1 - col0);
     double *dt = (double *)d.tbuf.p + col0 * TLD;
-    CK(h, cudaMemcpy2DAsync(dt, TLD * sizeof(double), TP + col0 * nf_t + R_X, nf_t * sizeof(double), 3 * sizeof(double),
-                            ncol, cudaMemcpyHostToDevice, st));
-    CK(h, cudaMemcpy2DAsync(dt + 3, TLD * sizeof(double), TP + col0 * nf_t + R_U, nf_t * sizeof(double), 15 * sizeof(double),
-                            ncol, cudaMemcpyHostToDevice, st));
+    const RowPiece pieces[2] = {{R_X * sizeof(double), 0, 3 * sizeof(double)},
+                                {R_U * sizeof(double), 3 * sizeof(double), 15 * sizeof(double)}};
+    TRY(h2d_pieces(h, st, dt, TLD * sizeof(double), TP + col0 * nf_t, nf_t * sizeof(double), pieces, 2, ncol));
     LeafUjArgs a;
     a.csr = csr[g];
     a.csr.wi_leaf += k0;
@@ -237,8 +236,8 @@ int vpm_nearfield_ranges(vpm_handle *h, double *TP, int64_t nf_t, int64_t np_t, 
     CK(h, cudaSetDevice(d.id));
     const int64_t col0 = cols[g].first;
     const size_t ncol = (size_t)(cols[g].second - col0);
-    CK(h, cudaMemcpy2DAsync(TP + col0 * nf_t + R_U, nf_t * sizeof(double), (double *)d.tbuf.p + col0 * TLD + 3,
-                            TLD * sizeof(double), 15 * sizeof(double), ncol, cudaMemcpyDeviceToHost, d.stream));
+    TRY(d2h_strided(h, d.stream, TP + col0 * nf_t + R_U, nf_t * sizeof(double), (double *)d.tbuf.p + col0 * TLD + 3,
+                    TLD * sizeof(double), 15 * sizeof(double), ncol));
     if (g == 0) CK(h, cudaEventRecord(d.ev[5], d.stream));
   }
   for (int g = G - 1; g >= 0; --g) {
@@ -361,8 +360,7 @@ static int leafpairs_field(vpm_handle *h, const char *fn, int mode, double *P, i
   }
   CK(h, cudaSetDevice(d.id));
   CK(h, cudaEventRecord(d.ev[4], st));
-  CK(h, cudaMemcpy2DAsync(P + out_row, nf * sizeof(double), d.sfs3.p, 3 * sizeof(double), 3 * sizeof(double),
-                          (size_t)np, cudaMemcpyDeviceToHost, st));
+  TRY(d2h_rows(h, st, P + out_row, nf, (const double *)d.sfs3.p, 3, np));
   CK(h, cudaEventRecord(d.ev[5], st));
   for (int g = G - 1; g >= 0; --g) {
     CK(h, cudaSetDevice(h->devs[g].id));
@@ -423,8 +421,7 @@ int vpm_zeta_direct(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
   h->launches++;
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(d.ev[4], st));
-  CK(h, cudaMemcpy2DAsync(P + R_J, nf * sizeof(double), d.sfs3.p, 3 * sizeof(double), 3 * sizeof(double),
-                          (size_t)np, cudaMemcpyDeviceToHost, st));
+  TRY(d2h_rows(h, st, P + R_J, nf, (const double *)d.sfs3.p, 3, np));
   CK(h, cudaEventRecord(d.ev[5], st));
   CK(h, cudaStreamSynchronize(st));
   h->timing.uj_pairs = 0;

@@ -28,6 +28,12 @@ struct Dev {
   cudaEvent_t scratch_ev = nullptr;
   bool scratch_pending = false;
   Buf in7, stat, res18, sfs3, rec, srec, partial, tbuf, sbuf, ibuf, jbuf, fld, scr, scr2, cubtmp, tree, tlist;
+  // two pinned slots through which the strided rows of a PAGEABLE host matrix travel (h2d_strided /
+  // d2h_strided in vpm_host_hook1.cuh); allocated on first use
+  char *ring[2] = {nullptr, nullptr};
+  cudaEvent_t ring_ev[2] = {};
+  bool ring_busy[2] = {false, false};
+  int ring_next = 0;
 };
 
 struct Plan {

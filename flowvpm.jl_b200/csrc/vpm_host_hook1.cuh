@@ -68,15 +68,151 @@ bool any_static(const R *P, int64_t nf, int64_t np) {
   return found.load();
 }
 
-// Strided rows [row.., row+nrows) of `np` columns of a host matrix (leading dimension nf)
-// -> compact device block: a 2-D DMA.  (Measured alternative: page-locking the matrix as
-// mapped memory and gathering the rows with a kernel reading host memory directly gave the
-// same 13.8 GB/s for the 56-byte rows at N = 2^22, so the plain copy stays.)
-int h2d_rows(vpm_handle *h, cudaStream_t st, double *dst, const double *src, int64_t nf, int nrows, int64_t np) {
-  if (np <= 0) return VPM_OK;
-  CK(h, cudaMemcpy2DAsync(dst, nrows * sizeof(double), src, nf * sizeof(double), nrows * sizeof(double), (size_t)np,
-                          cudaMemcpyHostToDevice, st));
+// Strided rows of `n` columns of a host matrix <-> device block, for every entry point other than Hook 1
+// (which stages whole fields through h_stage, above).
+//  * page-locked matrix (vpm_pin_host, or the caller's own pinned allocation): a 2-D DMA.  (Measured
+//    alternative: mapping the matrix and gathering the rows with a kernel reading host memory directly
+//    gave the same 13.8 GB/s for the 56-byte rows at N = 2^22, so the plain copy stays.)
+//  * pageable matrix: the driver stages such a 2-D copy row by row (measured 0.7 GB/s: zeta_fmm on 2^20
+//    particles spent 0.5 s uploading and 11 ms computing).  The rows go through a ring of two pinned
+//    slots per device instead: host threads gather a slot while the DMA of the other one runs.
+constexpr size_t kRingSlot = 16u << 20;
+constexpr size_t kRingMinBytes = 256u << 10;  // smaller copies: the 2-D copy costs no more than the ring's bookkeeping
+
+Dev *dev_of_stream(vpm_handle *h, cudaStream_t st) {
+  for (Dev &d : h->devs)
+    if (d.stream == st) return &d;
+  return nullptr;
+}
+int ring_ready(vpm_handle *h, Dev &d) {
+  if (d.ring[0]) return VPM_OK;
+  CK(h, cudaSetDevice(d.id));
+  for (int b = 0; b < 2; ++b) {
+    CK(h, cudaEventCreateWithFlags(&d.ring_ev[b], cudaEventDisableTiming));
+    CK(h, cudaMallocHost((void **)&d.ring[b], kRingSlot));
+  }
   return VPM_OK;
+}
+bool use_ring(vpm_handle *h, Dev *d, const void *host, size_t bytes) {
+  return d && !h->capturing && bytes >= kRingMinBytes && !host_is_pinned(host);
+}
+template <class F>
+void parallel_cols(int64_t n, F fn) {  // as parallel_chunks, finer grain (a ring slot is ~1e5 columns)
+  const int64_t min_chunk = 1 << 14;
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, 8), n / min_chunk);
+  if (nt <= 1) { fn((int64_t)0, n); return; }
+  std::vector<std::thread> th;
+  const int64_t chunk = (n + nt - 1) / nt;
+  for (int t = 1; t < nt; ++t) th.emplace_back([=] { fn(t * chunk, std::min<int64_t>(n, (t + 1) * chunk)); });
+  fn((int64_t)0, std::min<int64_t>(n, chunk));
+  for (auto &t : th) t.join();
+}
+
+// Device columns of `dpitch` bytes <- pieces of the host columns (pitch spitch): piece k is `width[k]` bytes
+// from byte offset soff[k] of the host column to byte offset doff[k] of the device column.  The ring path
+// needs the pieces to tile the device column (then a slot is a run of whole device columns and ONE
+// contiguous copy moves it -- measured: a 2-D copy of 3e5 56-byte rows out of a pinned slot ran at
+// 1.5 GB/s, the 1-D copy of the same bytes at PCIe rate: 106 -> 10 ms for the 19 rows of 2^20 particles).
+struct RowPiece { size_t soff, doff, width; };
+int h2d_pieces(vpm_handle *h, cudaStream_t st, void *dst, size_t dpitch, const void *src, size_t spitch,
+               const RowPiece *pc, int npc, int64_t n) {
+  if (n <= 0) return VPM_OK;
+  Dev *d = dev_of_stream(h, st);
+  size_t covered = 0;
+  bool tiles = true;
+  for (int k = 0; k < npc; ++k) {
+    tiles = tiles && pc[k].doff == covered;
+    covered += pc[k].width;
+  }
+  tiles = tiles && covered == dpitch;
+  if (!tiles || !use_ring(h, d, src, dpitch * (size_t)n)) {
+    for (int k = 0; k < npc; ++k)
+      CK(h, cudaMemcpy2DAsync((char *)dst + pc[k].doff, dpitch, (const char *)src + pc[k].soff, spitch, pc[k].width,
+                              (size_t)n, cudaMemcpyHostToDevice, st));
+    return VPM_OK;
+  }
+  TRY(ring_ready(h, *d));
+  const int64_t cols = (int64_t)(kRingSlot / dpitch);
+  RowPiece p[4];
+  if (npc > 4) return fail(h, VPM_EINVAL, "h2d_pieces: more than 4 pieces");
+  for (int k = 0; k < npc; ++k) p[k] = pc[k];
+  for (int64_t c0 = 0; c0 < n; c0 += cols) {
+    const int64_t nc = std::min(cols, n - c0);
+    const int b = d->ring_next;
+    d->ring_next ^= 1;
+    if (d->ring_busy[b]) CK(h, cudaEventSynchronize(d->ring_ev[b]));  // the DMA that last read this slot
+    char *slot = d->ring[b];
+    const char *s0 = (const char *)src + (size_t)c0 * spitch;
+    const RowPiece p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3];
+    parallel_cols(nc, [=](int64_t a, int64_t e) {
+      const RowPiece q[4] = {p0, p1, p2, p3};
+      for (int64_t i = a; i < e; ++i)
+        for (int k = 0; k < npc; ++k)
+          memcpy(slot + (size_t)i * dpitch + q[k].doff, s0 + (size_t)i * spitch + q[k].soff, q[k].width);
+    });
+    CK(h, cudaMemcpyAsync((char *)dst + (size_t)c0 * dpitch, slot, (size_t)nc * dpitch, cudaMemcpyHostToDevice, st));
+    CK(h, cudaEventRecord(d->ring_ev[b], st));
+    d->ring_busy[b] = true;
+  }
+  return VPM_OK;
+}
+int h2d_strided(vpm_handle *h, cudaStream_t st, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width,
+                int64_t n) {
+  const RowPiece p{0, 0, width};
+  return h2d_pieces(h, st, dst, dpitch, src, spitch, &p, 1, n);
+}
+
+// host columns (pitch dpitch) <- `width` bytes of each of n device columns (pitch spitch).  For a pageable
+// destination the call returns with the data in place (the scatter is host work); otherwise it is
+// asynchronous on `st` like the 2-D copy it wraps.  The ring path moves WHOLE device columns (one
+// contiguous copy per slot, see h2d_pieces) and scatters the `width` bytes it was asked for: meant for
+// spitch not much larger than width (the callers: equal, or 144 against 120 bytes).
+int d2h_strided(vpm_handle *h, cudaStream_t st, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width,
+                int64_t n) {
+  if (n <= 0) return VPM_OK;
+  Dev *d = dev_of_stream(h, st);
+  if (spitch > 2 * width || !use_ring(h, d, dst, width * (size_t)n)) {
+    CK(h, cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, (size_t)n, cudaMemcpyDeviceToHost, st));
+    return VPM_OK;
+  }
+  TRY(ring_ready(h, *d));
+  const int64_t cols = (int64_t)(kRingSlot / spitch);
+  int pb = -1;
+  int64_t pc0 = 0, pnc = 0;
+  auto scatter_prev = [&]() -> int {
+    if (pb < 0) return VPM_OK;
+    CK(h, cudaEventSynchronize(d->ring_ev[pb]));
+    d->ring_busy[pb] = false;
+    const char *slot = d->ring[pb];
+    char *d0 = (char *)dst + (size_t)pc0 * dpitch;
+    parallel_cols(pnc, [=](int64_t a, int64_t e) {
+      for (int64_t i = a; i < e; ++i) memcpy(d0 + (size_t)i * dpitch, slot + (size_t)i * spitch, width);
+    });
+    return VPM_OK;
+  };
+  for (int64_t c0 = 0; c0 < n; c0 += cols) {
+    const int64_t nc = std::min(cols, n - c0);
+    const int b = d->ring_next;
+    d->ring_next ^= 1;
+    if (d->ring_busy[b]) CK(h, cudaEventSynchronize(d->ring_ev[b]));
+    // the last column contributes only its `width` bytes (the device block may end there)
+    CK(h, cudaMemcpyAsync(d->ring[b], (const char *)src + (size_t)c0 * spitch, (size_t)(nc - 1) * spitch + width,
+                          cudaMemcpyDeviceToHost, st));
+    CK(h, cudaEventRecord(d->ring_ev[b], st));
+    d->ring_busy[b] = true;
+    TRY(scatter_prev());  // overlaps the copy just issued
+    pb = b; pc0 = c0; pnc = nc;
+  }
+  return scatter_prev();
+}
+
+// rows [row.., row+nrows) of `np` columns of a host matrix (leading dimension nf) <-> compact device block
+int h2d_rows(vpm_handle *h, cudaStream_t st, double *dst, const double *src, int64_t nf, int nrows, int64_t np) {
+  return h2d_strided(h, st, dst, nrows * sizeof(double), src, nf * sizeof(double), nrows * sizeof(double), np);
+}
+int d2h_rows(vpm_handle *h, cudaStream_t st, double *dst, int64_t nf, const double *src, int nrows, int64_t np) {
+  return d2h_strided(h, st, dst, nf * sizeof(double), src, nrows * sizeof(double), nrows * sizeof(double), np);
 }
 
 // ---- Hook 1 pieces (single device d; targets = all particles) ---------------

@@ -32,8 +32,8 @@ constexpr int kStages = 2;
 
 // far-field cutoffs in u = (r/sigma)^2 beyond which g == 1 and dg == 0 to
 // < 2e-16 relative (gaussianerf: s >= 9; gaussian: s >= 3.45, s^3 >= 41)
-__device__ constexpr double kFarU_gerf = 81.0;
-__device__ constexpr double kFarU_gaus = 11.9025;
+constexpr double kFarU_gerf = 81.0;
+constexpr double kFarU_gaus = 11.9025;
 // SFS: zeta below 1e-26 of zeta(0) (gaussianerf u >= 120; gaussian s^3 >= 60)
 __device__ constexpr double kSfsFarU_gerf = 120.0;
 __device__ constexpr double kSfsFarU_gaus = 15.4;

@@ -23,46 +23,12 @@ struct LeafCsr {
   const int64_t *sleaf_end;
 };
 
-// Walks the source bodies of one target leaf tile by tile.  A tile is filled with up to `tile`
-// bodies taken in list order and may span several source leaves (small leaves -- ncrit ~ 64 means
-// ~30 bodies -- would otherwise make tiles of a quarter of their capacity, each paying a
-// barrier round trip and an exposed TMA latency).  seg(first, n, filled) is called for every
-// contiguous piece; the producer issues one bulk copy per piece, the consumers only need the
-// total.  The per-target summation order is the list order either way.
-struct LeafTileIter {
-  int64_t li, le;    // position / end in csr_src
-  int64_t cur, end;  // remaining sorted-body range of the current source leaf
-  __device__ __forceinline__ void init(const LeafCsr &c, int leaf) {
-    li = c.csr_ptr[leaf];
-    le = c.csr_ptr[leaf + 1];
-    cur = end = 0;
-  }
-  template <class F>
-  __device__ __forceinline__ int next(const LeafCsr &c, int tile, F seg) {
-    int filled = 0;
-    while (filled < tile) {
-      while (cur >= end) {
-        if (li >= le) return filled;
-        const int s = c.csr_src[li++];
-        cur = c.sleaf_begin[s];
-        end = c.sleaf_end[s];
-      }
-      int64_t n = end - cur;
-      if (n > tile - filled) n = tile - filled;
-      seg(cur, (int)n, filled);
-      cur += n;
-      filled += (int)n;
-    }
-    return filled;
-  }
-  __device__ __forceinline__ int next(const LeafCsr &c, int tile) {
-    return next(c, tile, [](int64_t, int, int) {});
-  }
-};
-
-// Warp-cooperative tile producer (round 2).  LeafTileIter walks the source-leaf list piece by piece with
-// three dependent global loads per piece, on one thread, and every consumer thread repeats the walk to
-// learn the tile sizes: for CPU-style trees (ncrit 10..50: a 64-record tile is ~5 leaves) that serial
+// Warp-cooperative tile producer.  A tile is filled with up to TILE bodies taken in list order and may span
+// several source leaves (small leaves -- ncrit ~ 64 means ~30 bodies -- would otherwise make tiles of a
+// quarter of their capacity, each paying a barrier round trip and an exposed TMA latency); the per-target
+// summation order is the list order either way.  Round 1 walked the list piece by piece with three
+// dependent global loads per piece, on one thread, and every consumer thread repeated the walk to learn
+// the tile sizes: for CPU-style trees (ncrit 10..50: a 64-record tile is ~5 leaves) that serial
 // latency was as long as the arithmetic of the tile.  Here the 32 lanes of warp 0 each load ONE piece of
 // the list (csr_src -> leaf range), a warp scan places the pieces in the tile, lane 0 announces the bytes
 // of the step on the barrier (mbarrier.expect_tx, no arrival), every lane issues the bulk copy of its own
@@ -355,6 +321,7 @@ template <int K, int NT, int TILE, int MODE = MODE_SFS>
 __global__ void __launch_bounds__(NT) sfs_leaf_kernel(const LeafSfsArgs a) {
   __shared__ __align__(128) double tiles[kStages][TILE * kSfsRec];
   __shared__ __align__(8) uint64_t full[kStages];
+  __shared__ int tile_n[kStages];  // records in each stage's tile, published by the producer
   const int tid = threadIdx.x;
   const int leaf = a.csr.wi_leaf[blockIdx.x];
   const int64_t tb = a.csr.tleaf_begin[leaf] + a.csr.wi_off[blockIdx.x];
@@ -390,35 +357,21 @@ __global__ void __launch_bounds__(NT) sfs_leaf_kernel(const LeafSfsArgs a) {
   }
   __syncthreads();
 
-  LeafTileIter prod, cons;
+  LeafTileProducer prod;  // state lives (uniformly) in the lanes of warp 0
   prod.init(a.csr, leaf);
-  cons.init(a.csr, leaf);
-  int issued = 0;
-  auto issue = [&]() {
-    LeafTileIter dry = prod;
-    const int n = dry.next(a.csr, TILE);
-    if (n == 0) return;
-    const int st = issued % kStages;
-    mbar_expect_tx(&full[st], (uint32_t)n * kSfsRec * sizeof(double));
-    prod.next(a.csr, TILE, [&](int64_t first, int cnt, int filled) {
-      tma_bulk_g2s(&tiles[st][filled * kSfsRec], a.rec + first * kSfsRec, (uint32_t)cnt * kSfsRec * sizeof(double),
-                   &full[st]);
-    });
-    ++issued;
-  };
-  if (tid == 0)
-    for (int s = 0; s < kStages; ++s) issue();
+  if (tid < 32)
+    for (int s = 0; s < kStages; ++s) prod.issue<TILE, kSfsRec>(a.csr, a.rec, &tiles[s][0], &full[s], &tile_n[s]);
 
   for (int it = 0;; ++it) {
-    const int n = cons.next(a.csr, TILE);
-    if (n == 0) break;
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
+    const int n = tile_n[st];
+    if (n == 0) break;  // list exhausted (the same value for every thread of the CTA)
     const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
     if (nsplit == 1) sfs_tile<K, 1, MODE>(tile, n, tx, ty, tz, JT, acc, a.shortcut);
     else sfs_tile<K, 1, MODE, true>(tile, n, tx, ty, tz, JT, acc, a.shortcut, nsplit, phase);
     __syncthreads();
-    if (tid == 0) issue();
+    if (tid < 32) prod.issue<TILE, kSfsRec>(a.csr, a.rec, &tiles[st][0], &full[st], &tile_n[st]);
   }
   for (int o = glanes; o < 32; o <<= 1) {
 #pragma unroll

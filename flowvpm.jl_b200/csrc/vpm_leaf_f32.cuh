@@ -143,6 +143,7 @@ template <int K, int NT, int TILE>
 __global__ void __launch_bounds__(NT) uj_leaf_kernel_f32(const LeafUjArgsF a) {
   __shared__ __align__(128) float tiles[kStages][TILE * kRecFS];
   __shared__ __align__(8) uint64_t full[kStages];
+  __shared__ int tile_n[kStages];  // records in each stage's tile, published by the producer
   __shared__ __align__(16) float gtab[K == K_GERF ? kGerfIntervalsF * kGerfCoeffsF : 1];
   const int tid = threadIdx.x;
   if constexpr (K == K_GERF) {
@@ -173,30 +174,20 @@ __global__ void __launch_bounds__(NT) uj_leaf_kernel_f32(const LeafUjArgsF a) {
   }
   __syncthreads();
 
-  LeafTileIter prod, cons;
+  // 64-byte records = 8 doubles for the (byte-counting) producer of vpm_leaf.cuh
+  constexpr int kRecD = kRecFS * (int)sizeof(float) / (int)sizeof(double);
+  const double *recd = reinterpret_cast<const double *>(a.rec);
+  LeafTileProducer prod;  // state lives (uniformly) in the lanes of warp 0
   prod.init(a.csr, leaf);
-  cons.init(a.csr, leaf);
-  int issued = 0;
-  auto issue = [&]() {
-    LeafTileIter dry = prod;
-    const int n = dry.next(a.csr, TILE);
-    if (n == 0) return;
-    const int st = issued % kStages;
-    mbar_expect_tx(&full[st], (uint32_t)n * kRecFS * sizeof(float));
-    prod.next(a.csr, TILE, [&](int64_t first, int cnt, int filled) {
-      tma_bulk_g2s(&tiles[st][filled * kRecFS], a.rec + first * kRecFS, (uint32_t)cnt * kRecFS * sizeof(float),
-                   &full[st]);
-    });
-    ++issued;
-  };
-  if (tid == 0)
-    for (int s = 0; s < kStages; ++s) issue();
+  if (tid < 32)
+    for (int s = 0; s < kStages; ++s)
+      prod.issue<TILE, kRecD>(a.csr, recd, reinterpret_cast<double *>(&tiles[s][0]), &full[s], &tile_n[s]);
 
   for (int it = 0;; ++it) {
-    const int n = cons.next(a.csr, TILE);
-    if (n == 0) break;
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
+    const int n = tile_n[st];
+    if (n == 0) break;  // list exhausted (the same value for every thread of the CTA)
     const float4 *tile = reinterpret_cast<const float4 *>(&tiles[st][0]);
     float acc[kAcc];
 #pragma unroll
@@ -207,7 +198,8 @@ __global__ void __launch_bounds__(NT) uj_leaf_kernel_f32(const LeafUjArgsF a) {
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) dsum[k] += (double)acc[k];
     __syncthreads();
-    if (tid == 0) issue();
+    if (tid < 32)
+      prod.issue<TILE, kRecD>(a.csr, recd, reinterpret_cast<double *>(&tiles[st][0]), &full[st], &tile_n[st]);
   }
   for (int o = glanes; o < 32; o <<= 1) {
 #pragma unroll

@@ -370,3 +370,72 @@ def test_errors_are_codes_with_messages(vpm, handle):
     assert rc in (-6, 0)  # ESTATE unless a previous test left state resident
     with pytest.raises(vpm.VpmError):
         vpm.Handle(device_ids=[10_000])
+
+
+# ------------------------------- pageable host matrices: the pinned staging ring
+def _with_pinned(handle, P, fn):
+    handle.check(handle.lib.vpm_pin_host(handle.ptr, P.ctypes.data, P.nbytes))
+    try:
+        fn()
+    finally:
+        handle.check(handle.lib.vpm_unpin_host(handle.ptr, P.ctypes.data))
+
+
+def test_pageable_matrix_goes_through_ring_bit_identical(vpm, handle):
+    """A pageable matrix travels through the two pinned slots (h2d_strided / d2h_strided: several slots'
+    worth of columns at this size); a page-locked one by 2-D DMA.  Same kernels, same operands: the
+    results must be identical to the last bit, and rows the entry points do not own stay untouched."""
+    n = 330_000                                    # 56-byte rows: one 16 MB slot holds 299 593 columns
+    pf = vpm.fields.cloud_field(n, kernel=vpm.winckelmans, seed=21)
+    vpm.fields.random_results(pf, scale=1e-2)
+    ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=64, theta=0.4)
+    leaves = (ll["leaf_begin"], ll["leaf_end"])
+    order, dl = ll["sort_index"], ll["direct_list"]
+    start = pf.particles.copy(order="F")
+
+    def run(pinned, call):
+        pf.particles[...] = start
+        if pinned:
+            _with_pinned(handle, pf.particles, call)
+        else:
+            call()
+        return pf.particles.copy(order="F")
+
+    calls = {
+        "zeta_fmm": lambda: vpm.zeta_fmm(pf, order, leaves, dl),
+        "Estr_fmm": lambda: vpm.Estr_fmm(pf, order, order, leaves, leaves, dl),
+        "nearfield_ranges": lambda: vpm.fmm_nearfield_device(
+            pf, [range(0, 1000), range(150_000, 151_000), range(n - 500, n)], (False, True, True), pf,
+            [[range(0, 3000)], [range(149_000, 152_000)], [range(n - 2000, n)]]),
+    }
+    for name, call in calls.items():
+        a = run(False, call)
+        b = run(True, call)
+        assert np.array_equal(a, b), name
+        assert not np.array_equal(a, start), name   # the call did write something
+
+
+def test_pageable_f32_matrix_and_targets_through_ring(vpm, handle):
+    pf = vpm.fields.cloud_field(40_000, kernel=vpm.gaussianerf, seed=22, R=np.float32)
+    start = pf.particles.copy(order="F")
+    vpm.UJ_direct(pf, sfs=True, reset_sfs=True)
+    a = pf.particles.copy(order="F")
+    pf.particles[...] = start
+    _with_pinned(handle, pf.particles, lambda: vpm.UJ_direct(pf, sfs=True, reset_sfs=True))
+    assert np.array_equal(a, pf.particles)
+    # UJ_direct(source, target): targets accumulate
+    src = vpm.fields.cloud_field(20_000, kernel=vpm.winckelmans, seed=23)
+    tgt = vpm.fields.cloud_field(50_000, kernel=vpm.winckelmans, seed=24)
+    vpm.fields.random_results(tgt, scale=1e-2)
+    t0 = tgt.particles.copy(order="F")
+    vpm.UJ_direct(src, tgt)
+    a = tgt.particles.copy(order="F")
+    tgt.particles[...] = t0
+    _with_pinned(handle, tgt.particles, lambda: vpm.UJ_direct(src, tgt))
+    assert np.array_equal(a, tgt.particles)
+    # and the accumulated sums are right (oracle on the first 200 targets)
+    ref = np.zeros((16, 200), order="F")
+    ref[0:3] = t0[0:3, :200]
+    sb = np.asfortranarray(vpm.source_system_to_buffer(src))
+    oracle.direct_buffers(ref, 0, 200, sb, 0, src.np, "winckelmans")
+    assert relerr(a[9:12, :200] - t0[9:12, :200], ref[4:7]) < 1e-10   # difference of O(1e-2) numbers
