@@ -15,7 +15,8 @@ SYMBOLS = [
     "vpm_create", "vpm_destroy", "vpm_last_error", "vpm_abi_version", "vpm_num_devices",
     "vpm_uj_direct", "vpm_uj_direct_f32", "vpm_uj_direct_st",
     "vpm_upload_state", "vpm_eval", "vpm_download_results",
-    "vpm_pin_host", "vpm_unpin_host", "vpm_set_option", "vpm_nearfield_ranges",
+    "vpm_pin_host", "vpm_unpin_host", "vpm_set_option", "vpm_nearfield_ranges", "vpm_field_zeta_method",
+    "vpm_field_zeta",
     "vpm_p2p_buffers", "vpm_p2p_leafpairs", "vpm_estr_leafpairs",
     "vpm_zeta_direct", "vpm_zeta_leafpairs",
     "vpm_leaflists_build", "vpm_leaflists_get", "vpm_uj_nearfield",
@@ -103,6 +104,8 @@ def load():
     lib.vpm_field_step.argtypes = [p, P(VpmStepParams)]
     lib.vpm_field_rbf.argtypes = [p, i32, i32, dbl, i32, P(i32), P(dbl)]
     lib.vpm_field_tsgm.argtypes = [p, P(dbl), i32]
+    lib.vpm_field_zeta_method.argtypes = [p, i32, i64, dbl]
+    lib.vpm_field_zeta.argtypes = [p, i32]
     lib.vpm_uj_device.argtypes = [p, p, i64, i64, i64, p, i32, i32, p]
     lib.vpm_sfs_device.argtypes = [p, p, p, p, i64, i64, i64, p, i32, i32, p]
     lib.vpm_get_timing.argtypes = [p, P(VpmTiming)]

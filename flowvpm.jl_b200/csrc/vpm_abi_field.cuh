@@ -184,6 +184,29 @@ int vpm_field_rbf(vpm_handle *h, int kernel, int itmax, double tol, int iterror,
   return rc != VPM_OK ? rc : rs;
 }
 
+int vpm_field_zeta_method(vpm_handle *h, int method, int64_t ncrit, double theta) {
+  if (!h) return VPM_EINVAL;
+  if (method < VPM_ZETA_DIRECT || method > VPM_ZETA_FMM_RESET)
+    return fail(h, VPM_EINVAL, "vpm_field_zeta_method: method must be VPM_ZETA_DIRECT, VPM_ZETA_FMM or VPM_ZETA_FMM_RESET (got %d)", method);
+  if (method != VPM_ZETA_DIRECT && (ncrit < 1 || !(theta > 0.0)))
+    return fail(h, VPM_EINVAL, "vpm_field_zeta_method: ncrit >= 1 and theta > 0 required");
+  h->zeta_method = method;
+  if (method != VPM_ZETA_DIRECT) { h->zeta_ncrit = ncrit; h->zeta_theta = theta; }
+  return VPM_OK;
+}
+
+int vpm_field_zeta(vpm_handle *h, int kernel) {
+  if (!h) return VPM_EINVAL;
+  if (h->fld_np < 0) return fail(h, VPM_ESTATE, "vpm_field_zeta: no resident field (call vpm_field_upload first)");
+  if (!valid_kernel(kernel)) return fail(h, VPM_EINVAL, "vpm_field_zeta: unknown kernel_id %d", kernel);
+  h->launches = 0;
+  if (h->fld_np == 0) return VPM_OK;
+  int rc = field_zeta(h, kernel);
+  int rs = field_sync_all(h);
+  h->timing.kernel_launches = h->launches;
+  return rc != VPM_OK ? rc : rs;
+}
+
 int vpm_field_tsgm(vpm_handle *h, double *t_sgm, int set) {
   if (!h || !t_sgm) return VPM_EINVAL;
   if (set) h->fld_t_sgm = *t_sgm; else *t_sgm = h->fld_t_sgm;

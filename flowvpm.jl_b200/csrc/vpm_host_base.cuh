@@ -88,6 +88,13 @@ struct vpm_handle {
   // device-built leaf lists (vpm_leaflists_build), resident on device 0
   int64_t tree_np = -1, tree_nl = 0, tree_npairs = 0;
   unsigned long long tree_fingerprint = 0;  // of the X and sigma rows the lists were built from
+  int64_t tree_ncrit = 0;                   // parameters of that build
+  double tree_theta = 0.0;
+  // CoreSpreading's `zeta` on the resident field (vpm_field_zeta_method): 0 zeta_direct, 1 zeta_fmm
+  // (J[1:3] accumulated on, as the reference's does), 2 zeta_fmm with J[1:3] zeroed first
+  int zeta_method = 0;
+  int64_t zeta_ncrit = 50;
+  double zeta_theta = 0.4;
   // single-process multi-GPU (n_gpus > 1): NCCL communicators, one per device
   void *nccl_lib = nullptr;
   std::vector<void *> comms;

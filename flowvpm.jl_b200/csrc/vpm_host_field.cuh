@@ -91,8 +91,14 @@ int field_uj(vpm_handle *h, int kernel, int flags) {
 }
 
 
-// zeta_direct on the resident mirror(s): J[1:3] of every particle <- sum_j Gamma_j zeta_sigma_j
+int field_zeta_lists(vpm_handle *h, int kernel);
+template <class L>
+int field_on_all(vpm_handle *h, L launch);
+
+// cs.zeta(pfield) on the resident mirror(s).  zeta_direct (the default): J[1:3] of every particle <-
+// sum_j Gamma_j zeta_sigma_j; zeta_fmm: field_zeta_lists below.
 int field_zeta(vpm_handle *h, int kernel) {
+  if (h->zeta_method != 0) return field_zeta_lists(h, kernel);
   const int64_t nf = h->fld_nf, np = h->fld_np;
   if (np == 0) return VPM_OK;
   const int G = (int)h->devs.size();
@@ -118,6 +124,60 @@ int field_zeta(vpm_handle *h, int kernel) {
     }
   }
   return field_allgather(h);
+}
+
+// zeta_fmm on the resident mirror(s) (src/FLOWVPM_viscous.jl:523-558): the near field of leaf lists built on
+// the device from the resident X and sigma (csrc/vpm_tree.cuh; the reference builds a FastMultipole tree per
+// call).  The lists depend on X and sigma only: the CG iterations of the RBF change Gamma alone, so a build
+// serves every evaluation until positions or core sizes change (fingerprint of the rows, as vpm_uj_nearfield).
+// For a list entry (a, b) the bodies of leaf b RECEIVE from the bodies of leaf a (as vpm_zeta_leafpairs).
+// The O(N ncrit) sweep runs on device 0; with G devices the three sums per particle are broadcast over NVLink
+// and every device adds them to its own mirror, which keeps the mirrors bit-identical.
+int field_zeta_lists(vpm_handle *h, int kernel) {
+  const char *fn = "zeta_fmm (resident field)";
+  const int64_t nf = h->fld_nf, np = h->fld_np;
+  if (np == 0) return VPM_OK;
+  const int G = (int)h->devs.size();
+  Dev &d = h->devs[0];
+  cudaStream_t st = d.stream;
+  CK(h, cudaSetDevice(d.id));
+  double *F = (double *)d.fld.p;
+  unsigned long long fp = 0;
+  TRY(tree_fingerprint(h, d, F, nf, 6, np, &fp));
+  if (h->tree_np != np || fp != h->tree_fingerprint || h->tree_ncrit != h->zeta_ncrit || h->tree_theta != h->zeta_theta)
+    TRY(tree_build(h, F, nf, 6, np, h->zeta_ncrit, h->zeta_theta));
+  const TreeView tv = tree_view(h);
+  DevCsr c;
+  TRY(build_csr_device(h, fn, tv.lbegin, tv.lend, h->tree_nl, np, tv.lbegin, tv.lend, h->tree_nl, np, tv.ps, tv.pt,
+                       h->tree_npairs, 1, nullptr, 0, nullptr, 0, c, true));
+  const int64_t ns_pad = round_up(np, kTile);
+  TRY(scratch_acquire(h, d, st));
+  TRY(ensure(h, d.srec, (size_t)ns_pad * kSfsRec * sizeof(double)));
+  TRY(ensure(h, d.sfs3, (size_t)np * 3 * sizeof(double)));
+  CK(h, cudaMemsetAsync(d.sfs3.p, 0, (size_t)np * 3 * sizeof(double), st));
+  if (c.nwi > 0) {
+    SrcView sv{F, nf, 0, 3, 6};
+    // (the J operand of the record builder is not used in zeta mode)
+    prep_sfs_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, F, nf, R_J, nullptr, 1, tv.sidx, np, ns_pad, kernel, 1,
+                                                              (double *)d.srec.p);
+    LeafSfsArgs a;
+    a.csr = c.csr;
+    a.tpos = F; a.tld = nf; a.tJ = F + R_J; a.jld = nf; a.tindex = tv.sidx; a.rec = (const double *)d.srec.p;
+    a.out = (double *)d.sfs3.p; a.old = 3; a.orow = 0; a.transposed = 1; a.shortcut = 1;
+    launch_sfs_leaf(kernel, c.nt, (unsigned)c.nwi, a, st, MODE_ZETA);
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+  }
+  for (int g = 1; g < G; ++g) {
+    CK(h, cudaSetDevice(h->devs[g].id));
+    TRY(ensure(h, h->devs[g].sfs3, (size_t)np * 3 * sizeof(double)));
+  }
+  if (G > 1) TRY(bcast_from_dev0(h, &Dev::sfs3, (size_t)np * 3 * sizeof(double)));
+  const int accumulate = h->zeta_method == 1;
+  return field_on_all(h, [&](Dev &dg) {
+    add_rows3_kernel<<<blocks_for(np, 256), 256, 0, dg.stream>>>((const double *)dg.sfs3.p, np, (double *)dg.fld.p, nf, R_J,
+                                                                accumulate);
+  });
 }
 
 StepArgs step_args_of(vpm_handle *h, Dev &d) {

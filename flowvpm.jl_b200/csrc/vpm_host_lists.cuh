@@ -356,6 +356,7 @@ int tree_build(vpm_handle *h, const double *d_P, int64_t ld, int osig, int64_t n
   CK(h, cudaGetLastError());
   TRY(tree_fingerprint(h, d, d_P, ld, osig, np, &h->tree_fingerprint));
   h->tree_np = np; h->tree_nl = nl; h->tree_npairs = npairs;
+  h->tree_ncrit = ncrit; h->tree_theta = theta;
   return VPM_OK;
 }
 

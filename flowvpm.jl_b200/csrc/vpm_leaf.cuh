@@ -397,4 +397,14 @@ __global__ void add_sorted3_kernel(const double *__restrict__ sorted, const int6
   out[c * 3 + 2] += sorted[i * 3 + 2];
 }
 
+// M[c*ld + row + k] (+)= v[c*3 + k], k = 0..2, for every particle c (zeta_fmm on the resident field)
+__global__ void add_rows3_kernel(const double *__restrict__ v, int64_t np, double *__restrict__ M, int64_t ld, int row,
+                                 int accumulate) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= np) return;
+  double *o = M + c * ld + row;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) o[k] = (accumulate ? o[k] : 0.0) + v[c * 3 + k];
+}
+
 }  // namespace vpm

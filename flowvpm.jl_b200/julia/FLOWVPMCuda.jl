@@ -350,10 +350,16 @@ function nextstep_cuda!(pfield::vpm.ParticleField{Float64}, dt::Real; relax::Boo
     Uinf = pfield.Uinf(pfield.t)
     deltat = pfield.nt > 0 ? pfield.t / pfield.nt : 0.0
     V = pfield.viscous
-    cs = V isa vpm.CoreSpreading          # evaluated with zeta_direct on the device
+    cs = V isa vpm.CoreSpreading
     pse = V isa vpm.ParticleStrengthExchange   # per-particle part only (src/FLOWVPM_viscous.jl:257-298)
     nu, sgm0, cs_beta, cs_tol = cs ? (V.nu, V.sgm0, V.beta, V.tol) : (pse ? V.nu : 0.0, 1.0, 1.5, 1e-3)
     if cs
+        # the scheme's `zeta` argument (src/FLOWVPM_viscous.jl:63-141): zeta_fmm -> near field of device-built
+        # leaf lists with pfield.fmm's leaf size and acceptance, accumulating on J[1:3] exactly as the
+        # reference's zeta_fmm does; anything else -> zeta_direct
+        zfmm = V.zeta === vpm.zeta_fmm
+        check(ccall((:vpm_field_zeta_method, lib[]), Cint, (Ptr{Cvoid}, Cint, Int64, Cdouble), handle[],
+                    zfmm ? 1 : 0, pfield.fmm.ncrit, pfield.fmm.theta))
         t_sgm = Ref{Cdouble}(V.t_sgm)
         check(ccall((:vpm_field_tsgm, lib[]), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Cint), handle[], t_sgm, 1))
     end

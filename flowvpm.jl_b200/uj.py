@@ -291,6 +291,18 @@ class ResidentField:
                                              _flags(self.pfield, sfs, reset, reset_sfs)))
 
     SFS_SCHEMES = {False: 0, None: 0, "none": 0, True: 1, "constant": 1, "dynamic": 2}
+    ZETA_METHODS = {"direct": 0, "zeta_direct": 0, "fmm": 1, "zeta_fmm": 1, "fmm_reset": 2}
+
+    def zeta_method(self, zeta="direct", ncrit=50, theta=0.4):
+        """CoreSpreading's `zeta` argument (src/FLOWVPM_viscous.jl:63-141) for this field: "direct" (zeta_direct),
+        "fmm" (zeta_fmm, :523-558: near field of leaf lists with pfield.fmm's ncrit / theta, J[1:3] accumulated
+        on as the reference does) or "fmm_reset" (same sums, J[1:3] zeroed first).  Used by rbf_conjugategradient,
+        zeta() and the CoreSpreading branch of nextstep until changed."""
+        self.h.check(self.h.lib.vpm_field_zeta_method(self.h.ptr, self.ZETA_METHODS[zeta], int(ncrit), float(theta)))
+
+    def zeta(self):
+        """cs.zeta(pfield) on the resident matrix (results in J[1:3])"""
+        self.h.check(self.h.lib.vpm_field_zeta(self.h.ptr, self.pfield.kernel.id))
 
     def rbf_conjugategradient(self, itmax=15, tol=1e-3, iterror=True):
         """rbf_conjugategradient(pfield, cs) with cs.zeta = zeta_direct (src/FLOWVPM_viscous.jl:309-478):
@@ -318,8 +330,9 @@ class ResidentField:
                  control_magnitude=False, viscous=None):
         """sfs: False | "constant" (ConstantSFS, coefficient Cs) | "dynamic" (DynamicSFS with the
         pseudo-3-level procedure: alpha, sfs_rlxf, minC, maxC, force_positive);
-        viscous: None (Inviscid) | dict(nu=, sgm0=, beta=1.5, itmax=15, tol=1e-3, iterror=True) for
-        CoreSpreading(nu, sgm0, zeta_direct) (src/FLOWVPM_viscous.jl:63-223) |
+        viscous: None (Inviscid) | dict(nu=, sgm0=, beta=1.5, itmax=15, tol=1e-3, iterror=True[, zeta="direct" |
+        "fmm" | "fmm_reset", ncrit=50, theta=0.4]) for CoreSpreading(nu, sgm0, zeta) (src/FLOWVPM_viscous.jl:63-223;
+        without `zeta` the method set by zeta_method() stays) |
         dict(scheme="pse", nu=, recalculate_vols=True) for ParticleStrengthExchange (:228-298)"""
         if minC < 0 or maxC < 0 or minC > maxC:
             raise ValueError(f"Invalid C bounds: minC={minC}, maxC={maxC}")  # subfilterscale.jl:456-462
@@ -344,6 +357,8 @@ class ResidentField:
             sp.nu, sp.sgm0 = viscous["nu"], viscous["sgm0"]
             sp.cs_beta, sp.cs_tol = viscous.get("beta", 1.5), viscous.get("tol", 1e-3)
             sp.cs_itmax, sp.cs_iterror = int(viscous.get("itmax", 15)), int(viscous.get("iterror", True))
+            if "zeta" in viscous:
+                self.zeta_method(viscous["zeta"], viscous.get("ncrit", 50), viscous.get("theta", 0.4))
         self.h.check(self.h.lib.vpm_field_step(self.h.ptr, C.byref(sp)))
         self.pfield.t += dt
         self.pfield.nt += 1

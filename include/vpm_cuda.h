@@ -250,7 +250,7 @@ typedef struct vpm_step_params {
   double sfs_rlxf;    /* DynamicSFS: Lagrangian-average relaxation (default 0.005) */
   double minC, maxC;  /* DynamicSFS: bounds of |C| (defaults 0, 1) */
   double deltat;      /* pfield.t / pfield.nt, used by control_magnitude; <= 0 when pfield.nt == 0 */
-  double nu, sgm0;    /* CoreSpreading(nu, sgm0, zeta_direct): src/FLOWVPM_viscous.jl:63-141 */
+  double nu, sgm0;    /* CoreSpreading(nu, sgm0, zeta): src/FLOWVPM_viscous.jl:63-141; zeta = vpm_field_zeta_method */
   double cs_beta;     /* maximum core growth sigma/sgm0 before the RBF reset (default 1.5) */
   double cs_tol;      /* RBF tolerance (default 1e-3) */
   int32_t kernel_id;
@@ -277,11 +277,29 @@ int vpm_field_download(vpm_handle *h, double *particles, int64_t nfields, int64_
 int vpm_field_uj(vpm_handle *h, int kernel_id, int flags);
 /* nextstep's integration call: one euler / rungekutta3 step on the resident matrix */
 int vpm_field_step(vpm_handle *h, const vpm_step_params *params);
-/* rbf_conjugategradient(pfield, cs) with cs.zeta = zeta_direct on the resident matrix
+/* rbf_conjugategradient(pfield, cs) with cs.zeta = the method of vpm_field_zeta_method (zeta_direct unless set) on the resident matrix
  * (src/FLOWVPM_viscous.jl:309-478): target vorticity in M[7:9], new strengths in Gamma.
  * iterations / residuals (3) may be NULL. */
 int vpm_field_rbf(vpm_handle *h, int kernel_id, int itmax, double tol, int iterror, int *iterations,
                   double *residuals);
+/* CoreSpreading's third constructor argument `zeta` (src/FLOWVPM_viscous.jl:63-141) for the resident field: which
+ * basis-function evaluation vpm_field_rbf and the CoreSpreading branch of vpm_field_step call.
+ *   VPM_ZETA_DIRECT (default)  zeta_direct (:488-515): J[1:3] zeroed, all pairs.
+ *   VPM_ZETA_FMM               zeta_fmm (:523-558), what the reference's tests and examples pass: the near field
+ *                              of leaf lists with leaf size `ncrit` and acceptance `theta` (pfield.fmm), the far field
+ *                              neglected, and J[1:3] ACCUMULATED on -- the reference's zeta_fmm does not zero them.
+ *   VPM_ZETA_FMM_RESET         the same sums on zeroed J[1:3] (zeta_direct's contract).
+ * The lists are built on the device from the resident X and sigma (the recipe of vpm_leaflists_build, not
+ * FastMultipole's octree: which far pairs are dropped differs, their zeta is below 1e-16 of zeta(0) unless theta is
+ * set so loose that touching leaves are rejected) and are reused until X or sigma change: the RBF's CG iterations
+ * cost one O(N ncrit) sweep each.  They replace the lists vpm_leaflists_build left on the handle.
+ * ncrit / theta are ignored for VPM_ZETA_DIRECT. */
+#define VPM_ZETA_DIRECT 0
+#define VPM_ZETA_FMM 1
+#define VPM_ZETA_FMM_RESET 2
+int vpm_field_zeta_method(vpm_handle *h, int method, int64_t ncrit, double theta);
+/* cs.zeta(pfield) on the resident matrix with the selected method: results in J[1:3] (rows 16:18) */
+int vpm_field_zeta(vpm_handle *h, int kernel_id);
 /* CoreSpreading.t_sgm (time since the last core reset) kept with the resident field:
  * set != 0 stores *t_sgm, otherwise it is returned; vpm_field_upload resets it to 0 */
 int vpm_field_tsgm(vpm_handle *h, double *t_sgm, int set);

@@ -67,6 +67,8 @@ def lib():
         L.vpm_oracle_field_step.restype = i32
         L.vpm_oracle_rbf_cg.argtypes = [p, i64, i64, i32, i32, dbl, i32, p, i32]
         L.vpm_oracle_rbf_cg.restype = i32
+        L.vpm_oracle_set_cs_zeta.argtypes = [p]
+        L.vpm_oracle_set_cs_zeta.restype = None
         L.vpm_oracle_max_threads.restype = i32
         L.vpm_oracle_num_procs.restype = i32
         _lib = L
@@ -229,6 +231,47 @@ def rbf_conjugategradient(P, np_, kernel, itmax=15, tol=1e-3, iterror=True, nthr
     if rc < 0:
         raise RuntimeError("Maximum number of iterations reached before convergence")
     return rc, info
+
+
+_ZETA_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_int)
+_zeta_cb_keepalive = None
+
+
+class cs_zeta_fmm:
+    """Context manager: while active, rbf_conjugategradient and CoreSpreading (field_step) evaluate
+    cs.zeta = zeta_fmm (src/FLOWVPM_viscous.jl:523-558) instead of zeta_direct: leaf lists for the CURRENT
+    X and sigma from oracle/leaflists.py (the recipe the device builder restates; FastMultipole's tree is
+    not in the reference repo), then the list loop.  reset=False is the reference's behaviour (J[1:3] is
+    accumulated on); reset=True zeroes J[1:3] first."""
+
+    def __init__(self, ncrit=50, theta=0.4, reset=False):
+        self.ncrit, self.theta, self.reset = ncrit, theta, reset
+        self.calls = 0
+
+    def _eval(self, ptr, nf, np_, kernel_id):
+        from . import leaflists
+        P = np.ctypeslib.as_array((C.c_double * (nf * np_)).from_address(ptr)).reshape((nf, np_), order="F")
+        ll = leaflists.build_leaf_lists(P[0:3].copy(), P[6].copy(), ncrit=self.ncrit, theta=self.theta)
+        if self.reset:
+            P[15:18] = 0.0
+        si, lb, le = _i64(ll["sort_index"]), _i64(ll["leaf_begin"]), _i64(ll["leaf_end"])
+        dl = np.asarray(ll["direct_list"])
+        pt, ps = _i32(dl[:, 0]), _i32(dl[:, 1])
+        lib().vpm_oracle_zeta_leafpairs(ptr, nf, si.ctypes.data, lb.ctypes.data, le.ctypes.data, pt.ctypes.data,
+                                        ps.ctypes.data, len(pt), kernel_id)
+        self.calls += 1
+
+    def __enter__(self):
+        global _zeta_cb_keepalive
+        _zeta_cb_keepalive = _ZETA_CB(self._eval)
+        lib().vpm_oracle_set_cs_zeta(C.cast(_zeta_cb_keepalive, C.c_void_p))
+        return self
+
+    def __exit__(self, *exc):
+        global _zeta_cb_keepalive
+        lib().vpm_oracle_set_cs_zeta(None)
+        _zeta_cb_keepalive = None
+        return False
 
 
 def zeta_direct(P, np_, kernel, nthreads=0):

@@ -606,6 +606,19 @@ void vpm_oracle_zeta_leafpairs(double *P, int64_t nf, const int64_t *sort, const
   }
 }
 
+/*
+ * cs.zeta(pfield) as rbf_conjugategradient and CoreSpreading call it (src/FLOWVPM_viscous.jl:204,347,374):
+ * zeta_direct unless the test installed another evaluation (zeta_fmm: the Python side builds the leaf lists
+ * for the CURRENT X, sigma with oracle/leaflists.py and calls vpm_oracle_zeta_leafpairs).
+ */
+typedef void (*vpm_oracle_zeta_cb)(double *P, int64_t nf, int64_t np, int kernel);
+static vpm_oracle_zeta_cb g_cs_zeta = NULL;
+void vpm_oracle_set_cs_zeta(vpm_oracle_zeta_cb cb) { g_cs_zeta = cb; }
+static void o_cs_zeta(double *P, int64_t nf, int64_t np, int kernel, int nthreads) {
+  if (g_cs_zeta) g_cs_zeta(P, nf, np, kernel);
+  else vpm_oracle_zeta_direct(P, nf, np, kernel, nthreads);
+}
+
 /* ===========================================================================
  * Time step on the host (SURVEY 8 f-1 checker).  ReformulatedVPM{f,g} only.
  *   rungekutta3            src/FLOWVPM_timeintegration.jl:388-461
@@ -798,7 +811,7 @@ int vpm_oracle_rbf_cg(double *P, int64_t nf, int64_t np, int kernel, int itmax, 
       p[R_G + k] = p[R_M + k];
     }
   }
-  vpm_oracle_zeta_direct(P, nf, np, kernel, nthreads);
+  o_cs_zeta(P, nf, np, kernel, nthreads);
   for (int64_t i = 0; i < np; ++i) {
     double *p = P + nf * i;
     if (p[R_STATIC] != 0.0) continue;
@@ -816,7 +829,7 @@ int vpm_oracle_rbf_cg(double *P, int64_t nf, int64_t np, int kernel, int itmax, 
   for (int it = 1; it <= itmax; ++it) {
     if (!(flags[0] || flags[1] || flags[2])) break;
     it_done = it;
-    vpm_oracle_zeta_direct(P, nf, np, kernel, nthreads);
+    o_cs_zeta(P, nf, np, kernel, nthreads);
     for (int k = 0; k < 3; ++k) pAps[k] = 0;
     for (int64_t i = 0; i < np; ++i) {
       const double *p = P + nf * i;
@@ -887,7 +900,7 @@ static int o_corespreading(double *P, int64_t nf, int64_t np, int kernel, int in
     vis[4] += dt;
     double beta_cur = sqrt(2 * nu * vis[4] / (sgm0 * sgm0) + 1);
     if (beta_cur >= beta) {
-      vpm_oracle_zeta_direct(P, nf, np, kernel, nthreads);
+      o_cs_zeta(P, nf, np, kernel, nthreads);
       for (int64_t i = 0; i < np; ++i) {
         double *p = P + nf * i;
         if (p[R_STATIC] != 0.0) continue;

@@ -280,6 +280,32 @@ def test_corespreading_rbf_multi_gpu(vpm):
         h.close()
 
 
+def test_corespreading_zeta_fmm_multi_gpu(vpm):
+    """CoreSpreading(nu, sgm0, zeta_fmm) on a 2-GPU handle: the list sweep runs on device 0, its three sums per
+    particle are broadcast and added on every mirror (which must stay identical: the next UJ sweep is sharded)"""
+    g = _ngpu()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    h = vpm.Handle(2)
+    try:
+        pf = vpm.fields.ring_field(Nphi=60, nc=1, kernel=vpm.gaussianerf, R=1.0, Rcross=0.15, sigma=0.12)
+        pf.particles[7, :pf.np] = 4 / 3 * np.pi * 0.05**3
+        ref = pf.particles.copy(order="F")
+        vis = dict(nu=2e-3, sgm0=0.12, beta=1.02, itmax=20, tol=1e-4, iterror=True)
+        vis_ref = dict(vis, t_sgm=0.0)
+        kw = dict(integration="rungekutta3", f=0.0, g=0.2, sfs=False, relaxation="pedrizzetti", relax=True)
+        rf = vpm.ResidentField(pf, handle=h)
+        with oracle.cs_zeta_fmm(ncrit=20, theta=0.4, reset=True):
+            for _ in range(3):
+                rf.nextstep(5e-2, viscous=dict(vis, zeta="fmm_reset", ncrit=20, theta=0.4), **kw)
+                oracle.field_step(ref, pf.np, "gaussianerf", 5e-2, transposed=True, viscous=vis_ref, **kw)
+        rf.download()
+        for rows in (slice(0, 7), slice(9, 12), slice(15, 24), slice(27, 36)):
+            assert relerr(pf.particles[rows, :pf.np], ref[rows, :pf.np]) < 1e-8, rows
+    finally:
+        h.close()
+
+
 def test_nearfield_device_call_shape_multi_gpu(vpm):
     """Hook 3 in the reference's call shape (vpm_nearfield_ranges) on a multi-GPU handle: target ranges cut
     over the devices, every device moving its own columns; bit-identical to one device"""

@@ -141,6 +141,93 @@ def test_corespreading_step_matches_oracle(vpm, handle, integration):
         rf.nextstep(5e-2, viscous=vis, **kw)
 
 
+# ---- CoreSpreading(nu, sgm0, zeta_fmm): what the reference's own tests and examples construct
+# (test/runtests_singlevortexring.jl:27, runtests_leapfrog.jl:26)
+@pytest.mark.parametrize("method", ["fmm", "fmm_reset"])
+def test_field_zeta_fmm_matches_list_oracle(vpm, handle, method):
+    """zeta_fmm (src/FLOWVPM_viscous.jl:523-558) on the resident matrix: near field of device-built lists.
+    "fmm" accumulates on J[1:3] as the reference does, "fmm_reset" zeroes them first; nothing else is written."""
+    pf = vpm.fields.cloud_field(5000, kernel=vpm.gaussianerf, static_fraction=0.1, seed=31)
+    vpm.fields.random_results(pf, scale=1e-2)
+    n = pf.np
+    ref = pf.particles.copy(order="F")
+    z = oracle.cs_zeta_fmm(ncrit=40, theta=0.4, reset=method == "fmm_reset")
+    z._eval(ref.ctypes.data, ref.shape[0], n, pf.kernel.id)
+    rf = vpm.ResidentField(pf)
+    try:
+        rf.zeta_method(method, ncrit=40, theta=0.4)
+        rf.zeta()
+        rf.zeta()                       # second evaluation reuses the lists (X, sigma unchanged)
+        if method == "fmm":             # ... and accumulates again
+            z._eval(ref.ctypes.data, ref.shape[0], n, pf.kernel.id)
+        rf.download()
+    finally:
+        rf.zeta_method("direct")
+    assert relerr(pf.particles[15:18, :n], ref[15:18, :n]) < 1e-12
+    keep = np.r_[0:15, 18:pf.particles.shape[0]]
+    assert np.array_equal(pf.particles[keep][:, :n], ref[keep][:, :n])
+    with pytest.raises(vpm.VpmError):
+        rf.zeta_method("fmm", ncrit=0)
+
+
+@pytest.mark.parametrize("method,itmax,tol", [("fmm_reset", 30, 1e-6), ("fmm", 3, 1e-12)])
+def test_rbf_with_zeta_fmm_matches_oracle(vpm, handle, method, itmax, tol):
+    """rbf_conjugategradient with cs.zeta = zeta_fmm.  With J[1:3] zeroed per evaluation the CG converges and
+    gives the strengths back; with the reference's accumulating zeta_fmm the iteration is what it is -- the
+    resident path must still follow the oracle's arithmetic step by step (3 iterations compared)."""
+    pf = _vorticity_ring(vpm)
+    n = pf.np
+    G0 = pf.particles[3:6, :n].copy()
+    reset = method == "fmm_reset"
+    with oracle.cs_zeta_fmm(ncrit=20, theta=0.4, reset=reset) as z:
+        pf.particles[15:18, :n] = 0.0
+        z._eval(pf.particles.ctypes.data, pf.particles.shape[0], n, pf.kernel.id)
+        pf.particles[33:36, :n] = pf.particles[15:18, :n]      # M[7:9] <- target vorticity
+        ref = pf.particles.copy(order="F")
+        it_ref, res_ref = oracle.rbf_conjugategradient(ref, n, "gaussianerf", itmax=itmax, tol=tol, iterror=False)
+        assert z.calls == it_ref + 2                            # target, initial residual, one per iteration
+    rf = vpm.ResidentField(pf)
+    try:
+        rf.zeta_method(method, ncrit=20, theta=0.4)
+        it, res = rf.rbf_conjugategradient(itmax=itmax, tol=tol, iterror=False)
+        rf.download()
+    finally:
+        rf.zeta_method("direct")
+    assert it == it_ref and it >= 2
+    assert relerr(pf.particles[3:6, :n], ref[3:6, :n]) < 1e-9
+    assert relerr(pf.particles[27:33, :n], ref[27:33, :n]) < 1e-7
+    if reset:
+        assert relerr(pf.particles[3:6, :n], G0) < 1e-4                    # strengths recovered
+
+
+def test_corespreading_step_with_zeta_fmm_matches_oracle(vpm, handle):
+    """CoreSpreading(nu, sgm0, zeta_fmm) inside nextstep: the lists are rebuilt whenever sigma has changed
+    (core growth every stage, reset to sgm0 before the RBF) and reused across the CG iterations"""
+    pf = _vorticity_ring(vpm)
+    pf.particles[7, :pf.np] = 4 / 3 * np.pi * 0.05**3
+    ref = pf.particles.copy(order="F")
+    vis = dict(nu=2e-3, sgm0=0.12, beta=1.02, itmax=20, tol=1e-4, iterror=True)
+    vis_ref = dict(vis, t_sgm=0.0)
+    kw = dict(integration="rungekutta3", f=0.0, g=0.2, sfs=False, relaxation="pedrizzetti", relax=True)
+    rf = vpm.ResidentField(pf)
+    resets = 0
+    try:
+        with oracle.cs_zeta_fmm(ncrit=20, theta=0.4, reset=True):
+            for k in range(4):
+                rf.nextstep(5e-2, viscous=dict(vis, zeta="fmm_reset", ncrit=20, theta=0.4), **kw)
+                oracle.field_step(ref, pf.np, "gaussianerf", 5e-2, transposed=True, viscous=vis_ref, **kw)
+                assert abs(rf.t_sgm - vis_ref["t_sgm"]) < 1e-15
+                resets += vis_ref["t_sgm"] == 0.0
+    finally:
+        rf.zeta_method("direct")
+    assert 1 <= resets < 4
+    rf.download()
+    for name, r in ROWS.items():
+        if name in ("SFS", "C"):
+            continue
+        assert relerr(pf.particles[r, :pf.np], ref[r, :pf.np]) < 1e-8, name
+
+
 @pytest.mark.parametrize("integration", ["euler", "rungekutta3"])
 @pytest.mark.parametrize("recalculate_vols", [True, False])
 def test_pse_step_matches_oracle(vpm, handle, integration, recalculate_vols):
