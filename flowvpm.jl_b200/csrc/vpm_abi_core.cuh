@@ -67,7 +67,7 @@ int vpm_destroy(vpm_handle *h) {
     cudaSetDevice(d.id);
     cudaStreamSynchronize(d.stream);
     for (Buf *b : {&d.in7, &d.stat, &d.res18, &d.sfs3, &d.rec, &d.srec, &d.partial, &d.tbuf, &d.sbuf,
-                   &d.ibuf, &d.jbuf, &d.fld, &d.scr, &d.scr2, &d.cubtmp, &d.tree, &d.tlist})
+                   &d.ibuf, &d.jbuf, &d.fld, &d.scr, &d.scr2, &d.cubtmp, &d.tree, &d.tlist, &d.flg})
       if (b->p) cudaFree(b->p);
     for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
     if (d.scratch_ev) cudaEventDestroy(d.scratch_ev);

@@ -101,8 +101,8 @@ int vpm_field_step(vpm_handle *h, const vpm_step_params *sp) {
     a.alpha = sp->alpha; a.sfs_rlxf = sp->sfs_rlxf; a.minC = sp->minC; a.maxC = sp->maxC;
     a.force_positive = sp->force_positive;
     a.controls = sp->controls; a.deltat = sp->deltat;
-    TRY(ensure(h, d.ibuf, 4096));
-    a.nan_flag = (int *)d.ibuf.p;
+    TRY(ensure(h, d.flg, 256));
+    a.nan_flag = (int *)d.flg.p;
     CK(h, cudaMemsetAsync(a.nan_flag, 0, sizeof(int), d.stream));
   }
   // an O(N) kernel on every device's mirror (all mirrors hold the same data)

@@ -28,6 +28,7 @@ struct Dev {
   cudaEvent_t scratch_ev = nullptr;
   bool scratch_pending = false;
   Buf in7, stat, res18, sfs3, rec, srec, partial, tbuf, sbuf, ibuf, jbuf, fld, scr, scr2, cubtmp, tree, tlist;
+  Buf flg;  // the time step's NaN flag (its own block: ibuf and the scratch are rebuilt by list sweeps inside a step)
   // two pinned slots through which the strided rows of a PAGEABLE host matrix travel (h2d_strided /
   // d2h_strided in vpm_host_hook1.cuh); allocated on first use
   char *ring[2] = {nullptr, nullptr};
