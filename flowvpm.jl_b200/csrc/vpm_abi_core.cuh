@@ -427,8 +427,8 @@ int vpm_p2p_buffers(vpm_handle *h, double *tgt, int64_t ld, int64_t t0, int64_t 
   TRY(ensure(h, d.tbuf, (size_t)nt * ld * sizeof(double)));
   TRY(ensure(h, d.sbuf, (size_t)ns * 8 * sizeof(double)));
   CK(h, cudaEventRecord(d.ev[0], st));
-  CK(h, cudaMemcpyAsync(d.tbuf.p, tgt + t0 * ld, (size_t)nt * ld * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(h, cudaMemcpyAsync(d.sbuf.p, src + s0 * 8, (size_t)ns * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+  TRY(h2d_contig(h, st, d.tbuf.p, tgt + t0 * ld, (size_t)nt * ld * sizeof(double)));
+  TRY(h2d_contig(h, st, d.sbuf.p, src + s0 * 8, (size_t)ns * 8 * sizeof(double)));
   CK(h, cudaEventRecord(d.ev[1], st));
   SrcView sv{(const double *)d.sbuf.p, 8, 0, 4, 7};
   Plan plan;
@@ -444,7 +444,7 @@ int vpm_p2p_buffers(vpm_handle *h, double *tgt, int64_t ld, int64_t t0, int64_t 
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(d.ev[3], st));
   CK(h, cudaEventRecord(d.ev[4], st));
-  CK(h, cudaMemcpyAsync(tgt + t0 * ld, d.tbuf.p, (size_t)nt * ld * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TRY(d2h_contig(h, st, tgt + t0 * ld, d.tbuf.p, (size_t)nt * ld * sizeof(double)));
   CK(h, cudaEventRecord(d.ev[5], st));
   CK(h, cudaStreamSynchronize(st));
   h->timing.uj_pairs = nt * ns;

@@ -15,7 +15,7 @@ int vpm_field_upload(vpm_handle *h, const double *P, int64_t nf, int64_t np) {
   CK(h, cudaSetDevice(d0.id));
   if (np_pad > np)
     CK(h, cudaMemsetAsync((double *)d0.fld.p + np * nf, 0, (size_t)(np_pad - np) * nf * sizeof(double), d0.stream));
-  if (np > 0) CK(h, cudaMemcpyAsync(d0.fld.p, P, (size_t)np * nf * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
+  if (np > 0) TRY(h2d_contig(h, d0.stream, d0.fld.p, P, (size_t)np * nf * sizeof(double)));
   h->fld_nf = nf;
   h->fld_np = np;
   h->fld_t_sgm = 0.0;
@@ -34,7 +34,7 @@ int vpm_field_download(vpm_handle *h, double *P, int64_t nf, int64_t np) {
                 (long long)h->fld_nf, (long long)h->fld_np, (long long)nf, (long long)np);
   Dev &d = h->devs[0];
   CK(h, cudaSetDevice(d.id));
-  if (np > 0) CK(h, cudaMemcpyAsync(P, d.fld.p, (size_t)np * nf * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+  if (np > 0) TRY(d2h_contig(h, d.stream, P, d.fld.p, (size_t)np * nf * sizeof(double)));
   CK(h, cudaStreamSynchronize(d.stream));
   return VPM_OK;
 }

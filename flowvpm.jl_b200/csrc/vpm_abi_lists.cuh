@@ -44,7 +44,7 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
     TRY(h2d_rows_sharded(h, &Dev::sbuf, src, 8, 8, n_src));
     CK(h, cudaSetDevice(d0.id));
   } else {
-    CK(h, cudaMemcpyAsync(d0.sbuf.p, src, (size_t)n_src * 8 * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
+    TRY(h2d_contig(h, d0.stream, d0.sbuf.p, src, (size_t)n_src * 8 * sizeof(double)));
   }
   DevCsr c;
   TRY(build_csr_device(h, fn, tb, te, ntl, n_tgt, sb, se, nsl, n_src, pt, ps, npairs, G, nullptr, 0, nullptr, 0, c));
@@ -71,8 +71,7 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
     const int64_t lf = c.first_leaf[g], ll = c.last_leaf[g + 1];
     const int64_t col0 = G == 1 ? 0 : tb[lf] + c.first_off[g];
     const int64_t col1 = G == 1 ? n_tgt : std::min<int64_t>(te[ll], tb[ll] + c.last_off[g + 1] + c.nt);
-    CK(h, cudaMemcpyAsync((double *)d.tbuf.p + col0 * ld, tgt + col0 * ld, (size_t)(col1 - col0) * ld * sizeof(double),
-                          cudaMemcpyHostToDevice, st));
+    TRY(h2d_contig(h, st, (double *)d.tbuf.p + col0 * ld, tgt + col0 * ld, (size_t)(col1 - col0) * ld * sizeof(double)));
     LeafUjArgs a;
     a.csr = csr[g];
     a.csr.wi_leaf += k0;
@@ -97,8 +96,7 @@ int vpm_p2p_leafpairs(vpm_handle *h, double *tgt, int64_t ld, int64_t n_tgt, int
     if (cols[g].second <= cols[g].first) continue;
     CK(h, cudaSetDevice(d.id));
     const int64_t col0 = cols[g].first, col1 = cols[g].second;
-    CK(h, cudaMemcpyAsync(tgt + col0 * ld, (double *)d.tbuf.p + col0 * ld, (size_t)(col1 - col0) * ld * sizeof(double),
-                          cudaMemcpyDeviceToHost, d.stream));
+    TRY(d2h_contig(h, d.stream, tgt + col0 * ld, (double *)d.tbuf.p + col0 * ld, (size_t)(col1 - col0) * ld * sizeof(double)));
     if (g == 0) CK(h, cudaEventRecord(d.ev[5], d.stream));
   }
   for (int g = G - 1; g >= 0; --g) {

@@ -207,6 +207,88 @@ int d2h_strided(vpm_handle *h, cudaStream_t st, void *dst, size_t dpitch, const 
   return scatter_prev();
 }
 
+// Contiguous blocks (FastMultipole's buffers, the near-field list, the whole matrix of vpm_field_upload).  The
+// driver stages a copy from / to pageable memory through its own bounce buffer on the calling thread; for blocks
+// of megabytes the ring with eight copying threads is faster.  Device pointers and page-locked memory go straight
+// to cudaMemcpyAsync (cudaMemcpyDefault: the list entry points also accept device-resident tables).
+bool host_is_pageable(const void *ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+constexpr size_t kRingMinContig = 4u << 20;
+template <class F>
+void parallel_bytes(size_t n, F fn) {
+  const size_t min_chunk = 1u << 20;
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::min<size_t>(std::min<unsigned>(hw ? hw : 1, 8), n / min_chunk);
+  if (nt <= 1) { fn((size_t)0, n); return; }
+  std::vector<std::thread> th;
+  const size_t chunk = ((n + nt - 1) / nt + 63) & ~(size_t)63;
+  for (int t = 1; t < nt; ++t)
+    th.emplace_back([=] { if ((size_t)t * chunk < n) fn((size_t)t * chunk, std::min(n, (size_t)(t + 1) * chunk)); });
+  fn((size_t)0, std::min(n, chunk));
+  for (auto &t : th) t.join();
+}
+int h2d_contig(vpm_handle *h, cudaStream_t st, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return VPM_OK;
+  Dev *d = dev_of_stream(h, st);
+  if (!d || h->capturing || bytes < kRingMinContig || !host_is_pageable(src)) {
+    CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st));
+    return VPM_OK;
+  }
+  TRY(ring_ready(h, *d));
+  for (size_t off = 0; off < bytes; off += kRingSlot) {
+    const size_t nb = std::min(kRingSlot, bytes - off);
+    const int b = d->ring_next;
+    d->ring_next ^= 1;
+    if (d->ring_busy[b]) CK(h, cudaEventSynchronize(d->ring_ev[b]));
+    char *slot = d->ring[b];
+    const char *s0 = (const char *)src + off;
+    parallel_bytes(nb, [=](size_t a, size_t e) { memcpy(slot + a, s0 + a, e - a); });
+    CK(h, cudaMemcpyAsync((char *)dst + off, slot, nb, cudaMemcpyHostToDevice, st));
+    CK(h, cudaEventRecord(d->ring_ev[b], st));
+    d->ring_busy[b] = true;
+  }
+  return VPM_OK;
+}
+// (pageable destination: returns with the data in place, like d2h_strided)
+int d2h_contig(vpm_handle *h, cudaStream_t st, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return VPM_OK;
+  Dev *d = dev_of_stream(h, st);
+  if (!d || h->capturing || bytes < kRingMinContig || !host_is_pageable(dst)) {
+    CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st));
+    return VPM_OK;
+  }
+  TRY(ring_ready(h, *d));
+  int pb = -1;
+  size_t poff = 0, pnb = 0;
+  auto drain_prev = [&]() -> int {
+    if (pb < 0) return VPM_OK;
+    CK(h, cudaEventSynchronize(d->ring_ev[pb]));
+    d->ring_busy[pb] = false;
+    const char *slot = d->ring[pb];
+    char *d0 = (char *)dst + poff;
+    parallel_bytes(pnb, [=](size_t a, size_t e) { memcpy(d0 + a, slot + a, e - a); });
+    return VPM_OK;
+  };
+  for (size_t off = 0; off < bytes; off += kRingSlot) {
+    const size_t nb = std::min(kRingSlot, bytes - off);
+    const int b = d->ring_next;
+    d->ring_next ^= 1;
+    if (d->ring_busy[b]) CK(h, cudaEventSynchronize(d->ring_ev[b]));
+    CK(h, cudaMemcpyAsync(d->ring[b], (const char *)src + off, nb, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaEventRecord(d->ring_ev[b], st));
+    d->ring_busy[b] = true;
+    TRY(drain_prev());  // overlaps the copy just issued
+    pb = b; poff = off; pnb = nb;
+  }
+  return drain_prev();
+}
+
 // rows [row.., row+nrows) of `np` columns of a host matrix (leading dimension nf) <-> compact device block
 int h2d_rows(vpm_handle *h, cudaStream_t st, double *dst, const double *src, int64_t nf, int nrows, int64_t np) {
   return h2d_strided(h, st, dst, nrows * sizeof(double), src, nf * sizeof(double), nrows * sizeof(double), np);

@@ -101,18 +101,18 @@ int build_csr_device(vpm_handle *h, const char *fn, const int64_t *tb, const int
   tmp = std::max(tmp, t1);
   TRY(ensure(h, d.cubtmp, tmp + 16));
 
-  auto put = [&](auto *dst, const auto *srcp, size_t n) -> cudaError_t {
-    if (n == 0) return cudaSuccess;
-    return cudaMemcpyAsync((void *)dst, (const void *)srcp, n * sizeof(*srcp), cudaMemcpyDefault, st);
+  // (host tables of a pageable caller go through the pinned ring; device-resident tables are plain copies)
+  auto put = [&](auto *dst, const auto *srcp, size_t n) -> int {
+    return h2d_contig(h, st, (void *)dst, (const void *)srcp, n * sizeof(*srcp));
   };
-  CK(h, put(dtb, tb, (size_t)ntl));
-  CK(h, put(dte, te, (size_t)ntl));
-  CK(h, put(dsb, sb, (size_t)nsl));
-  CK(h, put(dse, se, (size_t)nsl));
-  CK(h, put(dpt, pt, (size_t)npairs));
-  CK(h, put(dsrc, ps, (size_t)npairs));  // already the CSR column array when the list is grouped
-  if (n_tsort) CK(h, put(dts, tsort, (size_t)n_tsort));
-  if (n_ssort) CK(h, put(dss, ssort, (size_t)n_ssort));
+  TRY(put(dtb, tb, (size_t)ntl));
+  TRY(put(dte, te, (size_t)ntl));
+  TRY(put(dsb, sb, (size_t)nsl));
+  TRY(put(dse, se, (size_t)nsl));
+  TRY(put(dpt, pt, (size_t)npairs));
+  TRY(put(dsrc, ps, (size_t)npairs));  // already the CSR column array when the list is grouped
+  if (n_tsort) TRY(put(dts, tsort, (size_t)n_tsort));
+  if (n_ssort) TRY(put(dss, ssort, (size_t)n_ssort));
   csr_init_stats_kernel<<<1, 32, 0, st>>>(stats);
   csr_zero_kernel<<<blocks_for(ntl + 1, 256), 256, 0, st>>>(dptr, ntl + 1);
   csr_zero_kernel<<<blocks_for(ntl, 256), 256, 0, st>>>(srcw, ntl);

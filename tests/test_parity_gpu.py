@@ -439,3 +439,51 @@ def test_pageable_f32_matrix_and_targets_through_ring(vpm, handle):
     sb = np.asfortranarray(vpm.source_system_to_buffer(src))
     oracle.direct_buffers(ref, 0, 200, sb, 0, src.np, "winckelmans")
     assert relerr(a[9:12, :200] - t0[9:12, :200], ref[4:7]) < 1e-10   # difference of O(1e-2) numbers
+
+
+def test_pageable_buffers_and_field_through_ring(vpm, handle):
+    """contiguous blocks from / to pageable memory (FastMultipole-style buffers and the near-field list of
+    Hook 3, the whole matrix of vpm_field_upload / _download) also travel through the pinned ring"""
+    n = 330_000
+    pf = vpm.fields.cloud_field(n, kernel=vpm.winckelmans, seed=25)
+    ll = leaflists.build_leaf_lists(pf.get_X(), pf.get_sigma(), ncrit=64, theta=0.4)
+    leaves = (ll["leaf_begin"], ll["leaf_end"])
+    order, dl = ll["sort_index"], ll["direct_list"]
+    sb = np.asfortranarray(vpm.source_system_to_buffer(pf)[:, order])
+    res = []
+    for pinned in (False, True):
+        tb = np.zeros((16, n), order="F")
+        tb[0:3] = pf.get_X()[:, order]
+        if pinned:
+            for a in (tb, sb):
+                handle.check(handle.lib.vpm_pin_host(handle.ptr, a.ctypes.data, a.nbytes))
+        try:
+            vpm.nearfield_device(tb, leaves, sb, leaves, dl, vpm.winckelmans)
+        finally:
+            if pinned:
+                for a in (tb, sb):
+                    handle.check(handle.lib.vpm_unpin_host(handle.ptr, a.ctypes.data))
+        res.append(tb)
+    assert np.array_equal(res[0], res[1]) and np.abs(res[0][4:16]).max() > 0
+    # Hook 2 on the same buffers (a slab of targets against a slab of sources)
+    out = []
+    for pinned in (False, True):
+        tb = np.zeros((16, n), order="F")
+        tb[0:3] = pf.get_X()[:, order]
+        if pinned:
+            handle.check(handle.lib.vpm_pin_host(handle.ptr, tb.ctypes.data, tb.nbytes))
+        try:
+            vpm.direct_buffers(tb, (1000, 41000), sb, (0, 50000), vpm.winckelmans)
+        finally:
+            if pinned:
+                handle.check(handle.lib.vpm_unpin_host(handle.ptr, tb.ctypes.data))
+        out.append(tb)
+    assert np.array_equal(out[0], out[1]) and np.abs(out[0][4:16, 1000:41000]).max() > 0
+    assert not out[0][4:16, :1000].any() and not out[0][4:16, 41000:].any()
+    # whole-matrix round trip of the resident field
+    vpm.fields.random_results(pf, scale=1.0)
+    before = pf.particles.copy(order="F")
+    rf = vpm.ResidentField(pf)
+    pf.particles[...] = 0.0
+    rf.download()
+    assert np.array_equal(pf.particles[:, :n], before[:, :n])
