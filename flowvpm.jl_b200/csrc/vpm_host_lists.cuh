@@ -399,7 +399,10 @@ void launch_uj_leaf_any(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, int 
     f.urow = a.urow; f.jrow = a.jrow; f.want_U = a.want_U; f.want_J = a.want_J; f.shortcut = a.shortcut;
     launch_uj_leaf_f32(kernel, nt, nwi, f, st);
   } else {
-    prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (double *)d.rec.p);
+    if (kernel == K_GERF)  // kLeafTab: the leaf kernels of this family read the G(u) table
+      prep_uj_records_tab<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (double *)d.rec.p);
+    else
+      prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(sv, 0, n_src, ns_pad, kernel, (double *)d.rec.p);
     launch_uj_leaf(kernel, nt, nwi, a, st);
   }
   h->launches += 2;

@@ -76,6 +76,26 @@ __device__ __forceinline__ double2 lds_v2(uint32_t addr) {
   return v;
 }
 
+// Where a thread reads the three 16-byte chunks of a table row from.
+struct TabShared {  // the bank-group-private copies: base = shared address of the table + 16 * (lane & 7)
+  uint32_t base;
+  __device__ __forceinline__ void load(unsigned row, double2 &c01, double2 &c23, double2 &c4t) const {
+    const uint32_t ra = base + row * kTabRowBytes;
+    c4t = lds_v2<256>(ra); c23 = lds_v2<128>(ra); c01 = lds_v2<0>(ra);
+  }
+};
+struct TabGlobal {  // the packed 48-byte rows in global memory, through L1: the leaf-list kernels, whose CTAs
+  const double2 *rows;  // (one to four warps, a few thousand pairs each) cannot amortise staging eight copies
+  __device__ __forceinline__ void load(unsigned row, double2 &c01, double2 &c23, double2 &c4t) const {
+    const double2 *r = rows + row * kTabRowChunks;
+    c4t = __ldg(r + 2); c23 = __ldg(r + 1); c01 = __ldg(r);
+  }
+};
+template <int K>
+__device__ __forceinline__ TabGlobal tab_global() {
+  return TabGlobal{reinterpret_cast<const double2 *>(TabOf<K>::words())};
+}
+
 // Records (prep_uj_records_tab), the same for both families:  [x y z q0 | G'x G'y G'z q1 | q2 q3],
 //   q0 = 1/sigma^2 (u = r^2 q0), q1 = 1/sigma^3 (A = q1 G), q2 = far cut-off in r^2, q3 = 2/sigma^5 (B = q3 dG/du)
 __global__ void prep_uj_records_tab(SrcView src, int64_t s0, int64_t ns, int64_t ns_pad, int kernel,
@@ -103,17 +123,17 @@ __global__ void prep_uj_records_tab(SrcView src, int64_t s0, int64_t ns, int64_t
 }
 
 // Value p and xi-derivative dp of the polynomial of row `row` at the in-interval coordinate
-// given by the low (52 - LOGN) mantissa bits of t.  lane_tab = shared address of the table + 16 * (lane & 7).
-template <int LOGN>
-__device__ __forceinline__ void tab_poly(int hi, unsigned lo, unsigned row, uint32_t lane_tab,
+// given by the low (52 - LOGN) mantissa bits of t.  tab: TabShared or TabGlobal.
+template <int LOGN, class TAB>
+__device__ __forceinline__ void tab_poly(int hi, unsigned lo, unsigned row, const TAB &tab,
                                          double &p, double &dp) {
   constexpr int MB = 20 - LOGN;  // mantissa bits of the high word below the row index
   const unsigned mh = (unsigned)hi & ((1u << MB) - 1u);
   // xi = (low 52-LOGN mantissa bits) / 2^(52-LOGN) - 1/2, exact in FP64; its top 23 bits in FP32
   const double xi = __hiloint2double((int)(0x3ff00000u | (mh << LOGN) | (lo >> (32 - LOGN))), (int)(lo << LOGN)) - 1.5;
   const float xf = __uint_as_float(0x3f800000u | (mh << (3 + LOGN)) | (lo >> (29 - LOGN))) - 1.5f;
-  const uint32_t ra = lane_tab + row * kTabRowBytes;
-  const double2 c4t = lds_v2<256>(ra), c23 = lds_v2<128>(ra), c01 = lds_v2<0>(ra);
+  double2 c01, c23, c4t;
+  tab.load(row, c01, c23, c4t);
   const float t5 = __int_as_float(__double2loint(c4t.y)), t6 = __int_as_float(__double2hiint(c4t.y));
   const float t7 = __int_as_float(__double2loint(c4t.x) << 12);
   // Horner with derivative: b_j = c_j + xi b_{j+1},  d_j = b_{j+1} + xi d_{j+1}
@@ -144,9 +164,9 @@ __device__ __forceinline__ void tab_poly(int hi, unsigned lo, unsigned row, uint
 // r2 == 0 (the reference skips those pairs, src/FLOWVPM_fmm.jl:118; c = dx x G' = 0 there, so only the
 // W sums need A = 0): A's scale factor gets a zero high word, i.e. A ~ 1e-320 (an exact 0 to any
 // tolerance); decided on the high word of r2 alone, so pairs closer than ~1e-154 count as coincident.
-template <int K>
+template <int K, class TAB>
 __device__ __forceinline__ void ab_tab(double t, double r2, bool far, double q1, double q3,
-                                       uint32_t lane_tab, double &A, double &B) {
+                                       const TAB &tab, double &A, double &B) {
   using TB = TabOf<K>;
   constexpr int LOGN = TB::logn, MB = 20 - LOGN;
   static_assert(TB::far == 128, "far rows are indexed with a 7-bit mask");
@@ -161,7 +181,7 @@ __device__ __forceinline__ void ab_tab(double t, double r2, bool far, double q1,
   const unsigned row_near = min((unsigned)(top - ((1023 + TB::emin) << LOGN) + TB::far), (unsigned)(TB::rows - 1));
   const unsigned row = far ? (unsigned)(top & (TB::far - 1)) : row_near;
   double p, dp;
-  tab_poly<LOGN>(hi, lo, row, lane_tab, p, dp);
+  tab_poly<LOGN>(hi, lo, row, tab, p, dp);
   const unsigned em = (unsigned)hi & 0xfff00000u;  // E << 20
   unsigned kq = ((unsigned)(hi + 0x100000) >> 21) * (unsigned)(-3 << 20) + ((1536u << 20) + C);  // -3 ((E - 1023) >> 1)
   kq = far ? kq : C;
@@ -208,14 +228,23 @@ __device__ __forceinline__ void ab_gaus_u(double r2, bool far, double q0, double
   B = select_zero(z, (0.5 * q3) * H);
 }
 
-template <int K, int UNROLL>
+// SPLIT (leaf kernels, as uj_tile): the lanes of a warp form nsplit groups that own the same targets and take
+// every nsplit-th record of the tile; a group past the end re-reads the last record with A = B = 0.
+template <int K, int T, int UNROLL, bool SPLIT, class TAB>
 __device__ __forceinline__ void uj_tile_tab(const double2 *__restrict__ tile, int n,
-                                            const double (&tx)[kTabT], const double (&ty)[kTabT],
-                                            const double (&tz)[kTabT], double (&acc)[kTabT][kAcc],
-                                            int shortcut, uint32_t lane_tab) {
-  constexpr int T = kTabT;
+                                            const double (&tx)[T], const double (&ty)[T],
+                                            const double (&tz)[T], double (&acc)[T][kAcc],
+                                            int shortcut, const TAB &tab, int nsplit = 1, int phase = 0) {
+  const int trips = SPLIT ? (n + nsplit - 1) / nsplit : n;
 #pragma unroll UNROLL
-  for (int j = 0; j < n; ++j) {
+  for (int jj = 0; jj < trips; ++jj) {
+    int j = jj;
+    bool live = true;
+    if constexpr (SPLIT) {
+      j = jj * nsplit + phase;
+      live = j < n;
+      j = live ? j : n - 1;
+    }
     double sx, sy, sz, q0, gx, gy, gz, q1, q2, q3;
     load_rec<false>(tile, j, sx, sy, sz, q0, gx, gy, gz, q1, q2, q3);
     double dx[T], dy[T], dz[T], A[T], B[T], r2[T];
@@ -245,12 +274,19 @@ __device__ __forceinline__ void uj_tile_tab(const double2 *__restrict__ tile, in
         for (int t = 0; t < T; ++t) ab_gaus_u(r2[t], far[t], q0, q1, q3, A[t], B[t]);
       } else {
 #pragma unroll
-        for (int t = 0; t < T; ++t) ab_tab<K>(tt[t], r2[t], far[t], q1, q3, lane_tab, A[t], B[t]);
+        for (int t = 0; t < T; ++t) ab_tab<K>(tt[t], r2[t], far[t], q1, q3, tab, A[t], B[t]);
       }
     } else {
       // every pair of the warp is in the far field: g = 1, dg = 0 (cheaper than the table)
 #pragma unroll
       for (int t = 0; t < T; ++t) ab_sing(r2[t], A[t], B[t]);
+    }
+    if constexpr (SPLIT) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        A[t] = select_zero(!live, A[t]);
+        B[t] = select_zero(!live, B[t]);
+      }
     }
 #pragma unroll
     for (int t = 0; t < T; ++t) {
@@ -338,7 +374,7 @@ __global__ void __launch_bounds__(THREADS, 1) uj_pairs_tab_kernel(const UjArgs a
     const int64_t first = (tile0 + it) * kTile;
     const int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
     const double2 *tile = reinterpret_cast<const double2 *>(tiles + st * kTile * kRec);
-    uj_tile_tab<K, UNROLL>(tile, n, tx, ty, tz, acc, a.shortcut, lane_tab);
+    uj_tile_tab<K, kTabT, UNROLL, false>(tile, n, tx, ty, tz, acc, a.shortcut, TabShared{lane_tab});
     __syncthreads();  // everyone is done reading stage st
     if (tid == 0 && it + kStages < ntl) issue(it + kStages);
   }
@@ -397,7 +433,7 @@ __global__ void test_tab_kernel(const double *in, double *out, double *out2, int
   const bool far = x > (K == K_GERF ? kFarU_gerf : kFarU_gaus);
   const double t = fma(x, 1.0, far ? 0.0 : (double)TabOf<K>::offset);
   if (K == K_GAUS && !far && __double2hiint(t) < ((1023 + TabOf<K>::emin) << 20)) ab_gaus_u(x, far, 1.0, 1.0, 2.0, A, B);
-  else ab_tab<K>(t, x, far, 1.0, 2.0, smem_u32(smem) + 16 * (threadIdx.x & 7), A, B);
+  else ab_tab<K>(t, x, far, 1.0, 2.0, TabShared{smem_u32(smem) + 16 * (threadIdx.x & 7)}, A, B);
   out[i] = A;
   if (out2) out2[i] = B;
 }

@@ -95,6 +95,14 @@ struct LeafTileProducer {
   }
 };
 
+// gaussianerf in the leaf kernels: G(u) rows of vpm_kernels_tab.cuh read through L1 (TabGlobal) and the records of
+// prep_uj_records_tab instead of round 1's degree-9 table (three 16-byte gathers and 9 DFMA per pair instead of
+// five and 18).  Measured on the 2^20 cloud (G pairs/s): ncrit 24: 163.9 -> 205.6, 50: 215.0 -> 227.9,
+// 128: 282.7 -> 300.6, 512: 296.0 -> 302.7, 1600: 328.9 -> 328.1 (mostly far pairs there).  The gaussian family
+// measured 1 % slower on its table here (its regularised range ends at s = 3.45: few pairs) and keeps ab_gaus.
+template <int K>
+constexpr bool kLeafTab = K == K_GERF;
+
 struct LeafUjArgs {
   LeafCsr csr;
   const double *tpos;  // sorted target buffer: tpos[i*tld + 0..2]
@@ -117,7 +125,7 @@ __global__ void __launch_bounds__(NT) uj_leaf_kernel(const LeafUjArgs a) {
   // gaussianerf: the 13 KB G(u) table is staged in shared memory only by CTAs wide enough to amortise the
   // copy; a one- or two-warp CTA of a small leaf reads it through L1 instead (its whole work item is a few
   // thousand pairs: the copy alone cost a third of the kernel at ncrit 24: 101 -> 139 G pairs/s)
-  constexpr bool kTabInSmem = K == K_GERF && NT >= 128;
+  constexpr bool kTabInSmem = K == K_GERF && NT >= 128 && !kLeafTab<K>;
   __shared__ __align__(16) double2 gtab_s[kTabInSmem ? kGerfIntervals * kGerfCoeffs / 2 : 1];
   if constexpr (kTabInSmem) load_gerf_table(gtab_s);  // visible after the __syncthreads below
   const double2 *gtab = kTabInSmem ? gtab_s : reinterpret_cast<const double2 *>(kGerfTable);
@@ -159,8 +167,13 @@ __global__ void __launch_bounds__(NT) uj_leaf_kernel(const LeafUjArgs a) {
     const int n = tile_n[st];
     if (n == 0) break;  // list exhausted (the same value for every thread of the CTA)
     const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
-    if (nsplit == 1) uj_tile<K, 1, 2>(tile, n, tx, ty, tz, acc, a.shortcut, gtab);
-    else uj_tile<K, 1, 2, false, true>(tile, n, tx, ty, tz, acc, a.shortcut, gtab, nsplit, phase);
+    if constexpr (kLeafTab<K>) {
+      if (nsplit == 1) uj_tile_tab<K, 1, 2, false>(tile, n, tx, ty, tz, acc, a.shortcut, tab_global<K>());
+      else uj_tile_tab<K, 1, 2, true>(tile, n, tx, ty, tz, acc, a.shortcut, tab_global<K>(), nsplit, phase);
+    } else {
+      if (nsplit == 1) uj_tile<K, 1, 2>(tile, n, tx, ty, tz, acc, a.shortcut, gtab);
+      else uj_tile<K, 1, 2, false, true>(tile, n, tx, ty, tz, acc, a.shortcut, gtab, nsplit, phase);
+    }
     __syncthreads();
     if (tid < 32) prod.issue<TILE, kRec>(a.csr, a.rec, &tiles[st][0], &full[st], &tile_n[st]);
   }
@@ -196,7 +209,7 @@ __global__ void __launch_bounds__(32, 16) uj_leaf1w_kernel(const LeafUjArgs a) {
   // gaussianerf: the 13 KB G(u) table is staged in shared memory only by CTAs wide enough to amortise the
   // copy; a one- or two-warp CTA of a small leaf reads it through L1 instead (its whole work item is a few
   // thousand pairs: the copy alone cost a third of the kernel at ncrit 24: 101 -> 139 G pairs/s)
-  constexpr bool kTabInSmem = K == K_GERF && NT >= 128;
+  constexpr bool kTabInSmem = K == K_GERF && NT >= 128 && !kLeafTab<K>;
   __shared__ __align__(16) double2 gtab_s[kTabInSmem ? kGerfIntervals * kGerfCoeffs / 2 : 1];
   if constexpr (kTabInSmem) load_gerf_table(gtab_s);  // visible after the __syncthreads below
   const double2 *gtab = kTabInSmem ? gtab_s : reinterpret_cast<const double2 *>(kGerfTable);
@@ -258,7 +271,15 @@ __global__ void __launch_bounds__(32, 16) uj_leaf1w_kernel(const LeafUjArgs a) {
     const int n = tile_n[st];
     if (n == 0) break;  // list exhausted (the same value for every thread of the CTA)
     const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
-    if (two) {
+    if constexpr (kLeafTab<K>) {
+      if (two) {
+        uj_tile_tab<K, 2, 1, true>(tile, n, tx2, ty2, tz2, acc, a.shortcut, tab_global<K>(), nsplit, ph);
+      } else {
+        double (&acc1)[1][kAcc] = *reinterpret_cast<double (*)[1][kAcc]>(&acc[0]);
+        if (nsplit == 1) uj_tile_tab<K, 1, 2, false>(tile, n, tx1, ty1, tz1, acc1, a.shortcut, tab_global<K>());
+        else uj_tile_tab<K, 1, 2, true>(tile, n, tx1, ty1, tz1, acc1, a.shortcut, tab_global<K>(), nsplit, ph);
+      }
+    } else if (two) {
       uj_tile<K, 2, 1, false, true>(tile, n, tx2, ty2, tz2, acc, a.shortcut, gtab, nsplit, ph);
     } else {
       double (&acc1)[1][kAcc] = *reinterpret_cast<double (*)[1][kAcc]>(&acc[0]);
