@@ -35,6 +35,15 @@ for ncrit in [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else 
     print(f"n={n} ncrit={ncrit} leaves={len(sizes)} mean={sizes.mean():.0f} max={sizes.max()} list={len(dl)} "
           f"interactions={pairs:.3e} host-build={t_build:.1f}s | call {dt*1e3:.1f} ms (h2d {tm['h2d_ms']:.1f} kernel {tm['uj_ms']:.1f} d2h {tm['d2h_ms']:.1f}) "
           f"-> kernel {pairs / tm['uj_ms'] / 1e6:.1f} G/s, e2e {pairs / dt / 1e9:.1f} G/s", flush=True)
+    if len(sys.argv) > 4 and sys.argv[4] == "estr":  # Estr_fmm! over the same list (SFS leaf kernel)
+        vpm.fields.random_results(pf, scale=1e-2)
+        for rep in range(2):
+            t = time.perf_counter()
+            vpm.Estr_fmm(pf, order, order, leaves, leaves, dl)
+            dt = time.perf_counter() - t
+        tm = h.timing()
+        print(f"   Estr_fmm: call {dt*1e3:.1f} ms (h2d {tm['h2d_ms']:.1f} kernel {tm['sfs_ms']:.1f} d2h {tm['d2h_ms']:.1f}) "
+              f"-> kernel {pairs / tm['sfs_ms'] / 1e6:.1f} G/s", flush=True)
     if len(sys.argv) > 4 and sys.argv[4] == "zeta":  # the zeta_fmm leaf kernel (SFS-family tile producer)
         for rep in range(2):
             t = time.perf_counter()
