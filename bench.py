@@ -561,6 +561,18 @@ def main():
                          "roofline_frac": n * n / (np.mean(skms) * 1e-3) * F_SFS[args.kernel] / 1e12 / peak_tflops}
         extras["by_kernel"] = family_rates(vpm, h, pf, peak_tflops, [k for k in sorted(F_UJ) if k != args.kernel])
         extras["dense_fields"] = dense_fields(vpm, h, peak_tflops)
+        # the constant-bank variant of the headline kernel (VPM_OPT_UJ_CONST: source records through __constant__
+        # memory, 768 per launch -- fewer three-register FP64 instructions; not the default)
+        h.set_option(vpm._cabi.OPT_UJ_CONST, 1)
+        try:
+            cm, ckm = timed_steps(lambda: field.uj(0), 1, 1)
+        finally:
+            h.set_option(vpm._cabi.OPT_UJ_CONST, 0)
+        extras["constant_bank_variant"] = {
+            "kernel": args.kernel, "interactions_per_s": n * n / (np.mean(cm) * 1e-3), "ms": float(np.mean(cm)),
+            "roofline_frac": n * n / (np.mean(cm) * 1e-3) * F_UJ[args.kernel] / 1e12 / peak_tflops,
+            "launches_per_sweep": h.timing()["kernel_launches"],
+            "what": "vpm_set_option(VPM_OPT_UJ_CONST, 1); whole sweep (all its launches) on the device clock"}
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import smalln_bench
         extras["small_n_latency"] = {"what": "one UJ_direct(pfield; sfs=true, reset=true, reset_sfs=true) call, wall clock "
