@@ -392,7 +392,7 @@ int vpm_uj_direct_st(vpm_handle *h, const double *S, int64_t nfs, int64_t nps, d
   f.nt = npt; f.out = (double *)d.res18.p; f.ld = RES_ROWS; f.urow = RES_U; f.jrow = RES_J;
   f.zrow0 = -1; f.zrow1 = -1; f.want_U = 1; f.want_J = 1; f.accumulate = 1; f.reset = 0;
   f.stat = nullptr; f.sld = 1;
-  uj_finish_kernel<<<blocks_for(npt, 256), 256, 0, st>>>(f);
+  launch_uj_finish(f, st);
   h->launches++;
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(d.ev[3], st));
@@ -439,7 +439,7 @@ int vpm_p2p_buffers(vpm_handle *h, double *tgt, int64_t ld, int64_t t0, int64_t 
   f.nt = nt; f.out = (double *)d.tbuf.p; f.ld = ld; f.urow = row_grad; f.jrow = row_hess;
   f.zrow0 = -1; f.zrow1 = -1; f.want_U = want_U; f.want_J = want_J; f.accumulate = 1; f.reset = 0;
   f.stat = nullptr; f.sld = 1;
-  uj_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+  launch_uj_finish(f, st);
   h->launches++;
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(d.ev[3], st));
@@ -475,7 +475,7 @@ int vpm_uj_device(vpm_handle *h, const double *d_src8, int64_t ns, int64_t t0, i
   f.nt = nt; f.out = d_out12; f.ld = 12; f.urow = 0; f.jrow = 3;
   f.zrow0 = -1; f.zrow1 = -1; f.want_U = 1; f.want_J = 1; f.accumulate = 0; f.reset = 0;
   f.stat = nullptr; f.sld = 1;
-  uj_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+  launch_uj_finish(f, st);
   h->launches++;
   CK(h, cudaGetLastError());
   TRY(scratch_release_async(h, d, st));

@@ -48,7 +48,7 @@ int field_uj(vpm_handle *h, int kernel, int flags) {
       f.nt = nt; f.out = F + t0 * nf; f.ld = nf; f.urow = R_U; f.jrow = R_J; f.zrow0 = R_W; f.zrow1 = R_PSE;
       f.want_U = 1; f.want_J = 1; f.accumulate = 1; f.reset = (flags & VPM_FLAG_RESET) ? 1 : 0;
       f.stat = F + t0 * nf + R_STATIC; f.sld = nf;
-      uj_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+      launch_uj_finish(f, st);
       h->launches++;
       CK(h, cudaGetLastError());
     }

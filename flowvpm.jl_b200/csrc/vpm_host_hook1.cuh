@@ -397,7 +397,7 @@ int h1_eval(vpm_handle *h, Dev &d, int64_t np, int kernel, int flags, bool has_s
       // nothing uploaded: vorticity / PSE rows of the block must still be defined
       CK(h, cudaMemsetAsync(d.res18.p, 0, (size_t)np * RES_ROWS * sizeof(double), st));
     }
-    uj_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(f);
+    launch_uj_finish(f, st);
     h->launches++;
     CK(h, cudaGetLastError());
   }

@@ -196,7 +196,7 @@ int uj_direct_multi(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
       f.zrow0 = RES_W; f.zrow1 = RES_PSE; f.want_U = 1; f.want_J = 1;
       f.accumulate = prior ? 1 : 0; f.reset = reset ? 1 : 0;
       f.stat = has_static ? (const double *)d.stat.p + t0 : nullptr; f.sld = 1;
-      uj_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+      launch_uj_finish(f, st);
       h->launches++;
       CK(h, cudaGetLastError());
     }

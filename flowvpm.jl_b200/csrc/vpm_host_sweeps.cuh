@@ -38,6 +38,17 @@ Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind, int variant 
   return p;
 }
 
+unsigned blocks_for(int64_t n, int threads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
+
+// finish kernel of a U/J sweep: many splits on a small field -> the wide form (one thread per target and accumulator)
+void launch_uj_finish(const UjFinishArgs &f, cudaStream_t st) {
+  if (f.nt <= 0) return;
+  if (f.nsplit >= 4 && f.nt <= (1 << 17))
+    uj_finish_wide_kernel<<<blocks_for(f.nt, kFinishWideTargets), 256, 0, st>>>(f);
+  else
+    uj_finish_kernel<<<blocks_for(f.nt, 256), 256, 0, st>>>(f);
+}
+
 constexpr double kTabNearFraction = 0.40;  // automatic choice: table kernel from this share of sampled warps with a near pair on
 
 // Plan of the table kernel (vpm_kernels_tab.cuh): one CTA per SM, 512 (or 384) threads x 2 targets.
@@ -146,7 +157,6 @@ void launch_sfs(int kernel, const Plan &p, const SfsArgs &a, cudaStream_t st, in
   }
 }
 
-unsigned blocks_for(int64_t n, int threads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
 
 // U/J sweep: records from `src` columns [s0, s0+ns), targets tpos[0..nt), partial
 // sums left in d.partial; the caller runs the finish kernel with its own output.
@@ -210,7 +220,7 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
   if (!use_tab) plan = make_plan(nt, ns, d.sm_count, PLAN_UJ, h->opt_uj_variant < 30 ? h->opt_uj_variant : 0);
   if (use_const) plan.nsplit = 1;  // the constant-bank form keeps ONE set of sums across its launches
   TRY(ensure(h, d.partial, (size_t)plan.nsplit * kAcc * plan.pstride * sizeof(double)));
-  if (use_tab)
+  if (use_tab || (kernel == K_GERF && !use_const))  // kPairsTab: uj_pairs_kernel<gaussianerf> reads the G(u) rows too
     prep_uj_records_tab<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, s0, ns, ns_pad, kernel, (double *)d.rec.p);
   else
     prep_uj_records<<<blocks_for(ns_pad, 256), 256, 0, st>>>(src, s0, ns, ns_pad, kernel, (double *)d.rec.p);

@@ -469,12 +469,19 @@ struct UjArgs {
   int shortcut;        // far-field shortcut for gaussian / gaussianerf
 };
 
+// The gaussianerf family evaluates its tiles from the G(u) table rows of vpm_kernels_tab.cuh (included after this
+// header), read through L1: the pair kernel calls through this hook, defined there.  Records: prep_uj_records_tab.
+template <int K, int T, int UNROLL> struct PairTileTab;
+template <int K>
+constexpr bool kPairsTab = K == K_GERF;
+
 template <int K, int T, int UNROLL>
 __global__ void __launch_bounds__(kThreads, (T == 1 ? 6 : T == 2 ? 4 : T == 3 ? 3 : 2)) uj_pairs_kernel(const UjArgs a) {
   __shared__ __align__(128) double tiles[kStages][kTile * kRec];
   __shared__ __align__(8) uint64_t full[kStages];
-  __shared__ __align__(16) double2 gtab[K == K_GERF ? kGerfIntervals * kGerfCoeffs / 2 : 1];
-  if constexpr (K == K_GERF) load_gerf_table(gtab);  // visible after the __syncthreads below
+  constexpr bool kStageGerf = K == K_GERF && !kPairsTab<K>;
+  __shared__ __align__(16) double2 gtab[kStageGerf ? kGerfIntervals * kGerfCoeffs / 2 : 1];
+  if constexpr (kStageGerf) load_gerf_table(gtab);  // visible after the __syncthreads below
 
   const int tid = threadIdx.x;
   const int64_t tbase = (int64_t)blockIdx.x * (kThreads * T);
@@ -526,7 +533,8 @@ __global__ void __launch_bounds__(kThreads, (T == 1 ? 6 : T == 2 ? 4 : T == 3 ? 
     const int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
     const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
 
-    uj_tile<K, T, UNROLL>(tile, n, tx, ty, tz, acc, a.shortcut, gtab);
+    if constexpr (kPairsTab<K>) PairTileTab<K, T, UNROLL>::run(tile, n, tx, ty, tz, acc, a.shortcut);
+    else uj_tile<K, T, UNROLL>(tile, n, tx, ty, tz, acc, a.shortcut, gtab);
     __syncthreads();  // everyone is done reading stage st
     if (tid == 0 && it + kStages < ntl) issue(it + kStages);
   }
@@ -607,17 +615,8 @@ struct UjFinishArgs {
   int64_t sld;
 };
 
-__global__ void uj_finish_kernel(const UjFinishArgs a) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.nt) return;
-  double s[kAcc];
-#pragma unroll
-  for (int k = 0; k < kAcc; ++k) s[k] = 0.0;
-  for (int sp = 0; sp < a.nsplit; ++sp) {
-    const double *p = a.partial + (int64_t)sp * kAcc * a.pstride + i;
-#pragma unroll
-    for (int k = 0; k < kAcc; ++k) s[k] += p[(int64_t)k * a.pstride];
-  }
+// rows of target i from its 14 sums (reset / accumulate / static rules: src/FLOWVPM_particlefield.jl:464-511)
+__device__ __forceinline__ void uj_finish_write(const UjFinishArgs &a, int64_t i, const double (&s)[kAcc]) {
   double U[3], J[9];
   finish_sums(s, U, J);
   double *o = a.out + i * a.ld;
@@ -634,6 +633,46 @@ __global__ void uj_finish_kernel(const UjFinishArgs a) {
   if (a.reset && !is_static) {
     if (a.zrow0 >= 0) { o[a.zrow0] = 0.0; o[a.zrow0 + 1] = 0.0; o[a.zrow0 + 2] = 0.0; }
     if (a.zrow1 >= 0) { o[a.zrow1] = 0.0; o[a.zrow1 + 1] = 0.0; o[a.zrow1 + 2] = 0.0; }
+  }
+}
+
+__global__ void uj_finish_kernel(const UjFinishArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nt) return;
+  double s[kAcc];
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) s[k] = 0.0;
+  for (int sp = 0; sp < a.nsplit; ++sp) {
+    const double *p = a.partial + (int64_t)sp * kAcc * a.pstride + i;
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) s[k] += p[(int64_t)k * a.pstride];
+  }
+  uj_finish_write(a, i, s);
+}
+
+// Small fields: the sources are split many ways to fill the machine (4 900 targets: 39 splits) and one thread per
+// target would walk 14 x nsplit partial sums on ~20 CTAs (50 us of a 390 us call).  Here a CTA owns 16 targets:
+// thread (k, t) adds the splits of accumulator k of target t, in the same order (the sums are bit-identical),
+// the 16 x 14 sums meet in shared memory and 16 threads write the rows.
+constexpr int kFinishWideTargets = 16;
+__global__ void __launch_bounds__(256) uj_finish_wide_kernel(const UjFinishArgs a) {
+  __shared__ double sums[kFinishWideTargets][kAcc + 1];
+  const int t = threadIdx.x & (kFinishWideTargets - 1), k = threadIdx.x / kFinishWideTargets;
+  const int64_t i = (int64_t)blockIdx.x * kFinishWideTargets + t;
+  if (k < kAcc && i < a.nt) {
+    const double *p = a.partial + (int64_t)k * a.pstride + i;
+    const int64_t step = (int64_t)kAcc * a.pstride;
+    double s = 0.0;
+#pragma unroll 4
+    for (int sp = 0; sp < a.nsplit; ++sp) s += p[sp * step];
+    sums[t][k] = s;
+  }
+  __syncthreads();
+  if (k == 0 && i < a.nt) {
+    double s[kAcc];
+#pragma unroll
+    for (int q = 0; q < kAcc; ++q) s[q] = sums[t][q];
+    uj_finish_write(a, i, s);
   }
 }
 

@@ -313,6 +313,16 @@ __device__ __forceinline__ void uj_tile_tab(const double2 *__restrict__ tile, in
   }
 }
 
+// hook of uj_pairs_kernel (vpm_kernels.cuh): 128-thread CTAs, table rows through L1
+template <int K, int T, int UNROLL>
+struct PairTileTab {
+  static __device__ __forceinline__ void run(const double2 *__restrict__ tile, int n, const double (&tx)[T],
+                                             const double (&ty)[T], const double (&tz)[T],
+                                             double (&acc)[T][kAcc], int shortcut) {
+    uj_tile_tab<K, T, UNROLL, false>(tile, n, tx, ty, tz, acc, shortcut, tab_global<K>());
+  }
+};
+
 // Same contract as uj_pairs_kernel (UjArgs, partial sums [split][kAcc][pstride]); one CTA =
 // 512 threads x 2 targets against one contiguous range of source tiles.  Dynamic shared
 // memory: [table copies][kStages tiles][mbarriers].
