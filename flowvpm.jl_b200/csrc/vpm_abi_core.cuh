@@ -507,7 +507,7 @@ int vpm_sfs_device(vpm_handle *h, const double *d_src8, const double *d_J9, cons
   f.nt = nt; f.tindex = nullptr; f.out = d_out3; f.ld = 3; f.row = 0; f.accumulate = 0; f.reset = 0;
   f.filter_static = 0;  // static targets get an (ignored) value; the caller masks them
   f.stat = nullptr; f.sld = 1;
-  sfs_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+  launch_sfs_finish(f, st);
   h->launches++;
   CK(h, cudaGetLastError());
   TRY(scratch_release_async(h, d, st));

@@ -415,7 +415,7 @@ int vpm_zeta_direct(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
   f.nt = np; f.tindex = nullptr; f.out = (double *)d.sfs3.p; f.ld = 3; f.row = 0;
   f.accumulate = 0; f.reset = 0;  // zeta_direct zeroes J[1:3] of every particle first (:487-489)
   f.filter_static = 0; f.stat = nullptr; f.sld = 1;
-  sfs_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(f);
+  launch_sfs_finish(f, st);
   h->launches++;
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(d.ev[4], st));

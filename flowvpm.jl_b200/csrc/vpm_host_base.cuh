@@ -43,6 +43,7 @@ struct Plan {
   int unroll = 2;
   int nsplit = 1;
   int tiles_per_split = 1;
+  int64_t src_per_split = 0;  // sources per split of the 128-thread FP64 kernels (tiles_per_split * kTile, or finer)
   int64_t pstride = 0;
   dim3 grid;
 };

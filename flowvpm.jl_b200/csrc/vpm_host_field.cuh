@@ -71,7 +71,7 @@ int field_uj(vpm_handle *h, int kernel, int flags) {
         q.nt = nt; q.tindex = nullptr; q.out = F + t0 * nf; q.ld = nf; q.row = R_SFS; q.accumulate = 1;
         q.reset = (flags & VPM_FLAG_RESET_SFS) ? 1 : 0; q.filter_static = 1;
         q.stat = F + t0 * nf + R_STATIC; q.sld = nf;
-        sfs_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(q);
+        launch_sfs_finish(q, st);
         h->launches++;
         CK(h, cudaGetLastError());
       }
@@ -118,7 +118,7 @@ int field_zeta(vpm_handle *h, int kernel) {
       q.partial = (const double *)d.partial.p; q.pstride = sp.pstride; q.nsplit = sp.nsplit;
       q.nt = nt; q.tindex = nullptr; q.out = F + t0 * nf; q.ld = nf; q.row = R_J; q.accumulate = 0; q.reset = 0;
       q.filter_static = 0; q.stat = nullptr; q.sld = 1;
-      sfs_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(q);
+      launch_sfs_finish(q, st);
       h->launches++;
       CK(h, cudaGetLastError());
     }

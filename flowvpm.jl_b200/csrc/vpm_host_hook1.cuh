@@ -415,7 +415,7 @@ int h1_eval(vpm_handle *h, Dev &d, int64_t np, int kernel, int flags, bool has_s
     f.accumulate = 1;  // sfs3 holds either the uploaded rows or (below) zeros
     f.reset = (flags & VPM_FLAG_RESET_SFS) ? 1 : 0;
     f.filter_static = 1; f.stat = stat; f.sld = 1;
-    sfs_finish_kernel<<<blocks_for(np, 256), 256, 0, st>>>(f);
+    launch_sfs_finish(f, st);
     h->launches++;
     CK(h, cudaGetLastError());
     h->timing.sfs_pairs = np * np;

@@ -231,7 +231,7 @@ int uj_direct_multi(vpm_handle *h, double *P, int64_t nf, int64_t np, int kernel
         f.nt = nt; f.tindex = nullptr; f.out = (double *)d.sfs3.p + t0 * 3; f.ld = 3; f.row = 0;
         f.accumulate = 1; f.reset = (flags & VPM_FLAG_RESET_SFS) ? 1 : 0;
         f.filter_static = 1; f.stat = stat ? stat + t0 : nullptr; f.sld = 1;
-        sfs_finish_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(f);
+        launch_sfs_finish(f, st);
         h->launches++;
         CK(h, cudaGetLastError());
       }

@@ -10,6 +10,7 @@ namespace {
 enum PlanKind { PLAN_UJ = 0, PLAN_SFS = 1, PLAN_UJ_F32 = 2 };
 // `variant`: 0 = automatic, else the validated value of VPM_OPT_UJ_VARIANT / VPM_OPT_SFS_VARIANT
 // ("<T><unroll>"; the plan is built FROM it, so grid and kernel always agree).
+constexpr int64_t kMinSrcPerSplit = 16, kMaxSmallSplits = 32;
 Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind, int variant = 0) {
   Plan p;
   const int64_t ntiles = std::max<int64_t>(1, (ns + kTile - 1) / kTile);
@@ -33,6 +34,25 @@ Plan make_plan(int64_t nt, int64_t ns, int sm_count, PlanKind kind, int variant 
   nsplit = std::min<int64_t>(nsplit, 1024);
   p.tiles_per_split = (int)((ntiles + nsplit - 1) / nsplit);
   p.nsplit = (int)((ntiles + p.tiles_per_split - 1) / p.tiles_per_split);
+  p.src_per_split = (int64_t)p.tiles_per_split * kTile;
+  // Small fields: with one tile per split and still less than one wave of CTAs (900 particles: 8 x 8 CTAs on 148
+  // SMs, each walking 128 sources with one warp per scheduler to hide its latencies) the FP64 kernels split the
+  // sources finer than a tile, down to kMinSrcPerSplit per CTA, until one wave is full.
+  // The same freedom evens out fields of a few waves: 4 900 particles are 39 x 39 = 1 521 CTAs = 1.7 waves of 888;
+  // 45 splits of 109 sources make it 1 755 = 1.98 waves of smaller CTAs.
+  const int64_t one_wave = (int64_t)sm_count * ctas_per_sm;
+  if (kind != PLAN_UJ_F32 && p.tiles_per_split == 1 && nblk * p.nsplit < 4 * one_wave) {
+    const int64_t waves = std::max<int64_t>(1, (nblk * p.nsplit + one_wave - 1) / one_wave);
+    const int64_t ws = std::max<int64_t>(1, waves * one_wave / nblk);  // splits that fill `waves` waves
+    int64_t sps = std::max<int64_t>(kMinSrcPerSplit, (std::max<int64_t>(ns, 1) + ws - 1) / ws);
+    // below one wave more splits only lengthen the finish kernel's sums: at most kMaxSmallSplits of them
+    // (measured: 900 particles 57 splits 93 us per call, 29-32 splits 86 us; 200 particles 13 splits 63 us, 7: 74 us)
+    if (nblk * p.nsplit < one_wave) sps = std::max<int64_t>(sps, (std::max<int64_t>(ns, 1) + kMaxSmallSplits - 1) / kMaxSmallSplits);
+    if (sps < kTile) {
+      p.src_per_split = sps;
+      p.nsplit = (int)((std::max<int64_t>(ns, 1) + sps - 1) / sps);
+    }
+  }
   p.pstride = round_up(std::max<int64_t>(nt, 1), 32);
   p.grid = dim3((unsigned)nblk, (unsigned)p.nsplit, 1);
   return p;
@@ -47,6 +67,14 @@ void launch_uj_finish(const UjFinishArgs &f, cudaStream_t st) {
     uj_finish_wide_kernel<<<blocks_for(f.nt, kFinishWideTargets), 256, 0, st>>>(f);
   else
     uj_finish_kernel<<<blocks_for(f.nt, 256), 256, 0, st>>>(f);
+}
+
+void launch_sfs_finish(const SfsFinishArgs &f, cudaStream_t st) {
+  if (f.nt <= 0) return;
+  if (f.nsplit >= 4 && f.nt <= (1 << 17))
+    sfs_finish_wide_kernel<<<blocks_for(f.nt, 64), 256, 0, st>>>(f);
+  else
+    sfs_finish_kernel<<<blocks_for(f.nt, 256), 256, 0, st>>>(f);
 }
 
 constexpr double kTabNearFraction = 0.40;  // automatic choice: table kernel from this share of sampled warps with a near pair on
@@ -72,6 +100,7 @@ Plan make_plan_tab(int64_t nt, int64_t ns, int sm_count, bool *fills, int varian
   nsplit = std::min<int64_t>(nsplit, 1024);
   p.tiles_per_split = (int)((ntiles + nsplit - 1) / nsplit);
   p.nsplit = (int)((ntiles + p.tiles_per_split - 1) / p.tiles_per_split);
+  p.src_per_split = (int64_t)p.tiles_per_split * kTile;
   p.pstride = round_up(std::max<int64_t>(nt, 1), 32);
   p.grid = dim3((unsigned)nblk, (unsigned)p.nsplit, 1);
   return p;
@@ -245,6 +274,7 @@ int uj_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *t
     a.tpos = tpos; a.tld = tld; a.nt = nt;
     a.rec = (const double *)d.rec.p; a.ns = ns;
     a.tiles_per_split = plan.tiles_per_split;
+    a.src_per_split = plan.src_per_split;
     a.partial = (double *)d.partial.p; a.pstride = plan.pstride;
     a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;
     if (time_pairs) CK(h, cudaEventRecord(d.ev[6], st));
@@ -278,7 +308,7 @@ int sfs_sweep(vpm_handle *h, Dev &d, cudaStream_t st, int kernel, const double *
     SfsArgs a;
     a.tpos = tpos; a.tld = tld; a.tJ = tJ; a.jld = jld; a.tindex = tindex; a.nt = nt;
     a.rec = (const double *)d.srec.p; a.ns = ns;
-    a.tiles_per_split = plan.tiles_per_split;
+    a.src_per_split = plan.src_per_split;
     a.partial = (double *)d.partial.p; a.pstride = plan.pstride;
     a.transposed = transposed;
     a.shortcut = (flags & VPM_FLAG_NO_FARFIELD_SHORTCUT) ? 0 : 1;

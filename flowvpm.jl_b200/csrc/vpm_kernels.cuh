@@ -463,7 +463,8 @@ struct UjArgs {
   int64_t nt;
   const double *rec;   // source records [ns_pad][kRec]
   int64_t ns;
-  int tiles_per_split;
+  int tiles_per_split;  // (table and FP32 kernels: tile-aligned splits)
+  int64_t src_per_split;  // uj_pairs_kernel: sources of one split (any count: small fields split finer than a tile)
   double *partial;     // [nsplit][kAcc][pstride]
   int64_t pstride;
   int shortcut;        // far-field shortcut for gaussian / gaussianerf
@@ -482,6 +483,9 @@ __global__ void __launch_bounds__(kThreads, (T == 1 ? 6 : T == 2 ? 4 : T == 3 ? 
   constexpr bool kStageGerf = K == K_GERF && !kPairsTab<K>;
   __shared__ __align__(16) double2 gtab[kStageGerf ? kGerfIntervals * kGerfCoeffs / 2 : 1];
   if constexpr (kStageGerf) load_gerf_table(gtab);  // visible after the __syncthreads below
+  // the table rows come through L1: ask for all of its lines at once while the first tile is on its way (a small
+  // field is one short wave of CTAs on cold caches: 900 particles, 48 -> 38 us per sweep)
+  if constexpr (kPairsTab<K>) PairTileTab<K, T, UNROLL>::prefetch();
 
   const int tid = threadIdx.x;
   const int64_t tbase = (int64_t)blockIdx.x * (kThreads * T);
@@ -500,11 +504,11 @@ __global__ void __launch_bounds__(kThreads, (T == 1 ? 6 : T == 2 ? 4 : T == 3 ? 
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) acc[t][k] = 0.0;
 
-  const int64_t ntiles = (a.ns + kTile - 1) / kTile;
-  const int64_t tile0 = (int64_t)blockIdx.y * a.tiles_per_split;
-  int64_t tile1 = tile0 + a.tiles_per_split;
-  if (tile1 > ntiles) tile1 = ntiles;
-  const int ntl = tile1 > tile0 ? (int)(tile1 - tile0) : 0;
+  // this CTA's sources: [s_begin, s_end), walked in tiles of <= kTile records
+  const int64_t s_begin = (int64_t)blockIdx.y * a.src_per_split;
+  int64_t s_end = s_begin + a.src_per_split;
+  if (s_end > a.ns) s_end = a.ns;
+  const int ntl = s_end > s_begin ? (int)((s_end - s_begin + kTile - 1) / kTile) : 0;
 
   if (tid == 0) {
 #pragma unroll
@@ -514,9 +518,8 @@ __global__ void __launch_bounds__(kThreads, (T == 1 ? 6 : T == 2 ? 4 : T == 3 ? 
   __syncthreads();
 
   auto issue = [&](int it) {
-    int64_t tile = tile0 + it;
-    int64_t first = tile * kTile;
-    int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
+    int64_t first = s_begin + (int64_t)it * kTile;
+    int n = (int)((s_end - first) < kTile ? (s_end - first) : kTile);
     uint32_t bytes = (uint32_t)n * kRec * sizeof(double);
     int st = it % kStages;
     mbar_expect_tx(&full[st], bytes);
@@ -529,8 +532,8 @@ __global__ void __launch_bounds__(kThreads, (T == 1 ? 6 : T == 2 ? 4 : T == 3 ? 
   for (int it = 0; it < ntl; ++it) {
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
-    const int64_t first = (tile0 + it) * kTile;
-    const int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
+    const int64_t first = s_begin + (int64_t)it * kTile;
+    const int n = (int)((s_end - first) < kTile ? (s_end - first) : kTile);
     const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
 
     if constexpr (kPairsTab<K>) PairTileTab<K, T, UNROLL>::run(tile, n, tx, ty, tz, acc, a.shortcut);
@@ -757,7 +760,7 @@ struct SfsArgs {
   int64_t nt;
   const double *rec;
   int64_t ns;
-  int tiles_per_split;
+  int64_t src_per_split;  // sources of one split (any count, as UjArgs)
   double *partial;     // [nsplit][3][pstride]
   int64_t pstride;
   int transposed;
@@ -795,11 +798,10 @@ __global__ void __launch_bounds__(kThreads) sfs_pairs_kernel(const SfsArgs a) {
     acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
   }
 
-  const int64_t ntiles = (a.ns + kTile - 1) / kTile;
-  const int64_t tile0 = (int64_t)blockIdx.y * a.tiles_per_split;
-  int64_t tile1 = tile0 + a.tiles_per_split;
-  if (tile1 > ntiles) tile1 = ntiles;
-  const int ntl = tile1 > tile0 ? (int)(tile1 - tile0) : 0;
+  const int64_t s_begin = (int64_t)blockIdx.y * a.src_per_split;  // as uj_pairs_kernel
+  int64_t s_end = s_begin + a.src_per_split;
+  if (s_end > a.ns) s_end = a.ns;
+  const int ntl = s_end > s_begin ? (int)((s_end - s_begin + kTile - 1) / kTile) : 0;
 
   if (tid == 0) {
 #pragma unroll
@@ -809,8 +811,8 @@ __global__ void __launch_bounds__(kThreads) sfs_pairs_kernel(const SfsArgs a) {
   __syncthreads();
 
   auto issue = [&](int it) {
-    int64_t first = (tile0 + it) * kTile;
-    int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
+    int64_t first = s_begin + (int64_t)it * kTile;
+    int n = (int)((s_end - first) < kTile ? (s_end - first) : kTile);
     uint32_t bytes = (uint32_t)n * kSfsRec * sizeof(double);
     int st = it % kStages;
     mbar_expect_tx(&full[st], bytes);
@@ -823,8 +825,8 @@ __global__ void __launch_bounds__(kThreads) sfs_pairs_kernel(const SfsArgs a) {
   for (int it = 0; it < ntl; ++it) {
     const int st = it % kStages;
     mbar_wait(&full[st], (uint32_t)((it / kStages) & 1));
-    const int64_t first = (tile0 + it) * kTile;
-    const int n = (int)((a.ns - first) < kTile ? (a.ns - first) : kTile);
+    const int64_t first = s_begin + (int64_t)it * kTile;
+    const int n = (int)((s_end - first) < kTile ? (s_end - first) : kTile);
     const double2 *tile = reinterpret_cast<const double2 *>(&tiles[st][0]);
 
     sfs_tile<K, T, MODE>(tile, n, tx, ty, tz, JT, acc, a.shortcut);
@@ -879,6 +881,25 @@ __global__ void sfs_finish_kernel(const SfsFinishArgs a) {
   o[0] = (keep ? o[0] : 0.0) + s0;
   o[1] = (keep ? o[1] : 0.0) + s1;
   o[2] = (keep ? o[2] : 0.0) + s2;
+}
+
+// small fields (many source splits, few targets): one thread per target and component, as uj_finish_wide_kernel;
+// the splits are added in the same order, so the sums are bit-identical to sfs_finish_kernel's
+__global__ void __launch_bounds__(256) sfs_finish_wide_kernel(const SfsFinishArgs a) {
+  const int t = threadIdx.x & 63, k = threadIdx.x >> 6;  // 64 targets x (3 components + 1 idle quarter)
+  const int64_t i = (int64_t)blockIdx.x * 64 + t;
+  if (k >= 3 || i >= a.nt) return;
+  const int64_t c = a.tindex ? a.tindex[i] : i;
+  const bool is_static = a.stat != nullptr && a.stat[c * a.sld] != 0.0;
+  if (is_static && a.filter_static) return;
+  const double *p = a.partial + (int64_t)k * a.pstride + i;
+  const int64_t step = 3 * a.pstride;
+  double s = 0.0;
+#pragma unroll 4
+  for (int sp = 0; sp < a.nsplit; ++sp) s += p[sp * step];
+  double *o = a.out + c * a.ld + a.row + k;
+  const bool keep = a.accumulate && !(a.reset && !is_static);
+  *o = (keep ? *o : 0.0) + s;
 }
 
 // reset-only (reset_sfs without sfs): zero SFS rows of non-static particles

@@ -321,6 +321,12 @@ struct PairTileTab {
                                              double (&acc)[T][kAcc], int shortcut) {
     uj_tile_tab<K, T, UNROLL, false>(tile, n, tx, ty, tz, acc, shortcut, tab_global<K>());
   }
+  static __device__ __forceinline__ void prefetch() {
+    const char *base = reinterpret_cast<const char *>(TabOf<K>::words());
+    constexpr int kLines = (TabOf<K>::rows * kTabRowChunks * 16 + 127) / 128;
+    for (int i = threadIdx.x; i < kLines; i += blockDim.x)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)i * 128));
+  }
 };
 
 // Same contract as uj_pairs_kernel (UjArgs, partial sums [split][kAcc][pstride]); one CTA =
