@@ -32,11 +32,11 @@ int ensure_stage(vpm_handle *h, size_t doubles) {
 
 // The O(N) host loops over the particle matrix (strided gathers / scatters, the static-flag
 // scan) are memory-latency bound on one core: at 2^24 particles they cost 0.1 s each.  Split
-// them over a few threads (chunks of >= 8 Ki particles: a thread costs ~50 us to start and copies ~8 Ki columns of
-// 18 rows in that time; small fields stay on the caller's thread).
+// them over a few threads (chunks of >= 64 Ki particles; small fields stay on the caller's thread: starting
+// threads for 8 Ki-particle chunks was measured 4 x SLOWER at 33 800 particles, 65 -> 310 us for the upload half).
 template <class F>
 void parallel_chunks(int64_t n, F fn) {
-  const int64_t min_chunk = 1 << 13;
+  const int64_t min_chunk = 1 << 16;
   unsigned hw = std::thread::hardware_concurrency();
   int nt = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, 8), n / min_chunk);
   if (nt <= 1) { fn((int64_t)0, n); return; }
