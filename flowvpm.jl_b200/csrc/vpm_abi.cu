@@ -8,6 +8,7 @@
 #include "../../include/vpm_cuda.h"
 
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -18,6 +19,9 @@
 #include <atomic>
 #include <chrono>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 

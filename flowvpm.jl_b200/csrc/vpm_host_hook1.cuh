@@ -30,22 +30,108 @@ int ensure_stage(vpm_handle *h, size_t doubles) {
   return VPM_OK;
 }
 
-// The O(N) host loops over the particle matrix (strided gathers / scatters, the static-flag
-// scan) are memory-latency bound on one core: at 2^24 particles they cost 0.1 s each.  Split
-// them over a few threads (chunks of >= 64 Ki particles; small fields stay on the caller's thread: starting
-// threads for 8 Ki-particle chunks was measured 4 x SLOWER at 33 800 particles, 65 -> 310 us for the upload half).
-template <class F>
-void parallel_chunks(int64_t n, F fn) {
-  const int64_t min_chunk = 1 << 16;
-  unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, 8), n / min_chunk);
-  if (nt <= 1) { fn((int64_t)0, n); return; }
-  std::vector<std::thread> th;
-  const int64_t chunk = (n + nt - 1) / nt;
-  for (int t = 1; t < nt; ++t) th.emplace_back([=] { fn(t * chunk, std::min<int64_t>(n, (t + 1) * chunk)); });
-  fn((int64_t)0, std::min<int64_t>(n, chunk));
-  for (auto &t : th) t.join();
+// ---- host threads ----------------------------------------------------------------------
+// The O(N) host loops over the particle matrix (strided gathers / scatters, the static-flag scan) and the copies
+// into / out of the pinned ring are memory-latency bound on one core (2^24 particles: 0.1 s each).  They are split
+// over a few threads.  Starting threads per loop costs ~120 us for seven (measured: the upload half of a
+// 33 800-particle call went from 65 to 310 us when its gathers were threaded that way), so the workers are a
+// persistent pool, one per process (handles on different host threads take turns), started on first use.
+class HostPool {
+ public:
+  static HostPool &get() {
+    static HostPool pool;
+    return pool;
+  }
+  int workers() const { return (int)th_.size(); }
+  // runs job(0) .. job(njobs - 1), the caller taking part; returns when all are done
+  void run(int njobs, const std::function<void(int)> &job) {
+    if (njobs <= 1 || th_.empty()) {
+      for (int j = 0; j < njobs; ++j) job(j);
+      return;
+    }
+    std::lock_guard<std::mutex> turn(turn_);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &job; njobs_ = njobs; next_ = 0; left_ = njobs; ++gen_;
+    }
+    go_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [&] { return left_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  HostPool() : pid_(getpid()) {
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n = (int)std::min<unsigned>(hw > 1 ? hw - 1 : 0, 7);
+    for (int t = 0; t < n; ++t) th_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    if (getpid() != pid_) {  // a forked child has no workers to join (run() there does every job on the caller)
+      for (auto &t : th_) t.detach();
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    go_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  void work() {
+    for (;;) {
+      int j;
+      const std::function<void(int)> *job;
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (job_ == nullptr || next_ >= njobs_) return;
+        j = next_++;
+        job = job_;
+      }
+      (*job)(j);
+      std::lock_guard<std::mutex> lk(m_);
+      if (--left_ == 0) done_.notify_all();
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        go_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_, turn_;
+  std::condition_variable go_, done_;
+  const std::function<void(int)> *job_ = nullptr;
+  int njobs_ = 0, next_ = 0, left_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+  pid_t pid_;
+};
+
+// fn(begin, end) over [0, n) in at most 8 contiguous pieces of >= min_chunk items (multiples of `align`)
+template <class I, class F>
+void parallel_ranges(I n, I min_chunk, I align, F fn) {
+  HostPool &pool = HostPool::get();
+  const int nt = (int)std::min<I>((I)(pool.workers() + 1), n / min_chunk);
+  if (nt <= 1) { fn((I)0, n); return; }
+  const I chunk = ((n + nt - 1) / nt + align - 1) / align * align;
+  pool.run(nt, [&](int t) {
+    const I a = (I)t * chunk;
+    if (a < n) fn(a, std::min<I>(n, a + chunk));
+  });
 }
+// particle columns of the host matrix: pieces of >= 64 Ki particles.  (Waking the pool for less does not pay: with
+// 8 Ki-particle pieces the 1.9 MB gather of a 33 800-particle call took 335 us instead of 65 us on one thread.)
+template <class F>
+void parallel_chunks(int64_t n, F fn) { parallel_ranges<int64_t>(n, (int64_t)1 << 16, 1, fn); }
 void gather_rows(double *dst, const double *P, int64_t nf, int row0, int nrows, int64_t np) {
   parallel_chunks(np, [=](int64_t a, int64_t b) {
     for (int64_t i = a; i < b; ++i) memcpy(dst + i * nrows, P + nf * i + row0, (size_t)nrows * sizeof(double));
@@ -98,17 +184,7 @@ bool use_ring(vpm_handle *h, Dev *d, const void *host, size_t bytes) {
   return d && !h->capturing && bytes >= kRingMinBytes && !host_is_pinned(host);
 }
 template <class F>
-void parallel_cols(int64_t n, F fn) {  // as parallel_chunks, finer grain (a ring slot is ~1e5 columns)
-  const int64_t min_chunk = 1 << 14;
-  unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, 8), n / min_chunk);
-  if (nt <= 1) { fn((int64_t)0, n); return; }
-  std::vector<std::thread> th;
-  const int64_t chunk = (n + nt - 1) / nt;
-  for (int t = 1; t < nt; ++t) th.emplace_back([=] { fn(t * chunk, std::min<int64_t>(n, (t + 1) * chunk)); });
-  fn((int64_t)0, std::min<int64_t>(n, chunk));
-  for (auto &t : th) t.join();
-}
+void parallel_cols(int64_t n, F fn) { parallel_ranges<int64_t>(n, (int64_t)1 << 14, 1, fn); }  // columns of a ring slot
 
 // Device columns of `dpitch` bytes <- pieces of the host columns (pitch spitch): piece k is `width[k]` bytes
 // from byte offset soff[k] of the host column to byte offset doff[k] of the device column.  The ring path
@@ -222,18 +298,7 @@ bool host_is_pageable(const void *ptr) {
 }
 constexpr size_t kRingMinContig = 4u << 20;
 template <class F>
-void parallel_bytes(size_t n, F fn) {
-  const size_t min_chunk = 1u << 20;
-  unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)std::min<size_t>(std::min<unsigned>(hw ? hw : 1, 8), n / min_chunk);
-  if (nt <= 1) { fn((size_t)0, n); return; }
-  std::vector<std::thread> th;
-  const size_t chunk = ((n + nt - 1) / nt + 63) & ~(size_t)63;
-  for (int t = 1; t < nt; ++t)
-    th.emplace_back([=] { if ((size_t)t * chunk < n) fn((size_t)t * chunk, std::min(n, (size_t)(t + 1) * chunk)); });
-  fn((size_t)0, std::min(n, chunk));
-  for (auto &t : th) t.join();
-}
+void parallel_bytes(size_t n, F fn) { parallel_ranges<size_t>(n, (size_t)1 << 20, 64, fn); }
 int h2d_contig(vpm_handle *h, cudaStream_t st, void *dst, const void *src, size_t bytes) {
   if (bytes == 0) return VPM_OK;
   Dev *d = dev_of_stream(h, st);
