@@ -154,12 +154,8 @@ int vpm_nearfield_ranges(vpm_handle *h, double *TP, int64_t nf_t, int64_t np_t, 
                     (long long)tb[a], (long long)te[a], (long long)b, (long long)tb[b], (long long)te[b]);
     }
   }
-  // the (target range, source range) list: entry i <-> (owner of k, i) for soff[k] <= i < soff[k+1]
-  std::vector<int32_t> pt((size_t)nsr), ps((size_t)nsr);
-  parallel_chunks(ntr, [&](int64_t k0, int64_t k1) {
-    for (int64_t k = k0; k < k1; ++k)
-      for (int64_t i = soff[k]; i < soff[k + 1]; ++i) { pt[(size_t)i] = (int32_t)owner[(size_t)k]; ps[(size_t)i] = (int32_t)i; }
-  });
+  // the (target range, source range) list: entry i <-> (owner of k, i) for soff[k] <= i < soff[k+1]; generated on
+  // the device from soff and owner (build_csr_device, csr_gen_pairs_kernel)
   h->launches = 0;
   int G = (int)h->devs.size();
   const int TLD = 18;  // device target buffer: rows 0:3 X, rows 3:18 = particle rows 10:24 (U, vorticity, J)
@@ -179,7 +175,8 @@ int vpm_nearfield_ranges(vpm_handle *h, double *TP, int64_t nf_t, int64_t np_t, 
   else TRY(h2d_rows(h, d0.stream, (double *)d0.in7.p, SP, nf_s, 7, np_s));
   CK(h, cudaSetDevice(d0.id));
   DevCsr c;
-  TRY(build_csr_device(h, fn, tb, te, ntr, np_t, sb, se, nsr, np_s, pt.data(), ps.data(), nsr, G, nullptr, 0, nullptr, 0, c));
+  TRY(build_csr_device(h, fn, tb, te, ntr, np_t, sb, se, nsr, np_s, nullptr, nullptr, nsr, G, nullptr, 0, nullptr, 0, c,
+                       false, soff, owner.data()));
   if (c.nwi == 0) return VPM_OK;
   G = c.G_eff;
   std::vector<LeafCsr> csr(G);

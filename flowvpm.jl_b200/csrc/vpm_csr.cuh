@@ -120,6 +120,22 @@ __global__ void csr_wi_fill_kernel(const int64_t *__restrict__ tb, const int64_t
   if (r == ntl - 1) stats[CS_NWI] = o + n;
 }
 
+// The list of vpm_nearfield_ranges generated in place: entry i belongs to the target range k with
+// off[k] <= i < off[k+1] (binary search) and its source "leaf" is the i-th source range itself:
+// pair_tgt[i] = owner[k], pair_src[i] = i.  (Built on the host and uploaded this was 0.7 GB at 2^24 / ncrit 128.)
+__global__ void csr_gen_pairs_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ owner, int64_t ntr,
+                                     int64_t n, int32_t *__restrict__ pair_tgt, int32_t *__restrict__ pair_src) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t lo = 0, hi = ntr;  // invariant: off[lo] <= i < off[hi]
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (off[mid] <= i) lo = mid; else hi = mid;
+  }
+  pair_tgt[i] = (int32_t)owner[lo];
+  pair_src[i] = (int32_t)i;
+}
+
 __global__ void csr_iota_kernel(int32_t *p, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = (int32_t)i;

@@ -47,7 +47,10 @@ LeafCsr rebase_csr(const LeafCsr &c, const void *from, const void *to) {
 int build_csr_device(vpm_handle *h, const char *fn, const int64_t *tb, const int64_t *te, int64_t ntl,
                      int64_t n_tgt, const int64_t *sb, const int64_t *se, int64_t nsl, int64_t n_src,
                      const int32_t *pt, const int32_t *ps, int64_t npairs, int G, const int64_t *tsort,
-                     int64_t n_tsort, const int64_t *ssort, int64_t n_ssort, DevCsr &out, bool dev_in = false) {
+                     int64_t n_tsort, const int64_t *ssort, int64_t n_ssort, DevCsr &out, bool dev_in = false,
+                     const int64_t *gen_off = nullptr, const int64_t *gen_owner = nullptr) {
+  // gen_off / gen_owner (host, ntl + 1 / ntl entries): pt and ps are NULL and the list is generated on the
+  // device (csr_gen_pairs_kernel: the call shape of vpm_nearfield_ranges)
   // O(leaves) checks stay on the host; everything O(list entries) runs on the device.
   // dev_in: the tables are device arrays produced by vpm_leaflists_build (already valid).
   int64_t max_wi = dev_in ? n_tgt / 32 + ntl : 0;
@@ -109,8 +112,19 @@ int build_csr_device(vpm_handle *h, const char *fn, const int64_t *tb, const int
   TRY(put(dte, te, (size_t)ntl));
   TRY(put(dsb, sb, (size_t)nsl));
   TRY(put(dse, se, (size_t)nsl));
-  TRY(put(dpt, pt, (size_t)npairs));
-  TRY(put(dsrc, ps, (size_t)npairs));  // already the CSR column array when the list is grouped
+  if (gen_off) {
+    // (the two small tables live in d.scr2, idle at this point: the unsorted-list branch below takes it over only
+    // after the stream has been synchronised)
+    TRY(ensure(h, d.scr2, (size_t)(2 * ntl + 2) * 8 + 64));
+    int64_t *goff = (int64_t *)d.scr2.p, *gown = goff + (ntl + 1);
+    TRY(put(goff, gen_off, (size_t)ntl + 1));
+    TRY(put(gown, gen_owner, (size_t)ntl));
+    csr_gen_pairs_kernel<<<blocks_for(npairs, 256), 256, 0, st>>>(goff, gown, ntl, npairs, dpt, dsrc);
+    h->launches++;
+  } else {
+    TRY(put(dpt, pt, (size_t)npairs));
+    TRY(put(dsrc, ps, (size_t)npairs));  // already the CSR column array when the list is grouped
+  }
   if (n_tsort) TRY(put(dts, tsort, (size_t)n_tsort));
   if (n_ssort) TRY(put(dss, ssort, (size_t)n_ssort));
   csr_init_stats_kernel<<<1, 32, 0, st>>>(stats);
@@ -128,7 +142,7 @@ int build_csr_device(vpm_handle *h, const char *fn, const int64_t *tb, const int
   if (hs[CS_BAD] != ~0ull) {
     const int64_t k = (int64_t)hs[CS_BAD] - 1;
     return fail(h, VPM_EINVAL, "%s: pair %lld = (%d,%d) outside the leaf tables", fn, (long long)k,
-                dev_in ? -1 : pt[k], dev_in ? -1 : ps[k]);
+                (dev_in || !pt) ? -1 : pt[k], (dev_in || !ps) ? -1 : ps[k]);
   }
   // CTA width: minimise the padded lane-work  sum_leaf ceil(size/NT)*NT * (its source bodies);
   // wider CTAs amortise the tile traffic better: require a 10 % gain to go narrower
