@@ -316,3 +316,56 @@ def test_oracle_pse_is_inviscid_plus_volumes(vpm):
     rows = [r for r in range(46) if r != 7]
     assert np.array_equal(a[rows], b[rows])
     assert np.allclose(a[7, :pf.np], 4 / 3 * np.pi * a[6, :pf.np] ** 3, rtol=1e-15) and not np.array_equal(a[7], b[7])
+
+
+def test_oracle_zeta_fmm_is_the_near_field_of_zeta_direct(vpm):
+    """zeta_fmm (src/FLOWVPM_viscous.jl:523-558) = zeta_direct with the far field neglected: on a compact field whose
+    leaf lists (theta = 0.4) cover every pair with a visible zeta the two agree to rounding; the reference's
+    zeta_fmm ACCUMULATES on J[1:3] (it has no reset), which the restatement reproduces; a list entry (a, b) makes
+    the bodies of leaf b receive from the bodies of leaf a"""
+    pf = vpm.fields.ring_field(Nphi=60, nc=1, kernel=vpm.gaussianerf, R=1.0, Rcross=0.15, sigma=0.12)
+    n = pf.np
+    P = pf.particles.copy(order="F")
+    oracle.zeta_direct(P, n, "gaussianerf")
+    W = P[15:18, :n].copy()
+    Q = pf.particles.copy(order="F")
+    Q[15:18, :n] = 0.0
+    z = oracle.cs_zeta_fmm(ncrit=20, theta=0.4, reset=False)
+    z._eval(Q.ctypes.data, Q.shape[0], n, pf.kernel.id)
+    assert relerr(Q[15:18, :n], W) < 1e-13
+    z._eval(Q.ctypes.data, Q.shape[0], n, pf.kernel.id)          # no reset: the second call doubles the rows
+    assert relerr(Q[15:18, :n], 2 * W) < 1e-13
+    zr = oracle.cs_zeta_fmm(ncrit=20, theta=0.4, reset=True)
+    zr._eval(Q.ctypes.data, Q.shape[0], n, pf.kernel.id)
+    assert relerr(Q[15:18, :n], W) < 1e-13
+    # a tight acceptance criterion drops visible pairs: then the list sum is NOT the direct sum
+    zt = oracle.cs_zeta_fmm(ncrit=5, theta=4.0, reset=True)
+    zt._eval(Q.ctypes.data, Q.shape[0], n, pf.kernel.id)
+    assert relerr(Q[15:18, :n], W) > 1e-6
+
+
+def test_oracle_rbf_with_zeta_fmm_context(vpm):
+    """the RBF restatement with cs.zeta = zeta_fmm installed (what CoreSpreading(nu, sgm0, zeta_fmm) runs): with the
+    rows zeroed per evaluation it converges like the zeta_direct one; with the reference's accumulating zeta_fmm
+    the same iteration does not (residuals grow) -- the behaviour the device path is checked against"""
+    pf = vpm.fields.ring_field(Nphi=60, nc=1, kernel=vpm.gaussianerf, R=1.0, Rcross=0.15, sigma=0.12)
+    n = pf.np
+    G0 = pf.particles[3:6, :n].copy()
+    out = {}
+    for reset in (True, False):
+        P = pf.particles.copy(order="F")
+        with oracle.cs_zeta_fmm(ncrit=20, theta=0.4, reset=reset) as z:
+            P[15:18, :n] = 0.0
+            z._eval(P.ctypes.data, P.shape[0], n, pf.kernel.id)
+            P[33:36, :n] = P[15:18, :n]
+            it, res = oracle.rbf_conjugategradient(P, n, "gaussianerf", itmax=6, tol=1e-6, iterror=False)
+            assert z.calls == it + 2
+        out[reset] = (it, res.max(), relerr(P[3:6, :n], G0))
+    assert out[True][0] < 6 and out[True][1] < 1e-6 and out[True][2] < 1e-4
+    assert out[False][0] == 6 and out[False][1] > 1e-2
+    # the callback is gone after the context: the default is zeta_direct again
+    P = pf.particles.copy(order="F")
+    oracle.zeta_direct(P, n, "gaussianerf")
+    P[33:36, :n] = P[15:18, :n]
+    it, res = oracle.rbf_conjugategradient(P, n, "gaussianerf", itmax=30, tol=1e-6)
+    assert res.max() < 1e-6
