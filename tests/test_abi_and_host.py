@@ -137,6 +137,37 @@ def test_leaf_lists_refine_cells_for_sparse_fields(vpm):
         assert (leaf_of[i], leaf_of[j]) in s
 
 
+@pytest.mark.parametrize("field", ["cloud", "ring", "jet"])
+@pytest.mark.parametrize("theta", [0.25, 0.4, 0.8])
+def test_leaf_lists_equal_brute_force_mac(vpm, field, theta):
+    """the stencil search of the builder (the recipe the device kernel restates) finds exactly the leaf pairs that
+    fail the acceptance criterion (r_i + r_j) <= theta d: compared with all nl^2 pairs tested directly, with the
+    leaf spheres recomputed independently from the sorted bodies"""
+    pf = {"cloud": lambda: vpm.fields.cloud_field(2500, seed=3),
+          "ring": lambda: vpm.fields.ring_field(Nphi=60, nc=2),
+          "jet": lambda: vpm.fields.jet_field(2000)}[field]()
+    n = pf.np
+    X, sig = pf.get_X()[:, :n], pf.get_sigma()[:n]
+    ll = leaflists.build_leaf_lists(X, sig, ncrit=24, theta=theta)
+    b, e, order = ll["leaf_begin"], ll["leaf_end"], ll["sort_index"]
+    nl = len(b)
+    ctr, rad = np.empty((nl, 3)), np.empty(nl)
+    for l in range(nl):
+        xs = X[:, order[b[l]:e[l]]]
+        c = 0.5 * (xs.min(axis=1) + xs.max(axis=1))
+        ctr[l] = c
+        rad[l] = np.sqrt(((xs - c[:, None]) ** 2).sum(axis=0).max()) + sig[order[b[l]:e[l]]].max()
+    d = np.sqrt(((ctr[:, None, :] - ctr[None, :, :]) ** 2).sum(axis=2))
+    near = (d == 0) | ((rad[:, None] + rad[None, :]) > theta * d)
+    want = set(zip(*np.nonzero(near)))
+    got = set(map(tuple, ll["direct_list"].tolist()))
+    # pairs within rounding of the criterion may fall either way between the two evaluations
+    margin = np.abs((rad[:, None] + rad[None, :]) - theta * d) <= 1e-12 * (rad[:, None] + rad[None, :])
+    diff = (want ^ got)
+    assert all(margin[i, j] for (i, j) in diff), (len(want), len(got), len(diff))
+    assert len(got) > nl                                   # more than the self pairs
+
+
 def test_direct_list_forms(vpm):
     """the list-taking wrappers accept the reference's (n, 2) direct_list or a tuple of its columns"""
     from flowvpm_jl_b200 import uj
