@@ -145,7 +145,11 @@ int vpm_nearfield_ranges(vpm_handle *h, double *TP, int64_t nf_t, int64_t np_t, 
       owner[(size_t)k] = k;
       if (soff[k + 1] > soff[k] && te[k] > tb[k]) ord.push_back(k);
     }
-    std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return tb[a] != tb[b] ? tb[a] < tb[b] : te[a] < te[b]; });
+    // (tree-ordered ranges arrive sorted: 270 912 of them at 2^24 / ncrit 128 -- sort only when they are not)
+    auto before = [&](int64_t a, int64_t b) { return tb[a] != tb[b] ? tb[a] < tb[b] : te[a] < te[b]; };
+    bool sorted = true;
+    for (size_t i = 1; i < ord.size() && sorted; ++i) sorted = !before(ord[i], ord[i - 1]);
+    if (!sorted) std::stable_sort(ord.begin(), ord.end(), before);
     for (size_t i = 1; i < ord.size(); ++i) {
       const int64_t a = ord[i - 1], b = ord[i];
       if (tb[a] == tb[b] && te[a] == te[b]) owner[(size_t)b] = owner[(size_t)a];
