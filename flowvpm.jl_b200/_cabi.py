@@ -23,7 +23,7 @@ SYMBOLS = [
     "vpm_field_upload", "vpm_field_download", "vpm_field_uj", "vpm_field_step", "vpm_field_rbf",
     "vpm_field_tsgm",
     "vpm_uj_device", "vpm_sfs_device",
-    "vpm_get_timing", "vpm_measure_dfma_peak", "vpm_measure_ffma_peak", "vpm_test_math",
+    "vpm_get_timing", "vpm_measure_dfma_peak", "vpm_measure_ffma_peak", "vpm_test_math", "vpm_plan_query",
 ]
 
 VPM_OK = 0
@@ -112,6 +112,7 @@ def load():
     lib.vpm_measure_dfma_peak.argtypes = [p, P(dbl), P(dbl)]
     lib.vpm_measure_ffma_peak.argtypes = [p, i32, P(dbl), P(dbl)]
     lib.vpm_test_math.argtypes = [p, i32, i32, p, p, p, i64]
+    lib.vpm_plan_query.argtypes = [i64, i64, i32, i32, p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name != "vpm_last_error":

@@ -104,4 +104,15 @@ int vpm_test_math(vpm_handle *h, int op, int arg, const double *in, double *out,
   return VPM_OK;
 }
 
+int vpm_plan_query(int64_t nt, int64_t ns, int sm_count, int kind, int64_t *out) {
+  if (!out || nt < 0 || ns < 0 || sm_count < 1 || kind < 0 || kind > 3) return VPM_EINVAL;
+  bool fills = false;
+  const Plan p = kind == 3 ? make_plan_tab(nt, ns, sm_count, &fills)
+                           : make_plan(nt, ns, sm_count, kind == 0 ? PLAN_UJ : kind == 1 ? PLAN_SFS : PLAN_UJ_F32);
+  out[0] = (int64_t)(p.tab ? p.tab : kThreads) * p.T;
+  out[1] = p.grid.x; out[2] = p.nsplit; out[3] = p.src_per_split; out[4] = p.tiles_per_split;
+  out[5] = p.T; out[6] = p.unroll; out[7] = fills ? 1 : 0;
+  return VPM_OK;
+}
+
 }  // extern "C"

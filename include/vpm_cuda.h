@@ -348,6 +348,12 @@ int vpm_measure_ffma_peak(vpm_handle *h, int mode, double *fma_per_s, double *el
 int vpm_test_math(vpm_handle *h, int op, int arg, const double *in, double *out, double *out2,
                   int64_t n);
 
+/* Launch plan of a direct sweep (host arithmetic only: needs no handle and no GPU; for tests and tuning aids).
+ * kind 0 U/J FP64, 1 SFS FP64, 2 U/J FP32, 3 U/J table kernel (gaussianerf / gaussian).
+ * out[0..7] = targets per CTA, grid.x, number of source splits (grid.y), sources per split, tiles per split,
+ * targets per thread, loop unroll, 1 if the field fills the machine for the table kernel (kind 3) else 0. */
+int vpm_plan_query(int64_t n_targets, int64_t n_sources, int sm_count, int kind, int64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -214,3 +214,54 @@ def test_save_xdmf_binary_roundtrip(vpm, tmp_path):
     assert vpm.save(empty, "e", path=str(tmp_path), num=3) == "e.3.xmf;"
     assert vpm.io.read(str(tmp_path / "e.3.xmf"))["np"] == 1
     assert vpm.save(pf, "plain", path=str(tmp_path / "sub"), add_num=False, createpath=True) == "plain.xmf;"
+
+
+# ---- launch plans (host arithmetic of the library, vpm_plan_query: no GPU needed) -------------------------------
+def _plan(vpm, nt, ns, sm=148, kind=0):
+    out = (ctypes.c_int64 * 8)()
+    assert vpm._cabi.load().vpm_plan_query(int(nt), int(ns), int(sm), int(kind), out) == 0
+    keys = ("targets_per_cta", "grid_x", "nsplit", "src_per_split", "tiles_per_split", "T", "unroll", "fills")
+    return dict(zip(keys, list(out)))
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_launch_plans_cover_every_pair_exactly_once(vpm, kind):
+    """every target belongs to one CTA column and every source to one non-empty split, for ragged sizes from one
+    particle to 2^24, on 1 ... 148 SMs; the FP32 and table kernels split on tile boundaries, the FP64 kernels may
+    split finer (small fields) but never below 16 sources unless the field is smaller than that"""
+    rng = np.random.Generator(np.random.PCG64(11))
+    sizes = [1, 2, 15, 16, 17, 31, 127, 128, 129, 200, 255, 257, 900, 1023, 1025, 4900, 8191, 8193, 33800, 100_000,
+             300_000, 1 << 20, (1 << 22) + 5, 1 << 24] + [int(v) for v in rng.integers(1, 60_000, 40)]
+    for sm in (1, 8, 132, 148):
+        for nt in sizes:
+            for ns in (sizes if nt in (200, 4900, 1 << 20) else [nt, max(1, nt // 3), 4900]):
+                p = _plan(vpm, nt, ns, sm, kind)
+                tpc = p["targets_per_cta"]
+                assert p["grid_x"] * tpc >= nt > (p["grid_x"] - 1) * tpc, (nt, ns, sm, p)
+                sps = p["src_per_split"]
+                assert 1 <= p["nsplit"] <= 1024 and p["nsplit"] * sps >= ns > (p["nsplit"] - 1) * sps, (nt, ns, sm, p)
+                if kind >= 2 or sps >= 128:
+                    assert sps == p["tiles_per_split"] * 128, (nt, ns, sm, p)
+                else:
+                    assert p["tiles_per_split"] == 1 and (sps >= 16 or p["nsplit"] == 1), (nt, ns, sm, p)
+                assert p["T"] in (1, 2) and p["unroll"] in (1, 2)
+                assert p == _plan(vpm, nt, ns, sm, kind)          # a function of its arguments only
+
+
+def test_small_field_plans_fill_one_wave_and_even_out_few_waves(vpm):
+    """what the sub-tile splits are for: 200 and 900 particles get tens of CTAs instead of 4 and
+    64, never more than 32 splits below one wave; 4 900 particles get 1.98 waves of 888 CTAs instead of 1.71; large
+    fields keep tile-aligned splits of several tiles"""
+    p = _plan(vpm, 200, 200)
+    assert (p["grid_x"], p["nsplit"], p["src_per_split"]) == (2, 13, 16)
+    p = _plan(vpm, 900, 900)
+    assert p["grid_x"] == 8 and p["nsplit"] <= 32 and 16 <= p["src_per_split"] < 128
+    p = _plan(vpm, 4900, 4900)
+    ctas, wave = p["grid_x"] * p["nsplit"], 148 * 6
+    assert 1.9 * wave <= ctas <= 2.0 * wave and p["src_per_split"] < 128
+    p = _plan(vpm, 1 << 20, 1 << 20)
+    assert p["T"] == 2 and p["tiles_per_split"] >= 4 and p["src_per_split"] == 128 * p["tiles_per_split"]
+    assert _plan(vpm, 1 << 20, 1 << 20, kind=3)["fills"] == 1 and _plan(vpm, 4900, 4900, kind=3)["fills"] == 0
+    lib = vpm._cabi.load()
+    assert lib.vpm_plan_query(10, 10, 0, 0, (ctypes.c_int64 * 8)()) == -1          # VPM_EINVAL
+    assert lib.vpm_plan_query(10, 10, 148, 7, (ctypes.c_int64 * 8)()) == -1
