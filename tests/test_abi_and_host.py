@@ -265,3 +265,42 @@ def test_small_field_plans_fill_one_wave_and_even_out_few_waves(vpm):
     lib = vpm._cabi.load()
     assert lib.vpm_plan_query(10, 10, 0, 0, (ctypes.c_int64 * 8)()) == -1          # VPM_EINVAL
     assert lib.vpm_plan_query(10, 10, 148, 7, (ctypes.c_int64 * 8)()) == -1
+
+
+def test_header_is_plain_c_and_links_without_a_gpu(vpm, tmp_path):
+    """include/vpm_cuda.h is the drop-in boundary: it must compile on its own as C11 and as C++ (no torch, no CUDA
+    headers), and a plain-C program must link against libvpm_cuda.so and call its GPU-free entry points
+    (vpm_abi_version, vpm_plan_query); vpm_create without a GPU returns VPM_ENODEV instead of aborting"""
+    import subprocess
+    from vpm_import import load_build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_path = load_build().build()
+    inc = os.path.join(root, "include")
+    for compiler, std, suffix in (("/usr/bin/gcc", "-std=c11", ".c"), ("/usr/bin/g++", "-std=c++17", ".cpp")):
+        src = tmp_path / ("hdr" + suffix)
+        src.write_text('#include "vpm_cuda.h"\nint main(void) { return 0; }\n')
+        subprocess.run([compiler, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    prog = tmp_path / "plan.c"
+    prog.write_text(r'''
+#include <stdio.h>
+#include "vpm_cuda.h"
+int main(void) {
+  int64_t out[8];
+  if (vpm_abi_version() != 1) return 2;
+  if (vpm_plan_query(4900, 4900, 148, 0, out) != VPM_OK) return 3;
+  printf("%lld %lld %lld\n", (long long)out[1], (long long)out[2], (long long)out[3]);
+  vpm_handle *h = 0;
+  int rc = vpm_create(&h, 1, 0);
+  if (rc == VPM_OK) { vpm_destroy(h); printf("gpu\n"); } else printf("rc %d\n", rc);
+  return 0;
+}
+''')
+    exe = str(tmp_path / "plan")
+    libdir = os.path.dirname(lib_path)
+    subprocess.run(["/usr/bin/gcc", "-std=c11", "-O1", "-I", inc, str(prog), "-L", libdir, "-lvpm_cuda",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, check=True)
+    lines = res.stdout.split("\n")
+    assert lines[0].split() == ["39", "45", "109"]
+    import torch
+    assert lines[1] == ("gpu" if torch.cuda.is_available() else "rc -4")
